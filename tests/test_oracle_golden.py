@@ -1,0 +1,213 @@
+"""Pins the CPU oracle against every known-answer vector the pandrs tests hold for the hot path
+(SURVEY.md §8c / §9.6).  CPU only."""
+import numpy as np
+import pytest
+
+A = "A B A B A C B C C A".split()
+VALUE = [10, 25, 15, 30, 22, 18, 24, 12, 16, 20]
+FLOAT = [1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9, 10.0]
+
+
+def _dict(strings):
+    pool = []
+    ids = []
+    for s in strings:
+        if s not in pool:
+            pool.append(s)
+        ids.append(pool.index(s))
+    return ids, pool
+
+
+def _by_key(res):
+    return {k[0] if len(k) == 1 else k: i for i, k in enumerate(res["key_strings"])}
+
+
+def test_pandas_compat_groupby_goldens(oracle):
+    # src/dataframe/pandas_compat/groupby.rs:480-617
+    o = oracle
+    ids, pool = _dict(["A", "B", "A", "B", "A"])
+    key = o.Col(o.DICT_U32, ids, pool=pool)
+    val = o.Col(o.F64, [10.0, 20.0, 30.0, 40.0, 50.0])
+    ops = [o.SUM, o.MEAN, o.MIN, o.MAX, o.COUNT, o.STD]
+    res = o.groupby([key], [val], [(0, op) for op in ops])
+    assert res["n_groups"] == 2
+    g = _by_key(res)
+    want = {"A": [90.0, 30.0, 10.0, 50.0, 3.0, 20.0], "B": [60.0, 30.0, 20.0, 40.0, 2.0, None]}
+    for k, w in want.items():
+        for a, x in enumerate(w):
+            if x is not None:
+                assert res["aggs"][a][g[k]] == x, (k, a)
+    assert abs(res["aggs"][5][g["B"]] - np.std([20.0, 40.0], ddof=1)) < 1e-12
+
+
+def test_ten_row_fixture(oracle):
+    # tests/optimized_groupby_enhanced_test.rs:12-23, goldens in SURVEY.md §9.6 (iv);
+    # the total 192 is asserted by tests/optimized_custom_aggregation_test.rs:49
+    o = oracle
+    ids, pool = _dict(A)
+    key = o.Col(o.DICT_U32, ids, pool=pool)
+    vi = o.Col(o.I64, VALUE)
+    vf = o.Col(o.F64, FLOAT)
+    ops = [o.COUNT, o.SUM, o.MEAN, o.MIN, o.MAX, o.STD]
+    res = o.groupby([key], [vi, vf], [(0, op) for op in ops] + [(1, op) for op in ops])
+    g = _by_key(res)
+    want_i = {"A": [4, 67, 16.75, 10, 22, 5.377421934967226],
+              "B": [3, 79, 26.333333333333332, 24, 30, 3.2145502536643185],
+              "C": [3, 46, 15.333333333333334, 12, 18, 3.055050463303893]}
+    want_f = {"A": [4, 19.9, 4.975, 1.1, 10.0, 3.8012059489939065],
+              "B": [3, 14.3, 4.766666666666667, 2.2, 7.7, 2.768272626265942],
+              "C": [3, 25.3, 8.433333333333334, 6.6, 9.9, 1.680277754817142]}
+    for k in "ABC":
+        for a in range(6):
+            assert res["aggs"][a][g[k]] == pytest.approx(want_i[k][a], rel=1e-15, abs=0), (k, a)
+            assert res["aggs"][6 + a][g[k]] == pytest.approx(want_f[k][a], rel=2e-15, abs=0), (k, a)
+    assert sum(res["aggs"][1]) == 192
+
+
+def test_concurrency_fixture_four_groups(oracle):
+    # tests/concurrency_test.rs:351-384 — 1,000 rows, category i % 4 -> 4 groups of 250
+    o = oracle
+    key = o.Col(o.I64, np.arange(1000) % 4)
+    res = o.groupby([key], [o.Col(o.F64, np.arange(1000, dtype=np.float64))], [(0, o.COUNT)])
+    assert res["n_groups"] == 4
+    assert list(res["aggs"][0]) == [250.0] * 4
+
+
+def test_join_goldens(oracle):
+    # tests/optimized_join_test.rs:6-237
+    o = oracle
+    L = o.Col(o.I64, [1, 2, 3, 4])
+    R = o.Col(o.I64, [1, 2, 5, 6])
+    li, ri = o.join(L, R, o.INNER)
+    assert list(zip(li, ri)) == [(0, 0), (1, 1)]
+    li, ri = o.join(L, R, o.LEFT)
+    assert list(zip(li, ri)) == [(0, 0), (1, 1), (2, -1), (3, -1)]
+    li, ri = o.join(L, R, o.RIGHT)
+    assert list(zip(li, ri)) == [(0, 0), (1, 1), (-1, 2), (-1, 3)]
+    li, ri = o.join(L, R, o.OUTER)
+    assert len(li) == 6 and list(zip(li, ri))[4:] == [(-1, 2), (-1, 3)]
+    li, ri = o.join(L, o.Col(o.I64, [5, 6, 7, 8]), o.INNER)
+    assert len(li) == 0
+
+
+def test_join_merge_ordering_golden(oracle):
+    # src/dataframe/pandas_compat/merge.rs:320-410 — left keys A,B,C,D / right B,C,D,E
+    o = oracle
+    pool = list("ABCDE")
+    L = o.Col(o.DICT_U32, [0, 1, 2, 3], pool=pool)
+    R = o.Col(o.DICT_U32, [1, 2, 3, 4], pool=pool)
+    li, ri = o.join(L, R, o.INNER)
+    assert [pool[L.data[i]] for i in li] == ["B", "C", "D"]
+    li, ri = o.join(L, R, o.LEFT)
+    assert [pool[L.data[i]] for i in li] == ["A", "B", "C", "D"] and ri[0] == -1
+    li, ri = o.join(L, R, o.OUTER)
+    keys = [pool[L.data[i]] if i >= 0 else pool[R.data[r]] for i, r in zip(li, ri)]
+    assert keys == ["A", "B", "C", "D", "E"]
+
+
+def test_null_semantics(oracle):
+    # NULL keys form one "NULL" group; Count counts NULL values; all-NULL -> 0.0;
+    # NULL join keys are dropped on both sides, also for Left.
+    o = oracle
+    key = o.Col(o.I64, [7, 7, 0, 0, 9], nulls=o.pack_bits([0, 0, 1, 1, 0]))
+    val = o.Col(o.F64, [1.0, 2.0, 3.0, 4.0, 5.0], nulls=o.pack_bits([0, 1, 0, 0, 1]))
+    ops = [o.SUM, o.MEAN, o.MIN, o.MAX, o.COUNT, o.STD]
+    res = o.groupby([key], [val], [(0, op) for op in ops])
+    g = _by_key(res)
+    assert set(g) == {"7", "NULL", "9"}
+    assert [res["aggs"][a][g["7"]] for a in range(6)] == [1.0, 1.0, 1.0, 1.0, 2.0, 0.0]
+    assert [res["aggs"][a][g["9"]] for a in range(6)] == [0.0, 0.0, 0.0, 0.0, 1.0, 0.0]
+    assert res["aggs"][0][g["NULL"]] == 7.0 and res["aggs"][4][g["NULL"]] == 2.0
+    L = o.Col(o.I64, [1, 2, 3], nulls=o.pack_bits([0, 1, 0]))
+    R = o.Col(o.I64, [1, 2, 3], nulls=o.pack_bits([0, 0, 1]))
+    li, ri = o.join(L, R, o.LEFT)
+    assert list(zip(li, ri)) == [(0, 0), (2, -1)]
+    # short null masks: bytes past the end read as "not NULL" (int64_column.rs:77)
+    k2 = o.Col(o.I64, np.arange(20) % 2, nulls=np.array([0xFF], np.uint8))
+    res = o.groupby([k2], [o.Col(o.F64, np.ones(20))], [(0, o.COUNT)])
+    g = _by_key(res)
+    assert res["aggs"][0][g["NULL"]] == 8 and res["aggs"][0][g["0"]] == 6 and res["aggs"][0][g["1"]] == 6
+
+
+def test_int_sentinels_and_wrapping(oracle):
+    # aggregation.rs:531-556 sentinel collapse; :508-513 wrapping i64 sum in release builds
+    o = oracle
+    key = o.Col(o.I64, [1, 1, 2, 2])
+    val = o.Col(o.I64, [2**63 - 1, 1, -(2**63), -(2**63)])
+    res = o.groupby([key], [val], [(0, o.SUM), (0, o.MIN), (0, o.MAX)])
+    g = _by_key(res)
+    assert res["aggs"][0][g["1"]] == float(-(2**63))       # wrapped
+    assert res["aggs"][2][g["1"]] == float(2**63 - 1)      # i64::MAX is a sentinel for Min only
+    assert res["aggs"][1][g["1"]] == 1.0
+    assert res["aggs"][2][g["2"]] == 0.0                   # max == i64::MIN -> 0.0
+    assert res["aggs"][0][g["2"]] == 0.0                   # MIN+MIN wraps to 0
+
+
+def test_lazy_mode_rejects_std(oracle):
+    # lazy.rs:377-382
+    o = oracle
+    res = o.groupby([o.Col(o.I64, [1, 2])], [o.Col(o.F64, [1.0, 2.0])], [(0, o.STD)], mode=o.MODE_LAZY)
+    assert res["error"] == 1
+    res = o.groupby([o.Col(o.I64, [1, 2])], [o.Col(o.F64, [1.0, 2.0])], [(0, o.SUM)], mode=o.MODE_LAZY)
+    assert res["error"] == 0
+
+
+def test_par_aggregate_equals_serial(oracle):
+    o = oracle
+    n = 20000
+    key = o.Col(o.I64, o.synth_keys(n, card=37))
+    val = o.Col(o.F64, o.synth_vals(n), nulls=o.synth_nulls(n))
+    aggs = [(0, op) for op in (o.SUM, o.MEAN, o.MIN, o.MAX, o.COUNT, o.STD)]
+    a = o.groupby([key], [val], aggs)
+    b = o.groupby([key], [val], aggs, mode=o.MODE_PAR_AGGREGATE, nthreads=4)
+    assert a["key_strings"] == b["key_strings"]
+    for x, y in zip(a["aggs"], b["aggs"]):
+        assert np.array_equal(x, y)
+
+
+def test_against_pandas(oracle):
+    import pandas as pd
+    o = oracle
+    n = 5000
+    k1 = o.synth_keys(n, seed=1, card=13)
+    k2 = o.synth_keys(n, seed=2, card=7)
+    v = o.synth_vals(n, seed=3)
+    res = o.groupby([o.Col(o.I64, k1), o.Col(o.I64, k2)], [o.Col(o.F64, v)],
+                    [(0, o.SUM), (0, o.MEAN), (0, o.MIN), (0, o.MAX), (0, o.COUNT), (0, o.STD)])
+    df = pd.DataFrame(dict(k1=k1, k2=k2, v=v)).groupby(["k1", "k2"])["v"].agg(["sum", "mean", "min", "max", "count", "std"])
+    assert res["n_groups"] == len(df)
+    for g, ks in enumerate(res["key_strings"]):
+        row = df.loc[(int(ks[0]), int(ks[1]))]
+        got = [res["aggs"][a][g] for a in range(6)]
+        assert np.allclose(got, row.values, rtol=1e-12, atol=0)
+    # join vs pandas merge
+    lk = o.synth_keys(300, seed=5, card=50)
+    rk = o.synth_keys(200, seed=6, card=50)
+    li, ri = o.join(o.Col(o.I64, lk), o.Col(o.I64, rk), o.INNER)
+    m = pd.DataFrame(dict(k=lk, l=np.arange(300))).merge(pd.DataFrame(dict(k=rk, r=np.arange(200))), on="k")
+    assert sorted(zip(li, ri)) == sorted(zip(m.l, m.r))
+
+
+def test_gather_and_filter(oracle):
+    o = oracle
+    col = o.Col(o.F64, [1.5, 2.5, 3.5], nulls=o.pack_bits([0, 1, 0]))
+    assert list(o.gather(col, [2, -1, 1, 0])) == [3.5, 0.0, 0.0, 1.5]
+    mask = o.Col(o.BOOL_BITS, o.pack_bits([1, 0, 1, 1, 0]), nulls=o.pack_bits([0, 0, 1, 0, 0]), length=5)
+    assert list(o.filter_indices(mask)) == [0, 3]
+
+
+def test_synth_matches_numpy_restatement(oracle):
+    # the generators are shared with the CUDA side; pin them with an independent numpy restatement
+    o = oracle
+
+    def sm(x):
+        x = (x + np.uint64(0x9E3779B97F4A7C15))
+        x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return x ^ (x >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        rows = np.arange(1000, dtype=np.uint64)
+        k = sm(np.uint64(42) * np.uint64(0x100000001B3) + rows) % np.uint64(1000)
+        assert np.array_equal(o.synth_keys(1000), k.astype(np.int64))
+        r = sm(np.uint64(43) * np.uint64(0x100000001B3) + rows)
+        assert np.array_equal(o.synth_vals(1000), (r >> np.uint64(11)).astype(np.float64) * (1000.0 / 2**53))
