@@ -1,0 +1,220 @@
+/* pandrs_b200.h — C ABI of libpandrs_b200.so: the B200 (sm_100a) execution path for pandrs's
+ * groupby-aggregate and inner/left hash-join hot paths.
+ *
+ * pandrs (cool-japan/pandrs) has no FFI/plugin interface for this path (its `src/gpu` is a cudarc
+ * shell for dense matrix ops, src/gpu/operations.rs:17-39), so the boundary is introduced at the
+ * Rust method level: the functions below are what `extern "C"` blocks in src/groupby,
+ * src/optimized/split_dataframe/{group,join}.rs and src/optimized/lazy.rs would bind (see
+ * INTEGRATION.md for the Rust side).  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++/torch types; no exceptions or panics cross the ABI.
+ *  - every function returns a pdrs_status (0 = ok, <0 = error); pdrs_last_error() gives the text.
+ *    (reference convention: Result<T, Error>, GPU errors -> Error::Computation, src/gpu/mod.rs:206-210)
+ *  - inputs are BORROWED for the duration of the call (the Rust side keeps its Arc<[T]> alive);
+ *    results are owned by the library and released only by the matching *_free().
+ *  - column memory layout is pandrs's own (zero-copy from Arc<[i64]>/Arc<[f64]>/Arc<[u32]>):
+ *    null bitmap LSB-first, bit SET = NULL, may be shorter than ceil(len/8) (missing bytes = not NULL)
+ *    (src/column/int64_column.rs:72-81, src/core/column.rs:163-177).
+ *  - a pdrs_ctx is bound to one device and one stream and is NOT re-entrant; use one per thread
+ *    (reference: global Mutex<Option<GpuManager>>, src/gpu/mod.rs:249-251).
+ *  - there is NO CPU fallback: an unsupported dtype/op returns PDRS_ERR_UNSUPPORTED.
+ */
+#ifndef PANDRS_B200_H
+#define PANDRS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDRS_ABI_VERSION 1
+
+typedef enum pdrs_status {
+  PDRS_OK = 0,
+  PDRS_ERR_BAD_ARG = -1,        /* Error::InvalidInput / IndexOutOfBounds */
+  PDRS_ERR_TYPE_MISMATCH = -2,  /* Error::ColumnTypeMismatch (join.rs:98-104) */
+  PDRS_ERR_OOM = -3,
+  PDRS_ERR_CUDA = -4,           /* Error::Computation(String) */
+  PDRS_ERR_NCCL = -5,
+  PDRS_ERR_UNSUPPORTED = -6     /* Error::OperationFailed (aggregation.rs:748-752) */
+} pdrs_status;
+
+/* ColumnType (src/core/column.rs:9-14) + I32 as a physical extension for packed multi-key groupbys */
+typedef enum pdrs_dtype {
+  PDRS_I64 = 0,       /* Int64Column.data: Arc<[i64]>      (src/column/int64_column.rs:9-13)   */
+  PDRS_F64 = 1,       /* Float64Column.data: Arc<[f64]>    (src/column/float64_column.rs:9-13) */
+  PDRS_DICT_U32 = 2,  /* StringColumn.indices: Arc<[u32]>, GLOBAL_STRING_POOL ids (string_column.rs:26-32) */
+  PDRS_BOOL_BITS = 3, /* BooleanColumn.data: BitMask, LSB-first, 1 = true (core/column.rs:72-156)  */
+  PDRS_I32 = 4
+} pdrs_dtype;
+
+/* AggregateOp, same order as src/optimized/split_dataframe/group/types.rs:11-34 */
+typedef enum pdrs_agg_op {
+  PDRS_SUM = 0, PDRS_MEAN = 1, PDRS_MIN = 2, PDRS_MAX = 3, PDRS_COUNT = 4, PDRS_STD = 5, PDRS_VAR = 6
+} pdrs_agg_op;
+
+/* JoinType (src/optimized/split_dataframe/join.rs:11-20); Right/Outer are "next" rows */
+typedef enum pdrs_join_type { PDRS_INNER = 0, PDRS_LEFT = 1 } pdrs_join_type;
+
+typedef enum pdrs_mem { PDRS_MEM_HOST = 0, PDRS_MEM_DEVICE = 1 } pdrs_mem;
+
+/* One borrowed column.  For PDRS_MEM_DEVICE columns `data` must be 16-byte aligned and
+ * `null_len` must cover ceil(len/8) bytes (pdrs_col_upload() guarantees both). */
+typedef struct pdrs_col {
+  int32_t dtype;            /* pdrs_dtype */
+  int32_t mem;              /* pdrs_mem: where data/null_bits live */
+  const void* data;
+  const uint8_t* null_bits; /* NULL = no NULLs */
+  int64_t null_len;         /* bytes available at null_bits */
+  int64_t len;              /* rows */
+  int64_t null_alias;       /* PDRS_DICT_U32 keys: pool id of the literal string "NULL" (it merges with the
+                               NULL group, grouping.rs:69-98), or -1 */
+} pdrs_col;
+
+typedef struct pdrs_agg {
+  int32_t value_col;        /* index into the `vals` array of pdrs_groupby_agg */
+  int32_t op;               /* pdrs_agg_op */
+} pdrs_agg;
+
+typedef enum pdrs_groupby_algo {
+  PDRS_GB_AUTO = 0,
+  PDRS_GB_SHARED = 1,       /* per-warp tables in shared memory, spill to the global table */
+  PDRS_GB_GLOBAL = 2,       /* global open-addressing table only (high cardinality) */
+  PDRS_GB_DENSE = 3         /* direct-mapped shared tables for small dense integer key ranges */
+} pdrs_groupby_algo;
+
+typedef struct pdrs_options {
+  int32_t device;           /* CUDA ordinal */
+  int32_t groupby_algo;     /* pdrs_groupby_algo; AUTO picks from a sampled cardinality estimate */
+  int64_t groups_hint;      /* expected number of groups, 0 = estimate from a sample */
+  void* stream;             /* cudaStream_t to run on, NULL = the context creates its own */
+  int32_t compat_filter_nulls; /* 1 = a fused row filter turns NULLs into defaults like data_ops.rs:64-71 */
+  int32_t reserved0;
+  int64_t reserved[4];
+} pdrs_options;
+
+typedef struct pdrs_stats {   /* filled by the last groupby/join call on the context */
+  int64_t kernel_launches;    /* kernels launched by the library since context creation */
+  int32_t groupby_algo_used;  /* pdrs_groupby_algo actually run */
+  int32_t retries;            /* table-overflow retries */
+  int64_t est_groups;         /* sampled cardinality estimate (0 when a hint was given) */
+  int64_t table_slots;        /* global table capacity used */
+  int64_t spilled_rows;       /* rows that bypassed the shared-memory tables */
+  float main_kernel_ms;       /* CUDA-event time of the dominant kernel of the last call */
+  float total_ms;             /* CUDA-event time of the whole device-side call */
+} pdrs_stats;
+
+typedef struct pdrs_ctx pdrs_ctx;
+typedef struct pdrs_groupby_result pdrs_groupby_result;
+typedef struct pdrs_join_result pdrs_join_result;
+
+/* ---- context (replaces src/gpu/mod.rs:249-282 get_gpu_manager / GpuConfig) ---- */
+int32_t pdrs_abi_version(void);
+int32_t pdrs_ctx_create(const pdrs_options* opts /* may be NULL */, pdrs_ctx** out);
+void pdrs_ctx_destroy(pdrs_ctx* ctx);
+const char* pdrs_last_error(pdrs_ctx* ctx /* NULL = creation errors */);
+int32_t pdrs_sync(pdrs_ctx* ctx);
+int32_t pdrs_get_stats(pdrs_ctx* ctx, pdrs_stats* out);
+int32_t pdrs_set_option(pdrs_ctx* ctx, const char* name, int64_t value);
+
+/* ---- device-resident columns (replaces src/gpu/memory_pool.rs:124-383 for this path) ----
+ * pdrs_col_upload copies a host column into 256-byte aligned device memory, pads the null bitmap to
+ * ceil(len/8) (+32) zero bytes, and returns a PDRS_MEM_DEVICE descriptor owned by the context. */
+int32_t pdrs_col_upload(pdrs_ctx* ctx, const pdrs_col* host_col, pdrs_col* dev_col_out);
+int32_t pdrs_col_free(pdrs_ctx* ctx, pdrs_col* dev_col);
+/* pinned host staging buffers for callers that want overlapped H2D (bench e2e leg) */
+int32_t pdrs_host_alloc(pdrs_ctx* ctx, int64_t bytes, void** out);
+int32_t pdrs_host_free(pdrs_ctx* ctx, void* p);
+
+/* ---- groupby-aggregate ----
+ * Replaces OptimizedDataFrame::group_by_with_options (group/grouping.rs:38-115) fused with
+ * GroupBy::aggregate / par_aggregate (group/aggregation.rs:763-871, 22-182) and the Aggregate arm of
+ * LazyFrame::execute (src/optimized/lazy.rs:186-404).
+ *  keys[nkeys]   key columns (I64, I32, DICT_U32, BOOL_BITS, F64 by text-equivalent bit pattern)
+ *  vals[nvals]   value columns (I64 or F64; other dtypes only under PDRS_COUNT)
+ *  aggs[naggs]   (value_col, op); every aggregate is returned as f64 (aggregation.rs:865)
+ *  filter        optional BOOL_BITS column: only rows where it is Some(true) take part
+ *                (data_ops.rs:49-55 fused in front of the aggregation), NULL = no filter
+ * Semantics follow SURVEY.md §9.1-9.2: NULL keys form one group, Count = group size incl. NULL values,
+ * empty/all-NULL -> 0.0, Min/Max sentinel collapse, Std/Var with n-1.  Group order is unspecified. */
+int32_t pdrs_groupby_agg(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals,
+                         int32_t nvals, const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter,
+                         pdrs_groupby_result** out);
+int64_t pdrs_groupby_n_groups(const pdrs_groupby_result* r);
+/* copy-out to host: key k as its physical type (i64/f64/u32/i32; BOOL as one byte per group) + 1 byte
+ * per group that is 1 where the key part is NULL (the Rust side prints "NULL", grouping.rs:74) */
+int32_t pdrs_groupby_key(const pdrs_groupby_result* r, int32_t k, void* out_values, uint8_t* out_is_null);
+int32_t pdrs_groupby_agg_values(const pdrs_groupby_result* r, int32_t a, double* out);
+int32_t pdrs_groupby_group_rows(const pdrs_groupby_result* r, int64_t* out);          /* = Count */
+int32_t pdrs_groupby_valid_n(const pdrs_groupby_result* r, int32_t value_col, int64_t* out);
+/* device pointers of the same arrays (valid until the result is freed) */
+const void* pdrs_groupby_key_dev(const pdrs_groupby_result* r, int32_t k);
+const uint8_t* pdrs_groupby_key_null_dev(const pdrs_groupby_result* r, int32_t k);
+const double* pdrs_groupby_agg_dev(const pdrs_groupby_result* r, int32_t a);
+const int64_t* pdrs_groupby_group_rows_dev(const pdrs_groupby_result* r);
+void pdrs_groupby_result_free(pdrs_groupby_result* r);
+
+/* Partial (mergeable) aggregation states for the multi-GPU path (no reference counterpart: pandrs has
+ * no comms backend).  A state row is 8 x 64-bit words per (group, value column), opaque
+ * to the caller:  [rows, n, pivot^tag, S1, S2, ~ord(min), ord(max), isum]  with S1 = sum(x - pivot),
+ * S2 = sum((x - pivot)^2), so that states of the same group merge exactly like Chan's update.
+ * pdrs_groupby_partial() runs the same kernels as pdrs_groupby_agg() but keeps the states
+ * (all_stats = 0: rows/n/sum only; 1: also min/max/variance terms);
+ * pdrs_groupby_merge() groups state rows by key again, merges them and finalises `aggs`. */
+int32_t pdrs_groupby_partial(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals,
+                             int32_t nvals, const pdrs_col* filter, int32_t all_stats,
+                             pdrs_groupby_result** out);
+const uint64_t* pdrs_groupby_states_dev(const pdrs_groupby_result* r, int32_t value_col); /* [n_groups][8] */
+int32_t pdrs_groupby_merge(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const uint64_t* const* states_dev,
+                           const int32_t* val_is_int, int32_t nvals, int64_t n_state_rows,
+                           const pdrs_agg* aggs, int32_t naggs, pdrs_groupby_result** out);
+/* destination rank of every row, dest = mix(hash(key tuple)) mod nparts (NULL-key group -> 0), as a
+ * permutation perm_dev[nrows] that groups the row ids by destination, and counts_host[nparts]. */
+int32_t pdrs_hash_partition(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, int32_t nparts,
+                            int64_t* perm_dev, int64_t* counts_host);
+
+/* ---- hash join ----
+ * Replaces the build/probe part of OptimizedDataFrame::join_impl (split_dataframe/join.rs:107-208).
+ * Emits index pairs (left_row, right_row); right_row = -1 stands for None (Left join, no match).
+ * NULL keys never match and are dropped from BOTH sides, also for Left (join.rs:112,152).
+ * Row order: left-row-major; the order of several matches of one left row is unspecified. */
+int32_t pdrs_join_pairs(pdrs_ctx* ctx, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how,
+                        pdrs_join_result** out);
+int64_t pdrs_join_len(const pdrs_join_result* r);
+int32_t pdrs_join_indices(const pdrs_join_result* r, int64_t* left_out, int64_t* right_out); /* host copy-out */
+const int64_t* pdrs_join_left_dev(const pdrs_join_result* r);
+const int64_t* pdrs_join_right_dev(const pdrs_join_result* r);
+void pdrs_join_result_free(pdrs_join_result* r);
+
+/* Replaces the materialisation loops of join_impl (join.rs:290-552) and filter_by_indices
+ * (data_ops.rs:124-211): out[j] = idx[j] < 0 || col[idx[j]] is NULL ? type default : col[idx[j]];
+ * the output carries no null mask.  DICT_U32 default is 0xFFFFFFFF (the empty string ""), BOOL_BITS
+ * gathers into one byte per row.  idx/out live where idx_mem/out_mem say. */
+int32_t pdrs_gather(pdrs_ctx* ctx, const pdrs_col* col, const int64_t* idx, int32_t idx_mem, int64_t n,
+                    void* out, int32_t out_mem);
+
+/* Replaces the index-building half of OptimizedDataFrame::filter (data_ops.rs:37-62):
+ * ascending row ids where the Boolean column is Some(true).  out_idx_dev must hold mask->len entries. */
+int32_t pdrs_filter_indices(pdrs_ctx* ctx, const pdrs_col* mask, int64_t* out_idx_dev, int64_t* n_out_host);
+
+/* ---- synthetic inputs for tests/benches (same counter-based arithmetic as oracle/pandrs_oracle.cpp) ---- */
+int32_t pdrs_synth_keys(pdrs_ctx* ctx, int64_t* out_dev, int64_t n, int64_t row0, uint64_t seed, uint64_t card, int32_t scramble);
+int32_t pdrs_synth_vals(pdrs_ctx* ctx, double* out_dev, int64_t n, int64_t row0, uint64_t seed);
+int32_t pdrs_synth_nulls(pdrs_ctx* ctx, uint8_t* out_dev, int64_t n, int64_t row0, uint64_t seed, uint32_t per_million);
+int32_t pdrs_synth_join_keys(pdrs_ctx* ctx, int64_t* out_dev, int64_t n, int64_t row0, uint64_t seed, uint64_t domain, int32_t unique);
+/* raw device memory helpers for hosts without a CUDA runtime binding of their own */
+int32_t pdrs_dev_alloc(pdrs_ctx* ctx, int64_t bytes, void** out);
+int32_t pdrs_dev_free(pdrs_ctx* ctx, void* p);
+int32_t pdrs_memcpy(pdrs_ctx* ctx, void* dst, const void* src, int64_t bytes, int32_t kind /*0 h2d,1 d2h,2 d2d*/);
+/* writes > L2-size bytes so the next timed call starts with a cold L2 */
+int32_t pdrs_flush_l2(pdrs_ctx* ctx);
+/* CUDA-event timing on the context stream for callers without a CUDA binding: begin/end return ms */
+int32_t pdrs_timer_begin(pdrs_ctx* ctx);
+int32_t pdrs_timer_end(pdrs_ctx* ctx, float* ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PANDRS_B200_H */

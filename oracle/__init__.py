@@ -72,6 +72,7 @@ def lib():
         L.orc_synth_keys.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int]
         L.orc_synth_vals.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
         L.orc_synth_nulls.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32]
+        L.orc_synth_join_keys.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int]
         _lib = L
     return _lib
 
@@ -177,6 +178,12 @@ def synth_vals(n, seed=42, row0=0):
 def synth_nulls(n, seed=42, per_million=50000, row0=0):
     out = np.empty((n + 7) // 8, np.uint8)
     lib().orc_synth_nulls(out.ctypes.data, n, row0, seed, per_million)
+    return out
+
+
+def synth_join_keys(n, seed=42, domain=1, unique=False, row0=0):
+    out = np.empty(n, np.int64)
+    lib().orc_synth_join_keys(out.ctypes.data, n, row0, seed, domain, int(unique))
     return out
 
 

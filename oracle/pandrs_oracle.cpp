@@ -329,6 +329,9 @@ void orc_synth_keys(int64_t* out, int64_t n, int64_t row0, uint64_t seed, uint64
 void orc_synth_vals(double* out, int64_t n, int64_t row0, uint64_t seed) {
   for (int64_t i = 0; i < n; i++) { uint64_t r = splitmix64((seed + 1) * 0x100000001B3ULL + (uint64_t)(row0 + i)); out[i] = (double)(r >> 11) * (1000.0 / 9007199254740992.0); }
 }
+void orc_synth_join_keys(int64_t* out, int64_t n, int64_t row0, uint64_t seed, uint64_t domain, int unique) {
+  for (int64_t i = 0; i < n; i++) { uint64_t id = unique ? (uint64_t)(row0 + i) : splitmix64((seed + 3) * 0x100000001B3ULL + (uint64_t)(row0 + i)) % domain; out[i] = (int64_t)(id * 0x9E3779B97F4A7C15ULL); }
+}
 void orc_synth_nulls(uint8_t* out, int64_t n, int64_t row0, uint64_t seed, uint32_t per_million) {   // n, row0 multiples of 8
   for (int64_t b = 0; b < (n + 7) / 8; b++) { uint8_t byte = 0; for (int j = 0; j < 8 && b * 8 + j < n; j++) { uint64_t r = splitmix64((seed + 2) * 0x100000001B3ULL + (uint64_t)(row0 + b * 8 + j)); if ((uint32_t)(r % 1000000ULL) < per_million) byte |= (uint8_t)(1u << j); } out[b] = byte; }
 }

@@ -1,0 +1,102 @@
+// Internal declarations shared by the translation units of libpandrs_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/pandrs_b200.h"
+
+#define PDRS_MAX_KEYS 4
+#define PDRS_MAX_WORDS 3
+#define PDRS_MAX_VALS 16
+#define PDRS_MAX_AGGS 64
+
+struct pdrs_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err;
+  pdrs_options opts{};
+  pdrs_stats stats{};
+  int sm_count = 148;
+  int smem_optin = 0;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  void* flush_buf = nullptr;
+  size_t flush_bytes = 0;
+  int64_t* pinned_scalars = nullptr;   // small pinned host area for D2H of counters (64 x i64)
+  // tunables (pdrs_set_option)
+  int64_t opt_warps = 0;               // 0 = auto (warps per CTA of the shared-memory groupby kernel)
+  int64_t opt_sample_rows = 1 << 18;
+  int64_t opt_ctas_per_sm = 0;
+  int64_t opt_ng = 0;                  // 0 = auto (accumulator replicas per warp)
+  int64_t opt_join_algo = 0;           // 0 = auto
+  int64_t opt_timing = 1;              // record CUDA-event times in pdrs_stats
+};
+
+int32_t pdrs_fail(pdrs_ctx* ctx, int32_t code, const char* fmt, ...);
+
+#define PDRS_CUDA(ctx, call)                                                                   \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return pdrs_fail((ctx), _e == cudaErrorMemoryAllocation ? PDRS_ERR_OOM : PDRS_ERR_CUDA,  \
+                       "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define PDRS_TRY(call)                 \
+  do {                                 \
+    int32_t _s = (call);               \
+    if (_s != PDRS_OK) return _s;      \
+  } while (0)
+
+// Stream-ordered device memory owned by a call; freed (stream-ordered) when the holder dies.
+struct DevBuf {
+  pdrs_ctx* ctx = nullptr;
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept { release(); ctx = o.ctx; p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; return *this; }
+  ~DevBuf() { release(); }
+  int32_t alloc(pdrs_ctx* c, size_t n, bool zero = false);
+  void release();
+  template <class T> T* as() const { return (T*)p; }
+};
+
+// A device view of one input column (uploaded on demand when the caller passed host memory).
+struct ColView {
+  int32_t dtype = 0;
+  const void* data = nullptr;
+  const uint8_t* nulls = nullptr;   // covers >= ceil(len/8) + 32 bytes when owned
+  int64_t len = 0;
+  int64_t null_alias = -1;
+  DevBuf own_data, own_nulls;
+};
+int32_t pdrs_view_col(pdrs_ctx* ctx, const pdrs_col* c, ColView* out);
+int pdrs_dtype_bytes(int32_t dtype);
+int pdrs_grid_for(pdrs_ctx* c, int64_t n, int threads);
+
+// ---- device helpers ----
+#ifdef __CUDACC__
+__host__ __device__ __forceinline__ uint64_t pdrs_mix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ULL;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ bool pdrs_bit(const uint8_t* bits, int64_t i) { return (bits[i >> 3] >> (i & 7)) & 1; }
+// order-preserving maps to unsigned; 0 is reserved as "empty" (only reachable by NaN payloads, which are skipped)
+__device__ __forceinline__ uint64_t pdrs_ord_f64(double v) {
+  uint64_t u = (uint64_t)__double_as_longlong(v);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double pdrs_unord_f64(uint64_t o) {
+  uint64_t u = (o >> 63) ? (o & 0x7FFFFFFFFFFFFFFFULL) : ~o;
+  return __longlong_as_double((long long)u);
+}
+#endif

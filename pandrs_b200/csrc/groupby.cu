@@ -1,0 +1,645 @@
+// Host orchestration of the groupby-aggregate path: key packing, cardinality estimate, algorithm
+// choice, one aggregation pass per value column, finalisation, partial states and their merge.
+//
+// Replaces group_by_with_options (split_dataframe/group/grouping.rs:38-115) + GroupBy::aggregate
+// (group/aggregation.rs:763-871) + calculate_aggregation (aggregation.rs:500-754) and the Aggregate arm
+// of LazyFrame::execute (optimized/lazy.rs:186-404).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "groupby_kernels.cuh"
+
+// ---------------------------------------------------------------- finalisation
+struct FinVal { const GState* st; int is_int; int flags; long long* validn_out; u64* states_out; };
+struct FinAgg { int val; int op; double* out; };
+struct FinParams {
+  GTable gt;
+  KeySpec ks;
+  void* key_out[PDRS_MAX_KEYS];
+  uint8_t* key_null_out[PDRS_MAX_KEYS];
+  long long* rows_out;
+  int nvals, naggs;
+  FinVal vals[PDRS_MAX_VALS];
+  FinAgg aggs[PDRS_MAX_AGGS];
+};
+
+__device__ __forceinline__ double fin_pivot(u64 px) { return px ? __longlong_as_double((long long)(px ^ GB_PIV_X)) : 0.0; }
+
+// aggregation.rs:500-754: every aggregate is an f64; empty / all-NULL -> 0.0; Min/Max sentinel collapse.
+__device__ double fin_eval(const GState& s, int is_int, int op, u64 rows) {
+  const double n = (double)s.n;
+  const double c = fin_pivot(s.pivotx);
+  switch (op) {
+    case PDRS_COUNT: return (double)rows;                                     // :743 group size, NULLs included
+    case PDRS_SUM:
+      if (s.n == 0) return 0.0;
+      return is_int ? (double)(long long)s.isum : (s.S1 + n * c);              // :507-515 / :625-633
+    case PDRS_MEAN:
+      if (s.n == 0) return 0.0;
+      return is_int ? (double)(long long)s.isum / n : (c + s.S1 / n);          // :516-530 / :634-648
+    case PDRS_MIN: {
+      if (s.mnc == 0) return 0.0;
+      u64 o = ~s.mnc;
+      if (is_int) return (double)(long long)(o ^ GB_SIGN);                     // :531-543 (i64::MAX never stored: collapses to 0.0)
+      double v = pdrs_unord_f64(o);
+      return v;                                                                // :649-661 (+INF never stored)
+    }
+    case PDRS_MAX: {
+      if (s.mxo == 0) return 0.0;
+      if (is_int) return (double)(long long)(s.mxo ^ GB_SIGN);                 // :544-556
+      return pdrs_unord_f64(s.mxo);                                            // :662-674
+    }
+    case PDRS_STD: case PDRS_VAR: {                                            // :557-584 / :675-702 / :881-903
+      if (s.n <= 1) return 0.0;
+      double var = (s.S2 - s.S1 * s.S1 / n) / (n - 1.0);
+      if (var < 0.0) var = 0.0;
+      return op == PDRS_STD ? sqrt(var) : var;
+    }
+  }
+  return 0.0;
+}
+
+__global__ void gb_finalize_kernel(const FinParams p) {
+  const long long total = p.gt.slots + 1;
+  const int lane = threadIdx.x & 31;
+  for (long long s0 = (long long)blockIdx.x * blockDim.x; s0 < total; s0 += (long long)gridDim.x * blockDim.x) {
+    const long long s = s0 + threadIdx.x;
+    u64 rw = 0;
+    if (s < total) rw = p.gt.hdr[s].rowsw;
+    const bool full = (rw & GB_FULL) != 0;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, full);
+    if (!m) continue;
+    u64 basepos = 0;
+    if (lane == 0) basepos = atomicAdd(&p.gt.counters[CNT_OUT], (u64)__popc(m));
+    basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
+    if (!full) continue;
+    const long long o = (long long)(basepos + __popc(m & ((1u << lane) - 1u)));
+    const u64 rows = rw & GB_CNT_MASK;
+    // keys
+    u64 w[PDRS_MAX_WORDS] = {0, 0, 0};
+    const bool nullgroup = s == p.gt.slots;
+    if (!nullgroup) {
+      w[0] = p.gt.hdr[s].key0;
+      if (p.ks.nwords > 1) w[1] = p.gt.kw1[s];
+      if (p.ks.nwords > 2) w[2] = p.gt.kw2[s];
+    }
+    for (int k = 0; k < p.ks.nkeys; k++) {
+      const KeyColDev& c = p.ks.c[k];
+      bool isnull = nullgroup;
+      if (!nullgroup && c.nword >= 0) isnull = (w[c.nword] >> c.nshift) & 1;
+      u64 v = 0;
+      if (!isnull) { v = w[c.word] >> c.shift; if (c.bits < 64) v &= (1ull << c.bits) - 1ull; }
+      switch (c.dtype) {
+        case PDRS_I64: case PDRS_F64: reinterpret_cast<u64*>(p.key_out[k])[o] = v; break;
+        case PDRS_I32: case PDRS_DICT_U32: reinterpret_cast<uint32_t*>(p.key_out[k])[o] = (uint32_t)v; break;
+        case PDRS_BOOL_BITS: reinterpret_cast<uint8_t*>(p.key_out[k])[o] = (uint8_t)v; break;
+      }
+      p.key_null_out[k][o] = isnull ? 1 : 0;
+    }
+    p.rows_out[o] = (long long)rows;
+    GState zero;
+    zero.n = 0; zero.pivotx = 0; zero.S1 = 0; zero.S2 = 0; zero.mnc = 0; zero.mxo = 0; zero.isum = 0; zero.pad = 0;
+    for (int v = 0; v < p.nvals; v++) {
+      const GState st = p.vals[v].st ? p.vals[v].st[s] : zero;
+      if (p.vals[v].validn_out) p.vals[v].validn_out[o] = (long long)st.n;
+      if (p.vals[v].states_out) {
+        u64* q = p.vals[v].states_out + 8 * o;
+        q[0] = rows; q[1] = st.n; q[2] = st.pivotx; q[3] = (u64)__double_as_longlong(st.S1);
+        q[4] = (u64)__double_as_longlong(st.S2); q[5] = st.mnc; q[6] = st.mxo; q[7] = st.isum;
+      }
+    }
+    for (int a = 0; a < p.naggs; a++) {
+      const FinAgg& ag = p.aggs[a];
+      if (ag.val < 0 || !p.vals[ag.val].st) { ag.out[o] = ag.op == PDRS_COUNT ? (double)rows : 0.0; continue; }
+      const GState st = p.vals[ag.val].st[s];
+      ag.out[o] = fin_eval(st, p.vals[ag.val].is_int, ag.op, rows);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- merge of partial states
+struct MergeParams {
+  KeySpec ks;
+  long long n;
+  GTable gt;
+  int nvals;
+  const u64* states[PDRS_MAX_VALS];
+  GState* st[PDRS_MAX_VALS];
+};
+template <int NW>
+__global__ void gb_merge_kernel(const MergeParams p) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    u64 w[NW];
+    bool knull = load_key_generic<NW>(p.ks, i, w);
+    long long gs = knull ? p.gt.slots : g_find_or_insert<NW>(p.gt, w);
+    if (gs < 0) continue;
+    if (knull && !(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL);
+    for (int v = 0; v < p.nvals; v++) {
+      const u64* q = p.states[v] + 8 * i;
+      GTable t = p.gt;
+      t.st = p.st[v];
+      const bool have_c = q[2] != 0;
+      g_update_batch<GB_ALL, true>(t, gs, v == 0 ? q[0] : 0ull, q[1], fin_pivot(q[2]), have_c,
+                                   __longlong_as_double((long long)q[3]), __longlong_as_double((long long)q[4]), q[7], q[5], q[6]);
+    }
+    if (p.nvals == 0) { /* keys only: nothing to add */ }
+  }
+}
+
+// ---------------------------------------------------------------- result object
+struct pdrs_groupby_result {
+  pdrs_ctx* ctx = nullptr;
+  int64_t n_groups = 0;
+  int nkeys = 0, nvals = 0, naggs = 0;
+  int key_dtype[PDRS_MAX_KEYS] = {0, 0, 0, 0};
+  DevBuf key_vals[PDRS_MAX_KEYS], key_nulls[PDRS_MAX_KEYS], rows;
+  DevBuf validn[PDRS_MAX_VALS], states[PDRS_MAX_VALS];
+  DevBuf aggs[PDRS_MAX_AGGS];
+};
+
+static int key_out_bytes(int dtype) {
+  switch (dtype) { case PDRS_I64: case PDRS_F64: return 8; case PDRS_I32: case PDRS_DICT_U32: return 4; default: return 1; }
+}
+
+// ---------------------------------------------------------------- key layout
+int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* ks) {
+  memset(ks, 0, sizeof(*ks));
+  ks->nkeys = nkeys;
+  if (nkeys == 1) {
+    ks->single_null = 1;
+    ks->nwords = 1;
+    KeyColDev& d = ks->c[0];
+    d.data = kv[0].data; d.nulls = kv[0].nulls; d.null_alias = kv[0].null_alias; d.dtype = kv[0].dtype;
+    d.word = 0; d.shift = 0; d.nword = -1; d.nshift = 0;
+    d.bits = (kv[0].dtype == PDRS_I64 || kv[0].dtype == PDRS_F64) ? 64 : (kv[0].dtype == PDRS_BOOL_BITS ? 1 : 32);
+    return PDRS_OK;
+  }
+  int used[PDRS_MAX_WORDS + 2] = {0, 0, 0, 0, 0};
+  int nwords = 0;
+  auto place = [&](int bits, int* word, int* shift) -> bool {
+    for (int w = 0; w < PDRS_MAX_WORDS; w++) {
+      if (used[w] + bits <= 64) { *word = w; *shift = used[w]; used[w] += bits; nwords = std::max(nwords, w + 1); return true; }
+    }
+    return false;
+  };
+  bool ok = true;
+  for (int pass = 0; pass < 2 && ok; pass++) {      // 64-bit parts first, then the narrow ones
+    for (int k = 0; k < nkeys && ok; k++) {
+      int bits = (kv[k].dtype == PDRS_I64 || kv[k].dtype == PDRS_F64) ? 64 : (kv[k].dtype == PDRS_BOOL_BITS ? 1 : 32);
+      if ((bits == 64) != (pass == 0)) continue;
+      KeyColDev& d = ks->c[k];
+      d.data = kv[k].data; d.nulls = kv[k].nulls; d.null_alias = kv[k].null_alias; d.dtype = kv[k].dtype; d.bits = bits;
+      ok = place(bits, &d.word, &d.shift);
+    }
+  }
+  for (int k = 0; k < nkeys && ok; k++) {
+    KeyColDev& d = ks->c[k];
+    d.nword = -1;
+    if (kv[k].nulls || (kv[k].dtype == PDRS_DICT_U32 && kv[k].null_alias >= 0)) ok = place(1, &d.nword, &d.nshift);
+  }
+  if (!ok) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "key tuple does not fit %d x 64 bits", PDRS_MAX_WORDS);
+  ks->nwords = nwords;
+  ks->single_null = 0;
+  return PDRS_OK;
+}
+
+// ---------------------------------------------------------------- dispatch helpers
+static int variant_of(const KeySpec& ks) {
+  if (ks.nkeys == 1 && ks.c[0].dtype == PDRS_I64) return 0;   // k1
+  return ks.nwords;                                            // g1, g2, g3
+}
+static cudaError_t launch_shared(int variant, const GbCfg& cfg, const GbParams& p, size_t smem, cudaStream_t s) {
+  switch (variant) {
+    case 0: return gb_launch_shared_k1(cfg, p, smem, s);
+    case 1: return gb_launch_shared_g1(cfg, p, smem, s);
+    case 2: return gb_launch_shared_g2(cfg, p, smem, s);
+    default: return gb_launch_shared_g3(cfg, p, smem, s);
+  }
+}
+static cudaError_t launch_global(int variant, const GbCfg& cfg, const GbParams& p, cudaStream_t s) {
+  switch (variant) {
+    case 0: return gb_launch_global_k1(cfg, p, s);
+    case 1: return gb_launch_global_g1(cfg, p, s);
+    case 2: return gb_launch_global_g2(cfg, p, s);
+    default: return gb_launch_global_g3(cfg, p, s);
+  }
+}
+static cudaError_t launch_sample(int variant, const GbParams& p, long long nb, long long stride, int ctas, cudaStream_t s) {
+  switch (variant) {
+    case 0: return gb_launch_sample_k1(p, nb, stride, ctas, s);
+    case 1: return gb_launch_sample_g1(p, nb, stride, ctas, s);
+    case 2: return gb_launch_sample_g2(p, nb, stride, ctas, s);
+    default: return gb_launch_sample_g3(p, nb, stride, ctas, s);
+  }
+}
+
+static long long pow2ceil(long long x) { long long p = 1; while (p < x) p <<= 1; return p; }
+static int ilog2(long long x) { int l = 0; while ((1ll << l) < x) l++; return l; }
+
+struct TableMem {
+  DevBuf hdr, kw1, kw2, counters;
+  GTable t{};
+};
+static int32_t alloc_table(pdrs_ctx* c, long long slots, int nwords, TableMem* tm) {
+  PDRS_TRY(tm->hdr.alloc(c, (size_t)(slots + 1) * sizeof(GHdr), true));
+  if (nwords > 1) PDRS_TRY(tm->kw1.alloc(c, (size_t)(slots + 1) * 8));
+  if (nwords > 2) PDRS_TRY(tm->kw2.alloc(c, (size_t)(slots + 1) * 8));
+  PDRS_TRY(tm->counters.alloc(c, CNT_N * 8, true));
+  tm->t.hdr = tm->hdr.as<GHdr>();
+  tm->t.kw1 = tm->kw1.as<u64>();
+  tm->t.kw2 = tm->kw2.as<u64>();
+  tm->t.st = nullptr;
+  tm->t.mask = (u64)slots - 1;
+  tm->t.slots = slots;
+  tm->t.counters = tm->counters.as<u64>();
+  return PDRS_OK;
+}
+static int32_t read_counters(pdrs_ctx* c, const TableMem& tm, u64* out /*[CNT_N + 1]: + NULL-group flag*/) {
+  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, tm.t.counters, CNT_N * 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + CNT_N, &tm.t.hdr[tm.t.slots].rowsw, 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i <= CNT_N; i++) out[i] = (u64)c->pinned_scalars[i];
+  return PDRS_OK;
+}
+
+// d distinct keys among s uniformly sampled rows -> number of groups under a uniform model
+static double invert_distinct(double d, double s) {
+  if (d >= s) return 1e18;
+  double lo = d, hi = 1e18;
+  for (int it = 0; it < 200; it++) {
+    double mid = std::sqrt(lo * hi);
+    double f = mid * (1.0 - std::exp(-s / mid));
+    if (f < d) lo = mid; else hi = mid;
+    if (hi / lo < 1.0001) break;
+  }
+  return std::sqrt(lo * hi);
+}
+
+struct PassPlan { int val; int flags; int is_int; };
+
+enum { MODE_AGG = 0, MODE_PARTIAL = 1 };
+
+static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
+                           const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, int mode, int partial_all,
+                           pdrs_groupby_result** out) {
+  if (!c) return PDRS_ERR_BAD_ARG;
+  if (!out || !keys || nkeys < 1 || nkeys > PDRS_MAX_KEYS || nvals < 0 || nvals > PDRS_MAX_VALS || naggs < 0 || naggs > PDRS_MAX_AGGS ||
+      (nvals && !vals) || (naggs && !aggs))
+    return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby: bad argument (nkeys %d, nvals %d, naggs %d)", nkeys, nvals, naggs);
+  PDRS_CUDA(c, cudaSetDevice(c->device));
+  const int64_t n = keys[0].len;
+  for (int k = 0; k < nkeys; k++) if (keys[k].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "key column %d has %lld rows, expected %lld", k, (long long)keys[k].len, (long long)n);
+  for (int v = 0; v < nvals; v++) if (vals[v].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "value column %d has %lld rows, expected %lld", v, (long long)vals[v].len, (long long)n);
+  if (filter && (filter->dtype != PDRS_BOOL_BITS || filter->len != n)) return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "filter must be a Boolean column of the same length");
+
+  // ---- which statistics does each value column need
+  int need[PDRS_MAX_VALS];   // -1 unused, GB_SUM, GB_ALL
+  for (int v = 0; v < nvals; v++) need[v] = mode == MODE_PARTIAL ? (partial_all ? GB_ALL : GB_SUM) : -1;
+  for (int a = 0; a < naggs; a++) {
+    const pdrs_agg& ag = aggs[a];
+    if (ag.op < PDRS_SUM || ag.op > PDRS_VAR) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: unknown op %d", a, ag.op);
+    if (ag.op == PDRS_COUNT) { if (ag.value_col >= nvals) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: value column %d out of range", a, ag.value_col); continue; }
+    if (ag.value_col < 0 || ag.value_col >= nvals) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: value column %d out of range", a, ag.value_col);
+    const int dt = vals[ag.value_col].dtype;
+    if (dt != PDRS_I64 && dt != PDRS_F64)   // aggregation.rs:748-752
+      return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "aggregate %d: op %d is not supported on a column of dtype %d (only Count is)", a, ag.op, dt);
+    const int f = (ag.op == PDRS_SUM || ag.op == PDRS_MEAN) ? GB_SUM : GB_ALL;
+    need[ag.value_col] = std::max(need[ag.value_col], f);
+  }
+  if (mode == MODE_PARTIAL) for (int v = 0; v < nvals; v++) if (vals[v].dtype != PDRS_I64 && vals[v].dtype != PDRS_F64) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "partial aggregation needs Int64/Float64 value columns");
+
+  auto* res = new pdrs_groupby_result();
+  res->ctx = c; res->nkeys = nkeys; res->nvals = nvals; res->naggs = naggs;
+  for (int k = 0; k < nkeys; k++) res->key_dtype[k] = keys[k].dtype;
+  struct Guard { pdrs_groupby_result* r; ~Guard() { delete r; } } guard{res};
+
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+  c->stats.groupby_algo_used = 0; c->stats.retries = 0; c->stats.est_groups = 0; c->stats.table_slots = 0; c->stats.spilled_rows = 0;
+  c->stats.main_kernel_ms = 0; c->stats.total_ms = 0;
+
+  // ---- views
+  std::vector<ColView> kv(nkeys), vv(nvals);
+  ColView fv;
+  for (int k = 0; k < nkeys; k++) PDRS_TRY(pdrs_view_col(c, &keys[k], &kv[k]));
+  for (int v = 0; v < nvals; v++) if (need[v] >= 0) PDRS_TRY(pdrs_view_col(c, &vals[v], &vv[v]));
+  if (filter) PDRS_TRY(pdrs_view_col(c, filter, &fv));
+
+  KeySpec ks;
+  PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));
+  const int variant = variant_of(ks);
+
+  std::vector<PassPlan> passes;
+  for (int v = 0; v < nvals; v++) if (need[v] >= 0) passes.push_back({v, need[v], vals[v].dtype == PDRS_I64});
+  if (passes.empty()) passes.push_back({-1, GB_SUM, 0});
+
+  GbParams base{};
+  base.ks = ks;
+  base.n = n;
+  base.fbits = filter ? (const uint8_t*)fv.data : nullptr;
+  base.fnull = filter ? fv.nulls : nullptr;
+  base.compat_nulls = (filter && c->opts.compat_filter_nulls) ? 1 : 0;
+
+  // ---- cardinality estimate
+  long long est = c->opts.groups_hint > 0 ? c->opts.groups_hint : 0;
+  if (n > 0 && est == 0) {
+    long long s_rows = std::min<long long>(n, std::max<long long>(4096, c->opt_sample_rows));
+    long long nb = (s_rows + 255) / 256;
+    long long stride = std::max<long long>(256, n / nb);
+    if (s_rows >= n) { nb = (n + 255) / 256; stride = 256; }
+    TableMem stm;
+    PDRS_TRY(alloc_table(c, pow2ceil(4 * nb * 256), ks.nwords, &stm));
+    GbParams sp = base;
+    sp.gt = stm.t;
+    PDRS_CUDA(c, launch_sample(variant, sp, nb, stride, (int)std::min<long long>(nb, c->sm_count * 8), c->stream));
+    c->stats.kernel_launches++;
+    u64 cn[CNT_N + 1];
+    PDRS_TRY(read_counters(c, stm, cn));
+    double d = (double)cn[CNT_NGROUPS], s = (double)std::min<long long>(n, nb * 256);
+    if (s_rows >= n) est = (long long)d;
+    else est = (long long)std::min<double>((double)n, invert_distinct(d, s) * 1.05 + 1.0);
+    if (est < 1) est = 1;
+    c->stats.est_groups = est;
+  }
+  if (est < 1) est = 1;
+
+  // ---- geometry of the shared-memory kernel per pass; fall back to the global table when it does not fit
+  auto shared_geometry = [&](const PassPlan& pp, GbParams* gp, GbCfg* cfg, size_t* smem) -> bool {
+    const int npl = pp.flags == GB_SUM ? 1 : (pp.is_int ? 4 : 3);
+    long long cap = est + std::max<long long>(est / 8, 16);
+    cap = (cap + 7) / 8 * 8;
+    if (cap > 60000) return false;
+    long long S = std::max<long long>(64, pow2ceil(2 * cap));
+    const size_t fixed = gb_sh_fixed_bytes(ks.nwords, (int)S);
+    const size_t budget = (size_t)c->smem_optin;
+    int warps = c->opt_warps > 0 ? (int)std::min<int64_t>(c->opt_warps, GB_MAX_WARPS) : GB_MAX_WARPS;
+    int ng = 0;
+    for (;;) {
+      for (int g = 32; g >= 1; g >>= 1) {
+        if (c->opt_ng > 0 && g > c->opt_ng) continue;
+        if (fixed + (size_t)warps * gb_sh_warp_bytes(npl, (int)cap, g) <= budget) { ng = g; break; }
+      }
+      if (ng || warps <= 4 || c->opt_warps > 0) break;
+      warps--;
+    }
+    if (!ng) return false;
+    gp->sh_cap = (int)cap; gp->sh_slots = (int)S; gp->sh_log_slots = ilog2(S); gp->sh_ng = ng;
+    cfg->warps = warps;
+    cfg->ctas = c->sm_count * (c->opt_ctas_per_sm > 0 ? (int)c->opt_ctas_per_sm : 1);
+    const long long units = (n + GB_UNIT_ROWS - 1) / GB_UNIT_ROWS;
+    cfg->ctas = (int)std::max<long long>(1, std::min<long long>(cfg->ctas, (units + warps - 1) / warps));
+    *smem = fixed + (size_t)warps * gb_sh_warp_bytes(npl, (int)cap, ng);
+    return true;
+  };
+
+  int algo = c->opts.groupby_algo;
+  if (algo == PDRS_GB_DENSE) algo = PDRS_GB_SHARED;
+  long long slots_mult = 1;
+  TableMem tm;
+  std::vector<DevBuf> states(passes.size());
+  u64 cn[CNT_N + 1] = {0};
+  for (int attempt = 0;; attempt++) {
+    if (attempt > 6) return pdrs_fail(c, PDRS_ERR_OOM, "groupby: hash table kept overflowing after %d retries", attempt);
+    bool use_shared = algo != PDRS_GB_GLOBAL;
+    std::vector<GbParams> gps(passes.size(), base);
+    std::vector<GbCfg> cfgs(passes.size());
+    std::vector<size_t> smems(passes.size(), 0);
+    if (use_shared) {
+      for (size_t i = 0; i < passes.size(); i++) {
+        cfgs[i] = GbCfg{ks.nwords, variant == 0 ? 0 : 1, passes[i].is_int, passes[i].flags, 0, 0};
+        if (!shared_geometry(passes[i], &gps[i], &cfgs[i], &smems[i])) { use_shared = false; break; }
+      }
+    }
+    if (!use_shared && algo == PDRS_GB_SHARED && attempt == 0 && c->opts.groups_hint > 0)
+      return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "groupby_algo=SHARED: %lld groups do not fit shared memory", est);
+    long long slots = std::max<long long>(1024, pow2ceil(2 * est + 1024)) * slots_mult;
+    tm = TableMem();
+    PDRS_TRY(alloc_table(c, slots, ks.nwords, &tm));
+    c->stats.table_slots = slots;
+    c->stats.groupby_algo_used = use_shared ? PDRS_GB_SHARED : PDRS_GB_GLOBAL;
+    if (n > 0) {
+      for (size_t i = 0; i < passes.size(); i++) {
+        GbParams& gp = gps[i];
+        gp.gt = tm.t;
+        gp.count_rows = i == 0;
+        if (passes[i].val >= 0) {
+          PDRS_TRY(states[i].alloc(c, (size_t)(slots + 1) * sizeof(GState), true));
+          gp.gt.st = states[i].as<GState>();
+          gp.val = vv[passes[i].val].data;
+          gp.vnull = vv[passes[i].val].nulls;
+        }
+        if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+        if (use_shared) PDRS_CUDA(c, launch_shared(variant, cfgs[i], gp, smems[i], c->stream));
+        else {
+          GbCfg cfg{ks.nwords, variant == 0 ? 0 : 1, passes[i].is_int, passes[i].flags, 8, 0};
+          cfg.ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (n + 1023) / 1024));
+          PDRS_CUDA(c, launch_global(variant, cfg, gp, c->stream));
+        }
+        if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+        c->stats.kernel_launches++;
+        if (c->opt_timing) {
+          PDRS_CUDA(c, cudaEventSynchronize(c->ev_b));
+          float ms = 0;
+          PDRS_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+          c->stats.main_kernel_ms += ms;
+        }
+      }
+    }
+    PDRS_TRY(read_counters(c, tm, cn));
+    c->stats.spilled_rows = (int64_t)cn[CNT_SPILLED];
+    if (cn[CNT_OVERFLOW] == 0 && cn[CNT_SPIN_FAIL] == 0) break;
+    c->stats.retries++;
+    slots_mult *= 4;
+    if (use_shared && (long long)cn[CNT_SPILLED] > n / 16) algo = PDRS_GB_GLOBAL;
+    for (auto& s : states) s.release();
+  }
+
+  // ---- finalise
+  const int64_t G = (int64_t)cn[CNT_NGROUPS] + ((cn[CNT_N] & GB_FULL) ? 1 : 0);
+  res->n_groups = G;
+  FinParams fp{};
+  fp.gt = tm.t;
+  fp.ks = ks;
+  const size_t Galloc = (size_t)std::max<int64_t>(G, 1);
+  for (int k = 0; k < nkeys; k++) {
+    PDRS_TRY(res->key_vals[k].alloc(c, Galloc * key_out_bytes(keys[k].dtype)));
+    PDRS_TRY(res->key_nulls[k].alloc(c, Galloc));
+    fp.key_out[k] = res->key_vals[k].p;
+    fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
+  }
+  PDRS_TRY(res->rows.alloc(c, Galloc * 8));
+  fp.rows_out = res->rows.as<long long>();
+  fp.nvals = nvals;
+  for (int v = 0; v < nvals; v++) { fp.vals[v].st = nullptr; fp.vals[v].is_int = vals[v].dtype == PDRS_I64; fp.vals[v].flags = std::max(need[v], 0); }
+  for (size_t i = 0; i < passes.size(); i++) {
+    const int v = passes[i].val;
+    if (v < 0) continue;
+    fp.vals[v].st = states[i].as<GState>();
+    PDRS_TRY(res->validn[v].alloc(c, Galloc * 8));
+    fp.vals[v].validn_out = res->validn[v].as<long long>();
+    if (mode == MODE_PARTIAL) {
+      PDRS_TRY(res->states[v].alloc(c, Galloc * 64));
+      fp.vals[v].states_out = res->states[v].as<u64>();
+    }
+  }
+  fp.naggs = naggs;
+  for (int a = 0; a < naggs; a++) {
+    PDRS_TRY(res->aggs[a].alloc(c, Galloc * 8));
+    fp.aggs[a].val = aggs[a].op == PDRS_COUNT ? -1 : aggs[a].value_col;
+    fp.aggs[a].op = aggs[a].op;
+    fp.aggs[a].out = res->aggs[a].as<double>();
+  }
+  if (G > 0) {
+    int g = pdrs_grid_for(c, tm.t.slots + 1, 256);
+    gb_finalize_kernel<<<g, 256, 0, c->stream>>>(fp);
+    c->stats.kernel_launches++;
+    PDRS_CUDA(c, cudaGetLastError());
+  }
+  if (c->opt_timing) {
+    PDRS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    PDRS_CUDA(c, cudaEventSynchronize(c->ev_t1));
+    PDRS_CUDA(c, cudaEventElapsedTime(&c->stats.total_ms, c->ev_t0, c->ev_t1));
+  } else {
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  guard.r = nullptr;
+  *out = res;
+  return PDRS_OK;
+}
+
+extern "C" {
+
+int32_t pdrs_groupby_agg(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
+                         const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, pdrs_groupby_result** out) {
+  return groupby_run(ctx, keys, nkeys, vals, nvals, aggs, naggs, filter, MODE_AGG, 0, out);
+}
+
+int32_t pdrs_groupby_partial(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
+                             const pdrs_col* filter, int32_t all_stats, pdrs_groupby_result** out) {
+  return groupby_run(ctx, keys, nkeys, vals, nvals, nullptr, 0, filter, MODE_PARTIAL, all_stats, out);
+}
+
+int32_t pdrs_groupby_merge(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const uint64_t* const* states_dev, const int32_t* val_is_int,
+                           int32_t nvals, int64_t n_state_rows, const pdrs_agg* aggs, int32_t naggs, pdrs_groupby_result** out) {
+  if (!c) return PDRS_ERR_BAD_ARG;
+  if (!out || !keys || nkeys < 1 || nkeys > PDRS_MAX_KEYS || nvals < 0 || nvals > PDRS_MAX_VALS || naggs < 0 || naggs > PDRS_MAX_AGGS || n_state_rows < 0)
+    return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby_merge: bad argument");
+  PDRS_CUDA(c, cudaSetDevice(c->device));
+  for (int k = 0; k < nkeys; k++) if (keys[k].len != n_state_rows) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "merge: key column %d length mismatch", k);
+  for (int a = 0; a < naggs; a++) if (aggs[a].op != PDRS_COUNT && (aggs[a].value_col < 0 || aggs[a].value_col >= nvals)) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "merge: aggregate %d: bad value column", a);
+  auto* res = new pdrs_groupby_result();
+  res->ctx = c; res->nkeys = nkeys; res->nvals = nvals; res->naggs = naggs;
+  for (int k = 0; k < nkeys; k++) res->key_dtype[k] = keys[k].dtype;
+  struct Guard { pdrs_groupby_result* r; ~Guard() { delete r; } } guard{res};
+  std::vector<ColView> kv(nkeys);
+  for (int k = 0; k < nkeys; k++) PDRS_TRY(pdrs_view_col(c, &keys[k], &kv[k]));
+  KeySpec ks;
+  PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));
+  const int64_t n = n_state_rows;
+  TableMem tm;
+  const long long slots = std::max<long long>(1024, pow2ceil(2 * n + 16));
+  PDRS_TRY(alloc_table(c, slots, ks.nwords, &tm));
+  std::vector<DevBuf> states(nvals);
+  MergeParams mp{};
+  mp.ks = ks; mp.n = n; mp.gt = tm.t; mp.nvals = nvals;
+  for (int v = 0; v < nvals; v++) {
+    PDRS_TRY(states[v].alloc(c, (size_t)(slots + 1) * sizeof(GState), true));
+    mp.states[v] = (const u64*)states_dev[v];
+    mp.st[v] = states[v].as<GState>();
+  }
+  if (n > 0) {
+    int g = pdrs_grid_for(c, n, 256);
+    switch (ks.nwords) {
+      case 1: gb_merge_kernel<1><<<g, 256, 0, c->stream>>>(mp); break;
+      case 2: gb_merge_kernel<2><<<g, 256, 0, c->stream>>>(mp); break;
+      default: gb_merge_kernel<3><<<g, 256, 0, c->stream>>>(mp); break;
+    }
+    c->stats.kernel_launches++;
+    PDRS_CUDA(c, cudaGetLastError());
+  }
+  u64 cn[CNT_N + 1];
+  PDRS_TRY(read_counters(c, tm, cn));
+  if (cn[CNT_OVERFLOW] || cn[CNT_SPIN_FAIL]) return pdrs_fail(c, PDRS_ERR_CUDA, "merge: hash table overflow");
+  const int64_t G = (int64_t)cn[CNT_NGROUPS] + ((cn[CNT_N] & GB_FULL) ? 1 : 0);
+  res->n_groups = G;
+  FinParams fp{};
+  fp.gt = tm.t; fp.ks = ks;
+  const size_t Galloc = (size_t)std::max<int64_t>(G, 1);
+  for (int k = 0; k < nkeys; k++) {
+    PDRS_TRY(res->key_vals[k].alloc(c, Galloc * key_out_bytes(keys[k].dtype)));
+    PDRS_TRY(res->key_nulls[k].alloc(c, Galloc));
+    fp.key_out[k] = res->key_vals[k].p;
+    fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
+  }
+  PDRS_TRY(res->rows.alloc(c, Galloc * 8));
+  fp.rows_out = res->rows.as<long long>();
+  fp.nvals = nvals;
+  for (int v = 0; v < nvals; v++) {
+    fp.vals[v].st = states[v].as<GState>();
+    fp.vals[v].is_int = val_is_int ? val_is_int[v] : 0;
+    fp.vals[v].flags = GB_ALL;
+    PDRS_TRY(res->validn[v].alloc(c, Galloc * 8));
+    fp.vals[v].validn_out = res->validn[v].as<long long>();
+    PDRS_TRY(res->states[v].alloc(c, Galloc * 64));
+    fp.vals[v].states_out = res->states[v].as<u64>();
+  }
+  fp.naggs = naggs;
+  for (int a = 0; a < naggs; a++) {
+    PDRS_TRY(res->aggs[a].alloc(c, Galloc * 8));
+    fp.aggs[a].val = aggs[a].op == PDRS_COUNT ? -1 : aggs[a].value_col;
+    fp.aggs[a].op = aggs[a].op;
+    fp.aggs[a].out = res->aggs[a].as<double>();
+  }
+  if (G > 0) {
+    gb_finalize_kernel<<<pdrs_grid_for(c, slots + 1, 256), 256, 0, c->stream>>>(fp);
+    c->stats.kernel_launches++;
+    PDRS_CUDA(c, cudaGetLastError());
+  }
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  guard.r = nullptr;
+  *out = res;
+  return PDRS_OK;
+}
+
+int64_t pdrs_groupby_n_groups(const pdrs_groupby_result* r) { return r ? r->n_groups : -1; }
+
+static int32_t copy_out(const pdrs_groupby_result* r, void* dst, const DevBuf& src, size_t bytes) {
+  pdrs_ctx* c = r->ctx;
+  if (!dst) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "NULL output pointer");
+  if (!src.p) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "result does not hold the requested array");
+  if (bytes == 0) return PDRS_OK;
+  PDRS_CUDA(c, cudaMemcpyAsync(dst, src.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PDRS_OK;
+}
+
+int32_t pdrs_groupby_key(const pdrs_groupby_result* r, int32_t k, void* out_values, uint8_t* out_is_null) {
+  if (!r || k < 0 || k >= r->nkeys) return PDRS_ERR_BAD_ARG;
+  PDRS_TRY(copy_out(r, out_values, r->key_vals[k], (size_t)r->n_groups * key_out_bytes(r->key_dtype[k])));
+  if (out_is_null) PDRS_TRY(copy_out(r, out_is_null, r->key_nulls[k], (size_t)r->n_groups));
+  return PDRS_OK;
+}
+int32_t pdrs_groupby_agg_values(const pdrs_groupby_result* r, int32_t a, double* out) {
+  if (!r || a < 0 || a >= r->naggs) return PDRS_ERR_BAD_ARG;
+  return copy_out(r, out, r->aggs[a], (size_t)r->n_groups * 8);
+}
+int32_t pdrs_groupby_group_rows(const pdrs_groupby_result* r, int64_t* out) {
+  if (!r) return PDRS_ERR_BAD_ARG;
+  return copy_out(r, out, r->rows, (size_t)r->n_groups * 8);
+}
+int32_t pdrs_groupby_valid_n(const pdrs_groupby_result* r, int32_t v, int64_t* out) {
+  if (!r || v < 0 || v >= r->nvals) return PDRS_ERR_BAD_ARG;
+  return copy_out(r, out, r->validn[v], (size_t)r->n_groups * 8);
+}
+const void* pdrs_groupby_key_dev(const pdrs_groupby_result* r, int32_t k) { return (r && k >= 0 && k < r->nkeys) ? r->key_vals[k].p : nullptr; }
+const uint8_t* pdrs_groupby_key_null_dev(const pdrs_groupby_result* r, int32_t k) { return (r && k >= 0 && k < r->nkeys) ? r->key_nulls[k].as<uint8_t>() : nullptr; }
+const double* pdrs_groupby_agg_dev(const pdrs_groupby_result* r, int32_t a) { return (r && a >= 0 && a < r->naggs) ? r->aggs[a].as<double>() : nullptr; }
+const int64_t* pdrs_groupby_group_rows_dev(const pdrs_groupby_result* r) { return r ? r->rows.as<int64_t>() : nullptr; }
+const uint64_t* pdrs_groupby_states_dev(const pdrs_groupby_result* r, int32_t v) { return (r && v >= 0 && v < r->nvals) ? r->states[v].as<uint64_t>() : nullptr; }
+void pdrs_groupby_result_free(pdrs_groupby_result* r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  delete r;
+}
+
+}  // extern "C"

@@ -1,0 +1,414 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: `pytest -m gpu`.
+
+Cases follow the reference's own tests for this path plus the edge cases of §9:
+empty and ragged inputs, NULL keys / values, sentinel collapse, duplicate-key fan-out, filters."""
+import numpy as np
+import pytest
+
+import pandrs_b200 as pb
+from _util import Spec, compare_groupby, compare_join, gpu_groupby_dict
+
+pytestmark = pytest.mark.gpu
+
+ALL6 = [pb.SUM, pb.MEAN, pb.MIN, pb.MAX, pb.COUNT, pb.STD]
+A = "A B A B A C B C C A".split()
+VALUE = [10, 25, 15, 30, 22, 18, 24, 12, 16, 20]
+FLOAT = [1.1, 2.2, 3.3, 4.4, 5.5, 6.6, 7.7, 8.8, 9.9, 10.0]
+
+
+def _dict(strings):
+    pool, ids = [], []
+    for s in strings:
+        if s not in pool:
+            pool.append(s)
+        ids.append(pool.index(s))
+    return ids, pool
+
+
+# ---------------------------------------------------------------- reference known-answer vectors
+def test_pandas_compat_groupby_goldens(ctx, oracle):
+    # src/dataframe/pandas_compat/groupby.rs:480-617
+    ids, pool = _dict(["A", "B", "A", "B", "A"])
+    key = Spec(pb.DICT_U32, ids, pool=pool)
+    val = Spec(pb.F64, [10.0, 20.0, 30.0, 40.0, 50.0])
+    got = compare_groupby(pb, oracle, ctx, [key], [val], [(0, op) for op in ALL6])
+    assert got[("A",)] == (3, [90.0, 30.0, 10.0, 50.0, 3.0, 20.0])
+    assert got[("B",)][1][:5] == [60.0, 30.0, 20.0, 40.0, 2.0]
+
+
+def test_ten_row_fixture(ctx, oracle):
+    # tests/optimized_groupby_enhanced_test.rs:12-23; total 192 (optimized_custom_aggregation_test.rs:49)
+    ids, pool = _dict(A)
+    key = Spec(pb.DICT_U32, ids, pool=pool)
+    ops = [pb.COUNT, pb.SUM, pb.MEAN, pb.MIN, pb.MAX, pb.STD]
+    got = compare_groupby(pb, oracle, ctx, [key], [Spec(pb.I64, VALUE), Spec(pb.F64, FLOAT)], [(0, op) for op in ops] + [(1, op) for op in ops])
+    want_i = {"A": [4, 67, 16.75, 10, 22, 5.377421934967226], "B": [3, 79, 26.333333333333332, 24, 30, 3.2145502536643185],
+              "C": [3, 46, 15.333333333333334, 12, 18, 3.055050463303893]}
+    want_f = {"A": [4, 19.9, 4.975, 1.1, 10.0, 3.8012059489939065], "B": [3, 14.3, 4.766666666666667, 2.2, 7.7, 2.768272626265942],
+              "C": [3, 25.3, 8.433333333333334, 6.6, 9.9, 1.680277754817142]}
+    for k in "ABC":
+        vals = got[(k,)][1]
+        assert vals[:6] == pytest.approx(want_i[k], rel=1e-14)
+        assert vals[6:] == pytest.approx(want_f[k], rel=1e-14)
+    assert sum(got[(k,)][1][1] for k in "ABC") == 192
+
+
+def test_concurrency_fixture_four_groups(ctx, oracle):
+    # tests/concurrency_test.rs:351-384 — 1,000 rows, category i % 4 -> 4 groups of 250
+    got = compare_groupby(pb, oracle, ctx, [Spec(pb.I64, np.arange(1000) % 4)], [Spec(pb.F64, np.arange(1000, dtype=np.float64))], [(0, pb.COUNT)])
+    assert sorted(v[0] for v in got.values()) == [250] * 4
+
+
+def test_join_goldens(ctx, oracle):
+    # tests/optimized_join_test.rs:6-237
+    L, R = Spec(pb.I64, [1, 2, 3, 4]), Spec(pb.I64, [1, 2, 5, 6])
+    li, ri = compare_join(pb, oracle, ctx, L, R, pb.INNER)
+    assert list(zip(li, ri)) == [(0, 0), (1, 1)]
+    li, ri = compare_join(pb, oracle, ctx, L, R, pb.LEFT)
+    assert list(zip(li, ri)) == [(0, 0), (1, 1), (2, -1), (3, -1)]
+    li, ri = compare_join(pb, oracle, ctx, L, Spec(pb.I64, [5, 6, 7, 8]), pb.INNER)
+    assert len(li) == 0
+    # src/dataframe/pandas_compat/merge.rs:320-410 — keys A,B,C,D / B,C,D,E, left order kept
+    pool = list("ABCDE")
+    li, ri = compare_join(pb, oracle, ctx, Spec(pb.DICT_U32, [0, 1, 2, 3], pool=pool), Spec(pb.DICT_U32, [1, 2, 3, 4], pool=pool), pb.LEFT)
+    assert list(li) == [0, 1, 2, 3] and list(ri) == [-1, 0, 1, 2]
+
+
+def test_join_type_mismatch_and_unsupported(ctx):
+    # join.rs:98-104 -> Error::ColumnTypeMismatch
+    with pytest.raises(pb.PandrsError) as e:
+        ctx.join_pairs(pb.Column.int64([1]), pb.Column.float64([1.0]))
+    assert e.value.kind == "ColumnTypeMismatch"
+    with pytest.raises(pb.PandrsError) as e:
+        ctx.join_pairs(pb.Column.int64([1]), pb.Column.int64([1]), how=3)
+    assert e.value.kind == "OperationFailed"
+    # aggregation.rs:748-752 -> Error::OperationFailed for Sum on a string column; Count is fine
+    with pytest.raises(pb.PandrsError) as e:
+        ctx.groupby_agg([pb.Column.int64([1, 2])], [pb.Column.dict_ids([0, 1])], [(0, pb.SUM)])
+    assert e.value.kind == "OperationFailed"
+    r = ctx.groupby_agg([pb.Column.int64([1, 1])], [pb.Column.dict_ids([0, 1])], [(0, pb.COUNT)])
+    assert r.n_groups == 1 and r.agg(0)[0] == 2.0
+    r.close()
+
+
+# ---------------------------------------------------------------- NULL semantics / sentinels
+def test_null_semantics(ctx, oracle):
+    key = Spec(pb.I64, [7, 7, 0, 0, 9], nulls=[0, 0, 1, 1, 0])
+    val = Spec(pb.F64, [1.0, 2.0, 3.0, 4.0, 5.0], nulls=[0, 1, 0, 0, 1])
+    got = compare_groupby(pb, oracle, ctx, [key], [val], [(0, op) for op in ALL6])
+    assert got[("7",)][1] == [1.0, 1.0, 1.0, 1.0, 2.0, 0.0]
+    assert got[("9",)][1] == [0.0, 0.0, 0.0, 0.0, 1.0, 0.0]
+    assert got[("NULL",)][1][0] == 7.0 and got[("NULL",)][1][4] == 2.0
+    li, ri = compare_join(pb, oracle, ctx, Spec(pb.I64, [1, 2, 3], nulls=[0, 1, 0]), Spec(pb.I64, [1, 2, 3], nulls=[0, 0, 1]), pb.LEFT)
+    assert list(zip(li, ri)) == [(0, 0), (2, -1)]
+
+
+def test_short_null_mask(ctx, oracle):
+    # int64_column.rs:77: bytes past the end of the mask read as "not NULL"
+    k = pb.Column(pb.I64, np.arange(20) % 2, nulls=np.array([0xFF], np.uint8))
+    r = ctx.groupby_agg([k], [pb.Column.float64(np.ones(20))], [(0, pb.COUNT)])
+    keys, isnull = r.key(0)
+    cnt = r.agg(0)
+    got = {("NULL" if isnull[g] else int(keys[g])): cnt[g] for g in range(r.n_groups)}
+    r.close()
+    assert got == {"NULL": 8.0, 0: 6.0, 1: 6.0}
+
+
+def test_int_sentinels_and_wrapping(ctx, oracle):
+    key = Spec(pb.I64, [1, 1, 2, 2])
+    val = Spec(pb.I64, [2**63 - 1, 1, -(2**63), -(2**63)])
+    got = compare_groupby(pb, oracle, ctx, [key], [val], [(0, pb.SUM), (0, pb.MIN), (0, pb.MAX), (0, pb.MEAN), (0, pb.STD)])
+    assert got[("1",)][1][0] == float(-(2**63)) and got[("2",)][1][2] == 0.0
+
+
+def test_float_specials(ctx, oracle):
+    inf, nan = np.inf, np.nan
+    key = Spec(pb.I64, [1, 1, 1, 2, 2, 3, 3, 4, 5, 5])
+    val = Spec(pb.F64, [1.0, nan, 3.0, inf, 2.0, -inf, -inf, nan, -0.0, 0.0])
+    compare_groupby(pb, oracle, ctx, [key], [val], [(0, op) for op in ALL6])
+
+
+def test_dict_null_alias_and_bool_f64_keys(ctx, oracle):
+    # a string literally "NULL" merges with the NULL group (grouping.rs:69-98)
+    pool = ["x", "NULL", "y"]
+    key = Spec(pb.DICT_U32, [0, 1, 2, 1, 0, 2], nulls=[0, 0, 0, 0, 1, 0], pool=pool, null_alias=1)
+    val = Spec(pb.F64, np.arange(6, dtype=np.float64))
+    got = compare_groupby(pb, oracle, ctx, [key], [val], [(0, pb.SUM), (0, pb.COUNT)])
+    assert got[("NULL",)] == (3, [8.0, 3.0])
+    rng = np.random.default_rng(5)
+    kb = Spec(pb.BOOL_BITS, rng.integers(0, 2, 500), nulls=rng.random(500) < 0.1)
+    kf = Spec(pb.F64, rng.choice([0.0, -0.0, 1.5, np.nan, 2.0, np.inf], 500))
+    v = Spec(pb.F64, rng.random(500))
+    compare_groupby(pb, oracle, ctx, [kb], [v], [(0, op) for op in ALL6])
+    compare_groupby(pb, oracle, ctx, [kf], [v], [(0, op) for op in ALL6])
+    compare_groupby(pb, oracle, ctx, [kb, kf], [v], [(0, op) for op in ALL6])
+
+
+# ---------------------------------------------------------------- randomized parity, both kernels
+def _synth(oracle, n, card, nulls=True, seed=42, scramble=False):
+    k = oracle.synth_keys(n, seed=seed, card=card, scramble=scramble)
+    v = oracle.synth_vals(n, seed=seed)
+    vn = None
+    if nulls:
+        vn = np.unpackbits(oracle.synth_nulls(n, seed=seed), bitorder="little")[:n].astype(bool)
+    return Spec(pb.I64, k), Spec(pb.F64, v, vn)
+
+
+def test_config1_shape(ctx, oracle):
+    # BASELINE.json configs[0]: 1M rows, i64 key (1K distinct), sum/mean/max of f64
+    k, v = _synth(oracle, 1_000_000, 1000, nulls=False)
+    got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, pb.SUM), (0, pb.MEAN), (0, pb.MAX)], device=True)
+    assert len(got) == 1000
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_SHARED
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 511, 512, 513, 1025, 100_003])
+def test_ragged_sizes(ctx, oracle, n):
+    k, v = _synth(oracle, n, 17)
+    compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6])
+    compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+
+
+def test_empty(ctx):
+    r = ctx.groupby_agg([pb.Column.int64([])], [pb.Column.float64([])], [(0, pb.SUM)])
+    assert r.n_groups == 0 and len(r.agg(0)) == 0
+    r.close()
+    j = ctx.join_pairs(pb.Column.int64([]), pb.Column.int64([1, 2]))
+    assert j.n == 0
+    j.close()
+    j = ctx.join_pairs(pb.Column.int64([1, 2]), pb.Column.int64([]), how=pb.LEFT)
+    assert list(zip(*j.indices())) == [(0, -1), (1, -1)]
+    j.close()
+
+
+@pytest.mark.parametrize("card", [1, 3, 100, 1000, 3000, 20000, 150000])
+@pytest.mark.parametrize("algo", [pb.GB_AUTO, pb.GB_GLOBAL])
+def test_cardinalities_all_aggs(ctx, oracle, card, algo):
+    # BASELINE.json configs[1] at oracle-sized n: six aggregates, 5% NULL values
+    n = 200_000
+    k, v = _synth(oracle, n, card, scramble=card > 100)
+    ctx.set_option("groupby_algo", algo)
+    try:
+        got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+    finally:
+        ctx.set_option("groupby_algo", pb.GB_AUTO)
+    assert len(got) == len(np.unique(k.values))
+
+
+@pytest.mark.parametrize("ops", [[pb.SUM], [pb.SUM, pb.MEAN, pb.COUNT], [pb.MIN, pb.MAX], [pb.STD], [pb.VAR, pb.MEAN], [pb.COUNT]])
+def test_agg_subsets_and_int_values(ctx, oracle, ops):
+    n = 50_000
+    k, v = _synth(oracle, n, 257)
+    rng = np.random.default_rng(1)
+    vi = Spec(pb.I64, rng.integers(-10**12, 10**12, n), nulls=rng.random(n) < 0.05)
+    compare_groupby(pb, oracle, ctx, [k], [v, vi], [(0, op) for op in ops] + [(1, op) for op in ops])
+
+
+def test_key_nulls_and_spill(ctx, oracle):
+    n = 120_000
+    rng = np.random.default_rng(2)
+    k = Spec(pb.I64, rng.integers(-50, 50, n), nulls=rng.random(n) < 0.03)
+    v = Spec(pb.F64, rng.normal(0, 1e6, n), nulls=rng.random(n) < 0.05)
+    compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6])
+    # under-estimated cardinality: the CTA tables overflow and rows spill to the global table
+    k2 = Spec(pb.I64, rng.integers(0, 1500, n))
+    ctx.set_option("groups_hint", 64)
+    try:
+        got = compare_groupby(pb, oracle, ctx, [k2], [v], [(0, op) for op in ALL6])
+        st = ctx.stats()
+    finally:
+        ctx.set_option("groups_hint", 0)
+    assert len(got) == 1500 and st["spilled_rows"] > 0
+
+
+def test_variance_is_stable_for_offset_groups(ctx, oracle):
+    # group means far apart and far from zero: a single global pivot would lose all digits
+    n = 100_000
+    rng = np.random.default_rng(3)
+    g = rng.integers(0, 50, n)
+    v = 1e9 * (g + 1) + rng.normal(0, 1.0, n)
+    compare_groupby(pb, oracle, ctx, [Spec(pb.I64, g)], [Spec(pb.F64, v)], [(0, pb.STD), (0, pb.VAR), (0, pb.MEAN), (0, pb.SUM)])
+
+
+def test_multi_key_and_dictionary(ctx, oracle):
+    # BASELINE.json configs[3] shape: (i32, i64) + dictionary-encoded string key, skewed keys
+    n = 150_000
+    rng = np.random.default_rng(4)
+    z = lambda a, dom: np.minimum(rng.zipf(a, n) - 1, dom - 1)
+    k1 = Spec(pb.I32, z(1.1, 1000).astype(np.int32) - 500)
+    k2 = Spec(pb.I64, z(1.1, 100000).astype(np.int64) * 7_000_000_007)
+    pool = [f"s{i}" for i in range(10000)]
+    k3 = Spec(pb.DICT_U32, z(1.1, 10000).astype(np.uint32), pool=pool)
+    v = Spec(pb.F64, rng.random(n) * 1000, nulls=rng.random(n) < 0.05)
+    compare_groupby(pb, oracle, ctx, [k1, k2, k3], [v], [(0, op) for op in ALL6], device=True)
+    compare_groupby(pb, oracle, ctx, [k1, k3], [v], [(0, pb.SUM), (0, pb.COUNT)])
+    # with NULL key parts: every distinct NULL pattern is its own group
+    k1n = Spec(pb.I32, k1.values, nulls=rng.random(n) < 0.2)
+    k3n = Spec(pb.DICT_U32, k3.values % 5, nulls=rng.random(n) < 0.2, pool=pool)
+    k2s = Spec(pb.I64, k2.values % 3, nulls=rng.random(n) < 0.2)
+    compare_groupby(pb, oracle, ctx, [k1n, k2s, k3n], [v], [(0, op) for op in ALL6])
+
+
+@pytest.mark.parametrize("compat", [False, True])
+def test_fused_filter(ctx, oracle, compat):
+    # BASELINE.json configs[4] shape: Boolean-mask filter -> groupby(returnflag, linestatus)
+    n = 80_000
+    rng = np.random.default_rng(6)
+    rf = Spec(pb.DICT_U32, rng.integers(0, 3, n).astype(np.uint32), pool=["A", "N", "R"])
+    ls = Spec(pb.DICT_U32, rng.integers(0, 2, n).astype(np.uint32), pool=["F", "O"])
+    qty = Spec(pb.F64, rng.integers(1, 51, n).astype(np.float64), nulls=rng.random(n) < 0.02)
+    price = Spec(pb.F64, rng.random(n) * 1e5)
+    mask = Spec(pb.BOOL_BITS, rng.random(n) < 0.98, nulls=rng.random(n) < 0.01)
+    aggs = [(0, pb.SUM), (1, pb.SUM), (0, pb.MEAN), (1, pb.MEAN), (0, pb.COUNT), (0, pb.MIN), (1, pb.STD)]
+    ctx.set_option("compat_filter_nulls", int(compat))
+    try:
+        got = compare_groupby(pb, oracle, ctx, [rf, ls], [qty, price], aggs, filter_spec=mask, compat_nulls=compat)
+        got2 = compare_groupby(pb, oracle, ctx, [rf, ls], [qty, price], aggs, filter_spec=mask, compat_nulls=compat, device=True)
+    finally:
+        ctx.set_option("compat_filter_nulls", 0)
+    assert len(got) == 6 and got.keys() == got2.keys()
+
+
+# ---------------------------------------------------------------- joins
+@pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
+def test_join_random_duplicates_and_nulls(ctx, oracle, how):
+    rng = np.random.default_rng(7)
+    L = Spec(pb.I64, rng.integers(0, 400, 3000), nulls=rng.random(3000) < 0.05)
+    R = Spec(pb.I64, rng.integers(0, 400, 2000), nulls=rng.random(2000) < 0.05)
+    compare_join(pb, oracle, ctx, L, R, how)
+    compare_join(pb, oracle, ctx, L, R, how, device=True)
+
+
+@pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
+def test_join_unique_build_config3_shape(ctx, oracle, how):
+    # BASELINE.json configs[2] at oracle-sized n: unique i64 build keys, ~50% hit rate
+    nb, npr = 100_000, 1_000_000
+    R = Spec(pb.I64, oracle.synth_join_keys(nb, unique=True))
+    L = Spec(pb.I64, oracle.synth_join_keys(npr, domain=2 * nb))
+    li, ri = compare_join(pb, oracle, ctx, L, R, how, device=True)
+    if how == pb.INNER:
+        assert 0.45 * npr < len(li) < 0.55 * npr
+    else:
+        assert len(li) == npr
+
+
+@pytest.mark.parametrize("dtype", ["f64", "i32", "dict", "bool"])
+def test_join_other_key_types(ctx, oracle, dtype):
+    rng = np.random.default_rng(8)
+    if dtype == "f64":
+        mk = lambda n: Spec(pb.F64, rng.choice([0.0, -0.0, 1.5, np.nan, 2.0, 7.25], n))
+    elif dtype == "i32":
+        mk = lambda n: Spec(pb.I32, rng.integers(-20, 20, n).astype(np.int32))
+    elif dtype == "dict":
+        pool = [f"k{i}" for i in range(30)]
+        mk = lambda n: Spec(pb.DICT_U32, rng.integers(0, 30, n).astype(np.uint32), pool=pool)
+    else:
+        mk = lambda n: Spec(pb.BOOL_BITS, rng.integers(0, 2, n), nulls=rng.random(n) < 0.3)
+    compare_join(pb, oracle, ctx, mk(300), mk(40), pb.INNER)
+    compare_join(pb, oracle, ctx, mk(300), mk(40), pb.LEFT)
+
+
+def test_gather_and_filter(ctx, oracle):
+    rng = np.random.default_rng(9)
+    n = 10_000
+    idx = rng.integers(-1, n, 25_000)
+    for spec in (Spec(pb.F64, rng.random(n), nulls=rng.random(n) < 0.1), Spec(pb.I64, rng.integers(-5, 5, n), nulls=rng.random(n) < 0.1),
+                 Spec(pb.DICT_U32, rng.integers(0, 9, n).astype(np.uint32), nulls=rng.random(n) < 0.1), Spec(pb.I32, rng.integers(-5, 5, n).astype(np.int32)),
+                 Spec(pb.BOOL_BITS, rng.integers(0, 2, n), nulls=rng.random(n) < 0.1)):
+        got = ctx.gather(spec.gpu(pb), idx)
+        want = oracle.gather(spec.cpu(oracle), idx)
+        assert np.array_equal(got, want)
+    for m in (5, 63, 64, 65, 100_001):
+        mask = Spec(pb.BOOL_BITS, rng.random(m) < 0.6, nulls=rng.random(m) < 0.1)
+        assert np.array_equal(ctx.filter_indices(mask.gpu(pb)), oracle.filter_indices(mask.cpu(oracle)))
+
+
+# ---------------------------------------------------------------- partial states, merge, partitioning (multi-GPU building blocks)
+def test_partial_merge_equals_whole(ctx, oracle):
+    n = 90_000
+    rng = np.random.default_rng(10)
+    k = Spec(pb.I64, rng.integers(0, 700, n), nulls=rng.random(n) < 0.01)
+    v = Spec(pb.F64, 1e6 + rng.normal(0, 3.0, n), nulls=rng.random(n) < 0.05)
+    vi = Spec(pb.I64, rng.integers(-10**9, 10**9, n))
+    aggs = [(0, op) for op in ALL6] + [(1, op) for op in ALL6]
+    cuts = [0, 20_000, 20_001, 55_555, n]
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sl = lambda s: Spec(s.dtype, s.values[a:b], None if s.nulls is None else s.nulls[a:b])
+        parts.append(ctx.groupby_partial([sl(k).gpu(pb)], [sl(v).gpu(pb), sl(vi).gpu(pb)], all_stats=True))
+    # concatenate the partial results on the device side of the ABI: keys + null flags + states
+    tot = sum(p.n_groups for p in parts)
+    keys = np.concatenate([p.key(0)[0] for p in parts])
+    knull = np.concatenate([p.key(0)[1] for p in parts])
+    sts = []
+    for vcol in range(2):
+        buf = ctx.dev_alloc(tot * 64)
+        off = 0
+        for p in parts:
+            ctx.memcpy(buf + off * 64, p.states_dev(vcol), p.n_groups * 64, 2)
+            off += p.n_groups
+        sts.append(buf)
+    merged = ctx.groupby_merge([pb.Column(pb.I64, keys, pb.pack_bits(knull))], sts, [False, True], tot, aggs)
+    got = gpu_groupby_dict(pb, merged, [k], len(aggs))
+    whole = compare_groupby(pb, oracle, ctx, [k], [v, vi], aggs)
+    assert got.keys() == whole.keys()
+    for kt in whole:
+        assert got[kt][0] == whole[kt][0]
+        for a, (g, w) in enumerate(zip(got[kt][1], whole[kt][1])):
+            if aggs[a][1] in (pb.COUNT, pb.MIN, pb.MAX) or a >= 6 and aggs[a][1] == pb.SUM:
+                assert g == w
+            else:
+                assert abs(g - w) <= 1e-12 * max(abs(w), 1e6 if a < 6 else 1e9), (kt, a, g, w)
+    merged.close()
+    for p in parts:
+        p.close()
+    for b in sts:
+        ctx.dev_free(b)
+
+
+def test_hash_partition(ctx):
+    n, parts = 50_000, 8
+    rng = np.random.default_rng(11)
+    k = rng.integers(0, 3000, n)
+    kn = rng.random(n) < 0.02
+    col = pb.Column.int64(k, kn)
+    perm = ctx.dev_alloc(n * 8)
+    counts = ctx.hash_partition([col], parts, perm)
+    p = ctx.to_host(perm, n, np.int64)
+    ctx.dev_free(perm)
+    assert counts.sum() == n and np.array_equal(np.sort(p), np.arange(n))
+    dest = np.repeat(np.arange(parts), counts)
+    d_of_row = np.empty(n, np.int64)
+    d_of_row[p] = dest
+    for key in np.unique(k[~kn])[:500]:
+        assert len(np.unique(d_of_row[(k == key) & ~kn])) == 1
+    assert np.all(d_of_row[kn] == 0)
+    assert counts.min() > n / parts * 0.7
+
+
+# ---------------------------------------------------------------- full-size properties (BASELINE.json sizes)
+def test_two_kernels_agree_at_scale(ctx):
+    # 2^27 rows: the shared-memory kernel and the global-table kernel are independent code paths and must
+    # agree: bit-exact keys / counts / min / max, 1e-12 on sum / mean / std; counts sum to n
+    n = 1 << 27
+    keys = ctx.synth_keys(n, card=1000)
+    vals = ctx.synth_vals(n, null_per_million=50_000)
+    aggs = [(0, op) for op in ALL6]
+    out = []
+    for algo in (pb.GB_SHARED, pb.GB_GLOBAL):
+        ctx.set_option("groupby_algo", algo)
+        r = ctx.groupby_agg([keys], [vals], aggs)
+        ctx.set_option("groupby_algo", pb.GB_AUTO)
+        k, isnull = r.key(0)
+        order = np.argsort(k)
+        out.append((k[order], r.group_rows()[order], r.valid_n(0)[order], [r.agg(a)[order] for a in range(6)]))
+        r.close()
+    a, b = out
+    assert len(a[0]) == 1000 and np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert a[1].sum() == n and abs(a[2].sum() / n - 0.95) < 1e-3
+    for i, op in enumerate(ALL6):
+        if op in (pb.MIN, pb.MAX, pb.COUNT):
+            assert np.array_equal(a[3][i], b[3][i])
+        else:
+            assert np.allclose(a[3][i], b[3][i], rtol=1e-12, atol=0)
+    assert np.array_equal(a[3][4], a[1].astype(np.float64))
