@@ -34,6 +34,7 @@ struct pdrs_ctx {
   int64_t opt_ng = 0;                  // 0 = auto (accumulator replicas per warp)
   int64_t opt_join_algo = 0;           // 0 = auto
   int64_t opt_timing = 1;              // record CUDA-event times in pdrs_stats
+  int64_t opt_dense = 1;               // allow the direct-mapped path for small dense integer keys
 };
 
 int32_t pdrs_fail(pdrs_ctx* ctx, int32_t code, const char* fmt, ...);

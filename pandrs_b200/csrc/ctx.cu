@@ -115,6 +115,7 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "ng")) c->opt_ng = value;
   else if (!strcmp(name, "join_algo")) c->opt_join_algo = value;
   else if (!strcmp(name, "timing")) c->opt_timing = value;
+  else if (!strcmp(name, "dense")) c->opt_dense = value;
   else return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown option '%s'", name);
   return PDRS_OK;
 }

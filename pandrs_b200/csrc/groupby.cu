@@ -43,12 +43,12 @@ __device__ double fin_eval(const GState& s, int is_int, int op, u64 rows) {
       u64 o = ~s.mnc;
       if (is_int) return (double)(long long)(o ^ GB_SIGN);                     // :531-543 (i64::MAX never stored: collapses to 0.0)
       double v = pdrs_unord_f64(o);
-      return v;                                                                // :649-661 (+INF never stored)
+      return v == __longlong_as_double(0x7FF0000000000000ll) ? 0.0 : v;        // :649-661 (min == +INF -> 0.0)
     }
     case PDRS_MAX: {
       if (s.mxo == 0) return 0.0;
       if (is_int) return (double)(long long)(s.mxo ^ GB_SIGN);                 // :544-556
-      return pdrs_unord_f64(s.mxo);                                            // :662-674
+      { double v = pdrs_unord_f64(s.mxo); return v == __longlong_as_double((long long)0xFFF0000000000000ull) ? 0.0 : v; }   // :662-674 (max == -INF -> 0.0)
     }
     case PDRS_STD: case PDRS_VAR: {                                            // :557-584 / :675-702 / :881-903
       if (s.n <= 1) return 0.0;
@@ -129,12 +129,16 @@ struct MergeParams {
 };
 template <int NW>
 __global__ void gb_merge_kernel(const MergeParams p) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i - lane < p.n; i += (long long)gridDim.x * blockDim.x) {
+    const bool inb = i < p.n;
     u64 w[NW];
-    bool knull = load_key_generic<NW>(p.ks, i, w);
-    long long gs = knull ? p.gt.slots : g_find_or_insert<NW>(p.gt, w);
-    if (gs < 0) continue;
-    if (knull && !(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL);
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = 0;
+    bool knull = inb ? load_key_generic<NW>(p.ks, i, w) : false;
+    long long gs = g_find_or_insert<NW>(p.gt, w, inb && !knull);
+    if (inb && knull) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
+    if (!inb || gs < 0) continue;
     for (int v = 0; v < p.nvals; v++) {
       const u64* q = p.states[v] + 8 * i;
       GTable t = p.gt;
@@ -143,7 +147,7 @@ __global__ void gb_merge_kernel(const MergeParams p) {
       g_update_batch<GB_ALL, true>(t, gs, v == 0 ? q[0] : 0ull, q[1], fin_pivot(q[2]), have_c,
                                    __longlong_as_double((long long)q[3]), __longlong_as_double((long long)q[4]), q[7], q[5], q[6]);
     }
-    if (p.nvals == 0) { /* keys only: nothing to add */ }
+    if (p.nvals == 0) { /* keys only */ }
   }
 }
 
@@ -342,6 +346,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
 
   // ---- cardinality estimate
   long long est = c->opts.groups_hint > 0 ? c->opts.groups_hint : 0;
+  bool dense_ok = false;
+  long long dense_base = 0, dense_range = 0;
   if (n > 0 && est == 0) {
     long long s_rows = std::min<long long>(n, std::max<long long>(4096, c->opt_sample_rows));
     long long nb = (s_rows + 255) / 256;
@@ -360,35 +366,43 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     else est = (long long)std::min<double>((double)n, invert_distinct(d, s) * 1.05 + 1.0);
     if (est < 1) est = 1;
     c->stats.est_groups = est;
+    if (variant == 0 && cn[CNT_KMINC]) {     // small dense integer keys: direct-mapped group ids, no key table
+      const long long kmin = (long long)(~cn[CNT_KMINC] ^ GB_SIGN), kmax = (long long)(cn[CNT_KMAX] ^ GB_SIGN);
+      const unsigned long long range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
+      if (range <= 60000ull && (long long)range <= 2 * est + 64) { dense_ok = true; dense_base = kmin; dense_range = (long long)range; }
+    }
   }
   if (est < 1) est = 1;
 
   // ---- geometry of the shared-memory kernel per pass; fall back to the global table when it does not fit
   auto shared_geometry = [&](const PassPlan& pp, GbParams* gp, GbCfg* cfg, size_t* smem) -> bool {
-    const int npl = pp.flags == GB_SUM ? 1 : (pp.is_int ? 4 : 3);
-    long long cap = est + std::max<long long>(est / 8, 16);
+    const int rec_bytes = (pp.flags == GB_SUM ? 8 : 16) + ((pp.flags == GB_ALL && pp.is_int) ? 8 : 0) + 8;
+    const int cta_bytes = pp.flags == GB_ALL ? 32 : 0;
+    const bool dense = variant == 0 && dense_ok && c->opt_dense != 0;
+    long long cap = dense ? dense_range + std::max<long long>(dense_range / 16, 8) : est + std::max<long long>(est / 16, 8);
     cap = (cap + 7) / 8 * 8;
     if (cap > 60000) return false;
-    long long S = std::max<long long>(64, pow2ceil(2 * cap));
-    const size_t fixed = gb_sh_fixed_bytes(ks.nwords, (int)S);
+    long long S = dense ? 0 : std::max<long long>(64, pow2ceil(cap + cap / 2));
+    const size_t fixed = gb_sh_fixed_bytes(ks.nwords, (int)S, (int)cap, cta_bytes, dense);
     const size_t budget = (size_t)c->smem_optin;
     int warps = c->opt_warps > 0 ? (int)std::min<int64_t>(c->opt_warps, GB_MAX_WARPS) : GB_MAX_WARPS;
     int ng = 0;
     for (;;) {
       for (int g = 32; g >= 1; g >>= 1) {
         if (c->opt_ng > 0 && g > c->opt_ng) continue;
-        if (fixed + (size_t)warps * gb_sh_warp_bytes(npl, (int)cap, g) <= budget) { ng = g; break; }
+        if (fixed + (size_t)warps * gb_sh_warp_bytes(rec_bytes, (int)cap, g) <= budget) { ng = g; break; }
       }
       if (ng || warps <= 4 || c->opt_warps > 0) break;
       warps--;
     }
     if (!ng) return false;
-    gp->sh_cap = (int)cap; gp->sh_slots = (int)S; gp->sh_log_slots = ilog2(S); gp->sh_ng = ng;
+    gp->sh_cap = (int)cap; gp->sh_slots = (int)S; gp->sh_log_slots = S ? ilog2(S) : 0; gp->sh_ng = ng;
+    gp->sh_dense = dense ? 1 : 0; gp->sh_dense_base = dense_base;
     cfg->warps = warps;
     cfg->ctas = c->sm_count * (c->opt_ctas_per_sm > 0 ? (int)c->opt_ctas_per_sm : 1);
     const long long units = (n + GB_UNIT_ROWS - 1) / GB_UNIT_ROWS;
     cfg->ctas = (int)std::max<long long>(1, std::min<long long>(cfg->ctas, (units + warps - 1) / warps));
-    *smem = fixed + (size_t)warps * gb_sh_warp_bytes(npl, (int)cap, ng);
+    *smem = fixed + (size_t)warps * gb_sh_warp_bytes(rec_bytes, (int)cap, ng);
     return true;
   };
 

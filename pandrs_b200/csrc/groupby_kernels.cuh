@@ -39,7 +39,7 @@ static constexpr u64 GB_CNT_MASK = GB_FULL - 1;
 static constexpr u64 GB_PIV_X = 0x7FF8C0DEC0DE0001ull;   // pivot bits are stored XOR this (0 = unset)
 static constexpr u64 GB_SIGN = 1ull << 63;
 
-enum { CNT_NGROUPS = 0, CNT_OVERFLOW = 1, CNT_SPILLED = 2, CNT_OUT = 3, CNT_SPIN_FAIL = 4, CNT_N = 8 };
+enum { CNT_NGROUPS = 0, CNT_OVERFLOW = 1, CNT_SPILLED = 2, CNT_OUT = 3, CNT_SPIN_FAIL = 4, CNT_KMINC = 5 /* ~(min key ^ SIGN) */, CNT_KMAX = 6 /* max key ^ SIGN */, CNT_N = 8 };
 
 struct KeyColDev {
   const void* data;
@@ -80,16 +80,34 @@ struct GbParams {
   int count_rows;                // this pass owns the group row counts
   int compat_nulls;              // filter present + compat_filter_nulls: NULL values count as 0 (data_ops.rs:64-71)
   int sh_cap, sh_slots, sh_log_slots, sh_ng;   // shared-memory kernel geometry
+  int sh_dense;                  // single I64 key: id = key - sh_dense_base when 0 <= id < sh_cap (no key table)
+  long long sh_dense_base;
 };
 
 // ---------------------------------------------------------------- small device helpers
-__device__ __forceinline__ u64 ld_cg_u64(const u64* p) { return __ldcg(p); }
-__device__ __forceinline__ ulonglong2 ld_cg_hdr(const GHdr* p) { return __ldcg(reinterpret_cast<const ulonglong2*>(p)); }
+// Loads of words that other threads publish (slot headers, keys, pivots): volatile, so that a spin on a
+// BUSY slot really re-reads memory (a plain __ldcg may legally be hoisted out of the retry loop).
+__device__ __forceinline__ u64 ld_cg_u64(const u64* p) {
+  u64 r;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ ulonglong2 ld_cg_hdr(const GHdr* p) {
+  ulonglong2 r;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+  return r;
+}
 
 // streaming 128-bit load that the compiler may not sink below the aggregation of the previous unit
 __device__ __forceinline__ ulonglong2 ld_stream_v2(const void* p) {
   ulonglong2 r;
   asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ ulonglong2 lds_volatile_v2(const void* p) {
+  ulonglong2 r;
+  asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
   return r;
 }
 
@@ -110,7 +128,7 @@ __device__ __forceinline__ u64 load_bits64(const uint8_t* bits, long long chunk)
 
 // Packs the key tuple of one row.  Returns true when the row belongs to the dedicated NULL group.
 template <int NW>
-__device__ __forceinline__ bool load_key_generic(const KeySpec& ks, long long row, u64 (&w)[NW]) {
+__device__ __noinline__ bool load_key_generic(const KeySpec& ks, long long row, u64 (&w)[NW]) {
 #pragma unroll
   for (int i = 0; i < NW; i++) w[i] = 0;
   for (int k = 0; k < ks.nkeys; k++) {
@@ -149,15 +167,18 @@ __device__ __forceinline__ bool load_key_generic(const KeySpec& ks, long long ro
 }
 
 // ---------------------------------------------------------------- global table
-// Returns the slot of the key (claiming a free one if INSERT), or -1 on overflow / not found.
-template <int NW, bool INSERT = true>
-__device__ __forceinline__ long long g_find_or_insert(const GTable& t, const u64 (&w)[NW]) {
-  u64 slot = (key_hash<NW>(w) >> 20) & t.mask;
-  int spins = 0;
-  for (u64 probe = 0; probe <= t.mask;) {
+// Slots are claimed with one CAS on the header word (0 -> BUSY), then the key words are written and the
+// header is published (FULL).  A thread that meets a BUSY slot must NOT spin on it: the publisher may be a
+// lane of the same warp, and a lane spinning inside a divergent loop can starve it.  So a probe attempt
+// returns G_RETRY instead, and the retry loop is warp-synchronous (every iteration reconverges at
+// __any_sync, which lets the publisher finish).  All 32 lanes of a warp must call g_find_or_insert together.
+static constexpr long long G_RETRY = -2;
+
+template <int NW>
+__device__ __forceinline__ long long g_try_insert(const GTable& t, const u64 (&w)[NW], u64& slot, u64& probe) {
+  while (probe <= t.mask) {
     ulonglong2 h = ld_cg_hdr(&t.hdr[slot]);
     if (h.y == 0) {
-      if (!INSERT) return -1;
       u64 old = atomicCAS(&t.hdr[slot].rowsw, 0ull, GB_BUSY);
       if (old == 0) {
         t.hdr[slot].key0 = w[0];
@@ -171,10 +192,7 @@ __device__ __forceinline__ long long g_find_or_insert(const GTable& t, const u64
       h.y = old;
       if (!(old & GB_BUSY)) h.x = ld_cg_u64(&t.hdr[slot].key0);
     }
-    if (h.y & GB_BUSY) {             // another thread is publishing this slot: look again
-      if (++spins > (1 << 22)) { atomicAdd(&t.counters[CNT_SPIN_FAIL], 1ull); return -1; }
-      continue;
-    }
+    if (h.y & GB_BUSY) return G_RETRY;     // somebody is publishing this slot: look again next round
     bool match = h.x == w[0];
     if (NW > 1) match = match && ld_cg_u64(&t.kw1[slot]) == w[1];
     if (NW > 2) match = match && ld_cg_u64(&t.kw2[slot]) == w[2];
@@ -182,8 +200,25 @@ __device__ __forceinline__ long long g_find_or_insert(const GTable& t, const u64
     slot = (slot + 1) & t.mask;
     probe++;
   }
-  if (INSERT) atomicAdd(&t.counters[CNT_OVERFLOW], 1ull);
+  atomicAdd(&t.counters[CNT_OVERFLOW], 1ull);
   return -1;
+}
+
+// Returns the slot of the key (claiming a free one if needed), or -1 on overflow / for inactive lanes.
+template <int NW>
+__device__ __forceinline__ long long g_find_or_insert(const GTable& t, const u64 (&w)[NW], bool active) {
+  u64 slot = (key_hash<NW>(w) >> 20) & t.mask, probe = 0;
+  long long res = -1;
+  bool pending = active;
+  int rounds = 0;
+  while (__any_sync(0xFFFFFFFFu, pending)) {
+    if (pending) {
+      long long r = g_try_insert<NW>(t, w, slot, probe);
+      if (r != G_RETRY) { res = r; pending = false; }
+    }
+    if (++rounds > (1 << 22)) { if (pending) atomicAdd(&t.counters[CNT_SPIN_FAIL], 1ull); break; }
+  }
+  return res;
 }
 
 // Global pivot of a group: first caller sets it, everybody gets the same value back.
@@ -277,26 +312,46 @@ __device__ __forceinline__ void g_update_batch(const GTable& t, long long slot, 
 }
 
 // ---------------------------------------------------------------- shared-memory layout
-// CTA-shared: key table u64[NW][S], id table u32[S] (0 = empty, SH_BUSY, else id + 1), misc u32[4].
-// Per warp: NPL planes of ulonglong2[E], E = (cap + 1) * ng  (+1: the NULL-key group).
-//   f64 SUM: P0 = {S1, cnt}            cnt = rows | n << 32
-//   i64 SUM: P0 = {isum, cnt}
-//   f64 ALL: P0 = {S1, S2}  P1 = {cnt, pivotx}  P2 = {min, max}
-//   i64 ALL: P0 = {S1, S2}  P1 = {cnt, pivotx}  P2 = {min, max}  P3 = {isum, -}
+// Measured on B200 (tools/microbench2.cu, profiles/microbench_r01.md): a random shared-memory access costs
+// ~2.6 SM-cycles per warp instruction per 4 bytes (LDS.32 2.6, LDS.64 5.0, LDS.128 9.3, same for STS),
+// a native 32-bit shared atomic costs the same 2.6, 64-bit / f64 shared atomics are CAS loops (18-31) and
+// MATCH.ANY costs 45.  The per-row shared-memory footprint is therefore kept minimal:
+//
+// CTA-shared   key table u64[NW][S] + id table u32[S] (0 = empty, SH_BUSY, else id + 1)   (not in dense mode)
+//              META[cap+1]  {pivot^tag, f32 min bound, f32 max bound}   read-mostly, one LDS.128 per row  (ALL)
+//              EXACT[cap+1] {~ord(min), ord(max)}                        touched only when a bound is beaten (ALL)
+//              misc u32[4]
+// per warp     ACC[E]  f64 {S1}, i64 {isum}                       (SUM)        E = (cap + 1) * ng
+//                      {S1, S2} (+ ISUM[E] for i64 values)        (ALL)
+//              CNT[E]  u32 rows: bumped with the native atomic; the returned ticket ranks the lanes of the
+//                      warp that hit the same record in this batch (re-read after __syncwarp gives the count)
+//              NUL[E]  u32 NULL values (n = rows - nulls)
+// S1 / S2 are plain LDS/STS read-modify-writes, one rank per round, so the per-row path has no 64-bit atomics.
 template <typename VT, int FLAGS> struct ShPlanes {
-  static constexpr int NPL = FLAGS == GB_SUM ? 1 : (ValTraits<VT>::is_int ? 4 : 3);
+  static constexpr bool IS_INT = ValTraits<VT>::is_int;
+  static constexpr int ACC_BYTES = FLAGS == GB_SUM ? 8 : 16;
+  static constexpr int REC_BYTES = ACC_BYTES + ((FLAGS == GB_ALL && IS_INT) ? 8 : 0) + 8;   // per warp per record
+  static constexpr int CTA_BYTES = FLAGS == GB_ALL ? 32 : 0;                                 // META + EXACT per group
 };
-__host__ __device__ inline size_t gb_sh_fixed_bytes(int nw, int slots) { return ((size_t)8 * nw * slots + (size_t)4 * slots + 16 + 15) / 16 * 16; }
-__host__ __device__ inline size_t gb_sh_warp_bytes(int npl, int cap, int ng) { return (size_t)npl * 16 * (size_t)(cap + 1) * ng; }
+__host__ __device__ inline size_t gb_sh_fixed_bytes(int nw, int slots, int cap, int cta_bytes, int dense) {
+  size_t b = dense ? 0 : ((size_t)8 * nw * slots + (size_t)4 * slots);
+  b = (b + 15) / 16 * 16;
+  b += (size_t)cta_bytes * (cap + 1);
+  return b + 16;
+}
+__host__ __device__ inline size_t gb_sh_warp_bytes(int rec_bytes, int cap, int ng) {
+  const size_t E = (size_t)(cap + 1) * ng;
+  return ((size_t)rec_bytes * E + 15) / 16 * 16;
+}
 
 static constexpr uint32_t SH_BUSY = 0xFFFFFFFFu;
 
-// key -> dense id through the CTA-shared key table; -1 = table full (spill)
+// key -> dense id through the CTA-shared key table; -1 = table full (spill).  Same no-spin protocol as the
+// global table: all 32 lanes of a warp call sh_lookup together.
+static constexpr int SH_RETRY = -2;
 template <int NW>
-__device__ __forceinline__ int sh_lookup(u64* ktab_key, uint32_t* ktab_id, uint32_t* misc, int S, int log_slots, int cap, const u64 (&w)[NW]) {
-  uint32_t slot = (uint32_t)(key_hash<NW>(w) >> (64 - log_slots));
-  int spins = 0;
-  for (int probe = 0; probe < S;) {
+__device__ __forceinline__ int sh_try(u64* ktab_key, uint32_t* ktab_id, uint32_t* misc, int S, int cap, const u64 (&w)[NW], uint32_t& slot, int& probe) {
+  while (probe < S) {
     // id first, key second (the publisher writes key -> fence -> id), both loads in flight together
     uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
     u64 kk[NW];
@@ -317,9 +372,9 @@ __device__ __forceinline__ int sh_lookup(u64* ktab_key, uint32_t* ktab_id, uint3
         *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]) = nid + 1;
         return (int)nid;
       }
-      idw = SH_BUSY;   // lost the race: the winner is publishing, look again
+      return SH_RETRY;   // lost the race: the winner is publishing (or gave the slot back), look again
     }
-    if (idw == SH_BUSY) { if (++spins > (1 << 20)) return -1; continue; }
+    if (idw == SH_BUSY) return SH_RETRY;
     bool match = true;
 #pragma unroll
     for (int i = 0; i < NW; i++) match = match && (kk[i] == w[i]);
@@ -329,12 +384,27 @@ __device__ __forceinline__ int sh_lookup(u64* ktab_key, uint32_t* ktab_id, uint3
   }
   return -1;
 }
+template <int NW>
+__device__ __noinline__ int sh_lookup(u64* ktab_key, uint32_t* ktab_id, uint32_t* misc, int S, int log_slots, int cap, const u64 (&w)[NW], bool active) {
+  uint32_t slot = (uint32_t)(key_hash<NW>(w) >> (64 - log_slots));
+  int probe = 0, res = -1, rounds = 0;
+  bool pending = active;
+  while (__any_sync(0xFFFFFFFFu, pending)) {
+    if (pending) {
+      int r = sh_try<NW>(ktab_key, ktab_id, misc, S, cap, w, slot, probe);
+      if (r != SH_RETRY) { res = r; pending = false; }
+    }
+    if (++rounds > (1 << 20)) break;   // res stays -1: the row spills
+  }
+  return res;
+}
 
 // One unit of a warp: 512 rows, lane owns rows base + 64*j + 2*lane + {0,1}, j = 0..7.
+// fl[j / 4] holds, 6 bits per j: {active(2), NULL value(2), NULL key(2)} of this lane's two rows.
 template <typename VT> struct GbUnit {
-  u64 k[GB_R];     // KM == 0 only: the 64-bit key column
+  u64 k[GB_R];     // KM != 1 only: the 64-bit key column
   u64 v[GB_R];     // value bits
-  u64 act[GB_R / 2], vn[GB_R / 2], kn[GB_R / 2];   // per 64-row chunk: active rows, NULL values, NULL keys
+  uint32_t fl[2];
 };
 
 template <int KM, typename VT>
@@ -347,15 +417,16 @@ __device__ __forceinline__ void gb_load_unit(const GbParams& p, long long base, 
     const long long r0 = base + 64 * j + 2 * lane;
     ulonglong2 kk = make_ulonglong2(0, 0), vv = make_ulonglong2(0, 0);
     if (r0 + 1 < n) {
-      if (KM == 0) kk = ld_stream_v2(keys + 8 * r0);
+      if (KM != 1) kk = ld_stream_v2(keys + 8 * r0);
       if (vals) vv = ld_stream_v2(vals + 8 * r0);
     } else if (r0 < n) {
-      if (KM == 0) kk.x = __ldg(reinterpret_cast<const u64*>(keys) + r0);
+      if (KM != 1) kk.x = __ldg(reinterpret_cast<const u64*>(keys) + r0);
       if (vals) vv.x = __ldg(reinterpret_cast<const u64*>(vals) + r0);
     }
     u.k[2 * j] = kk.x; u.k[2 * j + 1] = kk.y;
     u.v[2 * j] = vv.x; u.v[2 * j + 1] = vv.y;
   }
+  u.fl[0] = u.fl[1] = 0;
 #pragma unroll
   for (int j = 0; j < GB_R / 2; j++) {
     const long long c0 = base + 64 * j;
@@ -368,199 +439,286 @@ __device__ __forceinline__ void gb_load_unit(const GbParams& p, long long base, 
         if (p.fnull) m &= ~load_bits64(p.fnull, chunk);
       }
       if (p.vnull) vn = load_bits64(p.vnull, chunk);
-      if (KM == 0 && p.ks.c[0].nulls) kn = load_bits64(p.ks.c[0].nulls, chunk);
+      if (KM != 1 && p.ks.c[0].nulls) kn = load_bits64(p.ks.c[0].nulls, chunk);
     }
     if (!vals) vn = ~0ull;
-    u.act[j] = m; u.vn[j] = vn; u.kn[j] = kn;
+    const uint32_t a2 = (uint32_t)(m >> (2 * lane)) & 3u, v2 = (uint32_t)(vn >> (2 * lane)) & 3u, k2 = (uint32_t)(kn >> (2 * lane)) & 3u;
+    u.fl[j >> 2] |= (a2 | (v2 << 2) | (k2 << 4)) << (6 * (j & 3));
+  }
+  if (p.compat_nulls && vals) {   // filter + compat_filter_nulls: NULL values count as 0 (data_ops.rs:64-71)
+#pragma unroll
+    for (int jj = 0; jj < GB_R; jj++) {
+      const uint32_t bit = 1u << (6 * ((jj >> 1) & 3) + 2 + (jj & 1));
+      if (u.fl[jj >> 3] & bit) { u.fl[jj >> 3] &= ~bit; u.v[jj] = 0; }
+    }
   }
 }
 
 // ---------------------------------------------------------------- the shared-memory kernel
-template <int NW, int KM /*0: one 64-bit key column, direct loads; 1: generic packing*/, typename VT, int FLAGS>
+// Rare paths live in __noinline__ functions so that the unrolled hot loop stays inside the instruction cache.
+template <int NW, typename VT, int FLAGS>
+__device__ __noinline__ void gb_spill_rows(const GTable gt, u64 w0, u64 w1, u64 w2, bool spill, bool count_row, bool valid, VT v) {
+  u64 w[NW];
+  w[0] = w0;
+  if (NW > 1) w[1] = w1;
+  if (NW > 2) w[2] = w2;
+  long long gs = g_find_or_insert<NW>(gt, w, spill);
+  if (spill && gs >= 0) g_update_row<VT, FLAGS>(gt, gs, count_row, valid, v);
+  if (spill) atomicAdd(&gt.counters[CNT_SPILLED], 1ull);
+}
+
+// A value beat the f32 bound of its group: update the exact minimum / maximum (64-bit shared atomicMax is a
+// CAS loop, but this runs O(log rows) times per group) and tighten the bound.
+template <typename VT>
+__device__ __noinline__ void gb_minmax_slow(ulonglong2* META, ulonglong2* EXACT, int id, VT v, bool lo, bool hi) {
+  using T = ValTraits<VT>;
+  if (!T::orderable(v)) return;
+  if (lo) {
+    const u64 o = ~T::ord(v);
+    const u64 was = atomicMax(&EXACT[id].x, o);
+    const u64 best = ~(was > o ? was : o);     // ord() of the current exact minimum
+    float b;
+    if (T::is_int) b = __ll2float_rn((long long)(best ^ GB_SIGN)); else b = __double2float_rn(pdrs_unord_f64(best));
+    reinterpret_cast<volatile uint32_t*>(&META[id].y)[0] = __float_as_uint(b);   // bound = rn(some earlier exact min) >= rn(exact min)
+  }
+  if (hi) {
+    const u64 o = T::ord(v);
+    const u64 was = atomicMax(&EXACT[id].y, o);
+    const u64 best = was > o ? was : o;
+    float b;
+    if (T::is_int) b = __ll2float_rn((long long)(best ^ GB_SIGN)); else b = __double2float_rn(pdrs_unord_f64(best));
+    reinterpret_cast<volatile uint32_t*>(&META[id].y)[1] = __float_as_uint(b);   // bound = rn(some earlier exact max) <= rn(exact max)
+  }
+}
+
+static __device__ __noinline__ u64 gb_pivot_set(ulonglong2* META, int id, double x) {
+  const u64 mine = (u64)__double_as_longlong(x) ^ GB_PIV_X;
+  const u64 was = atomicCAS(&META[id].x, 0ull, mine);
+  return was ? was : mine;
+}
+
+#define GB_Q 4   // batches (of 32 rows) that share one ticket phase
+
+// KM: 0 = one 64-bit key column through the CTA-shared key table, 1 = generic packed key tuple,
+//     2 = one 64-bit key column with small dense integer keys (direct-mapped group ids, no key table)
+template <int NW, int KM, typename VT, int FLAGS>
 __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const GbParams p) {
   using T = ValTraits<VT>;
-  constexpr int NPL = ShPlanes<VT, FLAGS>::NPL;
+  using L = ShPlanes<VT, FLAGS>;
   constexpr bool IS_INT = T::is_int;
+  constexpr bool ALL = FLAGS == GB_ALL;
+  constexpr bool dense = KM == 2;
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.sh_slots, cap = p.sh_cap, NG = p.sh_ng;
   const int E = (cap + 1) * NG;
   u64* ktab_key = reinterpret_cast<u64*>(smem);
   uint32_t* ktab_id = reinterpret_cast<uint32_t*>(smem + (size_t)8 * NW * S);
-  uint32_t* misc = ktab_id + S;   // [0] = number of groups in this CTA, [1] = NULL group seen
-  const size_t fixed = gb_sh_fixed_bytes(NW, S);
-  const size_t warp_bytes = gb_sh_warp_bytes(NPL, cap, NG);
+  const size_t keys_bytes = dense ? 0 : (((size_t)8 * NW * S + (size_t)4 * S + 15) / 16 * 16);
+  ulonglong2* META = reinterpret_cast<ulonglong2*>(smem + keys_bytes);                 // ALL only
+  ulonglong2* EXACT = META + (cap + 1);                                               // ALL only
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + keys_bytes + (size_t)L::CTA_BYTES * (cap + 1));   // [0] groups in this CTA, [1] NULL group seen
+  const size_t fixed = gb_sh_fixed_bytes(NW, S, cap, L::CTA_BYTES, dense);
+  const size_t warp_bytes = gb_sh_warp_bytes(L::REC_BYTES, cap, NG);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  ulonglong2* P0 = reinterpret_cast<ulonglong2*>(smem + fixed + (size_t)warp * warp_bytes);
-  ulonglong2* P1 = P0 + E;
-  ulonglong2* P2 = P1 + E;
-  ulonglong2* P3 = P2 + E;
+  unsigned char* wbase = smem + fixed + (size_t)warp * warp_bytes;
+  // per-warp arrays: ACC (8 or 16 B), [ISUM 8 B], CNT u32, NUL u32
+  u64* ACC1 = reinterpret_cast<u64*>(wbase);                 // SUM: one 8-byte word per record
+  ulonglong2* ACC2 = reinterpret_cast<ulonglong2*>(wbase);   // ALL: {S1, S2}
+  u64* ISUM = reinterpret_cast<u64*>(wbase + (size_t)L::ACC_BYTES * E);
+  uint32_t* CNT = reinterpret_cast<uint32_t*>(wbase + (size_t)(L::REC_BYTES - 8) * E);
+  uint32_t* NUL = CNT + E;
 
   // ---- init
-  for (int i = threadIdx.x; i < S; i += blockDim.x) ktab_id[i] = 0;
+  if (!dense) for (int i = threadIdx.x; i < S; i += blockDim.x) ktab_id[i] = 0;
   if (threadIdx.x < 4) misc[threadIdx.x] = 0;
-  for (int e = lane; e < E; e += 32) {
-    P0[e] = make_ulonglong2(0, 0);
-    if (FLAGS == GB_ALL) {
-      P1[e] = make_ulonglong2(0, 0);
-      P2[e] = make_ulonglong2(T::to_bits(T::min_init()), T::to_bits(T::max_init()));
-      if (IS_INT) P3[e] = make_ulonglong2(0, 0);
+  if (ALL) {
+    const float inf = __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i <= cap; i += blockDim.x) {
+      META[i] = make_ulonglong2(0ull, ((u64)__float_as_uint(-inf) << 32) | (u64)__float_as_uint(inf));   // .y = {lo: min bound, hi: max bound}
+      EXACT[i] = make_ulonglong2(0ull, 0ull);
     }
   }
+  for (size_t i = lane; i < warp_bytes / 8; i += 32) reinterpret_cast<u64*>(wbase)[i] = 0;
   __syncthreads();
 
   const long long n = p.n;
   const long long total_units = (n + GB_UNIT_ROWS - 1) / GB_UNIT_ROWS;
   const long long gwarp = (long long)blockIdx.x * nwarps + warp, total_warps = (long long)gridDim.x * nwarps;
   const int rep = lane & (NG - 1);
-  const bool lane_private = NG == 32;
-  const unsigned lt_mask = (1u << lane) - 1u;
+  const u64 dense_base = (u64)p.sh_dense_base;
+  const bool count_rows = p.count_rows != 0;
 
-  GbUnit<VT> cur, nxt;
-  if (gwarp < total_units) gb_load_unit<KM, VT>(p, gwarp * GB_UNIT_ROWS, lane, cur);
+  // The aggregation (shared-memory bound, >1 cycle per row per SM) dominates a unit by far, so the loads of a
+  // unit are not double-buffered through registers; the next unit of this warp is pulled into L2 instead.
+  GbUnit<VT> cur;
   for (long long u = gwarp; u < total_units; u += total_warps) {
     const long long base = u * GB_UNIT_ROWS;
-    if (u + total_warps < total_units) gb_load_unit<KM, VT>(p, (u + total_warps) * GB_UNIT_ROWS, lane, nxt);
-
-#pragma unroll
-    for (int jj = 0; jj < GB_R; jj++) {
-      const int j = jj >> 1, h = jj & 1;
-      const int bitpos = 2 * lane + h;
-      const long long row = base + 64 * j + bitpos;
-      const bool active = (cur.act[j] >> bitpos) & 1;
-      bool valid = active && !((cur.vn[j] >> bitpos) & 1);
-      VT v = T::from_bits(cur.v[jj]);
-      if (p.compat_nulls && active && p.val && !valid) { valid = true; v = VT(0); }
-      u64 w[NW];
-      bool knull = false;
-      if (KM == 0) {
-        w[0] = cur.k[jj];
-        knull = (cur.kn[j] >> bitpos) & 1;
-      } else if (active) {
-        knull = load_key_generic<NW>(p.ks, row, w);
-      }
-      // -- key -> dense id through the CTA-shared key table
-      int id = -1;
-      if (active) {
-        if (knull) { id = cap; if (!*reinterpret_cast<volatile uint32_t*>(&misc[1])) *reinterpret_cast<volatile uint32_t*>(&misc[1]) = 1u; }
-        else {
-          id = sh_lookup<NW>(ktab_key, ktab_id, misc, S, p.sh_log_slots, cap, w);
-          if (id < 0) {   // rare: the key does not fit this CTA's table
-            long long gs = g_find_or_insert<NW>(p.gt, w);
-            if (gs >= 0) g_update_row<VT, FLAGS>(p.gt, gs, p.count_rows != 0, valid, v);
-            atomicAdd(&p.gt.counters[CNT_SPILLED], 1ull);
-          }
-        }
-      }
-      // -- plain read-modify-write of this warp's records; lanes of the warp that hit the same record
-      //    take turns by rank
-      const int e = id >= 0 ? id * NG + rep : -(1 + lane);
-      int rank = 0, maxr = 0;
-      if (!lane_private) {
-        unsigned peers = __match_any_sync(0xFFFFFFFFu, e);
-        rank = __popc(peers & lt_mask);
-        maxr = __reduce_max_sync(0xFFFFFFFFu, id >= 0 ? rank : 0);
-      }
-      const double x = T::to_f64(v);
-      for (int r = 0; r <= maxr; r++) {
-        if (id >= 0 && rank == r) {
-          if (FLAGS == GB_SUM) {
-            ulonglong2 a = P0[e];
-            a.y += 1ull + (valid ? (1ull << 32) : 0ull);
-            if (valid) {
-              if (IS_INT) a.x += (u64)T::to_bits(v);
-              else a.x = (u64)__double_as_longlong(__longlong_as_double((long long)a.x) + x);
-            }
-            P0[e] = a;
-          } else {
-            ulonglong2 b = P1[e];
-            b.x += 1ull + (valid ? (1ull << 32) : 0ull);
-            if (valid) {
-              ulonglong2 a = P0[e], m = P2[e];
-              const bool unset = b.y == 0;
-              const bool fin = is_finite_f64(x);
-              if (unset && fin) b.y = (u64)__double_as_longlong(x) ^ GB_PIV_X;
-              const double piv = b.y ? __longlong_as_double((long long)(b.y ^ GB_PIV_X)) : 0.0;
-              const double d = x - piv;
-              a.x = (u64)__double_as_longlong(__longlong_as_double((long long)a.x) + d);
-              a.y = (u64)__double_as_longlong(__longlong_as_double((long long)a.y) + d * d);
-              P0[e] = a;
-              const VT mn = T::from_bits(m.x), mx = T::from_bits(m.y);
-              if (v < mn || v > mx) {
-                if (v < mn) m.x = T::to_bits(v);
-                if (v > mx) m.y = T::to_bits(v);
-                P2[e] = m;
-              }
-              if (IS_INT) { ulonglong2 s = P3[e]; s.x += (u64)T::to_bits(v); P3[e] = s; }
-            }
-            P1[e] = b;
-          }
-        }
-        if (!lane_private) __syncwarp();
+    gb_load_unit<KM, VT>(p, base, lane, cur);
+    if (u + total_warps < total_units) {
+      const long long nb = (u + total_warps) * GB_UNIT_ROWS + 16 * lane;   // 32 lanes x 128 B = one unit of an 8-byte column
+      if (nb < n) {
+        if (KM != 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p.ks.c[0].data) + 8 * nb));
+        if (p.val) asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p.val) + 8 * nb));
       }
     }
-    cur = nxt;
+
+#pragma unroll
+    for (int g0 = 0; g0 < GB_R; g0 += GB_Q) {
+      int eidx[GB_Q];          // record index of the row, -1: nothing to add to the sums
+      int rr[GB_Q];
+      VT vv[GB_Q];
+      double dd[GB_Q];
+      uint32_t old[GB_Q];
+      u64 wsp[GB_Q][NW];
+      uint32_t spillmask = 0;
+      // -- phase 1: key -> record, bump the row counters (tickets), pivot / min / max
+#pragma unroll
+      for (int q = 0; q < GB_Q; q++) {
+        const int jj = g0 + q;
+        const uint32_t fl = cur.fl[jj >> 3];
+        constexpr int dummy = 0; (void)dummy;
+        const int sh = 6 * ((jj >> 1) & 3) + (jj & 1);
+        const bool active = (fl >> sh) & 1u;
+        const bool valid = active && !((fl >> (sh + 2)) & 1u);
+        bool knull = (fl >> (sh + 4)) & 1u;
+        const VT v = T::from_bits(cur.v[jj]);
+        u64 w[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = 0;
+        if (KM != 1) w[0] = cur.k[jj];
+        else if (active) knull = load_key_generic<NW>(p.ks, base + 64 * (jj >> 1) + 2 * lane + (jj & 1), w);
+        int id = -1;
+        if (dense) {                       // small dense integer keys: direct-mapped
+          const u64 off = w[0] - dense_base;
+          if (active && off < (u64)cap) id = (int)off;
+        } else {                           // CTA-shared key table
+          id = sh_lookup<NW>(ktab_key, ktab_id, misc, S, p.sh_log_slots, cap, w, active && !knull);
+        }
+        if (active && knull) { id = cap; if (!*reinterpret_cast<volatile uint32_t*>(&misc[1])) *reinterpret_cast<volatile uint32_t*>(&misc[1]) = 1u; }
+        if (active && id < 0) spillmask |= 1u << q;
+#pragma unroll
+        for (int i = 0; i < NW; i++) wsp[q][i] = w[i];
+        const int e = id * NG + rep;
+        old[q] = 0;
+        if (id >= 0) {
+          old[q] = atomicAdd(&CNT[e], 1u);
+          if (!valid) atomicAdd(&NUL[e], 1u);
+        }
+        const bool upd = id >= 0 && valid;
+        eidx[q] = upd ? e : -1;
+        vv[q] = v;
+        double x = T::to_f64(v);
+        dd[q] = x;
+        if (ALL && upd) {                  // pivot and min / max bounds: CTA-shared, read-mostly, one LDS.128
+          const ulonglong2 meta = lds_volatile_v2(&META[id]);
+          u64 px = meta.x;
+          if (px == 0 && is_finite_f64(x)) px = gb_pivot_set(META, id, x);   // first finite value of the group in this CTA
+          dd[q] = x - (px ? __longlong_as_double((long long)(px ^ GB_PIV_X)) : 0.0);
+          // f32 bounds hold round-to-nearest(exact min / max); rounding is monotonic, so a value below the exact
+          // minimum always satisfies xf <= bound (values equal to the bound after rounding take the slow path too)
+          const float xf = IS_INT ? __ll2float_rn((long long)T::to_bits(v)) : __double2float_rn(x);
+          const bool lo = xf <= __uint_as_float((uint32_t)meta.y), hi = xf >= __uint_as_float((uint32_t)(meta.y >> 32));
+          if (lo || hi) gb_minmax_slow<VT>(META, EXACT, id, v, lo, hi);
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, spillmask != 0)) {   // rare: keys that do not fit this CTA's table go to the global table
+#pragma unroll
+        for (int q = 0; q < GB_Q; q++) {
+          const int jj = g0 + q;
+          const bool valid = !((cur.fl[jj >> 3] >> (6 * ((jj >> 1) & 3) + (jj & 1) + 2)) & 1u);
+          gb_spill_rows<NW, VT, FLAGS>(p.gt, wsp[q][0], NW > 1 ? wsp[q][NW > 1 ? 1 : 0] : 0ull, NW > 2 ? wsp[q][NW > 2 ? 2 : 0] : 0ull,
+                                       (spillmask >> q) & 1u, count_rows, valid, vv[q]);
+        }
+      }
+      // -- phase 2: ranks from the tickets (unique per record across the whole group of GB_Q batches)
+      __syncwarp();
+      int mr = 0;
+#pragma unroll
+      for (int q = 0; q < GB_Q; q++) {
+        rr[q] = -1;
+        if (eidx[q] >= 0) { rr[q] = (int)(*reinterpret_cast<volatile uint32_t*>(&CNT[eidx[q]]) - old[q] - 1u); mr = max(mr, rr[q]); }
+      }
+      const int maxr = __reduce_max_sync(0xFFFFFFFFu, mr);
+      // -- phase 3: plain read-modify-write of this warp's sums, one rank per round
+      for (int r = 0; r <= maxr; r++) {
+        if (!ALL) {
+          u64 a[GB_Q];
+#pragma unroll
+          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) a[q] = ACC1[eidx[q]];
+#pragma unroll
+          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) {
+            if (IS_INT) a[q] += (u64)T::to_bits(vv[q]);
+            else a[q] = (u64)__double_as_longlong(__longlong_as_double((long long)a[q]) + dd[q]);
+            ACC1[eidx[q]] = a[q];
+          }
+        } else {
+          ulonglong2 a[GB_Q];
+#pragma unroll
+          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) a[q] = ACC2[eidx[q]];
+#pragma unroll
+          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) {
+            a[q].x = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].x) + dd[q]);
+            a[q].y = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].y) + dd[q] * dd[q]);
+            ACC2[eidx[q]] = a[q];
+            if (IS_INT) ISUM[eidx[q]] += (u64)T::to_bits(vv[q]);
+          }
+        }
+        __syncwarp();
+      }
+    }
   }
   __syncthreads();
 
   // ---- flush: reduce the warps' private records per group, then one batch update per (CTA, group)
-  for (int s = threadIdx.x; s <= S; s += blockDim.x) {
-    int id;
-    if (s == S) { if (!misc[1]) continue; id = cap; }
-    else { uint32_t idw = ktab_id[s]; if (idw == 0 || idw == SH_BUSY) continue; id = (int)idw - 1; }
-    u64 rows = 0, nv = 0, isum = 0;
-    double S1 = 0.0, S2 = 0.0, c = 0.0;
-    bool have_c = false;
-    VT mn = T::min_init(), mx = T::max_init();
+  const int nid = dense ? cap : S;
+  for (int s0 = 0; s0 <= nid; s0 += blockDim.x) {     // warp-uniform trip count (g_find_or_insert is warp-synchronous)
+    const int s = s0 + threadIdx.x;
+    int id = -1;
+    if (s == nid) { if (misc[1]) id = cap; }
+    else if (s < nid) {
+      if (dense) id = s;
+      else { uint32_t idw = ktab_id[s]; if (idw != 0 && idw != SH_BUSY) id = (int)idw - 1; }
+    }
+    bool have = id >= 0;
+    if (!have) id = 0;
+    u64 rows = 0, nulls = 0, isum = 0;
+    double S1 = 0.0, S2 = 0.0;
     for (int wq = 0; wq < nwarps; wq++) {
-      const ulonglong2* Q0 = reinterpret_cast<const ulonglong2*>(smem + fixed + (size_t)wq * warp_bytes);
+      const unsigned char* qb = smem + fixed + (size_t)wq * warp_bytes;
+      const uint32_t* QC = reinterpret_cast<const uint32_t*>(qb + (size_t)(L::REC_BYTES - 8) * E);
       for (int r = 0; r < NG; r++) {
         const int e = id * NG + r;
-        if (FLAGS == GB_SUM) {
-          ulonglong2 a = Q0[e];
-          rows += a.y & 0xFFFFFFFFull; nv += a.y >> 32;
-          if (IS_INT) isum += a.x; else S1 += __longlong_as_double((long long)a.x);
+        rows += QC[e];
+        nulls += QC[E + e];
+        if (!ALL) {
+          const u64 a = reinterpret_cast<const u64*>(qb)[e];
+          if (IS_INT) isum += a; else S1 += __longlong_as_double((long long)a);
         } else {
-          ulonglong2 a = Q0[e], b = Q0[E + e], m = Q0[2 * E + e];
-          const u64 n2 = b.x >> 32;
-          rows += b.x & 0xFFFFFFFFull;
-          if (n2) {
-            const double s1 = __longlong_as_double((long long)a.x), s2 = __longlong_as_double((long long)a.y);
-            const bool hc2 = b.y != 0;
-            const double c2 = hc2 ? __longlong_as_double((long long)(b.y ^ GB_PIV_X)) : 0.0;
-            if (!have_c && hc2) {    // adopt the pivot; what was accumulated so far had pivot 0 (non-finite values only)
-              const double dl = 0.0 - c2, nn = (double)nv;
-              S2 = S2 + 2.0 * dl * S1 + nn * dl * dl; S1 = S1 + nn * dl;
-              c = c2; have_c = true;
-            }
-            const double dl = (hc2 ? c2 : 0.0) - c, nn = (double)n2;
-            S1 += s1 + nn * dl;
-            S2 += s2 + 2.0 * dl * s1 + nn * dl * dl;
-            nv += n2;
-            const VT t0 = T::from_bits(m.x), t1 = T::from_bits(m.y);
-            if (t0 < mn) mn = t0;
-            if (t1 > mx) mx = t1;
-            if (IS_INT) isum += Q0[3 * E + e].x;
-          }
+          const ulonglong2 a = reinterpret_cast<const ulonglong2*>(qb)[e];
+          S1 += __longlong_as_double((long long)a.x);
+          S2 += __longlong_as_double((long long)a.y);
+          if (IS_INT) isum += reinterpret_cast<const u64*>(qb + (size_t)16 * E)[e];
         }
       }
     }
-    long long gs;
-    if (id == cap) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
-    else {
-      u64 w[NW];
+    if (have && rows == 0) have = false;       // dense mode: ids nobody hit
+    u64 w[NW];
 #pragma unroll
-      for (int i = 0; i < NW; i++) w[i] = ktab_key[i * S + s];
-      gs = g_find_or_insert<NW>(p.gt, w);
+    for (int i = 0; i < NW; i++) w[i] = 0;
+    if (have && id != cap) {
+      if (dense) w[0] = dense_base + (u64)id;
+      else {
+#pragma unroll
+        for (int i = 0; i < NW; i++) w[i] = ktab_key[i * S + s];
+      }
     }
-    if (gs < 0) continue;
-    u64 mnc = 0, mxo = 0;
-    if (FLAGS == GB_ALL) {
-      if (T::orderable(mn) && mn != T::min_init()) mnc = ~T::ord(mn);
-      if (T::orderable(mx) && mx != T::max_init()) mxo = T::ord(mx);
-    }
-    if (rows && !p.count_rows) rows = 0;
-    if (rows) atomicAdd(&p.gt.hdr[gs].rowsw, rows);
-    g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, nv, c, have_c, S1, S2, isum, mnc, mxo);
+    long long gs = g_find_or_insert<NW>(p.gt, w, have && id != cap);
+    if (have && id == cap) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
+    if (!have || gs < 0) continue;
+    u64 mnc = 0, mxo = 0, px = 0;
+    if (ALL) { px = META[id].x; mnc = EXACT[id].x; mxo = EXACT[id].y; }
+    if (p.count_rows) atomicAdd(&p.gt.hdr[gs].rowsw, rows);
+    g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, rows - nulls, px ? __longlong_as_double((long long)(px ^ GB_PIV_X)) : 0.0, px != 0, S1, S2, isum, mnc, mxo);
   }
 }
 
@@ -574,7 +732,9 @@ __global__ void __launch_bounds__(256) gb_global_kernel(const GbParams p) {
   const long long* __restrict__ keys64 = reinterpret_cast<const long long*>(p.ks.c[0].data);
   const uint8_t* knull0 = p.ks.c[0].nulls;
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += stride * R) {
+  const int lane = threadIdx.x & 31;
+  // warp-uniform loop bounds: g_find_or_insert is warp-synchronous
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 - lane < n; i0 += stride * R) {
     u64 k0[R];
     VT v[R];
 #pragma unroll
@@ -587,21 +747,25 @@ __global__ void __launch_bounds__(256) gb_global_kernel(const GbParams p) {
 #pragma unroll
     for (int j = 0; j < R; j++) {
       long long row = i0 + j * stride;
-      if (row >= n) continue;
-      if (p.fbits) {
-        if (!pdrs_bit(p.fbits, row)) continue;
-        if (p.fnull && pdrs_bit(p.fnull, row)) continue;
+      bool active = row < n;
+      if (active && p.fbits) {
+        if (!pdrs_bit(p.fbits, row)) active = false;
+        else if (p.fnull && pdrs_bit(p.fnull, row)) active = false;
       }
-      bool valid = vals && !(p.vnull && pdrs_bit(p.vnull, row));
+      bool valid = active && vals && !(p.vnull && pdrs_bit(p.vnull, row));
       VT vv = v[j];
-      if (p.compat_nulls && vals && !valid) { valid = true; vv = VT(0); }
+      if (p.compat_nulls && active && vals && !valid) { valid = true; vv = VT(0); }
       u64 w[NW];
+#pragma unroll
+      for (int i = 0; i < NW; i++) w[i] = 0;
       bool knull = false;
-      if (KM == 0) { w[0] = k0[j]; if (knull0) knull = pdrs_bit(knull0, row); }
-      else knull = load_key_generic<NW>(p.ks, row, w);
-      long long gs = knull ? p.gt.slots : g_find_or_insert<NW>(p.gt, w);
-      if (knull && !(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL);
-      if (gs >= 0) g_update_row<VT, FLAGS>(p.gt, gs, p.count_rows != 0, valid, vv);
+      if (active) {
+        if (KM == 0) { w[0] = k0[j]; if (knull0) knull = pdrs_bit(knull0, row); }
+        else knull = load_key_generic<NW>(p.ks, row, w);
+      }
+      long long gs = g_find_or_insert<NW>(p.gt, w, active && !knull);
+      if (active && knull) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
+      if (active && gs >= 0) g_update_row<VT, FLAGS>(p.gt, gs, p.count_rows != 0, valid, vv);
     }
   }
   (void)sizeof(T);
@@ -612,14 +776,24 @@ __global__ void __launch_bounds__(256) gb_global_kernel(const GbParams p) {
 // holds the number of distinct sampled keys.
 template <int NW, int KM>
 __global__ void gb_sample_kernel(const GbParams p, long long nblocks, long long block_stride_rows) {
+  u64 kmax = 0, kminc = 0;
   for (long long b = blockIdx.x; b < nblocks; b += gridDim.x) {
     long long row = b * block_stride_rows + threadIdx.x;
-    if (row >= p.n) continue;
+    const bool inb = row < p.n;
     u64 w[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = 0;
     bool knull = false;
-    if (KM == 0) { w[0] = (u64)__ldg(reinterpret_cast<const long long*>(p.ks.c[0].data) + row); knull = p.ks.c[0].nulls && pdrs_bit(p.ks.c[0].nulls, row); }
-    else knull = load_key_generic<NW>(p.ks, row, w);
-    if (!knull) g_find_or_insert<NW>(p.gt, w);
+    if (inb) {
+      if (KM == 0) { w[0] = (u64)__ldg(reinterpret_cast<const long long*>(p.ks.c[0].data) + row); knull = p.ks.c[0].nulls && pdrs_bit(p.ks.c[0].nulls, row); }
+      else knull = load_key_generic<NW>(p.ks, row, w);
+    }
+    if (KM == 0 && inb && !knull) { const u64 o = w[0] ^ GB_SIGN; kmax = max(kmax, o); kminc = max(kminc, ~o); }
+    g_find_or_insert<NW>(p.gt, w, inb && !knull);
+  }
+  if (KM == 0) {   // range of the sampled keys (dense-key fast path)
+    for (int d = 16; d; d >>= 1) { kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d)); kminc = max(kminc, __shfl_xor_sync(0xFFFFFFFFu, kminc, d)); }
+    if ((threadIdx.x & 31) == 0 && kminc) { atomicMax(&p.gt.counters[CNT_KMAX], kmax); atomicMax(&p.gt.counters[CNT_KMINC], kminc); }
   }
 }
 

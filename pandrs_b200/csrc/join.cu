@@ -53,35 +53,58 @@ __device__ __forceinline__ bool jload_key(const JKeyCol& c, long long row, u64* 
   return true;
 }
 
+__device__ __forceinline__ ulonglong2 ld_volatile_v2(const void* p) {
+  ulonglong2 r;
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ u64 ld_volatile_u64(const void* p) {
+  u64 r;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(p) : "memory");
+  return r;
+}
+
+// One insertion attempt; never waits on a BUSY slot (the claimer may be a lane of the same warp): returns
+// false to be called again after the warp has reconverged.
+__device__ __forceinline__ bool jtry_insert(JSlot* tab, u64 mask, long long* next, u64 key, long long r, u64& slot, u64& probe, u64* fail) {
+  while (probe <= mask) {
+    ulonglong2 s = ld_volatile_v2(&tab[slot]);
+    long long head = (long long)s.y;
+    if (head == J_EMPTY) {
+      long long old = (long long)atomicCAS(reinterpret_cast<u64*>(&tab[slot].head), (u64)J_EMPTY, (u64)J_BUSY);
+      if (old == J_EMPTY) {
+        tab[slot].key = key;
+        next[r] = -1;
+        __threadfence();
+        atomicExch(reinterpret_cast<u64*>(&tab[slot].head), (u64)r);
+        return true;
+      }
+      head = old;
+      if (head != J_BUSY) s.x = ld_volatile_u64(&tab[slot].key);
+    }
+    if (head == J_BUSY) return false;
+    if (s.x == key) {
+      long long old = (long long)atomicExch(reinterpret_cast<u64*>(&tab[slot].head), (u64)(r | J_MULTI));
+      next[r] = old & ~J_MULTI;
+      return true;
+    }
+    slot = (slot + 1) & mask;
+    probe++;
+  }
+  atomicAdd(fail, 1ull);
+  return true;
+}
+
 __global__ void __launch_bounds__(256) join_build_kernel(JSlot* tab, u64 mask, long long* next, JKeyCol col, long long n, u64* fail) {
-  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
-    u64 key;
-    if (!jload_key(col, r, &key)) continue;
-    u64 slot = (jhash(key) >> 20) & mask;
-    int spins = 0;
-    for (u64 probe = 0; probe <= mask;) {
-      ulonglong2 s = __ldcg(reinterpret_cast<const ulonglong2*>(&tab[slot]));
-      long long head = (long long)s.y;
-      if (head == J_EMPTY) {
-        long long old = (long long)atomicCAS(reinterpret_cast<u64*>(&tab[slot].head), (u64)J_EMPTY, (u64)J_BUSY);
-        if (old == J_EMPTY) {
-          tab[slot].key = key;
-          next[r] = -1;
-          __threadfence();
-          atomicExch(reinterpret_cast<u64*>(&tab[slot].head), (u64)r);
-          break;
-        }
-        head = old;
-        if (head != J_BUSY) s.x = __ldcg(&tab[slot].key);
-      }
-      if (head == J_BUSY) { if (++spins > (1 << 22)) { atomicAdd(fail, 1ull); break; } continue; }
-      if (s.x == key) {
-        long long old = (long long)atomicExch(reinterpret_cast<u64*>(&tab[slot].head), (u64)(r | J_MULTI));
-        next[r] = old & ~J_MULTI;
-        break;
-      }
-      slot = (slot + 1) & mask;
-      if (++probe > mask) atomicAdd(fail, 1ull);
+  const int lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r - lane < n; r += (long long)gridDim.x * blockDim.x) {
+    u64 key = 0;
+    bool pending = r < n && jload_key(col, r, &key);
+    u64 slot = (jhash(key) >> 20) & mask, probe = 0;
+    int rounds = 0;
+    while (__any_sync(0xFFFFFFFFu, pending)) {      // warp-synchronous retry loop
+      if (pending && jtry_insert(tab, mask, next, key, r, slot, probe, fail)) pending = false;
+      if (++rounds > (1 << 22)) { if (pending) atomicAdd(fail, 1ull); break; }
     }
   }
 }

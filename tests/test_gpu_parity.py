@@ -221,6 +221,28 @@ def test_key_nulls_and_spill(ctx, oracle):
     assert len(got) == 1500 and st["spilled_rows"] > 0
 
 
+@pytest.mark.parametrize("dense", [1, 0])
+def test_dense_and_hashed_key_paths(ctx, oracle, dense):
+    # small dense integer keys take the direct-mapped path (no key table); keys outside the sampled range
+    # (here: rows the sampler never visits) must still be grouped correctly through the spill path
+    n = 600_000
+    rng = np.random.default_rng(12)
+    k = rng.integers(-500, 500, n)
+    out = np.arange(400, n, 585 * 40)          # r % 585 == 400: outside every sampled run of 256 rows
+    k[out] = 10**15 + (np.arange(len(out)) % 3)
+    v = Spec(pb.F64, rng.random(n) * 1000, nulls=rng.random(n) < 0.05)
+    vi = Spec(pb.I64, rng.integers(-2**62, 2**62, n))
+    ctx.set_option("dense", dense)
+    try:
+        got = compare_groupby(pb, oracle, ctx, [Spec(pb.I64, k)], [v, vi], [(0, op) for op in ALL6] + [(1, op) for op in ALL6], device=True)
+        st = ctx.stats()
+    finally:
+        ctx.set_option("dense", 1)
+    assert len(got) == 1003 and st["groupby_algo_used"] == pb.GB_SHARED
+    if dense:   # two value columns = two passes, every outlier row spills in each of them
+        assert st["spilled_rows"] == 2 * len(out)
+
+
 def test_variance_is_stable_for_offset_groups(ctx, oracle):
     # group means far apart and far from zero: a single global pivot would lose all digits
     n = 100_000

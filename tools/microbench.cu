@@ -11,7 +11,9 @@ typedef unsigned long long u64;
 __device__ __forceinline__ uint32_t rng(uint32_t& s) { s ^= s << 13; s ^= s >> 17; s ^= s << 5; return s; }
 
 // mode: 0 LDS.64+STS.64 RMW f64 add, 1 LDS.128+STS.128 RMW, 2 atomicAdd u32 smem, 3 atomicAdd u64 smem, 4 atomicAdd f64 smem,
-//       5 match_any only, 6 match_any + rank loop + RMW 128, 7 smem byte election + RMW 128
+//       5 match_any only, 6 match_any + rank loop + RMW 128, 7 smem byte election + RMW 128,
+//       8 u32 atomic ticket + rank loop + RMW 128 (what gb_shared_kernel does), 9 loop overhead only,
+//       10 ticket + 3x LDS.128 + STS.128 + STS.128 (the six-aggregate record update)
 template <int MODE>
 __global__ void smem_kernel(int iters, int groups, u64* out, long long* cycles) {
   extern __shared__ __align__(16) unsigned char sm[];
@@ -25,8 +27,8 @@ __global__ void smem_kernel(int iters, int groups, u64* out, long long* cycles) 
   u64 acc = 0;
   long long t0 = clock64();
   for (int it = 0; it < iters; it++) {
-    int g = rng(s) % groups;
-    double x = (double)(s & 1023);
+    int g = (int)(((u64)rng(s) * (u64)groups) >> 32);
+    double x = __hiloint2double(0x40000000 | (s & 0xFFFFF), s);
     if (MODE == 0) {
       double* p = reinterpret_cast<double*>(tab) + g;   // 8-byte records
       *p += x;
@@ -50,6 +52,28 @@ __global__ void smem_kernel(int iters, int groups, u64* out, long long* cycles) 
         if (rank == r) { ulonglong2 a = tab[g]; a.x = (u64)__double_as_longlong(__longlong_as_double((long long)a.x) + x); a.y += 1; tab[g] = a; }
         __syncwarp();
       }
+    } else if (MODE == 8 || MODE == 10) {
+      uint32_t* cnt = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(own)) ;   // reuse the byte area (groups bytes >= 4*groups/4..): see smem size
+      uint32_t old = atomicAdd(&cnt[g >> 2], 1u);     // 4 groups share a counter word here: only the cost matters
+      __syncwarp();
+      uint32_t now = *reinterpret_cast<volatile uint32_t*>(&cnt[g >> 2]);
+      int rr = (int)(now - old - 1u);
+      int maxr = __reduce_max_sync(0xFFFFFFFFu, rr);
+      for (int r = 0; r <= maxr; r++) {
+        if (rr == r) {
+          ulonglong2 a = tab[g];
+          a.x = (u64)__double_as_longlong(__longlong_as_double((long long)a.x) + x); a.y += 1;
+          if (MODE == 10) {
+            ulonglong2 b = tab[(g + 1) % groups], m = tab[(g + 2) % groups];
+            b.x += 1; acc += m.x;
+            tab[(g + 1) % groups] = b;
+          }
+          tab[g] = a;
+        }
+        if (r < maxr) __syncwarp();
+      }
+    } else if (MODE == 9) {
+      acc += g + (u64)x;
     } else if (MODE == 7) {
       bool pending = true;
       while (__any_sync(0xFFFFFFFFu, pending)) {
@@ -106,6 +130,9 @@ int main() {
       run_smem<5>("MATCH.ANY only", warps, groups, iters);
       run_smem<6>("match_any + rank rounds + RMW128", warps, groups, iters);
       run_smem<7>("smem byte election + RMW128", warps, groups, iters);
+      run_smem<8>("u32 ticket + rank rounds + RMW128", warps, groups, iters);
+      run_smem<10>("u32 ticket + 3xLDS128 + 2xSTS128", warps, groups, iters);
+      run_smem<9>("loop overhead only", warps, groups, iters);
     }
   }
   for (int groups : {1000, 100000, 10000000}) {
