@@ -376,8 +376,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
 
   // ---- geometry of the shared-memory kernel per pass; fall back to the global table when it does not fit
   auto shared_geometry = [&](const PassPlan& pp, GbParams* gp, GbCfg* cfg, size_t* smem) -> bool {
-    const int rec_bytes = (pp.flags == GB_SUM ? 8 : 16) + ((pp.flags == GB_ALL && pp.is_int) ? 8 : 0) + 8;
-    const int cta_bytes = pp.flags == GB_ALL ? 32 : 0;
+    const int rec_bytes = (pp.flags == GB_SUM ? 8 : 16) + ((pp.flags == GB_ALL && pp.is_int) ? 8 : 0) + 4;   // ShPlanes::REC_BYTES
+    const int cta_bytes = (pp.flags == GB_ALL ? 32 : 0) + 4;                                                   // ShPlanes::CTA_BYTES
     const bool dense = variant == 0 && dense_ok && c->opt_dense != 0;
     long long cap = dense ? dense_range + std::max<long long>(dense_range / 16, 8) : est + std::max<long long>(est / 16, 8);
     cap = (cap + 7) / 8 * 8;

@@ -27,8 +27,6 @@
 
 // ---------------------------------------------------------------- flags / layout
 enum { GB_SUM = 0, GB_ALL = 1 };        // which statistics a pass maintains: {rows,n,sum} or everything
-#define GB_R 16                         // rows per lane per unit
-#define GB_UNIT_ROWS (32 * GB_R)
 #define GB_MAX_WARPS 8
 
 typedef unsigned long long u64;
@@ -320,28 +318,29 @@ __device__ __forceinline__ void g_update_batch(const GTable& t, long long slot, 
 // CTA-shared   key table u64[NW][S] + id table u32[S] (0 = empty, SH_BUSY, else id + 1)   (not in dense mode)
 //              META[cap+1]  {pivot^tag, f32 min bound, f32 max bound}   read-mostly, one LDS.128 per row  (ALL)
 //              EXACT[cap+1] {~ord(min), ord(max)}                        touched only when a bound is beaten (ALL)
+//              NUL[cap+1]   u32 NULL values (n = rows - nulls), native atomic, ~5% of the rows
 //              misc u32[4]
 // per warp     ACC[E]  f64 {S1}, i64 {isum}                       (SUM)        E = (cap + 1) * ng
 //                      {S1, S2} (+ ISUM[E] for i64 values)        (ALL)
 //              CNT[E]  u32 rows: bumped with the native atomic; the returned ticket ranks the lanes of the
 //                      warp that hit the same record in this batch (re-read after __syncwarp gives the count)
-//              NUL[E]  u32 NULL values (n = rows - nulls)
 // S1 / S2 are plain LDS/STS read-modify-writes, one rank per round, so the per-row path has no 64-bit atomics.
 template <typename VT, int FLAGS> struct ShPlanes {
   static constexpr bool IS_INT = ValTraits<VT>::is_int;
   static constexpr int ACC_BYTES = FLAGS == GB_SUM ? 8 : 16;
-  static constexpr int REC_BYTES = ACC_BYTES + ((FLAGS == GB_ALL && IS_INT) ? 8 : 0) + 8;   // per warp per record
-  static constexpr int CTA_BYTES = FLAGS == GB_ALL ? 32 : 0;                                 // META + EXACT per group
+  static constexpr int REC_BYTES = ACC_BYTES + ((FLAGS == GB_ALL && IS_INT) ? 8 : 0) + 4;   // per warp per record: sums + CNT
+  static constexpr int CTA_BYTES = (FLAGS == GB_ALL ? 32 : 0) + 4;                            // per group: [META + EXACT] + NUL
 };
 __host__ __device__ inline size_t gb_sh_fixed_bytes(int nw, int slots, int cap, int cta_bytes, int dense) {
   size_t b = dense ? 0 : ((size_t)8 * nw * slots + (size_t)4 * slots);
   b = (b + 15) / 16 * 16;
-  b += (size_t)cta_bytes * (cap + 1);
+  b += ((size_t)cta_bytes * (cap + 1) + 15) / 16 * 16;
   return b + 16;
 }
+// E = (cap + 1) * ng records + 1 trash record (lanes with nothing to count bump that one: no branches)
 __host__ __device__ inline size_t gb_sh_warp_bytes(int rec_bytes, int cap, int ng) {
-  const size_t E = (size_t)(cap + 1) * ng;
-  return ((size_t)rec_bytes * E + 15) / 16 * 16;
+  const size_t E1 = (size_t)(cap + 1) * ng + 1;
+  return ((size_t)rec_bytes * E1 + 15) / 16 * 16;
 }
 
 static constexpr uint32_t SH_BUSY = 0xFFFFFFFFu;
@@ -399,58 +398,60 @@ __device__ __noinline__ int sh_lookup(u64* ktab_key, uint32_t* ktab_id, uint32_t
   return res;
 }
 
-// One unit of a warp: 512 rows, lane owns rows base + 64*j + 2*lane + {0,1}, j = 0..7.
-// fl[j / 4] holds, 6 bits per j: {active(2), NULL value(2), NULL key(2)} of this lane's two rows.
+// One unit of a warp: 256 rows = GB_Q batches of 32; lane owns rows base + 64*j + 2*lane + h, batch q = 2*j + h.
+// Bitmap words are kept raw (the u32 word holding this lane's two bits of each 64-row chunk) and decoded
+// when the unit is aggregated, so that loading the NEXT unit never waits on a load.
+#define GB_Q 8
+#define GB_UNIT_ROWS (32 * GB_Q)
 template <typename VT> struct GbUnit {
-  u64 k[GB_R];     // KM != 1 only: the 64-bit key column
-  u64 v[GB_R];     // value bits
-  uint32_t fl[2];
+  u64 k[GB_Q];                 // KM != 1 only: the 64-bit key column
+  u64 v[GB_Q];                 // value bits
+  uint32_t vnw[GB_Q / 2];      // NULL-value bitmap words
+  uint32_t knw[GB_Q / 2];      // NULL-key bitmap words (KM != 1)
+  uint32_t fw[GB_Q / 2];       // filter: value & ~null
+  uint32_t act;                // partial unit only: bit q = row is in range
 };
 
-template <int KM, typename VT>
+template <int KM, bool FULL, typename VT>
 __device__ __forceinline__ void gb_load_unit(const GbParams& p, long long base, int lane, GbUnit<VT>& u) {
   const long long n = p.n;
-  const char* keys = reinterpret_cast<const char*>(p.ks.c[0].data);
-  const char* vals = reinterpret_cast<const char*>(p.val);
+  const u64* keys = reinterpret_cast<const u64*>(p.ks.c[0].data) + base + 2 * lane;
+  const u64* vals = reinterpret_cast<const u64*>(p.val) + base + 2 * lane;
+  const long long w0 = (base >> 5) + (lane >> 4);     // u32 bitmap word of this lane in chunk 0
+  u.act = (1u << GB_Q) - 1u;
+  if (FULL) {
 #pragma unroll
-  for (int j = 0; j < GB_R / 2; j++) {
-    const long long r0 = base + 64 * j + 2 * lane;
-    ulonglong2 kk = make_ulonglong2(0, 0), vv = make_ulonglong2(0, 0);
-    if (r0 + 1 < n) {
-      if (KM != 1) kk = ld_stream_v2(keys + 8 * r0);
-      if (vals) vv = ld_stream_v2(vals + 8 * r0);
-    } else if (r0 < n) {
-      if (KM != 1) kk.x = __ldg(reinterpret_cast<const u64*>(keys) + r0);
-      if (vals) vv.x = __ldg(reinterpret_cast<const u64*>(vals) + r0);
+    for (int j = 0; j < GB_Q / 2; j++) {
+      ulonglong2 kk = make_ulonglong2(0, 0), vv = make_ulonglong2(0, 0);
+      if (KM != 1) kk = ld_stream_v2(keys + 64 * j);
+      if (p.val) vv = ld_stream_v2(vals + 64 * j);
+      u.k[2 * j] = kk.x; u.k[2 * j + 1] = kk.y;
+      u.v[2 * j] = vv.x; u.v[2 * j + 1] = vv.y;
     }
-    u.k[2 * j] = kk.x; u.k[2 * j + 1] = kk.y;
-    u.v[2 * j] = vv.x; u.v[2 * j + 1] = vv.y;
-  }
-  u.fl[0] = u.fl[1] = 0;
+  } else {                                     // the last, partial unit
+    u.act = 0;
 #pragma unroll
-  for (int j = 0; j < GB_R / 2; j++) {
-    const long long c0 = base + 64 * j;
-    u64 m = 0, vn = 0, kn = 0;
-    if (c0 < n) {
-      const long long rem = n - c0, chunk = c0 >> 6;
-      m = rem >= 64 ? ~0ull : ((1ull << rem) - 1ull);
-      if (p.fbits) {   // filter: Some(true) rows only (data_ops.rs:49-55)
-        m &= load_bits64(p.fbits, chunk);
-        if (p.fnull) m &= ~load_bits64(p.fnull, chunk);
+    for (int j = 0; j < GB_Q / 2; j++) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const bool inb = base + 64 * j + 2 * lane + h < n;
+        u.k[2 * j + h] = (KM != 1 && inb) ? __ldg(keys + 64 * j + h) : 0ull;
+        u.v[2 * j + h] = (p.val && inb) ? __ldg(vals + 64 * j + h) : 0ull;
+        if (inb) u.act |= 1u << (2 * j + h);
       }
-      if (p.vnull) vn = load_bits64(p.vnull, chunk);
-      if (KM != 1 && p.ks.c[0].nulls) kn = load_bits64(p.ks.c[0].nulls, chunk);
     }
-    if (!vals) vn = ~0ull;
-    const uint32_t a2 = (uint32_t)(m >> (2 * lane)) & 3u, v2 = (uint32_t)(vn >> (2 * lane)) & 3u, k2 = (uint32_t)(kn >> (2 * lane)) & 3u;
-    u.fl[j >> 2] |= (a2 | (v2 << 2) | (k2 << 4)) << (6 * (j & 3));
   }
-  if (p.compat_nulls && vals) {   // filter + compat_filter_nulls: NULL values count as 0 (data_ops.rs:64-71)
 #pragma unroll
-    for (int jj = 0; jj < GB_R; jj++) {
-      const uint32_t bit = 1u << (6 * ((jj >> 1) & 3) + 2 + (jj & 1));
-      if (u.fl[jj >> 3] & bit) { u.fl[jj >> 3] &= ~bit; u.v[jj] = 0; }
+  for (int j = 0; j < GB_Q / 2; j++) {
+    const bool inb = FULL || base + 64 * j < n;
+    u.vnw[j] = (p.vnull && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.vnull) + w0 + 2 * j) : 0u;
+    u.knw[j] = (KM != 1 && p.ks.c[0].nulls && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.ks.c[0].nulls) + w0 + 2 * j) : 0u;
+    uint32_t f = 0xFFFFFFFFu;
+    if (p.fbits) {   // filter: Some(true) rows only (data_ops.rs:49-55)
+      f = inb ? __ldg(reinterpret_cast<const uint32_t*>(p.fbits) + w0 + 2 * j) : 0u;
+      if (p.fnull && inb) f &= ~__ldg(reinterpret_cast<const uint32_t*>(p.fnull) + w0 + 2 * j);
     }
+    u.fw[j] = f;
   }
 }
 
@@ -467,13 +468,13 @@ __device__ __noinline__ void gb_spill_rows(const GTable gt, u64 w0, u64 w1, u64 
   if (spill) atomicAdd(&gt.counters[CNT_SPILLED], 1ull);
 }
 
-// A value beat the f32 bound of its group: update the exact minimum / maximum (64-bit shared atomicMax is a
-// CAS loop, but this runs O(log rows) times per group) and tighten the bound.
+// A value reached the f32 bound of its group: update the exact minimum / maximum (64-bit shared atomicMax is a
+// CAS loop, but this runs O(log rows) times per group) and refresh the bounds.
 template <typename VT>
-__device__ __noinline__ void gb_minmax_slow(ulonglong2* META, ulonglong2* EXACT, int id, VT v, bool lo, bool hi) {
+__device__ __noinline__ void gb_minmax_slow(ulonglong2* META, ulonglong2* EXACT, int id, VT v) {
   using T = ValTraits<VT>;
   if (!T::orderable(v)) return;
-  if (lo) {
+  {
     const u64 o = ~T::ord(v);
     const u64 was = atomicMax(&EXACT[id].x, o);
     const u64 best = ~(was > o ? was : o);     // ord() of the current exact minimum
@@ -481,7 +482,7 @@ __device__ __noinline__ void gb_minmax_slow(ulonglong2* META, ulonglong2* EXACT,
     if (T::is_int) b = __ll2float_rn((long long)(best ^ GB_SIGN)); else b = __double2float_rn(pdrs_unord_f64(best));
     reinterpret_cast<volatile uint32_t*>(&META[id].y)[0] = __float_as_uint(b);   // bound = rn(some earlier exact min) >= rn(exact min)
   }
-  if (hi) {
+  {
     const u64 o = T::ord(v);
     const u64 was = atomicMax(&EXACT[id].y, o);
     const u64 best = was > o ? was : o;
@@ -491,13 +492,156 @@ __device__ __noinline__ void gb_minmax_slow(ulonglong2* META, ulonglong2* EXACT,
   }
 }
 
+// The CTA pivot of a group is the first finite value with its mantissa LSB forced to 1 (any value near the data
+// works as a pivot), so that 0 bits mean "unset" and the stored word IS the pivot: no decoding on the hot path.
 static __device__ __noinline__ u64 gb_pivot_set(ulonglong2* META, int id, double x) {
-  const u64 mine = (u64)__double_as_longlong(x) ^ GB_PIV_X;
+  const u64 mine = (u64)__double_as_longlong(x) | 1ull;
   const u64 was = atomicCAS(&META[id].x, 0ull, mine);
   return was ? was : mine;
 }
 
-#define GB_Q 4   // batches (of 32 rows) that share one ticket phase
+// Everything the per-unit body needs (kept in one struct so that the body can be instantiated twice:
+// full units in the main loop, the single partial unit after it).
+template <typename VT, int FLAGS> struct GbShared {
+  u64* ktab_key; uint32_t* ktab_id; uint32_t* misc;
+  ulonglong2* META; ulonglong2* EXACT; uint32_t* NUL;
+  u64* ACC1; ulonglong2* ACC2; u64* ISUM; uint32_t* CNT;
+  int S, cap, NG, E, rep, lane;
+  u64 dense_base;
+};
+
+template <int NW, int KM, typename VT, int FLAGS>
+__device__ __forceinline__ void gb_unit_body(const GbParams& p, const GbShared<VT, FLAGS>& sh, const GbUnit<VT>& cur, long long base) {
+  using T = ValTraits<VT>;
+  constexpr bool IS_INT = T::is_int;
+  constexpr bool ALL = FLAGS == GB_ALL;
+  constexpr bool dense = KM == 2;
+  const int lane = sh.lane, sh2 = (2 * lane) & 31;
+  int rec[GB_Q];           // record index (E = trash)
+  int ids[GB_Q];
+  u64 vb[GB_Q];            // value bits (0 where compat_filter_nulls turns a NULL into a default)
+  double dd[GB_Q];
+  uint32_t old[GB_Q];
+  uint32_t updmask = 0, spillmask = 0, slowmask = 0, nullkey = 0;
+  // -- phase 1: key -> record, bump the row counters (tickets), pivot / min / max bounds
+#pragma unroll
+  for (int q = 0; q < GB_Q; q++) {
+    const int j = q >> 1, h = q & 1;
+    const bool active = ((cur.act >> q) & 1u) && ((cur.fw[j] >> (sh2 + h)) & 1u);
+    bool vnull = !p.val || ((cur.vnw[j] >> (sh2 + h)) & 1u);
+    bool knull = (cur.knw[j] >> (sh2 + h)) & 1u;
+    vb[q] = cur.v[q];
+    if (p.compat_nulls && vnull && p.val) { vnull = false; vb[q] = 0; }   // filter + compat_filter_nulls (data_ops.rs:64-71)
+    const bool valid = active && !vnull;
+    int id = -1;
+    if (dense) {                       // small dense integer keys: direct-mapped
+      const u64 off = cur.k[q] - sh.dense_base;
+      if (active && off < (u64)sh.cap) id = (int)off;
+    } else {                           // CTA-shared key table
+      u64 w[NW];
+#pragma unroll
+      for (int i = 0; i < NW; i++) w[i] = 0;
+      if (KM != 1) w[0] = cur.k[q];
+      else if (active) knull = load_key_generic<NW>(p.ks, base + 64 * j + 2 * lane + h, w);
+      id = sh_lookup<NW>(sh.ktab_key, sh.ktab_id, sh.misc, sh.S, p.sh_log_slots, sh.cap, w, active && !knull);
+    }
+    if (active && knull) { id = sh.cap; nullkey = 1; }
+    if (active && id < 0) spillmask |= 1u << q;
+    ids[q] = id;
+    rec[q] = id >= 0 ? id * sh.NG + sh.rep : sh.E;
+    old[q] = atomicAdd(&sh.CNT[rec[q]], 1u);
+    if (id >= 0 && !valid) atomicAdd(&sh.NUL[id], 1u);
+    const bool upd = id >= 0 && valid;
+    if (upd) updmask |= 1u << q;
+    const VT v = T::from_bits(vb[q]);
+    const double x = T::to_f64(v);
+    dd[q] = x;
+    if (ALL) {                         // pivot and min / max bounds: CTA-shared, read-mostly, one LDS.128
+      const ulonglong2 meta = lds_volatile_v2(&sh.META[id >= 0 ? id : 0]);
+      dd[q] = x - __longlong_as_double((long long)meta.x);   // unset pivot = 0 bits = +0.0
+      // f32 bounds hold round-to-nearest(exact min / max); rounding is monotonic, so a value below the exact
+      // minimum always satisfies xf <= bound (values equal to the bound after rounding take the slow path too)
+      const float xf = IS_INT ? __ll2float_rn((long long)T::to_bits(v)) : __double2float_rn(x);
+      const bool slow = xf <= __uint_as_float((uint32_t)meta.y) || xf >= __uint_as_float((uint32_t)(meta.y >> 32)) || meta.x == 0;
+      if (upd && slow) slowmask |= 1u << q;
+    }
+  }
+  if (nullkey && !*reinterpret_cast<volatile uint32_t*>(&sh.misc[1])) *reinterpret_cast<volatile uint32_t*>(&sh.misc[1]) = 1u;
+  if (ALL && slowmask) {               // rare: first value of a group (pivot) or a value at / beyond a bound
+#pragma unroll
+    for (int q = 0; q < GB_Q; q++) if ((slowmask >> q) & 1u) {
+      const VT v = T::from_bits(vb[q]);
+      const double x = T::to_f64(v);
+      u64 px = *reinterpret_cast<volatile u64*>(&sh.META[ids[q]].x);
+      if (px == 0 && is_finite_f64(x)) px = gb_pivot_set(sh.META, ids[q], x);   // first finite value of the group in this CTA
+      dd[q] = x - __longlong_as_double((long long)px);
+      gb_minmax_slow<VT>(sh.META, sh.EXACT, ids[q], v);
+    }
+  }
+  if (__any_sync(0xFFFFFFFFu, spillmask != 0)) {   // rare: keys that do not fit this CTA's table go to the global table
+#pragma unroll
+    for (int q = 0; q < GB_Q; q++) {
+      u64 w[NW];
+#pragma unroll
+      for (int i = 0; i < NW; i++) w[i] = 0;
+      const bool sp = (spillmask >> q) & 1u;
+      if (KM != 1) w[0] = cur.k[q];
+      else if (sp) load_key_generic<NW>(p.ks, base + 64 * (q >> 1) + 2 * lane + (q & 1), w);
+      const bool vnull = !p.val || (!p.compat_nulls && ((cur.vnw[q >> 1] >> (sh2 + (q & 1))) & 1u));
+      gb_spill_rows<NW, VT, FLAGS>(p.gt, w[0], NW > 1 ? w[NW > 1 ? 1 : 0] : 0ull, NW > 2 ? w[NW > 2 ? 2 : 0] : 0ull, sp, p.count_rows != 0,
+                                   !vnull, T::from_bits(vb[q]));
+    }
+  }
+  // -- phase 2: ranks from the tickets (unique per record across the whole unit)
+  __syncwarp();
+  uint32_t latemask = 0;
+#pragma unroll
+  for (int q = 0; q < GB_Q; q++) {
+    const uint32_t now = *reinterpret_cast<volatile uint32_t*>(&sh.CNT[rec[q]]);
+    if (((updmask >> q) & 1u) && now - old[q] != 1u) latemask |= 1u << q;     // not the last ticket of its record: not rank 0
+  }
+  // -- phase 3a: rank 0 (the row holding the LAST ticket of its record) does a plain read-modify-write
+  const uint32_t firstmask = updmask & ~latemask;
+  if (!ALL) {
+    u64 a[GB_Q];
+#pragma unroll
+    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) a[q] = sh.ACC1[rec[q]];
+#pragma unroll
+    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) {
+      if (IS_INT) a[q] += vb[q];
+      else a[q] = (u64)__double_as_longlong(__longlong_as_double((long long)a[q]) + dd[q]);
+      sh.ACC1[rec[q]] = a[q];
+    }
+  } else {
+    ulonglong2 a[GB_Q];
+#pragma unroll
+    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) a[q] = sh.ACC2[rec[q]];
+#pragma unroll
+    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) {
+      a[q].x = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].x) + dd[q]);
+      a[q].y = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].y) + dd[q] * dd[q]);
+      sh.ACC2[rec[q]] = a[q];
+      if (IS_INT) sh.ISUM[rec[q]] += vb[q];
+    }
+  }
+  // -- phase 3b: the other rows of a record (same warp, same unit: ~10% of the rows at 1000 groups) add with
+  //    64-bit shared atomics (CAS loops) once the plain updates are done
+  if (__any_sync(0xFFFFFFFFu, latemask != 0)) {
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < GB_Q; q++) if ((latemask >> q) & 1u) {
+      if (!ALL) {
+        if (IS_INT) atomicAdd(&sh.ACC1[rec[q]], vb[q]);
+        else atomicAdd(reinterpret_cast<double*>(&sh.ACC1[rec[q]]), dd[q]);
+      } else {
+        atomicAdd(reinterpret_cast<double*>(&sh.ACC2[rec[q]].x), dd[q]);
+        atomicAdd(reinterpret_cast<double*>(&sh.ACC2[rec[q]].y), dd[q] * dd[q]);
+        if (IS_INT) atomicAdd(&sh.ISUM[rec[q]], vb[q]);
+      }
+    }
+  }
+  __syncwarp();
+}
 
 // KM: 0 = one 64-bit key column through the CTA-shared key table, 1 = generic packed key tuple,
 //     2 = one 64-bit key column with small dense integer keys (direct-mapped group ids, no key table)
@@ -510,30 +654,26 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
   constexpr bool dense = KM == 2;
   extern __shared__ __align__(16) unsigned char smem[];
   const int S = p.sh_slots, cap = p.sh_cap, NG = p.sh_ng;
-  const int E = (cap + 1) * NG;
+  const int E = (cap + 1) * NG;              // record E is the per-warp trash record
   u64* ktab_key = reinterpret_cast<u64*>(smem);
   uint32_t* ktab_id = reinterpret_cast<uint32_t*>(smem + (size_t)8 * NW * S);
   const size_t keys_bytes = dense ? 0 : (((size_t)8 * NW * S + (size_t)4 * S + 15) / 16 * 16);
   ulonglong2* META = reinterpret_cast<ulonglong2*>(smem + keys_bytes);                 // ALL only
   ulonglong2* EXACT = META + (cap + 1);                                               // ALL only
-  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + keys_bytes + (size_t)L::CTA_BYTES * (cap + 1));   // [0] groups in this CTA, [1] NULL group seen
+  uint32_t* NUL = reinterpret_cast<uint32_t*>(smem + keys_bytes + (size_t)(L::CTA_BYTES - 4) * (cap + 1));
   const size_t fixed = gb_sh_fixed_bytes(NW, S, cap, L::CTA_BYTES, dense);
+  uint32_t* misc = reinterpret_cast<uint32_t*>(smem + fixed - 16);   // [0] groups in this CTA, [1] NULL group seen
   const size_t warp_bytes = gb_sh_warp_bytes(L::REC_BYTES, cap, NG);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   unsigned char* wbase = smem + fixed + (size_t)warp * warp_bytes;
-  // per-warp arrays: ACC (8 or 16 B), [ISUM 8 B], CNT u32, NUL u32
-  u64* ACC1 = reinterpret_cast<u64*>(wbase);                 // SUM: one 8-byte word per record
-  ulonglong2* ACC2 = reinterpret_cast<ulonglong2*>(wbase);   // ALL: {S1, S2}
-  u64* ISUM = reinterpret_cast<u64*>(wbase + (size_t)L::ACC_BYTES * E);
-  uint32_t* CNT = reinterpret_cast<uint32_t*>(wbase + (size_t)(L::REC_BYTES - 8) * E);
-  uint32_t* NUL = CNT + E;
 
   // ---- init
   if (!dense) for (int i = threadIdx.x; i < S; i += blockDim.x) ktab_id[i] = 0;
   if (threadIdx.x < 4) misc[threadIdx.x] = 0;
-  if (ALL) {
-    const float inf = __int_as_float(0x7f800000);
-    for (int i = threadIdx.x; i <= cap; i += blockDim.x) {
+  for (int i = threadIdx.x; i <= cap; i += blockDim.x) {
+    NUL[i] = 0;
+    if (ALL) {
+      const float inf = __int_as_float(0x7f800000);
       META[i] = make_ulonglong2(0ull, ((u64)__float_as_uint(-inf) << 32) | (u64)__float_as_uint(inf));   // .y = {lo: min bound, hi: max bound}
       EXACT[i] = make_ulonglong2(0ull, 0ull);
     }
@@ -541,131 +681,34 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
   for (size_t i = lane; i < warp_bytes / 8; i += 32) reinterpret_cast<u64*>(wbase)[i] = 0;
   __syncthreads();
 
+  GbShared<VT, FLAGS> sh;
+  sh.ktab_key = ktab_key; sh.ktab_id = ktab_id; sh.misc = misc; sh.META = META; sh.EXACT = EXACT; sh.NUL = NUL;
+  // per-warp arrays over E + 1 records: ACC (8 or 16 B), [ISUM 8 B], CNT u32
+  sh.ACC1 = reinterpret_cast<u64*>(wbase);
+  sh.ACC2 = reinterpret_cast<ulonglong2*>(wbase);
+  sh.ISUM = reinterpret_cast<u64*>(wbase + (size_t)L::ACC_BYTES * (E + 1));
+  sh.CNT = reinterpret_cast<uint32_t*>(wbase + (size_t)(L::REC_BYTES - 4) * (E + 1));
+  sh.S = S; sh.cap = cap; sh.NG = NG; sh.E = E; sh.rep = lane & (NG - 1); sh.lane = lane;
+  sh.dense_base = (u64)p.sh_dense_base;
+
   const long long n = p.n;
-  const long long total_units = (n + GB_UNIT_ROWS - 1) / GB_UNIT_ROWS;
+  const long long full_units = n / GB_UNIT_ROWS;
   const long long gwarp = (long long)blockIdx.x * nwarps + warp, total_warps = (long long)gridDim.x * nwarps;
-  const int rep = lane & (NG - 1);
-  const u64 dense_base = (u64)p.sh_dense_base;
-  const bool count_rows = p.count_rows != 0;
 
-  // The aggregation (shared-memory bound, >1 cycle per row per SM) dominates a unit by far, so the loads of a
-  // unit are not double-buffered through registers; the next unit of this warp is pulled into L2 instead.
-  GbUnit<VT> cur;
-  for (long long u = gwarp; u < total_units; u += total_warps) {
-    const long long base = u * GB_UNIT_ROWS;
-    gb_load_unit<KM, VT>(p, base, lane, cur);
-    if (u + total_warps < total_units) {
-      const long long nb = (u + total_warps) * GB_UNIT_ROWS + 16 * lane;   // 32 lanes x 128 B = one unit of an 8-byte column
-      if (nb < n) {
-        if (KM != 1) asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p.ks.c[0].data) + 8 * nb));
-        if (p.val) asm volatile("prefetch.global.L2 [%0];" :: "l"(reinterpret_cast<const char*>(p.val) + 8 * nb));
-      }
-    }
-
-#pragma unroll
-    for (int g0 = 0; g0 < GB_R; g0 += GB_Q) {
-      int eidx[GB_Q];          // record index of the row, -1: nothing to add to the sums
-      int rr[GB_Q];
-      VT vv[GB_Q];
-      double dd[GB_Q];
-      uint32_t old[GB_Q];
-      u64 wsp[GB_Q][NW];
-      uint32_t spillmask = 0;
-      // -- phase 1: key -> record, bump the row counters (tickets), pivot / min / max
-#pragma unroll
-      for (int q = 0; q < GB_Q; q++) {
-        const int jj = g0 + q;
-        const uint32_t fl = cur.fl[jj >> 3];
-        constexpr int dummy = 0; (void)dummy;
-        const int sh = 6 * ((jj >> 1) & 3) + (jj & 1);
-        const bool active = (fl >> sh) & 1u;
-        const bool valid = active && !((fl >> (sh + 2)) & 1u);
-        bool knull = (fl >> (sh + 4)) & 1u;
-        const VT v = T::from_bits(cur.v[jj]);
-        u64 w[NW];
-#pragma unroll
-        for (int i = 0; i < NW; i++) w[i] = 0;
-        if (KM != 1) w[0] = cur.k[jj];
-        else if (active) knull = load_key_generic<NW>(p.ks, base + 64 * (jj >> 1) + 2 * lane + (jj & 1), w);
-        int id = -1;
-        if (dense) {                       // small dense integer keys: direct-mapped
-          const u64 off = w[0] - dense_base;
-          if (active && off < (u64)cap) id = (int)off;
-        } else {                           // CTA-shared key table
-          id = sh_lookup<NW>(ktab_key, ktab_id, misc, S, p.sh_log_slots, cap, w, active && !knull);
-        }
-        if (active && knull) { id = cap; if (!*reinterpret_cast<volatile uint32_t*>(&misc[1])) *reinterpret_cast<volatile uint32_t*>(&misc[1]) = 1u; }
-        if (active && id < 0) spillmask |= 1u << q;
-#pragma unroll
-        for (int i = 0; i < NW; i++) wsp[q][i] = w[i];
-        const int e = id * NG + rep;
-        old[q] = 0;
-        if (id >= 0) {
-          old[q] = atomicAdd(&CNT[e], 1u);
-          if (!valid) atomicAdd(&NUL[e], 1u);
-        }
-        const bool upd = id >= 0 && valid;
-        eidx[q] = upd ? e : -1;
-        vv[q] = v;
-        double x = T::to_f64(v);
-        dd[q] = x;
-        if (ALL && upd) {                  // pivot and min / max bounds: CTA-shared, read-mostly, one LDS.128
-          const ulonglong2 meta = lds_volatile_v2(&META[id]);
-          u64 px = meta.x;
-          if (px == 0 && is_finite_f64(x)) px = gb_pivot_set(META, id, x);   // first finite value of the group in this CTA
-          dd[q] = x - (px ? __longlong_as_double((long long)(px ^ GB_PIV_X)) : 0.0);
-          // f32 bounds hold round-to-nearest(exact min / max); rounding is monotonic, so a value below the exact
-          // minimum always satisfies xf <= bound (values equal to the bound after rounding take the slow path too)
-          const float xf = IS_INT ? __ll2float_rn((long long)T::to_bits(v)) : __double2float_rn(x);
-          const bool lo = xf <= __uint_as_float((uint32_t)meta.y), hi = xf >= __uint_as_float((uint32_t)(meta.y >> 32));
-          if (lo || hi) gb_minmax_slow<VT>(META, EXACT, id, v, lo, hi);
-        }
-      }
-      if (__any_sync(0xFFFFFFFFu, spillmask != 0)) {   // rare: keys that do not fit this CTA's table go to the global table
-#pragma unroll
-        for (int q = 0; q < GB_Q; q++) {
-          const int jj = g0 + q;
-          const bool valid = !((cur.fl[jj >> 3] >> (6 * ((jj >> 1) & 3) + (jj & 1) + 2)) & 1u);
-          gb_spill_rows<NW, VT, FLAGS>(p.gt, wsp[q][0], NW > 1 ? wsp[q][NW > 1 ? 1 : 0] : 0ull, NW > 2 ? wsp[q][NW > 2 ? 2 : 0] : 0ull,
-                                       (spillmask >> q) & 1u, count_rows, valid, vv[q]);
-        }
-      }
-      // -- phase 2: ranks from the tickets (unique per record across the whole group of GB_Q batches)
-      __syncwarp();
-      int mr = 0;
-#pragma unroll
-      for (int q = 0; q < GB_Q; q++) {
-        rr[q] = -1;
-        if (eidx[q] >= 0) { rr[q] = (int)(*reinterpret_cast<volatile uint32_t*>(&CNT[eidx[q]]) - old[q] - 1u); mr = max(mr, rr[q]); }
-      }
-      const int maxr = __reduce_max_sync(0xFFFFFFFFu, mr);
-      // -- phase 3: plain read-modify-write of this warp's sums, one rank per round
-      for (int r = 0; r <= maxr; r++) {
-        if (!ALL) {
-          u64 a[GB_Q];
-#pragma unroll
-          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) a[q] = ACC1[eidx[q]];
-#pragma unroll
-          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) {
-            if (IS_INT) a[q] += (u64)T::to_bits(vv[q]);
-            else a[q] = (u64)__double_as_longlong(__longlong_as_double((long long)a[q]) + dd[q]);
-            ACC1[eidx[q]] = a[q];
-          }
-        } else {
-          ulonglong2 a[GB_Q];
-#pragma unroll
-          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) a[q] = ACC2[eidx[q]];
-#pragma unroll
-          for (int q = 0; q < GB_Q; q++) if (rr[q] == r) {
-            a[q].x = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].x) + dd[q]);
-            a[q].y = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].y) + dd[q] * dd[q]);
-            ACC2[eidx[q]] = a[q];
-            if (IS_INT) ISUM[eidx[q]] += (u64)T::to_bits(vv[q]);
-          }
-        }
-        __syncwarp();
-      }
-    }
+  // Full units, double-buffered through registers: the loads of unit u + total_warps are issued before unit u is
+  // aggregated, and nothing of the next unit is touched until then.
+  GbUnit<VT> cur, nxt;
+  if (gwarp < full_units) gb_load_unit<KM, true, VT>(p, gwarp * GB_UNIT_ROWS, lane, cur);
+#pragma unroll 1
+  for (long long u = gwarp; u < full_units; u += total_warps) {
+    if (u + total_warps < full_units) gb_load_unit<KM, true, VT>(p, (u + total_warps) * GB_UNIT_ROWS, lane, nxt);
+    gb_unit_body<NW, KM, VT, FLAGS>(p, sh, cur, u * GB_UNIT_ROWS);
+    cur = nxt;
+  }
+  // The partial last unit (bounds-checked loads), by the warp whose turn it would be.
+  if (n % GB_UNIT_ROWS != 0 && gwarp == full_units % total_warps) {
+    gb_load_unit<KM, false, VT>(p, full_units * GB_UNIT_ROWS, lane, cur);
+    gb_unit_body<NW, KM, VT, FLAGS>(p, sh, cur, full_units * GB_UNIT_ROWS);
   }
   __syncthreads();
 
@@ -681,15 +724,15 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
     }
     bool have = id >= 0;
     if (!have) id = 0;
-    u64 rows = 0, nulls = 0, isum = 0;
+    u64 rows = 0, isum = 0;
+    const u64 nulls = NUL[id];
     double S1 = 0.0, S2 = 0.0;
     for (int wq = 0; wq < nwarps; wq++) {
       const unsigned char* qb = smem + fixed + (size_t)wq * warp_bytes;
-      const uint32_t* QC = reinterpret_cast<const uint32_t*>(qb + (size_t)(L::REC_BYTES - 8) * E);
+      const uint32_t* QC = reinterpret_cast<const uint32_t*>(qb + (size_t)(L::REC_BYTES - 4) * (E + 1));
       for (int r = 0; r < NG; r++) {
         const int e = id * NG + r;
         rows += QC[e];
-        nulls += QC[E + e];
         if (!ALL) {
           const u64 a = reinterpret_cast<const u64*>(qb)[e];
           if (IS_INT) isum += a; else S1 += __longlong_as_double((long long)a);
@@ -697,7 +740,7 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
           const ulonglong2 a = reinterpret_cast<const ulonglong2*>(qb)[e];
           S1 += __longlong_as_double((long long)a.x);
           S2 += __longlong_as_double((long long)a.y);
-          if (IS_INT) isum += reinterpret_cast<const u64*>(qb + (size_t)16 * E)[e];
+          if (IS_INT) isum += reinterpret_cast<const u64*>(qb + (size_t)16 * (E + 1))[e];
         }
       }
     }
@@ -706,7 +749,7 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
 #pragma unroll
     for (int i = 0; i < NW; i++) w[i] = 0;
     if (have && id != cap) {
-      if (dense) w[0] = dense_base + (u64)id;
+      if (dense) w[0] = sh.dense_base + (u64)id;
       else {
 #pragma unroll
         for (int i = 0; i < NW; i++) w[i] = ktab_key[i * S + s];
@@ -718,7 +761,7 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
     u64 mnc = 0, mxo = 0, px = 0;
     if (ALL) { px = META[id].x; mnc = EXACT[id].x; mxo = EXACT[id].y; }
     if (p.count_rows) atomicAdd(&p.gt.hdr[gs].rowsw, rows);
-    g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, rows - nulls, px ? __longlong_as_double((long long)(px ^ GB_PIV_X)) : 0.0, px != 0, S1, S2, isum, mnc, mxo);
+    g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, rows - nulls, __longlong_as_double((long long)px), px != 0, S1, S2, isum, mnc, mxo);
   }
 }
 
