@@ -500,24 +500,37 @@ static __device__ __noinline__ u64 gb_pivot_set(ulonglong2* META, int id, double
   return was ? was : mine;
 }
 
-// Everything the per-unit body needs (kept in one struct so that the body can be instantiated twice:
+// ---- explicit shared-memory accessors on 32-bit shared addresses (keeps the address arithmetic of the hot
+//      loop to one IMAD per access and the access width explicit)
+__device__ __forceinline__ uint32_t sm_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t sm_atom_add32(uint32_t a, uint32_t v) { uint32_t r; asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(v) : "memory"); return r; }
+__device__ __forceinline__ void sm_red_add32(uint32_t a, uint32_t v) { asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t sm_ld32(uint32_t a) { uint32_t r; asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ u64 sm_ld64(uint32_t a) { u64 r; asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(r) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ void sm_st64(uint32_t a, u64 v) { asm volatile("st.volatile.shared.u64 [%0], %1;" :: "r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ ulonglong2 sm_ld128(uint32_t a) { ulonglong2 r; asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "r"(a) : "memory"); return r; }
+__device__ __forceinline__ void sm_st128(uint32_t a, ulonglong2 v) { asm volatile("st.volatile.shared.v2.u64 [%0], {%1, %2};" :: "r"(a), "l"(v.x), "l"(v.y) : "memory"); }
+
+// Everything the per-unit body needs (kept in one struct so that the body can be instantiated several times:
 // full units in the main loop, the single partial unit after it).
 template <typename VT, int FLAGS> struct GbShared {
   u64* ktab_key; uint32_t* ktab_id; uint32_t* misc;
-  ulonglong2* META; ulonglong2* EXACT; uint32_t* NUL;
-  u64* ACC1; ulonglong2* ACC2; u64* ISUM; uint32_t* CNT;
+  ulonglong2* META; ulonglong2* EXACT;
+  uint32_t a_meta, a_nul, a_acc, a_isum, a_cnt;   // 32-bit shared addresses of META, NUL and this warp's ACC / ISUM / CNT
   int S, cap, NG, E, rep, lane;
   u64 dense_base;
 };
 
-template <int NW, int KM, typename VT, int FLAGS>
+// PLAIN: no row filter, no NULL keys, no compat_filter_nulls, full unit -> every row is active.
+template <int NW, int KM, typename VT, int FLAGS, bool PLAIN>
 __device__ __forceinline__ void gb_unit_body(const GbParams& p, const GbShared<VT, FLAGS>& sh, const GbUnit<VT>& cur, long long base) {
   using T = ValTraits<VT>;
   constexpr bool IS_INT = T::is_int;
   constexpr bool ALL = FLAGS == GB_ALL;
   constexpr bool dense = KM == 2;
+  constexpr int ACCB = ALL ? 16 : 8;
   const int lane = sh.lane, sh2 = (2 * lane) & 31;
-  int rec[GB_Q];           // record index (E = trash)
+  uint32_t arec[GB_Q];     // rec * 4 (byte offset into CNT; ACC offset = arec * ACCB / 4)
   int ids[GB_Q];
   u64 vb[GB_Q];            // value bits (0 where compat_filter_nulls turns a NULL into a default)
   double dd[GB_Q];
@@ -527,12 +540,14 @@ __device__ __forceinline__ void gb_unit_body(const GbParams& p, const GbShared<V
 #pragma unroll
   for (int q = 0; q < GB_Q; q++) {
     const int j = q >> 1, h = q & 1;
-    const bool active = ((cur.act >> q) & 1u) && ((cur.fw[j] >> (sh2 + h)) & 1u);
+    bool active = true, knull = false;
     bool vnull = !p.val || ((cur.vnw[j] >> (sh2 + h)) & 1u);
-    bool knull = (cur.knw[j] >> (sh2 + h)) & 1u;
     vb[q] = cur.v[q];
-    if (p.compat_nulls && vnull && p.val) { vnull = false; vb[q] = 0; }   // filter + compat_filter_nulls (data_ops.rs:64-71)
-    const bool valid = active && !vnull;
+    if (!PLAIN) {
+      active = ((cur.act >> q) & 1u) && ((cur.fw[j] >> (sh2 + h)) & 1u);
+      knull = (cur.knw[j] >> (sh2 + h)) & 1u;
+      if (p.compat_nulls && vnull && p.val) { vnull = false; vb[q] = 0; }   // filter + compat_filter_nulls (data_ops.rs:64-71)
+    }
     int id = -1;
     if (dense) {                       // small dense integer keys: direct-mapped
       const u64 off = cur.k[q] - sh.dense_base;
@@ -545,24 +560,24 @@ __device__ __forceinline__ void gb_unit_body(const GbParams& p, const GbShared<V
       else if (active) knull = load_key_generic<NW>(p.ks, base + 64 * j + 2 * lane + h, w);
       id = sh_lookup<NW>(sh.ktab_key, sh.ktab_id, sh.misc, sh.S, p.sh_log_slots, sh.cap, w, active && !knull);
     }
-    if (active && knull) { id = sh.cap; nullkey = 1; }
+    if (!PLAIN || KM == 1) { if (active && knull) { id = sh.cap; nullkey = 1; } }
     if (active && id < 0) spillmask |= 1u << q;
     ids[q] = id;
-    rec[q] = id >= 0 ? id * sh.NG + sh.rep : sh.E;
-    old[q] = atomicAdd(&sh.CNT[rec[q]], 1u);
-    if (id >= 0 && !valid) atomicAdd(&sh.NUL[id], 1u);
-    const bool upd = id >= 0 && valid;
+    arec[q] = (uint32_t)(id >= 0 ? id * sh.NG + sh.rep : sh.E) * 4u;
+    old[q] = sm_atom_add32(sh.a_cnt + arec[q], 1u);
+    if (id >= 0 && vnull) sm_red_add32(sh.a_nul + (uint32_t)id * 4u, 1u);
+    const bool upd = id >= 0 && !vnull;
     if (upd) updmask |= 1u << q;
     const VT v = T::from_bits(vb[q]);
     const double x = T::to_f64(v);
     dd[q] = x;
     if (ALL) {                         // pivot and min / max bounds: CTA-shared, read-mostly, one LDS.128
-      const ulonglong2 meta = lds_volatile_v2(&sh.META[id >= 0 ? id : 0]);
+      const ulonglong2 meta = sm_ld128(sh.a_meta + (uint32_t)(id >= 0 ? id : 0) * 16u);
       dd[q] = x - __longlong_as_double((long long)meta.x);   // unset pivot = 0 bits = +0.0
       // f32 bounds hold round-to-nearest(exact min / max); rounding is monotonic, so a value below the exact
       // minimum always satisfies xf <= bound (values equal to the bound after rounding take the slow path too)
       const float xf = IS_INT ? __ll2float_rn((long long)T::to_bits(v)) : __double2float_rn(x);
-      const bool slow = xf <= __uint_as_float((uint32_t)meta.y) || xf >= __uint_as_float((uint32_t)(meta.y >> 32)) || meta.x == 0;
+      const bool slow = xf <= __uint_as_float((uint32_t)meta.y) || xf >= __uint_as_float((uint32_t)(meta.y >> 32)) || !((uint32_t)meta.x & 1u);
       if (upd && slow) slowmask |= 1u << q;
     }
   }
@@ -597,50 +612,54 @@ __device__ __forceinline__ void gb_unit_body(const GbParams& p, const GbShared<V
   uint32_t latemask = 0;
 #pragma unroll
   for (int q = 0; q < GB_Q; q++) {
-    const uint32_t now = *reinterpret_cast<volatile uint32_t*>(&sh.CNT[rec[q]]);
-    if (((updmask >> q) & 1u) && now - old[q] != 1u) latemask |= 1u << q;     // not the last ticket of its record: not rank 0
+    const uint32_t now = sm_ld32(sh.a_cnt + arec[q]);
+    if (now - old[q] != 1u) latemask |= 1u << q;     // not the last ticket of its record
   }
-  // -- phase 3a: rank 0 (the row holding the LAST ticket of its record) does a plain read-modify-write
+  latemask &= updmask;
+  // -- phase 3a: the row holding the LAST ticket of its record does a plain read-modify-write
   const uint32_t firstmask = updmask & ~latemask;
   if (!ALL) {
     u64 a[GB_Q];
 #pragma unroll
-    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) a[q] = sh.ACC1[rec[q]];
+    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) a[q] = sm_ld64(sh.a_acc + arec[q] * 2u);
 #pragma unroll
     for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) {
       if (IS_INT) a[q] += vb[q];
       else a[q] = (u64)__double_as_longlong(__longlong_as_double((long long)a[q]) + dd[q]);
-      sh.ACC1[rec[q]] = a[q];
+      sm_st64(sh.a_acc + arec[q] * 2u, a[q]);
     }
   } else {
     ulonglong2 a[GB_Q];
 #pragma unroll
-    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) a[q] = sh.ACC2[rec[q]];
+    for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) a[q] = sm_ld128(sh.a_acc + arec[q] * 4u);
 #pragma unroll
     for (int q = 0; q < GB_Q; q++) if ((firstmask >> q) & 1u) {
       a[q].x = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].x) + dd[q]);
-      a[q].y = (u64)__double_as_longlong(__longlong_as_double((long long)a[q].y) + dd[q] * dd[q]);
-      sh.ACC2[rec[q]] = a[q];
-      if (IS_INT) sh.ISUM[rec[q]] += vb[q];
+      a[q].y = (u64)__double_as_longlong(fma(dd[q], dd[q], __longlong_as_double((long long)a[q].y)));
+      sm_st128(sh.a_acc + arec[q] * 4u, a[q]);
+      if (IS_INT) sm_st64(sh.a_isum + arec[q] * 2u, sm_ld64(sh.a_isum + arec[q] * 2u) + vb[q]);
     }
   }
   // -- phase 3b: the other rows of a record (same warp, same unit: ~10% of the rows at 1000 groups) add with
   //    64-bit shared atomics (CAS loops) once the plain updates are done
   if (__any_sync(0xFFFFFFFFu, latemask != 0)) {
     __syncwarp();
+    const char* accg = reinterpret_cast<const char*>(__cvta_shared_to_generic(sh.a_acc));
+    const char* isumg = reinterpret_cast<const char*>(__cvta_shared_to_generic(sh.a_isum));
 #pragma unroll
     for (int q = 0; q < GB_Q; q++) if ((latemask >> q) & 1u) {
       if (!ALL) {
-        if (IS_INT) atomicAdd(&sh.ACC1[rec[q]], vb[q]);
-        else atomicAdd(reinterpret_cast<double*>(&sh.ACC1[rec[q]]), dd[q]);
+        if (IS_INT) atomicAdd((u64*)(accg + arec[q] * 2u), vb[q]);
+        else atomicAdd((double*)(accg + arec[q] * 2u), dd[q]);
       } else {
-        atomicAdd(reinterpret_cast<double*>(&sh.ACC2[rec[q]].x), dd[q]);
-        atomicAdd(reinterpret_cast<double*>(&sh.ACC2[rec[q]].y), dd[q] * dd[q]);
-        if (IS_INT) atomicAdd(&sh.ISUM[rec[q]], vb[q]);
+        atomicAdd((double*)(accg + arec[q] * 4u), dd[q]);
+        atomicAdd((double*)(accg + arec[q] * 4u + 8), dd[q] * dd[q]);
+        if (IS_INT) atomicAdd((u64*)(isumg + arec[q] * 2u), vb[q]);
       }
     }
   }
   __syncwarp();
+  (void)ACCB;
 }
 
 // KM: 0 = one 64-bit key column through the CTA-shared key table, 1 = generic packed key tuple,
@@ -682,12 +701,12 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
   __syncthreads();
 
   GbShared<VT, FLAGS> sh;
-  sh.ktab_key = ktab_key; sh.ktab_id = ktab_id; sh.misc = misc; sh.META = META; sh.EXACT = EXACT; sh.NUL = NUL;
+  sh.ktab_key = ktab_key; sh.ktab_id = ktab_id; sh.misc = misc; sh.META = META; sh.EXACT = EXACT;
   // per-warp arrays over E + 1 records: ACC (8 or 16 B), [ISUM 8 B], CNT u32
-  sh.ACC1 = reinterpret_cast<u64*>(wbase);
-  sh.ACC2 = reinterpret_cast<ulonglong2*>(wbase);
-  sh.ISUM = reinterpret_cast<u64*>(wbase + (size_t)L::ACC_BYTES * (E + 1));
-  sh.CNT = reinterpret_cast<uint32_t*>(wbase + (size_t)(L::REC_BYTES - 4) * (E + 1));
+  sh.a_meta = sm_addr(META); sh.a_nul = sm_addr(NUL);
+  sh.a_acc = sm_addr(wbase);
+  sh.a_isum = sm_addr(wbase + (size_t)L::ACC_BYTES * (E + 1));
+  sh.a_cnt = sm_addr(wbase + (size_t)(L::REC_BYTES - 4) * (E + 1));
   sh.S = S; sh.cap = cap; sh.NG = NG; sh.E = E; sh.rep = lane & (NG - 1); sh.lane = lane;
   sh.dense_base = (u64)p.sh_dense_base;
 
@@ -697,18 +716,33 @@ __global__ void __launch_bounds__(GB_MAX_WARPS * 32, 1) gb_shared_kernel(const G
 
   // Full units, double-buffered through registers: the loads of unit u + total_warps are issued before unit u is
   // aggregated, and nothing of the next unit is touched until then.
+  // Units are double-buffered through registers: the loads of unit u + total_warps are issued before unit u is
+  // aggregated, and nothing of the next unit is touched until then.  The common case (no filter, no NULL keys)
+  // runs a leaner body over the full units; everything else, and the partial last unit, takes the general one.
+  const long long total_units = (n + GB_UNIT_ROWS - 1) / GB_UNIT_ROWS;
+  const bool plain = !p.fbits && !p.compat_nulls && (KM == 1 || !p.ks.c[0].nulls);
   GbUnit<VT> cur, nxt;
-  if (gwarp < full_units) gb_load_unit<KM, true, VT>(p, gwarp * GB_UNIT_ROWS, lane, cur);
+  long long u = gwarp;
+  if (plain) {
+    if (u < full_units) gb_load_unit<KM, true, VT>(p, u * GB_UNIT_ROWS, lane, cur);
 #pragma unroll 1
-  for (long long u = gwarp; u < full_units; u += total_warps) {
-    if (u + total_warps < full_units) gb_load_unit<KM, true, VT>(p, (u + total_warps) * GB_UNIT_ROWS, lane, nxt);
-    gb_unit_body<NW, KM, VT, FLAGS>(p, sh, cur, u * GB_UNIT_ROWS);
-    cur = nxt;
+    for (; u < full_units; u += total_warps) {
+      if (u + total_warps < full_units) gb_load_unit<KM, true, VT>(p, (u + total_warps) * GB_UNIT_ROWS, lane, nxt);
+      gb_unit_body<NW, KM, VT, FLAGS, true>(p, sh, cur, u * GB_UNIT_ROWS);
+      cur = nxt;
+    }
   }
-  // The partial last unit (bounds-checked loads), by the warp whose turn it would be.
-  if (n % GB_UNIT_ROWS != 0 && gwarp == full_units % total_warps) {
-    gb_load_unit<KM, false, VT>(p, full_units * GB_UNIT_ROWS, lane, cur);
-    gb_unit_body<NW, KM, VT, FLAGS>(p, sh, cur, full_units * GB_UNIT_ROWS);
+  if (u < total_units) {
+    if (u < full_units) gb_load_unit<KM, true, VT>(p, u * GB_UNIT_ROWS, lane, cur); else gb_load_unit<KM, false, VT>(p, u * GB_UNIT_ROWS, lane, cur);
+  }
+#pragma unroll 1
+  for (; u < total_units; u += total_warps) {
+    const long long un = u + total_warps;
+    if (un < total_units) {
+      if (un < full_units) gb_load_unit<KM, true, VT>(p, un * GB_UNIT_ROWS, lane, nxt); else gb_load_unit<KM, false, VT>(p, un * GB_UNIT_ROWS, lane, nxt);
+    }
+    gb_unit_body<NW, KM, VT, FLAGS, false>(p, sh, cur, u * GB_UNIT_ROWS);
+    cur = nxt;
   }
   __syncthreads();
 
