@@ -434,3 +434,50 @@ def test_two_kernels_agree_at_scale(ctx):
         else:
             assert np.allclose(a[3][i], b[3][i], rtol=1e-12, atol=0)
     assert np.array_equal(a[3][4], a[1].astype(np.float64))
+
+
+# ---------------------------------------------------------------- multi-GPU plumbing on one GPU (world size 1)
+class _OneRankDist:
+    """torch.distributed look-alike for a single rank: every collective is a copy."""
+
+    @staticmethod
+    def get_world_size(): return 1
+    @staticmethod
+    def get_rank(): return 0
+    @staticmethod
+    def all_gather(outs, t): outs[0].copy_(t)
+    @staticmethod
+    def all_to_all_single(out, inp, output_split_sizes=None, input_split_sizes=None): out.copy_(inp)
+
+
+def test_dist_operators_single_rank(ctx, oracle):
+    # the CUDA backend of pandrs_b200/dist.py (device pointers <-> tensors, state rows, NULL re-packing, permuted
+    # gathers) with identity collectives must reproduce the single-GPU result; world size 2 runs under gloo on CPU
+    # (tests/test_dist_gloo.py) and under NCCL in bench.py --gpus 2
+    import torch
+    from pandrs_b200.dist import CudaBackend, DistGroupBy, DistJoin
+    n = 60_000
+    rng = np.random.default_rng(13)
+    k = Spec(pb.I64, rng.integers(0, 900, n), nulls=rng.random(n) < 0.02)
+    v = Spec(pb.F64, rng.normal(10, 3, n), nulls=rng.random(n) < 0.05)
+    aggs = [(0, op) for op in ALL6]
+    want = compare_groupby(pb, oracle, ctx, [k], [v], aggs)
+    kc, vc = ctx.upload(k.gpu(pb)), ctx.upload(v.gpu(pb))
+    for method in ("groupby_agg_lowcard", "groupby_agg_shuffle"):
+        r = getattr(DistGroupBy(ctx, _OneRankDist), method)([kc], [vc], aggs)
+        got = gpu_groupby_dict(pb, r, [k], len(aggs))
+        r.close()
+        assert got.keys() == want.keys()
+        for kt in want:
+            assert got[kt][0] == want[kt][0]
+            assert np.allclose(got[kt][1], want[kt][1], rtol=1e-12, atol=0), (method, kt)
+    L = Spec(pb.I64, rng.integers(0, 500, 5000), nulls=rng.random(5000) < 0.03)
+    R = Spec(pb.I64, rng.integers(0, 500, 1500), nulls=rng.random(1500) < 0.03)
+    lc, rc = ctx.upload(L.gpu(pb)), ctx.upload(R.gpu(pb))
+    for how in (pb.INNER, pb.LEFT):
+        gl, gr = DistJoin(ctx, _OneRankDist).join_pairs(lc, rc, how, 1000, 7000)
+        wl, wr = oracle.join(L.cpu(oracle), R.cpu(oracle), how)
+        wr = np.where(wr >= 0, wr + 7000, -1)
+        assert sorted(zip(gl.cpu().tolist(), gr.cpu().tolist())) == sorted(zip((wl + 1000).tolist(), wr.tolist()))
+    for c in (kc, vc, lc, rc):
+        ctx.free(c)
