@@ -114,6 +114,8 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "compat_filter_nulls")) c->opts.compat_filter_nulls = (int32_t)value;
   else if (!strcmp(name, "ng")) c->opt_ng = value;
   else if (!strcmp(name, "join_algo")) c->opt_join_algo = value;
+  else if (!strcmp(name, "join_log_nb")) c->opt_join_log_nb = value;
+  else if (!strcmp(name, "join_ctas_per_sm")) c->opt_join_ctas_per_sm = value;
   else if (!strcmp(name, "timing")) c->opt_timing = value;
   else if (!strcmp(name, "dense")) c->opt_dense = value;
   else return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown option '%s'", name);

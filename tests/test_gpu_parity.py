@@ -314,6 +314,29 @@ def test_join_unique_build_config3_shape(ctx, oracle, how):
         assert len(li) == npr
 
 
+@pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
+def test_join_radix_partitioned_path(ctx, oracle, how):
+    # large tables take the radix-partitioned path (L2-resident table regions); its pairs come out in bucket
+    # order, so they are compared after the canonical sort (north star: "compared after a canonical sort")
+    rng = np.random.default_rng(14)
+    ctx.set_option("join_algo", 2)
+    try:
+        L = Spec(pb.I64, rng.integers(0, 5000, 40_000), nulls=rng.random(40_000) < 0.05)
+        R = Spec(pb.I64, rng.integers(0, 5000, 9_000), nulls=rng.random(9_000) < 0.05)
+        compare_join(pb, oracle, ctx, L, R, how, check_order=False)
+        nb, npr = 300_000, 2_000_003
+        Ru = Spec(pb.I64, oracle.synth_join_keys(nb, unique=True))
+        Lu = Spec(pb.I64, oracle.synth_join_keys(npr, domain=2 * nb))
+        compare_join(pb, oracle, ctx, Lu, Ru, how, device=True, check_order=False)
+        assert ctx.stats()["groupby_algo_used"] == 2
+        pool = [f"k{i}" for i in range(300)]
+        Ld = Spec(pb.DICT_U32, rng.integers(0, 300, 5000).astype(np.uint32), pool=pool)
+        Rd = Spec(pb.DICT_U32, rng.integers(0, 300, 700).astype(np.uint32), pool=pool)
+        compare_join(pb, oracle, ctx, Ld, Rd, how, check_order=False)
+    finally:
+        ctx.set_option("join_algo", 0)
+
+
 @pytest.mark.parametrize("dtype", ["f64", "i32", "dict", "bool"])
 def test_join_other_key_types(ctx, oracle, dtype):
     rng = np.random.default_rng(8)
