@@ -36,6 +36,7 @@ struct pdrs_ctx {
   int64_t opt_join_log_nb = 0;         // 0 = auto (log2 of the number of radix buckets)
   int64_t opt_join_ctas_per_sm = 0;    // 0 = auto
   int64_t opt_timing = 1;              // record CUDA-event times in pdrs_stats
+  int64_t opt_radix = 1;               // allow the radix-partitioned high-cardinality groupby path
   int64_t opt_dense = 1;               // allow the direct-mapped path for small dense integer keys
 };
 

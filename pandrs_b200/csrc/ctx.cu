@@ -118,6 +118,7 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "join_ctas_per_sm")) c->opt_join_ctas_per_sm = value;
   else if (!strcmp(name, "timing")) c->opt_timing = value;
   else if (!strcmp(name, "dense")) c->opt_dense = value;
+  else if (!strcmp(name, "radix")) c->opt_radix = value;
   else return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown option '%s'", name);
   return PDRS_OK;
 }

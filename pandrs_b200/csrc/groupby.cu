@@ -208,6 +208,8 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
   return PDRS_OK;
 }
 
+int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, float* kernel_ms);   // gb_radix.cu
+
 // ---------------------------------------------------------------- dispatch helpers
 static int variant_of(const KeySpec& ks) {
   if (ks.nkeys == 1 && ks.c[0].dtype == PDRS_I64) return 0;   // k1
@@ -255,6 +257,7 @@ static int32_t alloc_table(pdrs_ctx* c, long long slots, int nwords, TableMem* t
   tm->t.kw2 = tm->kw2.as<u64>();
   tm->t.st = nullptr;
   tm->t.mask = (u64)slots - 1;
+  tm->t.shift = 64 - ilog2(slots);
   tm->t.slots = slots;
   tm->t.counters = tm->counters.as<u64>();
   return PDRS_OK;
@@ -412,6 +415,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   TableMem tm;
   std::vector<DevBuf> states(passes.size());
   u64 cn[CNT_N + 1] = {0};
+  bool radix_used = false;
+  (void)radix_used;
   for (int attempt = 0;; attempt++) {
     if (attempt > 6) return pdrs_fail(c, PDRS_ERR_OOM, "groupby: hash table kept overflowing after %d retries", attempt);
     bool use_shared = algo != PDRS_GB_GLOBAL;
@@ -441,6 +446,14 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           gp.gt.st = states[i].as<GState>();
           gp.val = vv[passes[i].val].data;
           gp.vnull = vv[passes[i].val].nulls;
+        }
+        // high cardinality, one 64-bit key column: radix-partitioned rows + L2-resident table regions (gb_radix.cu)
+        const size_t tbytes = (size_t)(slots + 1) * (sizeof(GHdr) + (gp.gt.st ? sizeof(GState) : 0));
+        if (!use_shared && variant == 0 && c->opt_radix != 0 && tbytes > (64ull << 20) && n >= (1 << 20)) {
+          float ms = 0;
+          int32_t rs = gb_radix_pass(c, gp, passes[i].is_int, passes[i].flags, &ms);
+          if (rs == PDRS_OK) { c->stats.main_kernel_ms += ms; c->stats.groupby_algo_used = PDRS_GB_GLOBAL; radix_used = true; continue; }
+          if (rs != PDRS_ERR_UNSUPPORTED) return rs;
         }
         if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
         if (use_shared) PDRS_CUDA(c, launch_shared(variant, cfgs[i], gp, smems[i], c->stream));

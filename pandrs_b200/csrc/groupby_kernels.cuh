@@ -62,7 +62,8 @@ struct GTable {
   u64* kw1;                      // [slots + 1] when nwords > 1
   u64* kw2;                      // [slots + 1] when nwords > 2
   GState* st;                    // [slots + 1] state of the value column of this pass (may be NULL)
-  u64 mask;                      // slots - 1
+  u64 mask;                      // slots - 1 (slots is a power of two)
+  int shift;                     // 64 - log2(slots): slot = hash >> shift, so that the radix buckets (top hash bits) own contiguous regions
   long long slots;
   u64* counters;                 // CNT_*
 };
@@ -205,7 +206,7 @@ __device__ __forceinline__ long long g_try_insert(const GTable& t, const u64 (&w
 // Returns the slot of the key (claiming a free one if needed), or -1 on overflow / for inactive lanes.
 template <int NW>
 __device__ __forceinline__ long long g_find_or_insert(const GTable& t, const u64 (&w)[NW], bool active) {
-  u64 slot = (key_hash<NW>(w) >> 20) & t.mask, probe = 0;
+  u64 slot = key_hash<NW>(w) >> t.shift, probe = 0;
   long long res = -1;
   bool pending = active;
   int rounds = 0;
@@ -886,6 +887,7 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
   cudaError_t gb_launch_shared_##tag(const GbCfg& c, const GbParams& p, size_t smem, cudaStream_t s);               \
   cudaError_t gb_launch_global_##tag(const GbCfg& c, const GbParams& p, cudaStream_t s);                            \
   cudaError_t gb_launch_sample_##tag(const GbParams& p, long long nblocks, long long stride_rows, int ctas, cudaStream_t s);
+struct GbPart;   // gb_radix.cu
 GB_DECLARE_VARIANT(k1)   // NW = 1, one 64-bit key column, direct loads
 GB_DECLARE_VARIANT(g1)   // NW = 1, generic packing
 GB_DECLARE_VARIANT(g2)   // NW = 2

@@ -195,6 +195,24 @@ def test_cardinalities_all_aggs(ctx, oracle, card, algo):
     assert len(got) == len(np.unique(k.values))
 
 
+@pytest.mark.parametrize("radix", [1, 0])
+def test_high_cardinality_radix_path(ctx, oracle, radix):
+    # BASELINE.json configs[1] "10M distinct" shape at oracle-sized n: the table (slots x 80 B) no longer fits L2, so
+    # rows are radix-partitioned first (gb_radix.cu); radix=0 forces the plain global-table kernel on the same data
+    n = 2_500_000
+    k, v = _synth(oracle, n, 700_000, scramble=True)
+    kn = np.zeros(n, bool)
+    kn[::1009] = True
+    k = Spec(pb.I64, k.values, nulls=kn)
+    ctx.set_option("radix", radix)
+    try:
+        got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+        st = ctx.stats()
+    finally:
+        ctx.set_option("radix", 1)
+    assert st["groupby_algo_used"] == pb.GB_GLOBAL and len(got) > 600_000
+
+
 @pytest.mark.parametrize("ops", [[pb.SUM], [pb.SUM, pb.MEAN, pb.COUNT], [pb.MIN, pb.MAX], [pb.STD], [pb.VAR, pb.MEAN], [pb.COUNT]])
 def test_agg_subsets_and_int_values(ctx, oracle, ops):
     n = 50_000
