@@ -1,0 +1,435 @@
+// Low / medium-cardinality groupby (tens to ~2000 groups, one 64-bit key column): tile sort + register reduction.
+//
+// Replaces the row loop of grouping.rs:62-104 and the per-group gathers of aggregation.rs:507-742.
+//
+// Measured on B200 (profiles/microbench2_r01.txt): a random shared-memory access costs ~2.6 SM-cycles per warp
+// instruction per 4 bytes and 64-bit shared atomics are CAS loops, so updating {S1, S2, min, max, n} per row in
+// shared memory costs >= 50 cycles per 32 rows, while the HBM roofline allows ~22.  This kernel touches shared
+// memory per row only to SORT the values of a tile by group:
+//
+//   phase 1  key -> group id (direct-mapped for dense integer keys, else a CTA-shared key table); one native
+//            32-bit shared atomic per row on the tile histogram, whose return value is the row's rank in its group
+//   phase 2  exclusive scan of the histogram (1024 threads, two barriers)
+//   phase 3  value -> sorted[offset[group] + rank]                      (one LDS.32 + one STS.64 per row)
+//   phase 4  every thread OWNS one (or two) groups for the whole kernel: it walks its segment of the sorted tile
+//            and keeps rows / n / pivot / S1 / S2 / min / max / isum in REGISTERS - all six aggregates cost the
+//            same single sequential read.  Segments longer than TS_HEAVY rows (skewed keys) are reduced by the
+//            owner's whole warp with shuffles.
+//
+// Keys are loaded with 128-bit streaming loads one tile ahead (registers); values arrive through one bulk
+// asynchronous copy (cp.async.bulk, completion on an mbarrier) per tile into a staging buffer, issued a whole
+// tile period before they are consumed.  At the end every thread flushes its groups into the global table as
+// one pre-aggregated batch (same state and finalisation as the other groupby kernels).
+#include <algorithm>
+#include <cstdio>
+
+#include "groupby_kernels.cuh"
+#ifdef TS_DEBUG
+#define TSDBG(...) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 2) printf(__VA_ARGS__); } while (0)
+#else
+#define TSDBG(...)
+#endif
+
+namespace {
+
+constexpr int TS_NT = 1024;              // threads per CTA (one CTA per SM)
+constexpr int TS_RPT = 8;                // rows per thread per tile
+constexpr int TS_T = TS_NT * TS_RPT;     // rows per tile
+constexpr int TS_WROWS = 32 * TS_RPT;    // rows per warp per tile
+constexpr int TS_HEAVY = 64;             // longer segments are reduced by the whole warp
+
+// Group id -> histogram position.  Swaps the two low 5-bit fields so that consecutive ids (dense keys, or
+// first-seen order under skew) are owned by different warps, while the lanes of a warp own consecutive positions.
+__device__ __forceinline__ uint32_t ts_perm(uint32_t g) { return ((g & 31u) << 5) | ((g >> 5) & 31u) | (g & ~1023u); }
+
+__device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(cnt) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct TsRows {
+  u64 k[TS_RPT];
+  uint32_t vnw, knw, fw;   // lane l holds bitmap word (l & 7) of the warp's 256 rows: value NULLs, key NULLs, filter & ~filter NULLs
+  uint32_t act;            // bit q: row q of this lane is inside the column
+};
+
+// Rows of one warp in one tile: load j, lane l -> rows wbase + 64 j + 2 l + {0, 1} (one 128-bit load).
+template <bool PLAIN>
+__device__ __forceinline__ void ts_load(const GbParams& p, long long wbase, int lane, TsRows& r) {
+  const long long n = p.n;
+  const u64* keys = reinterpret_cast<const u64*>(p.ks.c[0].data) + wbase + 2 * lane;
+  if (wbase + TS_WROWS <= n) {
+    r.act = (1u << TS_RPT) - 1u;
+#pragma unroll
+    for (int j = 0; j < TS_RPT / 2; j++) {
+      const ulonglong2 kk = ld_stream_v2(keys + 64 * j);
+      r.k[2 * j] = kk.x; r.k[2 * j + 1] = kk.y;
+    }
+  } else {
+    r.act = 0;
+#pragma unroll
+    for (int q = 0; q < TS_RPT; q++) {
+      const bool inb = wbase + 64 * (q >> 1) + 2 * lane + (q & 1) < n;
+      r.k[q] = inb ? __ldg(keys + 64 * (q >> 1) + (q & 1)) : 0ull;
+      if (inb) r.act |= 1u << q;
+    }
+  }
+  const long long w = (wbase >> 5) + (lane & 7);
+  const bool inb = w * 32 < n;           // bitmaps cover ceil(n / 64) * 8 bytes (pdrs_view_col)
+  r.vnw = (p.vnull && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.vnull) + w) : 0u;
+  if (!PLAIN) {
+    r.knw = (p.ks.c[0].nulls && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.ks.c[0].nulls) + w) : 0u;
+    uint32_t f = 0xFFFFFFFFu;
+    if (p.fbits) {   // filter keeps Some(true) rows only (data_ops.rs:49-55)
+      f = inb ? __ldg(reinterpret_cast<const uint32_t*>(p.fbits) + w) : 0u;
+      if (p.fnull && inb) f &= ~__ldg(reinterpret_cast<const uint32_t*>(p.fnull) + w);
+    }
+    r.fw = f;
+  }
+}
+
+template <typename VT, int FLAGS> struct TsAcc {
+  uint32_t rows, n;
+  u64 piv;            // pivot bits (LSB forced to 1), 0 = unset
+  double S1, S2;
+  VT mn, mx;
+  u64 isum;
+};
+
+// NaN operands never win a comparison, i.e. they are ignored like f64::min / f64::max do (aggregation.rs:649-674)
+template <typename VT, int FLAGS>
+__device__ __forceinline__ void ts_add(double& S1, double& S2, VT& mn, VT& mx, u64& isum, double pv, u64 bits) {
+  using T = ValTraits<VT>;
+  const VT v = T::from_bits(bits);
+  if (T::is_int) isum += bits;
+  if (FLAGS == GB_ALL) {
+    const double d = T::to_f64(v) - pv;
+    S1 += d;
+    S2 = fma(d, d, S2);
+    mn = v < mn ? v : mn;
+    mx = v > mx ? v : mx;
+  } else if (!T::is_int) {
+    S1 += T::to_f64(v);
+  }
+}
+
+// Histogram word of a group in a tile: low 16 bits = rows with a value (after the scan: offset of the group's
+// segment), high 16 bits = rows whose value is NULL.  One native atomic per row serves both counts.
+template <typename VT, int FLAGS, int GPT, bool DENSE, bool PLAIN>
+__global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
+  using T = ValTraits<VT>;
+  constexpr bool IS_INT = T::is_int;
+  constexpr bool ALL = FLAGS == GB_ALL;
+  constexpr int NP = TS_NT * GPT, NPAD = NP + 32;
+  constexpr uint32_t TRASH = NP + 8;                                 // histogram slot of rows that are not aggregated here
+  extern __shared__ __align__(128) unsigned char smem[];
+  u64* sorted = reinterpret_cast<u64*>(smem);                        // [TS_T]
+  u64* stage = sorted + TS_T;                                        // [TS_T]
+  uint32_t* H = reinterpret_cast<uint32_t*>(stage + TS_T);           // [2][NPAD]
+  uint32_t* wsum = H + 2 * NPAD;                                     // [32]
+  uint32_t* misc = wsum + 32;                                        // [4]  0: ids handed out
+  u64* mbar = reinterpret_cast<u64*>(misc + 4);                      // [2]
+  u64* ktab_key = mbar + 2;                                          // [S]  (hashed keys only)
+  const int S = p.sh_slots, cap = p.sh_cap;
+  uint32_t* ktab_id = reinterpret_cast<uint32_t*>(ktab_key + S);     // [S]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t a_mbar = sm_addr(mbar), a_stage = sm_addr(stage), a_sorted = sm_addr(sorted);
+  const long long n = p.n;
+  const long long ntiles = (n + TS_T - 1) / TS_T;
+  const u64* vals = reinterpret_cast<const u64*>(p.val);
+
+  for (int i = tid; i < 2 * NPAD; i += TS_NT) H[i] = 0;
+  if (!DENSE) for (int i = tid; i < S; i += TS_NT) ktab_id[i] = 0;
+  if (tid < 4) misc[tid] = 0;
+  if (tid == 0) { mbar_init(a_mbar, 1); fence_proxy_async(); }
+  __syncthreads();
+
+  TsAcc<VT, FLAGS> acc[GPT];
+#pragma unroll
+  for (int s = 0; s < GPT; s++) { acc[s].rows = 0; acc[s].n = 0; acc[s].piv = 0; acc[s].S1 = 0.0; acc[s].S2 = 0.0; acc[s].mn = T::min_init(); acc[s].mx = T::max_init(); acc[s].isum = 0; }
+
+  long long tile = blockIdx.x;
+  // values of tile `t` -> stage: one bulk copy when the tile is full, a plain copy loop otherwise
+  auto issue_vals = [&](long long t) {
+    if ((t + 1) * (long long)TS_T <= n) {
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(a_mbar, TS_T * 8);
+#pragma unroll
+        for (int c = 0; c < 4; c++) bulk_g2s(a_stage + c * (TS_T * 2), vals + t * TS_T + c * (TS_T / 4), TS_T * 2, a_mbar);
+      }
+    } else {
+      for (int i = tid; i < TS_T; i += TS_NT) { const long long row = t * TS_T + i; stage[i] = row < n ? __ldg(vals + row) : 0ull; }
+    }
+  };
+  TsRows r;
+  if (tile < ntiles) { issue_vals(tile); ts_load<PLAIN>(p, tile * TS_T + (long long)warp * TS_WROWS, lane, r); }
+  uint32_t tma_phase = 0;
+  const int sh2 = (2 * lane) & 31;
+  int b = 0;
+#pragma unroll 1
+  for (; tile < ntiles; tile += gridDim.x, b ^= 1) {
+    uint32_t* Hc = H + b * NPAD;
+    const uint32_t a_h = sm_addr(Hc);
+    const long long tbase = tile * TS_T;
+    const bool tile_full = tbase + TS_T <= n;
+    // ---- phase 1: group ids, tile histogram (the atomic's return value ranks the row inside its group)
+    uint32_t pack[TS_RPT];
+    uint32_t skipmask = 0, zeromask = 0, spillmask = 0;
+#pragma unroll
+    for (int q = 0; q < TS_RPT; q++) {
+      const int j = q >> 1, h = q & 1;
+      const int wsrc = 2 * j + (lane >> 4);                                   // bitmap word of this lane's chunk-j rows
+      bool vnull = (__shfl_sync(0xFFFFFFFFu, r.vnw, wsrc) >> (sh2 + h)) & 1u;
+      bool active = (r.act >> q) & 1u, knull = false;
+      if (!PLAIN) {
+        const uint32_t fword = __shfl_sync(0xFFFFFFFFu, r.fw, wsrc), kword = __shfl_sync(0xFFFFFFFFu, r.knw, wsrc);   // every lane shuffles: no short-circuit
+        active = active && ((fword >> (sh2 + h)) & 1u);
+        knull = (kword >> (sh2 + h)) & 1u;
+        if (p.compat_nulls && vnull) { vnull = false; zeromask |= 1u << q; }   // filter + compat_filter_nulls (data_ops.rs:64-71)
+      }
+      uint32_t gid = 0;
+      bool ok;
+      if (DENSE) {
+        const u64 off = r.k[q] - (u64)p.sh_dense_base;
+        ok = off < (u64)cap;
+        gid = (uint32_t)off;
+      } else {                            // CTA-shared key table: lock-free probes first, insertion in the slow path
+        uint32_t slot = (uint32_t)(key_hash<1>({r.k[q]}) >> (64 - p.sh_log_slots));
+        ok = false;
+        bool miss = false;
+#pragma unroll 1
+        for (int pr = 0; pr < 8 && !ok && !miss; pr++) {
+          const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
+          const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
+          if (idw == 0 || idw == SH_BUSY) miss = true;
+          else if (kk == r.k[q]) { ok = true; gid = idw - 1; }
+          slot = (slot + 1) & (S - 1);
+        }
+        const bool need = active && !knull && !ok;
+        if (__any_sync(0xFFFFFFFFu, need)) {
+          u64 w[1] = {r.k[q]};
+          const int id = sh_lookup<1>(ktab_key, ktab_id, misc, S, p.sh_log_slots, cap, w, need);
+          if (need && id >= 0) { ok = true; gid = (uint32_t)id; }
+        }
+      }
+      if (!PLAIN) { ok = ok && !knull; if (knull) { gid = (uint32_t)cap; ok = true; } }
+      if (active && !ok) spillmask |= 1u << q;
+      ok = ok && active;
+      const uint32_t pp = ok ? ts_perm(gid) : TRASH;
+      const uint32_t old = sm_atom_add32(a_h + pp * 4u, vnull ? 0x10000u : 1u);
+      if (!ok || vnull) skipmask |= 1u << q;
+      pack[q] = pp | (old << 16);
+    }
+    if (__any_sync(0xFFFFFFFFu, spillmask != 0)) {   // rare: key outside the dense range / CTA key table full -> global table
+#pragma unroll 1
+      for (int q = 0; q < TS_RPT; q++) {
+        const bool sp = (spillmask >> q) & 1u;
+        const long long row = tbase + warp * TS_WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
+        u64 vb = 0, kq = 0;
+        bool vnull = false;
+#pragma unroll
+        for (int qq = 0; qq < TS_RPT; qq++) if (qq == q) kq = r.k[qq];
+        if (sp) {
+          vb = __ldg(vals + row);
+          vnull = p.vnull && pdrs_bit(p.vnull, row);
+          if (vnull && p.compat_nulls) { vnull = false; vb = 0; }
+        }
+        gb_spill_rows<1, VT, FLAGS>(p.gt, kq, 0ull, 0ull, sp, p.count_rows != 0, !vnull, T::from_bits(vb));
+      }
+    }
+    TSDBG("b%d t%d tile %lld phase1 done skip %x spill %x\n", blockIdx.x, threadIdx.x, tile, skipmask, spillmask);
+    // keys (and bitmap words) of this CTA's next tile: in flight during phases 2-4
+    if (tile + gridDim.x < ntiles) ts_load<PLAIN>(p, (tile + gridDim.x) * TS_T + (long long)warp * TS_WROWS, lane, r);
+    __syncthreads();
+    // ---- phase 2: exclusive scan of the histogram (thread t owns entries [t * GPT, t * GPT + GPT))
+    {
+      uint32_t c[GPT], tsum = 0;
+#pragma unroll
+      for (int s = 0; s < GPT; s++) { c[s] = Hc[tid * GPT + s]; tsum += c[s] & 0xFFFFu; }
+      uint32_t incl = tsum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      uint32_t ws = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
+      const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
+      uint32_t run = (warp ? wprefix : 0u) + incl - tsum;
+#pragma unroll
+      for (int s = 0; s < GPT; s++) { Hc[tid * GPT + s] = run | (c[s] & 0xFFFF0000u); run += c[s] & 0xFFFFu; }
+      if (tid == TS_NT - 1) Hc[NP] = run;
+      // the other buffer was last read in phase 4 of the previous tile: clear it for the next one
+#pragma unroll
+      for (int s = 0; s < GPT; s++) H[(b ^ 1) * NPAD + tid + s * TS_NT] = 0;
+      __syncthreads();
+    }
+    TSDBG("b%d t%d tile %lld phase2 done\n", blockIdx.x, threadIdx.x, tile);
+    // ---- phase 3: scatter the values into group order
+    {
+      uint32_t pos[TS_RPT];
+#pragma unroll
+      for (int q = 0; q < TS_RPT; q++) pos[q] = (sm_ld32(a_h + (pack[q] & 0xFFFFu) * 4u) & 0xFFFFu) + (pack[q] >> 16);
+      if (tile_full) { while (!mbar_try_wait(a_mbar, tma_phase)) {} tma_phase ^= 1u; }
+      const uint32_t a_src = a_stage + (uint32_t)(warp * TS_WROWS + 2 * lane) * 8u;
+#pragma unroll
+      for (int j = 0; j < TS_RPT / 2; j++) {
+        const ulonglong2 vv = sm_ld128(a_src + 64 * 8 * j);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int q = 2 * j + h;
+          u64 v = h ? vv.y : vv.x;
+          if (!PLAIN) { if ((zeromask >> q) & 1u) v = 0; }
+          if (!((skipmask >> q) & 1u)) sm_st64(a_sorted + pos[q] * 8u, v);
+        }
+      }
+    }
+    __syncthreads();
+    TSDBG("b%d t%d tile %lld phase3 done\n", blockIdx.x, threadIdx.x, tile);
+    if (tile + gridDim.x < ntiles) issue_vals(tile + gridDim.x);   // stage is free: values of the next tile
+    // ---- phase 4: every thread reduces the segments of the groups it owns
+    bool heavy[GPT];
+    uint32_t hoff[GPT], hend[GPT];
+#pragma unroll
+    for (int s = 0; s < GPT; s++) {
+      const int pidx = tid + s * TS_NT;
+      const uint32_t h0 = Hc[pidx];
+      const uint32_t off = h0 & 0xFFFFu, end = Hc[pidx + 1] & 0xFFFFu;
+      const uint32_t len = end - off;
+      acc[s].rows += len + (h0 >> 16);
+      acc[s].n += len;
+      hoff[s] = off; hend[s] = end;
+      if (ALL && len && acc[s].piv == 0) {     // pivot = first finite value of the group seen by this CTA
+        for (uint32_t i = off; i < end; i++) {
+          const double x = T::to_f64(T::from_bits(sorted[i]));
+          if (is_finite_f64(x)) { acc[s].piv = (u64)__double_as_longlong(x) | 1ull; break; }
+        }
+      }
+      heavy[s] = len > TS_HEAVY;
+      if (!heavy[s]) {
+        const double pv = __longlong_as_double((long long)acc[s].piv);
+        double S1 = acc[s].S1, S2 = acc[s].S2;
+        VT mn = acc[s].mn, mx = acc[s].mx;
+        u64 isum = acc[s].isum;
+        uint32_t i = off;
+#pragma unroll 1
+        for (; i + 4 <= end; i += 4) {
+          const u64 x0 = sorted[i], x1 = sorted[i + 1], x2 = sorted[i + 2], x3 = sorted[i + 3];
+          ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, x0);
+          ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, x1);
+          ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, x2);
+          ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, x3);
+        }
+#pragma unroll 1
+        for (; i < end; i++) ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, sorted[i]);
+        acc[s].S1 = S1; acc[s].S2 = S2; acc[s].mn = mn; acc[s].mx = mx; acc[s].isum = isum;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < GPT; s++) {
+      unsigned hm = __ballot_sync(0xFFFFFFFFu, heavy[s]);
+      while (hm) {
+        const int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        const uint32_t o = __shfl_sync(0xFFFFFFFFu, hoff[s], src), e = __shfl_sync(0xFFFFFFFFu, hend[s], src);
+        const u64 pvb = __shfl_sync(0xFFFFFFFFu, acc[s].piv, src);
+        const double pv = __longlong_as_double((long long)pvb);
+        double S1 = 0.0, S2 = 0.0;
+        VT mn = T::min_init(), mx = T::max_init();
+        u64 isum = 0;
+        for (uint32_t i = o + lane; i < e; i += 32) ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, sorted[i]);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+          if (ALL || !IS_INT) S1 += __shfl_xor_sync(0xFFFFFFFFu, S1, d);
+          if (IS_INT) isum += __shfl_xor_sync(0xFFFFFFFFu, isum, d);
+          if (ALL) {
+            S2 += __shfl_xor_sync(0xFFFFFFFFu, S2, d);
+            const VT omn = T::from_bits(__shfl_xor_sync(0xFFFFFFFFu, T::to_bits(mn), d)), omx = T::from_bits(__shfl_xor_sync(0xFFFFFFFFu, T::to_bits(mx), d));
+            mn = omn < mn ? omn : mn;
+            mx = omx > mx ? omx : mx;
+          }
+        }
+        if (lane == src) {
+          acc[s].S1 += S1; acc[s].S2 += S2; acc[s].isum += isum;
+          if (ALL) { acc[s].mn = mn < acc[s].mn ? mn : acc[s].mn; acc[s].mx = mx > acc[s].mx ? mx : acc[s].mx; }
+        }
+      }
+    }
+    TSDBG("b%d t%d tile %lld phase4 done rows %u n %u\n", blockIdx.x, threadIdx.x, tile, acc[0].rows, acc[0].n);
+    // no barrier here: the next tile's phase 1 only touches the other histogram buffer, and its scatter into
+    // `sorted` comes after that tile's first barrier, which every thread reaches only after this phase
+  }
+  __syncthreads();
+
+  TSDBG("b%d t%d main loop done\n", blockIdx.x, threadIdx.x);
+  // ---- flush: one pre-aggregated batch per (CTA, group)
+  u64* idkey = sorted;      // id -> key (hashed keys)
+  if (!DENSE) {
+    for (int s = tid; s < S; s += TS_NT) { const uint32_t idw = ktab_id[s]; if (idw != 0 && idw != SH_BUSY) idkey[idw - 1] = ktab_key[s]; }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int s = 0; s < GPT; s++) {
+    const uint32_t gid = ts_perm((uint32_t)(tid + s * TS_NT));
+    const bool have = acc[s].rows != 0;
+    const bool nullgroup = have && gid == (uint32_t)cap;
+    u64 w[1] = {0};
+    if (have && !nullgroup) w[0] = DENSE ? (u64)p.sh_dense_base + gid : idkey[gid];
+    long long gs = g_find_or_insert<1>(p.gt, w, have && !nullgroup);
+    if (nullgroup) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
+    TSDBG("b%d t%d flush slot %lld have %d null %d\n", blockIdx.x, threadIdx.x, gs, (int)have, (int)nullgroup);
+    if (!have || gs < 0) continue;
+    if (p.count_rows) atomicAdd(&p.gt.hdr[gs].rowsw, (u64)acc[s].rows);
+    u64 mnc = 0, mxo = 0;
+    if (ALL && acc[s].n) { mnc = ~T::ord(acc[s].mn); mxo = T::ord(acc[s].mx); }
+    g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, (u64)acc[s].n, __longlong_as_double((long long)acc[s].piv), acc[s].piv != 0, acc[s].S1, acc[s].S2, acc[s].isum, mnc, mxo);
+    TSDBG("b%d t%d flushed\n", blockIdx.x, threadIdx.x);
+  }
+}
+
+template <typename VT, int FLAGS, int GPT>
+cudaError_t ts_launch3(const GbParams& p, int ctas, size_t smem, cudaStream_t s) {
+  const bool plain = !p.fbits && !p.compat_nulls && !p.ks.c[0].nulls;
+  auto k = gb_tsort_kernel<VT, FLAGS, GPT, true, true>;
+  if (p.sh_dense) k = plain ? gb_tsort_kernel<VT, FLAGS, GPT, true, true> : gb_tsort_kernel<VT, FLAGS, GPT, true, false>;
+  else k = plain ? gb_tsort_kernel<VT, FLAGS, GPT, false, true> : gb_tsort_kernel<VT, FLAGS, GPT, false, false>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<ctas, TS_NT, smem, s>>>(p);
+  return cudaGetLastError();
+}
+template <typename VT, int FLAGS>
+cudaError_t ts_launch2(const GbParams& p, int gpt, int ctas, size_t smem, cudaStream_t s) {
+  return gpt == 1 ? ts_launch3<VT, FLAGS, 1>(p, ctas, smem, s) : ts_launch3<VT, FLAGS, 2>(p, ctas, smem, s);
+}
+
+}  // namespace
+
+// Geometry: returns false when the group count does not fit (cap + 1 ids over 1024 * GPT owners).
+bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int* gpt, int* slots, size_t* smem) {
+  if (cap + 1 > 2 * TS_NT) return false;
+  const int g = cap + 1 <= TS_NT ? 1 : 2;
+  long long S = 0;
+  if (!dense) { S = 64; while (S < cap + cap / 2) S <<= 1; }
+  const size_t np = (size_t)TS_NT * g;
+  const size_t bytes = (size_t)TS_T * 16 + 2 * (np + 32) * 4 + 32 * 4 + 16 + 16 + (size_t)S * 12;
+  if (bytes > (size_t)smem_budget) return false;
+  *gpt = g; *slots = (int)S; *smem = bytes;
+  return true;
+}
+long long gb_tsort_tile_rows() { return TS_T; }
+
+cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int gpt, int ctas, size_t smem, cudaStream_t s) {
+  if (!is_int) return flags == GB_SUM ? ts_launch2<double, GB_SUM>(p, gpt, ctas, smem, s) : ts_launch2<double, GB_ALL>(p, gpt, ctas, smem, s);
+  return flags == GB_SUM ? ts_launch2<long long, GB_SUM>(p, gpt, ctas, smem, s) : ts_launch2<long long, GB_ALL>(p, gpt, ctas, smem, s);
+}

@@ -209,6 +209,10 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
 }
 
 int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, float* kernel_ms);   // gb_radix.cu
+// gb_tsort.cu
+bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int* gpt, int* slots, size_t* smem);
+long long gb_tsort_tile_rows();
+cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int gpt, int ctas, size_t smem, cudaStream_t s);
 
 // ---------------------------------------------------------------- dispatch helpers
 static int variant_of(const KeySpec& ks) {
@@ -409,8 +413,27 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     return true;
   };
 
+  // ---- tile-sort kernel (gb_tsort.cu): one 64-bit key column, tens to ~2000 groups
+  int ts_gpt = 0, ts_slots = 0;
+  size_t ts_smem = 0;
+  bool ts_dense = false;
+  long long ts_cap = 0;
+  bool ts_fit = false;
+  if (variant == 0 && c->opt_tsort != 0 && est >= c->opt_tsort_min_groups && n >= 4 * gb_tsort_tile_rows() && n < (1ll << 38) &&
+      (c->opts.groupby_algo == PDRS_GB_AUTO || c->opts.groupby_algo == PDRS_GB_TILESORT)) {
+    ts_dense = dense_ok && c->opt_dense != 0;
+    ts_cap = ts_dense ? dense_range + std::max<long long>(dense_range / 16, 8) : est + std::max<long long>(est / 16, 8);
+    // one group per thread when the keys seen by the sample fit 1023 ids (later keys outside the range spill)
+    const long long ts_seen = ts_dense ? dense_range : est;
+    if (ts_cap > 1023 && ts_seen <= 1023) ts_cap = 1023;
+    if (ts_cap > 2047 && ts_seen <= 2047) ts_cap = 2047;
+    ts_fit = gb_tsort_geometry(ts_cap, ts_dense, c->smem_optin, &ts_gpt, &ts_slots, &ts_smem);
+  }
+  if (c->opts.groupby_algo == PDRS_GB_TILESORT && !ts_fit && c->opts.groups_hint > 0)
+    return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "groupby_algo=TILESORT: needs one Int64 key column and at most ~2000 groups (estimated %lld)", est);
+
   int algo = c->opts.groupby_algo;
-  if (algo == PDRS_GB_DENSE) algo = PDRS_GB_SHARED;
+  if (algo == PDRS_GB_DENSE || algo == PDRS_GB_TILESORT) algo = PDRS_GB_SHARED;
   long long slots_mult = 1;
   TableMem tm;
   std::vector<DevBuf> states(passes.size());
@@ -429,7 +452,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
         if (!shared_geometry(passes[i], &gps[i], &cfgs[i], &smems[i])) { use_shared = false; break; }
       }
     }
-    if (!use_shared && algo == PDRS_GB_SHARED && attempt == 0 && c->opts.groups_hint > 0)
+    if (!use_shared && !ts_fit && algo == PDRS_GB_SHARED && attempt == 0 && c->opts.groups_hint > 0)
       return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "groupby_algo=SHARED: %lld groups do not fit shared memory", est);
     long long slots = std::max<long long>(1024, pow2ceil(2 * est + 1024)) * slots_mult;
     tm = TableMem();
@@ -455,8 +478,15 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           if (rs == PDRS_OK) { c->stats.main_kernel_ms += ms; c->stats.groupby_algo_used = PDRS_GB_GLOBAL; radix_used = true; continue; }
           if (rs != PDRS_ERR_UNSUPPORTED) return rs;
         }
+        const bool use_ts = ts_fit && algo != PDRS_GB_GLOBAL && passes[i].val >= 0;
         if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
-        if (use_shared) PDRS_CUDA(c, launch_shared(variant, cfgs[i], gp, smems[i], c->stream));
+        if (use_ts) {
+          gp.sh_cap = (int)ts_cap; gp.sh_slots = ts_slots; gp.sh_log_slots = ts_slots ? ilog2(ts_slots) : 0;
+          gp.sh_dense = ts_dense ? 1 : 0; gp.sh_dense_base = dense_base;
+          const long long tiles = (n + gb_tsort_tile_rows() - 1) / gb_tsort_tile_rows();
+          PDRS_CUDA(c, gb_tsort_launch(gp, passes[i].is_int, passes[i].flags, ts_gpt, (int)std::min<long long>(c->sm_count, tiles), ts_smem, c->stream));
+          c->stats.groupby_algo_used = PDRS_GB_TILESORT;
+        } else if (use_shared) PDRS_CUDA(c, launch_shared(variant, cfgs[i], gp, smems[i], c->stream));
         else {
           GbCfg cfg{ks.nwords, variant == 0 ? 0 : 1, passes[i].is_int, passes[i].flags, 8, 0};
           cfg.ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (n + 1023) / 1024));
@@ -473,11 +503,14 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
       }
     }
     PDRS_TRY(read_counters(c, tm, cn));
+#ifdef TS_DEBUG
+    fprintf(stderr, "attempt %d: ngroups %llu overflow %llu spilled %llu spinfail %llu nullslot %llx\n", attempt, cn[CNT_NGROUPS], cn[CNT_OVERFLOW], cn[CNT_SPILLED], cn[CNT_SPIN_FAIL], cn[CNT_N]);
+#endif
     c->stats.spilled_rows = (int64_t)cn[CNT_SPILLED];
     if (cn[CNT_OVERFLOW] == 0 && cn[CNT_SPIN_FAIL] == 0) break;
     c->stats.retries++;
     slots_mult *= 4;
-    if (use_shared && (long long)cn[CNT_SPILLED] > n / 16) algo = PDRS_GB_GLOBAL;
+    if ((use_shared || ts_fit) && (long long)cn[CNT_SPILLED] > n / 16) algo = PDRS_GB_GLOBAL;
     for (auto& s : states) s.release();
   }
 
