@@ -21,26 +21,19 @@
 // tile period before they are consumed.  At the end every thread flushes its groups into the global table as
 // one pre-aggregated batch (same state and finalisation as the other groupby kernels).
 #include <algorithm>
-#include <cstdio>
 
 #include "groupby_kernels.cuh"
-#ifdef TS_DEBUG
-#define TSDBG(...) do { if ((threadIdx.x & 31) == 0 && blockIdx.x < 2) printf(__VA_ARGS__); } while (0)
-#else
-#define TSDBG(...)
-#endif
 
 namespace {
 
-constexpr int TS_NT = 1024;              // threads per CTA (one CTA per SM)
-constexpr int TS_RPT = 8;                // rows per thread per tile
-constexpr int TS_T = TS_NT * TS_RPT;     // rows per tile
-constexpr int TS_WROWS = 32 * TS_RPT;    // rows per warp per tile
+constexpr int TS_T = 8192;               // rows per tile
 constexpr int TS_HEAVY = 64;             // longer segments are reduced by the whole warp
 
-// Group id -> histogram position.  Swaps the two low 5-bit fields so that consecutive ids (dense keys, or
-// first-seen order under skew) are owned by different warps, while the lanes of a warp own consecutive positions.
-__device__ __forceinline__ uint32_t ts_perm(uint32_t g) { return ((g & 31u) << 5) | ((g >> 5) & 31u) | (g & ~1023u); }
+// Group id -> histogram position.  XORs the low bits of the id into the warp field so that consecutive ids (dense
+// keys, or first-seen order under skew) are owned by different warps, while the lanes of a warp own consecutive
+// positions.  An involution: the same function maps a position back to its id.
+template <int NT>
+__device__ __forceinline__ uint32_t ts_perm(uint32_t g) { return g ^ ((g << 5) & (uint32_t)((NT / 32 - 1) << 5)); }
 
 __device__ __forceinline__ void mbar_init(uint32_t a, uint32_t cnt) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(cnt) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t a, uint32_t bytes) {
@@ -56,34 +49,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t a, uint32_t parity) {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-struct TsRows {
-  u64 k[TS_RPT];
-  uint32_t vnw, knw, fw;   // lane l holds bitmap word (l & 7) of the warp's 256 rows: value NULLs, key NULLs, filter & ~filter NULLs
+template <int RPT> struct TsRows {
+  u64 k[RPT];
+  uint32_t vnw, knw, fw;   // lane l holds bitmap word (l % RPT) of the warp's 32 * RPT rows: value NULLs, key NULLs, filter & ~filter NULLs
   uint32_t act;            // bit q: row q of this lane is inside the column
 };
 
 // Rows of one warp in one tile: load j, lane l -> rows wbase + 64 j + 2 l + {0, 1} (one 128-bit load).
-template <bool PLAIN>
-__device__ __forceinline__ void ts_load(const GbParams& p, long long wbase, int lane, TsRows& r) {
+template <int RPT, bool PLAIN>
+__device__ __forceinline__ void ts_load(const GbParams& p, long long wbase, int lane, TsRows<RPT>& r) {
   const long long n = p.n;
   const u64* keys = reinterpret_cast<const u64*>(p.ks.c[0].data) + wbase + 2 * lane;
-  if (wbase + TS_WROWS <= n) {
-    r.act = (1u << TS_RPT) - 1u;
+  if (wbase + 32 * RPT <= n) {
+    r.act = (1u << RPT) - 1u;
 #pragma unroll
-    for (int j = 0; j < TS_RPT / 2; j++) {
+    for (int j = 0; j < RPT / 2; j++) {
       const ulonglong2 kk = ld_stream_v2(keys + 64 * j);
       r.k[2 * j] = kk.x; r.k[2 * j + 1] = kk.y;
     }
   } else {
     r.act = 0;
 #pragma unroll
-    for (int q = 0; q < TS_RPT; q++) {
+    for (int q = 0; q < RPT; q++) {
       const bool inb = wbase + 64 * (q >> 1) + 2 * lane + (q & 1) < n;
       r.k[q] = inb ? __ldg(keys + 64 * (q >> 1) + (q & 1)) : 0ull;
       if (inb) r.act |= 1u << q;
     }
   }
-  const long long w = (wbase >> 5) + (lane & 7);
+  const long long w = (wbase >> 5) + (lane & (RPT - 1));
   const bool inb = w * 32 < n;           // bitmaps cover ceil(n / 64) * 8 bytes (pdrs_view_col)
   r.vnw = (p.vnull && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.vnull) + w) : 0u;
   if (!PLAIN) {
@@ -124,12 +117,13 @@ __device__ __forceinline__ void ts_add(double& S1, double& S2, VT& mn, VT& mx, u
 
 // Histogram word of a group in a tile: low 16 bits = rows with a value (after the scan: offset of the group's
 // segment), high 16 bits = rows whose value is NULL.  One native atomic per row serves both counts.
-template <typename VT, int FLAGS, int GPT, bool DENSE, bool PLAIN>
-__global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
+template <int NT, typename VT, int FLAGS, int GPT, bool DENSE, bool PLAIN>
+__global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
   using T = ValTraits<VT>;
   constexpr bool IS_INT = T::is_int;
   constexpr bool ALL = FLAGS == GB_ALL;
-  constexpr int NP = TS_NT * GPT, NPAD = NP + 32;
+  constexpr int RPT = TS_T / NT, WROWS = 32 * RPT, NWARPS = NT / 32;
+  constexpr int NP = NT * GPT, NPAD = NP + 32;
   constexpr uint32_t TRASH = NP + 8;                                 // histogram slot of rows that are not aggregated here
   extern __shared__ __align__(128) unsigned char smem[];
   u64* sorted = reinterpret_cast<u64*>(smem);                        // [TS_T]
@@ -146,9 +140,10 @@ __global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
   const long long n = p.n;
   const long long ntiles = (n + TS_T - 1) / TS_T;
   const u64* vals = reinterpret_cast<const u64*>(p.val);
+  const u64 dense_base = (u64)p.sh_dense_base;
 
-  for (int i = tid; i < 2 * NPAD; i += TS_NT) H[i] = 0;
-  if (!DENSE) for (int i = tid; i < S; i += TS_NT) ktab_id[i] = 0;
+  for (int i = tid; i < 2 * NPAD; i += NT) H[i] = 0;
+  if (!DENSE) for (int i = tid; i < S; i += NT) ktab_id[i] = 0;
   if (tid < 4) misc[tid] = 0;
   if (tid == 0) { mbar_init(a_mbar, 1); fence_proxy_async(); }
   __syncthreads();
@@ -168,13 +163,14 @@ __global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
         for (int c = 0; c < 4; c++) bulk_g2s(a_stage + c * (TS_T * 2), vals + t * TS_T + c * (TS_T / 4), TS_T * 2, a_mbar);
       }
     } else {
-      for (int i = tid; i < TS_T; i += TS_NT) { const long long row = t * TS_T + i; stage[i] = row < n ? __ldg(vals + row) : 0ull; }
+      for (int i = tid; i < TS_T; i += NT) { const long long row = t * TS_T + i; stage[i] = row < n ? __ldg(vals + row) : 0ull; }
     }
   };
-  TsRows r;
-  if (tile < ntiles) { issue_vals(tile); ts_load<PLAIN>(p, tile * TS_T + (long long)warp * TS_WROWS, lane, r); }
+  TsRows<RPT> r;
+  if (tile < ntiles) { issue_vals(tile); ts_load<RPT, PLAIN>(p, tile * TS_T + (long long)warp * WROWS, lane, r); }
   uint32_t tma_phase = 0;
   const int sh2 = (2 * lane) & 31;
+  const uint32_t vm0 = 1u << sh2, vm1 = 2u << sh2;      // this lane's two bits in a bitmap word
   int b = 0;
 #pragma unroll 1
   for (; tile < ntiles; tile += gridDim.x, b ^= 1) {
@@ -183,73 +179,109 @@ __global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
     const long long tbase = tile * TS_T;
     const bool tile_full = tbase + TS_T <= n;
     // ---- phase 1: group ids, tile histogram (the atomic's return value ranks the row inside its group)
-    uint32_t pack[TS_RPT];
-    uint32_t skipmask = 0, zeromask = 0, spillmask = 0;
+    uint32_t pack[RPT];
+    uint32_t skipmask = 0, zeromask = 0;
+    const bool fast = PLAIN && DENSE && __all_sync(0xFFFFFFFFu, r.act == (1u << RPT) - 1u);
+    if (fast) {
+      // every row is inside the column, no filter, no NULL keys, direct-mapped ids: ~16 instructions per row
+      bool bad = false;
 #pragma unroll
-    for (int q = 0; q < TS_RPT; q++) {
-      const int j = q >> 1, h = q & 1;
-      const int wsrc = 2 * j + (lane >> 4);                                   // bitmap word of this lane's chunk-j rows
-      bool vnull = (__shfl_sync(0xFFFFFFFFu, r.vnw, wsrc) >> (sh2 + h)) & 1u;
-      bool active = (r.act >> q) & 1u, knull = false;
-      if (!PLAIN) {
-        const uint32_t fword = __shfl_sync(0xFFFFFFFFu, r.fw, wsrc), kword = __shfl_sync(0xFFFFFFFFu, r.knw, wsrc);   // every lane shuffles: no short-circuit
-        active = active && ((fword >> (sh2 + h)) & 1u);
-        knull = (kword >> (sh2 + h)) & 1u;
-        if (p.compat_nulls && vnull) { vnull = false; zeromask |= 1u << q; }   // filter + compat_filter_nulls (data_ops.rs:64-71)
-      }
-      uint32_t gid = 0;
-      bool ok;
-      if (DENSE) {
-        const u64 off = r.k[q] - (u64)p.sh_dense_base;
-        ok = off < (u64)cap;
-        gid = (uint32_t)off;
-      } else {                            // CTA-shared key table: lock-free probes first, insertion in the slow path
-        uint32_t slot = (uint32_t)(key_hash<1>({r.k[q]}) >> (64 - p.sh_log_slots));
-        ok = false;
-        bool miss = false;
-#pragma unroll 1
-        for (int pr = 0; pr < 8 && !ok && !miss; pr++) {
-          const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
-          const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
-          if (idw == 0 || idw == SH_BUSY) miss = true;
-          else if (kk == r.k[q]) { ok = true; gid = idw - 1; }
-          slot = (slot + 1) & (S - 1);
-        }
-        const bool need = active && !knull && !ok;
-        if (__any_sync(0xFFFFFFFFu, need)) {
-          u64 w[1] = {r.k[q]};
-          const int id = sh_lookup<1>(ktab_key, ktab_id, misc, S, p.sh_log_slots, cap, w, need);
-          if (need && id >= 0) { ok = true; gid = (uint32_t)id; }
-        }
-      }
-      if (!PLAIN) { ok = ok && !knull; if (knull) { gid = (uint32_t)cap; ok = true; } }
-      if (active && !ok) spillmask |= 1u << q;
-      ok = ok && active;
-      const uint32_t pp = ok ? ts_perm(gid) : TRASH;
-      const uint32_t old = sm_atom_add32(a_h + pp * 4u, vnull ? 0x10000u : 1u);
-      if (!ok || vnull) skipmask |= 1u << q;
-      pack[q] = pp | (old << 16);
-    }
-    if (__any_sync(0xFFFFFFFFu, spillmask != 0)) {   // rare: key outside the dense range / CTA key table full -> global table
-#pragma unroll 1
-      for (int q = 0; q < TS_RPT; q++) {
-        const bool sp = (spillmask >> q) & 1u;
-        const long long row = tbase + warp * TS_WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
-        u64 vb = 0, kq = 0;
-        bool vnull = false;
+      for (int j = 0; j < RPT / 2; j++) {
+        const uint32_t vw = __shfl_sync(0xFFFFFFFFu, r.vnw, 2 * j + (lane >> 4));
 #pragma unroll
-        for (int qq = 0; qq < TS_RPT; qq++) if (qq == q) kq = r.k[qq];
-        if (sp) {
-          vb = __ldg(vals + row);
-          vnull = p.vnull && pdrs_bit(p.vnull, row);
-          if (vnull && p.compat_nulls) { vnull = false; vb = 0; }
+        for (int h = 0; h < 2; h++) {
+          const int q = 2 * j + h;
+          const u64 off = r.k[q] - dense_base;
+          const bool ok = off < (u64)cap;
+          const bool vnull = (vw & (h ? vm1 : vm0)) != 0;
+          const uint32_t pp = ok ? ts_perm<NT>((uint32_t)off) : TRASH;
+          const uint32_t old = sm_atom_add32(a_h + pp * 4u, vnull ? 0x10000u : 1u);
+          bad = bad || !ok;
+          if (!ok || vnull) skipmask |= 1u << q;
+          pack[q] = pp | (old << 16);
         }
-        gb_spill_rows<1, VT, FLAGS>(p.gt, kq, 0ull, 0ull, sp, p.count_rows != 0, !vnull, T::from_bits(vb));
+      }
+      if (__any_sync(0xFFFFFFFFu, bad)) {   // rare: key outside the dense range -> global table
+#pragma unroll 1
+        for (int q = 0; q < RPT; q++) {
+          u64 kq = 0;
+#pragma unroll
+          for (int qq = 0; qq < RPT; qq++) if (qq == q) kq = r.k[qq];
+          const bool sp = kq - dense_base >= (u64)cap;
+          const long long row = tbase + warp * WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
+          u64 vb = 0;
+          bool vnull = false;
+          if (sp) { vb = __ldg(vals + row); vnull = p.vnull && pdrs_bit(p.vnull, row); }
+          gb_spill_rows<1, VT, FLAGS>(p.gt, kq, 0ull, 0ull, sp, p.count_rows != 0, !vnull, T::from_bits(vb));
+        }
+      }
+    } else {
+      uint32_t spillmask = 0;
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        const int j = q >> 1, h = q & 1;
+        const int wsrc = 2 * j + (lane >> 4);                                   // bitmap word of this lane's chunk-j rows
+        bool vnull = (__shfl_sync(0xFFFFFFFFu, r.vnw, wsrc) & (h ? vm1 : vm0)) != 0;
+        bool active = (r.act >> q) & 1u, knull = false;
+        if (!PLAIN) {
+          const uint32_t fword = __shfl_sync(0xFFFFFFFFu, r.fw, wsrc), kword = __shfl_sync(0xFFFFFFFFu, r.knw, wsrc);   // every lane shuffles: no short-circuit
+          active = active && (fword & (h ? vm1 : vm0)) != 0;
+          knull = (kword & (h ? vm1 : vm0)) != 0;
+          if (p.compat_nulls && vnull) { vnull = false; zeromask |= 1u << q; }   // filter + compat_filter_nulls (data_ops.rs:64-71)
+        }
+        uint32_t gid = 0;
+        bool ok;
+        if (DENSE) {
+          const u64 off = r.k[q] - dense_base;
+          ok = off < (u64)cap;
+          gid = (uint32_t)off;
+        } else {                            // CTA-shared key table: lock-free probes first, insertion in the slow path
+          uint32_t slot = (uint32_t)(key_hash<1>({r.k[q]}) >> (64 - p.sh_log_slots));
+          ok = false;
+          bool miss = false;
+#pragma unroll 1
+          for (int pr = 0; pr < 8 && !ok && !miss; pr++) {
+            const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
+            const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
+            if (idw == 0 || idw == SH_BUSY) miss = true;
+            else if (kk == r.k[q]) { ok = true; gid = idw - 1; }
+            slot = (slot + 1) & (S - 1);
+          }
+          const bool need = active && !knull && !ok;
+          if (__any_sync(0xFFFFFFFFu, need)) {
+            u64 w[1] = {r.k[q]};
+            const int id = sh_lookup<1>(ktab_key, ktab_id, misc, S, p.sh_log_slots, cap, w, need);
+            if (need && id >= 0) { ok = true; gid = (uint32_t)id; }
+          }
+        }
+        if (!PLAIN) { ok = ok && !knull; if (knull) { gid = (uint32_t)cap; ok = true; } }
+        if (active && !ok) spillmask |= 1u << q;
+        ok = ok && active;
+        const uint32_t pp = ok ? ts_perm<NT>(gid) : TRASH;
+        const uint32_t old = sm_atom_add32(a_h + pp * 4u, vnull ? 0x10000u : 1u);
+        if (!ok || vnull) skipmask |= 1u << q;
+        pack[q] = pp | (old << 16);
+      }
+      if (__any_sync(0xFFFFFFFFu, spillmask != 0)) {   // rare: key outside the dense range / CTA key table full -> global table
+#pragma unroll 1
+        for (int q = 0; q < RPT; q++) {
+          const bool sp = (spillmask >> q) & 1u;
+          const long long row = tbase + warp * WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
+          u64 vb = 0, kq = 0;
+          bool vnull = false;
+#pragma unroll
+          for (int qq = 0; qq < RPT; qq++) if (qq == q) kq = r.k[qq];
+          if (sp) {
+            vb = __ldg(vals + row);
+            vnull = p.vnull && pdrs_bit(p.vnull, row);
+            if (vnull && p.compat_nulls) { vnull = false; vb = 0; }
+          }
+          gb_spill_rows<1, VT, FLAGS>(p.gt, kq, 0ull, 0ull, sp, p.count_rows != 0, !vnull, T::from_bits(vb));
+        }
       }
     }
-    TSDBG("b%d t%d tile %lld phase1 done skip %x spill %x\n", blockIdx.x, threadIdx.x, tile, skipmask, spillmask);
     // keys (and bitmap words) of this CTA's next tile: in flight during phases 2-4
-    if (tile + gridDim.x < ntiles) ts_load<PLAIN>(p, (tile + gridDim.x) * TS_T + (long long)warp * TS_WROWS, lane, r);
+    if (tile + gridDim.x < ntiles) ts_load<RPT, PLAIN>(p, (tile + gridDim.x) * TS_T + (long long)warp * WROWS, lane, r);
     __syncthreads();
     // ---- phase 2: exclusive scan of the histogram (thread t owns entries [t * GPT, t * GPT + GPT))
     {
@@ -261,29 +293,28 @@ __global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
       if (lane == 31) wsum[warp] = incl;
       __syncthreads();
-      uint32_t ws = wsum[lane];
+      uint32_t ws = lane < NWARPS ? wsum[lane] : 0u;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
       const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
       uint32_t run = (warp ? wprefix : 0u) + incl - tsum;
 #pragma unroll
       for (int s = 0; s < GPT; s++) { Hc[tid * GPT + s] = run | (c[s] & 0xFFFF0000u); run += c[s] & 0xFFFFu; }
-      if (tid == TS_NT - 1) Hc[NP] = run;
+      if (tid == NT - 1) Hc[NP] = run;
       // the other buffer was last read in phase 4 of the previous tile: clear it for the next one
 #pragma unroll
-      for (int s = 0; s < GPT; s++) H[(b ^ 1) * NPAD + tid + s * TS_NT] = 0;
+      for (int s = 0; s < GPT; s++) H[(b ^ 1) * NPAD + tid + s * NT] = 0;
       __syncthreads();
     }
-    TSDBG("b%d t%d tile %lld phase2 done\n", blockIdx.x, threadIdx.x, tile);
     // ---- phase 3: scatter the values into group order
     {
-      uint32_t pos[TS_RPT];
+      uint32_t pos[RPT];
 #pragma unroll
-      for (int q = 0; q < TS_RPT; q++) pos[q] = (sm_ld32(a_h + (pack[q] & 0xFFFFu) * 4u) & 0xFFFFu) + (pack[q] >> 16);
+      for (int q = 0; q < RPT; q++) pos[q] = (sm_ld32(a_h + (pack[q] & 0xFFFFu) * 4u) & 0xFFFFu) + (pack[q] >> 16);
       if (tile_full) { while (!mbar_try_wait(a_mbar, tma_phase)) {} tma_phase ^= 1u; }
-      const uint32_t a_src = a_stage + (uint32_t)(warp * TS_WROWS + 2 * lane) * 8u;
+      const uint32_t a_src = a_stage + (uint32_t)(warp * WROWS + 2 * lane) * 8u;
 #pragma unroll
-      for (int j = 0; j < TS_RPT / 2; j++) {
+      for (int j = 0; j < RPT / 2; j++) {
         const ulonglong2 vv = sm_ld128(a_src + 64 * 8 * j);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -295,14 +326,13 @@ __global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
       }
     }
     __syncthreads();
-    TSDBG("b%d t%d tile %lld phase3 done\n", blockIdx.x, threadIdx.x, tile);
     if (tile + gridDim.x < ntiles) issue_vals(tile + gridDim.x);   // stage is free: values of the next tile
     // ---- phase 4: every thread reduces the segments of the groups it owns
     bool heavy[GPT];
     uint32_t hoff[GPT], hend[GPT];
 #pragma unroll
     for (int s = 0; s < GPT; s++) {
-      const int pidx = tid + s * TS_NT;
+      const int pidx = tid + s * NT;
       const uint32_t h0 = Hc[pidx];
       const uint32_t off = h0 & 0xFFFFu, end = Hc[pidx + 1] & 0xFFFFu;
       const uint32_t len = end - off;
@@ -365,71 +395,70 @@ __global__ void __launch_bounds__(TS_NT, 1) gb_tsort_kernel(const GbParams p) {
         }
       }
     }
-    TSDBG("b%d t%d tile %lld phase4 done rows %u n %u\n", blockIdx.x, threadIdx.x, tile, acc[0].rows, acc[0].n);
     // no barrier here: the next tile's phase 1 only touches the other histogram buffer, and its scatter into
     // `sorted` comes after that tile's first barrier, which every thread reaches only after this phase
   }
   __syncthreads();
 
-  TSDBG("b%d t%d main loop done\n", blockIdx.x, threadIdx.x);
   // ---- flush: one pre-aggregated batch per (CTA, group)
   u64* idkey = sorted;      // id -> key (hashed keys)
   if (!DENSE) {
-    for (int s = tid; s < S; s += TS_NT) { const uint32_t idw = ktab_id[s]; if (idw != 0 && idw != SH_BUSY) idkey[idw - 1] = ktab_key[s]; }
+    for (int s = tid; s < S; s += NT) { const uint32_t idw = ktab_id[s]; if (idw != 0 && idw != SH_BUSY) idkey[idw - 1] = ktab_key[s]; }
     __syncthreads();
   }
 #pragma unroll
   for (int s = 0; s < GPT; s++) {
-    const uint32_t gid = ts_perm((uint32_t)(tid + s * TS_NT));
+    const uint32_t gid = ts_perm<NT>((uint32_t)(tid + s * NT));
     const bool have = acc[s].rows != 0;
     const bool nullgroup = have && gid == (uint32_t)cap;
     u64 w[1] = {0};
-    if (have && !nullgroup) w[0] = DENSE ? (u64)p.sh_dense_base + gid : idkey[gid];
+    if (have && !nullgroup) w[0] = DENSE ? dense_base + gid : idkey[gid];
     long long gs = g_find_or_insert<1>(p.gt, w, have && !nullgroup);
     if (nullgroup) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
-    TSDBG("b%d t%d flush slot %lld have %d null %d\n", blockIdx.x, threadIdx.x, gs, (int)have, (int)nullgroup);
     if (!have || gs < 0) continue;
     if (p.count_rows) atomicAdd(&p.gt.hdr[gs].rowsw, (u64)acc[s].rows);
     u64 mnc = 0, mxo = 0;
     if (ALL && acc[s].n) { mnc = ~T::ord(acc[s].mn); mxo = T::ord(acc[s].mx); }
     g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, (u64)acc[s].n, __longlong_as_double((long long)acc[s].piv), acc[s].piv != 0, acc[s].S1, acc[s].S2, acc[s].isum, mnc, mxo);
-    TSDBG("b%d t%d flushed\n", blockIdx.x, threadIdx.x);
   }
 }
 
-template <typename VT, int FLAGS, int GPT>
-cudaError_t ts_launch3(const GbParams& p, int ctas, size_t smem, cudaStream_t s) {
+template <int NT, typename VT, int FLAGS, int GPT>
+cudaError_t ts_launch4(const GbParams& p, int ctas, size_t smem, cudaStream_t s) {
   const bool plain = !p.fbits && !p.compat_nulls && !p.ks.c[0].nulls;
-  auto k = gb_tsort_kernel<VT, FLAGS, GPT, true, true>;
-  if (p.sh_dense) k = plain ? gb_tsort_kernel<VT, FLAGS, GPT, true, true> : gb_tsort_kernel<VT, FLAGS, GPT, true, false>;
-  else k = plain ? gb_tsort_kernel<VT, FLAGS, GPT, false, true> : gb_tsort_kernel<VT, FLAGS, GPT, false, false>;
+  auto k = gb_tsort_kernel<NT, VT, FLAGS, GPT, true, true>;
+  if (p.sh_dense) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, true, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, true, false>;
+  else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, false, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, false, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<ctas, TS_NT, smem, s>>>(p);
+  k<<<ctas, NT, smem, s>>>(p);
   return cudaGetLastError();
 }
 template <typename VT, int FLAGS>
-cudaError_t ts_launch2(const GbParams& p, int gpt, int ctas, size_t smem, cudaStream_t s) {
-  return gpt == 1 ? ts_launch3<VT, FLAGS, 1>(p, ctas, smem, s) : ts_launch3<VT, FLAGS, 2>(p, ctas, smem, s);
+cudaError_t ts_launch2(const GbParams& p, int nt, int gpt, int ctas, size_t smem, cudaStream_t s) {
+  if (nt == 1024) return gpt == 1 ? ts_launch4<1024, VT, FLAGS, 1>(p, ctas, smem, s) : ts_launch4<1024, VT, FLAGS, 2>(p, ctas, smem, s);
+  return gpt == 2 ? ts_launch4<512, VT, FLAGS, 2>(p, ctas, smem, s) : ts_launch4<512, VT, FLAGS, 4>(p, ctas, smem, s);
 }
 
 }  // namespace
 
-// Geometry: returns false when the group count does not fit (cap + 1 ids over 1024 * GPT owners).
-bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int* gpt, int* slots, size_t* smem) {
-  if (cap + 1 > 2 * TS_NT) return false;
-  const int g = cap + 1 <= TS_NT ? 1 : 2;
+// Geometry: cap + 1 group ids over nt * gpt owners (nt threads, gpt groups per thread).  Returns false when the
+// group count does not fit.  nt_pref: 0 = auto, else 512 / 1024.
+bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem) {
+  if (cap + 1 > 2048) return false;
+  const int t = nt_pref == 1024 ? 1024 : 512;
+  const int g = cap + 1 <= 1024 ? 1024 / t : 2048 / t;
   long long S = 0;
   if (!dense) { S = 64; while (S < cap + cap / 2) S <<= 1; }
-  const size_t np = (size_t)TS_NT * g;
+  const size_t np = (size_t)t * g;
   const size_t bytes = (size_t)TS_T * 16 + 2 * (np + 32) * 4 + 32 * 4 + 16 + 16 + (size_t)S * 12;
   if (bytes > (size_t)smem_budget) return false;
-  *gpt = g; *slots = (int)S; *smem = bytes;
+  *nt = t; *gpt = g; *slots = (int)S; *smem = bytes;
   return true;
 }
 long long gb_tsort_tile_rows() { return TS_T; }
 
-cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int gpt, int ctas, size_t smem, cudaStream_t s) {
-  if (!is_int) return flags == GB_SUM ? ts_launch2<double, GB_SUM>(p, gpt, ctas, smem, s) : ts_launch2<double, GB_ALL>(p, gpt, ctas, smem, s);
-  return flags == GB_SUM ? ts_launch2<long long, GB_SUM>(p, gpt, ctas, smem, s) : ts_launch2<long long, GB_ALL>(p, gpt, ctas, smem, s);
+cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int nt, int gpt, int ctas, size_t smem, cudaStream_t s) {
+  if (!is_int) return flags == GB_SUM ? ts_launch2<double, GB_SUM>(p, nt, gpt, ctas, smem, s) : ts_launch2<double, GB_ALL>(p, nt, gpt, ctas, smem, s);
+  return flags == GB_SUM ? ts_launch2<long long, GB_SUM>(p, nt, gpt, ctas, smem, s) : ts_launch2<long long, GB_ALL>(p, nt, gpt, ctas, smem, s);
 }

@@ -210,9 +210,9 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
 
 int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, float* kernel_ms);   // gb_radix.cu
 // gb_tsort.cu
-bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int* gpt, int* slots, size_t* smem);
+bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
-cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int gpt, int ctas, size_t smem, cudaStream_t s);
+cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int nt, int gpt, int ctas, size_t smem, cudaStream_t s);
 
 // ---------------------------------------------------------------- dispatch helpers
 static int variant_of(const KeySpec& ks) {
@@ -414,7 +414,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   };
 
   // ---- tile-sort kernel (gb_tsort.cu): one 64-bit key column, tens to ~2000 groups
-  int ts_gpt = 0, ts_slots = 0;
+  int ts_nt = 0, ts_gpt = 0, ts_slots = 0;
   size_t ts_smem = 0;
   bool ts_dense = false;
   long long ts_cap = 0;
@@ -427,7 +427,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     const long long ts_seen = ts_dense ? dense_range : est;
     if (ts_cap > 1023 && ts_seen <= 1023) ts_cap = 1023;
     if (ts_cap > 2047 && ts_seen <= 2047) ts_cap = 2047;
-    ts_fit = gb_tsort_geometry(ts_cap, ts_dense, c->smem_optin, &ts_gpt, &ts_slots, &ts_smem);
+    ts_fit = gb_tsort_geometry(ts_cap, ts_dense, c->smem_optin, (int)c->opt_tsort_threads, &ts_nt, &ts_gpt, &ts_slots, &ts_smem);
   }
   if (c->opts.groupby_algo == PDRS_GB_TILESORT && !ts_fit && c->opts.groups_hint > 0)
     return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "groupby_algo=TILESORT: needs one Int64 key column and at most ~2000 groups (estimated %lld)", est);
@@ -484,7 +484,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           gp.sh_cap = (int)ts_cap; gp.sh_slots = ts_slots; gp.sh_log_slots = ts_slots ? ilog2(ts_slots) : 0;
           gp.sh_dense = ts_dense ? 1 : 0; gp.sh_dense_base = dense_base;
           const long long tiles = (n + gb_tsort_tile_rows() - 1) / gb_tsort_tile_rows();
-          PDRS_CUDA(c, gb_tsort_launch(gp, passes[i].is_int, passes[i].flags, ts_gpt, (int)std::min<long long>(c->sm_count, tiles), ts_smem, c->stream));
+          PDRS_CUDA(c, gb_tsort_launch(gp, passes[i].is_int, passes[i].flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, tiles), ts_smem, c->stream));
           c->stats.groupby_algo_used = PDRS_GB_TILESORT;
         } else if (use_shared) PDRS_CUDA(c, launch_shared(variant, cfgs[i], gp, smems[i], c->stream));
         else {
@@ -503,9 +503,6 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
       }
     }
     PDRS_TRY(read_counters(c, tm, cn));
-#ifdef TS_DEBUG
-    fprintf(stderr, "attempt %d: ngroups %llu overflow %llu spilled %llu spinfail %llu nullslot %llx\n", attempt, cn[CNT_NGROUPS], cn[CNT_OVERFLOW], cn[CNT_SPILLED], cn[CNT_SPIN_FAIL], cn[CNT_N]);
-#endif
     c->stats.spilled_rows = (int64_t)cn[CNT_SPILLED];
     if (cn[CNT_OVERFLOW] == 0 && cn[CNT_SPIN_FAIL] == 0) break;
     c->stats.retries++;
