@@ -25,7 +25,7 @@ NULL_PER_MILLION = 50_000
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000_000, help="rows per GPU")
@@ -40,14 +40,16 @@ def parse():
 
 # ---------------------------------------------------------------- clocks
 class ClockSampler:
+    """nvidia-smi sampled every 20 ms from before the warm-up; the summary uses the samples that fall inside the
+    timed region (mark_begin / mark_end), or, if the region was shorter than one sample, the samples under load."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index=0):
-        self.samples, self.proc, self.index = [], None, index
+        self.samples, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -55,26 +57,42 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.05)
             self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for s in self.samples:
-            f = [x.strip() for x in s.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx = max(mx, float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+
+        def parse(rows):
+            sm, mx, reasons = [], 0, set()
+            for _, s in rows:
+                f = [x.strip() for x in s.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx = max(mx, float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            return sm, mx, reasons
+        inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1 + 0.03]
+        sm, mx, reasons = parse(inside)
+        where = "timed region"
+        if not sm:
+            sm, mx, reasons = parse(self.samples)
+            where = "whole run (timed region shorter than one sample)"
         sm.sort()
         hi = [x for x in sm if x > 0.5 * mx] or sm
-        return {"sm_mhz": hi[len(hi) // 2] if hi else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": hi[len(hi) // 2] if hi else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": where}
 
 
 # ---------------------------------------------------------------- the reference arm / CPU baseline
@@ -168,13 +186,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step()
-    launches0 = ctx.stats()["kernel_launches"]
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step()
+    launches0 = ctx.stats()["kernel_launches"]
     barrier()
+    clocks.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms = []
     e0.record(stream)
@@ -183,6 +202,7 @@ def main():
         kernel_ms.append(ctx.stats()["main_kernel_ms"])
     e1.record(stream)
     barrier()
+    clocks.mark_end()
     ms = e0.elapsed_time(e1)
     if dist is not None:
         t = torch.tensor([ms], device="cuda")
@@ -193,7 +213,7 @@ def main():
     ms_per_step = ms / args.steps
     value = n * world / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (gb_shared_kernel): algorithmic bytes / CUDA-event duration of that launch
+    # ---- roofline of the dominant kernel (gb_tsort_kernel at 1K groups): algorithmic bytes / CUDA-event duration of that launch
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -203,14 +223,14 @@ def main():
     k_ms = sum(kernel_ms) / len(kernel_ms)
     achieved = ALG_BYTES_PER_ROW * n / (k_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "gb_shared_kernel" if ctx.stats()["groupby_algo_used"] == pb.GB_SHARED else "gb_global_kernel",
+                "kernel": {pb.GB_TILESORT: "gb_tsort_kernel", pb.GB_SHARED: "gb_shared_kernel"}.get(ctx.stats()["groupby_algo_used"], "gb_global_kernel"),
                 "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json (of measured)" if peaks else "fallback 6.65 TB/s (of fallback)",
                 "alg_bytes_per_row": ALG_BYTES_PER_ROW}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
             tr = json.load(open(traffic_file))
-            roofline["traffic"] = tr.get("gb_shared_kernel_bytes_per_row", 0) * n or None
+            roofline["traffic"] = tr.get(roofline["kernel"] + "_bytes_per_row", 0) * n or None
         except Exception:
             pass
 
