@@ -180,7 +180,10 @@ int32_t pdrs_hash_partition(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, 
  * Replaces the build/probe part of OptimizedDataFrame::join_impl (split_dataframe/join.rs:107-208).
  * Emits index pairs (left_row, right_row); right_row = -1 stands for None (Left join, no match).
  * NULL keys never match and are dropped from BOTH sides, also for Left (join.rs:112,152).
- * Row order: left-row-major; the order of several matches of one left row is unspecified. */
+ * Row order: small inputs keep the reference's order (left-row-major, ascending right row).  Large inputs
+ * take the radix-partitioned path and emit the same multiset of pairs in an unspecified order; parity is
+ * defined after a canonical sort of the pairs (BASELINE.json north_star).  With unique build keys the
+ * result arrays are sized for one pair per left row; pdrs_join_len() gives the number of valid pairs. */
 int32_t pdrs_join_pairs(pdrs_ctx* ctx, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how,
                         pdrs_join_result** out);
 int64_t pdrs_join_len(const pdrs_join_result* r);

@@ -35,6 +35,10 @@ struct pdrs_ctx {
   int64_t opt_join_algo = 0;           // 0 = auto
   int64_t opt_join_log_nb = 0;         // 0 = auto (log2 of the number of radix buckets)
   int64_t opt_join_ctas_per_sm = 0;    // 0 = auto
+  int64_t opt_join_part = 0;           // 0 = auto (one-pass padded partition, exact two-pass on overflow), 2 = always two-pass
+  int64_t opt_join_slots_mult = 0;     // table slots per build row (0 = default 2)
+  int64_t opt_join_prefetch = 1;       // stream the next radix bucket's table region into L2 ahead of its first probes
+  int64_t opt_join_emit = 0;           // 0 = auto (single-pass probe + emit when the build keys are unique), 2 = always count / scan / write
   int64_t opt_timing = 1;              // record CUDA-event times in pdrs_stats
   int64_t opt_radix = 1;               // allow the radix-partitioned high-cardinality groupby path
   int64_t opt_dense = 1;               // allow the direct-mapped path for small dense integer keys

@@ -116,6 +116,10 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "join_algo")) c->opt_join_algo = value;
   else if (!strcmp(name, "join_log_nb")) c->opt_join_log_nb = value;
   else if (!strcmp(name, "join_ctas_per_sm")) c->opt_join_ctas_per_sm = value;
+  else if (!strcmp(name, "join_part")) c->opt_join_part = value;
+  else if (!strcmp(name, "join_emit")) c->opt_join_emit = value;
+  else if (!strcmp(name, "join_prefetch")) c->opt_join_prefetch = value;
+  else if (!strcmp(name, "join_slots_mult")) c->opt_join_slots_mult = value;
   else if (!strcmp(name, "timing")) c->opt_timing = value;
   else if (!strcmp(name, "dense")) c->opt_dense = value;
   else if (!strcmp(name, "radix")) c->opt_radix = value;

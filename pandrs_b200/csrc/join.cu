@@ -28,7 +28,11 @@
 
 typedef unsigned long long u64;
 
-struct JSlot { u64 key; long long head; };
+// Structure of arrays: a probe reads one 32-byte sector = the 4 keys of a bucket; the head word is read on a hit only.
+struct JTab { u64* keys; uint32_t* heads; u64 slots; };   // slots is a multiple of 4; index `slots` is the reserved slot of the all-ones key
+// head word: newest build row of the key (rows < 2^31), bit 31 = the key has more rows (chained through next[]), all ones = none
+static constexpr uint32_t JH_EMPTY = 0xFFFFFFFFu, JH_MULTI = 0x80000000u;
+__device__ __forceinline__ long long jhead_decode(uint32_t h) { return (long long)(h & ~JH_MULTI) | ((h & JH_MULTI) ? (1ll << 62) : 0ll); }
 static constexpr long long J_EMPTY = -1, J_BUSY = -2, J_NOMATCH = -1, J_NULLKEY = -3;
 static constexpr long long J_MULTI = 1ll << 62;
 #define JOIN_THREADS 256
@@ -36,15 +40,17 @@ static constexpr long long J_MULTI = 1ll << 62;
 
 struct JKeyCol { const void* data; const uint8_t* nulls; int dtype; };
 
-__device__ __forceinline__ u64 jhash(u64 k) {
-  u64 h = k * 0x9E3779B97F4A7C15ull;
-  h ^= h >> 32;
-  return h * 0xD6E8FEB86659FD93ull;
+// Top 32 bits of (fold(k) * odd constant): the fold brings the high word into the low one, so keys that differ only
+// in high bits still spread; the multiply carries every low bit into the top word.  3 integer multiplies.
+__device__ __forceinline__ uint32_t jhash32(u64 k) {
+  const uint32_t lo = (uint32_t)k ^ (uint32_t)(k >> 32), hi = (uint32_t)(k >> 32);
+  constexpr uint32_t CL = 0x7F4A7C15u, CH = 0x9E3779B9u;
+  return __umulhi(lo, CL) + lo * CH + hi * CL;
 }
 
 // slot = floor(hash_hi32 * slots / 2^32): monotone in the hash, so the rows of one radix bucket (top hash bits)
 // fall into one contiguous region of the table; `slots` need not be a power of two
-__device__ __forceinline__ u64 jslot(u64 key, u64 slots) { return (u64)__umulhi((uint32_t)(jhash(key) >> 32), (uint32_t)slots); }   // slots < 2^32
+__device__ __forceinline__ u64 jslot(u64 key, u64 slots) { return (u64)__umulhi(jhash32(key), (uint32_t)slots); }   // slots < 2^32
 
 // `Some(v) -> v.to_string()` equality restated on the physical values (join.rs:112-139)
 __device__ __forceinline__ bool jload_key(const JKeyCol& c, long long row, u64* k) {
@@ -76,56 +82,20 @@ __device__ __forceinline__ u64 ld_volatile_u64(const void* p) {
 
 // Rows come either straight from a key column (row id = position) or from a radix-partitioned copy
 // (canonical 64-bit keys + original row ids, NULL keys already dropped).
-struct JSrc { JKeyCol col; const u64* pkeys; const uint32_t* prows; };
+// Partitioned layouts: flat (bucket after bucket, cap == 0) or padded (bucket b owns positions [b * cap, b * cap + cnt[b]),
+// cap a multiple of every tile size, so that a tile never straddles two buckets).
+struct JSrc { JKeyCol col; const u64* pkeys; const uint32_t* prows; long long cap; const u64* cnt; int log_nb; };
+// end of the valid positions of the tile [lo, lo + tile)
+__device__ __forceinline__ long long jsrc_tile_hi(const JSrc& s, long long lo, long long tile, long long n) {
+  if (s.cap == 0) return min(n, lo + tile);
+  const long long b = lo / s.cap;
+  const long long c = min((long long)__ldg(s.cnt + b), s.cap);
+  return min(lo + tile, b * s.cap + c);
+}
 __device__ __forceinline__ bool jsrc_load(const JSrc& s, long long i, u64* key, long long* row) {
   if (s.pkeys) { *key = __ldcs(s.pkeys + i); *row = (long long)__ldcs(s.prows + i); return true; }
   *row = i;
   return jload_key(s.col, i, key);
-}
-
-// Insertion: the slot is claimed by a CAS on the key word itself (all-ones = empty), so there is no "being
-// published" state, nobody ever waits and no fence is needed (the probe runs in a later kernel).  Rows with the
-// same key are chained: head <- row (exchange), next[row] <- old head; next[] is pre-filled with -1 so that
-// unique keys never write it, and a second row of a key sets the MULTI flag of the head.
-// The one key whose bit pattern is all-ones lives in the reserved slot `slots` (never reached by probing).
-static constexpr u64 J_EMPTY_KEY = ~0ull;
-#define JB_TILE 2048
-__global__ void __launch_bounds__(256) join_build_kernel(JSlot* tab, u64 slots, long long* next, JSrc src, long long n, u64* fail) {
-  // tiles are handed out in order by a global counter (fail[1]): whatever the relative speed of the CTAs, the rows
-  // in flight form one contiguous window, i.e. they stay inside one or two radix buckets = L2-resident table regions
-  __shared__ long long sh_tile;
-  const long long ntiles = (n + JB_TILE - 1) / JB_TILE;
-  for (;;) {
-    if (threadIdx.x == 0) sh_tile = (long long)atomicAdd(&fail[1], 1ull);
-    __syncthreads();
-    const long long tile = sh_tile;
-    __syncthreads();
-    if (tile >= ntiles) break;
-    const long long hi = min(n, (tile + 1) * JB_TILE);
-    for (long long i = tile * JB_TILE + threadIdx.x; i < hi; i += blockDim.x) {
-      u64 key = 0;
-      long long r = 0;
-      if (!jsrc_load(src, i, &key, &r)) continue;
-      u64 slot = jslot(key, slots);
-      bool done = false;
-      if (key == J_EMPTY_KEY) slot = slots;
-      for (u64 probe = 0; probe <= slots; probe++) {
-        u64 k = key == J_EMPTY_KEY ? key : __ldcg(&tab[slot].key);
-        if (k == J_EMPTY_KEY && key != J_EMPTY_KEY) k = atomicCAS(&tab[slot].key, J_EMPTY_KEY, key), k = (k == J_EMPTY_KEY) ? key : k;
-        if (k == key) {
-          const long long old = (long long)atomicExch(reinterpret_cast<u64*>(&tab[slot].head), (u64)r);
-          if (old != J_EMPTY) {      // not the first row of this key: link, and flag the head
-            next[r] = old & ~J_MULTI;
-            atomicOr(reinterpret_cast<u64*>(&tab[slot].head), (u64)J_MULTI);
-          }
-          done = true;
-          break;
-        }
-        slot = slot + 1 >= slots ? 0 : slot + 1;
-      }
-      if (!done) atomicAdd(fail, 1ull);
-    }
-  }
 }
 
 // L2 cache policies: the table region of the current radix bucket must stay in L2 (evict_last) while the key /
@@ -135,27 +105,124 @@ __device__ __forceinline__ u64 l2_policy_evict_first() { u64 p; asm volatile("cr
 __device__ __forceinline__ u64 ld_stream_u64(const u64* a, u64 pol) { u64 v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(a), "l"(pol)); return v; }
 __device__ __forceinline__ void st_stream_u64(long long* a, long long v, u64 pol) { asm volatile("st.global.L1::no_allocate.L2::cache_hint.u64 [%0], %1, %2;" :: "l"(a), "l"(v), "l"(pol) : "memory"); }
 
-// Probing reads one 32-byte sector (two slots) per step: `slots` is even and pairs are sector-aligned.
-// Returns the head word of the matching slot or J_NOMATCH.
-__device__ __forceinline__ long long jprobe(const JSlot* tab, u64 slots, u64 key, u64 pol) {
-  if (key == J_EMPTY_KEY) { const long long h = (long long)__ldg(reinterpret_cast<const u64*>(&tab[slots].head)); return h == J_EMPTY ? J_NOMATCH : h; }
-  const uint32_t nslots = (uint32_t)slots;
-  const uint32_t home = (uint32_t)jslot(key, slots);
-  uint32_t pair = home & ~1u;
-  bool skip_even = home & 1u;          // the even slot of the first pair precedes the home slot: not part of the probe sequence
-  for (uint32_t step = 0; step <= nslots; step += 2) {
-    ulonglong4 s;
-    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(s.x), "=l"(s.y), "=l"(s.z), "=l"(s.w) : "l"(tab + pair), "l"(pol));
-    if (!skip_even) {
-      if (s.x == key) return (long long)s.y;
-      if (s.x == J_EMPTY_KEY) return J_NOMATCH;
+// Cold table regions: the first probes (or inserts) of a radix bucket miss L2 and would fetch the region from DRAM one
+// random 32-byte sector at a time.  Instead every tile streams the matching slice of the NEXT bucket's region (keys
+// and head words) into L2 with full-line loads and the evict_last policy; the loaded values are not used.
+__device__ __forceinline__ void jprefetch_next_region(const JTab& t, const JSrc& s, long long lo, long long tile, u64 pol, int tid, int nthreads) {
+  if (s.cap == 0 || s.log_nb == 0) return;
+  const long long b = lo / s.cap, nb = 1ll << s.log_nb;
+  if (b + 1 >= nb) return;
+  const long long cnt = max(1ll, min((long long)__ldg(s.cnt + b), s.cap));
+  const long long p0 = lo - b * s.cap, p1 = min(p0 + tile, cnt);
+  if (p0 >= cnt) return;
+  const int sh = 32 - s.log_nb;
+  const u64 s0 = (u64)__umulhi((uint32_t)((b + 1) << sh), (uint32_t)t.slots) & ~3ull;
+  const u64 s1 = b + 2 >= nb ? t.slots : ((u64)__umulhi((uint32_t)((b + 2) << sh), (uint32_t)t.slots) & ~3ull);
+  u64 a = s0 + (u64)((double)(s1 - s0) * ((double)p0 / (double)cnt));
+  u64 e = s0 + (u64)((double)(s1 - s0) * ((double)p1 / (double)cnt)) + 16;
+  a &= ~15ull;                                   // 16 slots = one 128-byte line of keys (and of heads)
+  if (e > s1) e = s1;
+  for (u64 x = a + 2ull * tid; x < e; x += 2ull * nthreads) {
+    ulonglong2 k;
+    u64 h;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(k.x), "=l"(k.y) : "l"(t.keys + x), "l"(pol));
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(h) : "l"(t.heads + x), "l"(pol));
+  }
+}
+
+// Insertion: the slot is claimed by a CAS on the key word itself (all-ones = empty), so there is no "being
+// published" state, nobody ever waits and no fence is needed (the probe runs in a later kernel).  Rows with the
+// same key are chained: head <- row (exchange), next[row] <- old head; next[] is pre-filled with -1 so that
+// unique keys never write it, and a second row of a key sets the MULTI flag of the head.
+// The one key whose bit pattern is all-ones lives in the reserved slot `slots` (never reached by probing).
+static constexpr u64 J_EMPTY_KEY = ~0ull;
+#define JB_TILE 256    // rows per ticket: ~4700 resident warps x 256 rows keep the window of rows in flight inside one or two radix buckets
+#define JB_ITEMS 4
+__global__ void __launch_bounds__(256) join_build_kernel(JTab t, long long* next, JSrc src, long long n, u64* fail) {
+  // Every warp works on its own.  Tiles are handed out in order by a global counter (fail[1]): whatever the relative
+  // speed of the warps, the rows in flight form one contiguous window, i.e. they stay inside one or two radix
+  // buckets = L2-resident table regions.  A lane keeps JB_ITEMS insertions in flight (claim CAS, then head exchange).
+  const long long ntiles = (n + JB_TILE - 1) / JB_TILE;
+  const u64 slots = t.slots;
+  const u64 pol_keep = l2_policy_evict_last();
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(&fail[1], 1ull);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    if (tile >= ntiles) break;
+    const long long hi = jsrc_tile_hi(src, tile * JB_TILE, JB_TILE, n);
+    jprefetch_next_region(t, src, tile * JB_TILE, JB_TILE, pol_keep, lane, 32);
+    for (long long i0 = tile * JB_TILE + lane; i0 < hi; i0 += 32 * JB_ITEMS) {
+      u64 key[JB_ITEMS], slot[JB_ITEMS], seen[JB_ITEMS];
+      long long r[JB_ITEMS];
+      uint32_t live = 0;
+#pragma unroll
+      for (int j = 0; j < JB_ITEMS; j++) {
+        const long long i = i0 + 32 * j;
+        key[j] = 0; r[j] = 0;
+        if (i < hi && jsrc_load(src, i, &key[j], &r[j])) live |= 1u << j;
+        slot[j] = key[j] == J_EMPTY_KEY ? slots : (jslot(key[j], slots) & ~3ull);   // the probe sequence starts at the first slot of the home bucket
+      }
+      // claim: CAS straight away (the home slot is free for most keys at load factor 1/3)
+      uint32_t todo = live;
+      for (u64 probe = 0; todo && probe <= slots; probe++) {
+#pragma unroll
+        for (int j = 0; j < JB_ITEMS; j++)
+          if ((todo >> j) & 1u) seen[j] = key[j] == J_EMPTY_KEY ? key[j] : atomicCAS(&t.keys[slot[j]], J_EMPTY_KEY, key[j]);
+#pragma unroll
+        for (int j = 0; j < JB_ITEMS; j++) {
+          if (!((todo >> j) & 1u)) continue;
+          if (seen[j] == J_EMPTY_KEY || seen[j] == key[j]) todo &= ~(1u << j);
+          else slot[j] = slot[j] + 1 >= slots ? 0 : slot[j] + 1;
+        }
+      }
+      if (todo) { atomicAdd(fail, (u64)__popc(todo)); live &= ~todo; }
+      uint32_t old[JB_ITEMS];
+#pragma unroll
+      for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) old[j] = atomicExch(&t.heads[slot[j]], (uint32_t)r[j]);
+#pragma unroll
+      for (int j = 0; j < JB_ITEMS; j++) {
+        if (!((live >> j) & 1u) || old[j] == JH_EMPTY) continue;
+        atomicAdd(&fail[3], 1ull);       // duplicate build keys: link, flag the head; the single-pass probe does not apply
+        next[r[j]] = (long long)(old[j] & ~JH_MULTI);
+        atomicOr(&t.heads[slot[j]], JH_MULTI);
+      }
     }
-    if (s.z == key) return (long long)s.w;
-    if (s.z == J_EMPTY_KEY) return J_NOMATCH;
-    skip_even = false;
-    pair = pair + 2 >= nslots ? 0 : pair + 2;
+  }
+}
+
+__device__ __forceinline__ ulonglong4 ld_bucket(const u64* p, u64 pol) {
+  ulonglong4 s;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0, %1, %2, %3}, [%4], %5;" : "=l"(s.x), "=l"(s.y), "=l"(s.z), "=l"(s.w) : "l"(p), "l"(pol));
+  return s;
+}
+// index (0..3) of `key` in a bucket, 4 = the bucket ends the probe sequence, 5 = go on with the next bucket.
+// Insertion always takes the first empty slot of the sequence, so the occupied slots of a bucket form a prefix:
+// the sequence ends inside this bucket iff its last slot is empty.
+__device__ __forceinline__ int jbucket_find(const ulonglong4& b, u64 key) {
+  int f = b.w == J_EMPTY_KEY ? 4 : 5;
+  f = b.w == key ? 3 : f;
+  f = b.z == key ? 2 : f;
+  f = b.y == key ? 1 : f;
+  f = b.x == key ? 0 : f;
+  return f;
+}
+// Probing reads one 32-byte sector (the four keys of a bucket) per step.  Returns the head word of the matching
+// slot or J_NOMATCH.
+__device__ __forceinline__ long long jprobe_from(const JTab& t, uint32_t bkt, u64 key, u64 pol) {
+  const uint32_t nslots = (uint32_t)t.slots;
+  for (uint32_t step = 0; step <= nslots; step += 4) {
+    const int f = jbucket_find(ld_bucket(t.keys + bkt, pol), key);
+    if (f < 4) return jhead_decode(__ldg(t.heads + bkt + f));
+    if (f == 4) return J_NOMATCH;
+    bkt = bkt + 4 >= nslots ? 0 : bkt + 4;
   }
   return J_NOMATCH;
+}
+__device__ __forceinline__ long long jprobe(const JTab& t, u64 key, u64 pol) {
+  if (key == J_EMPTY_KEY) { const uint32_t h = __ldg(&t.heads[t.slots]); return h == JH_EMPTY ? J_NOMATCH : jhead_decode(h); }
+  return jprobe_from(t, (uint32_t)jslot(key, t.slots) & ~3u, key, pol);
 }
 
 __device__ __forceinline__ long long jcount(long long stash, const long long* next, int left_join) {
@@ -172,7 +239,7 @@ __device__ __forceinline__ long long jcount(long long stash, const long long* ne
 // work inside the same radix bucket at any time (L2-resident table region).
 #define JOIN_TILE (JOIN_THREADS * JOIN_ITEMS * 4)
 
-__global__ void __launch_bounds__(JOIN_THREADS) join_probe_kernel(const JSlot* __restrict__ tab, u64 slots, const long long* __restrict__ next, JSrc src, long long n,
+__global__ void __launch_bounds__(JOIN_THREADS) join_probe_kernel(JTab tab, const long long* __restrict__ next, JSrc src, long long n,
                                                                   int left_join, long long* __restrict__ stash, u64* __restrict__ tile_counts, u64* __restrict__ tile_ctr) {
   __shared__ u64 wsum[JOIN_THREADS / 32];
   const long long ntiles = (n + JOIN_TILE - 1) / JOIN_TILE;
@@ -184,7 +251,8 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_probe_kernel(const JSlot* _
     __syncthreads();
     const long long tile = sh_tile;
     if (tile >= ntiles) break;
-    const long long lo = tile * JOIN_TILE, hi = min(n, lo + JOIN_TILE);
+    const long long lo = tile * JOIN_TILE, hi = jsrc_tile_hi(src, lo, JOIN_TILE, n);
+    jprefetch_next_region(tab, src, lo, JOIN_TILE, pol_keep, threadIdx.x, blockDim.x);
     u64 cnt = 0;
     for (long long i0 = lo + threadIdx.x; i0 < hi; i0 += (long long)JOIN_THREADS * JOIN_ITEMS) {
       u64 key[JOIN_ITEMS];
@@ -197,7 +265,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_probe_kernel(const JSlot* _
       }
       long long st[JOIN_ITEMS];
 #pragma unroll
-      for (int j = 0; j < JOIN_ITEMS; j++) st[j] = ok[j] ? jprobe(tab, slots, key[j], pol_keep) : J_NULLKEY;
+      for (int j = 0; j < JOIN_ITEMS; j++) st[j] = ok[j] ? jprobe(tab, key[j], pol_keep) : J_NULLKEY;
 #pragma unroll
       for (int j = 0; j < JOIN_ITEMS; j++) {
         long long i = i0 + (long long)j * JOIN_THREADS;
@@ -238,14 +306,15 @@ __global__ void join_scan_kernel(u64* v, int n, u64* total) {   // exclusive sca
 }
 
 __global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long long* __restrict__ stash, const long long* __restrict__ next, long long n, int left_join,
-                                                                  const u64* __restrict__ tile_offsets, const uint32_t* __restrict__ prows,
+                                                                  const u64* __restrict__ tile_offsets, JSrc src,
                                                                   long long* __restrict__ out_l, long long* __restrict__ out_r) {
+  const uint32_t* __restrict__ prows = src.prows;
   __shared__ u64 wsum[JOIN_THREADS / 32];
   __shared__ u64 sh_base;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long ntiles = (n + JOIN_TILE - 1) / JOIN_TILE;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const long long lo = tile * JOIN_TILE, hi = min(n, lo + JOIN_TILE);
+    const long long lo = tile * JOIN_TILE, hi = jsrc_tile_hi(src, lo, JOIN_TILE, n);
     if (threadIdx.x == 0) sh_base = tile_offsets[tile];
     __syncthreads();
     // thread t owns JOIN_ITEMS consecutive rows of every chunk, so positions are monotone in the row position
@@ -296,7 +365,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long lon
 #define JP_TILE (JP_THREADS * JP_ITEMS)
 #define JP_MAX_BUCKETS 1024
 
-__device__ __forceinline__ uint32_t jbucket(u64 key, int log_nb) { return (uint32_t)(jhash(key) >> (64 - log_nb)); }
+__device__ __forceinline__ uint32_t jbucket(u64 key, int log_nb) { return jhash32(key) >> (32 - log_nb); }
 
 __global__ void __launch_bounds__(JP_THREADS) jpart_hist_kernel(JKeyCol col, long long n, int log_nb, u64* __restrict__ hist) {
   __shared__ uint32_t sh[JP_MAX_BUCKETS];
@@ -380,6 +449,228 @@ __global__ void __launch_bounds__(JP_THREADS, 4) jpart_scatter_kernel(JKeyCol co
   }
 }
 
+// ---------------------------------------------------------------- one-pass radix partition into padded buckets
+// No histogram pass: bucket b owns the fixed range [b * cap, (b + 1) * cap) of the output (cap = expected rows per
+// bucket + slack; the hash spreads distinct keys evenly, heavy duplicates can overflow -> the caller falls back to
+// the exact two-pass partition above).  Per tile of 8192 rows: shared-memory histogram whose atomics return the
+// row's rank, one global reservation per bucket, rows staged in shared memory in bucket order, then every bucket's
+// run (8192 / nb rows) is written out contiguously.  2 CTAs per SM overlap each other's barriers.
+#define JQ_NT 1024
+#define JQ_ITEMS 8
+#define JQ_TILE (JQ_NT * JQ_ITEMS)
+__global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long n, int log_nb, long long cap, u64* __restrict__ cursor,
+                                                          u64* __restrict__ out_keys, uint32_t* __restrict__ out_rows, u64* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char jsm[];
+  u64* st_key = reinterpret_cast<u64*>(jsm);                                 // [JQ_TILE]
+  uint32_t* st_row = reinterpret_cast<uint32_t*>(st_key + JQ_TILE);         // [JQ_TILE]
+  uint32_t* H = st_row + JQ_TILE;                                           // [1024 + 32] counts -> exclusive offsets
+  uint32_t* G = H + 1056;                                                   // [1024] reserved start inside the bucket
+  __shared__ uint32_t wsum[32];
+  const int nb = 1 << log_nb;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool fast = col.dtype == PDRS_I64 && !col.nulls;
+  for (long long t0 = (long long)blockIdx.x * JQ_TILE; t0 < n; t0 += (long long)gridDim.x * JQ_TILE) {
+    H[tid] = 0;
+    __syncthreads();
+    u64 key[JQ_ITEMS];
+    uint32_t br[JQ_ITEMS];            // bucket << 16 | rank inside the bucket (tile <= 8192 rows); all ones = no row
+    if (fast && t0 + JQ_TILE <= n) {
+#pragma unroll
+      for (int j = 0; j < JQ_ITEMS; j++) key[j] = (u64)__ldcs((const long long*)col.data + t0 + (long long)j * JQ_NT + tid);
+#pragma unroll
+      for (int j = 0; j < JQ_ITEMS; j++) { const uint32_t b = jbucket(key[j], log_nb); br[j] = (b << 16) | atomicAdd(&H[b], 1u); }
+    } else {
+#pragma unroll
+      for (int j = 0; j < JQ_ITEMS; j++) {
+        const long long i = t0 + (long long)j * JQ_NT + tid;
+        br[j] = 0xFFFFFFFFu;
+        if (i < n && jload_key(col, i, &key[j])) { const uint32_t b = jbucket(key[j], log_nb); br[j] = (b << 16) | atomicAdd(&H[b], 1u); }
+      }
+    }
+    __syncthreads();
+    {   // exclusive scan of the bucket counts (thread b owns bucket b) + one global reservation per bucket
+      const uint32_t c = tid < nb ? H[tid] : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+      if (lane == 31) wsum[warp] = incl;
+      uint32_t g = 0;
+      if (c) {
+        const u64 at = atomicAdd(&cursor[tid], (u64)c);
+        if (at + c > (u64)cap) { atomicAdd(overflow, 1ull); g = 0xFFFFFFFFu; } else g = (uint32_t)at;
+      }
+      __syncthreads();
+      uint32_t ws = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
+      const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
+      const uint32_t excl = (warp ? wprefix : 0u) + incl - c;
+      H[tid] = excl;
+      if (tid == JQ_NT - 1) H[JQ_NT] = excl + c;
+      G[tid] = g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < JQ_ITEMS; j++) {
+      if (br[j] == 0xFFFFFFFFu) continue;
+      const uint32_t pos = H[br[j] >> 16] + (br[j] & 0xFFFFu);
+      st_key[pos] = key[j];
+      st_row[pos] = (uint32_t)(t0 + (long long)j * JQ_NT + tid);
+    }
+    __syncthreads();
+    for (int b = warp; b < nb; b += JQ_NT / 32) {     // one warp per bucket run
+      const uint32_t off = H[b], cnt = H[b + 1] - off, g = G[b];
+      if (g == 0xFFFFFFFFu) continue;                 // overflow: the caller discards this partition
+      const long long dst = (long long)b * cap + g;
+      for (uint32_t i = lane; i < cnt; i += 32) { out_keys[dst + i] = st_key[off + i]; out_rows[dst + i] = st_row[off + i]; }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------- single-pass probe + emit (unique build keys)
+// With at most one match per probe row the output position of a row is a prefix count of match flags: ballots
+// inside the warp, a scan of 8 warp totals, and one atomicAdd per tile on the global output cursor.  No stash, no
+// second pass over the probe side.  Pairs come out in tile order of arrival (the ABI leaves the order open; parity
+// is checked after the canonical sort).  out_l / out_r must hold one entry per probe row.
+#define JE_THREADS 256
+#define JE_HALF 4                            // probes a thread keeps in flight
+#define JE_ITEMS 8                           // rows per lane per compaction step
+#define JE_UNIT (32 * JE_ITEMS)              // rows per warp per compaction step
+#define JE_TILE (JE_UNIT * 8)                // rows per tile ticket (one warp)
+__device__ __forceinline__ uint32_t ld_keep_u32(const uint32_t* a, u64 pol) { uint32_t v; asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol)); return v; }
+__device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* a, u64 pol) { uint32_t v; asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol)); return v; }
+// Every WARP works on its own: tiles of 2048 positions are handed out in order by a global counter (so the probes in
+// flight stay inside one or two radix buckets = L2-resident table regions), and there is no block-level barrier on
+// the path - a warp's chain of dependent memory round trips (keys -> bucket -> head word -> output reservation)
+// overlaps with the chains of the 23 other warps of the SM.
+__global__ void __launch_bounds__(JE_THREADS, 3) join_probe_emit_kernel(JTab tab, JSrc src, long long n, int left_join,
+                                                                      long long* __restrict__ out_l, long long* __restrict__ out_r,
+                                                                      u64* __restrict__ out_cursor, u64* __restrict__ tile_ctr) {
+  constexpr uint32_t NONE = 0xFFFFFFFFu;
+  const long long ntiles = (n + JE_TILE - 1) / JE_TILE;
+  const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  const int lane = threadIdx.x & 31;
+  const uint32_t nslots = (uint32_t)tab.slots;
+  for (;;) {
+    long long tile = 0;
+    if (lane == 0) tile = (long long)atomicAdd(tile_ctr, 1ull);
+    tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+    if (tile >= ntiles) break;
+    const long long tlo = tile * JE_TILE, hi = jsrc_tile_hi(src, tlo, JE_TILE, n);
+    jprefetch_next_region(tab, src, tlo, JE_TILE, pol_keep, lane, 32);
+#pragma unroll 1
+    for (long long lo = tlo; lo < hi; lo += JE_UNIT) {
+      uint32_t res[JE_ITEMS];             // matching right row (build rows < 2^32 on this path), NONE = no match
+      uint32_t lrow[JE_ITEMS];
+      uint32_t okmask = 0;
+      if (src.pkeys && lo + JE_UNIT <= hi) {
+        // ---- fast path: a full unit of partitioned rows.  All 16 stream loads first, then the bucket loads of 4 rows
+        //      at a time, then their head words; the all-ones key (= the empty marker) takes the general path.
+        u64 key[JE_ITEMS];
+        const u64* kp = src.pkeys + lo + lane;
+        const uint32_t* rp = src.prows + lo + lane;
+#pragma unroll
+        for (int j = 0; j < JE_ITEMS; j++) { key[j] = ld_stream_u64(kp + j * 32, pol_stream); lrow[j] = ld_stream_u32(rp + j * 32, pol_stream); }
+        okmask = (1u << JE_ITEMS) - 1u;
+        uint32_t pend = 0, special = 0;       // rows whose probe sequence goes on past the home bucket / all-ones keys
+#pragma unroll
+        for (int half = 0; half < JE_ITEMS / JE_HALF; half++) {
+          ulonglong4 bk[JE_HALF];
+          uint32_t home[JE_HALF];
+#pragma unroll
+          for (int jj = 0; jj < JE_HALF; jj++) {
+            home[jj] = __umulhi(jhash32(key[half * JE_HALF + jj]), nslots) & ~3u;
+            bk[jj] = ld_bucket(tab.keys + home[jj], pol_keep);
+          }
+#pragma unroll
+          for (int jj = 0; jj < JE_HALF; jj++) {
+            const int j = half * JE_HALF + jj;
+            const int f = jbucket_find(bk[jj], key[j]);
+            res[j] = NONE;
+            if (f < 4) res[j] = ld_keep_u32(tab.heads + home[jj] + f, pol_keep);   // the row (unique keys: no flag bit)
+            if (f == 5) pend |= 1u << j;
+            if (key[j] == J_EMPTY_KEY) special |= 1u << j;
+          }
+        }
+        pend &= ~special;
+        // longer probe sequences (a few % of the rows): every lane resolves its first two pending rows per round, so a
+        // round costs one dependent round trip for the whole warp, not one per row
+        uint32_t steps = 0;                    // 4 bits per row: buckets examined beyond the home bucket
+        while (__any_sync(0xFFFFFFFFu, pend != 0)) {
+          const int j0 = pend ? __ffs(pend) - 1 : -1;
+          const uint32_t p2 = pend & (pend - 1u);
+          const int j1 = p2 ? __ffs(p2) - 1 : -1;
+          u64 k0 = 0, k1 = 0;
+#pragma unroll
+          for (int j = 0; j < JE_ITEMS; j++) { if (j == j0) k0 = key[j]; if (j == j1) k1 = key[j]; }
+          uint32_t b0 = 0, b1 = 0;
+          ulonglong4 q0 = make_ulonglong4(0, 0, 0, J_EMPTY_KEY), q1 = q0;
+          if (j0 >= 0) {
+            const uint32_t st = ((steps >> (4 * j0)) & 15u) + 1u;
+            b0 = (uint32_t)(((u64)(__umulhi(jhash32(k0), nslots) & ~3u) + 4ull * st) % nslots);
+            q0 = ld_bucket(tab.keys + b0, pol_keep);
+          }
+          if (j1 >= 0) {
+            const uint32_t st = ((steps >> (4 * j1)) & 15u) + 1u;
+            b1 = (uint32_t)(((u64)(__umulhi(jhash32(k1), nslots) & ~3u) + 4ull * st) % nslots);
+            q1 = ld_bucket(tab.keys + b1, pol_keep);
+          }
+          const int f0 = j0 >= 0 ? jbucket_find(q0, k0) : 4, f1 = j1 >= 0 ? jbucket_find(q1, k1) : 4;
+          uint32_t r0 = NONE, r1 = NONE;
+          if (f0 < 4) r0 = ld_keep_u32(tab.heads + b0 + f0, pol_keep);
+          if (f1 < 4) r1 = ld_keep_u32(tab.heads + b1 + f1, pol_keep);
+#pragma unroll
+          for (int j = 0; j < JE_ITEMS; j++) { if (j == j0 && f0 < 4) res[j] = r0; if (j == j1 && f1 < 4) res[j] = r1; }
+          if (j0 >= 0) { if (f0 != 5) pend &= ~(1u << j0); else if (((steps >> (4 * j0)) & 15u) == 14u) { pend &= ~(1u << j0); special |= 1u << j0; } else steps += 1u << (4 * j0); }
+          if (j1 >= 0) { if (f1 != 5) pend &= ~(1u << j1); else if (((steps >> (4 * j1)) & 15u) == 14u) { pend &= ~(1u << j1); special |= 1u << j1; } else steps += 1u << (4 * j1); }
+        }
+        if (special) {                         // all-ones keys, probe sequences longer than 16 buckets: the general routine
+#pragma unroll
+          for (int j = 0; j < JE_ITEMS; j++) if ((special >> j) & 1u) { const long long h = jprobe(tab, key[j], pol_keep); res[j] = h == J_NOMATCH ? NONE : (uint32_t)h; }
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < JE_ITEMS; j++) {
+          const long long i = lo + (long long)j * 32 + lane;
+          uint32_t r = NONE, lr = (uint32_t)i;
+          if (i < hi) {
+            u64 key;
+            bool ok;
+            if (src.pkeys) { key = __ldcs(src.pkeys + i); lr = __ldcs(src.prows + i); ok = true; }
+            else ok = jload_key(src.col, i, &key);
+            if (ok) { okmask |= 1u << j; const long long h = jprobe(tab, key, pol_keep); r = h == J_NOMATCH ? NONE : (uint32_t)h; }
+          }
+#pragma unroll
+          for (int jj = 0; jj < JE_ITEMS; jj++) if (jj == j) { res[jj] = r; lrow[jj] = lr; }
+        }
+      }
+      // compaction inside the warp: slab j = the 32 rows of item j; one output reservation per unit
+      uint32_t emit = 0, wcnt = 0;
+      uint32_t woff[JE_ITEMS];
+#pragma unroll
+      for (int j = 0; j < JE_ITEMS; j++) {
+        const bool e = ((okmask >> j) & 1u) && (left_join || res[j] != NONE);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, e);
+        if (e) emit |= 1u << j;
+        woff[j] = wcnt + __popc(m & ((1u << lane) - 1u));
+        wcnt += __popc(m);
+      }
+      u64 base = 0;
+      if (lane == 0 && wcnt) base = atomicAdd(out_cursor, (u64)wcnt);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      long long* ol = out_l + base;
+      long long* orr = out_r + base;
+#pragma unroll
+      for (int j = 0; j < JE_ITEMS; j++) {
+        if (!((emit >> j) & 1u)) continue;
+        st_stream_u64(ol + woff[j], (long long)lrow[j], pol_stream);
+        st_stream_u64(orr + woff[j], res[j] == NONE ? -1ll : (long long)res[j], pol_stream);
+      }
+    }
+  }
+}
+
 struct JPart { DevBuf keys, rows; long long n = 0; };
 static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out) {
   const int nb = 1 << log_nb;
@@ -400,6 +691,29 @@ static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_
   jpart_scatter_kernel<<<ctas, JP_THREADS, smem, c->stream>>>(col, n, log_nb, h + nb, out->keys.as<u64>(), out->rows.as<uint32_t>());
   c->stats.kernel_launches += 3;
   PDRS_CUDA(c, cudaGetLastError());
+  return PDRS_OK;
+}
+
+// One-pass partition into padded buckets; *ok = false when a bucket overflowed (heavily duplicated keys).
+static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out, DevBuf* counts, long long* cap_out, bool* ok) {
+  const int nb = 1 << log_nb;
+  long long cap = n / nb + n / (nb * 32ll) + 65536;           // ~3% + 64K rows of slack per bucket
+  cap = (cap + JQ_TILE - 1) / JQ_TILE * JQ_TILE;             // multiple of every tile size used downstream
+  *cap_out = cap;
+  PDRS_TRY(counts->alloc(c, (size_t)(nb + 2) * 8, true));    // [nb] bucket cursors, [nb] overflow count
+  PDRS_TRY(out->keys.alloc(c, (size_t)nb * cap * 8));
+  PDRS_TRY(out->rows.alloc(c, (size_t)nb * cap * 4));
+  out->n = (long long)nb * cap;
+  const size_t smem = (size_t)JQ_TILE * 12 + (1056 + 1024) * 4;
+  static bool attr_set = false;
+  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + JQ_TILE - 1) / JQ_TILE));
+  jpart1_kernel<<<ctas, JQ_NT, smem, c->stream>>>(col, n, log_nb, cap, counts->as<u64>(), out->keys.as<u64>(), out->rows.as<uint32_t>(), counts->as<u64>() + nb);
+  c->stats.kernel_launches++;
+  PDRS_CUDA(c, cudaGetLastError());
+  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, counts->as<u64>() + nb, 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  *ok = c->pinned_scalars[8] == 0;
   return PDRS_OK;
 }
 
@@ -428,9 +742,9 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   res->ctx = c;
   struct Guard { pdrs_join_result* r; ~Guard() { delete r; } } guard{res};
 
-  const long long slots = std::max<long long>(1024, 2 * nr);           // load factor <= 1/2; any even size (see jslot)
-  if (slots >= (1ll << 32) - 2) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
-  const size_t table_bytes = (size_t)(slots + 2) * sizeof(JSlot);      // + the reserved slot of the all-ones key
+  const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;   // load factor <= 1/3: 4-slot buckets overflow for ~5% of the keys (see jslot)
+  if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
+  const size_t table_bytes = (size_t)(slots + 4) * 12;                  // u64 keys[slots + 4] + u32 heads[slots + 4]; slot `slots` is reserved for the all-ones key
   // Large tables: radix-partition both sides so that one bucket's table region (<= 32 MB) stays in L2.
   // join_algo: 0 auto, 1 = always the direct (left-row-major output) path, 2 = always partitioned.
   int log_nb = 0;
@@ -447,30 +761,68 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   mark("start");
   DevBuf tab, next, counts, fail;
   PDRS_TRY(tab.alloc(c, table_bytes));
-  PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));   // head = -1 (EMPTY)
+  PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));   // key = all ones (EMPTY), head = -1 (EMPTY)
+  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
   PDRS_TRY(next.alloc(c, (size_t)std::max<int64_t>(nr, 1) * 8));
   PDRS_CUDA(c, cudaMemsetAsync(next.p, 0xFF, (size_t)std::max<int64_t>(nr, 1) * 8, c->stream));      // -1 = end of chain
-  PDRS_TRY(fail.alloc(c, 32, true));      // [0] failed inserts, [1] build tile counter, [2] probe tile counter
+  PDRS_TRY(fail.alloc(c, 64, true));      // [0] failed inserts, [1] build tile counter, [2] probe tile counter (two-pass) / output cursor (single pass), [3] duplicate build keys, [4] probe tile counter (single pass)
   c->stats.table_slots = slots;
   JKeyCol rc{rv.data, rv.nulls, rv.dtype}, lc{lv.data, lv.nulls, lv.dtype};
   JPart lp, rp;
-  JSrc rsrc{rc, nullptr, nullptr}, lsrc{lc, nullptr, nullptr};
+  DevBuf lcnt, rcnt;
+  JSrc rsrc{rc, nullptr, nullptr, 0, nullptr, 0}, lsrc{lc, nullptr, nullptr, 0, nullptr, 0};
   long long nl_eff = nl, nr_eff = nr;
   if (radix) {
     mark("memset");
-    PDRS_TRY(jpartition(c, rc, nr, log_nb, &rp));
+    // one-pass partition into padded buckets; exact two-pass partition when a bucket overflows (skewed keys)
+    bool ok1 = c->opt_join_part != 2;
+    long long rcap = 0, lcap = 0;
+    if (ok1) PDRS_TRY(jpartition1(c, rc, nr, log_nb, &rp, &rcnt, &rcap, &ok1));
+    if (ok1) { rsrc.cap = rcap; rsrc.cnt = rcnt.as<u64>(); rsrc.log_nb = c->opt_join_prefetch ? log_nb : 0; }
+    else { rp = JPart(); PDRS_TRY(jpartition(c, rc, nr, log_nb, &rp)); }
     mark("partition build side");
-    PDRS_TRY(jpartition(c, lc, nl, log_nb, &lp));
+    bool ok2 = c->opt_join_part != 2;
+    if (ok2) PDRS_TRY(jpartition1(c, lc, nl, log_nb, &lp, &lcnt, &lcap, &ok2));
+    if (ok2) { lsrc.cap = lcap; lsrc.cnt = lcnt.as<u64>(); lsrc.log_nb = c->opt_join_prefetch ? log_nb : 0; }
+    else { lp = JPart(); PDRS_TRY(jpartition(c, lc, nl, log_nb, &lp)); }
     mark("partition probe side");
     rsrc.pkeys = rp.keys.as<u64>(); rsrc.prows = rp.rows.as<uint32_t>(); nr_eff = rp.n;
     lsrc.pkeys = lp.keys.as<u64>(); lsrc.prows = lp.rows.as<uint32_t>(); nl_eff = lp.n;
   }
   if (nr_eff > 0) {
-    join_build_kernel<<<(int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (nr_eff + 255) / 256)), 256, 0, c->stream>>>(tab.as<JSlot>(), (u64)slots, next.as<long long>(), rsrc, nr_eff, fail.as<u64>());
+    join_build_kernel<<<(int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (nr_eff + 255) / 256)), 256, 0, c->stream>>>(jt, next.as<long long>(), rsrc, nr_eff, fail.as<u64>());
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
   }
   mark("build");
+  // unique build keys (the usual dimension-table join): single-pass probe + emit.  Needs one output slot per probe row.
+  bool single_pass = radix && c->opt_join_emit != 2;   // small inputs keep the reference's left-row-major order
+  if (single_pass) {
+    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, fail.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->pinned_scalars[0] != 0) return pdrs_fail(c, PDRS_ERR_CUDA, "join build: hash table insertion failed for %lld rows", (long long)c->pinned_scalars[0]);
+    single_pass = c->pinned_scalars[3] == 0;
+  }
+  int64_t M = 0;
+  if (single_pass) {
+    PDRS_TRY(res->left.alloc(c, (size_t)std::max<int64_t>(nl, 1) * 8));
+    PDRS_TRY(res->right.alloc(c, (size_t)std::max<int64_t>(nl, 1) * 8));
+    if (nl_eff > 0) {
+      const long long ntiles = (nl_eff + JE_TILE - 1) / JE_TILE;
+      const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * (c->opt_join_ctas_per_sm > 0 ? c->opt_join_ctas_per_sm : 8), ntiles));
+      if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+      join_probe_emit_kernel<<<ctas, JE_THREADS, 0, c->stream>>>(jt, lsrc, nl_eff, how == PDRS_LEFT, res->left.as<long long>(), res->right.as<long long>(),
+                                                                 fail.as<u64>() + 2, fail.as<u64>() + 4);
+      if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+      c->stats.kernel_launches++;
+      PDRS_CUDA(c, cudaGetLastError());
+      PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, fail.as<u64>() + 2, 8, cudaMemcpyDeviceToHost, c->stream));
+      PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+      M = c->pinned_scalars[0];
+    }
+    res->n = M;
+    mark("probe+emit");
+  } else {
   const long long ntiles = (nl_eff + JOIN_TILE - 1) / JOIN_TILE;
   const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * (c->opt_join_ctas_per_sm > 0 ? c->opt_join_ctas_per_sm : 8), ntiles));
   PDRS_TRY(counts.alloc(c, (size_t)(ntiles + 4) * 8, true));
@@ -479,7 +831,7 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   u64* cc = counts.as<u64>();
   if (nl_eff > 0) {
     if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
-    join_probe_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(tab.as<JSlot>(), (u64)slots, next.as<long long>(), lsrc, nl_eff, how == PDRS_LEFT, stash.as<long long>(), cc, fail.as<u64>() + 2);
+    join_probe_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(jt, next.as<long long>(), lsrc, nl_eff, how == PDRS_LEFT, stash.as<long long>(), cc, fail.as<u64>() + 2);
     if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
     join_scan_kernel<<<1, 1024, 0, c->stream>>>(cc, (int)ntiles, cc + ntiles + 2);
     c->stats.kernel_launches += 2;
@@ -490,15 +842,16 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 1, fail.p, 8, cudaMemcpyDeviceToHost, c->stream));
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->pinned_scalars[1] != 0) return pdrs_fail(c, PDRS_ERR_CUDA, "join build: hash table insertion failed for %lld rows", (long long)c->pinned_scalars[1]);
-  const int64_t M = nl_eff > 0 ? c->pinned_scalars[0] : 0;
+  M = nl_eff > 0 ? c->pinned_scalars[0] : 0;
   res->n = M;
   PDRS_TRY(res->left.alloc(c, (size_t)std::max<int64_t>(M, 1) * 8));
   PDRS_TRY(res->right.alloc(c, (size_t)std::max<int64_t>(M, 1) * 8));
   if (M > 0) {
-    join_write_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(stash.as<long long>(), next.as<long long>(), nl_eff, how == PDRS_LEFT, cc, lsrc.prows,
+    join_write_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(stash.as<long long>(), next.as<long long>(), nl_eff, how == PDRS_LEFT, cc, lsrc,
                                                             res->left.as<long long>(), res->right.as<long long>());
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
+  }
   }
   mark("write");
   c->stats.groupby_algo_used = radix ? 2 : 1;
