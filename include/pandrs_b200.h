@@ -83,7 +83,8 @@ typedef enum pdrs_groupby_algo {
   PDRS_GB_SHARED = 1,       /* per-warp tables in shared memory, spill to the global table */
   PDRS_GB_GLOBAL = 2,       /* global open-addressing table only (high cardinality) */
   PDRS_GB_DENSE = 3,        /* direct-mapped shared tables for small dense integer key ranges */
-  PDRS_GB_TILESORT = 4      /* tile sort in shared memory + per-thread register aggregation (tens to ~2000 groups) */
+  PDRS_GB_TILESORT = 4,     /* tile sort in shared memory + per-thread register aggregation (tens to ~2000 groups) */
+  PDRS_GB_PARTITIONED = 5   /* reported only: hash-partitioned rows + tile sort per partition (thousands to millions of groups) */
 } pdrs_groupby_algo;
 
 typedef struct pdrs_options {

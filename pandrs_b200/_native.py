@@ -18,7 +18,7 @@ I64, F64, DICT_U32, BOOL_BITS, I32 = 0, 1, 2, 3, 4
 SUM, MEAN, MIN, MAX, COUNT, STD, VAR = range(7)
 INNER, LEFT = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
-GB_AUTO, GB_SHARED, GB_GLOBAL, GB_DENSE, GB_TILESORT = 0, 1, 2, 3, 4
+GB_AUTO, GB_SHARED, GB_GLOBAL, GB_DENSE, GB_TILESORT, GB_PARTITIONED = 0, 1, 2, 3, 4, 5
 
 OK, ERR_BAD_ARG, ERR_TYPE_MISMATCH, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 

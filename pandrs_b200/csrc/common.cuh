@@ -43,6 +43,7 @@ struct pdrs_ctx {
   int64_t opt_radix = 1;               // allow the radix-partitioned high-cardinality groupby path
   int64_t opt_dense = 1;               // allow the direct-mapped path for small dense integer keys
   int64_t opt_tsort = 1;               // allow the tile-sort kernel (gb_tsort.cu)
+  int64_t opt_part = 1;                // allow the hash-partitioned high-cardinality path (gb_part.cu)
   int64_t opt_tsort_threads = 0;       // 0 = auto, else 512 / 1024 threads per CTA
   int64_t opt_tsort_min_groups = 16;   // fewer groups: the per-warp shared tables win
 };

@@ -1,0 +1,247 @@
+// High-cardinality groupby (thousands to tens of millions of groups, one 64-bit key column): hash-partition the
+// (key, value) rows until every partition holds at most ~600 groups, then run the tile-sort kernel (gb_tsort.cu)
+// partition by partition.  Replaces grouping.rs:62-104 + aggregation.rs:507-742 like the other groupby kernels.
+//
+// Why not a global hash table: with millions of groups every row costs 3-5 L2 atomics on random addresses
+// (rows, n, S1, S2, min / max), and the L2 atomic units, not HBM, bound the kernel (measured 70 ms for 1e9 rows
+// and 1e7 groups, profiles/bench_r01.json "groupby_all6_10m").  After partitioning, all rows of a group sit in one
+// partition, a partition's groups fit the register accumulators of one CTA, and the only global-table traffic
+// is one pre-aggregated batch per group.
+//
+//   gp_part_kernel<true>   level 1: columns (+ value NULL bitmap, row filter) -> 2^bits1 padded buckets of
+//                          (key, value, flag byte); rows whose value is NULL only count (Count includes NULLs,
+//                          aggregation.rs:743) and travel with flag bit 0 set
+//   gp_part_kernel<false>  level 2: every level-1 bucket -> 2^bits2 sub-buckets; partition id = top bits1+bits2
+//                          bits of the key hash
+// Both levels are ONE pass (no histogram pass): bucket b owns a fixed padded range of the output, a tile's rows
+// are ranked by a shared-memory histogram, one global reservation per bucket and tile, rows staged in shared
+// memory in bucket order and written out as contiguous runs.  A bucket that overflows its range (heavily skewed
+// keys) makes the caller fall back to the global-table path.
+#include <algorithm>
+
+#include "groupby_kernels.cuh"
+
+bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
+long long gb_tsort_tile_rows();
+cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int nt, int gpt, int ctas, size_t smem, cudaStream_t s);
+
+namespace {
+
+constexpr int GP_NT = 512, GP_ITEMS = 8, GP_TILE = GP_NT * GP_ITEMS;
+
+__device__ __forceinline__ uint32_t gp_hash32(u64 k) {     // = ts_hash32 (gb_tsort.cu)
+  const uint32_t lo = (uint32_t)k ^ (uint32_t)(k >> 32), hi = (uint32_t)(k >> 32);
+  constexpr uint32_t CL = 0x7F4A7C15u, CH = 0x9E3779B9u;
+  return __umulhi(lo, CL) + lo * CH + hi * CL;
+}
+
+struct GpIn {
+  // level 1: the columns
+  const u64* keys; const u64* vals; const uint8_t* vnull; const uint8_t* fbits; const uint8_t* fnull;
+  long long n;
+  int compat_nulls;
+  // level 2: padded buckets of level 1
+  const u64* pkeys; const u64* pvals; const uint8_t* pflags; const u64* pcnt; long long pcap;
+};
+
+template <bool FROM_COLS>
+__global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr, int local_bits, long long cap_out, u64* __restrict__ cursor,
+                                                          u64* __restrict__ out_keys, u64* __restrict__ out_vals, uint8_t* __restrict__ out_flags,
+                                                          u64* __restrict__ overflow) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  u64* st_key = reinterpret_cast<u64*>(gsm);              // [GP_TILE]
+  u64* st_val = st_key + GP_TILE;                         // [GP_TILE]
+  uint32_t* H = reinterpret_cast<uint32_t*>(st_val + GP_TILE);   // [256 + 32] counts -> exclusive offsets
+  uint32_t* G = H + 288;                                  // [256] reserved start inside the output bucket
+  uint32_t* QB = G + 256;                                 // [256] output bucket of local bucket b
+  uint8_t* st_fl = reinterpret_cast<uint8_t*>(QB + 256);  // [GP_TILE] (only when the value column has NULLs)
+  __shared__ uint32_t wsum[GP_NT / 32];
+  const int nb = 1 << local_bits;
+  const uint32_t lmask = (uint32_t)nb - 1u;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // level 2: blockIdx.y = level-1 bucket, its tiles are strided over gridDim.x
+  long long t0 = (long long)blockIdx.x * GP_TILE, tstride = (long long)gridDim.x * GP_TILE;
+  long long lim = in.n, base0 = 0;
+  if (!FROM_COLS) { lim = min((long long)__ldg(in.pcnt + blockIdx.y), in.pcap); base0 = (long long)blockIdx.y * in.pcap; }
+  u64 key[GP_ITEMS], val[GP_ITEMS];
+  // Bitmap words of a tile: the 32 rows of item j of a warp share one 32-bit word, lane j holds it (value NULLs,
+  // filter, filter NULLs).  Level 2: the raw flag byte of every row.  Nothing here is consumed at load time, so the
+  // loads of a tile stay in flight while the previous tile is written out.
+  uint32_t wv = 0, wf = 0xFFFFFFFFu, wfn = 0, fl[FROM_COLS ? 1 : GP_ITEMS];
+  auto load_tile = [&](long long tb) {
+#pragma unroll
+    for (int j = 0; j < GP_ITEMS; j++) {
+      const long long i = tb + (long long)j * GP_NT + tid;
+      const bool inb = i < lim;
+      if (FROM_COLS) {
+        key[j] = inb ? __ldcs(in.keys + i) : 0ull;
+        val[j] = inb ? __ldcs(in.vals + i) : 0ull;
+      } else {
+        key[j] = inb ? __ldcs(in.pkeys + base0 + i) : 0ull;
+        val[j] = inb ? __ldcs(in.pvals + base0 + i) : 0ull;
+        fl[j] = (inb && in.pflags) ? (uint32_t)__ldcs(in.pflags + base0 + i) : 0u;
+      }
+    }
+    if (FROM_COLS) {
+      wv = 0; wf = 0xFFFFFFFFu; wfn = 0;
+      const long long row0 = tb + (long long)(lane & (GP_ITEMS - 1)) * GP_NT + warp * 32;
+      if (row0 < lim) {                     // bitmaps cover ceil(n / 64) * 8 bytes (pdrs_view_col)
+        if (in.vnull) wv = __ldg(reinterpret_cast<const uint32_t*>(in.vnull) + (row0 >> 5));
+        if (in.fbits) wf = __ldg(reinterpret_cast<const uint32_t*>(in.fbits) + (row0 >> 5));
+        if (in.fnull) wfn = __ldg(reinterpret_cast<const uint32_t*>(in.fnull) + (row0 >> 5));
+      }
+    }
+  };
+  if (t0 < lim) load_tile(t0);
+  for (; t0 < lim; t0 += tstride) {
+    if (tid < 288) H[tid] = 0;
+    __syncthreads();
+    uint32_t br[GP_ITEMS];            // local bucket << 16 | rank inside the bucket; all ones = no row
+    uint32_t vnullmask = 0;           // rows whose value is NULL: they only count (aggregation.rs:743)
+#pragma unroll
+    for (int j = 0; j < GP_ITEMS; j++) {
+      br[j] = 0xFFFFFFFFu;
+      bool live = t0 + (long long)j * GP_NT + tid < lim;
+      if (FROM_COLS) {
+        const uint32_t keep = __shfl_sync(0xFFFFFFFFu, wf & ~wfn, j);        // filter keeps Some(true) rows only (data_ops.rs:49-55)
+        const uint32_t vn = __shfl_sync(0xFFFFFFFFu, wv, j);
+        live = live && ((keep >> lane) & 1u);
+        if ((vn >> lane) & 1u) { if (in.compat_nulls) val[j] = 0; else vnullmask |= 1u << j; }
+      } else if (fl[j] & 1u) vnullmask |= 1u << j;
+      if (!live) continue;
+      const uint32_t q = gp_hash32(key[j]) >> hash_shr;
+      const uint32_t b = q & lmask;
+      QB[b] = q;                      // every row of local bucket b carries the same q (same level-1 bucket)
+      br[j] = (b << 16) | atomicAdd(&H[b], 1u);
+    }
+    __syncthreads();
+    {   // exclusive scan of the bucket counts (thread b owns bucket b) + one global reservation per bucket
+      const uint32_t c = tid < nb ? H[tid] : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+      if (lane == 31) wsum[warp] = incl;
+      uint32_t g = 0;
+      if (c) {
+        const u64 at = atomicAdd(&cursor[QB[tid]], (u64)c);
+        if (at + c > (u64)cap_out) { atomicAdd(overflow, 1ull); g = 0xFFFFFFFFu; } else g = (uint32_t)at;
+      }
+      __syncthreads();
+      uint32_t ws = lane < GP_NT / 32 ? wsum[lane] : 0u;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
+      const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
+      const uint32_t excl = (warp ? wprefix : 0u) + incl - c;
+      if (tid < 288) H[tid] = excl;           // H[nb .. 287] = total
+      if (tid < 256) G[tid] = g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < GP_ITEMS; j++) {
+      if (br[j] == 0xFFFFFFFFu) continue;
+      const uint32_t pos = H[br[j] >> 16] + (br[j] & 0xFFFFu);
+      st_key[pos] = key[j];
+      st_val[pos] = val[j];
+      if (out_flags) st_fl[pos] = (uint8_t)((vnullmask >> j) & 1u);
+    }
+    if (t0 + tstride < lim) load_tile(t0 + tstride);      // next tile: in flight during the write-out below
+    __syncthreads();
+    for (int b = warp; b < nb; b += GP_NT / 32) {     // one warp per bucket run
+      const uint32_t off = H[b], cnt = H[b + 1] - off, g = G[b];
+      if (cnt == 0 || g == 0xFFFFFFFFu) continue;     // overflow: the caller discards this partitioning
+      const long long dst = (long long)QB[b] * cap_out + g;
+      for (uint32_t i = lane; i < cnt; i += 32) { out_keys[dst + i] = st_key[off + i]; out_vals[dst + i] = st_val[off + i]; }
+      if (out_flags) for (uint32_t i = lane; i < cnt; i += 32) out_flags[dst + i] = st_fl[off + i];
+    }
+    __syncthreads();
+  }
+}
+
+long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
+
+}  // namespace
+
+// One aggregation pass through the partitioned path.  Returns PDRS_ERR_UNSUPPORTED when it does not apply or a
+// bucket overflowed (the caller then takes the global-table path; *dirty = the table was touched: never, today).
+int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty) {
+  *dirty = false;
+  const long long n = gp.n;
+  const long long T = gb_tsort_tile_rows();
+  if (gp.ks.c[0].nulls || !gp.val || n < (1 << 20)) return PDRS_ERR_UNSUPPORTED;
+  // partitions of <= ~600 expected groups (the tile-sort kernel holds 1023 ids with 512 threads x 2 groups)
+  int bits = 1;
+  while (bits < 16 && (est_groups >> bits) > 600) bits++;
+  if ((est_groups >> bits) > 700) return PDRS_ERR_UNSUPPORTED;
+  if ((n >> bits) < 2 * T) return PDRS_ERR_UNSUPPORTED;          // too few rows per partition: the per-partition overheads dominate
+  const int bits1 = bits <= 8 ? bits : (bits + 1) / 2, bits2 = bits - bits1;
+  const long long nb1 = 1ll << bits1, nparts = 1ll << bits;
+  const long long cap1 = round_up(n / nb1 + n / (nb1 * 32) + 65536, T);
+  const long long cap2 = bits2 ? round_up(n / nparts + n / (nparts * 8) + 8192, T) : cap1;
+  const size_t need = (size_t)nb1 * cap1 * 16 + (bits2 ? (size_t)nparts * cap2 * 16 : 0);
+  size_t free_b = 0, total_b = 0;
+  PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  if (need + (2ull << 30) > free_b) return PDRS_ERR_UNSUPPORTED;
+
+  int ts_nt = 0, ts_gpt = 0, ts_slots = 0;
+  size_t ts_smem = 0;
+  const long long ts_cap = 1023;
+  if (!gb_tsort_geometry(ts_cap, false, c->smem_optin, 512, &ts_nt, &ts_gpt, &ts_slots, &ts_smem)) return PDRS_ERR_UNSUPPORTED;
+
+  DevBuf cnt, k1, v1, f1, k2, v2, f2;
+  const bool has_flags = gp.vnull != nullptr && !gp.compat_nulls;
+  PDRS_TRY(cnt.alloc(c, (size_t)(nb1 + nparts + 8) * 8, true));     // [nb1] level-1 cursors, [nparts] level-2 cursors, [1] overflow
+  u64* cur1 = cnt.as<u64>();
+  u64* cur2 = cur1 + nb1;
+  u64* ovf = cur2 + nparts;
+  PDRS_TRY(k1.alloc(c, (size_t)nb1 * cap1 * 8));
+  PDRS_TRY(v1.alloc(c, (size_t)nb1 * cap1 * 8));
+  if (has_flags) PDRS_TRY(f1.alloc(c, (size_t)nb1 * cap1 + 64));
+  const size_t smem = (size_t)GP_TILE * 17 + (288 + 256 + 256) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+  GpIn in{};
+  in.keys = reinterpret_cast<const u64*>(gp.ks.c[0].data); in.vals = reinterpret_cast<const u64*>(gp.val); in.vnull = gp.vnull;
+  in.fbits = gp.fbits; in.fnull = gp.fnull; in.n = n; in.compat_nulls = gp.compat_nulls;
+  const int ctas1 = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + GP_TILE - 1) / GP_TILE));
+  gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf);
+  c->stats.kernel_launches++;
+  const u64 *pk = k1.as<u64>(), *pv = v1.as<u64>(), *pc = cur1;
+  const uint8_t* pf = has_flags ? f1.as<uint8_t>() : nullptr;
+  long long pcap = cap1;
+  if (bits2) {
+    PDRS_TRY(k2.alloc(c, (size_t)nparts * cap2 * 8));
+    PDRS_TRY(v2.alloc(c, (size_t)nparts * cap2 * 8));
+    if (has_flags) PDRS_TRY(f2.alloc(c, (size_t)nparts * cap2 + 64));
+    GpIn in2{};
+    in2.pkeys = k1.as<u64>(); in2.pvals = v1.as<u64>(); in2.pflags = pf; in2.pcnt = cur1; in2.pcap = cap1;
+    const int gx = (int)std::max<long long>(1, std::min<long long>((cap1 + GP_TILE - 1) / GP_TILE, std::max<long long>(1, (long long)c->sm_count * 2 * 2 / nb1)));
+    gp_part_kernel<false><<<dim3(gx, (unsigned)nb1), GP_NT, smem, c->stream>>>(in2, 32 - bits, bits2, cap2, cur2, k2.as<u64>(), v2.as<u64>(), has_flags ? f2.as<uint8_t>() : nullptr, ovf);
+    c->stats.kernel_launches++;
+    pk = k2.as<u64>(); pv = v2.as<u64>(); pc = cur2; pcap = cap2;
+    pf = has_flags ? f2.as<uint8_t>() : nullptr;
+  }
+  PDRS_CUDA(c, cudaGetLastError());
+  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, ovf, 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->pinned_scalars[8] != 0) return PDRS_ERR_UNSUPPORTED;      // skewed keys: a bucket overflowed its padded range
+  if (bits2) { k1.release(); v1.release(); f1.release(); }                        // only the last level is read below
+  GbParams tp = gp;
+  tp.part_keys = pk; tp.part_vals = pv; tp.part_flags = pf; tp.part_cnt = pc; tp.part_cap = pcap; tp.part_bits = bits;
+  tp.sh_cap = (int)ts_cap; tp.sh_slots = ts_slots; tp.sh_dense = 0; tp.sh_dense_base = 0;
+  int lg = 0;
+  while ((1 << lg) < ts_slots) lg++;
+  tp.sh_log_slots = lg;
+  PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts), ts_smem, c->stream));
+  c->stats.kernel_launches++;
+  if (c->opt_timing) {
+    PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    PDRS_CUDA(c, cudaEventSynchronize(c->ev_b));
+    PDRS_CUDA(c, cudaEventElapsedTime(kernel_ms, c->ev_a, c->ev_b));
+  }
+  return PDRS_OK;
+}

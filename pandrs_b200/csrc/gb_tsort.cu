@@ -52,41 +52,97 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 template <int RPT> struct TsRows {
   u64 k[RPT];
   uint32_t vnw, knw, fw;   // lane l holds bitmap word (l % RPT) of the warp's 32 * RPT rows: value NULLs, key NULLs, filter & ~filter NULLs
-  uint32_t act;            // bit q: row q of this lane is inside the column
+  uint32_t fl[RPT / 2];    // partitioned input: the flag bytes of rows 2 j, 2 j + 1 (bit 0 / bit 8: value is NULL)
+  uint32_t act;            // bit q: row q of this lane is inside the column / partition
 };
 
+// One unit of work of a CTA: a tile of up to TS_T consecutive rows.  Plain input: tiles blockIdx, blockIdx + grid, ...
+// of the columns.  Partitioned input: the tiles of partitions blockIdx, blockIdx + grid, ...; `last` marks the last
+// tile of a partition (the CTA then flushes its groups and starts over with empty tables).
+struct TsItem { long long base; long long part; int valid; int last; };
+template <bool PART>
+__device__ __forceinline__ TsItem ts_first_item(const GbParams& p) {
+  TsItem it;
+  it.part = blockIdx.x; it.last = 0;
+  if (!PART) {
+    it.base = (long long)blockIdx.x * TS_T;
+    it.valid = it.base < p.n ? (int)min((long long)TS_T, p.n - it.base) : 0;
+    return it;
+  }
+  const long long nparts = 1ll << p.part_bits;
+  it.base = 0; it.valid = 0;
+  while (it.part < nparts) {
+    const long long c = min((long long)__ldg(p.part_cnt + it.part), p.part_cap);
+    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TS_T, c); it.last = c <= TS_T; return it; }
+    it.part += gridDim.x;
+  }
+  return it;
+}
+template <bool PART>
+__device__ __forceinline__ TsItem ts_next_item(const GbParams& p, const TsItem& cur) {
+  TsItem it = cur;
+  if (!PART) {
+    it.base = cur.base + (long long)gridDim.x * TS_T;
+    it.valid = it.base < p.n ? (int)min((long long)TS_T, p.n - it.base) : 0;
+    return it;
+  }
+  const long long nparts = 1ll << p.part_bits;
+  if (!cur.last) {
+    const long long c = min((long long)__ldg(p.part_cnt + cur.part), p.part_cap);
+    const long long off = cur.base - cur.part * p.part_cap + TS_T;
+    it.base = cur.base + TS_T; it.valid = (int)min((long long)TS_T, c - off); it.last = c - off <= TS_T;
+    return it;
+  }
+  it.valid = 0; it.last = 0;
+  for (it.part = cur.part + gridDim.x; it.part < nparts; it.part += gridDim.x) {
+    const long long c = min((long long)__ldg(p.part_cnt + it.part), p.part_cap);
+    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TS_T, c); it.last = c <= TS_T; return it; }
+  }
+  return it;
+}
+
 // Rows of one warp in one tile: load j, lane l -> rows wbase + 64 j + 2 l + {0, 1} (one 128-bit load).
-template <int RPT, bool PLAIN>
-__device__ __forceinline__ void ts_load(const GbParams& p, long long wbase, int lane, TsRows<RPT>& r) {
-  const long long n = p.n;
-  const u64* keys = reinterpret_cast<const u64*>(p.ks.c[0].data) + wbase + 2 * lane;
-  if (wbase + 32 * RPT <= n) {
-    r.act = (1u << RPT) - 1u;
+// Partitioned input: the tile's memory always exists (partitions are padded to whole tiles), rows >= valid are masked.
+template <int RPT, bool PLAIN, bool PART>
+__device__ __forceinline__ void ts_load(const GbParams& p, const TsItem& it, int warp, int lane, TsRows<RPT>& r) {
+  const long long wbase = it.base + (long long)warp * (32 * RPT);
+  const int wfirst = warp * (32 * RPT);           // first row of the warp inside the tile
+  const u64* keys = (PART ? p.part_keys : reinterpret_cast<const u64*>(p.ks.c[0].data)) + wbase + 2 * lane;
+  if (PART || wfirst + 32 * RPT <= it.valid) {
 #pragma unroll
     for (int j = 0; j < RPT / 2; j++) {
       const ulonglong2 kk = ld_stream_v2(keys + 64 * j);
       r.k[2 * j] = kk.x; r.k[2 * j + 1] = kk.y;
     }
-  } else {
+  }
+  if (wfirst + 32 * RPT <= it.valid) r.act = (1u << RPT) - 1u;
+  else {
     r.act = 0;
 #pragma unroll
     for (int q = 0; q < RPT; q++) {
-      const bool inb = wbase + 64 * (q >> 1) + 2 * lane + (q & 1) < n;
-      r.k[q] = inb ? __ldg(keys + 64 * (q >> 1) + (q & 1)) : 0ull;
+      const bool inb = wfirst + 64 * (q >> 1) + 2 * lane + (q & 1) < it.valid;
+      if (!PART) r.k[q] = inb ? __ldg(keys + 64 * (q >> 1) + (q & 1)) : 0ull;
       if (inb) r.act |= 1u << q;
     }
   }
-  const long long w = (wbase >> 5) + (lane & (RPT - 1));
-  const bool inb = w * 32 < n;           // bitmaps cover ceil(n / 64) * 8 bytes (pdrs_view_col)
-  r.vnw = (p.vnull && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.vnull) + w) : 0u;
-  if (!PLAIN) {
-    r.knw = (p.ks.c[0].nulls && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.ks.c[0].nulls) + w) : 0u;
-    uint32_t f = 0xFFFFFFFFu;
-    if (p.fbits) {   // filter keeps Some(true) rows only (data_ops.rs:49-55)
-      f = inb ? __ldg(reinterpret_cast<const uint32_t*>(p.fbits) + w) : 0u;
-      if (p.fnull && inb) f &= ~__ldg(reinterpret_cast<const uint32_t*>(p.fnull) + w);
+  r.vnw = 0;
+  if (PART) {
+#pragma unroll
+    for (int j = 0; j < RPT / 2; j++) r.fl[j] = p.part_flags ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.part_flags + wbase + 2 * lane) + 32 * j) : 0u;
+  }
+  if (!PART) {
+    const long long w = (wbase >> 5) + (lane & (RPT - 1));
+    const bool inb = w * 32 < p.n;           // bitmaps cover ceil(n / 64) * 8 bytes (pdrs_view_col)
+    r.vnw = (p.vnull && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.vnull) + w) : 0u;
+    if (!PLAIN) {
+      r.knw = (p.ks.c[0].nulls && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.ks.c[0].nulls) + w) : 0u;
+      uint32_t f = 0xFFFFFFFFu;
+      if (p.fbits) {   // filter keeps Some(true) rows only (data_ops.rs:49-55)
+        f = inb ? __ldg(reinterpret_cast<const uint32_t*>(p.fbits) + w) : 0u;
+        if (p.fnull && inb) f &= ~__ldg(reinterpret_cast<const uint32_t*>(p.fnull) + w);
+      }
+      r.fw = f;
     }
-    r.fw = f;
   }
 }
 
@@ -115,13 +171,59 @@ __device__ __forceinline__ void ts_add(double& S1, double& S2, VT& mn, VT& mx, u
   }
 }
 
+// Top 32 bits of (fold(k) * odd constant); the radix partitions take the top bits, the CTA key table the bits below.
+__device__ __host__ __forceinline__ uint32_t ts_hash32(u64 k) {
+  const uint32_t lo = (uint32_t)k ^ (uint32_t)(k >> 32), hi = (uint32_t)(k >> 32);
+  constexpr uint32_t CL = 0x7F4A7C15u, CH = 0x9E3779B9u;
+  return (uint32_t)(((u64)lo * CL) >> 32) + lo * CH + hi * CL;
+}
+
+// CTA key table of the hashed modes: open addressing over S slots {key, id + 1}; ids are handed out in first-seen
+// order.  Same no-spin protocol as sh_try / sh_lookup (groupby_kernels.cuh): every lane of the warp calls together.
+__device__ __noinline__ int ts_insert(u64* ktab_key, uint32_t* ktab_id, uint32_t* misc, int S, int cap, u64 key, uint32_t slot, bool active) {
+  int probe = 0, res = -1, rounds = 0;
+  bool pending = active;
+  while (__any_sync(0xFFFFFFFFu, pending)) {
+    if (pending) {
+      int r = SH_RETRY;
+      while (probe < S) {
+        const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
+        const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
+        if (idw == 0) {
+          if (*reinterpret_cast<volatile uint32_t*>(&misc[0]) >= (uint32_t)cap) { r = -1; break; }
+          const uint32_t old = atomicCAS(&ktab_id[slot], 0u, SH_BUSY);
+          if (old == 0) {
+            const uint32_t nid = atomicAdd(&misc[0], 1u);
+            if (nid >= (uint32_t)cap) { *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]) = 0; r = -1; break; }   // table full: give the slot back, spill the row
+            *reinterpret_cast<volatile u64*>(&ktab_key[slot]) = key;
+            __threadfence_block();
+            *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]) = nid + 1;
+            r = (int)nid;
+          }
+          break;                       // lost the race: look at the slot again next round
+        }
+        if (idw == SH_BUSY) break;
+        if (kk == key) { r = (int)idw - 1; break; }
+        slot = (slot + 1) & (S - 1);
+        probe++;
+      }
+      if (probe >= S) r = -1;
+      if (r != SH_RETRY) { res = r; pending = false; }
+    }
+    if (++rounds > (1 << 20)) break;
+  }
+  return res;
+}
+
+// KMODE: 0 = direct-mapped ids (small dense integer keys), 1 = CTA key table, 2 = CTA key table over hash-partitioned rows.
 // Histogram word of a group in a tile: low 16 bits = rows with a value (after the scan: offset of the group's
 // segment), high 16 bits = rows whose value is NULL.  One native atomic per row serves both counts.
-template <int NT, typename VT, int FLAGS, int GPT, bool DENSE, bool PLAIN>
+template <int NT, typename VT, int FLAGS, int GPT, int KMODE, bool PLAIN>
 __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
   using T = ValTraits<VT>;
   constexpr bool IS_INT = T::is_int;
   constexpr bool ALL = FLAGS == GB_ALL;
+  constexpr bool DENSE = KMODE == 0, PART = KMODE == 2;
   constexpr int RPT = TS_T / NT, WROWS = 32 * RPT, NWARPS = NT / 32;
   constexpr int NP = NT * GPT, NPAD = NP + 32;
   constexpr uint32_t TRASH = NP + 8;                                 // histogram slot of rows that are not aggregated here
@@ -135,12 +237,12 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
   u64* ktab_key = mbar + 2;                                          // [S]  (hashed keys only)
   const int S = p.sh_slots, cap = p.sh_cap;
   uint32_t* ktab_id = reinterpret_cast<uint32_t*>(ktab_key + S);     // [S]
+  u64* idkey = reinterpret_cast<u64*>(ktab_id + S);                  // [cap + 1] id -> key (hashed keys only)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t a_mbar = sm_addr(mbar), a_stage = sm_addr(stage), a_sorted = sm_addr(sorted);
-  const long long n = p.n;
-  const long long ntiles = (n + TS_T - 1) / TS_T;
-  const u64* vals = reinterpret_cast<const u64*>(p.val);
+  const u64* vals = PART ? p.part_vals : reinterpret_cast<const u64*>(p.val);
   const u64 dense_base = (u64)p.sh_dense_base;
+  const int slot_lsh = PART ? p.part_bits : 0, slot_rsh = 32 - p.sh_log_slots;   // key table slot = (hash32 << lsh) >> rsh
 
   for (int i = tid; i < 2 * NPAD; i += NT) H[i] = 0;
   if (!DENSE) for (int i = tid; i < S; i += NT) ktab_id[i] = 0;
@@ -149,40 +251,64 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
   __syncthreads();
 
   TsAcc<VT, FLAGS> acc[GPT];
+  auto reset_acc = [&]() {
 #pragma unroll
-  for (int s = 0; s < GPT; s++) { acc[s].rows = 0; acc[s].n = 0; acc[s].piv = 0; acc[s].S1 = 0.0; acc[s].S2 = 0.0; acc[s].mn = T::min_init(); acc[s].mx = T::max_init(); acc[s].isum = 0; }
+    for (int s = 0; s < GPT; s++) { acc[s].rows = 0; acc[s].n = 0; acc[s].piv = 0; acc[s].S1 = 0.0; acc[s].S2 = 0.0; acc[s].mn = T::min_init(); acc[s].mx = T::max_init(); acc[s].isum = 0; }
+  };
+  reset_acc();
 
-  long long tile = blockIdx.x;
-  // values of tile `t` -> stage: one bulk copy when the tile is full, a plain copy loop otherwise
-  auto issue_vals = [&](long long t) {
-    if ((t + 1) * (long long)TS_T <= n) {
+  // values of a tile -> stage: one bulk copy when the whole tile exists in memory, a plain copy loop otherwise
+  auto tile_bulk = [&](const TsItem& it) { return PART || it.valid == TS_T; };
+  auto issue_vals = [&](const TsItem& it) {
+    if (tile_bulk(it)) {
       if (tid == 0) {
         fence_proxy_async();
         mbar_expect_tx(a_mbar, TS_T * 8);
 #pragma unroll
-        for (int c = 0; c < 4; c++) bulk_g2s(a_stage + c * (TS_T * 2), vals + t * TS_T + c * (TS_T / 4), TS_T * 2, a_mbar);
+        for (int c = 0; c < 4; c++) bulk_g2s(a_stage + c * (TS_T * 2), vals + it.base + c * (TS_T / 4), TS_T * 2, a_mbar);
       }
     } else {
-      for (int i = tid; i < TS_T; i += NT) { const long long row = t * TS_T + i; stage[i] = row < n ? __ldg(vals + row) : 0ull; }
+      for (int i = tid; i < TS_T; i += NT) stage[i] = i < it.valid ? __ldg(vals + it.base + i) : 0ull;
     }
   };
+  // one pre-aggregated batch per (CTA, group) into the global table
+  auto flush = [&]() {
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < GPT; s++) {
+      const uint32_t gid = ts_perm<NT>((uint32_t)(tid + s * NT));
+      const bool have = acc[s].rows != 0;
+      const bool nullgroup = have && gid == (uint32_t)cap;
+      u64 w[1] = {0};
+      if (have && !nullgroup) w[0] = DENSE ? dense_base + gid : idkey[gid];
+      long long gs = g_find_or_insert<1>(p.gt, w, have && !nullgroup);
+      if (nullgroup) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
+      if (!have || gs < 0) continue;
+      if (p.count_rows) atomicAdd(&p.gt.hdr[gs].rowsw, (u64)acc[s].rows);
+      u64 mnc = 0, mxo = 0;
+      if (ALL && acc[s].n) { mnc = ~T::ord(acc[s].mn); mxo = T::ord(acc[s].mx); }
+      g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, (u64)acc[s].n, __longlong_as_double((long long)acc[s].piv), acc[s].piv != 0, acc[s].S1, acc[s].S2, acc[s].isum, mnc, mxo);
+    }
+  };
+
+  TsItem cur = ts_first_item<PART>(p);
   TsRows<RPT> r;
-  if (tile < ntiles) { issue_vals(tile); ts_load<RPT, PLAIN>(p, tile * TS_T + (long long)warp * WROWS, lane, r); }
+  if (cur.valid) { issue_vals(cur); ts_load<RPT, PLAIN, PART>(p, cur, warp, lane, r); }
   uint32_t tma_phase = 0;
   const int sh2 = (2 * lane) & 31;
   const uint32_t vm0 = 1u << sh2, vm1 = 2u << sh2;      // this lane's two bits in a bitmap word
   int b = 0;
 #pragma unroll 1
-  for (; tile < ntiles; tile += gridDim.x, b ^= 1) {
+  for (; cur.valid; b ^= 1) {
+    const TsItem nxt = ts_next_item<PART>(p, cur);
     uint32_t* Hc = H + b * NPAD;
     const uint32_t a_h = sm_addr(Hc);
-    const long long tbase = tile * TS_T;
-    const bool tile_full = tbase + TS_T <= n;
+    const bool tile_tma = tile_bulk(cur);
     // ---- phase 1: group ids, tile histogram (the atomic's return value ranks the row inside its group)
     uint32_t pack[RPT];
     uint32_t skipmask = 0, zeromask = 0;
-    const bool fast = PLAIN && DENSE && __all_sync(0xFFFFFFFFu, r.act == (1u << RPT) - 1u);
-    if (fast) {
+    const bool fullw = __all_sync(0xFFFFFFFFu, r.act == (1u << RPT) - 1u);
+    if (PLAIN && DENSE && fullw) {
       // every row is inside the column, no filter, no NULL keys, direct-mapped ids: ~16 instructions per row
       bool bad = false;
 #pragma unroll
@@ -208,10 +334,79 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
 #pragma unroll
           for (int qq = 0; qq < RPT; qq++) if (qq == q) kq = r.k[qq];
           const bool sp = kq - dense_base >= (u64)cap;
-          const long long row = tbase + warp * WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
+          const long long row = cur.base + warp * WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
           u64 vb = 0;
           bool vnull = false;
           if (sp) { vb = __ldg(vals + row); vnull = p.vnull && pdrs_bit(p.vnull, row); }
+          gb_spill_rows<1, VT, FLAGS>(p.gt, kq, 0ull, 0ull, sp, p.count_rows != 0, !vnull, T::from_bits(vb));
+        }
+      }
+    } else if (PLAIN && !DENSE) {
+      // no filter, no NULL keys; key -> id through the CTA key table: up to three lock-free probes per row
+      // (the table runs at a load factor <= 1/4, so > 90% of the rows hit their home slot), insertion of new keys
+      // and longer probe sequences in the warp-synchronous slow path
+      uint32_t slowmask = 0, ids[RPT];
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        uint32_t slot = (ts_hash32(r.k[q]) << slot_lsh) >> slot_rsh;
+        uint32_t id = 0xFFFFFFFFu;
+        bool done = false;
+#pragma unroll
+        for (int pr = 0; pr < 3; pr++) {
+          if (!done) {
+            const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
+            const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
+            if (idw == 0 || idw == SH_BUSY) done = true;                       // new key / being inserted: slow path
+            else if (kk == r.k[q]) { id = idw - 1; done = true; }
+            else slot = (slot + 1) & (S - 1);
+          }
+        }
+        ids[q] = id;
+        if (id == 0xFFFFFFFFu && ((r.act >> q) & 1u)) slowmask |= 1u << q;
+      }
+      uint32_t spillmask = 0;
+      if (__any_sync(0xFFFFFFFFu, slowmask != 0)) {
+#pragma unroll 1
+        for (int q = 0; q < RPT; q++) {
+          if (!__any_sync(0xFFFFFFFFu, (slowmask >> q) & 1u)) continue;
+          u64 kq = 0;
+#pragma unroll
+          for (int qq = 0; qq < RPT; qq++) if (qq == q) kq = r.k[qq];
+          const bool need = (slowmask >> q) & 1u;
+          const int id = ts_insert(ktab_key, ktab_id, misc, S, cap, kq, (ts_hash32(kq) << slot_lsh) >> slot_rsh, need);
+          if (need) {
+            if (id >= 0) {
+              idkey[id] = kq;            // benign duplicate stores of the same value
+#pragma unroll
+              for (int qq = 0; qq < RPT; qq++) if (qq == q) ids[qq] = (uint32_t)id;
+            } else spillmask |= 1u << q;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RPT / 2; j++) {
+        const uint32_t vw = PART ? 0u : __shfl_sync(0xFFFFFFFFu, r.vnw, 2 * j + (lane >> 4));
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int q = 2 * j + h;
+          const bool ok = ids[q] != 0xFFFFFFFFu && ((r.act >> q) & 1u);
+          const bool vnull = PART ? ((r.fl[j] >> (8 * h)) & 1u) != 0 : (vw & (h ? vm1 : vm0)) != 0;
+          const uint32_t pp = ok ? ts_perm<NT>(ids[q]) : TRASH;
+          const uint32_t old = sm_atom_add32(a_h + pp * 4u, vnull ? 0x10000u : 1u);
+          if (!ok || vnull) skipmask |= 1u << q;
+          pack[q] = pp | (old << 16);
+        }
+      }
+      if (__any_sync(0xFFFFFFFFu, spillmask != 0)) {   // rare: CTA key table full -> global table
+#pragma unroll 1
+        for (int q = 0; q < RPT; q++) {
+          const bool sp = (spillmask >> q) & 1u;
+          const long long row = cur.base + warp * WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
+          u64 vb = 0, kq = 0;
+          bool vnull = false;
+#pragma unroll
+          for (int qq = 0; qq < RPT; qq++) if (qq == q) kq = r.k[qq];
+          if (sp) { vb = __ldg(vals + row); vnull = PART ? (p.part_flags && (p.part_flags[row] & 1)) : (p.vnull && pdrs_bit(p.vnull, row)); }
           gb_spill_rows<1, VT, FLAGS>(p.gt, kq, 0ull, 0ull, sp, p.count_rows != 0, !vnull, T::from_bits(vb));
         }
       }
@@ -235,24 +430,10 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
           const u64 off = r.k[q] - dense_base;
           ok = off < (u64)cap;
           gid = (uint32_t)off;
-        } else {                            // CTA-shared key table: lock-free probes first, insertion in the slow path
-          uint32_t slot = (uint32_t)(key_hash<1>({r.k[q]}) >> (64 - p.sh_log_slots));
-          ok = false;
-          bool miss = false;
-#pragma unroll 1
-          for (int pr = 0; pr < 8 && !ok && !miss; pr++) {
-            const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
-            const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
-            if (idw == 0 || idw == SH_BUSY) miss = true;
-            else if (kk == r.k[q]) { ok = true; gid = idw - 1; }
-            slot = (slot + 1) & (S - 1);
-          }
-          const bool need = active && !knull && !ok;
-          if (__any_sync(0xFFFFFFFFu, need)) {
-            u64 w[1] = {r.k[q]};
-            const int id = sh_lookup<1>(ktab_key, ktab_id, misc, S, p.sh_log_slots, cap, w, need);
-            if (need && id >= 0) { ok = true; gid = (uint32_t)id; }
-          }
+        } else {
+          const int id = ts_insert(ktab_key, ktab_id, misc, S, cap, r.k[q], (ts_hash32(r.k[q]) << slot_lsh) >> slot_rsh, active && !knull);
+          ok = active && !knull && id >= 0;
+          if (ok) { gid = (uint32_t)id; idkey[id] = r.k[q]; }
         }
         if (!PLAIN) { ok = ok && !knull; if (knull) { gid = (uint32_t)cap; ok = true; } }
         if (active && !ok) spillmask |= 1u << q;
@@ -266,14 +447,14 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
 #pragma unroll 1
         for (int q = 0; q < RPT; q++) {
           const bool sp = (spillmask >> q) & 1u;
-          const long long row = tbase + warp * WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
+          const long long row = cur.base + warp * WROWS + 64 * (q >> 1) + 2 * lane + (q & 1);
           u64 vb = 0, kq = 0;
           bool vnull = false;
 #pragma unroll
           for (int qq = 0; qq < RPT; qq++) if (qq == q) kq = r.k[qq];
           if (sp) {
             vb = __ldg(vals + row);
-            vnull = p.vnull && pdrs_bit(p.vnull, row);
+            vnull = !PART && p.vnull && pdrs_bit(p.vnull, row);
             if (vnull && p.compat_nulls) { vnull = false; vb = 0; }
           }
           gb_spill_rows<1, VT, FLAGS>(p.gt, kq, 0ull, 0ull, sp, p.count_rows != 0, !vnull, T::from_bits(vb));
@@ -281,7 +462,7 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
       }
     }
     // keys (and bitmap words) of this CTA's next tile: in flight during phases 2-4
-    if (tile + gridDim.x < ntiles) ts_load<RPT, PLAIN>(p, (tile + gridDim.x) * TS_T + (long long)warp * WROWS, lane, r);
+    if (nxt.valid) ts_load<RPT, PLAIN, PART>(p, nxt, warp, lane, r);
     __syncthreads();
     // ---- phase 2: exclusive scan of the histogram (thread t owns entries [t * GPT, t * GPT + GPT))
     {
@@ -311,7 +492,7 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
       uint32_t pos[RPT];
 #pragma unroll
       for (int q = 0; q < RPT; q++) pos[q] = (sm_ld32(a_h + (pack[q] & 0xFFFFu) * 4u) & 0xFFFFu) + (pack[q] >> 16);
-      if (tile_full) { while (!mbar_try_wait(a_mbar, tma_phase)) {} tma_phase ^= 1u; }
+      if (tile_tma) { while (!mbar_try_wait(a_mbar, tma_phase)) {} tma_phase ^= 1u; }
       const uint32_t a_src = a_stage + (uint32_t)(warp * WROWS + 2 * lane) * 8u;
 #pragma unroll
       for (int j = 0; j < RPT / 2; j++) {
@@ -326,7 +507,7 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
       }
     }
     __syncthreads();
-    if (tile + gridDim.x < ntiles) issue_vals(tile + gridDim.x);   // stage is free: values of the next tile
+    if (nxt.valid) issue_vals(nxt);   // stage is free: values of the next tile
     // ---- phase 4: every thread reduces the segments of the groups it owns
     bool heavy[GPT];
     uint32_t hoff[GPT], hend[GPT];
@@ -397,38 +578,26 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
     }
     // no barrier here: the next tile's phase 1 only touches the other histogram buffer, and its scatter into
     // `sorted` comes after that tile's first barrier, which every thread reaches only after this phase
+    if (PART && cur.last) {              // end of a partition: flush its groups, start over with empty tables
+      flush();
+      __syncthreads();
+      reset_acc();
+      for (int i = tid; i < S; i += NT) ktab_id[i] = 0;
+      if (tid == 0) misc[0] = 0;
+      __syncthreads();
+    }
+    cur = nxt;
   }
-  __syncthreads();
-
-  // ---- flush: one pre-aggregated batch per (CTA, group)
-  u64* idkey = sorted;      // id -> key (hashed keys)
-  if (!DENSE) {
-    for (int s = tid; s < S; s += NT) { const uint32_t idw = ktab_id[s]; if (idw != 0 && idw != SH_BUSY) idkey[idw - 1] = ktab_key[s]; }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int s = 0; s < GPT; s++) {
-    const uint32_t gid = ts_perm<NT>((uint32_t)(tid + s * NT));
-    const bool have = acc[s].rows != 0;
-    const bool nullgroup = have && gid == (uint32_t)cap;
-    u64 w[1] = {0};
-    if (have && !nullgroup) w[0] = DENSE ? dense_base + gid : idkey[gid];
-    long long gs = g_find_or_insert<1>(p.gt, w, have && !nullgroup);
-    if (nullgroup) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
-    if (!have || gs < 0) continue;
-    if (p.count_rows) atomicAdd(&p.gt.hdr[gs].rowsw, (u64)acc[s].rows);
-    u64 mnc = 0, mxo = 0;
-    if (ALL && acc[s].n) { mnc = ~T::ord(acc[s].mn); mxo = T::ord(acc[s].mx); }
-    g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, (u64)acc[s].n, __longlong_as_double((long long)acc[s].piv), acc[s].piv != 0, acc[s].S1, acc[s].S2, acc[s].isum, mnc, mxo);
-  }
+  if (!PART) flush();
 }
 
 template <int NT, typename VT, int FLAGS, int GPT>
 cudaError_t ts_launch4(const GbParams& p, int ctas, size_t smem, cudaStream_t s) {
   const bool plain = !p.fbits && !p.compat_nulls && !p.ks.c[0].nulls;
-  auto k = gb_tsort_kernel<NT, VT, FLAGS, GPT, true, true>;
-  if (p.sh_dense) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, true, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, true, false>;
-  else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, false, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, false, false>;
+  auto k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true>;
+  if (p.part_keys) k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 2, true>;
+  else if (p.sh_dense) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, false>;
+  else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<ctas, NT, smem, s>>>(p);
@@ -443,15 +612,21 @@ cudaError_t ts_launch2(const GbParams& p, int nt, int gpt, int ctas, size_t smem
 }  // namespace
 
 // Geometry: cap + 1 group ids over nt * gpt owners (nt threads, gpt groups per thread).  Returns false when the
-// group count does not fit.  nt_pref: 0 = auto, else 512 / 1024.
+// group count does not fit.  nt_pref: 0 = auto, else 512 / 1024.  Hashed keys: the key table gets >= 4 slots per id
+// when shared memory allows (load factor <= 1/4), else >= 2.
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem) {
   if (cap + 1 > 2048) return false;
   const int t = nt_pref == 1024 ? 1024 : 512;
   const int g = cap + 1 <= 1024 ? 1024 / t : 2048 / t;
-  long long S = 0;
-  if (!dense) { S = 64; while (S < cap + cap / 2) S <<= 1; }
   const size_t np = (size_t)t * g;
-  const size_t bytes = (size_t)TS_T * 16 + 2 * (np + 32) * 4 + 32 * 4 + 16 + 16 + (size_t)S * 12;
+  const size_t fixed = (size_t)TS_T * 16 + 2 * (np + 32) * 4 + 32 * 4 + 16 + 16;
+  long long S = 0;
+  if (!dense) {
+    S = 64;
+    while (S < 4 * cap) S <<= 1;
+    while (S > 2 * cap && fixed + (size_t)S * 12 + (size_t)(cap + 1) * 8 > (size_t)smem_budget) S >>= 1;
+  }
+  const size_t bytes = fixed + (size_t)S * 12 + (dense ? 0 : (size_t)(cap + 1) * 8);
   if (bytes > (size_t)smem_budget) return false;
   *nt = t; *gpt = g; *slots = (int)S; *smem = bytes;
   return true;

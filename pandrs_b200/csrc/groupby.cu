@@ -209,6 +209,7 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
 }
 
 int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, float* kernel_ms);   // gb_radix.cu
+int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty);   // gb_part.cu
 // gb_tsort.cu
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
@@ -438,7 +439,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   TableMem tm;
   std::vector<DevBuf> states(passes.size());
   u64 cn[CNT_N + 1] = {0};
-  bool radix_used = false;
+  bool radix_used = false, restart = false;
+  bool part_ok = c->opt_part != 0 && c->opts.groupby_algo == PDRS_GB_AUTO;
   (void)radix_used;
   for (int attempt = 0;; attempt++) {
     if (attempt > 6) return pdrs_fail(c, PDRS_ERR_OOM, "groupby: hash table kept overflowing after %d retries", attempt);
@@ -469,6 +471,16 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           gp.gt.st = states[i].as<GState>();
           gp.val = vv[passes[i].val].data;
           gp.vnull = vv[passes[i].val].nulls;
+        }
+        // high cardinality, one 64-bit key column: hash-partition the rows, tile-sort kernel per partition (gb_part.cu)
+        if (variant == 0 && part_ok && !ts_fit && algo != PDRS_GB_GLOBAL && passes[i].val >= 0 && est > 2047) {
+          float ms = 0;
+          bool dirty = false;
+          int32_t rs = gb_part_pass(c, gp, passes[i].is_int, passes[i].flags, est, &ms, &dirty);
+          if (rs == PDRS_OK) { c->stats.main_kernel_ms += ms; c->stats.groupby_algo_used = PDRS_GB_PARTITIONED; continue; }
+          if (rs != PDRS_ERR_UNSUPPORTED) return rs;
+          part_ok = false;
+          if (dirty || i > 0) { restart = true; break; }     // the table already holds counts of this attempt: start over without this path
         }
         // high cardinality, one 64-bit key column: radix-partitioned rows + L2-resident table regions (gb_radix.cu)
         const size_t tbytes = (size_t)(slots + 1) * (sizeof(GHdr) + (gp.gt.st ? sizeof(GState) : 0));
@@ -502,6 +514,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
         }
       }
     }
+    if (restart) { restart = false; for (auto& s : states) s.release(); attempt--; continue; }
     PDRS_TRY(read_counters(c, tm, cn));
     c->stats.spilled_rows = (int64_t)cn[CNT_SPILLED];
     if (cn[CNT_OVERFLOW] == 0 && cn[CNT_SPIN_FAIL] == 0) break;

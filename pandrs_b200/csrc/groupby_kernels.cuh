@@ -81,6 +81,9 @@ struct GbParams {
   int sh_cap, sh_slots, sh_log_slots, sh_ng;   // shared-memory kernel geometry
   int sh_dense;                  // single I64 key: id = key - sh_dense_base when 0 <= id < sh_cap (no key table)
   long long sh_dense_base;
+  // tile-sort kernel over hash-partitioned rows (gb_tsort.cu): partition q owns rows [q * part_cap, q * part_cap + part_cnt[q])
+  // of part_keys / part_vals (no NULLs, filter already applied); part_bits = log2(number of partitions)
+  const u64* part_keys; const u64* part_vals; const uint8_t* part_flags /* 1 = value is NULL; may be NULL */; const u64* part_cnt; long long part_cap; int part_bits;
 };
 
 // ---------------------------------------------------------------- small device helpers
