@@ -51,10 +51,12 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
   extern __shared__ __align__(16) unsigned char gsm[];
   u64* st_key = reinterpret_cast<u64*>(gsm);              // [GP_TILE]
   u64* st_val = st_key + GP_TILE;                         // [GP_TILE]
-  uint32_t* H = reinterpret_cast<uint32_t*>(st_val + GP_TILE);   // [256 + 32] counts -> exclusive offsets
-  uint32_t* G = H + 288;                                  // [256] reserved start inside the output bucket
-  uint32_t* QB = G + 256;                                 // [256] output bucket of local bucket b
+  uint32_t* st_dst = reinterpret_cast<uint32_t*>(st_val + GP_TILE);   // [GP_TILE] output position of the staged row
+  uint32_t* H = st_dst + GP_TILE;                         // [256 + 32] bucket counts of the tile
+  uint2* HD = reinterpret_cast<uint2*>(H + 288);          // [256] {offset of the bucket in the staging area, output position of its first row}
+  uint32_t* QB = reinterpret_cast<uint32_t*>(HD + 256);   // [256] output bucket of local bucket b
   uint8_t* st_fl = reinterpret_cast<uint8_t*>(QB + 256);  // [GP_TILE] (only when the value column has NULLs)
+  __shared__ uint32_t sh_total;
   __shared__ uint32_t wsum[GP_NT / 32];
   const int nb = 1 << local_bits;
   const uint32_t lmask = (uint32_t)nb - 1u;
@@ -121,10 +123,11 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
       if (lane == 31) wsum[warp] = incl;
-      uint32_t g = 0;
+      uint32_t g = 0xFFFFFFFFu;
       if (c) {
         const u64 at = atomicAdd(&cursor[QB[tid]], (u64)c);
-        if (at + c > (u64)cap_out) { atomicAdd(overflow, 1ull); g = 0xFFFFFFFFu; } else g = (uint32_t)at;
+        if (at + c > (u64)cap_out) atomicAdd(overflow, 1ull);          // the caller discards this partitioning
+        else g = (uint32_t)((u64)QB[tid] * (u64)cap_out + at);        // < 2^32 (checked by the caller)
       }
       __syncthreads();
       uint32_t ws = lane < GP_NT / 32 ? wsum[lane] : 0u;
@@ -132,26 +135,29 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
       const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
       const uint32_t excl = (warp ? wprefix : 0u) + incl - c;
-      if (tid < 288) H[tid] = excl;           // H[nb .. 287] = total
-      if (tid < 256) G[tid] = g;
+      if (tid < 256) HD[tid] = make_uint2(excl, g);
+      if (tid == GP_NT - 1) sh_total = excl + c;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < GP_ITEMS; j++) {
       if (br[j] == 0xFFFFFFFFu) continue;
-      const uint32_t pos = H[br[j] >> 16] + (br[j] & 0xFFFFu);
+      const uint2 hd = HD[br[j] >> 16];
+      const uint32_t rank = br[j] & 0xFFFFu, pos = hd.x + rank;
       st_key[pos] = key[j];
       st_val[pos] = val[j];
+      st_dst[pos] = hd.y == 0xFFFFFFFFu ? 0xFFFFFFFFu : hd.y + rank;
       if (out_flags) st_fl[pos] = (uint8_t)((vnullmask >> j) & 1u);
     }
     if (t0 + tstride < lim) load_tile(t0 + tstride);      // next tile: in flight during the write-out below
     __syncthreads();
-    for (int b = warp; b < nb; b += GP_NT / 32) {     // one warp per bucket run
-      const uint32_t off = H[b], cnt = H[b + 1] - off, g = G[b];
-      if (cnt == 0 || g == 0xFFFFFFFFu) continue;     // overflow: the caller discards this partitioning
-      const long long dst = (long long)QB[b] * cap_out + g;
-      for (uint32_t i = lane; i < cnt; i += 32) { out_keys[dst + i] = st_key[off + i]; out_vals[dst + i] = st_val[off + i]; }
-      if (out_flags) for (uint32_t i = lane; i < cnt; i += 32) out_flags[dst + i] = st_fl[off + i];
+    const uint32_t total = sh_total;
+    for (uint32_t pos = tid; pos < total; pos += GP_NT) {   // consecutive staged rows of a bucket go to consecutive output rows
+      const uint32_t d = st_dst[pos];
+      if (d == 0xFFFFFFFFu) continue;
+      out_keys[d] = st_key[pos];
+      out_vals[d] = st_val[pos];
+      if (out_flags) out_flags[d] = st_fl[pos];
     }
     __syncthreads();
   }
@@ -177,7 +183,8 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   const long long nb1 = 1ll << bits1, nparts = 1ll << bits;
   const long long cap1 = round_up(n / nb1 + n / (nb1 * 32) + 65536, T);
   const long long cap2 = bits2 ? round_up(n / nparts + n / (nparts * 8) + 8192, T) : cap1;
-  const size_t need = (size_t)nb1 * cap1 * 16 + (bits2 ? (size_t)nparts * cap2 * 16 : 0);
+  if ((unsigned long long)nb1 * cap1 >= (1ull << 32) || (unsigned long long)nparts * cap2 >= (1ull << 32)) return PDRS_ERR_UNSUPPORTED;   // 32-bit output positions
+  const size_t need = (size_t)nb1 * cap1 * 17 + (bits2 ? (size_t)nparts * cap2 * 17 : 0);
   size_t free_b = 0, total_b = 0;
   PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   if (need + (2ull << 30) > free_b) return PDRS_ERR_UNSUPPORTED;
@@ -196,7 +203,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   PDRS_TRY(k1.alloc(c, (size_t)nb1 * cap1 * 8));
   PDRS_TRY(v1.alloc(c, (size_t)nb1 * cap1 * 8));
   if (has_flags) PDRS_TRY(f1.alloc(c, (size_t)nb1 * cap1 + 64));
-  const size_t smem = (size_t)GP_TILE * 17 + (288 + 256 + 256) * 4;
+  const size_t smem = (size_t)GP_TILE * 21 + (288 + 512 + 256) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
