@@ -49,13 +49,10 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
                                                           u64* __restrict__ out_keys, u64* __restrict__ out_vals, uint8_t* __restrict__ out_flags,
                                                           u64* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char gsm[];
-  u64* st_key = reinterpret_cast<u64*>(gsm);              // [GP_TILE]
-  u64* st_val = st_key + GP_TILE;                         // [GP_TILE]
-  uint32_t* st_dst = reinterpret_cast<uint32_t*>(st_val + GP_TILE);   // [GP_TILE] output position of the staged row
+  ulonglong2* st_kv = reinterpret_cast<ulonglong2*>(gsm);      // [GP_TILE] staged (key, value)
+  uint32_t* st_dst = reinterpret_cast<uint32_t*>(st_kv + GP_TILE);   // [GP_TILE] output position of the staged row (< 2^31), bit 31 = value is NULL
   uint32_t* H = st_dst + GP_TILE;                         // [256 + 32] bucket counts of the tile
   uint2* HD = reinterpret_cast<uint2*>(H + 288);          // [256] {offset of the bucket in the staging area, output position of its first row}
-  uint32_t* QB = reinterpret_cast<uint32_t*>(HD + 256);   // [256] output bucket of local bucket b
-  uint8_t* st_fl = reinterpret_cast<uint8_t*>(QB + 256);  // [GP_TILE] (only when the value column has NULLs)
   __shared__ uint32_t sh_total;
   __shared__ uint32_t wsum[GP_NT / 32];
   const int nb = 1 << local_bits;
@@ -111,9 +108,7 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
         if ((vn >> lane) & 1u) { if (in.compat_nulls) val[j] = 0; else vnullmask |= 1u << j; }
       } else if (fl[j] & 1u) vnullmask |= 1u << j;
       if (!live) continue;
-      const uint32_t q = gp_hash32(key[j]) >> hash_shr;
-      const uint32_t b = q & lmask;
-      QB[b] = q;                      // every row of local bucket b carries the same q (same level-1 bucket)
+      const uint32_t b = (gp_hash32(key[j]) >> hash_shr) & lmask;
       br[j] = (b << 16) | atomicAdd(&H[b], 1u);
     }
     __syncthreads();
@@ -125,9 +120,11 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
       if (lane == 31) wsum[warp] = incl;
       uint32_t g = 0xFFFFFFFFu;
       if (c) {
-        const u64 at = atomicAdd(&cursor[QB[tid]], (u64)c);
+        // output bucket: level 1 = the local bucket; level 2 = (level-1 bucket of this CTA's rows) * 2^bits + local bucket
+        const u64 q = FROM_COLS ? (u64)tid : (((u64)blockIdx.y << local_bits) | (u64)tid);
+        const u64 at = atomicAdd(&cursor[q], (u64)c);
         if (at + c > (u64)cap_out) atomicAdd(overflow, 1ull);          // the caller discards this partitioning
-        else g = (uint32_t)((u64)QB[tid] * (u64)cap_out + at);        // < 2^32 (checked by the caller)
+        else g = (uint32_t)(q * (u64)cap_out + at);                   // < 2^31 (checked by the caller)
       }
       __syncthreads();
       uint32_t ws = lane < GP_NT / 32 ? wsum[lane] : 0u;
@@ -144,20 +141,20 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
       if (br[j] == 0xFFFFFFFFu) continue;
       const uint2 hd = HD[br[j] >> 16];
       const uint32_t rank = br[j] & 0xFFFFu, pos = hd.x + rank;
-      st_key[pos] = key[j];
-      st_val[pos] = val[j];
-      st_dst[pos] = hd.y == 0xFFFFFFFFu ? 0xFFFFFFFFu : hd.y + rank;
-      if (out_flags) st_fl[pos] = (uint8_t)((vnullmask >> j) & 1u);
+      st_kv[pos] = make_ulonglong2(key[j], val[j]);
+      st_dst[pos] = hd.y == 0xFFFFFFFFu ? 0xFFFFFFFFu : ((hd.y + rank) | (((vnullmask >> j) & 1u) << 31));
     }
     if (t0 + tstride < lim) load_tile(t0 + tstride);      // next tile: in flight during the write-out below
     __syncthreads();
     const uint32_t total = sh_total;
     for (uint32_t pos = tid; pos < total; pos += GP_NT) {   // consecutive staged rows of a bucket go to consecutive output rows
-      const uint32_t d = st_dst[pos];
-      if (d == 0xFFFFFFFFu) continue;
-      out_keys[d] = st_key[pos];
-      out_vals[d] = st_val[pos];
-      if (out_flags) out_flags[d] = st_fl[pos];
+      const uint32_t dd = st_dst[pos];
+      if (dd == 0xFFFFFFFFu) continue;
+      const uint32_t d = dd & 0x7FFFFFFFu;
+      const ulonglong2 kv = st_kv[pos];
+      out_keys[d] = kv.x;
+      out_vals[d] = kv.y;
+      if (out_flags) out_flags[d] = (uint8_t)(dd >> 31);
     }
     __syncthreads();
   }
@@ -183,7 +180,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   const long long nb1 = 1ll << bits1, nparts = 1ll << bits;
   const long long cap1 = round_up(n / nb1 + n / (nb1 * 32) + 65536, T);
   const long long cap2 = bits2 ? round_up(n / nparts + n / (nparts * 8) + 8192, T) : cap1;
-  if ((unsigned long long)nb1 * cap1 >= (1ull << 32) || (unsigned long long)nparts * cap2 >= (1ull << 32)) return PDRS_ERR_UNSUPPORTED;   // 32-bit output positions
+  if ((unsigned long long)nb1 * cap1 >= (1ull << 31) || (unsigned long long)nparts * cap2 >= (1ull << 31)) return PDRS_ERR_UNSUPPORTED;   // 31-bit output positions
   const size_t need = (size_t)nb1 * cap1 * 17 + (bits2 ? (size_t)nparts * cap2 * 17 : 0);
   size_t free_b = 0, total_b = 0;
   PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
@@ -203,7 +200,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   PDRS_TRY(k1.alloc(c, (size_t)nb1 * cap1 * 8));
   PDRS_TRY(v1.alloc(c, (size_t)nb1 * cap1 * 8));
   if (has_flags) PDRS_TRY(f1.alloc(c, (size_t)nb1 * cap1 + 64));
-  const size_t smem = (size_t)GP_TILE * 21 + (288 + 512 + 256) * 4;
+  const size_t smem = (size_t)GP_TILE * 20 + (288 + 512) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -26,7 +26,8 @@
 
 namespace {
 
-constexpr int TS_T = 8192;               // rows per tile
+constexpr int TS_T = 8192;               // rows per tile (4096 in the two-CTAs-per-SM geometry of 256 threads)
+template <int NT> struct TsGeom { static constexpr int TT = NT == 256 ? 4096 : 8192; static constexpr int CTAS = NT == 256 ? 2 : 1; };
 constexpr int TS_HEAVY = 64;             // longer segments are reduced by the whole warp
 
 // Group id -> histogram position.  XORs the low bits of the id into the warp field so that consecutive ids (dense
@@ -60,43 +61,43 @@ template <int RPT> struct TsRows {
 // of the columns.  Partitioned input: the tiles of partitions blockIdx, blockIdx + grid, ...; `last` marks the last
 // tile of a partition (the CTA then flushes its groups and starts over with empty tables).
 struct TsItem { long long base; long long part; int valid; int last; };
-template <bool PART>
+template <bool PART, int TT>
 __device__ __forceinline__ TsItem ts_first_item(const GbParams& p) {
   TsItem it;
   it.part = blockIdx.x; it.last = 0;
   if (!PART) {
-    it.base = (long long)blockIdx.x * TS_T;
-    it.valid = it.base < p.n ? (int)min((long long)TS_T, p.n - it.base) : 0;
+    it.base = (long long)blockIdx.x * TT;
+    it.valid = it.base < p.n ? (int)min((long long)TT, p.n - it.base) : 0;
     return it;
   }
   const long long nparts = 1ll << p.part_bits;
   it.base = 0; it.valid = 0;
   while (it.part < nparts) {
     const long long c = min((long long)__ldg(p.part_cnt + it.part), p.part_cap);
-    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TS_T, c); it.last = c <= TS_T; return it; }
+    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TT, c); it.last = c <= TT; return it; }
     it.part += gridDim.x;
   }
   return it;
 }
-template <bool PART>
+template <bool PART, int TT>
 __device__ __forceinline__ TsItem ts_next_item(const GbParams& p, const TsItem& cur) {
   TsItem it = cur;
   if (!PART) {
-    it.base = cur.base + (long long)gridDim.x * TS_T;
-    it.valid = it.base < p.n ? (int)min((long long)TS_T, p.n - it.base) : 0;
+    it.base = cur.base + (long long)gridDim.x * TT;
+    it.valid = it.base < p.n ? (int)min((long long)TT, p.n - it.base) : 0;
     return it;
   }
   const long long nparts = 1ll << p.part_bits;
   if (!cur.last) {
     const long long c = min((long long)__ldg(p.part_cnt + cur.part), p.part_cap);
-    const long long off = cur.base - cur.part * p.part_cap + TS_T;
-    it.base = cur.base + TS_T; it.valid = (int)min((long long)TS_T, c - off); it.last = c - off <= TS_T;
+    const long long off = cur.base - cur.part * p.part_cap + TT;
+    it.base = cur.base + TT; it.valid = (int)min((long long)TT, c - off); it.last = c - off <= TT;
     return it;
   }
   it.valid = 0; it.last = 0;
   for (it.part = cur.part + gridDim.x; it.part < nparts; it.part += gridDim.x) {
     const long long c = min((long long)__ldg(p.part_cnt + it.part), p.part_cap);
-    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TS_T, c); it.last = c <= TS_T; return it; }
+    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TT, c); it.last = c <= TT; return it; }
   }
   return it;
 }
@@ -219,18 +220,19 @@ __device__ __noinline__ int ts_insert(u64* ktab_key, uint32_t* ktab_id, uint32_t
 // Histogram word of a group in a tile: low 16 bits = rows with a value (after the scan: offset of the group's
 // segment), high 16 bits = rows whose value is NULL.  One native atomic per row serves both counts.
 template <int NT, typename VT, int FLAGS, int GPT, int KMODE, bool PLAIN>
-__global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
+__global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const GbParams p) {
   using T = ValTraits<VT>;
   constexpr bool IS_INT = T::is_int;
   constexpr bool ALL = FLAGS == GB_ALL;
   constexpr bool DENSE = KMODE == 0, PART = KMODE == 2;
-  constexpr int RPT = TS_T / NT, WROWS = 32 * RPT, NWARPS = NT / 32;
+  constexpr int TT = TsGeom<NT>::TT;
+  constexpr int RPT = TT / NT, WROWS = 32 * RPT, NWARPS = NT / 32;
   constexpr int NP = NT * GPT, NPAD = NP + 32;
   constexpr uint32_t TRASH = NP + 8;                                 // histogram slot of rows that are not aggregated here
   extern __shared__ __align__(128) unsigned char smem[];
-  u64* sorted = reinterpret_cast<u64*>(smem);                        // [TS_T]
-  u64* stage = sorted + TS_T;                                        // [TS_T]
-  uint32_t* H = reinterpret_cast<uint32_t*>(stage + TS_T);           // [2][NPAD]
+  u64* sorted = reinterpret_cast<u64*>(smem);                        // [TT]
+  u64* stage = sorted + TT;                                        // [TT]
+  uint32_t* H = reinterpret_cast<uint32_t*>(stage + TT);           // [2][NPAD]
   uint32_t* wsum = H + 2 * NPAD;                                     // [32]
   uint32_t* misc = wsum + 32;                                        // [4]  0: ids handed out
   u64* mbar = reinterpret_cast<u64*>(misc + 4);                      // [2]
@@ -258,17 +260,17 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
   reset_acc();
 
   // values of a tile -> stage: one bulk copy when the whole tile exists in memory, a plain copy loop otherwise
-  auto tile_bulk = [&](const TsItem& it) { return PART || it.valid == TS_T; };
+  auto tile_bulk = [&](const TsItem& it) { return PART || it.valid == TT; };
   auto issue_vals = [&](const TsItem& it) {
     if (tile_bulk(it)) {
       if (tid == 0) {
         fence_proxy_async();
-        mbar_expect_tx(a_mbar, TS_T * 8);
+        mbar_expect_tx(a_mbar, TT * 8);
 #pragma unroll
-        for (int c = 0; c < 4; c++) bulk_g2s(a_stage + c * (TS_T * 2), vals + it.base + c * (TS_T / 4), TS_T * 2, a_mbar);
+        for (int c = 0; c < 4; c++) bulk_g2s(a_stage + c * (TT * 2), vals + it.base + c * (TT / 4), TT * 2, a_mbar);
       }
     } else {
-      for (int i = tid; i < TS_T; i += NT) stage[i] = i < it.valid ? __ldg(vals + it.base + i) : 0ull;
+      for (int i = tid; i < TT; i += NT) stage[i] = i < it.valid ? __ldg(vals + it.base + i) : 0ull;
     }
   };
   // one pre-aggregated batch per (CTA, group) into the global table
@@ -291,7 +293,7 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
     }
   };
 
-  TsItem cur = ts_first_item<PART>(p);
+  TsItem cur = ts_first_item<PART, TT>(p);
   TsRows<RPT> r;
   if (cur.valid) { issue_vals(cur); ts_load<RPT, PLAIN, PART>(p, cur, warp, lane, r); }
   uint32_t tma_phase = 0;
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(NT, 1) gb_tsort_kernel(const GbParams p) {
   int b = 0;
 #pragma unroll 1
   for (; cur.valid; b ^= 1) {
-    const TsItem nxt = ts_next_item<PART>(p, cur);
+    const TsItem nxt = ts_next_item<PART, TT>(p, cur);
     uint32_t* Hc = H + b * NPAD;
     const uint32_t a_h = sm_addr(Hc);
     const bool tile_tma = tile_bulk(cur);
@@ -606,6 +608,7 @@ cudaError_t ts_launch4(const GbParams& p, int ctas, size_t smem, cudaStream_t s)
 template <typename VT, int FLAGS>
 cudaError_t ts_launch2(const GbParams& p, int nt, int gpt, int ctas, size_t smem, cudaStream_t s) {
   if (nt == 1024) return gpt == 1 ? ts_launch4<1024, VT, FLAGS, 1>(p, ctas, smem, s) : ts_launch4<1024, VT, FLAGS, 2>(p, ctas, smem, s);
+  if (nt == 256) return ts_launch4<256, VT, FLAGS, 4>(p, ctas, smem, s);
   return gpt == 2 ? ts_launch4<512, VT, FLAGS, 2>(p, ctas, smem, s) : ts_launch4<512, VT, FLAGS, 4>(p, ctas, smem, s);
 }
 
@@ -616,21 +619,25 @@ cudaError_t ts_launch2(const GbParams& p, int nt, int gpt, int ctas, size_t smem
 // when shared memory allows (load factor <= 1/4), else >= 2.
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem) {
   if (cap + 1 > 2048) return false;
-  const int t = nt_pref == 1024 ? 1024 : 512;
+  int t = nt_pref == 1024 ? 1024 : 512;
+  if (nt_pref == 256 && cap + 1 <= 1024) t = 256;          // two CTAs per SM, 4096-row tiles
   const int g = cap + 1 <= 1024 ? 1024 / t : 2048 / t;
   const size_t np = (size_t)t * g;
-  const size_t fixed = (size_t)TS_T * 16 + 2 * (np + 32) * 4 + 32 * 4 + 16 + 16;
+  const size_t tile = t == 256 ? 4096 : TS_T;
+  const size_t budget = t == 256 ? (size_t)smem_budget / 2 - 1024 : (size_t)smem_budget;
+  const size_t fixed = tile * 16 + 2 * (np + 32) * 4 + 32 * 4 + 16 + 16;
   long long S = 0;
   if (!dense) {
     S = 64;
     while (S < 4 * cap) S <<= 1;
-    while (S > 2 * cap && fixed + (size_t)S * 12 + (size_t)(cap + 1) * 8 > (size_t)smem_budget) S >>= 1;
+    while (S > 2 * cap && fixed + (size_t)S * 12 + (size_t)(cap + 1) * 8 > budget) S >>= 1;
   }
   const size_t bytes = fixed + (size_t)S * 12 + (dense ? 0 : (size_t)(cap + 1) * 8);
-  if (bytes > (size_t)smem_budget) return false;
+  if (bytes > budget) return false;
   *nt = t; *gpt = g; *slots = (int)S; *smem = bytes;
   return true;
 }
+long long gb_tsort_tile_rows_for(int nt) { return nt == 256 ? 4096 : TS_T; }
 long long gb_tsort_tile_rows() { return TS_T; }
 
 cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int nt, int gpt, int ctas, size_t smem, cudaStream_t s) {

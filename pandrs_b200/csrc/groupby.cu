@@ -213,6 +213,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
 // gb_tsort.cu
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
+long long gb_tsort_tile_rows_for(int nt);
 cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int nt, int gpt, int ctas, size_t smem, cudaStream_t s);
 
 // ---------------------------------------------------------------- dispatch helpers
@@ -495,8 +496,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
         if (use_ts) {
           gp.sh_cap = (int)ts_cap; gp.sh_slots = ts_slots; gp.sh_log_slots = ts_slots ? ilog2(ts_slots) : 0;
           gp.sh_dense = ts_dense ? 1 : 0; gp.sh_dense_base = dense_base;
-          const long long tiles = (n + gb_tsort_tile_rows() - 1) / gb_tsort_tile_rows();
-          PDRS_CUDA(c, gb_tsort_launch(gp, passes[i].is_int, passes[i].flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, tiles), ts_smem, c->stream));
+          const long long trows = gb_tsort_tile_rows_for(ts_nt), tiles = (n + trows - 1) / trows;
+          PDRS_CUDA(c, gb_tsort_launch(gp, passes[i].is_int, passes[i].flags, ts_nt, ts_gpt, (int)std::min<long long>((long long)c->sm_count * (ts_nt == 256 ? 2 : 1), tiles), ts_smem, c->stream));
           c->stats.groupby_algo_used = PDRS_GB_TILESORT;
         } else if (use_shared) PDRS_CUDA(c, launch_shared(variant, cfgs[i], gp, smems[i], c->stream));
         else {

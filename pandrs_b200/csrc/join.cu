@@ -455,74 +455,81 @@ __global__ void __launch_bounds__(JP_THREADS, 4) jpart_scatter_kernel(JKeyCol co
 // the exact two-pass partition above).  Per tile of 8192 rows: shared-memory histogram whose atomics return the
 // row's rank, one global reservation per bucket, rows staged in shared memory in bucket order, then every bucket's
 // run (8192 / nb rows) is written out contiguously.  2 CTAs per SM overlap each other's barriers.
-#define JQ_NT 1024
+#define JQ_NT 512
 #define JQ_ITEMS 8
 #define JQ_TILE (JQ_NT * JQ_ITEMS)
 __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long n, int log_nb, long long cap, u64* __restrict__ cursor,
                                                           u64* __restrict__ out_keys, uint32_t* __restrict__ out_rows, u64* __restrict__ overflow) {
   extern __shared__ __align__(16) unsigned char jsm[];
-  u64* st_key = reinterpret_cast<u64*>(jsm);                                 // [JQ_TILE]
-  uint32_t* st_row = reinterpret_cast<uint32_t*>(st_key + JQ_TILE);         // [JQ_TILE]
-  uint32_t* H = st_row + JQ_TILE;                                           // [1024 + 32] counts -> exclusive offsets
-  uint32_t* G = H + 1056;                                                   // [1024] reserved start inside the bucket
-  __shared__ uint32_t wsum[32];
+  u64* st_key = reinterpret_cast<u64*>(jsm);                                 // [JQ_TILE] staged keys
+  uint32_t* st_row = reinterpret_cast<uint32_t*>(st_key + JQ_TILE);         // [JQ_TILE] staged row ids
+  uint32_t* st_dst = st_row + JQ_TILE;                                      // [JQ_TILE] output position of the staged row
+  uint32_t* H = st_dst + JQ_TILE;                                           // [1024 + 32] bucket counts of the tile
+  uint2* HD = reinterpret_cast<uint2*>(H + 1056);                           // [1024] {offset in the staging area, output position of the first row}
+  __shared__ uint32_t wsum[JQ_NT / 32];
+  __shared__ uint32_t sh_total;
   const int nb = 1 << log_nb;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool fast = col.dtype == PDRS_I64 && !col.nulls;
-  for (long long t0 = (long long)blockIdx.x * JQ_TILE; t0 < n; t0 += (long long)gridDim.x * JQ_TILE) {
-    H[tid] = 0;
+  const long long tstride = (long long)gridDim.x * JQ_TILE;
+  long long t0 = (long long)blockIdx.x * JQ_TILE;
+  u64 key[JQ_ITEMS];
+  // plain Int64 keys: the loads of a tile are issued one stage ahead (in flight while the previous tile is written out)
+  auto load_tile = [&](long long tb) {
+#pragma unroll
+    for (int j = 0; j < JQ_ITEMS; j++) { const long long i = tb + (long long)j * JQ_NT + tid; key[j] = i < n ? (u64)__ldcs((const long long*)col.data + i) : 0ull; }
+  };
+  if (fast && t0 < n) load_tile(t0);
+  for (; t0 < n; t0 += tstride) {
+    for (int i = tid; i < 1056; i += JQ_NT) H[i] = 0;
     __syncthreads();
-    u64 key[JQ_ITEMS];
-    uint32_t br[JQ_ITEMS];            // bucket << 16 | rank inside the bucket (tile <= 8192 rows); all ones = no row
-    if (fast && t0 + JQ_TILE <= n) {
+    uint32_t br[JQ_ITEMS];            // bucket << 16 | rank inside the bucket (tile <= 4096 rows); all ones = no row
 #pragma unroll
-      for (int j = 0; j < JQ_ITEMS; j++) key[j] = (u64)__ldcs((const long long*)col.data + t0 + (long long)j * JQ_NT + tid);
-#pragma unroll
-      for (int j = 0; j < JQ_ITEMS; j++) { const uint32_t b = jbucket(key[j], log_nb); br[j] = (b << 16) | atomicAdd(&H[b], 1u); }
-    } else {
-#pragma unroll
-      for (int j = 0; j < JQ_ITEMS; j++) {
-        const long long i = t0 + (long long)j * JQ_NT + tid;
-        br[j] = 0xFFFFFFFFu;
-        if (i < n && jload_key(col, i, &key[j])) { const uint32_t b = jbucket(key[j], log_nb); br[j] = (b << 16) | atomicAdd(&H[b], 1u); }
-      }
+    for (int j = 0; j < JQ_ITEMS; j++) {
+      const long long i = t0 + (long long)j * JQ_NT + tid;
+      br[j] = 0xFFFFFFFFu;
+      bool live = i < n;
+      if (!fast) live = live && jload_key(col, i, &key[j]);
+      if (live) { const uint32_t b = jbucket(key[j], log_nb); br[j] = (b << 16) | atomicAdd(&H[b], 1u); }
     }
     __syncthreads();
-    {   // exclusive scan of the bucket counts (thread b owns bucket b) + one global reservation per bucket
-      const uint32_t c = tid < nb ? H[tid] : 0u;
+    {   // exclusive scan of the bucket counts (thread t owns buckets 2t, 2t + 1) + one global reservation per bucket
+      const uint32_t c0 = H[2 * tid], c1 = H[2 * tid + 1], c = c0 + c1;
       uint32_t incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
       if (lane == 31) wsum[warp] = incl;
-      uint32_t g = 0;
-      if (c) {
-        const u64 at = atomicAdd(&cursor[tid], (u64)c);
-        if (at + c > (u64)cap) { atomicAdd(overflow, 1ull); g = 0xFFFFFFFFu; } else g = (uint32_t)at;
-      }
+      uint32_t g0 = 0xFFFFFFFFu, g1 = 0xFFFFFFFFu;
+      if (c0) { const u64 at = atomicAdd(&cursor[2 * tid], (u64)c0); if (at + c0 > (u64)cap) atomicAdd(overflow, 1ull); else g0 = (uint32_t)((u64)(2 * tid) * (u64)cap + at); }
+      if (c1) { const u64 at = atomicAdd(&cursor[2 * tid + 1], (u64)c1); if (at + c1 > (u64)cap) atomicAdd(overflow, 1ull); else g1 = (uint32_t)((u64)(2 * tid + 1) * (u64)cap + at); }
       __syncthreads();
-      uint32_t ws = wsum[lane];
+      uint32_t ws = lane < JQ_NT / 32 ? wsum[lane] : 0u;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
       const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
       const uint32_t excl = (warp ? wprefix : 0u) + incl - c;
-      H[tid] = excl;
-      if (tid == JQ_NT - 1) H[JQ_NT] = excl + c;
-      G[tid] = g;
+      HD[2 * tid] = make_uint2(excl, g0);
+      HD[2 * tid + 1] = make_uint2(excl + c0, g1);
+      if (tid == JQ_NT - 1) sh_total = excl + c;
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < JQ_ITEMS; j++) {
       if (br[j] == 0xFFFFFFFFu) continue;
-      const uint32_t pos = H[br[j] >> 16] + (br[j] & 0xFFFFu);
+      const uint2 hd = HD[br[j] >> 16];
+      const uint32_t rank = br[j] & 0xFFFFu, pos = hd.x + rank;
       st_key[pos] = key[j];
       st_row[pos] = (uint32_t)(t0 + (long long)j * JQ_NT + tid);
+      st_dst[pos] = hd.y == 0xFFFFFFFFu ? 0xFFFFFFFFu : hd.y + rank;       // all ones: the bucket overflowed, the caller discards this partitioning
     }
+    if (fast && t0 + tstride < n) load_tile(t0 + tstride);
     __syncthreads();
-    for (int b = warp; b < nb; b += JQ_NT / 32) {     // one warp per bucket run
-      const uint32_t off = H[b], cnt = H[b + 1] - off, g = G[b];
-      if (g == 0xFFFFFFFFu) continue;                 // overflow: the caller discards this partition
-      const long long dst = (long long)b * cap + g;
-      for (uint32_t i = lane; i < cnt; i += 32) { out_keys[dst + i] = st_key[off + i]; out_rows[dst + i] = st_row[off + i]; }
+    const uint32_t total = sh_total;
+    for (uint32_t pos = tid; pos < total; pos += JQ_NT) {     // consecutive staged rows of a bucket go to consecutive output rows
+      const uint32_t d = st_dst[pos];
+      if (d == 0xFFFFFFFFu) continue;
+      out_keys[d] = st_key[pos];
+      out_rows[d] = st_row[pos];
     }
     __syncthreads();
   }
@@ -704,7 +711,8 @@ static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log
   PDRS_TRY(out->keys.alloc(c, (size_t)nb * cap * 8));
   PDRS_TRY(out->rows.alloc(c, (size_t)nb * cap * 4));
   out->n = (long long)nb * cap;
-  const size_t smem = (size_t)JQ_TILE * 12 + (1056 + 1024) * 4;
+  if ((unsigned long long)nb * (unsigned long long)cap >= (1ull << 32)) { *ok = false; return PDRS_OK; }   // 32-bit output positions
+  const size_t smem = (size_t)JQ_TILE * 16 + 1056 * 4 + 1024 * 8;
   static bool attr_set = false;
   if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
   const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + JQ_TILE - 1) / JQ_TILE));
