@@ -195,6 +195,49 @@ def test_cardinalities_all_aggs(ctx, oracle, card, algo):
     assert len(got) == len(np.unique(k.values))
 
 
+@pytest.mark.parametrize("dense", [1, 0])
+def test_skewed_keys_take_the_warp_cooperative_reduce(ctx, oracle, dense):
+    # Zipf-like skew (BASELINE.json configs[3] style) and a group that owns 90% of the rows: segments of the sorted
+    # tile longer than 64 rows are reduced by the owner's whole warp (gb_tsort.cu); int and float values, NULLs
+    rng = np.random.default_rng(5)
+    n = 300_000
+    w = 1.0 / np.arange(1, 401) ** 1.1
+    zipf = rng.choice(400, size=n, p=w / w.sum())
+    heavy = np.where(rng.random(n) < 0.9, 7, rng.integers(0, 40, n))
+    for keys in (zipf, heavy):
+        kv = keys.astype(np.int64) * (1 if dense else 1_000_003) - (0 if dense else 17)
+        k = Spec(pb.I64, kv)
+        v = Spec(pb.F64, 50.0 + rng.normal(0, 5.0, n), nulls=rng.random(n) < 0.05)
+        vi = Spec(pb.I64, rng.integers(-10**6, 10**6, n))
+        ctx.set_option("dense", dense)
+        try:
+            got = compare_groupby(pb, oracle, ctx, [k], [v, vi], [(0, op) for op in ALL6] + [(1, op) for op in ALL6], device=True)
+        finally:
+            ctx.set_option("dense", 1)
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_TILESORT and len(got) == len(np.unique(kv))
+
+
+def test_partitioned_high_cardinality_path(ctx, oracle):
+    # thousands of groups, >= 2 tiles per partition: one- and two-level hash partition + tile sort per partition
+    # (gb_part.cu); NULL values travel as flag bytes, a row filter is applied by the first partition pass
+    rng = np.random.default_rng(6)
+    for n, card in ((3_000_000, 60_000), (3_000_000, 5_000), (9_000_000, 200_000)):     # the last one needs two levels
+        kv = rng.integers(0, card, n) * 7_919 - 1_000_000
+        k = Spec(pb.I64, kv)
+        v = Spec(pb.F64, rng.normal(10.0, 3.0, n), nulls=rng.random(n) < 0.05)
+        f = Spec(pb.BOOL_BITS, rng.random(n) < 0.9)
+        got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED and len(got) == len(np.unique(kv))
+        got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], filter_spec=f, device=True)
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+        ctx.set_option("part", 0)
+        try:
+            compare_groupby(pb, oracle, ctx, [k], [v], [(0, pb.SUM), (0, pb.COUNT)], device=True)
+            assert ctx.stats()["groupby_algo_used"] != pb.GB_PARTITIONED
+        finally:
+            ctx.set_option("part", 1)
+
+
 @pytest.mark.parametrize("radix", [1, 0])
 def test_high_cardinality_radix_path(ctx, oracle, radix):
     # BASELINE.json configs[1] "10M distinct" shape at oracle-sized n: the table (slots x 80 B) no longer fits L2, so
