@@ -18,6 +18,7 @@
 // memory in bucket order and written out as contiguous runs.  A bucket that overflows its range (heavily skewed
 // keys) makes the caller fall back to the global-table path.
 #include <algorithm>
+#include <cmath>
 
 #include "groupby_kernels.cuh"
 
@@ -171,15 +172,21 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   const long long n = gp.n;
   const long long T = gb_tsort_tile_rows();
   if (gp.ks.c[0].nulls || !gp.val || n < (1 << 20)) return PDRS_ERR_UNSUPPORTED;
-  // partitions of <= ~600 expected groups (the tile-sort kernel holds 1023 ids with 512 threads x 2 groups)
+  // partitions of <= ~600 expected groups (the tile-sort kernel holds 1023 ids with 512 threads x 2 groups).  Few
+  // partitions are fine: the aggregation kernel cuts every partition into chunks of tiles, one work item each.
   int bits = 1;
   while (bits < 16 && (est_groups >> bits) > 600) bits++;
-  if ((est_groups >> bits) > 700) return PDRS_ERR_UNSUPPORTED;
-  if ((n >> bits) < 2 * T) return PDRS_ERR_UNSUPPORTED;          // too few rows per partition: the per-partition overheads dominate
+  if ((est_groups >> bits) > 700 || (n >> bits) < 2 * T) return PDRS_ERR_UNSUPPORTED;
   const int bits1 = bits <= 8 ? bits : (bits + 1) / 2, bits2 = bits - bits1;
   const long long nb1 = 1ll << bits1, nparts = 1ll << bits;
-  const long long cap1 = round_up(n / nb1 + n / (nb1 * 32) + 65536, T);
-  const long long cap2 = bits2 ? round_up(n / nparts + n / (nparts * 8) + 8192, T) : cap1;
+  // a bucket holds whole groups: with m groups per bucket its size varies by ~1/sqrt(m) -> 6 sigma of slack
+  auto padded = [&](long long buckets, long long extra) {
+    const double m = std::max(1.0, (double)est_groups / (double)buckets);
+    const double mean = (double)n / (double)buckets;
+    return round_up((long long)(mean * (1.0 + std::max(1.0 / 32.0, 6.0 / std::sqrt(m)))) + extra, T);
+  };
+  const long long cap1 = padded(nb1, 65536);
+  const long long cap2 = bits2 ? padded(nparts, 8192) : cap1;
   if ((unsigned long long)nb1 * cap1 >= (1ull << 31) || (unsigned long long)nparts * cap2 >= (1ull << 31)) return PDRS_ERR_UNSUPPORTED;   // 31-bit output positions
   const size_t need = (size_t)nb1 * cap1 * 17 + (bits2 ? (size_t)nparts * cap2 * 17 : 0);
   size_t free_b = 0, total_b = 0;
@@ -236,11 +243,18 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   if (bits2) { k1.release(); v1.release(); f1.release(); }                        // only the last level is read below
   GbParams tp = gp;
   tp.part_keys = pk; tp.part_vals = pv; tp.part_flags = pf; tp.part_cnt = pc; tp.part_cap = pcap; tp.part_bits = bits;
+  {   // work items: ~16 chunks per CTA, each chunk a run of whole tiles of one partition
+    const long long tiles_cap = pcap / T, want = 16ll * c->sm_count;
+    long long cpp = std::max<long long>(1, std::min<long long>(tiles_cap, (want + nparts - 1) / nparts));
+    tp.part_chunk_tiles = (int)((tiles_cap + cpp - 1) / cpp);
+    tp.part_cpp = (int)((tiles_cap + tp.part_chunk_tiles - 1) / tp.part_chunk_tiles);
+  }
+  tp.ts_heavy = c->opt_tsort_heavy > 0 ? (int)c->opt_tsort_heavy : 128;
   tp.sh_cap = (int)ts_cap; tp.sh_slots = ts_slots; tp.sh_dense = 0; tp.sh_dense_base = 0;
   int lg = 0;
   while ((1 << lg) < ts_slots) lg++;
   tp.sh_log_slots = lg;
-  PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts), ts_smem, c->stream));
+  PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts * tp.part_cpp), ts_smem, c->stream));
   c->stats.kernel_launches++;
   if (c->opt_timing) {
     PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));

@@ -13,7 +13,7 @@
 //   phase 3  value -> sorted[offset[group] + rank]                      (one LDS.32 + one STS.64 per row)
 //   phase 4  every thread OWNS one (or two) groups for the whole kernel: it walks its segment of the sorted tile
 //            and keeps rows / n / pivot / S1 / S2 / min / max / isum in REGISTERS - all six aggregates cost the
-//            same single sequential read.  Segments longer than TS_HEAVY rows (skewed keys) are reduced by the
+//            same single sequential read.  Segments longer than ts_heavy (128) rows (skewed keys, few groups) are reduced by the
 //            owner's whole warp with shuffles.
 //
 // Keys are loaded with 128-bit streaming loads one tile ahead (registers); values arrive through one bulk
@@ -28,7 +28,6 @@ namespace {
 
 constexpr int TS_T = 8192;               // rows per tile (4096 in the two-CTAs-per-SM geometry of 256 threads)
 template <int NT> struct TsGeom { static constexpr int TT = NT == 256 ? 4096 : 8192; static constexpr int CTAS = NT == 256 ? 2 : 1; };
-constexpr int TS_HEAVY = 64;             // longer segments are reduced by the whole warp
 
 // Group id -> histogram position.  XORs the low bits of the id into the warp field so that consecutive ids (dense
 // keys, or first-seen order under skew) are owned by different warps, while the lanes of a warp own consecutive
@@ -60,22 +59,31 @@ template <int RPT> struct TsRows {
 // One unit of work of a CTA: a tile of up to TS_T consecutive rows.  Plain input: tiles blockIdx, blockIdx + grid, ...
 // of the columns.  Partitioned input: the tiles of partitions blockIdx, blockIdx + grid, ...; `last` marks the last
 // tile of a partition (the CTA then flushes its groups and starts over with empty tables).
-struct TsItem { long long base; long long part; int valid; int last; };
+struct TsItem { long long base; long long part; int valid; int last; };   // partitioned input: `part` = chunk index
+// tiles [t0, t1) of chunk `ch` (partition ch / cpp, chunk ch % cpp of it) that hold rows
+template <int TT>
+__device__ __forceinline__ bool ts_chunk_range(const GbParams& p, long long ch, long long* pbase, long long* cnt, long long* t0, long long* t1) {
+  const long long q = ch / p.part_cpp, k = ch % p.part_cpp;
+  *cnt = min((long long)__ldg(p.part_cnt + q), p.part_cap);
+  *pbase = q * p.part_cap;
+  const long long tiles = (*cnt + TT - 1) / TT;
+  *t0 = k * p.part_chunk_tiles;
+  *t1 = min(tiles, *t0 + p.part_chunk_tiles);
+  return *t0 < *t1;
+}
 template <bool PART, int TT>
 __device__ __forceinline__ TsItem ts_first_item(const GbParams& p) {
   TsItem it;
-  it.part = blockIdx.x; it.last = 0;
+  it.part = blockIdx.x; it.last = 0; it.base = 0; it.valid = 0;
   if (!PART) {
     it.base = (long long)blockIdx.x * TT;
     it.valid = it.base < p.n ? (int)min((long long)TT, p.n - it.base) : 0;
     return it;
   }
-  const long long nparts = 1ll << p.part_bits;
-  it.base = 0; it.valid = 0;
-  while (it.part < nparts) {
-    const long long c = min((long long)__ldg(p.part_cnt + it.part), p.part_cap);
-    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TT, c); it.last = c <= TT; return it; }
-    it.part += gridDim.x;
+  const long long nchunks = (1ll << p.part_bits) * p.part_cpp;
+  for (; it.part < nchunks; it.part += gridDim.x) {
+    long long pb, c, t0, t1;
+    if (ts_chunk_range<TT>(p, it.part, &pb, &c, &t0, &t1)) { it.base = pb + t0 * TT; it.valid = (int)min((long long)TT, c - t0 * TT); it.last = t0 + 1 == t1; return it; }
   }
   return it;
 }
@@ -87,17 +95,17 @@ __device__ __forceinline__ TsItem ts_next_item(const GbParams& p, const TsItem& 
     it.valid = it.base < p.n ? (int)min((long long)TT, p.n - it.base) : 0;
     return it;
   }
-  const long long nparts = 1ll << p.part_bits;
+  long long pb, c, t0, t1;
   if (!cur.last) {
-    const long long c = min((long long)__ldg(p.part_cnt + cur.part), p.part_cap);
-    const long long off = cur.base - cur.part * p.part_cap + TT;
-    it.base = cur.base + TT; it.valid = (int)min((long long)TT, c - off); it.last = c - off <= TT;
+    ts_chunk_range<TT>(p, cur.part, &pb, &c, &t0, &t1);
+    const long long t = (cur.base - pb) / TT + 1;
+    it.base = cur.base + TT; it.valid = (int)min((long long)TT, c - t * TT); it.last = t + 1 == t1;
     return it;
   }
+  const long long nchunks = (1ll << p.part_bits) * p.part_cpp;
   it.valid = 0; it.last = 0;
-  for (it.part = cur.part + gridDim.x; it.part < nparts; it.part += gridDim.x) {
-    const long long c = min((long long)__ldg(p.part_cnt + it.part), p.part_cap);
-    if (c > 0) { it.base = it.part * p.part_cap; it.valid = (int)min((long long)TT, c); it.last = c <= TT; return it; }
+  for (it.part = cur.part + gridDim.x; it.part < nchunks; it.part += gridDim.x) {
+    if (ts_chunk_range<TT>(p, it.part, &pb, &c, &t0, &t1)) { it.base = pb + t0 * TT; it.valid = (int)min((long long)TT, c - t0 * TT); it.last = t0 + 1 == t1; return it; }
   }
   return it;
 }
@@ -528,7 +536,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
           if (is_finite_f64(x)) { acc[s].piv = (u64)__double_as_longlong(x) | 1ull; break; }
         }
       }
-      heavy[s] = len > TS_HEAVY;
+      heavy[s] = len > (uint32_t)p.ts_heavy;
       if (!heavy[s]) {
         const double pv = __longlong_as_double((long long)acc[s].piv);
         double S1 = acc[s].S1, S2 = acc[s].S2;

@@ -84,6 +84,8 @@ struct GbParams {
   // tile-sort kernel over hash-partitioned rows (gb_tsort.cu): partition q owns rows [q * part_cap, q * part_cap + part_cnt[q])
   // of part_keys / part_vals (no NULLs, filter already applied); part_bits = log2(number of partitions)
   const u64* part_keys; const u64* part_vals; const uint8_t* part_flags /* 1 = value is NULL; may be NULL */; const u64* part_cnt; long long part_cap; int part_bits;
+  int part_cpp, part_chunk_tiles;   // work items: every partition is cut into part_cpp chunks of part_chunk_tiles tiles (one flush per chunk)
+  int ts_heavy;                     // tile-sort kernel: segments longer than this are reduced by the whole warp
 };
 
 // ---------------------------------------------------------------- small device helpers
