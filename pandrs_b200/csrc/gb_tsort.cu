@@ -24,6 +24,13 @@
 
 #include "groupby_kernels.cuh"
 
+#ifdef TS_PROFILE
+__device__ unsigned long long ts_prof[8];
+#define TSP_MARK(k) do { const long long _t = clock64(); tacc[k] += (unsigned long long)(_t - tprev); tprev = _t; } while (0)
+#else
+#define TSP_MARK(k)
+#endif
+
 namespace {
 
 constexpr int TS_T = 8192;               // rows per tile (4096 in the two-CTAs-per-SM geometry of 256 threads)
@@ -309,6 +316,10 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
   const uint32_t vm0 = 1u << sh2, vm1 = 2u << sh2;      // this lane's two bits in a bitmap word
   int b = 0;
 #pragma unroll 1
+#ifdef TS_PROFILE
+  unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#endif
   for (; cur.valid; b ^= 1) {
     const TsItem nxt = ts_next_item<PART, TT>(p, cur);
     uint32_t* Hc = H + b * NPAD;
@@ -473,7 +484,9 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
     }
     // keys (and bitmap words) of this CTA's next tile: in flight during phases 2-4
     if (nxt.valid) ts_load<RPT, PLAIN, PART>(p, nxt, warp, lane, r);
+    TSP_MARK(0);
     __syncthreads();
+    TSP_MARK(1);
     // ---- phase 2: exclusive scan of the histogram (thread t owns entries [t * GPT, t * GPT + GPT))
     {
       uint32_t c[GPT], tsum = 0;
@@ -497,6 +510,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
       for (int s = 0; s < GPT; s++) H[(b ^ 1) * NPAD + tid + s * NT] = 0;
       __syncthreads();
     }
+    TSP_MARK(2);
     // ---- phase 3: scatter the values into group order
     {
       uint32_t pos[RPT];
@@ -516,7 +530,9 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
         }
       }
     }
+    TSP_MARK(3);
     __syncthreads();
+    TSP_MARK(4);
     if (nxt.valid) issue_vals(nxt);   // stage is free: values of the next tile
     // ---- phase 4: every thread reduces the segments of the groups it owns
     bool heavy[GPT];
@@ -588,6 +604,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
     }
     // no barrier here: the next tile's phase 1 only touches the other histogram buffer, and its scatter into
     // `sorted` comes after that tile's first barrier, which every thread reaches only after this phase
+    TSP_MARK(5);
     if (PART && cur.last) {              // end of a partition: flush its groups, start over with empty tables
       flush();
       __syncthreads();
@@ -598,6 +615,9 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
     }
     cur = nxt;
   }
+#ifdef TS_PROFILE
+  if (lane == 0) for (int k = 0; k < 6; k++) atomicAdd(&ts_prof[k], tacc[k]);
+#endif
   if (!PART) flush();
 }
 
@@ -652,3 +672,11 @@ cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int nt, in
   if (!is_int) return flags == GB_SUM ? ts_launch2<double, GB_SUM>(p, nt, gpt, ctas, smem, s) : ts_launch2<double, GB_ALL>(p, nt, gpt, ctas, smem, s);
   return flags == GB_SUM ? ts_launch2<long long, GB_SUM>(p, nt, gpt, ctas, smem, s) : ts_launch2<long long, GB_ALL>(p, nt, gpt, ctas, smem, s);
 }
+
+#ifdef TS_PROFILE
+extern "C" int pdrs_debug_tsprof(unsigned long long* out, int reset) {
+  if (out) cudaMemcpyFromSymbol(out, ts_prof, sizeof(ts_prof));
+  if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(ts_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif

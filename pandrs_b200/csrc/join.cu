@@ -122,11 +122,11 @@ __device__ __forceinline__ void jprefetch_next_region(const JTab& t, const JSrc&
   u64 e = s0 + (u64)((double)(s1 - s0) * ((double)p1 / (double)cnt)) + 16;
   a &= ~15ull;                                   // 16 slots = one 128-byte line of keys (and of heads)
   if (e > s1) e = s1;
-  for (u64 x = a + 2ull * tid; x < e; x += 2ull * nthreads) {
-    ulonglong2 k;
-    u64 h;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;" : "=l"(k.x), "=l"(k.y) : "l"(t.keys + x), "l"(pol));
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(h) : "l"(t.heads + x), "l"(pol));
+  // one prefetch per 64 bytes: 16 slots = 128 B of keys + 64 B of heads per lane and step; no destination registers
+  for (u64 x = a + 16ull * tid; x < e; x += 16ull * nthreads) {
+    asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(t.keys + x));
+    asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(t.keys + x + 8));
+    asm volatile("prefetch.global.L2::evict_last [%0];" :: "l"(t.heads + x));
   }
 }
 
