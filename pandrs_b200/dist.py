@@ -168,12 +168,23 @@ class DistGroupBy:
 
     def groupby_agg_lowcard(self, keys: Sequence[Column], vals: Sequence[Column], aggs, filter=None):
         """Local partial aggregate + all_gather of the (small) state rows + merge on every rank.
-        Every rank returns the full result."""
+        Every rank returns the full result.  Keys, NULL flags and states travel as ONE packed int64 matrix
+        [groups, nkeys * 2 + 8 * nvals]: one size exchange and one all_gather per call."""
         all_stats = any(op in (N.MIN, N.MAX, N.STD, N.VAR) for _, op in aggs)
         kt, kn, st, _rows = self.b.partial(keys, vals, filter, all_stats)
-        gk = [all_gather_varlen(self.dist, t)[0] for t in kt]
-        gn = [all_gather_varlen(self.dist, t)[0] for t in kn]
-        gs = [all_gather_varlen(self.dist, s)[0] for s in st]
+        G = int(kt[0].shape[0]) if kt else 0
+        nk, nv = len(kt), len(st)
+        packed = torch.empty((G, 2 * nk + 8 * nv), dtype=torch.int64, device=kt[0].device)
+        for i, t in enumerate(kt):
+            packed[:, i] = t.view(torch.int64) if t.dtype == torch.float64 else t.to(torch.int64)
+        for i, t in enumerate(kn):
+            packed[:, nk + i] = t.to(torch.int64)
+        for i, s in enumerate(st):
+            packed[:, 2 * nk + 8 * i: 2 * nk + 8 * (i + 1)] = s
+        allp, _ = all_gather_varlen(self.dist, packed)
+        gk = [(allp[:, i].contiguous().view(torch.float64) if t.dtype == torch.float64 else allp[:, i].to(t.dtype)).contiguous() for i, t in enumerate(kt)]
+        gn = [allp[:, nk + i].to(torch.uint8).contiguous() for i in range(nk)]
+        gs = [allp[:, 2 * nk + 8 * i: 2 * nk + 8 * (i + 1)].contiguous() for i in range(nv)]
         return self.b.merge([c.dtype for c in keys], gk, gn, gs, [c.dtype == N.I64 for c in vals], aggs)
 
     def groupby_agg_shuffle(self, keys: Sequence[Column], vals: Sequence[Column], aggs):
