@@ -366,24 +366,41 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
       // no filter, no NULL keys; key -> id through the CTA key table: up to three lock-free probes per row
       // (the table runs at a load factor <= 1/4, so > 90% of the rows hit their home slot), insertion of new keys
       // and longer probe sequences in the warp-synchronous slow path
-      uint32_t slowmask = 0, ids[RPT];
+      uint32_t slowmask = 0, pend = 0, ids[RPT];
+      // home slot of every row: one lock-free probe each, all loads in flight together
 #pragma unroll
       for (int q = 0; q < RPT; q++) {
-        uint32_t slot = (ts_hash32(r.k[q]) << slot_lsh) >> slot_rsh;
-        uint32_t id = 0xFFFFFFFFu;
-        bool done = false;
+        const uint32_t slot = (ts_hash32(r.k[q]) << slot_lsh) >> slot_rsh;
+        const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
+        const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
+        const bool live = (r.act >> q) & 1u;
+        const bool hit = idw != 0 && idw != SH_BUSY && kk == r.k[q];
+        ids[q] = hit ? idw - 1 : 0xFFFFFFFFu;
+        if (live && !hit) { if (idw == 0 || idw == SH_BUSY) slowmask |= 1u << q; else pend |= 1u << q; }   // new key -> insertion; else go on probing
+      }
+      // rows displaced from their home slot (~10% at load factor 1/4): every lane follows the probe sequence of its
+      // first pending row per round, so a round costs the warp one shared-memory round trip, not one per row
+      {
+        uint32_t dist = 1;
+        int cur = -1;
+        while (__any_sync(0xFFFFFFFFu, pend != 0)) {
+          const int j = pend ? __ffs(pend) - 1 : -1;
+          if (j != cur) { cur = j; dist = 1; }
+          u64 kq = 0;
 #pragma unroll
-        for (int pr = 0; pr < 3; pr++) {
-          if (!done) {
+          for (int qq = 0; qq < RPT; qq++) if (qq == j) kq = r.k[qq];
+          if (j >= 0) {
+            const uint32_t slot = (((ts_hash32(kq) << slot_lsh) >> slot_rsh) + dist) & (uint32_t)(S - 1);
             const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
             const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
-            if (idw == 0 || idw == SH_BUSY) done = true;                       // new key / being inserted: slow path
-            else if (kk == r.k[q]) { id = idw - 1; done = true; }
-            else slot = (slot + 1) & (S - 1);
+            if (idw == 0 || idw == SH_BUSY || dist >= 64u) { slowmask |= 1u << j; pend &= ~(1u << j); }
+            else if (kk == kq) {
+#pragma unroll
+              for (int qq = 0; qq < RPT; qq++) if (qq == j) ids[qq] = idw - 1;
+              pend &= ~(1u << j);
+            } else dist++;
           }
         }
-        ids[q] = id;
-        if (id == 0xFFFFFFFFu && ((r.act >> q) & 1u)) slowmask |= 1u << q;
       }
       uint32_t spillmask = 0;
       if (__any_sync(0xFFFFFFFFu, slowmask != 0)) {

@@ -427,8 +427,10 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     ts_cap = ts_dense ? dense_range + std::max<long long>(dense_range / 16, 8) : est + std::max<long long>(est / 16, 8);
     // one group per thread when the keys seen by the sample fit 1023 ids (later keys outside the range spill)
     const long long ts_seen = ts_dense ? dense_range : est;
-    if (ts_cap > 1023 && ts_seen <= 1023) ts_cap = 1023;
-    if (ts_cap > 2047 && ts_seen <= 2047) ts_cap = 2047;
+    // (the sampled estimate is inflated by ~5%: up to 1100 / 2150 estimated groups still try the smaller geometry; keys
+    //  that do not fit spill to the global table)
+    if (ts_cap > 1023 && ts_seen <= (ts_dense ? 1023 : 1100)) ts_cap = 1023;
+    if (ts_cap > 2047 && ts_seen <= (ts_dense ? 2047 : 2150)) ts_cap = 2047;
     ts_fit = gb_tsort_geometry(ts_cap, ts_dense, c->smem_optin, (int)c->opt_tsort_threads, &ts_nt, &ts_gpt, &ts_slots, &ts_smem);
   }
   if (c->opts.groupby_algo == PDRS_GB_TILESORT && !ts_fit && c->opts.groups_hint > 0)
