@@ -55,8 +55,8 @@ typedef enum pdrs_agg_op {
   PDRS_SUM = 0, PDRS_MEAN = 1, PDRS_MIN = 2, PDRS_MAX = 3, PDRS_COUNT = 4, PDRS_STD = 5, PDRS_VAR = 6
 } pdrs_agg_op;
 
-/* JoinType (src/optimized/split_dataframe/join.rs:11-20); Right/Outer are "next" rows */
-typedef enum pdrs_join_type { PDRS_INNER = 0, PDRS_LEFT = 1 } pdrs_join_type;
+/* JoinType (src/optimized/split_dataframe/join.rs:11-20) */
+typedef enum pdrs_join_type { PDRS_INNER = 0, PDRS_LEFT = 1, PDRS_RIGHT = 2, PDRS_OUTER = 3 } pdrs_join_type;
 
 typedef enum pdrs_mem { PDRS_MEM_HOST = 0, PDRS_MEM_DEVICE = 1 } pdrs_mem;
 
@@ -179,7 +179,9 @@ int32_t pdrs_hash_partition(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, 
 
 /* ---- hash join ----
  * Replaces the build/probe part of OptimizedDataFrame::join_impl (split_dataframe/join.rs:107-208).
- * Emits index pairs (left_row, right_row); right_row = -1 stands for None (Left join, no match).
+ * Emits index pairs (left_row, right_row); -1 stands for None: right_row = -1 for a left row without a match
+ * (Left / Outer), left_row = -1 for the right rows that no pair references, appended in ascending right row after
+ * the other pairs (Right / Outer, join.rs:211-224; right rows with a NULL key are among them).
  * NULL keys never match and are dropped from BOTH sides, also for Left (join.rs:112,152).
  * Row order: small inputs keep the reference's order (left-row-major, ascending right row).  Large inputs
  * take the radix-partitioned path and emit the same multiset of pairs in an unspecified order; parity is

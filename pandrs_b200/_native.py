@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 # pdrs_dtype / pdrs_agg_op / pdrs_join_type / pdrs_mem / pdrs_groupby_algo (include/pandrs_b200.h)
 I64, F64, DICT_U32, BOOL_BITS, I32 = 0, 1, 2, 3, 4
 SUM, MEAN, MIN, MAX, COUNT, STD, VAR = range(7)
-INNER, LEFT = 0, 1
+INNER, LEFT, RIGHT, OUTER = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 GB_AUTO, GB_SHARED, GB_GLOBAL, GB_DENSE, GB_TILESORT, GB_PARTITIONED = 0, 1, 2, 3, 4, 5
 

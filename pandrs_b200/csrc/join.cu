@@ -678,6 +678,52 @@ __global__ void __launch_bounds__(JE_THREADS, 3) join_probe_emit_kernel(JTab tab
   }
 }
 
+// ---------------------------------------------------------------- Right / Outer: unmatched rows of the right frame
+// join.rs:211-224: after the pairs of the left rows, every right row that no pair references is appended as
+// (None, r) in ascending r - including right rows whose key is NULL (they never match).
+__global__ void jmark_matched_kernel(const long long* __restrict__ out_r, long long m, uint8_t* __restrict__ matched) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+    const long long r = out_r[j];
+    if (r >= 0) matched[r] = 1;
+  }
+}
+#define JU_TILE 4096
+__global__ void __launch_bounds__(256) junmatched_count_kernel(const uint8_t* __restrict__ matched, long long nr, u64* __restrict__ tile_counts) {
+  __shared__ uint32_t sh;
+  for (long long tile = blockIdx.x; tile * JU_TILE < nr; tile += gridDim.x) {
+    if (threadIdx.x == 0) sh = 0;
+    __syncthreads();
+    uint32_t c = 0;
+    for (long long i = tile * JU_TILE + threadIdx.x; i < min(nr, (tile + 1) * JU_TILE); i += 256) c += matched[i] ? 0u : 1u;
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, d);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sh, c);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_counts[tile] = sh;
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(256) junmatched_write_kernel(const uint8_t* __restrict__ matched, long long nr, const u64* __restrict__ tile_offsets,
+                                                               long long* __restrict__ out_l, long long* __restrict__ out_r) {
+  __shared__ uint32_t wsum[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (long long tile = blockIdx.x; tile * JU_TILE < nr; tile += gridDim.x) {
+    // thread t owns 16 consecutive rows of the tile: positions stay ascending in r
+    const long long r0 = tile * JU_TILE + (long long)threadIdx.x * 16;
+    uint32_t mask = 0;
+    for (int k = 0; k < 16; k++) if (r0 + k < nr && !matched[r0 + k]) mask |= 1u << k;
+    const uint32_t mine = __popc(mask);
+    uint32_t incl = mine;
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += t; }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += wsum[w];
+    u64 pos = tile_offsets[tile] + wbase + incl - mine;
+    for (int k = 0; k < 16; k++) if ((mask >> k) & 1u) { out_l[pos] = -1; out_r[pos] = r0 + k; pos++; }
+    __syncthreads();
+  }
+}
+
 struct JPart { DevBuf keys, rows; long long n = 0; };
 static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out) {
   const int nb = 1 << log_nb;
@@ -736,7 +782,9 @@ extern "C" {
 int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, pdrs_join_result** out) {
   if (!c) return PDRS_ERR_BAD_ARG;
   if (!left_key || !right_key || !out) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_pairs: NULL argument");
-  if (how != PDRS_INNER && how != PDRS_LEFT) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join type %d is not implemented (Inner and Left are)", how);
+  if (how < PDRS_INNER || how > PDRS_OUTER) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown join type %d", how);
+  const int32_t how_req = how;
+  how = (how == PDRS_RIGHT) ? PDRS_INNER : (how == PDRS_OUTER ? PDRS_LEFT : how);   // Right / Outer = Inner / Left + the unmatched right rows
   if (left_key->dtype != right_key->dtype)   // join.rs:98-104
     return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "join key columns have different types (%d vs %d)", left_key->dtype, right_key->dtype);
   PDRS_CUDA(c, cudaSetDevice(c->device));
@@ -862,6 +910,38 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   }
   }
   mark("write");
+  if (how_req == PDRS_RIGHT || how_req == PDRS_OUTER) {
+    DevBuf matched, ucounts;
+    PDRS_TRY(matched.alloc(c, (size_t)std::max<int64_t>(nr, 1), true));
+    const long long utiles = (nr + JU_TILE - 1) / JU_TILE;
+    PDRS_TRY(ucounts.alloc(c, (size_t)(utiles + 4) * 8, true));
+    const int ug = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, utiles));
+    if (M > 0) jmark_matched_kernel<<<pdrs_grid_for(c, M, 256), 256, 0, c->stream>>>(res->right.as<long long>(), M, matched.as<uint8_t>());
+    long long U = 0;
+    if (nr > 0) {
+      junmatched_count_kernel<<<ug, 256, 0, c->stream>>>(matched.as<uint8_t>(), nr, ucounts.as<u64>());
+      join_scan_kernel<<<1, 1024, 0, c->stream>>>(ucounts.as<u64>(), (int)utiles, ucounts.as<u64>() + utiles + 2);
+      PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, ucounts.as<u64>() + utiles + 2, 8, cudaMemcpyDeviceToHost, c->stream));
+      PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+      U = c->pinned_scalars[0];
+    }
+    if (U > 0) {
+      DevBuf nl2, nr2;
+      PDRS_TRY(nl2.alloc(c, (size_t)(M + U) * 8));
+      PDRS_TRY(nr2.alloc(c, (size_t)(M + U) * 8));
+      if (M > 0) {
+        PDRS_CUDA(c, cudaMemcpyAsync(nl2.p, res->left.p, (size_t)M * 8, cudaMemcpyDeviceToDevice, c->stream));
+        PDRS_CUDA(c, cudaMemcpyAsync(nr2.p, res->right.p, (size_t)M * 8, cudaMemcpyDeviceToDevice, c->stream));
+      }
+      junmatched_write_kernel<<<ug, 256, 0, c->stream>>>(matched.as<uint8_t>(), nr, ucounts.as<u64>(), nl2.as<long long>() + M, nr2.as<long long>() + M);
+      res->left = std::move(nl2);
+      res->right = std::move(nr2);
+      res->n = M + U;
+    }
+    c->stats.kernel_launches += 4;
+    PDRS_CUDA(c, cudaGetLastError());
+    mark("unmatched right rows");
+  }
   c->stats.groupby_algo_used = radix ? 2 : 1;
   if (!marks.empty()) {
     cudaStreamSynchronize(c->stream);

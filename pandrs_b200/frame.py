@@ -307,11 +307,11 @@ class OptimizedDataFrame:
     def left_join(self, other: "OptimizedDataFrame", left_on: str, right_on: str) -> "OptimizedDataFrame":
         return self._join(other, left_on, right_on, JoinType.Left)
 
-    def right_join(self, other, left_on, right_on):
-        raise OperationFailed("right_join is outside the accelerated path (Inner and Left are implemented; no CPU fallback)")
+    def right_join(self, other: "OptimizedDataFrame", left_on: str, right_on: str) -> "OptimizedDataFrame":
+        return self._join(other, left_on, right_on, JoinType.Right)
 
-    def outer_join(self, other, left_on, right_on):
-        raise OperationFailed("outer_join is outside the accelerated path (Inner and Left are implemented; no CPU fallback)")
+    def outer_join(self, other: "OptimizedDataFrame", left_on: str, right_on: str) -> "OptimizedDataFrame":
+        return self._join(other, left_on, right_on, JoinType.Outer)
 
     def _join(self, other, left_on, right_on, how) -> "OptimizedDataFrame":
         if left_on not in self._cols:
@@ -323,7 +323,7 @@ class OptimizedDataFrame:
             raise ColumnTypeMismatch(f"column '{left_on}': expected {lk.column_type}, found {rk.column_type}")
         ctx = get_context()
         try:
-            res = ctx.join_pairs(lk.raw, rk.raw, N.INNER if how == JoinType.Inner else N.LEFT)
+            res = ctx.join_pairs(lk.raw, rk.raw, {JoinType.Inner: N.INNER, JoinType.Left: N.LEFT, JoinType.Right: N.RIGHT, JoinType.Outer: N.OUTER}[how])
         except PandrsError as e:
             raise (ColumnTypeMismatch if e.code == N.ERR_TYPE_MISMATCH else OperationFailed)(str(e)) from e
         li, ri = res.indices()
@@ -340,11 +340,22 @@ class OptimizedDataFrame:
         for name in self._order:                                  # join.rs:290-552: [left non-key..., key, right non-key...]
             if name != left_on:
                 out.add_column(name, _gathered(ctx, self._cols[name], li))
-        out.add_column(left_on, _gathered(ctx, lk, li))
+        out.add_column(left_on, _gathered_key(ctx, lk, rk, li, ri))          # the left key, or the right key on right-only rows (join.rs:395-472)
         for name in other._order:
             if name != right_on:
                 out.add_column(name + "_right" if name in out._cols else name, _gathered(ctx, other._cols[name], ri))
         return out
+
+
+def _gathered_key(ctx: Context, lk: _TypedColumn, rk: _TypedColumn, li: np.ndarray, ri: np.ndarray) -> _TypedColumn:
+    a = _gathered(ctx, lk, li)
+    if not (li < 0).any():
+        return a
+    b = _gathered(ctx, rk, ri)
+    pick = li < 0
+    if lk.dtype == N.DICT_U32:
+        return StringColumn(None, _ids=np.where(pick, b.ids, a.ids))
+    return type(a)(np.where(pick, b.values, a.values))
 
 
 def _empty_like(col: _TypedColumn) -> _TypedColumn:

@@ -137,10 +137,12 @@ def test_gpu_join_tests_of_the_reference(frame):
     joined = left.left_join(right, "id", "id")
     assert joined.row_count() == 4 and joined.column_count() == 3
     assert joined.column("value").values.tolist() == [100, 200, 0, 0]            # missing side -> type default, no null mask
-    with pytest.raises(fr.OperationFailed):
-        left.right_join(right, "id", "id")
-    with pytest.raises(fr.OperationFailed):
-        left.outer_join(right, "id", "id")
+    joined = left.right_join(right, "id", "id")                                  # test_right_join: ids 1, 2, 5, 6
+    assert joined.row_count() == v["right_rows"] and joined.column_count() == 3
+    assert sorted(joined.column("id").values.tolist()) == [1, 2, 5, 6] and sorted(joined.column("value").values.tolist()) == [100, 200, 500, 600]
+    assert sorted(joined.column("name").to_list()) == ["", "", "Alice", "Bob"]   # right-only rows: left columns take the type default
+    joined = left.outer_join(right, "id", "id")                                  # test_outer_join: ids 1..6
+    assert joined.row_count() == v["outer_rows"] and sorted(joined.column("id").values.tolist()) == [1, 2, 3, 4, 5, 6]
     # test_empty_join: no matching ids -> 0 rows
     other = fr.OptimizedDataFrame.new()
     other.add_column("id", fr.Int64Column(v["right_ids_disjoint"]))

@@ -80,8 +80,8 @@ def test_join_type_mismatch_and_unsupported(ctx):
         ctx.join_pairs(pb.Column.int64([1]), pb.Column.float64([1.0]))
     assert e.value.kind == "ColumnTypeMismatch"
     with pytest.raises(pb.PandrsError) as e:
-        ctx.join_pairs(pb.Column.int64([1]), pb.Column.int64([1]), how=3)
-    assert e.value.kind == "OperationFailed"
+        ctx.join_pairs(pb.Column.int64([1]), pb.Column.int64([1]), how=7)
+    assert e.value.kind == "InvalidInput"
     # aggregation.rs:748-752 -> Error::OperationFailed for Sum on a string column; Count is fine
     with pytest.raises(pb.PandrsError) as e:
         ctx.groupby_agg([pb.Column.int64([1, 2])], [pb.Column.dict_ids([0, 1])], [(0, pb.SUM)])
@@ -360,6 +360,34 @@ def test_join_random_duplicates_and_nulls(ctx, oracle, how):
     R = Spec(pb.I64, rng.integers(0, 400, 2000), nulls=rng.random(2000) < 0.05)
     compare_join(pb, oracle, ctx, L, R, how)
     compare_join(pb, oracle, ctx, L, R, how, device=True)
+
+
+@pytest.mark.parametrize("how", [pb.RIGHT, pb.OUTER])
+@pytest.mark.parametrize("size", ["small", "radix"])
+def test_right_and_outer_joins(ctx, oracle, how, size):
+    # join.rs:211-224: unmatched right rows are appended as (None, r), NULL-key right rows included
+    rng = np.random.default_rng(11)
+    if size == "small":
+        nl, nr, dom = 5000, 3000, 2500
+    else:
+        nl, nr, dom = 400_000, 120_000, 200_000
+    L = Spec(pb.I64, rng.integers(0, dom, nl), nulls=rng.random(nl) < 0.02)
+    R = Spec(pb.I64, rng.integers(0, dom, nr), nulls=rng.random(nr) < 0.02)
+    if size == "radix":
+        ctx.set_option("join_algo", 2)
+    try:
+        li, ri = compare_join(pb, oracle, ctx, L, R, how, device=True, check_order=False)
+    finally:
+        ctx.set_option("join_algo", 0)
+    assert (li < 0).sum() > 0 and ((ri < 0).sum() > 0) == (how == pb.OUTER)
+    # unique build keys take the single-pass probe + emit on the radix path
+    Ru = Spec(pb.I64, rng.permutation(dom)[:nr])
+    if size == "radix":
+        ctx.set_option("join_algo", 2)
+    try:
+        compare_join(pb, oracle, ctx, L, Ru, how, device=True, check_order=False)
+    finally:
+        ctx.set_option("join_algo", 0)
 
 
 @pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
