@@ -61,6 +61,7 @@ template <int RPT> struct TsRows {
   uint32_t vnw, knw, fw;   // lane l holds bitmap word (l % RPT) of the warp's 32 * RPT rows: value NULLs, key NULLs, filter & ~filter NULLs
   uint32_t fl[RPT / 2];    // partitioned input: the flag bytes of rows 2 j, 2 j + 1 (bit 0 / bit 8: value is NULL)
   uint32_t act;            // bit q: row q of this lane is inside the column / partition
+  uint32_t knm;            // generic (packed) keys: bit q: the key of row q is NULL (single-column keys only)
 };
 
 // One unit of work of a CTA: a tile of up to TS_T consecutive rows.  Plain input: tiles blockIdx, blockIdx + grid, ...
@@ -119,19 +120,78 @@ __device__ __forceinline__ TsItem ts_next_item(const GbParams& p, const TsItem& 
 
 // Rows of one warp in one tile: load j, lane l -> rows wbase + 64 j + 2 l + {0, 1} (one 128-bit load).
 // Partitioned input: the tile's memory always exists (partitions are padded to whole tiles), rows >= valid are masked.
-template <int RPT, bool PLAIN, bool PART>
+template <int RPT, bool PLAIN, bool PART, bool GENERIC, bool PACK32>
 __device__ __forceinline__ void ts_load(const GbParams& p, const TsItem& it, int warp, int lane, TsRows<RPT>& r) {
   const long long wbase = it.base + (long long)warp * (32 * RPT);
   const int wfirst = warp * (32 * RPT);           // first row of the warp inside the tile
   const u64* keys = (PART ? p.part_keys : reinterpret_cast<const u64*>(p.ks.c[0].data)) + wbase + 2 * lane;
-  if (PART || wfirst + 32 * RPT <= it.valid) {
+  r.knm = 0;
+  if (PACK32) {           // one or two 4-byte key columns without null bitmaps: RAW loads only (two rows of column k, chunk j in
+                          // r.k[k * RPT / 2 + j]); nothing is consumed here, the tuple is packed at the start of phase 1
+    r.act = 0;
+#pragma unroll
+    for (int q = 0; q < RPT; q++) { r.k[q] = 0; if (wfirst + 64 * (q >> 1) + 2 * lane + (q & 1) < it.valid) r.act |= 1u << q; }
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+      if (k < p.ks.nkeys) {
+        const uint32_t* d = reinterpret_cast<const uint32_t*>(p.ks.c[k].data) + wbase + 2 * lane;
+#pragma unroll
+        for (int j = 0; j < RPT / 2; j++) {
+          if ((r.act >> (2 * j + 1)) & 1u) { const uint2 t = __ldcs(reinterpret_cast<const uint2*>(d + 64 * j)); r.k[k * (RPT / 2) + j] = (u64)t.x | ((u64)t.y << 32); }
+          else if ((r.act >> (2 * j)) & 1u) r.k[k * (RPT / 2) + j] = (u64)__ldg(d + 64 * j);
+        }
+      }
+    }
+  } else if (GENERIC) {   // any key tuple that packs into one 64-bit word (dictionary ids, i32, bool, pairs of them)
+    // column by column, two adjacent rows per load (the packing of load_key_generic, restated without per-row calls)
+    r.act = 0;
+#pragma unroll
+    for (int q = 0; q < RPT; q++) { r.k[q] = 0; if (wfirst + 64 * (q >> 1) + 2 * lane + (q & 1) < it.valid) r.act |= 1u << q; }
+    for (int k = 0; k < p.ks.nkeys; k++) {
+      const KeyColDev c = p.ks.c[k];
+#pragma unroll
+      for (int j = 0; j < RPT / 2; j++) {
+        const long long row0 = wbase + 64 * j + 2 * lane;
+        const bool in0 = (r.act >> (2 * j)) & 1u, in1 = (r.act >> (2 * j + 1)) & 1u;
+        u64 v0 = 0, v1 = 0;
+        bool n0 = false, n1 = false;
+        if (c.nulls && in0) { const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(c.nulls) + (row0 >> 5)); n0 = (w >> (row0 & 31)) & 1u; n1 = (w >> ((row0 & 31) + 1)) & 1u; }
+        switch (c.dtype) {
+          case PDRS_I64: case PDRS_F64: {
+            const u64* d = reinterpret_cast<const u64*>(c.data) + row0;
+            if (in1) { const ulonglong2 t = ld_stream_v2(d); v0 = t.x; v1 = t.y; } else if (in0) v0 = __ldg(d);
+            if (c.dtype == PDRS_F64) {       // all NaNs print "NaN"
+              if (__longlong_as_double((long long)v0) != __longlong_as_double((long long)v0)) v0 = 0x7FF8000000000000ull;
+              if (__longlong_as_double((long long)v1) != __longlong_as_double((long long)v1)) v1 = 0x7FF8000000000000ull;
+            }
+            break;
+          }
+          case PDRS_I32: case PDRS_DICT_U32: {
+            const uint32_t* d = reinterpret_cast<const uint32_t*>(c.data) + row0;
+            if (in1) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(d)); v0 = t.x; v1 = t.y; } else if (in0) v0 = __ldg(d);
+            if (c.dtype == PDRS_DICT_U32) { if ((long long)v0 == c.null_alias) n0 = true; if ((long long)v1 == c.null_alias) n1 = true; }
+            break;
+          }
+          default: {                           // PDRS_BOOL_BITS
+            if (in0) { const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(c.data) + (row0 >> 5)); v0 = (w >> (row0 & 31)) & 1u; v1 = (w >> ((row0 & 31) + 1)) & 1u; }
+            break;
+          }
+        }
+        if (n0) { if (p.ks.single_null) r.knm |= 1u << (2 * j); else if (c.nword >= 0) r.k[2 * j] |= 1ull << c.nshift; }
+        else r.k[2 * j] |= v0 << c.shift;
+        if (n1) { if (p.ks.single_null) r.knm |= 1u << (2 * j + 1); else if (c.nword >= 0) r.k[2 * j + 1] |= 1ull << c.nshift; }
+        else r.k[2 * j + 1] |= v1 << c.shift;
+      }
+    }
+  } else if (PART || wfirst + 32 * RPT <= it.valid) {
 #pragma unroll
     for (int j = 0; j < RPT / 2; j++) {
       const ulonglong2 kk = ld_stream_v2(keys + 64 * j);
       r.k[2 * j] = kk.x; r.k[2 * j + 1] = kk.y;
     }
   }
-  if (wfirst + 32 * RPT <= it.valid) r.act = (1u << RPT) - 1u;
+  if (GENERIC || PACK32) {
+  } else if (wfirst + 32 * RPT <= it.valid) r.act = (1u << RPT) - 1u;
   else {
     r.act = 0;
 #pragma unroll
@@ -151,7 +211,7 @@ __device__ __forceinline__ void ts_load(const GbParams& p, const TsItem& it, int
     const bool inb = w * 32 < p.n;           // bitmaps cover ceil(n / 64) * 8 bytes (pdrs_view_col)
     r.vnw = (p.vnull && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.vnull) + w) : 0u;
     if (!PLAIN) {
-      r.knw = (p.ks.c[0].nulls && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.ks.c[0].nulls) + w) : 0u;
+      r.knw = (!GENERIC && !PACK32 && p.ks.c[0].nulls && inb) ? __ldg(reinterpret_cast<const uint32_t*>(p.ks.c[0].nulls) + w) : 0u;
       uint32_t f = 0xFFFFFFFFu;
       if (p.fbits) {   // filter keeps Some(true) rows only (data_ops.rs:49-55)
         f = inb ? __ldg(reinterpret_cast<const uint32_t*>(p.fbits) + w) : 0u;
@@ -231,7 +291,9 @@ __device__ __noinline__ int ts_insert(u64* ktab_key, uint32_t* ktab_id, uint32_t
   return res;
 }
 
-// KMODE: 0 = direct-mapped ids (small dense integer keys), 1 = CTA key table, 2 = CTA key table over hash-partitioned rows.
+// KMODE: 0 = direct-mapped ids (small dense integer keys), 1 = CTA key table, 2 = CTA key table over hash-partitioned rows,
+//        3 = CTA key table over generic key tuples packed into one 64-bit word (load_key_generic),
+//        4 = the same for one or two 4-byte key columns without null bitmaps (raw loads stay in flight, packed in phase 1).
 // Histogram word of a group in a tile: low 16 bits = rows with a value (after the scan: offset of the group's
 // segment), high 16 bits = rows whose value is NULL.  One native atomic per row serves both counts.
 template <int NT, typename VT, int FLAGS, int GPT, int KMODE, bool PLAIN>
@@ -239,7 +301,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
   using T = ValTraits<VT>;
   constexpr bool IS_INT = T::is_int;
   constexpr bool ALL = FLAGS == GB_ALL;
-  constexpr bool DENSE = KMODE == 0, PART = KMODE == 2;
+  constexpr bool DENSE = KMODE == 0, PART = KMODE == 2, PACK32 = KMODE == 4, GENERIC = KMODE == 3 || KMODE == 4;
   constexpr int TT = TsGeom<NT>::TT;
   constexpr int RPT = TT / NT, WROWS = 32 * RPT, NWARPS = NT / 32;
   constexpr int NP = NT * GPT, NPAD = NP + 32;
@@ -310,7 +372,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
 
   TsItem cur = ts_first_item<PART, TT>(p);
   TsRows<RPT> r;
-  if (cur.valid) { issue_vals(cur); ts_load<RPT, PLAIN, PART>(p, cur, warp, lane, r); }
+  if (cur.valid) { issue_vals(cur); ts_load<RPT, PLAIN, PART, GENERIC && !PACK32, PACK32>(p, cur, warp, lane, r); }
   uint32_t tma_phase = 0;
   const int sh2 = (2 * lane) & 31;
   const uint32_t vm0 = 1u << sh2, vm1 = 2u << sh2;      // this lane's two bits in a bitmap word
@@ -328,6 +390,29 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
     // ---- phase 1: group ids, tile histogram (the atomic's return value ranks the row inside its group)
     uint32_t pack[RPT];
     uint32_t skipmask = 0, zeromask = 0;
+    if (PACK32) {        // raw 4-byte key columns -> the packed key tuple of every row (the layout of load_key_generic)
+      u64 t[RPT];
+      uint32_t knm = 0;
+      const KeyColDev c0 = p.ks.c[0], c1 = p.ks.c[1];
+      const bool two = p.ks.nkeys == 2;
+#pragma unroll
+      for (int q = 0; q < RPT; q++) {
+        const int j = q >> 1, h = q & 1;
+        u64 word = 0;
+        const uint32_t a = (uint32_t)(r.k[j] >> (32 * h));
+        if (c0.dtype == PDRS_DICT_U32 && (long long)a == c0.null_alias) { if (p.ks.single_null) knm |= 1u << q; else if (c0.nword >= 0) word |= 1ull << c0.nshift; }
+        else word |= (u64)a << c0.shift;
+        if (two) {
+          const uint32_t bq = (uint32_t)(r.k[RPT / 2 + j] >> (32 * h));
+          if (c1.dtype == PDRS_DICT_U32 && (long long)bq == c1.null_alias) { if (c1.nword >= 0) word |= 1ull << c1.nshift; }
+          else word |= (u64)bq << c1.shift;
+        }
+        t[q] = word;
+      }
+#pragma unroll
+      for (int q = 0; q < RPT; q++) r.k[q] = t[q];
+      r.knm = knm;
+    }
     const bool fullw = __all_sync(0xFFFFFFFFu, r.act == (1u << RPT) - 1u);
     if (PLAIN && DENSE && fullw) {
       // every row is inside the column, no filter, no NULL keys, direct-mapped ids: ~16 instructions per row
@@ -374,8 +459,9 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
         const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
         const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
         const bool live = (r.act >> q) & 1u;
-        const bool hit = idw != 0 && idw != SH_BUSY && kk == r.k[q];
+        bool hit = idw != 0 && idw != SH_BUSY && kk == r.k[q];
         ids[q] = hit ? idw - 1 : 0xFFFFFFFFu;
+        if (GENERIC && ((r.knm >> q) & 1u)) { hit = true; ids[q] = (uint32_t)cap; }      // the NULL-key group
         if (live && !hit) { if (idw == 0 || idw == SH_BUSY) slowmask |= 1u << q; else pend |= 1u << q; }   // new key -> insertion; else go on probing
       }
       // rows displaced from their home slot (~10% at load factor 1/4): every lane follows the probe sequence of its
@@ -459,7 +545,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
         if (!PLAIN) {
           const uint32_t fword = __shfl_sync(0xFFFFFFFFu, r.fw, wsrc), kword = __shfl_sync(0xFFFFFFFFu, r.knw, wsrc);   // every lane shuffles: no short-circuit
           active = active && (fword & (h ? vm1 : vm0)) != 0;
-          knull = (kword & (h ? vm1 : vm0)) != 0;
+          knull = GENERIC ? ((r.knm >> q) & 1u) != 0 : (kword & (h ? vm1 : vm0)) != 0;
           if (p.compat_nulls && vnull) { vnull = false; zeromask |= 1u << q; }   // filter + compat_filter_nulls (data_ops.rs:64-71)
         }
         uint32_t gid = 0;
@@ -500,7 +586,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
       }
     }
     // keys (and bitmap words) of this CTA's next tile: in flight during phases 2-4
-    if (nxt.valid) ts_load<RPT, PLAIN, PART>(p, nxt, warp, lane, r);
+    if (nxt.valid) ts_load<RPT, PLAIN, PART, GENERIC && !PACK32, PACK32>(p, nxt, warp, lane, r);
     TSP_MARK(0);
     __syncthreads();
     TSP_MARK(1);
@@ -640,9 +726,16 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
 
 template <int NT, typename VT, int FLAGS, int GPT>
 cudaError_t ts_launch4(const GbParams& p, int ctas, size_t smem, cudaStream_t s) {
-  const bool plain = !p.fbits && !p.compat_nulls && !p.ks.c[0].nulls;
+  const bool generic = p.ts_generic != 0;
+  const bool plain = !p.fbits && !p.compat_nulls && (generic || !p.ks.c[0].nulls);
   auto k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true>;
   if (p.part_keys) k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 2, true>;
+  else if (generic) {
+    bool pack32 = p.ks.nkeys <= 2;
+    for (int i = 0; i < p.ks.nkeys; i++) pack32 = pack32 && !p.ks.c[i].nulls && (p.ks.c[i].dtype == PDRS_I32 || p.ks.c[i].dtype == PDRS_DICT_U32);
+    if (pack32) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, false>;
+    else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, false>;
+  }
   else if (p.sh_dense) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, false>;
   else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

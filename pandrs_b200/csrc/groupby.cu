@@ -421,7 +421,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   bool ts_dense = false;
   long long ts_cap = 0;
   bool ts_fit = false;
-  if (variant == 0 && c->opt_tsort != 0 && est >= c->opt_tsort_min_groups && n >= 4 * gb_tsort_tile_rows() && n < (1ll << 38) &&
+  const bool ts_generic = variant == 1;     // any key tuple that packs into one 64-bit word (dictionary ids, i32, bool, pairs of them)
+  if ((variant == 0 || ts_generic) && c->opt_tsort != 0 && est >= c->opt_tsort_min_groups && n >= 4 * gb_tsort_tile_rows() && n < (1ll << 38) &&
       (c->opts.groupby_algo == PDRS_GB_AUTO || c->opts.groupby_algo == PDRS_GB_TILESORT)) {
     ts_dense = dense_ok && c->opt_dense != 0;
     ts_cap = ts_dense ? dense_range + std::max<long long>(dense_range / 16, 8) : est + std::max<long long>(est / 16, 8);
@@ -499,6 +500,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           gp.sh_cap = (int)ts_cap; gp.sh_slots = ts_slots; gp.sh_log_slots = ts_slots ? ilog2(ts_slots) : 0;
           gp.sh_dense = ts_dense ? 1 : 0; gp.sh_dense_base = dense_base;
           gp.ts_heavy = c->opt_tsort_heavy > 0 ? (int)c->opt_tsort_heavy : 128;
+          gp.ts_generic = ts_generic ? 1 : 0;
           const long long trows = gb_tsort_tile_rows_for(ts_nt), tiles = (n + trows - 1) / trows;
           PDRS_CUDA(c, gb_tsort_launch(gp, passes[i].is_int, passes[i].flags, ts_nt, ts_gpt, (int)std::min<long long>((long long)c->sm_count * (ts_nt == 256 ? 2 : 1), tiles), ts_smem, c->stream));
           c->stats.groupby_algo_used = PDRS_GB_TILESORT;

@@ -332,6 +332,34 @@ def test_multi_key_and_dictionary(ctx, oracle):
     compare_groupby(pb, oracle, ctx, [k1n, k2s, k3n], [v], [(0, op) for op in ALL6])
 
 
+def test_packed_keys_through_the_tile_sort_kernel(ctx, oracle):
+    # string (dictionary) keys, i32 keys and key pairs that pack into one 64-bit word take the tile-sort kernel
+    # through load_key_generic; NULL keys, a literal "NULL" string, a row filter, int and float values
+    n = 180_000
+    rng = np.random.default_rng(12)
+    pool = [f"name{i}" for i in range(300)] + ["NULL"]
+    ids = rng.integers(0, 301, n).astype(np.uint32)
+    ks = Spec(pb.DICT_U32, ids, nulls=rng.random(n) < 0.03, pool=pool, null_alias=300)
+    k32 = Spec(pb.I32, rng.integers(-40, 40, n).astype(np.int32), nulls=rng.random(n) < 0.1)
+    kb = Spec(pb.BOOL_BITS, rng.random(n) < 0.5)
+    v = Spec(pb.F64, rng.normal(5.0, 2.0, n), nulls=rng.random(n) < 0.05)
+    vi = Spec(pb.I64, rng.integers(-1000, 1000, n))
+    f = Spec(pb.BOOL_BITS, rng.random(n) < 0.8, nulls=rng.random(n) < 0.05)
+    aggs = [(0, op) for op in ALL6] + [(1, op) for op in ALL6]
+    k32d = Spec(pb.I32, rng.integers(-40, 40, n).astype(np.int32))                       # 32 + 32 bits: exactly one word
+    ksd = Spec(pb.DICT_U32, rng.integers(0, 20, n).astype(np.uint32), pool=pool)
+    for keys in ([ks], [k32], [k32d, ksd], [kb, k32]):
+        compare_groupby(pb, oracle, ctx, keys, [v, vi], aggs, device=True)
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_TILESORT, [k.dtype for k in keys]
+    compare_groupby(pb, oracle, ctx, [kb, k32], [v, vi], aggs, filter_spec=f, device=True)
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_TILESORT
+    ctx.set_option("compat_filter_nulls", 1)
+    try:
+        compare_groupby(pb, oracle, ctx, [ks], [v], [(0, pb.SUM), (0, pb.STD)], filter_spec=f, device=True, compat_nulls=True)
+    finally:
+        ctx.set_option("compat_filter_nulls", 0)
+
+
 @pytest.mark.parametrize("compat", [False, True])
 def test_fused_filter(ctx, oracle, compat):
     # BASELINE.json configs[4] shape: Boolean-mask filter -> groupby(returnflag, linestatus)
