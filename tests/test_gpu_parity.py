@@ -238,6 +238,18 @@ def test_partitioned_high_cardinality_path(ctx, oracle):
             ctx.set_option("part", 1)
 
 
+def test_partition_overflow_falls_back(ctx, oracle):
+    # heavily skewed high-cardinality keys: one key owns half of the rows, so its hash bucket overflows the padded
+    # range of the one-pass partition; the call must restart on the global-table path and still match the oracle
+    rng = np.random.default_rng(8)
+    n = 3_000_000
+    kv = np.where(rng.random(n) < 0.5, 123_456_789, rng.integers(0, 40_000, n) * 104_729)
+    k = Spec(pb.I64, kv)
+    v = Spec(pb.F64, rng.normal(1.0, 1.0, n), nulls=rng.random(n) < 0.05)
+    got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+    assert len(got) == len(np.unique(kv)) and ctx.stats()["groupby_algo_used"] != pb.GB_PARTITIONED
+
+
 @pytest.mark.parametrize("radix", [1, 0])
 def test_high_cardinality_radix_path(ctx, oracle, radix):
     # BASELINE.json configs[1] "10M distinct" shape at oracle-sized n: the table (slots x 80 B) no longer fits L2, so
