@@ -589,6 +589,69 @@ def test_two_kernels_agree_at_scale(ctx):
     assert np.array_equal(a[3][4], a[1].astype(np.float64))
 
 
+def test_full_size_groupby_properties(ctx):
+    # BASELINE.json configs[1] at its full size (1e9 rows, 5% NULL values) through size-independent properties:
+    # counts sum to n, valid counts to the non-NULL rows, sum = mean * n, min <= mean <= max, std >= 0, and the
+    # 1K-group result agrees with the sum over a finer grouping (key and key // 1000 of the same rows)
+    n = 1_000_000_000
+    vals = ctx.synth_vals(n, null_per_million=50_000)
+    fine = ctx.synth_keys(n, card=1_000_000)                 # hash-partitioned path
+    aggs = [(0, op) for op in ALL6]
+    res = {}
+    for name, card in (("1k", 1000), ("10m", 10_000_000)):
+        keys = ctx.synth_keys(n, card=card)
+        r = ctx.groupby_agg([keys], [vals], aggs)
+        k, _ = r.key(0)
+        rows, nv = r.group_rows(), r.valid_n(0)
+        a = [r.agg(i) for i in range(6)]
+        r.close()
+        del keys
+        assert len(k) == card and len(np.unique(k)) == card
+        assert rows.sum() == n and abs(nv.sum() / n - 0.95) < 1e-4
+        assert np.array_equal(a[4], rows.astype(np.float64))
+        ok = nv > 0
+        assert np.allclose(a[0][ok], a[1][ok] * nv[ok], rtol=1e-12)
+        assert (a[2][ok] <= a[1][ok]).all() and (a[1][ok] <= a[3][ok]).all() and (a[5] >= 0).all()
+        assert (a[2][ok] >= 0).all() and (a[3] < 1000.0).all()
+        res[name] = (rows.sum(), nv.sum(), a[0].sum())
+    r = ctx.groupby_agg([fine], [vals], [(0, pb.SUM), (0, pb.COUNT)])
+    s_fine, c_fine = r.agg(0).sum(), r.agg(1).sum()
+    r.close()
+    assert c_fine == n
+    for name in res:
+        assert abs(res[name][2] - s_fine) <= 1e-9 * abs(s_fine)      # the same 1e9 values summed along three different groupings
+
+
+def test_full_size_join_properties(ctx):
+    # BASELINE.json configs[2] at its full size (1e9-row probe x 1e8-row build, unique keys, ~50% hits):
+    # |left| = n_probe, |inner| + unmatched = n_probe, every pair joins equal keys, no probe row appears twice
+    nb, npr = 100_000_000, 1_000_000_000
+    build = ctx.synth_join_keys(nb, unique=True)
+    probe = ctx.synth_join_keys(npr, domain=2 * nb)
+    j = ctx.join_pairs(probe, build, pb.INNER)
+    m_inner = j.n
+    assert 0.49 * npr < m_inner < 0.51 * npr
+    # key equality on the device for a sample window of the pairs + the whole left index column is a set
+    w = min(m_inner, 20_000_000)
+    for off in (0, m_inner - w):
+        lk = ctx.gather(probe, j.left_dev() + 8 * off, n=w, idx_dev=True, out_dev=ctx.dev_alloc(w * 8))
+        rk = ctx.gather(build, j.right_dev() + 8 * off, n=w, idx_dev=True, out_dev=ctx.dev_alloc(w * 8))
+        a, b = ctx.to_host(lk, w, np.int64), ctx.to_host(rk, w, np.int64)
+        ctx.dev_free(lk); ctx.dev_free(rk)
+        assert np.array_equal(a, b)
+    li = ctx.to_host(j.left_dev(), min(m_inner, 50_000_000), np.int64)
+    assert len(np.unique(li)) == len(li) and li.min() >= 0 and li.max() < npr
+    j.close()
+    j = ctx.join_pairs(probe, build, pb.LEFT)
+    assert j.n == npr
+    ri = ctx.to_host(j.right_dev(), 50_000_000, np.int64)
+    assert ((ri >= -1) & (ri < nb)).all()
+    j.close()
+    j = ctx.join_pairs(probe, build, pb.RIGHT)          # unique build keys: inner pairs + the build rows nobody asked for
+    assert j.n >= m_inner and j.n - m_inner < nb
+    j.close()
+
+
 # ---------------------------------------------------------------- multi-GPU plumbing on one GPU (world size 1)
 class _OneRankDist:
     """torch.distributed look-alike for a single rank: every collective is a copy."""
