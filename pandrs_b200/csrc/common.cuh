@@ -44,7 +44,9 @@ struct pdrs_ctx {
   int64_t opt_dense = 1;               // allow the direct-mapped path for small dense integer keys
   int64_t opt_tsort = 1;               // allow the tile-sort kernel (gb_tsort.cu)
   int64_t opt_part = 1;                // allow the hash-partitioned high-cardinality path (gb_part.cu)
-  int64_t opt_tsort_heavy = 0;         // 0 = default 128
+  int64_t opt_tsort_heavy = 0;         // 0 = default 256
+  int64_t opt_tsort_mid = 0;           // 0 = default 48
+  int64_t opt_tsort_team = 0;          // 0 = auto (estimated groups < 500), 1 = always, 2 = never
   int64_t opt_tsort_threads = 0;       // 0 = auto, else 512 / 1024 threads per CTA
   int64_t opt_tsort_min_groups = 2;    // a single group serialises the tile histogram: the per-warp shared tables win
 };

@@ -126,6 +126,8 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "tsort")) c->opt_tsort = value;
   else if (!strcmp(name, "part")) c->opt_part = value;
   else if (!strcmp(name, "tsort_heavy")) c->opt_tsort_heavy = value;
+  else if (!strcmp(name, "tsort_mid")) c->opt_tsort_mid = value;
+  else if (!strcmp(name, "tsort_team")) c->opt_tsort_team = value;
   else if (!strcmp(name, "tsort_threads")) c->opt_tsort_threads = value;
   else if (!strcmp(name, "tsort_min_groups")) c->opt_tsort_min_groups = value;
   else return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown option '%s'", name);

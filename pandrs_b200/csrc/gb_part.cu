@@ -249,7 +249,9 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
     tp.part_chunk_tiles = (int)((tiles_cap + cpp - 1) / cpp);
     tp.part_cpp = (int)((tiles_cap + tp.part_chunk_tiles - 1) / tp.part_chunk_tiles);
   }
-  tp.ts_heavy = c->opt_tsort_heavy > 0 ? (int)c->opt_tsort_heavy : 128;
+  tp.ts_heavy = c->opt_tsort_heavy > 0 ? (int)c->opt_tsort_heavy : 256;
+  tp.ts_mid = c->opt_tsort_mid > 0 ? (int)c->opt_tsort_mid : 48;
+  tp.ts_team = (est_groups >> bits) < 64;          // a partition with few groups has long segments
   tp.sh_cap = (int)ts_cap; tp.sh_slots = ts_slots; tp.sh_dense = 0; tp.sh_dense_base = 0;
   int lg = 0;
   while ((1 << lg) < ts_slots) lg++;

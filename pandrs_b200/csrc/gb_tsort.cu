@@ -296,7 +296,7 @@ __device__ __noinline__ int ts_insert(u64* ktab_key, uint32_t* ktab_id, uint32_t
 //        4 = the same for one or two 4-byte key columns without null bitmaps (raw loads stay in flight, packed in phase 1).
 // Histogram word of a group in a tile: low 16 bits = rows with a value (after the scan: offset of the group's
 // segment), high 16 bits = rows whose value is NULL.  One native atomic per row serves both counts.
-template <int NT, typename VT, int FLAGS, int GPT, int KMODE, bool PLAIN>
+template <int NT, typename VT, int FLAGS, int GPT, int KMODE, bool PLAIN, bool TEAM>
 __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const GbParams p) {
   using T = ValTraits<VT>;
   constexpr bool IS_INT = T::is_int;
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
     TSP_MARK(4);
     if (nxt.valid) issue_vals(nxt);   // stage is free: values of the next tile
     // ---- phase 4: every thread reduces the segments of the groups it owns
-    bool heavy[GPT];
+    bool heavy[GPT], medium[GPT];
     uint32_t hoff[GPT], hend[GPT];
 #pragma unroll
     for (int s = 0; s < GPT; s++) {
@@ -656,7 +656,8 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
         }
       }
       heavy[s] = len > (uint32_t)p.ts_heavy;
-      if (!heavy[s]) {
+      medium[s] = TEAM && !heavy[s] && len > (uint32_t)p.ts_mid;
+      if (!heavy[s] && !medium[s]) {
         const double pv = __longlong_as_double((long long)acc[s].piv);
         double S1 = acc[s].S1, S2 = acc[s].S2;
         VT mn = acc[s].mn, mx = acc[s].mx;
@@ -673,6 +674,53 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
 #pragma unroll 1
         for (; i < end; i++) ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, sorted[i]);
         acc[s].S1 = S1; acc[s].S2 = S2; acc[s].mn = mn; acc[s].mx = mx; acc[s].isum = isum;
+      }
+    }
+    // segments of ts_mid .. ts_heavy rows: teams of 8 lanes, four groups of the warp at a time (a whole-warp reduce
+    // would spend more on the 5 x 8 shuffles than on the rows; one lane alone would serialise ~100 rows)
+#pragma unroll
+    for (int s = 0; s < GPT; s++) {
+      unsigned mm = TEAM ? __ballot_sync(0xFFFFFFFFu, medium[s]) : 0u;
+      while (TEAM && mm) {
+        const int team = lane >> 3, rr = lane & 7;
+        const int src = __fns(mm, 0, team + 1);                     // owner lane of this team's group, -1 if none
+        const bool on = src >= 0 && src < 32;
+        const int srcl = on ? src : 0;
+        const uint32_t o = __shfl_sync(0xFFFFFFFFu, hoff[s], srcl), e = __shfl_sync(0xFFFFFFFFu, hend[s], srcl);     // every lane shuffles
+        const u64 pvb = __shfl_sync(0xFFFFFFFFu, acc[s].piv, srcl);
+        const double pv = __longlong_as_double((long long)pvb);
+        double S1 = 0.0, S2 = 0.0;
+        VT mn = T::min_init(), mx = T::max_init();
+        u64 isum = 0;
+        uint32_t i = o + rr;
+        const uint32_t ee = on ? e : 0u;
+#pragma unroll 1
+        for (; i + 8 < ee; i += 16) { const u64 x0 = sorted[i], x1 = sorted[i + 8]; ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, x0); ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, x1); }
+        if (i < ee) ts_add<VT, FLAGS>(S1, S2, mn, mx, isum, pv, sorted[i]);
+#pragma unroll
+        for (int d = 4; d; d >>= 1) {
+          if (ALL || !IS_INT) S1 += __shfl_xor_sync(0xFFFFFFFFu, S1, d);
+          if (IS_INT) isum += __shfl_xor_sync(0xFFFFFFFFu, isum, d);
+          if (ALL) {
+            S2 += __shfl_xor_sync(0xFFFFFFFFu, S2, d);
+            const VT omn = T::from_bits(__shfl_xor_sync(0xFFFFFFFFu, T::to_bits(mn), d)), omx = T::from_bits(__shfl_xor_sync(0xFFFFFFFFu, T::to_bits(mx), d));
+            mn = omn < mn ? omn : mn;
+            mx = omx > mx ? omx : mx;
+          }
+        }
+        // hand the team results to the owner lanes: the k-th selected owner reads lane 8 k
+        const int rank = __popc(mm & ((1u << lane) - 1u));
+        const bool mine = ((mm >> lane) & 1u) && rank < 4;
+        const int from = mine ? rank * 8 : lane;
+        const double rS1 = __shfl_sync(0xFFFFFFFFu, S1, from), rS2 = __shfl_sync(0xFFFFFFFFu, S2, from);
+        const u64 risum = __shfl_sync(0xFFFFFFFFu, isum, from);
+        const VT rmn = T::from_bits(__shfl_sync(0xFFFFFFFFu, T::to_bits(mn), from)), rmx = T::from_bits(__shfl_sync(0xFFFFFFFFu, T::to_bits(mx), from));
+        if (mine) {
+          acc[s].S1 += rS1; acc[s].S2 += rS2; acc[s].isum += risum;
+          if (ALL) { acc[s].mn = rmn < acc[s].mn ? rmn : acc[s].mn; acc[s].mx = rmx > acc[s].mx ? rmx : acc[s].mx; }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) mm &= mm - 1;
       }
     }
 #pragma unroll
@@ -724,30 +772,33 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
   if (!PART) flush();
 }
 
-template <int NT, typename VT, int FLAGS, int GPT>
-cudaError_t ts_launch4(const GbParams& p, int ctas, size_t smem, cudaStream_t s) {
+template <int NT, typename VT, int FLAGS, int GPT, bool TEAM>
+cudaError_t ts_launch5(const GbParams& p, int ctas, size_t smem, cudaStream_t s) {
   const bool generic = p.ts_generic != 0;
   const bool plain = !p.fbits && !p.compat_nulls && (generic || !p.ks.c[0].nulls);
-  auto k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true>;
-  if (p.part_keys) k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 2, true>;
+  auto k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true, TEAM>;
+  if (p.part_keys) k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 2, true, TEAM>;
   else if (generic) {
     bool pack32 = p.ks.nkeys <= 2;
     for (int i = 0; i < p.ks.nkeys; i++) pack32 = pack32 && !p.ks.c[i].nulls && (p.ks.c[i].dtype == PDRS_I32 || p.ks.c[i].dtype == PDRS_DICT_U32);
-    if (pack32) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, false>;
-    else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, false>;
+    if (pack32) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, true, TEAM> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, false, TEAM>;
+    else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, true, TEAM> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, false, TEAM>;
   }
-  else if (p.sh_dense) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, false>;
-  else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, true> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, false>;
+  else if (p.sh_dense) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, true, TEAM> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 0, false, TEAM>;
+  else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, true, TEAM> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 1, false, TEAM>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<ctas, NT, smem, s>>>(p);
   return cudaGetLastError();
 }
+// team: the variant with the team-of-8 reduce for segments of ts_mid .. ts_heavy rows (few hundred groups or fewer, skew);
+// with ~1000 uniform groups no segment is that long and the leaner variant is ~2% faster
 template <typename VT, int FLAGS>
 cudaError_t ts_launch2(const GbParams& p, int nt, int gpt, int ctas, size_t smem, cudaStream_t s) {
-  if (nt == 1024) return gpt == 1 ? ts_launch4<1024, VT, FLAGS, 1>(p, ctas, smem, s) : ts_launch4<1024, VT, FLAGS, 2>(p, ctas, smem, s);
-  if (nt == 256) return ts_launch4<256, VT, FLAGS, 4>(p, ctas, smem, s);
-  return gpt == 2 ? ts_launch4<512, VT, FLAGS, 2>(p, ctas, smem, s) : ts_launch4<512, VT, FLAGS, 4>(p, ctas, smem, s);
+  const bool team = p.ts_team != 0;
+  (void)nt;
+  if (gpt == 2) return team ? ts_launch5<512, VT, FLAGS, 2, true>(p, ctas, smem, s) : ts_launch5<512, VT, FLAGS, 2, false>(p, ctas, smem, s);
+  return team ? ts_launch5<512, VT, FLAGS, 4, true>(p, ctas, smem, s) : ts_launch5<512, VT, FLAGS, 4, false>(p, ctas, smem, s);
 }
 
 }  // namespace
@@ -757,8 +808,8 @@ cudaError_t ts_launch2(const GbParams& p, int nt, int gpt, int ctas, size_t smem
 // when shared memory allows (load factor <= 1/4), else >= 2.
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem) {
   if (cap + 1 > 2048) return false;
-  int t = nt_pref == 1024 ? 1024 : 512;
-  if (nt_pref == 256 && cap + 1 <= 1024) t = 256;          // two CTAs per SM, 4096-row tiles
+  (void)nt_pref;                                          // 1024 x 1 group and 2 x 256 threads with 4096-row tiles were measured: no faster
+  const int t = 512;
   const int g = cap + 1 <= 1024 ? 1024 / t : 2048 / t;
   const size_t np = (size_t)t * g;
   const size_t tile = t == 256 ? 4096 : TS_T;

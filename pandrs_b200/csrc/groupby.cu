@@ -499,8 +499,10 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
         if (use_ts) {
           gp.sh_cap = (int)ts_cap; gp.sh_slots = ts_slots; gp.sh_log_slots = ts_slots ? ilog2(ts_slots) : 0;
           gp.sh_dense = ts_dense ? 1 : 0; gp.sh_dense_base = dense_base;
-          gp.ts_heavy = c->opt_tsort_heavy > 0 ? (int)c->opt_tsort_heavy : 128;
+          gp.ts_heavy = c->opt_tsort_heavy > 0 ? (int)c->opt_tsort_heavy : 256;
           gp.ts_generic = ts_generic ? 1 : 0;
+          gp.ts_mid = c->opt_tsort_mid > 0 ? (int)c->opt_tsort_mid : 48;
+          gp.ts_team = (est < 500 || c->opt_tsort_team == 1) && c->opt_tsort_team != 2;   // long segments are expected (skewed keys spill over to the whole-warp reduce at ts_heavy)
           const long long trows = gb_tsort_tile_rows_for(ts_nt), tiles = (n + trows - 1) / trows;
           PDRS_CUDA(c, gb_tsort_launch(gp, passes[i].is_int, passes[i].flags, ts_nt, ts_gpt, (int)std::min<long long>((long long)c->sm_count * (ts_nt == 256 ? 2 : 1), tiles), ts_smem, c->stream));
           c->stats.groupby_algo_used = PDRS_GB_TILESORT;

@@ -86,6 +86,8 @@ struct GbParams {
   const u64* part_keys; const u64* part_vals; const uint8_t* part_flags /* 1 = value is NULL; may be NULL */; const u64* part_cnt; long long part_cap; int part_bits;
   int part_cpp, part_chunk_tiles;   // work items: every partition is cut into part_cpp chunks of part_chunk_tiles tiles (one flush per chunk)
   int ts_heavy;                     // tile-sort kernel: segments longer than this are reduced by the whole warp
+  int ts_team;                      // tile-sort kernel: use the variant with the team-of-8 reduce
+  int ts_mid;                       // ... longer than this (and up to ts_heavy) by a team of 8 lanes, shorter ones by their owner thread
   int ts_generic;                   // tile-sort kernel: keys are generic tuples packed into one word (not one Int64 column)
 };
 
