@@ -488,22 +488,36 @@ __global__ void __launch_bounds__(NT, TsGeom<NT>::CTAS) gb_tsort_kernel(const Gb
           }
         }
       }
+      // new keys (every row of the first tile of a partition): each lane inserts the key of its FIRST unresolved row
+      // through the warp-synchronous routine, then probes its other unresolved rows again without locks - after one
+      // round most keys of the tile are in the table, so a cold tile costs 2-3 rounds, not one insertion per row
       uint32_t spillmask = 0;
-      if (__any_sync(0xFFFFFFFFu, slowmask != 0)) {
-#pragma unroll 1
+      while (__any_sync(0xFFFFFFFFu, slowmask != 0)) {
+        const int j = slowmask ? __ffs(slowmask) - 1 : -1;
+        u64 kq = 0;
+#pragma unroll
+        for (int qq = 0; qq < RPT; qq++) if (qq == j) kq = r.k[qq];
+        const int id = ts_insert(ktab_key, ktab_id, misc, S, cap, kq, (ts_hash32(kq) << slot_lsh) >> slot_rsh, j >= 0);
+        if (j >= 0) {
+          if (id >= 0) {
+            idkey[id] = kq;            // benign duplicate stores of the same value
+#pragma unroll
+            for (int qq = 0; qq < RPT; qq++) if (qq == j) ids[qq] = (uint32_t)id;
+          } else spillmask |= 1u << j;
+          slowmask &= ~(1u << j);
+        }
+        __syncwarp();
+#pragma unroll
         for (int q = 0; q < RPT; q++) {
-          if (!__any_sync(0xFFFFFFFFu, (slowmask >> q) & 1u)) continue;
-          u64 kq = 0;
-#pragma unroll
-          for (int qq = 0; qq < RPT; qq++) if (qq == q) kq = r.k[qq];
-          const bool need = (slowmask >> q) & 1u;
-          const int id = ts_insert(ktab_key, ktab_id, misc, S, cap, kq, (ts_hash32(kq) << slot_lsh) >> slot_rsh, need);
-          if (need) {
-            if (id >= 0) {
-              idkey[id] = kq;            // benign duplicate stores of the same value
-#pragma unroll
-              for (int qq = 0; qq < RPT; qq++) if (qq == q) ids[qq] = (uint32_t)id;
-            } else spillmask |= 1u << q;
+          if (!((slowmask >> q) & 1u)) continue;
+          uint32_t slot = (ts_hash32(r.k[q]) << slot_lsh) >> slot_rsh;
+#pragma unroll 1
+          for (int pr = 0; pr < 4; pr++) {
+            const uint32_t idw = *reinterpret_cast<volatile uint32_t*>(&ktab_id[slot]);
+            const u64 kk = *reinterpret_cast<volatile u64*>(&ktab_key[slot]);
+            if (idw == 0 || idw == SH_BUSY) break;                       // not there (yet): stays for the next round
+            if (kk == r.k[q]) { ids[q] = idw - 1; slowmask &= ~(1u << q); break; }
+            slot = (slot + 1) & (uint32_t)(S - 1);
           }
         }
       }
