@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--dist-join", action="store_true", help="also time the sharded inner join (fused partition + NVLink shuffle), rows/GPU = --rows x --rows/10")
     return ap.parse_args()
 
 
@@ -278,6 +279,12 @@ def main():
     if not args.no_extras and world == 1:
         out["extras"] = extras(ctx, pb, args, n, keys, vals, peak)
 
+    if args.dist_join:
+        try:
+            out["dist_join"] = dist_join(ctx, pb, dist, rank, world, n, peaks)
+        except Exception as e:  # noqa: BLE001
+            out["dist_join"] = {"error": str(e)[:300]}
+
     # ---- the reference's CPU algorithm on this box's host cores, bounded sample
     if rank == 0 and not args.no_cpu:
         import oracle as orc
@@ -294,8 +301,70 @@ def main():
         dist.destroy_process_group()
 
 
+class _OneRank:
+    """torch.distributed stand-in for --dist-join on one GPU (every collective is a copy)."""
+    class ReduceOp:
+        MIN = MAX = None
+    @staticmethod
+    def get_world_size(): return 1
+    @staticmethod
+    def get_rank(): return 0
+    @staticmethod
+    def all_gather(outs, t): outs[0].copy_(t)
+    @staticmethod
+    def all_reduce(t, op=None): return None
+    @staticmethod
+    def barrier(): return None
+
+
+def dist_join(ctx, pb, dist, rank, world, n_probe, peaks):
+    """BASELINE.json configs[2] sharded over the ranks (weak scaling: n_probe probe rows and n_probe / 10 unique build
+    rows per GPU, keys drawn over the GLOBAL domain so ~(world-1)/world of all rows change GPU): the one-pass radix
+    partition stores its bucket runs straight into the destination GPU's receive area through NVLink
+    (pdrs_xjoin_shuffle), one barrier, local build / probe (pdrs_xjoin_local).  Times are CUDA events of the two
+    phases, max over ranks; the NVLink figure counts the 12-byte (key, row) records that leave each GPU."""
+    import torch
+    from pandrs_b200.dist import DistJoin
+    d = dist if dist is not None else _OneRank
+    nb_, np_ = n_probe // 10, n_probe
+    build = ctx.synth_join_keys(nb_, unique=True, row0=rank * nb_)
+    probe = ctx.synth_join_keys(np_, domain=2 * nb_ * world, row0=rank * np_)
+    dj = DistJoin(ctx, d)
+    if not dj.setup_fused(np_, nb_, nb_ * world):
+        return {"error": "fused setup failed: " + getattr(dj, "fused_error", "?")[:200]}
+    best = None
+    pairs = 0
+    for rep in range(3):
+        tm = {}
+        t0 = time.perf_counter()
+        j = dj.join_pairs_fused(probe, build, pb.INNER, rank * np_, rank * nb_, timings=tm)
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        if j is None:
+            return {"error": "sub-bucket overflow: " + getattr(dj, "fused_error", "?")[:200]}
+        pairs = j.n
+        j.close()
+        t = torch.tensor([tm["shuffle_ms"], tm["local_ms"], wall], device="cuda", dtype=torch.float64)
+        tot = torch.tensor([float(pairs)], device="cuda", dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        sh, lo, wl = (float(v) for v in t.tolist())
+        if rep and (best is None or sh + lo < best[0] + best[1]):
+            best = (sh, lo, wl, float(tot.item()))
+    dj.x.close()
+    sh, lo, wl, total_pairs = best
+    sent = (np_ + nb_) * 12.0 * (world - 1) / world          # bytes leaving each GPU
+    nvl_peak = float(peaks.get("nvlink_gbs", 770.0))
+    return {"rows_per_s": (np_ + nb_) * world / ((sh + lo) * 1e-3), "shuffle_ms": sh, "local_ms": lo, "wall_ms": wl, "pairs": total_pairs,
+            "rows_per_gpu": np_ + nb_, "nvlink_bytes_per_gpu": sent, "nvlink_gbs_achieved": sent / (sh * 1e-3) / 1e9 if world > 1 else None,
+            "nvlink_peak_gbs": nvl_peak, "nvlink_frac": sent / (sh * 1e-3) / 1e9 / nvl_peak if world > 1 else None,
+            "note": "weak scaling; shuffle_ms = fused partition + peer stores of both sides; local_ms = table memset + build + probe/emit"}
+
+
 def extras(ctx, pb, args, n, keys, vals, peak):
-    """Sum-only groupby, the 10M-group groupby and the inner / left join of BASELINE.json configs[1..2]."""
+    """Sum-only groupby, the 10M-group groupby, the inner / left join (pairs, and with 2 payload columns) of BASELINE.json
+    configs[1..2], then configs[3..4] (extras_c4_c5)."""
     ex = {}
 
     def timed(fn, reps=3):
@@ -335,8 +404,124 @@ def extras(ctx, pb, args, n, keys, vals, peak):
             ms, kms = timed(jn, reps=2)
             alg = 8 * (np_ + nb_) + 16 * m[0]      # index-pairs variant of SURVEY.md §8(d)
             ex[name] = {"rows_per_s": (np_ + nb_) / (ms * 1e-3), "ms": ms, "probe_kernel_ms": kms, "pairs": m[0], "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak}
+        # configs[2] with its 2 build-side payload columns (i64, f64) gathered into the result (join.rs:290-552)
+        p1, p2 = ctx.synth_keys(nb_, card=1 << 40, seed=9), ctx.synth_vals(nb_, seed=9)
+        o1, o2 = ctx.dev_alloc(np_ * 8), ctx.dev_alloc(np_ * 8)
+        m = [0]
+
+        def jn_payload():
+            j = ctx.join_pairs(probe, build, pb.INNER)
+            m[0] = j.n
+            ctx.gather(p1, j.right_dev(), n=j.n, idx_dev=True, out_dev=o1)
+            ctx.gather(p2, j.right_dev(), n=j.n, idx_dev=True, out_dev=o2)
+            j.close()
+        ms, _ = timed(jn_payload, reps=2)
+        alg = 8 * np_ + nb_ * (8 + 16) + m[0] * (16 + 16)      # SURVEY.md §8(d), P = 2 payload columns
+        ex["join_inner_2payload"] = {"rows_per_s": (np_ + nb_) / (ms * 1e-3), "ms": ms, "pairs": m[0], "alg_bytes": alg, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak}
+        ctx.dev_free(o1); ctx.dev_free(o2)
+        del p1, p2, build, probe
     except Exception as e:  # noqa: BLE001
         ex["join"] = {"error": str(e)[:200]}
+    try:
+        ex.update(extras_c4_c5(ctx, pb, peak, timed))
+    except Exception as e:  # noqa: BLE001
+        ex["c4_c5"] = {"error": str(e)[:200]}
+    return ex
+
+
+def extras_c4_c5(ctx, pb, peak, timed):
+    """BASELINE.json configs[3] (multi-key + dictionary key, 500M rows, Zipf 1.1) and one GPU's shard of configs[4]
+    (Q1-style filter -> groupby(returnflag, linestatus), 7.5e8 rows).  Columns are generated with torch on the device
+    (same stream as the context) and handed over as borrowed device pointers."""
+    import torch
+    dev = torch.device("cuda", ctx.device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)
+    CH = 1 << 26
+
+    def zipf(n, domain, dtype, s=1.1):
+        w = torch.arange(1, domain + 1, device=dev, dtype=torch.float64).pow(-s)
+        cdf = (w.cumsum(0) / w.sum()).to(torch.float32)
+        out = torch.empty(n, dtype=dtype, device=dev)
+        for a in range(0, n, CH):
+            b = min(n, a + CH)
+            out[a:b] = torch.searchsorted(cdf, torch.rand(b - a, device=dev, generator=g)).clamp_(max=domain - 1).to(dtype)
+        return out
+
+    def uniform(n, lo, hi):
+        out = torch.empty(n, dtype=torch.float64, device=dev)
+        for a in range(0, n, CH):
+            b = min(n, a + CH)
+            out[a:b] = torch.rand(b - a, device=dev, generator=g, dtype=torch.float64) * (hi - lo) + lo
+        return out
+
+    def bits(n, p_true):
+        nbytes = (n + 63) // 64 * 8
+        out = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        wts = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.int32, device=dev)
+        for a in range(0, n, CH):
+            b = min(n, a + CH)
+            f = torch.zeros((b - a + 7) // 8 * 8, dtype=torch.int32, device=dev)
+            f[: b - a] = (torch.rand(b - a, device=dev, generator=g) < p_true).to(torch.int32)
+            out[a // 8: a // 8 + f.numel() // 8] = (f.view(-1, 8) * wts).sum(1).to(torch.uint8)
+        return out
+
+    def col(dtype, t, n=None):
+        return pb.Column(dtype, device_ptr=t.data_ptr(), length=int(n if n is not None else t.numel()), owner=t)
+
+    ALL6 = (pb.SUM, pb.MEAN, pb.MIN, pb.MAX, pb.COUNT, pb.STD)
+    ex = {}
+
+    def run(name, keys, vals, aggs, alg_bytes, n, filt=None, reps=2):
+        ng = [0]
+
+        def f():
+            r = ctx.groupby_agg(keys, vals, aggs, filter=filt)
+            ng[0] = r.n_groups
+            r.close()
+        try:
+            ms, _ = timed(f, reps=reps)
+            ex[name] = {"rows_per_s": n / (ms * 1e-3), "ms": ms, "groups": ng[0], "alg_bytes_per_row": alg_bytes / n,
+                        "roofline_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "algo": ctx.stats()["groupby_algo_used"]}
+        except Exception as e:  # noqa: BLE001
+            ex[name] = {"error": str(e)[:200]}
+
+    # ---- configs[3]
+    n = 500_000_000
+    k1 = zipf(n, 1000, torch.int32)
+    k2 = zipf(n, 100_000, torch.int64)
+    k3 = zipf(n, 10_000, torch.int32)           # dictionary ids over a 10,000-string pool (u32, same bits)
+    v = uniform(n, 0.0, 1000.0)
+    torch.cuda.current_stream(dev).synchronize()
+    aggs6 = [(0, op) for op in ALL6]
+    run("c4_dict_key_zipf", [col(pb.DICT_U32, k3)], [col(pb.F64, v)], aggs6, n * 12.0, n)
+    run("c4_i32_i64_keys_zipf", [col(pb.I32, k1), col(pb.I64, k2)], [col(pb.F64, v)], aggs6, n * 20.0, n)
+    run("c4_i32_i64_dict_keys_zipf", [col(pb.I32, k1), col(pb.I64, k2), col(pb.DICT_U32, k3)], [col(pb.F64, v)], aggs6, n * 24.0, n)
+    del k1, k2, k3, v
+    torch.cuda.empty_cache()
+
+    # ---- configs[4], one GPU's shard: 6e9 / 8 rows
+    n = 750_000_000
+    rf = torch.empty(n, dtype=torch.int32, device=dev)
+    ls = torch.empty(n, dtype=torch.int32, device=dev)
+    for a in range(0, n, CH):
+        b = min(n, a + CH)
+        rf[a:b] = torch.randint(0, 3, (b - a,), device=dev, generator=g, dtype=torch.int32)
+        ls[a:b] = torch.randint(0, 2, (b - a,), device=dev, generator=g, dtype=torch.int32)
+    qty, price, disc, tax = uniform(n, 1, 50), uniform(n, 900, 105000), uniform(n, 0, 0.1), uniform(n, 0, 0.08)
+    disc_price = torch.empty_like(price)
+    charge = torch.empty_like(price)
+    for a in range(0, n, CH):
+        b = min(n, a + CH)
+        disc_price[a:b] = price[a:b] * (1 - disc[a:b])
+        charge[a:b] = disc_price[a:b] * (1 + tax[a:b])
+    del tax
+    mask = bits(n, 0.98)                         # shipdate <= cutoff as a precomputed Boolean column (data_ops.rs:37-62)
+    torch.cuda.current_stream(dev).synchronize()
+    vals = [col(pb.F64, t) for t in (qty, price, disc_price, charge, disc)]
+    aggs = [(0, pb.SUM), (1, pb.SUM), (2, pb.SUM), (3, pb.SUM), (0, pb.MEAN), (1, pb.MEAN), (4, pb.MEAN), (0, pb.COUNT)]
+    run("c5_q1_shard_filter_groupby", [col(pb.DICT_U32, rf), col(pb.DICT_U32, ls)], vals, aggs, n * (8 + 5 * 8 + 0.125), n,
+        filt=col(pb.BOOL_BITS, mask, n))
     return ex
 
 

@@ -195,6 +195,33 @@ const int64_t* pdrs_join_left_dev(const pdrs_join_result* r);
 const int64_t* pdrs_join_right_dev(const pdrs_join_result* r);
 void pdrs_join_result_free(pdrs_join_result* r);
 
+/* ---- multi-GPU join: fused radix partition + shuffle over NVLink peer memory ----
+ * No reference counterpart (pandrs has no comms backend; PartitionStrategy::Hash is only an enum,
+ * src/distributed/core/partition.rs:11-18).  Semantics = join_impl (join.rs:107-208) applied to the union of the ranks'
+ * rows, Inner / Left; rank r returns the pairs of the keys whose rank hash maps to r, in GLOBAL row numbers.
+ * One pdrs_xjoin per rank (process / GPU).  Protocol, identical on every rank:
+ *   create(rank, world, max rows per rank of each side, total right rows)    same arguments => same layout everywhere
+ *   ipc_handle -> all_gather of the 64-byte handles (torch.distributed / MPI) -> attach_ipc       [once]
+ *   shuffle(left_key, right_key, right_row0)   the one-pass partition kernel stores every (key, row) run straight into the
+ *                                              destination rank's receive area (CUDA IPC mapping, NVLink stores)
+ *   <barrier over all ranks>
+ *   local(how, left_row0[world]) -> pdrs_join_result   build / probe of the received sub-buckets
+ *   <barrier before the next shuffle>
+ * world must be 1, 2, 4 or 8 (one NVSwitch domain).  attach_ptrs replaces the IPC exchange when all ranks live in
+ * one process.  PDRS_ERR_UNSUPPORTED from shuffle = a padded sub-bucket overflowed (skewed keys): fall back to
+ * pdrs_hash_partition + all_to_all + pdrs_join_pairs. */
+typedef struct pdrs_xjoin pdrs_xjoin;
+int32_t pdrs_xjoin_create(pdrs_ctx* ctx, int32_t rank, int32_t world, int64_t max_left_rows, int64_t max_right_rows,
+                          int64_t total_right_rows, pdrs_xjoin** out);
+int64_t pdrs_xjoin_bytes(const pdrs_xjoin* x);                       /* size of the receive area */
+void* pdrs_xjoin_base(const pdrs_xjoin* x);                          /* device pointer of the receive area */
+int32_t pdrs_xjoin_ipc_handle(pdrs_xjoin* x, uint8_t* handle64);     /* cudaIpcMemHandle_t of the receive area */
+int32_t pdrs_xjoin_attach_ipc(pdrs_xjoin* x, const uint8_t* handles /* world x 64 bytes */);
+int32_t pdrs_xjoin_attach_ptrs(pdrs_xjoin* x, void* const* bases /* world */);
+int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_col* right_key, int64_t right_row0);
+int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0 /* world */, pdrs_join_result** out);
+void pdrs_xjoin_destroy(pdrs_xjoin* x);
+
 /* Replaces the materialisation loops of join_impl (join.rs:290-552) and filter_by_indices
  * (data_ops.rs:124-211): out[j] = idx[j] < 0 || col[idx[j]] is NULL ? type default : col[idx[j]];
  * the output carries no null mask.  DICT_U32 default is 0xFFFFFFFF (the empty string ""), BOOL_BITS

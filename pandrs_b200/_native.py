@@ -80,6 +80,15 @@ SIGNATURES = {
     "pdrs_join_left_dev": (_vp, [_vp]),
     "pdrs_join_right_dev": (_vp, [_vp]),
     "pdrs_join_result_free": (None, [_vp]),
+    "pdrs_xjoin_create": (_i32, [_vp, _i32, _i32, _i64, _i64, _i64, _P(_vp)]),
+    "pdrs_xjoin_bytes": (_i64, [_vp]),
+    "pdrs_xjoin_base": (_vp, [_vp]),
+    "pdrs_xjoin_ipc_handle": (_i32, [_vp, _vp]),
+    "pdrs_xjoin_attach_ipc": (_i32, [_vp, _vp]),
+    "pdrs_xjoin_attach_ptrs": (_i32, [_vp, _P(_vp)]),
+    "pdrs_xjoin_shuffle": (_i32, [_vp, _P(PdrsCol), _P(PdrsCol), _i64]),
+    "pdrs_xjoin_local": (_i32, [_vp, _i32, _P(_i64), _P(_vp)]),
+    "pdrs_xjoin_destroy": (None, [_vp]),
     "pdrs_gather": (_i32, [_vp, _P(PdrsCol), _vp, _i32, _i64, _vp, _i32]),
     "pdrs_filter_indices": (_i32, [_vp, _P(PdrsCol), _vp, _P(_i64)]),
     "pdrs_synth_keys": (_i32, [_vp, _vp, _i64, _i64, _u64, _u64, _i32]),

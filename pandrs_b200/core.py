@@ -169,6 +169,55 @@ class JoinResult:
             pass
 
 
+class XJoin:
+    """pdrs_xjoin: this rank's end of the fused partition + shuffle join (include/pandrs_b200.h)."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, max_left_rows: int, max_right_rows: int, total_right_rows: int):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        h = C.c_void_p()
+        ctx._chk(ctx.L.pdrs_xjoin_create(ctx._h, rank, world, int(max_left_rows), int(max_right_rows), int(total_right_rows), C.byref(h)))
+        self._h = h
+        self.bytes = int(ctx.L.pdrs_xjoin_bytes(h))
+        self.base = ctx.L.pdrs_xjoin_base(h)
+
+    def ipc_handle(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self.ctx._chk(self.ctx.L.pdrs_xjoin_ipc_handle(self._h, buf))
+        return bytes(buf)
+
+    def attach_ipc(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.world
+        buf = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        self.ctx._chk(self.ctx.L.pdrs_xjoin_attach_ipc(self._h, buf))
+
+    def attach_ptrs(self, bases: Sequence[int]):
+        arr = (C.c_void_p * self.world)(*bases)
+        self.ctx._chk(self.ctx.L.pdrs_xjoin_attach_ptrs(self._h, arr))
+
+    def shuffle(self, left: Column, right: Column, right_row0: int):
+        lc, rc = left.c(), right.c()
+        self.ctx._chk(self.ctx.L.pdrs_xjoin_shuffle(self._h, C.byref(lc), C.byref(rc), int(right_row0)))
+
+    def local(self, how: int, left_row0: Sequence[int]) -> JoinResult:
+        arr = (C.c_int64 * self.world)(*[int(v) for v in left_row0])
+        h = C.c_void_p()
+        self.ctx._chk(self.ctx.L.pdrs_xjoin_local(self._h, how, arr, C.byref(h)))
+        return JoinResult(self.ctx, h)
+
+    def close(self):
+        if self._h:
+            self.ctx.L.pdrs_xjoin_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """pdrs_ctx: one device + one stream, not re-entrant (include/pandrs_b200.h)."""
 

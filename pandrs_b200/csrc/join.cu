@@ -20,8 +20,10 @@
 //   join_write_kernel   per-CTA base offsets from the scan of those counts, block-level exclusive
 //                       scans inside each CTA's contiguous row range, ordered writes of the pairs
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <vector>
 
 #include "common.cuh"
@@ -84,7 +86,13 @@ __device__ __forceinline__ u64 ld_volatile_u64(const void* p) {
 // (canonical 64-bit keys + original row ids, NULL keys already dropped).
 // Partitioned layouts: flat (bucket after bucket, cap == 0) or padded (bucket b owns positions [b * cap, b * cap + cnt[b]),
 // cap a multiple of every tile size, so that a tile never straddles two buckets).
-struct JSrc { JKeyCol col; const u64* pkeys; const uint32_t* prows; long long cap; const u64* cnt; int log_nb; };
+// Multi-GPU exchange path (pdrs_xjoin_*): a bucket is split into 2^log_srcs sub-buckets, one per source rank
+// (sub-bucket = bucket << log_srcs | source), cap / cnt describe sub-buckets, prows are row numbers LOCAL to the
+// source rank and row0[source] turns them into global row numbers when pairs are emitted.
+struct JSrc { JKeyCol col; const u64* pkeys; const uint32_t* prows; long long cap; const u64* cnt; int log_nb; const long long* row0; int log_srcs; };
+__device__ __forceinline__ long long jsrc_row_add(const JSrc& s, long long pos) {
+  return s.row0 ? __ldg(s.row0 + ((pos / s.cap) & ((1ll << s.log_srcs) - 1))) : 0ll;
+}
 // end of the valid positions of the tile [lo, lo + tile)
 __device__ __forceinline__ long long jsrc_tile_hi(const JSrc& s, long long lo, long long tile, long long n) {
   if (s.cap == 0) return min(n, lo + tile);
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long lon
       for (int j = 0; j < JOIN_ITEMS; j++) {
         long long i = c0 + (long long)threadIdx.x * JOIN_ITEMS + j;
         if (cn[j] == 0) continue;
-        if (prows) i = (long long)__ldg(prows + i);      // partitioned probe side: position -> original left row
+        if (prows) i = (long long)__ldg(prows + i) + jsrc_row_add(src, i);      // partitioned probe side: position -> original left row
         if (st[j] == J_NOMATCH) { out_l[pos] = i; out_r[pos] = -1; pos++; }
         else if (!(st[j] & J_MULTI)) { out_l[pos] = i; out_r[pos] = st[j]; pos++; }
         else {
@@ -365,7 +373,15 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long lon
 #define JP_TILE (JP_THREADS * JP_ITEMS)
 #define JP_MAX_BUCKETS 1024
 
-__device__ __forceinline__ uint32_t jbucket(u64 key, int log_nb) { return jhash32(key) >> (32 - log_nb); }
+__device__ __forceinline__ uint32_t jbucket(u64 key, int log_nb) { return log_nb ? jhash32(key) >> (32 - log_nb) : 0u; }
+// Destination rank of a key on the multi-GPU exchange path: a second, independent multiplicative hash, so that the
+// rows a rank receives still spread over the whole range of jhash32 (= over all of its radix buckets and table slots).
+__device__ __forceinline__ uint32_t jhash_rank(u64 k) { return (uint32_t)(((k ^ (k >> 29)) * 0xD6E8FEB86659FD93ull) >> 32); }
+// Where the one-pass partition writes: one (keys, rows) buffer per destination rank.  Single GPU: world = 1, the
+// buffers are local.  Exchange path: keys[r] / rows[r] are rank r's receive buffers mapped into this process (CUDA
+// IPC), so the partition pass IS the shuffle - every bucket run is stored straight through NVLink; combined bucket
+// = rank << log_nb | radix bucket; inside rank r's buffers this rank `me` owns sub-bucket (bucket << log_world | me).
+struct JXDst { u64* keys[8]; uint32_t* rows[8]; int log_world; int me; uint32_t row_add; };
 
 __global__ void __launch_bounds__(JP_THREADS) jpart_hist_kernel(JKeyCol col, long long n, int log_nb, u64* __restrict__ hist) {
   __shared__ uint32_t sh[JP_MAX_BUCKETS];
@@ -458,14 +474,21 @@ __global__ void __launch_bounds__(JP_THREADS, 4) jpart_scatter_kernel(JKeyCol co
 #define JQ_NT 512
 #define JQ_ITEMS 8
 #define JQ_TILE (JQ_NT * JQ_ITEMS)
+#define JQ_SMEM ((size_t)JQ_TILE * 16 + 1056 * 4 + 1024 * 8 + JQ_TILE)
+template <bool XCHG>
 __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long n, int log_nb, long long cap, u64* __restrict__ cursor,
-                                                          u64* __restrict__ out_keys, uint32_t* __restrict__ out_rows, u64* __restrict__ overflow) {
+                                                          const JXDst x, u64* __restrict__ overflow) {
+  u64* __restrict__ out_keys = x.keys[0];
+  uint32_t* __restrict__ out_rows = x.rows[0];
   extern __shared__ __align__(16) unsigned char jsm[];
   u64* st_key = reinterpret_cast<u64*>(jsm);                                 // [JQ_TILE] staged keys
   uint32_t* st_row = reinterpret_cast<uint32_t*>(st_key + JQ_TILE);         // [JQ_TILE] staged row ids
   uint32_t* st_dst = st_row + JQ_TILE;                                      // [JQ_TILE] output position of the staged row
   uint32_t* H = st_dst + JQ_TILE;                                           // [1024 + 32] bucket counts of the tile
   uint2* HD = reinterpret_cast<uint2*>(H + 1056);                           // [1024] {offset in the staging area, output position of the first row}
+  uint8_t* st_rk = reinterpret_cast<uint8_t*>(HD + 1024);                   // [JQ_TILE] destination rank of the staged row (exchange path)
+  const int lw = XCHG ? x.log_world : 0;
+  const uint32_t nbmask = (1u << log_nb) - 1u;
   __shared__ uint32_t wsum[JQ_NT / 32];
   __shared__ uint32_t sh_total;
   const int nb = 1 << log_nb;
@@ -490,9 +513,15 @@ __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long
       br[j] = 0xFFFFFFFFu;
       bool live = i < n;
       if (!fast) live = live && jload_key(col, i, &key[j]);
-      if (live) { const uint32_t b = jbucket(key[j], log_nb); br[j] = (b << 16) | atomicAdd(&H[b], 1u); }
+      if (live) {
+        uint32_t b = jbucket(key[j], log_nb);
+        if (XCHG && lw) b |= (jhash_rank(key[j]) >> (32 - lw)) << log_nb;
+        br[j] = (b << 16) | atomicAdd(&H[b], 1u);
+      }
     }
     __syncthreads();
+    // first output position of combined bucket cb (see JXDst); single GPU: cb * cap
+    auto obase = [&](uint32_t cb) -> u64 { return XCHG ? (u64)((((cb & nbmask) << lw) | (uint32_t)x.me)) * (u64)cap : (u64)cb * (u64)cap; };
     {   // exclusive scan of the bucket counts (thread t owns buckets 2t, 2t + 1) + one global reservation per bucket
       const uint32_t c0 = H[2 * tid], c1 = H[2 * tid + 1], c = c0 + c1;
       uint32_t incl = c;
@@ -500,8 +529,8 @@ __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
       if (lane == 31) wsum[warp] = incl;
       uint32_t g0 = 0xFFFFFFFFu, g1 = 0xFFFFFFFFu;
-      if (c0) { const u64 at = atomicAdd(&cursor[2 * tid], (u64)c0); if (at + c0 > (u64)cap) atomicAdd(overflow, 1ull); else g0 = (uint32_t)((u64)(2 * tid) * (u64)cap + at); }
-      if (c1) { const u64 at = atomicAdd(&cursor[2 * tid + 1], (u64)c1); if (at + c1 > (u64)cap) atomicAdd(overflow, 1ull); else g1 = (uint32_t)((u64)(2 * tid + 1) * (u64)cap + at); }
+      if (c0) { const u64 at = atomicAdd(&cursor[2 * tid], (u64)c0); if (at + c0 > (u64)cap) atomicAdd(overflow, 1ull); else g0 = (uint32_t)(obase(2 * tid) + at); }
+      if (c1) { const u64 at = atomicAdd(&cursor[2 * tid + 1], (u64)c1); if (at + c1 > (u64)cap) atomicAdd(overflow, 1ull); else g1 = (uint32_t)(obase(2 * tid + 1) + at); }
       __syncthreads();
       uint32_t ws = lane < JQ_NT / 32 ? wsum[lane] : 0u;
 #pragma unroll
@@ -521,6 +550,7 @@ __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long
       st_key[pos] = key[j];
       st_row[pos] = (uint32_t)(t0 + (long long)j * JQ_NT + tid);
       st_dst[pos] = hd.y == 0xFFFFFFFFu ? 0xFFFFFFFFu : hd.y + rank;       // all ones: the bucket overflowed, the caller discards this partitioning
+      if (XCHG) st_rk[pos] = (uint8_t)(br[j] >> (16 + log_nb));
     }
     if (fast && t0 + tstride < n) load_tile(t0 + tstride);
     __syncthreads();
@@ -528,11 +558,28 @@ __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long
     for (uint32_t pos = tid; pos < total; pos += JQ_NT) {     // consecutive staged rows of a bucket go to consecutive output rows
       const uint32_t d = st_dst[pos];
       if (d == 0xFFFFFFFFu) continue;
-      out_keys[d] = st_key[pos];
-      out_rows[d] = st_row[pos];
+      if (XCHG) {     // consecutive staged rows of a combined bucket form one contiguous run in the destination rank's buffer (NVLink stores)
+        const int r = st_rk[pos];
+        x.keys[r][d] = st_key[pos];
+        x.rows[r][d] = st_row[pos] + x.row_add;
+      } else {
+        out_keys[d] = st_key[pos];
+        out_rows[d] = st_row[pos];
+      }
     }
     __syncthreads();
   }
+}
+
+// Exchange path: after the partition pass every rank tells its peers how many rows it stored into each of its
+// sub-buckets (cursor[cb] of this rank -> cnt[(bucket << log_world) | me] of rank cb >> log_nb).
+struct JXCnt { u64* cnt[8]; };
+__global__ void jx_publish_counts_kernel(const u64* __restrict__ cursor, const JXCnt dst, int log_nb, int log_world, int me, long long cap) {
+  const int cb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cb >= (1 << (log_nb + log_world))) return;
+  const int r = cb >> log_nb, b = cb & ((1 << log_nb) - 1);
+  const u64 c = cursor[cb];
+  dst.cnt[r][(b << log_world) | me] = c < (u64)cap ? c : (u64)cap;
 }
 
 // ---------------------------------------------------------------- single-pass probe + emit (unique build keys)
@@ -668,10 +715,11 @@ __global__ void __launch_bounds__(JE_THREADS, 3) join_probe_emit_kernel(JTab tab
       base = __shfl_sync(0xFFFFFFFFu, base, 0);
       long long* ol = out_l + base;
       long long* orr = out_r + base;
+      const long long radd = jsrc_row_add(src, lo);     // a unit never straddles two sub-buckets
 #pragma unroll
       for (int j = 0; j < JE_ITEMS; j++) {
         if (!((emit >> j) & 1u)) continue;
-        st_stream_u64(ol + woff[j], (long long)lrow[j], pol_stream);
+        st_stream_u64(ol + woff[j], (long long)lrow[j] + radd, pol_stream);
         st_stream_u64(orr + woff[j], res[j] == NONE ? -1ll : (long long)res[j], pol_stream);
       }
     }
@@ -758,11 +806,13 @@ static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log
   PDRS_TRY(out->rows.alloc(c, (size_t)nb * cap * 4));
   out->n = (long long)nb * cap;
   if ((unsigned long long)nb * (unsigned long long)cap >= (1ull << 32)) { *ok = false; return PDRS_OK; }   // 32-bit output positions
-  const size_t smem = (size_t)JQ_TILE * 16 + 1056 * 4 + 1024 * 8;
+  const size_t smem = JQ_SMEM;
   static bool attr_set = false;
-  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
   const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + JQ_TILE - 1) / JQ_TILE));
-  jpart1_kernel<<<ctas, JQ_NT, smem, c->stream>>>(col, n, log_nb, cap, counts->as<u64>(), out->keys.as<u64>(), out->rows.as<uint32_t>(), counts->as<u64>() + nb);
+  JXDst x{};
+  x.keys[0] = out->keys.as<u64>(); x.rows[0] = out->rows.as<uint32_t>();
+  jpart1_kernel<false><<<ctas, JQ_NT, smem, c->stream>>>(col, n, log_nb, cap, counts->as<u64>(), x, counts->as<u64>() + nb);
   c->stats.kernel_launches++;
   PDRS_CUDA(c, cudaGetLastError());
   PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, counts->as<u64>() + nb, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -777,74 +827,12 @@ struct pdrs_join_result {
   DevBuf left, right;
 };
 
-extern "C" {
-
-int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, pdrs_join_result** out) {
-  if (!c) return PDRS_ERR_BAD_ARG;
-  if (!left_key || !right_key || !out) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_pairs: NULL argument");
-  if (how < PDRS_INNER || how > PDRS_OUTER) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown join type %d", how);
-  const int32_t how_req = how;
-  how = (how == PDRS_RIGHT) ? PDRS_INNER : (how == PDRS_OUTER ? PDRS_LEFT : how);   // Right / Outer = Inner / Left + the unmatched right rows
-  if (left_key->dtype != right_key->dtype)   // join.rs:98-104
-    return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "join key columns have different types (%d vs %d)", left_key->dtype, right_key->dtype);
-  PDRS_CUDA(c, cudaSetDevice(c->device));
-  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-  c->stats.main_kernel_ms = 0; c->stats.total_ms = 0;
-  ColView lv, rv;
-  PDRS_TRY(pdrs_view_col(c, left_key, &lv));
-  PDRS_TRY(pdrs_view_col(c, right_key, &rv));
-  const int64_t nl = lv.len, nr = rv.len;
-  auto* res = new pdrs_join_result();
-  res->ctx = c;
-  struct Guard { pdrs_join_result* r; ~Guard() { delete r; } } guard{res};
-
-  const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;   // load factor <= 1/3: 4-slot buckets overflow for ~5% of the keys (see jslot)
-  if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
-  const size_t table_bytes = (size_t)(slots + 4) * 12;                  // u64 keys[slots + 4] + u32 heads[slots + 4]; slot `slots` is reserved for the all-ones key
-  // Large tables: radix-partition both sides so that one bucket's table region (<= 32 MB) stays in L2.
-  // join_algo: 0 auto, 1 = always the direct (left-row-major output) path, 2 = always partitioned.
-  int log_nb = 0;
-  while (log_nb < 10 && (table_bytes >> log_nb) > (40ull << 20)) log_nb++;      // measured: 25-50 MB regions are L2-resident, fewer buckets partition faster
-  if (c->opt_join_log_nb > 0) log_nb = (int)c->opt_join_log_nb;
-  bool radix = log_nb > 1 && nl < (1ll << 32) && nr < (1ll << 32);
-  if (c->opt_join_algo == 1) radix = false;
-  if (c->opt_join_algo == 2 && nl < (1ll << 32) && nr < (1ll << 32)) { radix = true; log_nb = std::max(log_nb, 2); }
-  std::vector<std::pair<const char*, cudaEvent_t>> marks;
-  auto mark = [&](const char* name) {
-    if (c->opt_timing < 2) return;
-    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); marks.push_back({name, e});
-  };
-  mark("start");
-  DevBuf tab, next, counts, fail;
-  PDRS_TRY(tab.alloc(c, table_bytes));
-  PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));   // key = all ones (EMPTY), head = -1 (EMPTY)
-  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
-  PDRS_TRY(next.alloc(c, (size_t)std::max<int64_t>(nr, 1) * 8));
-  PDRS_CUDA(c, cudaMemsetAsync(next.p, 0xFF, (size_t)std::max<int64_t>(nr, 1) * 8, c->stream));      // -1 = end of chain
-  PDRS_TRY(fail.alloc(c, 64, true));      // [0] failed inserts, [1] build tile counter, [2] probe tile counter (two-pass) / output cursor (single pass), [3] duplicate build keys, [4] probe tile counter (single pass)
-  c->stats.table_slots = slots;
-  JKeyCol rc{rv.data, rv.nulls, rv.dtype}, lc{lv.data, lv.nulls, lv.dtype};
-  JPart lp, rp;
-  DevBuf lcnt, rcnt;
-  JSrc rsrc{rc, nullptr, nullptr, 0, nullptr, 0}, lsrc{lc, nullptr, nullptr, 0, nullptr, 0};
-  long long nl_eff = nl, nr_eff = nr;
-  if (radix) {
-    mark("memset");
-    // one-pass partition into padded buckets; exact two-pass partition when a bucket overflows (skewed keys)
-    bool ok1 = c->opt_join_part != 2;
-    long long rcap = 0, lcap = 0;
-    if (ok1) PDRS_TRY(jpartition1(c, rc, nr, log_nb, &rp, &rcnt, &rcap, &ok1));
-    if (ok1) { rsrc.cap = rcap; rsrc.cnt = rcnt.as<u64>(); rsrc.log_nb = c->opt_join_prefetch ? log_nb : 0; }
-    else { rp = JPart(); PDRS_TRY(jpartition(c, rc, nr, log_nb, &rp)); }
-    mark("partition build side");
-    bool ok2 = c->opt_join_part != 2;
-    if (ok2) PDRS_TRY(jpartition1(c, lc, nl, log_nb, &lp, &lcnt, &lcap, &ok2));
-    if (ok2) { lsrc.cap = lcap; lsrc.cnt = lcnt.as<u64>(); lsrc.log_nb = c->opt_join_prefetch ? log_nb : 0; }
-    else { lp = JPart(); PDRS_TRY(jpartition(c, lc, nl, log_nb, &lp)); }
-    mark("partition probe side");
-    rsrc.pkeys = rp.keys.as<u64>(); rsrc.prows = rp.rows.as<uint32_t>(); nr_eff = rp.n;
-    lsrc.pkeys = lp.keys.as<u64>(); lsrc.prows = lp.rows.as<uint32_t>(); nl_eff = lp.n;
-  }
+// Build the table from `rsrc`, probe it with `lsrc` and materialise the pairs into `res` (left / right arrays).
+// nl_out = number of probe rows (capacity of the single-pass output); nl_eff / nr_eff = positions to scan (padded
+// partition layouts scan cap rows per bucket).
+static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& next, DevBuf& fail, const JSrc& rsrc, long long nr_eff, const JSrc& lsrc, long long nl_eff,
+                            int64_t nl, bool radix, int how, pdrs_join_result* res, int64_t* M_out, const std::function<void(const char*)>& mark) {
+  DevBuf counts;
   if (nr_eff > 0) {
     join_build_kernel<<<(int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (nr_eff + 255) / 256)), 256, 0, c->stream>>>(jt, next.as<long long>(), rsrc, nr_eff, fail.as<u64>());
     c->stats.kernel_launches++;
@@ -909,6 +897,81 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
     PDRS_CUDA(c, cudaGetLastError());
   }
   }
+  *M_out = M;
+  return PDRS_OK;
+}
+
+
+extern "C" {
+
+int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, pdrs_join_result** out) {
+  if (!c) return PDRS_ERR_BAD_ARG;
+  if (!left_key || !right_key || !out) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_pairs: NULL argument");
+  if (how < PDRS_INNER || how > PDRS_OUTER) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown join type %d", how);
+  const int32_t how_req = how;
+  how = (how == PDRS_RIGHT) ? PDRS_INNER : (how == PDRS_OUTER ? PDRS_LEFT : how);   // Right / Outer = Inner / Left + the unmatched right rows
+  if (left_key->dtype != right_key->dtype)   // join.rs:98-104
+    return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "join key columns have different types (%d vs %d)", left_key->dtype, right_key->dtype);
+  PDRS_CUDA(c, cudaSetDevice(c->device));
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+  c->stats.main_kernel_ms = 0; c->stats.total_ms = 0;
+  ColView lv, rv;
+  PDRS_TRY(pdrs_view_col(c, left_key, &lv));
+  PDRS_TRY(pdrs_view_col(c, right_key, &rv));
+  const int64_t nl = lv.len, nr = rv.len;
+  auto* res = new pdrs_join_result();
+  res->ctx = c;
+  struct Guard { pdrs_join_result* r; ~Guard() { delete r; } } guard{res};
+
+  const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;   // load factor <= 1/3: 4-slot buckets overflow for ~5% of the keys (see jslot)
+  if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
+  const size_t table_bytes = (size_t)(slots + 4) * 12;                  // u64 keys[slots + 4] + u32 heads[slots + 4]; slot `slots` is reserved for the all-ones key
+  // Large tables: radix-partition both sides so that one bucket's table region (<= 32 MB) stays in L2.
+  // join_algo: 0 auto, 1 = always the direct (left-row-major output) path, 2 = always partitioned.
+  int log_nb = 0;
+  while (log_nb < 10 && (table_bytes >> log_nb) > (40ull << 20)) log_nb++;      // measured: 25-50 MB regions are L2-resident, fewer buckets partition faster
+  if (c->opt_join_log_nb > 0) log_nb = (int)c->opt_join_log_nb;
+  bool radix = log_nb > 1 && nl < (1ll << 32) && nr < (1ll << 32);
+  if (c->opt_join_algo == 1) radix = false;
+  if (c->opt_join_algo == 2 && nl < (1ll << 32) && nr < (1ll << 32)) { radix = true; log_nb = std::max(log_nb, 2); }
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  std::function<void(const char*)> mark = [&](const char* name) {
+    if (c->opt_timing < 2) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); marks.push_back({name, e});
+  };
+  mark("start");
+  DevBuf tab, next, fail;
+  PDRS_TRY(tab.alloc(c, table_bytes));
+  PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));   // key = all ones (EMPTY), head = -1 (EMPTY)
+  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
+  PDRS_TRY(next.alloc(c, (size_t)std::max<int64_t>(nr, 1) * 8));
+  PDRS_CUDA(c, cudaMemsetAsync(next.p, 0xFF, (size_t)std::max<int64_t>(nr, 1) * 8, c->stream));      // -1 = end of chain
+  PDRS_TRY(fail.alloc(c, 64, true));      // [0] failed inserts, [1] build tile counter, [2] probe tile counter (two-pass) / output cursor (single pass), [3] duplicate build keys, [4] probe tile counter (single pass)
+  c->stats.table_slots = slots;
+  JKeyCol rc{rv.data, rv.nulls, rv.dtype}, lc{lv.data, lv.nulls, lv.dtype};
+  JPart lp, rp;
+  DevBuf lcnt, rcnt;
+  JSrc rsrc{rc, nullptr, nullptr, 0, nullptr, 0}, lsrc{lc, nullptr, nullptr, 0, nullptr, 0};
+  long long nl_eff = nl, nr_eff = nr;
+  if (radix) {
+    mark("memset");
+    // one-pass partition into padded buckets; exact two-pass partition when a bucket overflows (skewed keys)
+    bool ok1 = c->opt_join_part != 2;
+    long long rcap = 0, lcap = 0;
+    if (ok1) PDRS_TRY(jpartition1(c, rc, nr, log_nb, &rp, &rcnt, &rcap, &ok1));
+    if (ok1) { rsrc.cap = rcap; rsrc.cnt = rcnt.as<u64>(); rsrc.log_nb = c->opt_join_prefetch ? log_nb : 0; }
+    else { rp = JPart(); PDRS_TRY(jpartition(c, rc, nr, log_nb, &rp)); }
+    mark("partition build side");
+    bool ok2 = c->opt_join_part != 2;
+    if (ok2) PDRS_TRY(jpartition1(c, lc, nl, log_nb, &lp, &lcnt, &lcap, &ok2));
+    if (ok2) { lsrc.cap = lcap; lsrc.cnt = lcnt.as<u64>(); lsrc.log_nb = c->opt_join_prefetch ? log_nb : 0; }
+    else { lp = JPart(); PDRS_TRY(jpartition(c, lc, nl, log_nb, &lp)); }
+    mark("partition probe side");
+    rsrc.pkeys = rp.keys.as<u64>(); rsrc.prows = rp.rows.as<uint32_t>(); nr_eff = rp.n;
+    lsrc.pkeys = lp.keys.as<u64>(); lsrc.prows = lp.rows.as<uint32_t>(); nl_eff = lp.n;
+  }
+  int64_t M = 0;
+  PDRS_TRY(jbuild_probe(c, jt, next, fail, rsrc, nr_eff, lsrc, nl_eff, nl, radix, how, res, &M, mark));
   mark("write");
   if (how_req == PDRS_RIGHT || how_req == PDRS_OUTER) {
     DevBuf matched, ucounts;
@@ -959,6 +1022,221 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   guard.r = nullptr;
   *out = res;
   return PDRS_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU join: fused partition + shuffle over peer memory
+// One pdrs_xjoin per rank (= per GPU / process).  Its receive area holds, for both join sides, (key, row) rows in
+// padded sub-buckets [radix bucket][source rank] plus one row count per sub-bucket.  pdrs_xjoin_shuffle runs the
+// one-pass partition kernel with the peers' receive areas as its output (CUDA IPC mappings, stores go through
+// NVLink / NVSwitch): there is no send buffer, no separate all-to-all and no second pass on the receiving side -
+// after a barrier the local build / probe kernels read the received sub-buckets exactly like single-GPU radix buckets.
+struct XSide { size_t keys = 0, rows = 0, cnt = 0; long long cap = 0; };      // byte offsets inside the receive area
+}  // extern "C"
+struct pdrs_xjoin {
+  pdrs_ctx* ctx = nullptr;
+  int rank = 0, world = 1, log_world = 0, log_nb = 0;
+  int64_t total_right = 0;
+  XSide L, R;
+  size_t bytes = 0;
+  void* base = nullptr;                 // this rank's receive area (cudaMalloc: exportable through CUDA IPC)
+  void* peer[8] = {};                   // receive areas of all ranks as seen from this process (peer[rank] == base)
+  bool ipc_open[8] = {};
+  bool attached = false, shuffled = false;
+};
+extern "C" {
+
+int32_t pdrs_xjoin_create(pdrs_ctx* c, int32_t rank, int32_t world, int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_xjoin** out) {
+  if (!c) return PDRS_ERR_BAD_ARG;
+  if (!out || rank < 0 || rank >= world || world > 8 || (world & (world - 1)) || max_left_rows < 0 || max_right_rows < 0)
+    return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_create: world must be 1, 2, 4 or 8 and 0 <= rank < world");
+  if (max_left_rows >= (1ll << 32) || total_right_rows >= (1ll << 31))
+    return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_create: more than 2^32 left rows per rank or 2^31 right rows in total");
+  PDRS_CUDA(c, cudaSetDevice(c->device));
+  auto* x = new pdrs_xjoin();
+  x->ctx = c; x->rank = rank; x->world = world; x->total_right = total_right_rows;
+  while ((1 << x->log_world) < world) x->log_world++;
+  // radix buckets: the table region of one bucket of the rows this rank RECEIVES (~ total / world) stays L2-resident
+  const size_t table_bytes = (size_t)(3 * (total_right_rows / world + 1) + 8) * 12;
+  while (x->log_nb + x->log_world < 10 && (table_bytes >> x->log_nb) > (40ull << 20)) x->log_nb++;
+  if (c->opt_join_log_nb > 0) x->log_nb = (int)std::min<int64_t>(c->opt_join_log_nb, 10 - x->log_world);
+  const long long sb = 1ll << (x->log_nb + x->log_world);            // sub-buckets per rank and side = combined buckets per source
+  auto cap_for = [&](int64_t n) {
+    const double m = (double)n / (double)sb;                         // rows one source sends to one sub-bucket (hash-uniform keys)
+    long long cap = (long long)(m + m / 32.0 + 6.0 * std::sqrt(m + 1.0)) + 256;
+    return (cap + JQ_TILE - 1) / JQ_TILE * JQ_TILE;                  // multiple of every tile size used downstream
+  };
+  x->L.cap = cap_for(max_left_rows); x->R.cap = cap_for(max_right_rows);
+  if ((unsigned long long)sb * x->L.cap >= (1ull << 32) - 1 || (unsigned long long)sb * x->R.cap >= (1ull << 32) - 1) {
+    delete x;
+    return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_create: receive area exceeds 32-bit positions");
+  }
+  size_t off = 0;
+  auto place = [&](size_t n) { const size_t at = off; off += (n + 255) / 256 * 256; return at; };
+  for (XSide* s : {&x->R, &x->L}) { s->keys = place((size_t)sb * s->cap * 8); s->rows = place((size_t)sb * s->cap * 4); s->cnt = place((size_t)sb * 8); }
+  x->bytes = off;
+  const cudaError_t e = cudaMalloc(&x->base, x->bytes);
+  if (e != cudaSuccess) { delete x; return pdrs_fail(c, PDRS_ERR_OOM, "pdrs_xjoin_create: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(e)); }
+  x->peer[rank] = x->base;
+  x->attached = world == 1;
+  *out = x;
+  return PDRS_OK;
+}
+
+int64_t pdrs_xjoin_bytes(const pdrs_xjoin* x) { return x ? (int64_t)x->bytes : -1; }
+void* pdrs_xjoin_base(const pdrs_xjoin* x) { return x ? x->base : nullptr; }
+
+int32_t pdrs_xjoin_ipc_handle(pdrs_xjoin* x, uint8_t* handle64) {
+  if (!x || !handle64) return PDRS_ERR_BAD_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+  cudaIpcMemHandle_t h;
+  PDRS_CUDA(x->ctx, cudaSetDevice(x->ctx->device));
+  PDRS_CUDA(x->ctx, cudaIpcGetMemHandle(&h, x->base));
+  memcpy(handle64, &h, 64);
+  return PDRS_OK;
+}
+
+// handles: world x 64 bytes, entry r = what rank r's pdrs_xjoin_ipc_handle returned (all_gather by the caller)
+int32_t pdrs_xjoin_attach_ipc(pdrs_xjoin* x, const uint8_t* handles) {
+  if (!x || !handles) return PDRS_ERR_BAD_ARG;
+  PDRS_CUDA(x->ctx, cudaSetDevice(x->ctx->device));
+  for (int r = 0; r < x->world; r++) {
+    if (r == x->rank || x->ipc_open[r]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handles + 64 * r, 64);
+    PDRS_CUDA(x->ctx, cudaIpcOpenMemHandle(&x->peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    x->ipc_open[r] = true;
+  }
+  x->attached = true;
+  return PDRS_OK;
+}
+
+// same-process peers (one process driving several contexts / devices with peer access enabled): bases[r] = pdrs_xjoin_base of rank r
+int32_t pdrs_xjoin_attach_ptrs(pdrs_xjoin* x, void* const* bases) {
+  if (!x || !bases) return PDRS_ERR_BAD_ARG;
+  for (int r = 0; r < x->world; r++) if (r != x->rank) x->peer[r] = bases[r];
+  x->attached = true;
+  return PDRS_OK;
+}
+
+// Partition both key columns by (destination rank, radix bucket) straight into the peers' receive areas and publish
+// the sub-bucket counts.  Returns after this rank's stores are complete; the caller then runs a barrier over all
+// ranks (and another one before the next shuffle, so that nobody overwrites an area that is still being read).
+// Rows travel as (key, row): right rows carry GLOBAL row numbers (right_row0 + local row, < 2^31), left rows local
+// ones (the receiver adds the source's left_row0).  Returns PDRS_ERR_UNSUPPORTED when a sub-bucket overflowed
+// (heavily duplicated / skewed keys): the caller falls back to the all_to_all path.
+int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_col* right_key, int64_t right_row0) {
+  if (!x || !left_key || !right_key) return PDRS_ERR_BAD_ARG;
+  pdrs_ctx* c = x->ctx;
+  if (!x->attached) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: peers are not attached");
+  if (left_key->dtype != right_key->dtype)
+    return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "join key columns have different types (%d vs %d)", left_key->dtype, right_key->dtype);
+  PDRS_CUDA(c, cudaSetDevice(c->device));
+  ColView lv, rv;
+  PDRS_TRY(pdrs_view_col(c, left_key, &lv));
+  PDRS_TRY(pdrs_view_col(c, right_key, &rv));
+  if (right_row0 + rv.len > x->total_right) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: right rows beyond total_right_rows");
+  const int ncb = 1 << (x->log_nb + x->log_world);
+  DevBuf cur;
+  PDRS_TRY(cur.alloc(c, (size_t)(2 * ncb + 8) * 8, true));          // [ncb] right cursors, [ncb] left cursors, [1] overflow
+  u64* ovf = cur.as<u64>() + 2 * ncb;
+  static bool attr_set = false;
+  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JQ_SMEM)); attr_set = true; }
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+  for (int side = 0; side < 2; side++) {
+    const ColView& v = side ? lv : rv;
+    const XSide& s = side ? x->L : x->R;
+    u64* cursor = cur.as<u64>() + side * ncb;
+    JXDst d{};
+    JXCnt dc{};
+    for (int r = 0; r < x->world; r++) {
+      d.keys[r] = reinterpret_cast<u64*>((char*)x->peer[r] + s.keys);
+      d.rows[r] = reinterpret_cast<uint32_t*>((char*)x->peer[r] + s.rows);
+      dc.cnt[r] = reinterpret_cast<u64*>((char*)x->peer[r] + s.cnt);
+    }
+    d.log_world = x->log_world; d.me = x->rank; d.row_add = side ? 0u : (uint32_t)right_row0;
+    const JKeyCol col{v.data, v.nulls, v.dtype};
+    if (v.len > 0) {
+      const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (v.len + JQ_TILE - 1) / JQ_TILE));
+      jpart1_kernel<true><<<ctas, JQ_NT, JQ_SMEM, c->stream>>>(col, v.len, x->log_nb, s.cap, cursor, d, ovf);
+      c->stats.kernel_launches++;
+    }
+    jx_publish_counts_kernel<<<(ncb + 255) / 256, 256, 0, c->stream>>>(cursor, dc, x->log_nb, x->log_world, x->rank, s.cap);
+    c->stats.kernel_launches++;
+    PDRS_CUDA(c, cudaGetLastError());
+  }
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, ovf, 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->opt_timing) { PDRS_CUDA(c, cudaEventElapsedTime(&c->stats.total_ms, c->ev_t0, c->ev_t1)); c->stats.main_kernel_ms = c->stats.total_ms; }
+  x->shuffled = true;
+  if (c->pinned_scalars[8] != 0) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_shuffle: a sub-bucket overflowed its padded range (skewed keys)");
+  return PDRS_OK;
+}
+
+// Local join of the received rows (after the barrier): same build / probe kernels as pdrs_join_pairs on the radix
+// path.  left_row0[world] = global number of the first left row of every rank.  Pairs are in GLOBAL row numbers;
+// this rank returns the pairs of the keys whose rank hash maps to it.  Inner and Left only.
+int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, pdrs_join_result** out) {
+  if (!x || !out || !left_row0) return PDRS_ERR_BAD_ARG;
+  pdrs_ctx* c = x->ctx;
+  if (how != PDRS_INNER && how != PDRS_LEFT) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_local: only Inner and Left joins are sharded");
+  if (!x->shuffled) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_local: nothing was shuffled");
+  PDRS_CUDA(c, cudaSetDevice(c->device));
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
+  c->stats.main_kernel_ms = 0; c->stats.total_ms = 0;
+  const long long sb = 1ll << (x->log_nb + x->log_world);
+  char* base = (char*)x->base;
+  // rows received per side
+  std::vector<u64> hc((size_t)2 * sb);
+  PDRS_CUDA(c, cudaMemcpyAsync(hc.data(), base + x->R.cnt, (size_t)sb * 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaMemcpyAsync(hc.data() + sb, base + x->L.cnt, (size_t)sb * 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  int64_t nr = 0, nl = 0;
+  for (long long i = 0; i < sb; i++) { nr += (int64_t)hc[i]; nl += (int64_t)hc[sb + i]; }
+  auto* res = new pdrs_join_result();
+  res->ctx = c;
+  struct Guard { pdrs_join_result* r; ~Guard() { delete r; } } guard{res};
+  const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;
+  if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
+  const size_t table_bytes = (size_t)(slots + 4) * 12;
+  DevBuf tab, next, fail, row0;
+  PDRS_TRY(tab.alloc(c, table_bytes));
+  PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));
+  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
+  PDRS_TRY(next.alloc(c, (size_t)std::max<int64_t>(x->total_right, 1) * 8));            // chains of duplicate build keys, indexed by GLOBAL right row
+  PDRS_CUDA(c, cudaMemsetAsync(next.p, 0xFF, (size_t)std::max<int64_t>(x->total_right, 1) * 8, c->stream));
+  PDRS_TRY(fail.alloc(c, 64, true));
+  PDRS_TRY(row0.alloc(c, 64));
+  PDRS_CUDA(c, cudaMemcpyAsync(row0.p, left_row0, (size_t)x->world * 8, cudaMemcpyHostToDevice, c->stream));
+  c->stats.table_slots = slots;
+  JSrc rsrc{}, lsrc{};
+  rsrc.pkeys = reinterpret_cast<const u64*>(base + x->R.keys); rsrc.prows = reinterpret_cast<const uint32_t*>(base + x->R.rows);
+  rsrc.cap = x->R.cap; rsrc.cnt = reinterpret_cast<const u64*>(base + x->R.cnt);
+  lsrc.pkeys = reinterpret_cast<const u64*>(base + x->L.keys); lsrc.prows = reinterpret_cast<const uint32_t*>(base + x->L.rows);
+  lsrc.cap = x->L.cap; lsrc.cnt = reinterpret_cast<const u64*>(base + x->L.cnt);
+  lsrc.row0 = row0.as<long long>(); lsrc.log_srcs = x->log_world;
+  int64_t M = 0;
+  PDRS_TRY(jbuild_probe(c, jt, next, fail, rsrc, sb * x->R.cap, lsrc, sb * x->L.cap, nl, true, how, res, &M, [](const char*) {}));
+  c->stats.groupby_algo_used = 2;
+  if (c->opt_timing) {
+    PDRS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
+    PDRS_CUDA(c, cudaEventSynchronize(c->ev_t1));
+    PDRS_CUDA(c, cudaEventElapsedTime(&c->stats.total_ms, c->ev_t0, c->ev_t1));
+  } else {
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  guard.r = nullptr;
+  *out = res;
+  return PDRS_OK;
+}
+
+void pdrs_xjoin_destroy(pdrs_xjoin* x) {
+  if (!x) return;
+  cudaSetDevice(x->ctx->device);
+  cudaStreamSynchronize(x->ctx->stream);
+  for (int r = 0; r < x->world; r++) if (x->ipc_open[r]) cudaIpcCloseMemHandle(x->peer[r]);
+  if (x->base) cudaFree(x->base);
+  delete x;
 }
 
 int64_t pdrs_join_len(const pdrs_join_result* r) { return r ? r->n : -1; }

@@ -228,3 +228,60 @@ class DistJoin:
         gl = lids[li]
         gr = torch.where(ri >= 0, rids[ri.clamp(min=0)], torch.full_like(ri, -1)) if rids.numel() else torch.full_like(ri, -1)
         return gl, gr
+
+    # ---- fused partition + shuffle over NVLink peer memory (pdrs_xjoin_*)
+    def setup_fused(self, max_left_rows: int, max_right_rows: int, total_right_rows: int) -> bool:
+        """Allocates this rank's receive area, exchanges the CUDA IPC handles (all_gather) and maps the peers'
+        areas.  Collective; every rank passes the same numbers.  Returns False (on every rank) when any rank
+        could not set it up - the caller then keeps using join_pairs."""
+        from .core import XJoin
+        ctx = self.b.ctx
+        dev = self.b.device
+        ok, handle = 1, bytes(64)
+        try:
+            self.x = XJoin(ctx, self.rank, self.world, max_left_rows, max_right_rows, total_right_rows)
+            handle = self.x.ipc_handle()
+        except Exception as e:  # noqa: BLE001
+            ok, self.x, self.fused_error = 0, None, str(e)
+        mine = torch.tensor(list(handle) + [ok], dtype=torch.uint8, device=dev)
+        allh = [torch.empty_like(mine) for _ in range(self.world)]
+        self.dist.all_gather(allh, mine)
+        allh = [bytes(t.cpu().tolist()) for t in allh]
+        if ok and all(h[64] for h in allh) and self.world > 1:
+            try:
+                self.x.attach_ipc([h[:64] for h in allh])
+            except Exception as e:  # noqa: BLE001
+                ok, self.fused_error = 0, str(e)
+        flag = torch.tensor([ok if all(h[64] for h in allh) else 0], dtype=torch.int32, device=dev)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        self.fused = bool(flag.item())
+        if not self.fused and getattr(self, "x", None) is not None:
+            self.x.close()
+            self.x = None
+        return self.fused
+
+    def join_pairs_fused(self, left: Column, right: Column, how: int, left_row0: int, right_row0: int, timings: Optional[dict] = None):
+        """The partition pass of the radix join IS the shuffle: every rank's partition kernel stores its (key, row)
+        runs straight into the destination rank's receive area through NVLink; after one barrier the local build /
+        probe kernels run on the received sub-buckets.  Returns a JoinResult holding this rank's pairs in GLOBAL
+        row numbers, or None (on every rank) when a sub-bucket overflowed anywhere (skewed keys)."""
+        dev = self.b.device
+        self.b._sync()
+        self.dist.barrier()                        # every rank has finished reading its receive area (previous call)
+        ok = 1
+        try:
+            self.x.shuffle(left, right, right_row0)
+            if timings is not None:
+                timings["shuffle_ms"] = self.b.ctx.stats()["total_ms"]
+        except Exception as e:  # noqa: BLE001
+            ok, self.fused_error = 0, str(e)
+        info = torch.tensor([ok, left_row0], dtype=torch.int64, device=dev)
+        allinfo = [torch.empty_like(info) for _ in range(self.world)]
+        self.dist.all_gather(allinfo, info)        # doubles as the barrier: all stores into my area are complete
+        allinfo = [t.cpu().tolist() for t in allinfo]
+        if not all(a[0] for a in allinfo):
+            return None
+        j = self.x.local(how, [a[1] for a in allinfo])
+        if timings is not None:
+            timings["local_ms"] = self.b.ctx.stats()["total_ms"]
+        return j

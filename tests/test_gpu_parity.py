@@ -697,3 +697,86 @@ def test_dist_operators_single_rank(ctx, oracle):
         assert sorted(zip(gl.cpu().tolist(), gr.cpu().tolist())) == sorted(zip((wl + 1000).tolist(), wr.tolist()))
     for c in (kc, vc, lc, rc):
         ctx.free(c)
+
+
+# ---------------------------------------------------------------- fused partition + shuffle join (pdrs_xjoin_*)
+def _xjoin_simulated(ctx, oracle, world, L, R, how, opt_log_nb=0):
+    """All `world` ranks live in this process on one GPU: rank r's receive area is handed to the others as a plain
+    device pointer (attach_ptrs), so the partition kernel's peer stores, the sub-bucket layout, the count
+    publication and the global row numbers are exercised exactly as with CUDA IPC between processes."""
+    nl, nr = len(L), len(R)
+    lcut = [nl * r // world for r in range(world + 1)]
+    rcut = [nr * r // world for r in range(world + 1)]
+    if opt_log_nb:
+        ctx.set_option("join_log_nb", opt_log_nb)
+    xs = [pb.XJoin(ctx, r, world, max(lcut[i + 1] - lcut[i] for i in range(world)), max(rcut[i + 1] - rcut[i] for i in range(world)), nr)
+          for r in range(world)]
+    try:
+        for x in xs:
+            x.attach_ptrs([y.base for y in xs])
+        cols = []
+        for r, x in enumerate(xs):
+            lspec = Spec(L.dtype, L.values[lcut[r]:lcut[r + 1]], None if L.nulls is None else L.nulls[lcut[r]:lcut[r + 1]])
+            rspec = Spec(R.dtype, R.values[rcut[r]:rcut[r + 1]], None if R.nulls is None else R.nulls[rcut[r]:rcut[r + 1]])
+            lc, rc = ctx.upload(lspec.gpu(pb)), ctx.upload(rspec.gpu(pb))
+            cols += [lc, rc]
+            x.shuffle(lc, rc, rcut[r])
+        got = []
+        for x in xs:
+            j = x.local(how, lcut[:world])
+            li, ri = j.indices()
+            j.close()
+            got += list(zip(li.tolist(), ri.tolist()))
+        for c in cols:
+            ctx.free(c)
+    finally:
+        for x in xs:
+            x.close()
+        if opt_log_nb:
+            ctx.set_option("join_log_nb", 0)
+    wl, wr = oracle.join(L.cpu(oracle), R.cpu(oracle), how)
+    assert sorted(got) == sorted(zip(wl.tolist(), wr.tolist())), (world, how)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 8])
+@pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
+def test_xjoin_fused_shuffle_unique_build(ctx, oracle, world, how):
+    rng = np.random.default_rng(21 + world)
+    nb, npr = 40_000, 300_001
+    bk = rng.permutation(2 * nb)[:nb].astype(np.int64) * 7919 - 100_000          # unique build keys, ~50% hits
+    pk = (rng.integers(0, 2 * nb, npr) * 7919 - 100_000).astype(np.int64)
+    _xjoin_simulated(ctx, oracle, world, Spec(pb.I64, pk), Spec(pb.I64, bk), how, opt_log_nb=3)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4])
+def test_xjoin_fused_shuffle_duplicates_nulls_and_extremes(ctx, oracle, world):
+    # duplicate build keys take the count / scan / write path with chains indexed by GLOBAL right rows; NULL keys
+    # never travel; the all-ones key lives in the reserved slot
+    rng = np.random.default_rng(5)
+    nl, nr = 50_000, 9_000
+    lk = rng.integers(-300, 300, nl).astype(np.int64)
+    rk = rng.integers(-300, 300, nr).astype(np.int64)
+    lk[::97] = -1
+    rk[::53] = -1
+    lk[5], rk[7] = np.iinfo(np.int64).min, np.iinfo(np.int64).min
+    for how in (pb.INNER, pb.LEFT):
+        _xjoin_simulated(ctx, oracle, world, Spec(pb.I64, lk, nulls=rng.random(nl) < 0.02), Spec(pb.I64, rk, nulls=rng.random(nr) < 0.02), how)
+
+
+@pytest.mark.gpu
+def test_xjoin_overflow_is_reported_not_hidden(ctx):
+    # one key repeated: every row goes to one sub-bucket, which overflows its padded range -> UNSUPPORTED (the host falls back)
+    n = 2_000_000
+    lc, rc = ctx.upload(pb.Column.int64(np.full(n, 12345))), ctx.upload(pb.Column.int64(np.full(n, 12345)))
+    ctx.set_option("join_log_nb", 6)                  # 64 sub-buckets of ~n / 64 rows
+    x = pb.XJoin(ctx, 0, 1, n, n, n)
+    ctx.set_option("join_log_nb", 0)
+    try:
+        with pytest.raises(pb.PandrsError) as e:
+            x.shuffle(lc, rc, 0)
+        assert e.value.kind == "OperationFailed"
+    finally:
+        x.close()
+        ctx.free(lc); ctx.free(rc)
