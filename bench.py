@@ -35,6 +35,7 @@ def parse():
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extras-scale", type=float, default=1.0, help="scales the row counts of the configs[3..4] extras (debugging)")
     ap.add_argument("--dist-join", action="store_true", help="also time the sharded inner join (fused partition + NVLink shuffle), rows/GPU = --rows x --rows/10")
     return ap.parse_args()
 
@@ -239,6 +240,7 @@ def main():
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": workload_config(args, n), "roofline": roofline, "gpu_launches": int(launches), "clocks": clk}
 
+    log(f"headline: {ms_per_step:.3f} ms/step")
     # ---- end to end through the C ABI with HOST (pinned) buffers: H2D of the inputs and D2H of the result inside the timed region
     if not args.no_e2e:
         nb = (n + 7) // 8
@@ -275,6 +277,7 @@ def main():
         for p in (hk, hv, hn):
             ctx.host_free(p)
 
+    log("e2e done")
     # ---- the other configs, a few steps each (explanatory; not the headline)
     if not args.no_extras and world == 1:
         out["extras"] = extras(ctx, pb, args, n, keys, vals, peak)
@@ -381,6 +384,7 @@ def extras(ctx, pb, args, n, keys, vals, peak):
     def gb(k, v, aggs):
         r = ctx.groupby_agg([k], [v], aggs)
         r.close()
+    log("extras: sum only, 10M groups, joins")
     ms, kms = timed(lambda: gb(keys, vals, [(0, pb.SUM)]))
     ex["groupby_sum_1k"] = {"rows_per_s": n / (ms * 1e-3), "ms": ms, "kernel_ms": kms, "roofline_frac": ALG_BYTES_PER_ROW * n / (kms * 1e-3) / 1e9 / peak}
     try:
@@ -415,6 +419,7 @@ def extras(ctx, pb, args, n, keys, vals, peak):
             ctx.gather(p1, j.right_dev(), n=j.n, idx_dev=True, out_dev=o1)
             ctx.gather(p2, j.right_dev(), n=j.n, idx_dev=True, out_dev=o2)
             j.close()
+        log("extra join_inner_2payload ...")
         ms, _ = timed(jn_payload, reps=2)
         alg = 8 * np_ + nb_ * (8 + 16) + m[0] * (16 + 16)      # SURVEY.md §8(d), P = 2 payload columns
         ex["join_inner_2payload"] = {"rows_per_s": (np_ + nb_) / (ms * 1e-3), "ms": ms, "pairs": m[0], "alg_bytes": alg, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak}
@@ -423,13 +428,17 @@ def extras(ctx, pb, args, n, keys, vals, peak):
     except Exception as e:  # noqa: BLE001
         ex["join"] = {"error": str(e)[:200]}
     try:
-        ex.update(extras_c4_c5(ctx, pb, peak, timed))
+        ex.update(extras_c4_c5(ctx, pb, peak, timed, args.extras_scale))
     except Exception as e:  # noqa: BLE001
         ex["c4_c5"] = {"error": str(e)[:200]}
     return ex
 
 
-def extras_c4_c5(ctx, pb, peak, timed):
+def log(msg):
+    print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
+def extras_c4_c5(ctx, pb, peak, timed, scale=1.0):
     """BASELINE.json configs[3] (multi-key + dictionary key, 500M rows, Zipf 1.1) and one GPU's shard of configs[4]
     (Q1-style filter -> groupby(returnflag, linestatus), 7.5e8 rows).  Columns are generated with torch on the device
     (same stream as the context) and handed over as borrowed device pointers."""
@@ -479,15 +488,18 @@ def extras_c4_c5(ctx, pb, peak, timed):
             r = ctx.groupby_agg(keys, vals, aggs, filter=filt)
             ng[0] = r.n_groups
             r.close()
+        log(f"extra {name} ...")
         try:
             ms, _ = timed(f, reps=reps)
+            log(f"extra {name}: {ms:.2f} ms")
             ex[name] = {"rows_per_s": n / (ms * 1e-3), "ms": ms, "groups": ng[0], "alg_bytes_per_row": alg_bytes / n,
                         "roofline_frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "algo": ctx.stats()["groupby_algo_used"]}
         except Exception as e:  # noqa: BLE001
             ex[name] = {"error": str(e)[:200]}
 
     # ---- configs[3]
-    n = 500_000_000
+    n = int(500_000_000 * scale)
+    log("generating configs[3] columns")
     k1 = zipf(n, 1000, torch.int32)
     k2 = zipf(n, 100_000, torch.int64)
     k3 = zipf(n, 10_000, torch.int32)           # dictionary ids over a 10,000-string pool (u32, same bits)
@@ -501,7 +513,8 @@ def extras_c4_c5(ctx, pb, peak, timed):
     torch.cuda.empty_cache()
 
     # ---- configs[4], one GPU's shard: 6e9 / 8 rows
-    n = 750_000_000
+    n = int(750_000_000 * scale)
+    log("generating configs[4] columns")
     rf = torch.empty(n, dtype=torch.int32, device=dev)
     ls = torch.empty(n, dtype=torch.int32, device=dev)
     for a in range(0, n, CH):

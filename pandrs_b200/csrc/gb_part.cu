@@ -43,9 +43,11 @@ struct GpIn {
   int compat_nulls;
   // level 2: padded buckets of level 1
   const u64* pkeys; const u64* pvals; const uint8_t* pflags; const u64* pcnt; long long pcap;
+  // level 1, GENERIC: any key tuple that packs into one 64-bit word (dictionary ids, i32, bool and pairs of them, no NULLs)
+  KeySpec ks;
 };
 
-template <bool FROM_COLS>
+template <bool FROM_COLS, bool GENERIC = false>
 __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr, int local_bits, long long cap_out, u64* __restrict__ cursor,
                                                           u64* __restrict__ out_keys, u64* __restrict__ out_vals, uint8_t* __restrict__ out_flags,
                                                           u64* __restrict__ overflow) {
@@ -74,7 +76,8 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
       const long long i = tb + (long long)j * GP_NT + tid;
       const bool inb = i < lim;
       if (FROM_COLS) {
-        key[j] = inb ? __ldcs(in.keys + i) : 0ull;
+        if (GENERIC) { u64 w[1] = {0ull}; if (inb) load_key_generic<1>(in.ks, i, w); key[j] = w[0]; }
+        else key[j] = inb ? __ldcs(in.keys + i) : 0ull;
         val[j] = inb ? __ldcs(in.vals + i) : 0ull;
       } else {
         key[j] = inb ? __ldcs(in.pkeys + base0 + i) : 0ull;
@@ -167,11 +170,15 @@ long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 // One aggregation pass through the partitioned path.  Returns PDRS_ERR_UNSUPPORTED when it does not apply or a
 // bucket overflowed (the caller then takes the global-table path; *dirty = the table was touched: never, today).
-int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty) {
+int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed) {
   *dirty = false;
+  *skewed = false;
   const long long n = gp.n;
   const long long T = gb_tsort_tile_rows();
-  if (gp.ks.c[0].nulls || !gp.val || n < (1 << 20)) return PDRS_ERR_UNSUPPORTED;
+  const bool generic = !(gp.ks.nkeys == 1 && gp.ks.c[0].dtype == PDRS_I64);
+  if (gp.ks.nwords != 1 || !gp.val || n < (1 << 20)) return PDRS_ERR_UNSUPPORTED;
+  for (int k = 0; k < gp.ks.nkeys; k++)
+    if (gp.ks.c[k].nulls || (gp.ks.c[k].dtype == PDRS_DICT_U32 && gp.ks.c[k].null_alias >= 0)) return PDRS_ERR_UNSUPPORTED;   // NULL keys: other paths
   // partitions of <= ~600 expected groups (the tile-sort kernel holds 1023 ids with 512 threads x 2 groups).  Few
   // partitions are fine: the aggregation kernel cuts every partition into chunks of tiles, one work item each.
   int bits = 1;
@@ -211,6 +218,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   static bool attr_set = false;
   if (!attr_set) {
     PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
@@ -219,7 +227,9 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   in.keys = reinterpret_cast<const u64*>(gp.ks.c[0].data); in.vals = reinterpret_cast<const u64*>(gp.val); in.vnull = gp.vnull;
   in.fbits = gp.fbits; in.fnull = gp.fnull; in.n = n; in.compat_nulls = gp.compat_nulls;
   const int ctas1 = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + GP_TILE - 1) / GP_TILE));
-  gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf);
+  in.ks = gp.ks;
+  if (generic) gp_part_kernel<true, true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf);
+  else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf);
   c->stats.kernel_launches++;
   const u64 *pk = k1.as<u64>(), *pv = v1.as<u64>(), *pc = cur1;
   const uint8_t* pf = has_flags ? f1.as<uint8_t>() : nullptr;
@@ -239,9 +249,10 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   PDRS_CUDA(c, cudaGetLastError());
   PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, ovf, 8, cudaMemcpyDeviceToHost, c->stream));
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->pinned_scalars[8] != 0) return PDRS_ERR_UNSUPPORTED;      // skewed keys: a bucket overflowed its padded range
+  if (c->pinned_scalars[8] != 0) { *skewed = true; return PDRS_ERR_UNSUPPORTED; }      // skewed keys: a bucket overflowed its padded range
   if (bits2) { k1.release(); v1.release(); f1.release(); }                        // only the last level is read below
   GbParams tp = gp;
+  tp.ts_generic = 0;               // the partitions hold packed key words
   tp.part_keys = pk; tp.part_vals = pv; tp.part_flags = pf; tp.part_cnt = pc; tp.part_cap = pcap; tp.part_bits = bits;
   {   // work items: ~16 chunks per CTA, each chunk a run of whole tiles of one partition
     const long long tiles_cap = pcap / T, want = 16ll * c->sm_count;

@@ -209,7 +209,7 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
 }
 
 int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, float* kernel_ms);   // gb_radix.cu
-int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty);   // gb_part.cu
+int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed);   // gb_part.cu
 // gb_tsort.cu
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
@@ -477,13 +477,20 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           gp.vnull = vv[passes[i].val].nulls;
         }
         // high cardinality, one 64-bit key column: hash-partition the rows, tile-sort kernel per partition (gb_part.cu)
-        if (variant == 0 && part_ok && !ts_fit && algo != PDRS_GB_GLOBAL && passes[i].val >= 0 && est > 2047) {
+        if ((variant == 0 || variant == 1) && part_ok && !ts_fit && algo != PDRS_GB_GLOBAL && passes[i].val >= 0 && est > 2047) {
           float ms = 0;
-          bool dirty = false;
-          int32_t rs = gb_part_pass(c, gp, passes[i].is_int, passes[i].flags, est, &ms, &dirty);
+          bool dirty = false, skewed = false;
+          int32_t rs = gb_part_pass(c, gp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed);
           if (rs == PDRS_OK) { c->stats.main_kernel_ms += ms; c->stats.groupby_algo_used = PDRS_GB_PARTITIONED; continue; }
           if (rs != PDRS_ERR_UNSUPPORTED) return rs;
           part_ok = false;
+          // Skewed keys (a hash bucket overflowed its padded range): a few hot keys carry most of the rows.  The
+          // tile-sort kernel keeps the first 2047 keys every CTA meets (the hot ones, with high probability) in its
+          // register accumulators and sends the rows of the remaining keys to the global table one by one.
+          if (skewed && c->opt_tsort != 0 && n >= 4 * gb_tsort_tile_rows() && n < (1ll << 38)) {
+            ts_dense = false; ts_cap = 2047;
+            ts_fit = gb_tsort_geometry(ts_cap, false, c->smem_optin, (int)c->opt_tsort_threads, &ts_nt, &ts_gpt, &ts_slots, &ts_smem);
+          }
           if (dirty || i > 0) { restart = true; break; }     // the table already holds counts of this attempt: start over without this path
         }
         // high cardinality, one 64-bit key column: radix-partitioned rows + L2-resident table regions (gb_radix.cu)

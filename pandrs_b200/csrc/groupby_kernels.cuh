@@ -218,6 +218,17 @@ __device__ __forceinline__ long long g_find_or_insert(const GTable& t, const u64
   long long res = -1;
   bool pending = active;
   int rounds = 0;
+  {
+    // Fail fast when the table fills up (cardinality underestimated by the sample, e.g. Zipf-skewed keys): linear
+    // probing degenerates into scans of the whole table long before it is full, and the attempt is thrown away by
+    // the host anyway (it retries with 4x the slots).  One 16-byte load of {groups, overflow flag} per call.
+    const ulonglong2 c01 = ld_cg_hdr(reinterpret_cast<const GHdr*>(t.counters + CNT_NGROUPS));
+    const bool full = c01.y != 0 || c01.x > (u64)t.slots - ((u64)t.slots >> 2);
+    if (__any_sync(0xFFFFFFFFu, full)) {          // warp-uniform decision: the retry loop below is warp-synchronous
+      if (full && c01.y == 0) atomicAdd(&t.counters[CNT_OVERFLOW], 1ull);   // (also by lanes without a row: rows of this warp are dropped)
+      return -1;
+    }
+  }
   while (__any_sync(0xFFFFFFFFu, pending)) {
     if (pending) {
       long long r = g_try_insert<NW>(t, w, slot, probe);

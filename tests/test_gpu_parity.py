@@ -699,6 +699,53 @@ def test_dist_operators_single_rank(ctx, oracle):
         ctx.free(c)
 
 
+# ---------------------------------------------------------------- Zipf-skewed keys (BASELINE.json configs[3])
+def _zipf(rng, n, domain, s=1.1):
+    w = 1.0 / np.arange(1, domain + 1) ** s
+    return rng.choice(domain, size=n, p=w / w.sum())
+
+
+@pytest.mark.gpu
+def test_zipf_dictionary_key_takes_the_skew_fallback(ctx, oracle):
+    # ~10^4 groups: too many for one tile-sort table, and the hot keys overflow their hash partition -> the tile-sort
+    # kernel keeps the hot keys in registers and spills the tail row by row to the global table
+    n = 1_300_000
+    rng = np.random.default_rng(31)
+    pool = [f"s{i}" for i in range(10_000)]
+    k = Spec(pb.DICT_U32, _zipf(rng, n, 10_000).astype(np.uint32), pool=pool)
+    v = Spec(pb.F64, rng.normal(50.0, 20.0, n), nulls=rng.random(n) < 0.05)
+    compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+    assert ctx.stats()["groupby_algo_used"] in (pb.GB_TILESORT, pb.GB_PARTITIONED)
+    ku = Spec(pb.DICT_U32, rng.integers(0, 10_000, n).astype(np.uint32), pool=pool)      # uniform: the partitioned path, packed keys
+    compare_groupby(pb, oracle, ctx, [ku], [v], [(0, op) for op in ALL6], device=True)
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+    k32 = Spec(pb.I32, rng.integers(-3000, 3000, n).astype(np.int32))                   # (i32, bool) pair in one word
+    kb = Spec(pb.BOOL_BITS, rng.random(n) < 0.3)
+    compare_groupby(pb, oracle, ctx, [k32, kb], [v], [(0, pb.SUM), (0, pb.STD), (0, pb.COUNT)], device=True)
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+
+
+@pytest.mark.gpu
+def test_zipf_multi_key_underestimated_cardinality_retries_fast(ctx, oracle):
+    # (i32, i64) and (i32, i64, dictionary) tuples are wider than one word: global table.  A tiny sample of Zipf keys
+    # underestimates the number of groups by far; the table must report the overflow quickly (not degenerate into
+    # whole-table probe sequences) and the retry must give the right answer.
+    n = 400_000
+    rng = np.random.default_rng(32)
+    pool = [f"p{i}" for i in range(10_000)]
+    k1 = Spec(pb.I32, _zipf(rng, n, 1000).astype(np.int32))
+    k2 = Spec(pb.I64, _zipf(rng, n, 100_000).astype(np.int64) * 1_000_003)
+    k3 = Spec(pb.DICT_U32, _zipf(rng, n, 10_000).astype(np.uint32), pool=pool)
+    v = Spec(pb.F64, rng.random(n) * 1000.0)
+    ctx.set_option("sample_rows", 4096)
+    try:
+        for keys in ([k1, k2], [k1, k2, k3]):
+            compare_groupby(pb, oracle, ctx, keys, [v], [(0, op) for op in ALL6], device=True)
+            assert ctx.stats()["retries"] >= 1
+    finally:
+        ctx.set_option("sample_rows", 1 << 18)
+
+
 # ---------------------------------------------------------------- fused partition + shuffle join (pdrs_xjoin_*)
 def _xjoin_simulated(ctx, oracle, world, L, R, how, opt_log_nb=0):
     """All `world` ranks live in this process on one GPU: rank r's receive area is handed to the others as a plain
