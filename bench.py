@@ -332,6 +332,8 @@ def dist_join(ctx, pb, dist, rank, world, n_probe, peaks):
     nb_, np_ = n_probe // 10, n_probe
     build = ctx.synth_join_keys(nb_, unique=True, row0=rank * nb_)
     probe = ctx.synth_join_keys(np_, domain=2 * nb_ * world, row0=rank * np_)
+    if os.environ.get("PDRS_XJOIN_MODE"):
+        ctx.set_option("xjoin_mode", int(os.environ["PDRS_XJOIN_MODE"]))      # 1 = fused, 2 = staged (default: auto)
     dj = DistJoin(ctx, d)
     if not dj.setup_fused(np_, nb_, nb_ * world):
         return {"error": "fused setup failed: " + getattr(dj, "fused_error", "?")[:200]}
@@ -356,13 +358,30 @@ def dist_join(ctx, pb, dist, rank, world, n_probe, peaks):
         if rep and (best is None or sh + lo < best[0] + best[1]):
             best = (sh, lo, wl, float(tot.item()))
     dj.x.close()
+    # the same join through the plain path: pdrs_hash_partition + gathers + NCCL all_to_all + pdrs_join_pairs (wall clock, max over ranks)
+    base_ms = None
+    try:
+        if dist is not None:
+            for rep in range(2):
+                dist.barrier(); torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                gl, gr = dj.join_pairs(probe, build, pb.INNER, rank * np_, rank * nb_)
+                torch.cuda.synchronize()
+                tb = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda", dtype=torch.float64)
+                del gl, gr
+                dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+                base_ms = float(tb.item())
+    except Exception as e:  # noqa: BLE001
+        base_ms = "error: " + str(e)[:120]
     sh, lo, wl, total_pairs = best
     sent = (np_ + nb_) * 12.0 * (world - 1) / world          # bytes leaving each GPU
     nvl_peak = float(peaks.get("nvlink_gbs", 770.0))
     return {"rows_per_s": (np_ + nb_) * world / ((sh + lo) * 1e-3), "shuffle_ms": sh, "local_ms": lo, "wall_ms": wl, "pairs": total_pairs,
             "rows_per_gpu": np_ + nb_, "nvlink_bytes_per_gpu": sent, "nvlink_gbs_achieved": sent / (sh * 1e-3) / 1e9 if world > 1 else None,
             "nvlink_peak_gbs": nvl_peak, "nvlink_frac": sent / (sh * 1e-3) / 1e9 / nvl_peak if world > 1 else None,
-            "note": "weak scaling; shuffle_ms = fused partition + peer stores of both sides; local_ms = table memset + build + probe/emit"}
+            "nccl_all_to_all_path_wall_ms": base_ms,
+            "xjoin_mode": os.environ.get("PDRS_XJOIN_MODE", "auto"),
+            "note": "weak scaling; shuffle_ms = partition kernel storing into the peers' receive areas, both sides; local_ms = (staged mode: local radix partition +) table memset + build + probe/emit"}
 
 
 def extras(ctx, pb, args, n, keys, vals, peak):

@@ -39,6 +39,7 @@ struct pdrs_ctx {
   int64_t opt_join_slots_mult = 0;     // table slots per build row (0 = default 2)
   int64_t opt_join_prefetch = 1;       // stream the next radix bucket's table region into L2 ahead of its first probes
   int64_t opt_join_emit = 0;           // 0 = auto (single-pass probe + emit when the build keys are unique), 2 = always count / scan / write
+  int64_t opt_xjoin_mode = 0;          // exchange join: 0 = auto, 1 = fused (rank x radix bucket in one pass), 2 = staged (shuffle by rank, local radix partition)
   int64_t opt_timing = 1;              // record CUDA-event times in pdrs_stats
   int64_t opt_radix = 1;               // allow the radix-partitioned high-cardinality groupby path
   int64_t opt_dense = 1;               // allow the direct-mapped path for small dense integer keys

@@ -89,9 +89,15 @@ __device__ __forceinline__ u64 ld_volatile_u64(const void* p) {
 // Multi-GPU exchange path (pdrs_xjoin_*): a bucket is split into 2^log_srcs sub-buckets, one per source rank
 // (sub-bucket = bucket << log_srcs | source), cap / cnt describe sub-buckets, prows are row numbers LOCAL to the
 // source rank and row0[source] turns them into global row numbers when pairs are emitted.
-struct JSrc { JKeyCol col; const u64* pkeys; const uint32_t* prows; long long cap; const u64* cnt; int log_nb; const long long* row0; int log_srcs; };
+// Staged exchange (two steps: shuffle by rank, then a local radix partition that mixes the sources): prows of the left
+// side are (source rank << row_shift | local row) and are decoded by value.
+struct JSrc { JKeyCol col; const u64* pkeys; const uint32_t* prows; long long cap; const u64* cnt; int log_nb; const long long* row0; int log_srcs; int row_shift; };
 __device__ __forceinline__ long long jsrc_row_add(const JSrc& s, long long pos) {
-  return s.row0 ? __ldg(s.row0 + ((pos / s.cap) & ((1ll << s.log_srcs) - 1))) : 0ll;
+  return (s.row0 && !s.row_shift) ? __ldg(s.row0 + ((pos / s.cap) & ((1ll << s.log_srcs) - 1))) : 0ll;
+}
+__device__ __forceinline__ long long jsrc_left_row(const JSrc& s, uint32_t enc, long long radd) {
+  if (s.row_shift) return __ldg(s.row0 + (enc >> s.row_shift)) + (long long)(enc & ((1u << s.row_shift) - 1u));
+  return (long long)enc + radd;
 }
 // end of the valid positions of the tile [lo, lo + tile)
 __device__ __forceinline__ long long jsrc_tile_hi(const JSrc& s, long long lo, long long tile, long long n) {
@@ -347,7 +353,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long lon
       for (int j = 0; j < JOIN_ITEMS; j++) {
         long long i = c0 + (long long)threadIdx.x * JOIN_ITEMS + j;
         if (cn[j] == 0) continue;
-        if (prows) i = (long long)__ldg(prows + i) + jsrc_row_add(src, i);      // partitioned probe side: position -> original left row
+        if (prows) i = jsrc_left_row(src, __ldg(prows + i), jsrc_row_add(src, i));      // partitioned probe side: position -> original left row
         if (st[j] == J_NOMATCH) { out_l[pos] = i; out_r[pos] = -1; pos++; }
         else if (!(st[j] & J_MULTI)) { out_l[pos] = i; out_r[pos] = st[j]; pos++; }
         else {
@@ -382,6 +388,9 @@ __device__ __forceinline__ uint32_t jhash_rank(u64 k) { return (uint32_t)(((k ^ 
 // IPC), so the partition pass IS the shuffle - every bucket run is stored straight through NVLink; combined bucket
 // = rank << log_nb | radix bucket; inside rank r's buffers this rank `me` owns sub-bucket (bucket << log_world | me).
 struct JXDst { u64* keys[8]; uint32_t* rows[8]; int log_world; int me; uint32_t row_add; };
+// Input of the local partition on the staged exchange path: (key, row) records received from the peers, one padded
+// region of `cap` positions per source rank holding cnt[source] rows.
+struct JStaged { const u64* keys; const uint32_t* rows; const u64* cnt; long long cap; };
 
 __global__ void __launch_bounds__(JP_THREADS) jpart_hist_kernel(JKeyCol col, long long n, int log_nb, u64* __restrict__ hist) {
   __shared__ uint32_t sh[JP_MAX_BUCKETS];
@@ -475,9 +484,9 @@ __global__ void __launch_bounds__(JP_THREADS, 4) jpart_scatter_kernel(JKeyCol co
 #define JQ_ITEMS 8
 #define JQ_TILE (JQ_NT * JQ_ITEMS)
 #define JQ_SMEM ((size_t)JQ_TILE * 16 + 1056 * 4 + 1024 * 8 + JQ_TILE)
-template <bool XCHG>
+template <bool XCHG, bool STAGED = false>
 __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long n, int log_nb, long long cap, u64* __restrict__ cursor,
-                                                          const JXDst x, u64* __restrict__ overflow) {
+                                                          const JXDst x, u64* __restrict__ overflow, const JStaged sin = JStaged{}) {
   u64* __restrict__ out_keys = x.keys[0];
   uint32_t* __restrict__ out_rows = x.rows[0];
   extern __shared__ __align__(16) unsigned char jsm[];
@@ -493,8 +502,9 @@ __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long
   __shared__ uint32_t sh_total;
   const int nb = 1 << log_nb;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const bool fast = col.dtype == PDRS_I64 && !col.nulls;
+  const bool fast = !STAGED && col.dtype == PDRS_I64 && !col.nulls;
   const long long tstride = (long long)gridDim.x * JQ_TILE;
+  uint32_t srow[STAGED ? JQ_ITEMS : 1];
   long long t0 = (long long)blockIdx.x * JQ_TILE;
   u64 key[JQ_ITEMS];
   // plain Int64 keys: the loads of a tile are issued one stage ahead (in flight while the previous tile is written out)
@@ -512,7 +522,11 @@ __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long
       const long long i = t0 + (long long)j * JQ_NT + tid;
       br[j] = 0xFFFFFFFFu;
       bool live = i < n;
-      if (!fast) live = live && jload_key(col, i, &key[j]);
+      if (STAGED) {      // a tile never straddles two source regions (cap is a multiple of the tile)
+        const long long r = i / sin.cap;
+        live = live && (i - r * sin.cap) < (long long)__ldg(sin.cnt + r);
+        if (live) { key[j] = __ldcs(sin.keys + i); srow[j] = __ldcs(sin.rows + i); }
+      } else if (!fast) live = live && jload_key(col, i, &key[j]);
       if (live) {
         uint32_t b = jbucket(key[j], log_nb);
         if (XCHG && lw) b |= (jhash_rank(key[j]) >> (32 - lw)) << log_nb;
@@ -548,13 +562,32 @@ __global__ void __launch_bounds__(JQ_NT, 2) jpart1_kernel(JKeyCol col, long long
       const uint2 hd = HD[br[j] >> 16];
       const uint32_t rank = br[j] & 0xFFFFu, pos = hd.x + rank;
       st_key[pos] = key[j];
-      st_row[pos] = (uint32_t)(t0 + (long long)j * JQ_NT + tid);
+      st_row[pos] = STAGED ? srow[j] : (uint32_t)(t0 + (long long)j * JQ_NT + tid);
       st_dst[pos] = hd.y == 0xFFFFFFFFu ? 0xFFFFFFFFu : hd.y + rank;       // all ones: the bucket overflowed, the caller discards this partitioning
       if (XCHG) st_rk[pos] = (uint8_t)(br[j] >> (16 + log_nb));
     }
     if (fast && t0 + tstride < n) load_tile(t0 + tstride);
     __syncthreads();
     const uint32_t total = sh_total;
+    if (XCHG && log_nb == 0) {
+      // Staged exchange: one long run per destination rank.  Peer stores move whole 128-byte lines, so the rows are
+      // handed to the lanes by DESTINATION position: lane l writes positions = l (mod 32), every warp store covers
+      // aligned lines (2 for the keys, 1 for the row ids) and no line is sent twice.
+      const int R = 1 << lw;
+      for (int r = 0; r < R; r++) {
+        const uint2 hd = HD[r];
+        const uint32_t len = (r + 1 < R ? HD[r + 1].x : total) - hd.x;
+        if (hd.y == 0xFFFFFFFFu || len == 0) continue;
+        const uint32_t mis = hd.y & 31u;
+        u64* __restrict__ dk = x.keys[r] + (hd.y - mis);
+        uint32_t* __restrict__ dr = x.rows[r] + (hd.y - mis);
+        for (uint32_t q = tid; q < len + mis; q += JQ_NT) {
+          if (q < mis) continue;
+          dk[q] = st_key[hd.x + q - mis];
+          dr[q] = st_row[hd.x + q - mis] + x.row_add;
+        }
+      }
+    } else
     for (uint32_t pos = tid; pos < total; pos += JQ_NT) {     // consecutive staged rows of a bucket go to consecutive output rows
       const uint32_t d = st_dst[pos];
       if (d == 0xFFFFFFFFu) continue;
@@ -719,7 +752,7 @@ __global__ void __launch_bounds__(JE_THREADS, 3) join_probe_emit_kernel(JTab tab
 #pragma unroll
       for (int j = 0; j < JE_ITEMS; j++) {
         if (!((emit >> j) & 1u)) continue;
-        st_stream_u64(ol + woff[j], (long long)lrow[j] + radd, pol_stream);
+        st_stream_u64(ol + woff[j], jsrc_left_row(src, lrow[j], radd), pol_stream);
         st_stream_u64(orr + woff[j], res[j] == NONE ? -1ll : (long long)res[j], pol_stream);
       }
     }
@@ -796,9 +829,13 @@ static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_
 }
 
 // One-pass partition into padded buckets; *ok = false when a bucket overflowed (heavily duplicated keys).
-static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out, DevBuf* counts, long long* cap_out, bool* ok) {
+// `staged` (exchange path): the input is the (key, row) records received from the peers - n positions in padded
+// source regions holding `rows_in` rows - instead of a key column.
+static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out, DevBuf* counts, long long* cap_out, bool* ok,
+                           const JStaged* staged = nullptr, long long rows_in = 0) {
   const int nb = 1 << log_nb;
-  long long cap = n / nb + n / (nb * 32ll) + 65536;           // ~3% + 64K rows of slack per bucket
+  const long long nrows = staged ? rows_in : n;
+  long long cap = nrows / nb + nrows / (nb * 32ll) + 65536;           // ~3% + 64K rows of slack per bucket
   cap = (cap + JQ_TILE - 1) / JQ_TILE * JQ_TILE;             // multiple of every tile size used downstream
   *cap_out = cap;
   PDRS_TRY(counts->alloc(c, (size_t)(nb + 2) * 8, true));    // [nb] bucket cursors, [nb] overflow count
@@ -808,11 +845,16 @@ static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log
   if ((unsigned long long)nb * (unsigned long long)cap >= (1ull << 32)) { *ok = false; return PDRS_OK; }   // 32-bit output positions
   const size_t smem = JQ_SMEM;
   static bool attr_set = false;
-  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  if (!attr_set) {
+    PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
   const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + JQ_TILE - 1) / JQ_TILE));
   JXDst x{};
   x.keys[0] = out->keys.as<u64>(); x.rows[0] = out->rows.as<uint32_t>();
-  jpart1_kernel<false><<<ctas, JQ_NT, smem, c->stream>>>(col, n, log_nb, cap, counts->as<u64>(), x, counts->as<u64>() + nb);
+  if (staged) jpart1_kernel<false, true><<<ctas, JQ_NT, smem, c->stream>>>(col, n, log_nb, cap, counts->as<u64>(), x, counts->as<u64>() + nb, *staged);
+  else jpart1_kernel<false><<<ctas, JQ_NT, smem, c->stream>>>(col, n, log_nb, cap, counts->as<u64>(), x, counts->as<u64>() + nb);
   c->stats.kernel_launches++;
   PDRS_CUDA(c, cudaGetLastError());
   PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, counts->as<u64>() + nb, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1034,7 +1076,10 @@ struct XSide { size_t keys = 0, rows = 0, cnt = 0; long long cap = 0; };      //
 }  // extern "C"
 struct pdrs_xjoin {
   pdrs_ctx* ctx = nullptr;
-  int rank = 0, world = 1, log_world = 0, log_nb = 0;
+  int rank = 0, world = 1, log_world = 0;
+  int log_nb = 0;                       // radix buckets of the local join
+  int sh_log_nb = 0;                    // radix bits applied by the shuffle kernel itself (fused mode: log_nb, staged mode: 0)
+  int row_shift = 0;                    // staged mode: left rows travel as (source rank << row_shift | local row)
   int64_t total_right = 0;
   XSide L, R;
   size_t bytes = 0;
@@ -1059,7 +1104,19 @@ int32_t pdrs_xjoin_create(pdrs_ctx* c, int32_t rank, int32_t world, int64_t max_
   const size_t table_bytes = (size_t)(3 * (total_right_rows / world + 1) + 8) * 12;
   while (x->log_nb + x->log_world < 10 && (table_bytes >> x->log_nb) > (40ull << 20)) x->log_nb++;
   if (c->opt_join_log_nb > 0) x->log_nb = (int)std::min<int64_t>(c->opt_join_log_nb, 10 - x->log_world);
-  const long long sb = 1ll << (x->log_nb + x->log_world);            // sub-buckets per rank and side = combined buckets per source
+  // Two ways to get the rows into radix buckets on the right GPU (xjoin_mode: 0 auto, 1 fused, 2 staged):
+  //  fused   the shuffle kernel partitions by (rank, radix bucket) at once: one pass, but a tile of 4096 rows is cut into
+  //          world x 2^log_nb runs, and peer stores move whole 128-byte lines (tools/peer_store_bench.cu: 32-byte runs reach
+  //          219 GB/s, 64-byte runs 438 GB/s, >= 128 bytes 716 GB/s over NVLink) - only good while runs stay >= 128 bytes
+  //  staged  the shuffle kernel partitions by rank only (runs of 4096 / world rows = full NVLink speed), the receiver
+  //          runs the ordinary local radix partition over what arrived (one more HBM pass, ~6 ms per 1e9 rows).  Left rows
+  //          then lose their position-implied source, so they travel as (source << row_shift | local row).
+  x->row_shift = 32 - x->log_world;
+  const bool staged_ok = x->log_world > 0 && max_left_rows < (1ll << x->row_shift);
+  const bool staged = c->opt_xjoin_mode == 2 ? staged_ok : (c->opt_xjoin_mode == 1 ? false : (staged_ok && x->log_world > 0));
+  if (!staged) x->row_shift = 0;
+  x->sh_log_nb = staged ? 0 : x->log_nb;
+  const long long sb = 1ll << (x->sh_log_nb + x->log_world);         // sub-buckets per rank and side = combined buckets per source
   auto cap_for = [&](int64_t n) {
     const double m = (double)n / (double)sb;                         // rows one source sends to one sub-bucket (hash-uniform keys)
     long long cap = (long long)(m + m / 32.0 + 6.0 * std::sqrt(m + 1.0)) + 256;
@@ -1135,7 +1192,7 @@ int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_c
   PDRS_TRY(pdrs_view_col(c, left_key, &lv));
   PDRS_TRY(pdrs_view_col(c, right_key, &rv));
   if (right_row0 + rv.len > x->total_right) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: right rows beyond total_right_rows");
-  const int ncb = 1 << (x->log_nb + x->log_world);
+  const int ncb = 1 << (x->sh_log_nb + x->log_world);
   DevBuf cur;
   PDRS_TRY(cur.alloc(c, (size_t)(2 * ncb + 8) * 8, true));          // [ncb] right cursors, [ncb] left cursors, [1] overflow
   u64* ovf = cur.as<u64>() + 2 * ncb;
@@ -1153,14 +1210,15 @@ int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_c
       d.rows[r] = reinterpret_cast<uint32_t*>((char*)x->peer[r] + s.rows);
       dc.cnt[r] = reinterpret_cast<u64*>((char*)x->peer[r] + s.cnt);
     }
-    d.log_world = x->log_world; d.me = x->rank; d.row_add = side ? 0u : (uint32_t)right_row0;
+    d.log_world = x->log_world; d.me = x->rank;
+    d.row_add = side ? (x->row_shift ? (uint32_t)x->rank << x->row_shift : 0u) : (uint32_t)right_row0;
     const JKeyCol col{v.data, v.nulls, v.dtype};
     if (v.len > 0) {
       const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (v.len + JQ_TILE - 1) / JQ_TILE));
-      jpart1_kernel<true><<<ctas, JQ_NT, JQ_SMEM, c->stream>>>(col, v.len, x->log_nb, s.cap, cursor, d, ovf);
+      jpart1_kernel<true><<<ctas, JQ_NT, JQ_SMEM, c->stream>>>(col, v.len, x->sh_log_nb, s.cap, cursor, d, ovf);
       c->stats.kernel_launches++;
     }
-    jx_publish_counts_kernel<<<(ncb + 255) / 256, 256, 0, c->stream>>>(cursor, dc, x->log_nb, x->log_world, x->rank, s.cap);
+    jx_publish_counts_kernel<<<(ncb + 255) / 256, 256, 0, c->stream>>>(cursor, dc, x->sh_log_nb, x->log_world, x->rank, s.cap);
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
   }
@@ -1184,7 +1242,7 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   PDRS_CUDA(c, cudaSetDevice(c->device));
   if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
   c->stats.main_kernel_ms = 0; c->stats.total_ms = 0;
-  const long long sb = 1ll << (x->log_nb + x->log_world);
+  const long long sb = 1ll << (x->sh_log_nb + x->log_world);
   char* base = (char*)x->base;
   // rows received per side
   std::vector<u64> hc((size_t)2 * sb);
@@ -1214,9 +1272,29 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   rsrc.cap = x->R.cap; rsrc.cnt = reinterpret_cast<const u64*>(base + x->R.cnt);
   lsrc.pkeys = reinterpret_cast<const u64*>(base + x->L.keys); lsrc.prows = reinterpret_cast<const uint32_t*>(base + x->L.rows);
   lsrc.cap = x->L.cap; lsrc.cnt = reinterpret_cast<const u64*>(base + x->L.cnt);
-  lsrc.row0 = row0.as<long long>(); lsrc.log_srcs = x->log_world;
+  lsrc.row0 = row0.as<long long>(); lsrc.log_srcs = x->log_world; lsrc.row_shift = x->row_shift;
+  long long nr_eff = sb * x->R.cap, nl_eff = sb * x->L.cap;
+  JPart lp, rp;
+  DevBuf lcnt, rcnt;
+  if (x->row_shift && x->log_nb > 1) {
+    // staged mode: the ordinary one-pass radix partition of the single-GPU join, reading the received records
+    for (int side = 0; side < 2; side++) {
+      const XSide& s = side ? x->L : x->R;
+      JSrc& src = side ? lsrc : rsrc;
+      JPart& part = side ? lp : rp;
+      DevBuf& cnt = side ? lcnt : rcnt;
+      const JStaged st{src.pkeys, src.prows, src.cnt, s.cap};
+      long long cap = 0;
+      bool ok = true;
+      PDRS_TRY(jpartition1(c, JKeyCol{}, sb * s.cap, x->log_nb, &part, &cnt, &cap, &ok, &st, side ? nl : nr));
+      if (!ok) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_local: a radix bucket overflowed its padded range (skewed keys)");
+      src.pkeys = part.keys.as<u64>(); src.prows = part.rows.as<uint32_t>(); src.cap = cap; src.cnt = cnt.as<u64>();
+      src.log_nb = c->opt_join_prefetch ? x->log_nb : 0;
+      (side ? nl_eff : nr_eff) = part.n;
+    }
+  }
   int64_t M = 0;
-  PDRS_TRY(jbuild_probe(c, jt, next, fail, rsrc, sb * x->R.cap, lsrc, sb * x->L.cap, nl, true, how, res, &M, [](const char*) {}));
+  PDRS_TRY(jbuild_probe(c, jt, next, fail, rsrc, nr_eff, lsrc, nl_eff, nl, true, how, res, &M, [](const char*) {}));
   c->stats.groupby_algo_used = 2;
   if (c->opt_timing) {
     PDRS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));

@@ -27,10 +27,18 @@ def main():
     lcut = [npr * r // world for r in range(world + 1)]
     rcut = [nb * r // world for r in range(world + 1)]
     dj = DistJoin(ctx, dist)
-    assert dj.setup_fused(max(lcut[i + 1] - lcut[i] for i in range(world)), max(rcut[i + 1] - rcut[i] for i in range(world)), nb), getattr(dj, "fused_error", "")
+    cfg = None
     lc = ctx.upload(pb.Column.int64(pk[lcut[rank]:lcut[rank + 1]], pnull[lcut[rank]:lcut[rank + 1]]))
     rc = ctx.upload(pb.Column.int64(bk[rcut[rank]:rcut[rank + 1]]))
-    for how in (pb.INNER, pb.LEFT, pb.INNER):            # the receive areas are reused call after call
+    # xjoin_mode 1 = fused (rank x radix bucket in one pass), 2 = staged (by rank, then the local radix partition), 0 = auto
+    for mode, log_nb, how in ((1, 3, pb.INNER), (1, 3, pb.LEFT), (2, 3, pb.INNER), (2, 3, pb.LEFT), (0, 0, pb.INNER), (0, 0, pb.INNER)):
+        if getattr(dj, "x", None) is None or (mode, log_nb) != cfg:     # the receive areas are reused call after call
+            if getattr(dj, "x", None) is not None:
+                dj.x.close()
+            ctx.set_option("xjoin_mode", mode)
+            ctx.set_option("join_log_nb", log_nb)
+            assert dj.setup_fused(max(lcut[i + 1] - lcut[i] for i in range(world)), max(rcut[i + 1] - rcut[i] for i in range(world)), nb), getattr(dj, "fused_error", "")
+            cfg = (mode, log_nb)
         j = dj.join_pairs_fused(lc, rc, how, lcut[rank], rcut[rank])
         assert j is not None, getattr(dj, "fused_error", "")
         li, ri = j.indices()

@@ -747,7 +747,7 @@ def test_zipf_multi_key_underestimated_cardinality_retries_fast(ctx, oracle):
 
 
 # ---------------------------------------------------------------- fused partition + shuffle join (pdrs_xjoin_*)
-def _xjoin_simulated(ctx, oracle, world, L, R, how, opt_log_nb=0):
+def _xjoin_simulated(ctx, oracle, world, L, R, how, opt_log_nb=0, mode=0):
     """All `world` ranks live in this process on one GPU: rank r's receive area is handed to the others as a plain
     device pointer (attach_ptrs), so the partition kernel's peer stores, the sub-bucket layout, the count
     publication and the global row numbers are exercised exactly as with CUDA IPC between processes."""
@@ -756,6 +756,7 @@ def _xjoin_simulated(ctx, oracle, world, L, R, how, opt_log_nb=0):
     rcut = [nr * r // world for r in range(world + 1)]
     if opt_log_nb:
         ctx.set_option("join_log_nb", opt_log_nb)
+    ctx.set_option("xjoin_mode", mode)        # 1 = fused (rank x bucket in one pass), 2 = staged (by rank, then the local radix partition)
     xs = [pb.XJoin(ctx, r, world, max(lcut[i + 1] - lcut[i] for i in range(world)), max(rcut[i + 1] - rcut[i] for i in range(world)), nr)
           for r in range(world)]
     try:
@@ -781,19 +782,21 @@ def _xjoin_simulated(ctx, oracle, world, L, R, how, opt_log_nb=0):
             x.close()
         if opt_log_nb:
             ctx.set_option("join_log_nb", 0)
+        ctx.set_option("xjoin_mode", 0)
     wl, wr = oracle.join(L.cpu(oracle), R.cpu(oracle), how)
     assert sorted(got) == sorted(zip(wl.tolist(), wr.tolist())), (world, how)
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("world", [1, 2, 8])
 @pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
-def test_xjoin_fused_shuffle_unique_build(ctx, oracle, world, how):
+def test_xjoin_fused_shuffle_unique_build(ctx, oracle, world, how, mode):
     rng = np.random.default_rng(21 + world)
     nb, npr = 40_000, 300_001
     bk = rng.permutation(2 * nb)[:nb].astype(np.int64) * 7919 - 100_000          # unique build keys, ~50% hits
     pk = (rng.integers(0, 2 * nb, npr) * 7919 - 100_000).astype(np.int64)
-    _xjoin_simulated(ctx, oracle, world, Spec(pb.I64, pk), Spec(pb.I64, bk), how, opt_log_nb=3)
+    _xjoin_simulated(ctx, oracle, world, Spec(pb.I64, pk), Spec(pb.I64, bk), how, opt_log_nb=3, mode=mode)
 
 
 @pytest.mark.gpu
@@ -808,8 +811,10 @@ def test_xjoin_fused_shuffle_duplicates_nulls_and_extremes(ctx, oracle, world):
     lk[::97] = -1
     rk[::53] = -1
     lk[5], rk[7] = np.iinfo(np.int64).min, np.iinfo(np.int64).min
+    ln, rn = rng.random(nl) < 0.02, rng.random(nr) < 0.02
     for how in (pb.INNER, pb.LEFT):
-        _xjoin_simulated(ctx, oracle, world, Spec(pb.I64, lk, nulls=rng.random(nl) < 0.02), Spec(pb.I64, rk, nulls=rng.random(nr) < 0.02), how)
+        for mode, log_nb in ((1, 0), (2, 0), (2, 2)):
+            _xjoin_simulated(ctx, oracle, world, Spec(pb.I64, lk, nulls=ln), Spec(pb.I64, rk, nulls=rn), how, opt_log_nb=log_nb, mode=mode)
 
 
 @pytest.mark.gpu
