@@ -329,6 +329,8 @@ def dist_join(ctx, pb, dist, rank, world, n_probe, peaks):
     import torch
     from pandrs_b200.dist import DistJoin
     d = dist if dist is not None else _OneRank
+    if world > 2:      # staged exchange: left rows travel as (source rank << (32 - log2 world) | local row)
+        n_probe = min(n_probe, (1 << (32 - (world - 1).bit_length())) // 100_000_000 * 100_000_000 or n_probe)
     nb_, np_ = n_probe // 10, n_probe
     build = ctx.synth_join_keys(nb_, unique=True, row0=rank * nb_)
     probe = ctx.synth_join_keys(np_, domain=2 * nb_ * world, row0=rank * np_)

@@ -50,7 +50,7 @@ struct GpIn {
 template <bool FROM_COLS, bool GENERIC = false>
 __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr, int local_bits, long long cap_out, u64* __restrict__ cursor,
                                                           u64* __restrict__ out_keys, u64* __restrict__ out_vals, uint8_t* __restrict__ out_flags,
-                                                          u64* __restrict__ overflow) {
+                                                          u64* __restrict__ overflow, u64* __restrict__ side = nullptr, long long side_base = 0, long long side_cap = 0) {
   extern __shared__ __align__(16) unsigned char gsm[];
   ulonglong2* st_kv = reinterpret_cast<ulonglong2*>(gsm);      // [GP_TILE] staged (key, value)
   uint32_t* st_dst = reinterpret_cast<uint32_t*>(st_kv + GP_TILE);   // [GP_TILE] output position of the staged row (< 2^31), bit 31 = value is NULL
@@ -127,8 +127,18 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
         // output bucket: level 1 = the local bucket; level 2 = (level-1 bucket of this CTA's rows) * 2^bits + local bucket
         const u64 q = FROM_COLS ? (u64)tid : (((u64)blockIdx.y << local_bits) | (u64)tid);
         const u64 at = atomicAdd(&cursor[q], (u64)c);
-        if (at + c > (u64)cap_out) atomicAdd(overflow, 1ull);          // the caller discards this partitioning
-        else g = (uint32_t)(q * (u64)cap_out + at);                   // < 2^31 (checked by the caller)
+        if (at + c > (u64)cap_out) {
+          // The bucket is full (hot keys).  Level 1 parks the run in the side area behind the buckets - the caller
+          // aggregates it as extra partitions; side[0] = its cursor, side[1 + q] = where the rows of bucket q end (the
+          // one reservation that straddles the end of the range records it; later ones start beyond the range).
+          bool placed = false;
+          if (side) {
+            if (at < (u64)cap_out) side[1 + q] = at;
+            const u64 at2 = atomicAdd(&side[0], (u64)c);
+            if (at2 + c <= (u64)side_cap) { g = (uint32_t)((u64)side_base + at2); placed = true; }
+          }
+          if (!placed) atomicAdd(overflow, 1ull);                      // the caller discards this partitioning
+        } else g = (uint32_t)(q * (u64)cap_out + at);                 // < 2^31 (checked by the caller)
       }
       __syncthreads();
       uint32_t ws = lane < GP_NT / 32 ? wsum[lane] : 0u;
@@ -164,6 +174,16 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
   }
 }
 
+// final row counts of the partitions: hash buckets (clamped to where their rows end) followed by the chunks of the side area
+__global__ void gp_counts_kernel(const u64* __restrict__ cursor, const u64* __restrict__ side, int nb, long long cap, int nside, u64* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nb) { u64 c = cursor[q]; if (c > (u64)cap) c = min((u64)cap, side[1 + q]); out[q] = c; }
+  else if (q < nb + nside) {
+    const long long total = (long long)side[0], j = q - nb;
+    out[q] = (u64)max(0ll, min(cap, total - j * cap));
+  }
+}
+
 long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 }  // namespace
@@ -194,8 +214,15 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   };
   const long long cap1 = padded(nb1, 65536);
   const long long cap2 = bits2 ? padded(nparts, 8192) : cap1;
-  if ((unsigned long long)nb1 * cap1 >= (1ull << 31) || (unsigned long long)nparts * cap2 >= (1ull << 31)) return PDRS_ERR_UNSUPPORTED;   // 31-bit output positions
-  const size_t need = (size_t)nb1 * cap1 * 17 + (bits2 ? (size_t)nparts * cap2 * 17 : 0);
+  // single level: a side area of up to n / 4 rows behind the buckets takes the runs of buckets that fill up (hot keys of
+  // a skewed distribution); it is aggregated as `nside` more partitions of cap1 rows
+  long long nside = 0;
+  if (!bits2 && c->opt_part_side != 0) {
+    nside = std::max<long long>(1, (n / 4 + cap1 - 1) / cap1);
+    while (nside > 0 && (unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31)) nside--;
+  }
+  if ((unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31) || (unsigned long long)nparts * cap2 >= (1ull << 31)) return PDRS_ERR_UNSUPPORTED;   // 31-bit output positions
+  const size_t need = (size_t)(nb1 + nside) * cap1 * 17 + (bits2 ? (size_t)nparts * cap2 * 17 : 0);
   size_t free_b = 0, total_b = 0;
   PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   if (need + (2ull << 30) > free_b) return PDRS_ERR_UNSUPPORTED;
@@ -205,15 +232,23 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   const long long ts_cap = 1023;
   if (!gb_tsort_geometry(ts_cap, false, c->smem_optin, 512, &ts_nt, &ts_gpt, &ts_slots, &ts_smem)) return PDRS_ERR_UNSUPPORTED;
 
-  DevBuf cnt, k1, v1, f1, k2, v2, f2;
+  DevBuf cnt, k1, v1, f1, k2, v2, f2, side, pcnt;
   const bool has_flags = gp.vnull != nullptr && !gp.compat_nulls;
   PDRS_TRY(cnt.alloc(c, (size_t)(nb1 + nparts + 8) * 8, true));     // [nb1] level-1 cursors, [nparts] level-2 cursors, [1] overflow
   u64* cur1 = cnt.as<u64>();
   u64* cur2 = cur1 + nb1;
   u64* ovf = cur2 + nparts;
-  PDRS_TRY(k1.alloc(c, (size_t)nb1 * cap1 * 8));
-  PDRS_TRY(v1.alloc(c, (size_t)nb1 * cap1 * 8));
-  if (has_flags) PDRS_TRY(f1.alloc(c, (size_t)nb1 * cap1 + 64));
+  PDRS_TRY(k1.alloc(c, (size_t)(nb1 + nside) * cap1 * 8));
+  PDRS_TRY(v1.alloc(c, (size_t)(nb1 + nside) * cap1 * 8));
+  if (has_flags) PDRS_TRY(f1.alloc(c, (size_t)(nb1 + nside) * cap1 + 64));
+  if (nside) {
+    PDRS_TRY(side.alloc(c, (size_t)(nb1 + 2) * 8));
+    PDRS_CUDA(c, cudaMemsetAsync(side.p, 0xFF, (size_t)(nb1 + 2) * 8, c->stream));     // bucket ends: none recorded
+    PDRS_CUDA(c, cudaMemsetAsync(side.p, 0, 8, c->stream));                             // side cursor
+    PDRS_TRY(pcnt.alloc(c, (size_t)(nb1 + nside + 2) * 8, true));
+  }
+  u64* sidep = nside ? side.as<u64>() : nullptr;
+  const long long side_base = nb1 * cap1, side_cap = nside * cap1;
   const size_t smem = (size_t)GP_TILE * 20 + (288 + 512) * 4;
   static bool attr_set = false;
   if (!attr_set) {
@@ -228,10 +263,11 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   in.fbits = gp.fbits; in.fnull = gp.fnull; in.n = n; in.compat_nulls = gp.compat_nulls;
   const int ctas1 = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + GP_TILE - 1) / GP_TILE));
   in.ks = gp.ks;
-  if (generic) gp_part_kernel<true, true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf);
-  else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf);
+  if (generic) gp_part_kernel<true, true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
+  else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
+  if (nside) { gp_counts_kernel<<<(int)((nb1 + nside + 255) / 256), 256, 0, c->stream>>>(cur1, sidep, (int)nb1, cap1, (int)nside, pcnt.as<u64>()); c->stats.kernel_launches++; }
   c->stats.kernel_launches++;
-  const u64 *pk = k1.as<u64>(), *pv = v1.as<u64>(), *pc = cur1;
+  const u64 *pk = k1.as<u64>(), *pv = v1.as<u64>(), *pc = nside ? pcnt.as<u64>() : cur1;
   const uint8_t* pf = has_flags ? f1.as<uint8_t>() : nullptr;
   long long pcap = cap1;
   if (bits2) {
@@ -254,9 +290,11 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   GbParams tp = gp;
   tp.ts_generic = 0;               // the partitions hold packed key words
   tp.part_keys = pk; tp.part_vals = pv; tp.part_flags = pf; tp.part_cnt = pc; tp.part_cap = pcap; tp.part_bits = bits;
+  const long long nparts_all = nparts + nside;
+  tp.part_n = (int)nparts_all;
   {   // work items: ~16 chunks per CTA, each chunk a run of whole tiles of one partition
     const long long tiles_cap = pcap / T, want = 16ll * c->sm_count;
-    long long cpp = std::max<long long>(1, std::min<long long>(tiles_cap, (want + nparts - 1) / nparts));
+    long long cpp = std::max<long long>(1, std::min<long long>(tiles_cap, (want + nparts_all - 1) / nparts_all));
     tp.part_chunk_tiles = (int)((tiles_cap + cpp - 1) / cpp);
     tp.part_cpp = (int)((tiles_cap + tp.part_chunk_tiles - 1) / tp.part_chunk_tiles);
   }
@@ -267,7 +305,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   int lg = 0;
   while ((1 << lg) < ts_slots) lg++;
   tp.sh_log_slots = lg;
-  PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts * tp.part_cpp), ts_smem, c->stream));
+  PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts_all * tp.part_cpp), ts_smem, c->stream));
   c->stats.kernel_launches++;
   if (c->opt_timing) {
     PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));

@@ -88,7 +88,7 @@ __device__ __forceinline__ TsItem ts_first_item(const GbParams& p) {
     it.valid = it.base < p.n ? (int)min((long long)TT, p.n - it.base) : 0;
     return it;
   }
-  const long long nchunks = (1ll << p.part_bits) * p.part_cpp;
+  const long long nchunks = (long long)p.part_n * p.part_cpp;
   for (; it.part < nchunks; it.part += gridDim.x) {
     long long pb, c, t0, t1;
     if (ts_chunk_range<TT>(p, it.part, &pb, &c, &t0, &t1)) { it.base = pb + t0 * TT; it.valid = (int)min((long long)TT, c - t0 * TT); it.last = t0 + 1 == t1; return it; }
@@ -110,7 +110,7 @@ __device__ __forceinline__ TsItem ts_next_item(const GbParams& p, const TsItem& 
     it.base = cur.base + TT; it.valid = (int)min((long long)TT, c - t * TT); it.last = t + 1 == t1;
     return it;
   }
-  const long long nchunks = (1ll << p.part_bits) * p.part_cpp;
+  const long long nchunks = (long long)p.part_n * p.part_cpp;
   it.valid = 0; it.last = 0;
   for (it.part = cur.part + gridDim.x; it.part < nchunks; it.part += gridDim.x) {
     if (ts_chunk_range<TT>(p, it.part, &pb, &c, &t0, &t1)) { it.base = pb + t0 * TT; it.valid = (int)min((long long)TT, c - t0 * TT); it.last = t0 + 1 == t1; return it; }

@@ -445,6 +445,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   u64 cn[CNT_N + 1] = {0};
   bool radix_used = false, restart = false;
   bool part_ok = c->opt_part != 0 && c->opts.groupby_algo == PDRS_GB_AUTO;
+  bool ts_skew = false;          // the tile-sort kernel runs as the skew fallback: its spills go to a side buffer + a second pass
   (void)radix_used;
   for (int attempt = 0;; attempt++) {
     if (attempt > 6) return pdrs_fail(c, PDRS_ERR_OOM, "groupby: hash table kept overflowing after %d retries", attempt);
@@ -490,6 +491,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           if (skewed && c->opt_tsort != 0 && n >= 4 * gb_tsort_tile_rows() && n < (1ll << 38)) {
             ts_dense = false; ts_cap = 2047;
             ts_fit = gb_tsort_geometry(ts_cap, false, c->smem_optin, (int)c->opt_tsort_threads, &ts_nt, &ts_gpt, &ts_slots, &ts_smem);
+            ts_skew = ts_fit;
           }
           if (dirty || i > 0) { restart = true; break; }     // the table already holds counts of this attempt: start over without this path
         }
@@ -502,6 +504,18 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           if (rs != PDRS_ERR_UNSUPPORTED) return rs;
         }
         const bool use_ts = ts_fit && algo != PDRS_GB_GLOBAL && passes[i].val >= 0;
+        DevBuf spill_k, spill_v;
+        if (use_ts && ts_skew && c->opt_spillbuf != 0) {
+          const long long cap = std::max<long long>(n / 3, 1 << 20);
+          size_t free_b = 0, total_b = 0;
+          PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+          if ((size_t)cap * 16 + (4ull << 30) < free_b) {
+            PDRS_TRY(spill_k.alloc(c, (size_t)cap * 8));
+            PDRS_TRY(spill_v.alloc(c, (size_t)cap * 8));
+            gp.gt.spill_k = spill_k.as<u64>(); gp.gt.spill_v = spill_v.as<u64>(); gp.gt.spill_cap = cap;
+            PDRS_CUDA(c, cudaMemsetAsync(gp.gt.counters + CNT_SPILLBUF, 0, 8, c->stream));
+          }
+        }
         if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
         if (use_ts) {
           gp.sh_cap = (int)ts_cap; gp.sh_slots = ts_slots; gp.sh_log_slots = ts_slots ? ilog2(ts_slots) : 0;
@@ -526,6 +540,40 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           float ms = 0;
           PDRS_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
           c->stats.main_kernel_ms += ms;
+        }
+        if (gp.gt.spill_k) {
+          // second pass of the skew fallback: the side buffer holds the rows of the keys outside the per-CTA hot sets
+          // as (key word, value) - an Int64-keyed groupby into the SAME table; without the hot keys the hash
+          // partitions are balanced, so the partitioned path applies (global-table kernel when it does not)
+          PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 9, gp.gt.counters + CNT_SPILLBUF, 8, cudaMemcpyDeviceToHost, c->stream));
+          PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+          const long long ns = std::min<long long>((long long)c->pinned_scalars[9], gp.gt.spill_cap);
+          if (ns > 0) {
+            GbParams sp = gp;
+            memset(&sp.ks, 0, sizeof(sp.ks));
+            sp.ks.nkeys = 1; sp.ks.nwords = 1; sp.ks.single_null = 1;
+            sp.ks.c[0].data = gp.gt.spill_k; sp.ks.c[0].dtype = PDRS_I64; sp.ks.c[0].bits = 64; sp.ks.c[0].nword = -1; sp.ks.c[0].null_alias = -1;
+            sp.val = gp.gt.spill_v; sp.vnull = nullptr; sp.fbits = nullptr; sp.fnull = nullptr; sp.compat_nulls = 0; sp.n = ns;
+            sp.gt.spill_k = nullptr; sp.gt.spill_v = nullptr; sp.gt.spill_cap = 0;
+            sp.ts_generic = 0;
+            float ms = 0;
+            bool dirty = false, skewed = false;
+            int32_t rs = gb_part_pass(c, sp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed);
+            if (rs != PDRS_OK && rs != PDRS_ERR_UNSUPPORTED) return rs;
+            if (rs == PDRS_ERR_UNSUPPORTED) {
+              GbCfg cfg{1, 0, passes[i].is_int, passes[i].flags, 8, 0};
+              cfg.ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (ns + 1023) / 1024));
+              if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+              PDRS_CUDA(c, launch_global(0, cfg, sp, c->stream));
+              c->stats.kernel_launches++;
+              if (c->opt_timing) {
+                PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+                PDRS_CUDA(c, cudaEventSynchronize(c->ev_b));
+                PDRS_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+              }
+            }
+            c->stats.main_kernel_ms += ms;
+          }
         }
       }
     }

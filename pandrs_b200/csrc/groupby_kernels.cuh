@@ -37,7 +37,8 @@ static constexpr u64 GB_CNT_MASK = GB_FULL - 1;
 static constexpr u64 GB_PIV_X = 0x7FF8C0DEC0DE0001ull;   // pivot bits are stored XOR this (0 = unset)
 static constexpr u64 GB_SIGN = 1ull << 63;
 
-enum { CNT_NGROUPS = 0, CNT_OVERFLOW = 1, CNT_SPILLED = 2, CNT_OUT = 3, CNT_SPIN_FAIL = 4, CNT_KMINC = 5 /* ~(min key ^ SIGN) */, CNT_KMAX = 6 /* max key ^ SIGN */, CNT_N = 8 };
+enum { CNT_NGROUPS = 0, CNT_OVERFLOW = 1, CNT_SPILLED = 2, CNT_OUT = 3, CNT_SPIN_FAIL = 4, CNT_KMINC = 5 /* ~(min key ^ SIGN) */, CNT_KMAX = 6 /* max key ^ SIGN */,
+       CNT_SPILLBUF = 7 /* rows appended to the spill side buffer */, CNT_N = 8 };
 
 struct KeyColDev {
   const void* data;
@@ -66,6 +67,10 @@ struct GTable {
   int shift;                     // 64 - log2(slots): slot = hash >> shift, so that the radix buckets (top hash bits) own contiguous regions
   long long slots;
   u64* counters;                 // CNT_*
+  // Skew fallback of the tile-sort kernel (one-word keys): rows whose key got no register accumulator are appended
+  // here as (key word, value bits) instead of being applied to the table with ~6 atomics each; the host aggregates
+  // the buffer - the tail of the distribution, hot keys removed - in a second pass.  NULL when unused.
+  u64* spill_k; u64* spill_v; long long spill_cap;
 };
 
 struct GbParams {
@@ -84,6 +89,7 @@ struct GbParams {
   // tile-sort kernel over hash-partitioned rows (gb_tsort.cu): partition q owns rows [q * part_cap, q * part_cap + part_cnt[q])
   // of part_keys / part_vals (no NULLs, filter already applied); part_bits = log2(number of partitions)
   const u64* part_keys; const u64* part_vals; const uint8_t* part_flags /* 1 = value is NULL; may be NULL */; const u64* part_cnt; long long part_cap; int part_bits;
+  int part_n;                       // number of partitions (2^part_bits hash partitions + the chunks of the overflow side area)
   int part_cpp, part_chunk_tiles;   // work items: every partition is cut into part_cpp chunks of part_chunk_tiles tiles (one flush per chunk)
   int ts_heavy;                     // tile-sort kernel: segments longer than this are reduced by the whole warp
   int ts_team;                      // tile-sort kernel: use the variant with the team-of-8 reduce
@@ -479,6 +485,17 @@ __device__ __forceinline__ void gb_load_unit(const GbParams& p, long long base, 
 // Rare paths live in __noinline__ functions so that the unrolled hot loop stays inside the instruction cache.
 template <int NW, typename VT, int FLAGS>
 __device__ __noinline__ void gb_spill_rows(const GTable gt, u64 w0, u64 w1, u64 w2, bool spill, bool count_row, bool valid, VT v) {
+  if (NW == 1 && gt.spill_k) {     // rows with a value go to the side buffer (warp-aggregated append); NULL values only count: below
+    const bool tobuf = spill && valid;
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, tobuf);
+    if (m) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      u64 at = 0;
+      if (lane == leader) { at = atomicAdd(&gt.counters[CNT_SPILLBUF], (u64)__popc(m)); atomicAdd(&gt.counters[CNT_SPILLED], (u64)__popc(m)); }
+      at = __shfl_sync(0xFFFFFFFFu, at, leader) + (u64)__popc(m & ((1u << lane) - 1u));
+      if (tobuf && at < (u64)gt.spill_cap) { gt.spill_k[at] = w0; gt.spill_v[at] = ValTraits<VT>::to_bits(v); spill = false; }
+    }
+  }
   u64 w[NW];
   w[0] = w0;
   if (NW > 1) w[1] = w1;
