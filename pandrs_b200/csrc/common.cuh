@@ -39,6 +39,7 @@ struct pdrs_ctx {
   int64_t opt_join_slots_mult = 0;     // table slots per build row (0 = default 2)
   int64_t opt_join_prefetch = 1;       // stream the next radix bucket's table region into L2 ahead of its first probes
   int64_t opt_join_emit = 0;           // 0 = auto (single-pass probe + emit when the build keys are unique), 2 = always count / scan / write
+  int64_t opt_key_compress = 1;        // pack multi-key tuples by value range when that brings them down to one 64-bit word
   int64_t opt_part_side = 1;           // partitioned groupby: runs of full buckets (hot keys) go to a side area that is aggregated as extra partitions
   int64_t opt_spillbuf = 1;            // skew fallback of the tile-sort kernel: spilled rows go to a side buffer + second pass (0: straight to the global table)
   int64_t opt_xjoin_mode = 0;          // exchange join: 0 = auto, 1 = fused (rank x radix bucket in one pass), 2 = staged (shuffle by rank, local radix partition)

@@ -122,6 +122,7 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "xjoin_mode")) c->opt_xjoin_mode = value;
   else if (!strcmp(name, "spillbuf")) c->opt_spillbuf = value;
   else if (!strcmp(name, "part_side")) c->opt_part_side = value;
+  else if (!strcmp(name, "key_compress")) c->opt_key_compress = value;
   else if (!strcmp(name, "join_slots_mult")) c->opt_join_slots_mult = value;
   else if (!strcmp(name, "timing")) c->opt_timing = value;
   else if (!strcmp(name, "dense")) c->opt_dense = value;

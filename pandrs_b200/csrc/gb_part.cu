@@ -25,6 +25,7 @@
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
 cudaError_t gb_tsort_launch(const GbParams& p, int is_int, int flags, int nt, int gpt, int ctas, size_t smem, cudaStream_t s);
+int32_t gb_estimate_groups_i64(pdrs_ctx* c, const u64* keys, long long n, long long sample_rows, long long* est_out);   // groupby.cu
 
 namespace {
 
@@ -190,9 +191,16 @@ long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 // One aggregation pass through the partitioned path.  Returns PDRS_ERR_UNSUPPORTED when it does not apply or a
 // bucket overflowed (the caller then takes the global-table path; *dirty = the table was touched: never, today).
-int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed) {
+// est_refined (may be NULL): the cardinality estimate of the caller comes from 2^18 rows spread over the whole input and is
+// far too low for heavy-tailed keys (Zipf tuples: most sampled keys are hot ones).  After level 1 the first bucket
+// holds ALL rows of 1 / 2^bits1 of the key space, so a sample of it sees 2^bits1 times more of that slice: when
+// groups(bucket 0) x 2^bits1 exceeds the estimate by more than 1.5x the pass stops, *est_refined is set, and the
+// caller starts over with the better estimate (right-sized table, right number of partitions).
+int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed,
+                     long long* est_refined) {
   *dirty = false;
   *skewed = false;
+  if (est_refined) *est_refined = 0;
   const long long n = gp.n;
   const long long T = gb_tsort_tile_rows();
   const bool generic = !(gp.ks.nkeys == 1 && gp.ks.c[0].dtype == PDRS_I64);
@@ -203,7 +211,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   // partitions are fine: the aggregation kernel cuts every partition into chunks of tiles, one work item each.
   int bits = 1;
   while (bits < 16 && (est_groups >> bits) > 600) bits++;
-  if ((est_groups >> bits) > 700 || (n >> bits) < 2 * T) return PDRS_ERR_UNSUPPORTED;
+  if ((est_groups >> bits) > 700 || (n >> bits) < T / 2) return PDRS_ERR_UNSUPPORTED;
   const int bits1 = bits <= 8 ? bits : (bits + 1) / 2, bits2 = bits - bits1;
   const long long nb1 = 1ll << bits1, nparts = 1ll << bits;
   // a bucket holds whole groups: with m groups per bucket its size varies by ~1/sqrt(m) -> 6 sigma of slack
@@ -267,6 +275,18 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
   if (nside) { gp_counts_kernel<<<(int)((nb1 + nside + 255) / 256), 256, 0, c->stream>>>(cur1, sidep, (int)nb1, cap1, (int)nside, pcnt.as<u64>()); c->stats.kernel_launches++; }
   c->stats.kernel_launches++;
+  if (est_refined && nb1 >= 4) {
+    PDRS_CUDA(c, cudaGetLastError());
+    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, ovf, 8, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 9, cur1, 8, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->pinned_scalars[8] != 0) { *skewed = true; return PDRS_ERR_UNSUPPORTED; }
+    const long long cnt0 = std::min<long long>((long long)c->pinned_scalars[9], cap1);
+    long long est0 = 0;
+    PDRS_TRY(gb_estimate_groups_i64(c, k1.as<u64>(), cnt0, 1 << 20, &est0));
+    const long long refined = std::min<long long>(est0 * nb1, n);
+    if (refined > est_groups + est_groups / 2) { *est_refined = refined; return PDRS_ERR_UNSUPPORTED; }
+  }
   const u64 *pk = k1.as<u64>(), *pv = v1.as<u64>(), *pc = nside ? pcnt.as<u64>() : cur1;
   const uint8_t* pf = has_flags ? f1.as<uint8_t>() : nullptr;
   long long pcap = cap1;

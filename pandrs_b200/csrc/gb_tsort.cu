@@ -160,6 +160,7 @@ __device__ __forceinline__ void ts_load(const GbParams& p, const TsItem& it, int
           case PDRS_I64: case PDRS_F64: {
             const u64* d = reinterpret_cast<const u64*>(c.data) + row0;
             if (in1) { const ulonglong2 t = ld_stream_v2(d); v0 = t.x; v1 = t.y; } else if (in0) v0 = __ldg(d);
+            if (c.dtype == PDRS_I64) { if (in0) v0 -= (u64)c.offset; if (in1) v1 -= (u64)c.offset; }      // range-compressed tuples (offset 0 otherwise)
             if (c.dtype == PDRS_F64) {       // all NaNs print "NaN"
               if (__longlong_as_double((long long)v0) != __longlong_as_double((long long)v0)) v0 = 0x7FF8000000000000ull;
               if (__longlong_as_double((long long)v1) != __longlong_as_double((long long)v1)) v1 = 0x7FF8000000000000ull;
@@ -169,7 +170,11 @@ __device__ __forceinline__ void ts_load(const GbParams& p, const TsItem& it, int
           case PDRS_I32: case PDRS_DICT_U32: {
             const uint32_t* d = reinterpret_cast<const uint32_t*>(c.data) + row0;
             if (in1) { const uint2 t = __ldg(reinterpret_cast<const uint2*>(d)); v0 = t.x; v1 = t.y; } else if (in0) v0 = __ldg(d);
-            if (c.dtype == PDRS_DICT_U32) { if ((long long)v0 == c.null_alias) n0 = true; if ((long long)v1 == c.null_alias) n1 = true; }
+            if (c.dtype == PDRS_DICT_U32) { if ((long long)v0 == c.null_alias) n0 = true; if ((long long)v1 == c.null_alias) n1 = true; if (in0) v0 -= (u64)c.offset; if (in1) v1 -= (u64)c.offset; }
+            else {
+              if (in0) v0 = ((u64)(long long)(int)(uint32_t)v0 - (u64)c.offset) & 0xFFFFFFFFull;
+              if (in1) v1 = ((u64)(long long)(int)(uint32_t)v1 - (u64)c.offset) & 0xFFFFFFFFull;
+            }
             break;
           }
           default: {                           // PDRS_BOOL_BITS
@@ -794,7 +799,7 @@ cudaError_t ts_launch5(const GbParams& p, int ctas, size_t smem, cudaStream_t s)
   if (p.part_keys) k = gb_tsort_kernel<NT, VT, FLAGS, GPT, 2, true, TEAM>;
   else if (generic) {
     bool pack32 = p.ks.nkeys <= 2;
-    for (int i = 0; i < p.ks.nkeys; i++) pack32 = pack32 && !p.ks.c[i].nulls && (p.ks.c[i].dtype == PDRS_I32 || p.ks.c[i].dtype == PDRS_DICT_U32);
+    for (int i = 0; i < p.ks.nkeys; i++) pack32 = pack32 && !p.ks.c[i].nulls && (p.ks.c[i].dtype == PDRS_I32 || p.ks.c[i].dtype == PDRS_DICT_U32) && p.ks.c[i].offset == 0 && p.ks.c[i].bits == 32;
     if (pack32) k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, true, TEAM> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 4, false, TEAM>;
     else k = plain ? gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, true, TEAM> : gb_tsort_kernel<NT, VT, FLAGS, GPT, 3, false, TEAM>;
   }

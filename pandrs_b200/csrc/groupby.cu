@@ -89,7 +89,7 @@ __global__ void gb_finalize_kernel(const FinParams p) {
       bool isnull = nullgroup;
       if (!nullgroup && c.nword >= 0) isnull = (w[c.nword] >> c.nshift) & 1;
       u64 v = 0;
-      if (!isnull) { v = w[c.word] >> c.shift; if (c.bits < 64) v &= (1ull << c.bits) - 1ull; }
+      if (!isnull) { v = w[c.word] >> c.shift; if (c.bits < 64) v &= (1ull << c.bits) - 1ull; v += (u64)c.offset; }
       switch (c.dtype) {
         case PDRS_I64: case PDRS_F64: reinterpret_cast<u64*>(p.key_out[k])[o] = v; break;
         case PDRS_I32: case PDRS_DICT_U32: reinterpret_cast<uint32_t*>(p.key_out[k])[o] = (uint32_t)v; break;
@@ -167,6 +167,80 @@ static int key_out_bytes(int dtype) {
 }
 
 // ---------------------------------------------------------------- key layout
+// Smallest and largest value of every integer key column (signed; dictionary ids as non-negative numbers; values under
+// NULL bits are included, which can only widen the range).  out[2 k] = min, out[2 k + 1] = max, pre-set to +max / -max.
+__global__ void gb_key_range_kernel(const KeySpec ks, long long n, long long* __restrict__ out) {
+  long long mn[PDRS_MAX_KEYS], mx[PDRS_MAX_KEYS];
+  for (int k = 0; k < PDRS_MAX_KEYS; k++) { mn[k] = 0x7FFFFFFFFFFFFFFFll; mx[k] = -0x7FFFFFFFFFFFFFFFll - 1; }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    for (int k = 0; k < ks.nkeys; k++) {
+      long long v;
+      switch (ks.c[k].dtype) {
+        case PDRS_I64: v = __ldcs((const long long*)ks.c[k].data + i); break;
+        case PDRS_I32: v = (long long)__ldcs((const int*)ks.c[k].data + i); break;
+        case PDRS_DICT_U32: v = (long long)__ldcs((const uint32_t*)ks.c[k].data + i); break;
+        default: continue;
+      }
+      mn[k] = min(mn[k], v); mx[k] = max(mx[k], v);
+    }
+  }
+  for (int k = 0; k < ks.nkeys; k++) {
+    for (int d = 16; d; d >>= 1) { mn[k] = min(mn[k], __shfl_xor_sync(0xFFFFFFFFu, mn[k], d)); mx[k] = max(mx[k], __shfl_xor_sync(0xFFFFFFFFu, mx[k], d)); }
+    if ((threadIdx.x & 31) == 0) { atomicMin(out + 2 * k, mn[k]); atomicMax(out + 2 * k + 1, mx[k]); }
+  }
+}
+
+// Multi-key tuples that need more than one 64-bit word in their natural widths (an Int64 part takes a whole word) but
+// whose VALUE RANGES fit one word together - (i32, i64) ids, (returnflag, linestatus, day) ... - are packed as
+// (value - column minimum) in ceil(log2(range)) bits each.  One word = the tile-sort / partitioned kernels instead of
+// the global table.  Costs one extra read of the key columns; exact ranges, so no row can fall outside its field.
+// Used for pdrs_groupby_agg / _partial only: hashes that must agree between ranks (pdrs_hash_partition) and the merge of
+// partial states keep the natural layout.
+static int32_t compress_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, long long n, KeySpec* ks) {
+  if (nkeys < 2 || ks->nwords < 2 || n < (1 << 16) || c->opt_key_compress == 0) return PDRS_OK;
+  for (int k = 0; k < nkeys; k++) if (kv[k].dtype == PDRS_F64) return PDRS_OK;
+  DevBuf rng;
+  PDRS_TRY(rng.alloc(c, 2 * PDRS_MAX_KEYS * 8));
+  long long init[2 * PDRS_MAX_KEYS];
+  for (int k = 0; k < PDRS_MAX_KEYS; k++) { init[2 * k] = 0x7FFFFFFFFFFFFFFFll; init[2 * k + 1] = -0x7FFFFFFFFFFFFFFFll - 1; }
+  PDRS_CUDA(c, cudaMemcpyAsync(rng.p, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+  gb_key_range_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(*ks, n, rng.as<long long>());
+  c->stats.kernel_launches++;
+  PDRS_CUDA(c, cudaGetLastError());
+  long long h[2 * PDRS_MAX_KEYS];
+  PDRS_CUDA(c, cudaMemcpyAsync(h, rng.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  int bits[PDRS_MAX_KEYS], total = 0;
+  for (int k = 0; k < nkeys; k++) {
+    if (kv[k].dtype == PDRS_BOOL_BITS) bits[k] = 1;
+    else {
+      const unsigned long long range = (unsigned long long)h[2 * k + 1] - (unsigned long long)h[2 * k];     // max - min, exact in 64 bits
+      if (h[2 * k + 1] < h[2 * k]) return PDRS_OK;
+      int b = 1;
+      while (b < 64 && (range >> b) != 0) b++;
+      const int natural = kv[k].dtype == PDRS_I64 ? 64 : 32;
+      bits[k] = std::min(b, natural);
+    }
+    total += bits[k] + ((kv[k].nulls || (kv[k].dtype == PDRS_DICT_U32 && kv[k].null_alias >= 0)) ? 1 : 0);
+  }
+  if (total > 64) return PDRS_OK;
+  int used = 0;
+  for (int k = 0; k < nkeys; k++) {
+    KeyColDev& d = ks->c[k];
+    d.word = 0; d.shift = used; d.bits = bits[k]; used += bits[k];
+    const int natural = kv[k].dtype == PDRS_I64 ? 64 : (kv[k].dtype == PDRS_BOOL_BITS ? 1 : 32);
+    d.offset = (kv[k].dtype == PDRS_BOOL_BITS || bits[k] == natural) ? 0 : h[2 * k];
+    if (kv[k].dtype == PDRS_DICT_U32 && d.null_alias >= 0 && bits[k] != natural) d.offset = h[2 * k];
+  }
+  for (int k = 0; k < nkeys; k++) {
+    KeyColDev& d = ks->c[k];
+    d.nword = -1; d.nshift = 0;
+    if (kv[k].nulls || (kv[k].dtype == PDRS_DICT_U32 && kv[k].null_alias >= 0)) { d.nword = 0; d.nshift = used++; }
+  }
+  ks->nwords = 1;
+  return PDRS_OK;
+}
+
 int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* ks) {
   memset(ks, 0, sizeof(*ks));
   ks->nkeys = nkeys;
@@ -209,7 +283,8 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
 }
 
 int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, float* kernel_ms);   // gb_radix.cu
-int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed);   // gb_part.cu
+int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed,
+                     long long* est_refined);   // gb_part.cu
 // gb_tsort.cu
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
@@ -289,6 +364,30 @@ static double invert_distinct(double d, double s) {
   return std::sqrt(lo * hi);
 }
 
+// Estimated number of distinct values among n Int64 keys on the device, from blocks of 256 consecutive rows spread over
+// the array (all rows when n <= sample_rows: then the count is exact).
+int32_t gb_estimate_groups_i64(pdrs_ctx* c, const u64* keys, long long n, long long sample_rows, long long* est_out) {
+  *est_out = 0;
+  if (n <= 0) return PDRS_OK;
+  const long long s_rows = std::min<long long>(n, std::max<long long>(4096, sample_rows));
+  long long nb = (s_rows + 255) / 256, stride = std::max<long long>(256, n / nb);
+  if (s_rows >= n) { nb = (n + 255) / 256; stride = 256; }
+  TableMem stm;
+  PDRS_TRY(alloc_table(c, pow2ceil(4 * nb * 256), 1, &stm));
+  GbParams sp{};
+  sp.ks.nkeys = 1; sp.ks.nwords = 1; sp.ks.single_null = 1;
+  sp.ks.c[0].data = keys; sp.ks.c[0].dtype = PDRS_I64; sp.ks.c[0].bits = 64; sp.ks.c[0].nword = -1; sp.ks.c[0].null_alias = -1;
+  sp.n = n;
+  sp.gt = stm.t;
+  PDRS_CUDA(c, launch_sample(0, sp, nb, stride, (int)std::min<long long>(nb, c->sm_count * 8), c->stream));
+  c->stats.kernel_launches++;
+  u64 cn[CNT_N + 1];
+  PDRS_TRY(read_counters(c, stm, cn));
+  const double d = (double)cn[CNT_NGROUPS], s = (double)std::min<long long>(n, nb * 256);
+  *est_out = s_rows >= n ? (long long)d : (long long)std::min<double>((double)n, invert_distinct(d, s) * 1.05 + 1.0);
+  return PDRS_OK;
+}
+
 struct PassPlan { int val; int flags; int is_int; };
 
 enum { MODE_AGG = 0, MODE_PARTIAL = 1 };
@@ -340,6 +439,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
 
   KeySpec ks;
   PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));
+  PDRS_TRY(compress_keyspec(c, kv.data(), nkeys, n, &ks));
   const int variant = variant_of(ks);
 
   std::vector<PassPlan> passes;
@@ -445,6 +545,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   u64 cn[CNT_N + 1] = {0};
   bool radix_used = false, restart = false;
   bool part_ok = c->opt_part != 0 && c->opts.groupby_algo == PDRS_GB_AUTO;
+  bool reestimated = false;      // the partitioned path may correct the sampled cardinality estimate once (gb_part_pass)
   bool ts_skew = false;          // the tile-sort kernel runs as the skew fallback: its spills go to a side buffer + a second pass
   (void)radix_used;
   for (int attempt = 0;; attempt++) {
@@ -481,14 +582,19 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
         if ((variant == 0 || variant == 1) && part_ok && !ts_fit && algo != PDRS_GB_GLOBAL && passes[i].val >= 0 && est > 2047) {
           float ms = 0;
           bool dirty = false, skewed = false;
-          int32_t rs = gb_part_pass(c, gp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed);
+          long long est_new = 0;
+          int32_t rs = gb_part_pass(c, gp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed, reestimated ? nullptr : &est_new);
           if (rs == PDRS_OK) { c->stats.main_kernel_ms += ms; c->stats.groupby_algo_used = PDRS_GB_PARTITIONED; continue; }
           if (rs != PDRS_ERR_UNSUPPORTED) return rs;
+          if (est_new > 0) {        // the first bucket shows far more groups than the sample predicted: start over with that estimate
+            est = est_new; c->stats.est_groups = est; reestimated = true; restart = true;
+            break;
+          }
           part_ok = false;
           // Skewed keys (a hash bucket overflowed its padded range): a few hot keys carry most of the rows.  The
           // tile-sort kernel keeps the first 2047 keys every CTA meets (the hot ones, with high probability) in its
           // register accumulators and sends the rows of the remaining keys to the global table one by one.
-          if (skewed && c->opt_tsort != 0 && n >= 4 * gb_tsort_tile_rows() && n < (1ll << 38)) {
+          if (skewed && est <= 1000000 && c->opt_tsort != 0 && n >= 4 * gb_tsort_tile_rows() && n < (1ll << 38)) {
             ts_dense = false; ts_cap = 2047;
             ts_fit = gb_tsort_geometry(ts_cap, false, c->smem_optin, (int)c->opt_tsort_threads, &ts_nt, &ts_gpt, &ts_slots, &ts_smem);
             ts_skew = ts_fit;
@@ -558,7 +664,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
             sp.ts_generic = 0;
             float ms = 0;
             bool dirty = false, skewed = false;
-            int32_t rs = gb_part_pass(c, sp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed);
+            int32_t rs = gb_part_pass(c, sp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed, nullptr);
             if (rs != PDRS_OK && rs != PDRS_ERR_UNSUPPORTED) return rs;
             if (rs == PDRS_ERR_UNSUPPORTED) {
               GbCfg cfg{1, 0, passes[i].is_int, passes[i].flags, 8, 0};

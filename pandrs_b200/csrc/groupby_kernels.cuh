@@ -44,6 +44,7 @@ struct KeyColDev {
   const void* data;
   const uint8_t* nulls;
   long long null_alias;
+  long long offset;    // range compression of multi-key tuples: the part holds (value - offset) in `bits` bits (0 / natural width otherwise)
   int dtype, word, shift, bits;
   int nword, nshift;   // where the "part is NULL" flag lives (nword < 0: none)
 };
@@ -150,16 +151,16 @@ __device__ __noinline__ bool load_key_generic(const KeySpec& ks, long long row, 
     u64 v = 0;
     if (!isnull) {
       switch (c.dtype) {
-        case PDRS_I64: v = (u64)__ldg((const long long*)c.data + row); break;
+        case PDRS_I64: v = (u64)__ldg((const long long*)c.data + row) - (u64)c.offset; break;
         case PDRS_F64: {
           double d = __ldg((const double*)c.data + row);
           v = (d != d) ? 0x7FF8000000000000ull : (u64)__double_as_longlong(d);   // all NaNs print "NaN"
           break;
         }
-        case PDRS_I32: v = (u64)(uint32_t)__ldg((const int*)c.data + row); break;
+        case PDRS_I32: v = ((u64)(long long)__ldg((const int*)c.data + row) - (u64)c.offset) & 0xFFFFFFFFull; break;
         case PDRS_DICT_U32: {
           uint32_t id = __ldg((const uint32_t*)c.data + row);
-          if ((long long)id == c.null_alias) isnull = true; else v = id;
+          if ((long long)id == c.null_alias) isnull = true; else v = (u64)id - (u64)c.offset;
           break;
         }
         case PDRS_BOOL_BITS: v = pdrs_bit((const uint8_t*)c.data, row); break;

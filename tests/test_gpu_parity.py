@@ -743,12 +743,45 @@ def test_zipf_multi_key_underestimated_cardinality_retries_fast(ctx, oracle):
     k3 = Spec(pb.DICT_U32, _zipf(rng, n, 10_000).astype(np.uint32), pool=pool)
     v = Spec(pb.F64, rng.random(n) * 1000.0)
     ctx.set_option("sample_rows", 4096)
+    ctx.set_option("key_compress", 0)        # keep the tuples two / three words wide
     try:
         for keys in ([k1, k2], [k1, k2, k3]):
             compare_groupby(pb, oracle, ctx, keys, [v], [(0, op) for op in ALL6], device=True)
             assert ctx.stats()["retries"] >= 1
     finally:
         ctx.set_option("sample_rows", 1 << 18)
+        ctx.set_option("key_compress", 1)
+
+
+@pytest.mark.gpu
+def test_multi_key_tuples_are_packed_by_value_range(ctx, oracle):
+    # (i32, i64[, dictionary, bool]) needs 2-3 words at natural widths; the exact value ranges fit one word, so the tuple
+    # is packed as (value - column minimum) fields and takes the one-word kernels.  Negative minima, a large i64
+    # offset, NULL parts, a "NULL" dictionary alias and a row filter must survive the round trip through the packing.
+    n = 500_000
+    rng = np.random.default_rng(41)
+    pool = [f"d{i}" for i in range(5000)] + ["NULL"]
+    k1 = Spec(pb.I32, rng.integers(-700, 300, n).astype(np.int32), nulls=rng.random(n) < 0.03)
+    k2 = Spec(pb.I64, rng.integers(0, 900, n).astype(np.int64) * 7 + 9_000_000_000_000)
+    k3 = Spec(pb.DICT_U32, rng.integers(3, 5001, n).astype(np.uint32), pool=pool, null_alias=5000)
+    kb = Spec(pb.BOOL_BITS, rng.random(n) < 0.5)
+    v = Spec(pb.F64, rng.normal(3.0, 1.0, n), nulls=rng.random(n) < 0.05)
+    f = Spec(pb.BOOL_BITS, rng.random(n) < 0.9, nulls=rng.random(n) < 0.02)
+    aggs = [(0, op) for op in ALL6]
+    k1z = Spec(pb.I32, _zipf(rng, n, 40).astype(np.int32) - 20)
+    k2z = Spec(pb.I64, _zipf(rng, n, 30).astype(np.int64) * 1000 - 5)
+    compare_groupby(pb, oracle, ctx, [k1z, k2z], [v], aggs, device=True)             # ~1000 groups: tile-sort
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_TILESORT
+    compare_groupby(pb, oracle, ctx, [k1, k2], [v], aggs, device=True)               # NULL parts in the tuple (one word, global table)
+    compare_groupby(pb, oracle, ctx, [k2, k3, kb, k1], [v], aggs, filter_spec=f, device=True)
+    k1n = Spec(pb.I32, rng.integers(-700, 300, n).astype(np.int32))
+    m = 1_200_000                                                                    # 10^4 tuples, no NULLs: partitioned path on packed words
+    k1p = Spec(pb.I32, rng.integers(-70, 30, m).astype(np.int32))
+    k2p = Spec(pb.I64, rng.integers(0, 100, m).astype(np.int64) * 7 + 9_000_000_000_000)
+    compare_groupby(pb, oracle, ctx, [k1p, k2p], [Spec(pb.F64, rng.normal(3.0, 1.0, m))], aggs, device=True)
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+    wide = Spec(pb.I64, rng.integers(-2**62, 2**62, n))                              # range does not fit: natural layout
+    compare_groupby(pb, oracle, ctx, [k1n, wide], [v], [(0, pb.SUM), (0, pb.COUNT)], device=True)
 
 
 # ---------------------------------------------------------------- fused partition + shuffle join (pdrs_xjoin_*)
