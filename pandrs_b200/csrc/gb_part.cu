@@ -224,13 +224,16 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   const long long cap2 = bits2 ? padded(nparts, 8192) : cap1;
   // single level: a side area of up to n / 4 rows behind the buckets takes the runs of buckets that fill up (hot keys of
   // a skewed distribution); it is aggregated as `nside` more partitions of cap1 rows
+  // Two levels: level 2 gets a side area of its own behind its partitions; the rows level 1 parked are copied to its
+  // front (they belong to many level-1 buckets, so level 2 cannot re-partition them; they are dominated by the hot keys
+  // anyway), and the whole area is aggregated as extra partitions of cap2 rows.
   long long nside = 0;
-  if (!bits2 && c->opt_part_side != 0) {
+  if (c->opt_part_side != 0) {
     nside = std::max<long long>(1, (n / 4 + cap1 - 1) / cap1);
     while (nside > 0 && (unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31)) nside--;
   }
   if ((unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31) || (unsigned long long)nparts * cap2 >= (1ull << 31)) return PDRS_ERR_UNSUPPORTED;   // 31-bit output positions
-  const size_t need = (size_t)(nb1 + nside) * cap1 * 17 + (bits2 ? (size_t)nparts * cap2 * 17 : 0);
+  const size_t need = (size_t)(nb1 + nside) * cap1 * 17 + (bits2 ? ((size_t)nparts * cap2 + (nside ? (size_t)n / 2 : 0)) * 17 : 0);
   size_t free_b = 0, total_b = 0;
   PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   if (need + (2ull << 30) > free_b) return PDRS_ERR_UNSUPPORTED;
@@ -240,7 +243,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   const long long ts_cap = 1023;
   if (!gb_tsort_geometry(ts_cap, false, c->smem_optin, 512, &ts_nt, &ts_gpt, &ts_slots, &ts_smem)) return PDRS_ERR_UNSUPPORTED;
 
-  DevBuf cnt, k1, v1, f1, k2, v2, f2, side, pcnt;
+  DevBuf cnt, k1, v1, f1, k2, v2, f2, side, pcnt, side2, pcnt2;
   const bool has_flags = gp.vnull != nullptr && !gp.compat_nulls;
   PDRS_TRY(cnt.alloc(c, (size_t)(nb1 + nparts + 8) * 8, true));     // [nb1] level-1 cursors, [nparts] level-2 cursors, [1] overflow
   u64* cur1 = cnt.as<u64>();
@@ -275,12 +278,17 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
   if (nside) { gp_counts_kernel<<<(int)((nb1 + nside + 255) / 256), 256, 0, c->stream>>>(cur1, sidep, (int)nb1, cap1, (int)nside, pcnt.as<u64>()); c->stats.kernel_launches++; }
   c->stats.kernel_launches++;
-  if (est_refined && nb1 >= 4) {
+  long long side_rows1 = 0;         // rows level 1 parked in its side area
+  if ((est_refined && nb1 >= 4) || (bits2 && nside)) {
     PDRS_CUDA(c, cudaGetLastError());
     PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, ovf, 8, cudaMemcpyDeviceToHost, c->stream));
     PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 9, cur1, 8, cudaMemcpyDeviceToHost, c->stream));
+    if (nside) PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 10, sidep, 8, cudaMemcpyDeviceToHost, c->stream));
     PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (c->pinned_scalars[8] != 0) { *skewed = true; return PDRS_ERR_UNSUPPORTED; }
+    if (nside) side_rows1 = std::min<long long>((long long)c->pinned_scalars[10], side_cap);
+  }
+  if (est_refined && nb1 >= 4) {
     const long long cnt0 = std::min<long long>((long long)c->pinned_scalars[9], cap1);
     long long est0 = 0;
     PDRS_TRY(gb_estimate_groups_i64(c, k1.as<u64>(), cnt0, 1 << 20, &est0));
@@ -290,16 +298,39 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   const u64 *pk = k1.as<u64>(), *pv = v1.as<u64>(), *pc = nside ? pcnt.as<u64>() : cur1;
   const uint8_t* pf = has_flags ? f1.as<uint8_t>() : nullptr;
   long long pcap = cap1;
+  long long nside2 = 0;
   if (bits2) {
-    PDRS_TRY(k2.alloc(c, (size_t)nparts * cap2 * 8));
-    PDRS_TRY(v2.alloc(c, (size_t)nparts * cap2 * 8));
-    if (has_flags) PDRS_TRY(f2.alloc(c, (size_t)nparts * cap2 + 64));
+    if (nside) {
+      nside2 = (side_rows1 + n / 4 + cap2 - 1) / cap2;
+      while (nside2 > 0 && (unsigned long long)(nparts + nside2) * cap2 >= (1ull << 31)) nside2--;
+      if (nside2 * cap2 < side_rows1) { *skewed = true; return PDRS_ERR_UNSUPPORTED; }
+    }
+    const long long side_base2 = nparts * cap2, side_cap2 = nside2 * cap2;
+    PDRS_TRY(k2.alloc(c, (size_t)(nparts + nside2) * cap2 * 8));
+    PDRS_TRY(v2.alloc(c, (size_t)(nparts + nside2) * cap2 * 8));
+    if (has_flags) PDRS_TRY(f2.alloc(c, (size_t)(nparts + nside2) * cap2 + 64));
+    u64* side2p = nullptr;
+    if (nside2) {
+      PDRS_TRY(side2.alloc(c, (size_t)(nparts + 2) * 8));
+      PDRS_TRY(pcnt2.alloc(c, (size_t)(nparts + nside2 + 2) * 8, true));
+      side2p = side2.as<u64>();
+      PDRS_CUDA(c, cudaMemsetAsync(side2.p, 0xFF, (size_t)(nparts + 2) * 8, c->stream));       // partition ends: none recorded
+      c->pinned_scalars[11] = side_rows1;                                                        // level 2 appends behind level 1's rows
+      PDRS_CUDA(c, cudaMemcpyAsync(side2.p, c->pinned_scalars + 11, 8, cudaMemcpyHostToDevice, c->stream));
+      if (side_rows1 > 0) {
+        PDRS_CUDA(c, cudaMemcpyAsync(k2.as<u64>() + side_base2, k1.as<u64>() + side_base, (size_t)side_rows1 * 8, cudaMemcpyDeviceToDevice, c->stream));
+        PDRS_CUDA(c, cudaMemcpyAsync(v2.as<u64>() + side_base2, v1.as<u64>() + side_base, (size_t)side_rows1 * 8, cudaMemcpyDeviceToDevice, c->stream));
+        if (has_flags) PDRS_CUDA(c, cudaMemcpyAsync(f2.as<uint8_t>() + side_base2, f1.as<uint8_t>() + side_base, (size_t)side_rows1, cudaMemcpyDeviceToDevice, c->stream));
+      }
+    }
     GpIn in2{};
-    in2.pkeys = k1.as<u64>(); in2.pvals = v1.as<u64>(); in2.pflags = pf; in2.pcnt = cur1; in2.pcap = cap1;
+    in2.pkeys = k1.as<u64>(); in2.pvals = v1.as<u64>(); in2.pflags = pf; in2.pcnt = pc; in2.pcap = cap1;      // pc: level-1 counts (clamped when a side area exists)
     const int gx = (int)std::max<long long>(1, std::min<long long>((cap1 + GP_TILE - 1) / GP_TILE, std::max<long long>(1, (long long)c->sm_count * 2 * 2 / nb1)));
-    gp_part_kernel<false><<<dim3(gx, (unsigned)nb1), GP_NT, smem, c->stream>>>(in2, 32 - bits, bits2, cap2, cur2, k2.as<u64>(), v2.as<u64>(), has_flags ? f2.as<uint8_t>() : nullptr, ovf);
+    gp_part_kernel<false><<<dim3(gx, (unsigned)nb1), GP_NT, smem, c->stream>>>(in2, 32 - bits, bits2, cap2, cur2, k2.as<u64>(), v2.as<u64>(), has_flags ? f2.as<uint8_t>() : nullptr, ovf,
+                                                                                side2p, side_base2, side_cap2);
     c->stats.kernel_launches++;
-    pk = k2.as<u64>(); pv = v2.as<u64>(); pc = cur2; pcap = cap2;
+    if (nside2) { gp_counts_kernel<<<(int)((nparts + nside2 + 255) / 256), 256, 0, c->stream>>>(cur2, side2p, (int)nparts, cap2, (int)nside2, pcnt2.as<u64>()); c->stats.kernel_launches++; }
+    pk = k2.as<u64>(); pv = v2.as<u64>(); pc = nside2 ? pcnt2.as<u64>() : cur2; pcap = cap2;
     pf = has_flags ? f2.as<uint8_t>() : nullptr;
   }
   PDRS_CUDA(c, cudaGetLastError());
@@ -310,7 +341,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   GbParams tp = gp;
   tp.ts_generic = 0;               // the partitions hold packed key words
   tp.part_keys = pk; tp.part_vals = pv; tp.part_flags = pf; tp.part_cnt = pc; tp.part_cap = pcap; tp.part_bits = bits;
-  const long long nparts_all = nparts + nside;
+  const long long nparts_all = nparts + (bits2 ? nside2 : nside);
   tp.part_n = (int)nparts_all;
   {   // work items: ~16 chunks per CTA, each chunk a run of whole tiles of one partition
     const long long tiles_cap = pcap / T, want = 16ll * c->sm_count;

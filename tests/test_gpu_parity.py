@@ -731,6 +731,22 @@ def test_zipf_dictionary_key_takes_the_skew_fallback(ctx, oracle):
 
 
 @pytest.mark.gpu
+def test_zipf_high_cardinality_two_level_partition_with_side_areas(ctx, oracle):
+    # hundreds of thousands of groups AND hot keys (the top key owns ~13% of the rows): two partition levels, both
+    # with a side area for the runs of full buckets; level 1's parked rows are carried over to level 2's area
+    n = 3_000_000
+    rng = np.random.default_rng(33)
+    k = Spec(pb.I64, _zipf(rng, n, 400_000).astype(np.int64) * 1_000_003 - 77)
+    v = Spec(pb.F64, rng.normal(10.0, 4.0, n), nulls=rng.random(n) < 0.05)
+    got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+    assert len(got) == len(np.unique(k.values))
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+    k32 = Spec(pb.I32, _zipf(rng, n, 700).astype(np.int32) - 350)                        # the same through a packed (i32, i64) tuple
+    k64 = Spec(pb.I64, _zipf(rng, n, 3000).astype(np.int64) * 11 + 5_000_000_000)
+    compare_groupby(pb, oracle, ctx, [k32, k64], [v], [(0, pb.SUM), (0, pb.MEAN), (0, pb.STD), (0, pb.COUNT)], device=True)
+
+
+@pytest.mark.gpu
 def test_zipf_multi_key_underestimated_cardinality_retries_fast(ctx, oracle):
     # (i32, i64) and (i32, i64, dictionary) tuples are wider than one word: global table.  A tiny sample of Zipf keys
     # underestimates the number of groups by far; the table must report the overflow quickly (not degenerate into
