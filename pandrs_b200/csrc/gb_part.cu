@@ -15,8 +15,9 @@
 //                          bits of the key hash
 // Both levels are ONE pass (no histogram pass): bucket b owns a fixed padded range of the output, a tile's rows
 // are ranked by a shared-memory histogram, one global reservation per bucket and tile, rows staged in shared
-// memory in bucket order and written out as contiguous runs.  A bucket that overflows its range (heavily skewed
-// keys) makes the caller fall back to the global-table path.
+// memory in bucket order and written out as contiguous runs.  A bucket that fills up (hot keys) sends its further runs
+// to a side area behind the buckets, which is aggregated as extra partitions; only when that overflows too does the
+// caller fall back (tile-sort over the columns with a spill buffer, or the global-table path).
 #include <algorithm>
 #include <cmath>
 
