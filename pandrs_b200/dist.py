@@ -13,6 +13,10 @@ ranks' rows:
                              hash maps to it.
   join                       both sides are hash-partitioned by key and exchanged the same way, then joined
                              locally; row ids travel with the keys so the result is in GLOBAL row numbers.
+  join, exchange path        (DistJoin.setup_fused / join_pairs_fused, pdrs_xjoin_*) the join's partition kernel
+                             stores its runs straight into the destination GPU's receive area (CUDA IPC mappings,
+                             NVLink stores): no send buffers, no all_to_all; torch.distributed only carries the
+                             64-byte IPC handles once and one small all_gather per call (the barrier).
 
 The compute steps are methods of a `backend` object (default: the CUDA Context); the collective steps only see
 tensors.  tests/test_dist_gloo.py drives the same code on CPU tensors with the gloo backend and an oracle-based
@@ -228,6 +232,18 @@ class DistJoin:
         gl = lids[li]
         gr = torch.where(ri >= 0, rids[ri.clamp(min=0)], torch.full_like(ri, -1)) if rids.numel() else torch.full_like(ri, -1)
         return gl, gr
+
+    def join_pairs_auto(self, left: Column, right: Column, how: int, left_row0: int, right_row0: int):
+        """The exchange join when it was set up (setup_fused) and no padded region overflows, the all_to_all path
+        otherwise.  Always returns (global left rows, global right rows) tensors; -1 stands for None."""
+        if getattr(self, "fused", False) and getattr(self, "x", None) is not None and how in (N.INNER, N.LEFT):
+            j = self.join_pairs_fused(left, right, how, left_row0, right_row0)
+            if j is not None:
+                try:
+                    return (self.b.tensor_from_ptr(j.left_dev(), j.n, torch.int64), self.b.tensor_from_ptr(j.right_dev(), j.n, torch.int64))
+                finally:
+                    j.close()
+        return self.join_pairs(left, right, how, left_row0, right_row0)
 
     # ---- fused partition + shuffle over NVLink peer memory (pdrs_xjoin_*)
     def setup_fused(self, max_left_rows: int, max_right_rows: int, total_right_rows: int) -> bool:

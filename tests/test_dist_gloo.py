@@ -175,7 +175,7 @@ def _worker(rank, world, port, case):
             rn = rng.random(800) < 0.04
             lc, rc = [0, 1000, 3000], [0, 500, 800]
             for how in (0, 1):
-                gl, gr = DistJoin(be, dist).join_pairs(TCol(I64, lk[lc[rank]:lc[rank + 1]], ln[lc[rank]:lc[rank + 1]]),
+                gl, gr = DistJoin(be, dist).join_pairs_auto(TCol(I64, lk[lc[rank]:lc[rank + 1]], ln[lc[rank]:lc[rank + 1]]),
                                                        TCol(I64, rk[rc[rank]:rc[rank + 1]], rn[rc[rank]:rc[rank + 1]]), how, lc[rank], rc[rank])
                 pl, _ = all_gather_varlen(dist, gl)
                 pr, _ = all_gather_varlen(dist, gr)

@@ -740,7 +740,7 @@ def test_zipf_high_cardinality_two_level_partition_with_side_areas(ctx, oracle):
     v = Spec(pb.F64, rng.normal(10.0, 4.0, n), nulls=rng.random(n) < 0.05)
     got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
     assert len(got) == len(np.unique(k.values))
-    assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+    assert ctx.stats()["groupby_algo_used"] in (pb.GB_PARTITIONED, pb.GB_TILESORT)       # (tile-sort + spill buffer if a side area overflowed)
     k32 = Spec(pb.I32, _zipf(rng, n, 700).astype(np.int32) - 350)                        # the same through a packed (i32, i64) tuple
     k64 = Spec(pb.I64, _zipf(rng, n, 3000).astype(np.int64) * 11 + 5_000_000_000)
     compare_groupby(pb, oracle, ctx, [k32, k64], [v], [(0, pb.SUM), (0, pb.MEAN), (0, pb.STD), (0, pb.COUNT)], device=True)
