@@ -1070,10 +1070,11 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
 // One pdrs_xjoin per rank (= per GPU / process).  Its receive area holds, for both join sides, (key, row) rows in
 // padded sub-buckets [radix bucket][source rank] plus one row count per sub-bucket.  pdrs_xjoin_shuffle runs the
 // one-pass partition kernel with the peers' receive areas as its output (CUDA IPC mappings, stores go through
-// NVLink / NVSwitch): there is no send buffer, no separate all-to-all and no second pass on the receiving side -
-// after a barrier the local build / probe kernels read the received sub-buckets exactly like single-GPU radix buckets.
-struct XSide { size_t keys = 0, rows = 0, cnt = 0; long long cap = 0; };      // byte offsets inside the receive area
+// NVLink / NVSwitch): there is no send buffer and no separate all-to-all.  Fused layout: the receiver probes the
+// sub-buckets as they arrived; staged layout (default for > 1 rank): regions [source rank] only, written with
+// line-aligned stores, and the receiver runs the ordinary local radix partition over them (see pdrs_xjoin_create).
 }  // extern "C"
+struct XSide { size_t keys = 0, rows = 0, cnt = 0; long long cap = 0; };      // byte offsets inside the receive area
 struct pdrs_xjoin {
   pdrs_ctx* ctx = nullptr;
   int rank = 0, world = 1, log_world = 0;
