@@ -113,6 +113,20 @@ def cpu_reference_step(orc, n, groups, threads, seed=42):
     return dt
 
 
+def cpu_idealised(orc, n, groups, threads, seed=42):
+    """SURVEY.md §8(d) 'idealised CPU' line: typed i64 keys in per-thread flat hash tables, merged at the end - NOT the
+    reference's algorithm, reported beside it so that the comparison does not only flatter the GPU.  rows/s."""
+    k = orc.synth_keys(n, seed=seed, card=groups)
+    v = orc.synth_vals(n, seed=seed)
+    vn = orc.synth_nulls(n, seed=seed, per_million=NULL_PER_MILLION)
+    orc.ideal_groupby(k[: n // 8], v[: n // 8], vn, nthreads=threads)
+    t0 = time.perf_counter()
+    _, ng = orc.ideal_groupby(k, v, vn, nthreads=threads)
+    dt = time.perf_counter() - t0
+    assert ng == min(groups, n) or n < 50 * groups
+    return n / dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -131,7 +145,8 @@ def run_reference(args):
         "impl": "reference", "metric": "groupby_agg_rows_per_s", "value": val, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "config": workload_config(args, n),
-        "cpu_baseline": {"value": val, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample,
+                         "idealised_typed_key_rows_per_s": cpu_idealised(orc, 8 * n, args.groups, threads)},
         "e2e": {"value": val, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -296,7 +311,9 @@ def main():
         cpu_reference_step(orc, 200_000, args.groups, threads)
         dt = cpu_reference_step(orc, args.cpu_rows, args.groups, threads)
         out["cpu_baseline"] = {"value": args.cpu_rows / dt, "unit": "rows/s", "cores": threads, "kind": "port",
-                               "sample": f"{args.cpu_rows} rows, same generator/cardinality/NULLs; oracle restatement of grouping.rs + aggregation.rs (string keys, serial grouping, {threads}-thread aggregation)"}
+                               "sample": f"{args.cpu_rows} rows, same generator/cardinality/NULLs; oracle restatement of grouping.rs + aggregation.rs (string keys, serial grouping, {threads}-thread aggregation)",
+                               # not the reference's algorithm: typed keys, per-thread flat tables (SURVEY.md §8d "idealised CPU"), 8x the sample
+                               "idealised_typed_key_rows_per_s": cpu_idealised(orc, 8 * args.cpu_rows, args.groups, threads)}
     if rank == 0:
         print(json.dumps(out))
     ctx.close()
