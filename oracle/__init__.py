@@ -16,7 +16,7 @@ _SO = os.path.join(_HERE, "libpandrs_oracle.so")
 
 I64, F64, DICT_U32, BOOL_BITS, I32 = 0, 1, 2, 3, 4
 SUM, MEAN, MIN, MAX, COUNT, STD, VAR = range(7)
-MODE_AGGREGATE, MODE_PAR_AGGREGATE, MODE_LAZY = 0, 1, 2
+MODE_AGGREGATE, MODE_PAR_AGGREGATE, MODE_LAZY, MODE_EXACT = 0, 1, 2, 3
 INNER, LEFT, RIGHT, OUTER = 0, 1, 2, 3
 
 _NP = {I64: np.int64, F64: np.float64, DICT_U32: np.uint32, BOOL_BITS: np.uint8, I32: np.int32}
@@ -28,9 +28,13 @@ class _Col(C.Structure):
                 ("pool", C.POINTER(C.c_char_p)), ("pool_len", C.c_int64)]
 
 
+class _JSynth(C.Structure):
+    _fields_ = [("n", C.c_int64), ("seed", C.c_uint64), ("domain", C.c_uint64), ("unique", C.c_int)]
+
+
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "pandrs_oracle.cpp")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("pandrs_oracle.cpp", "typed_oracle.cpp")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-B", "libpandrs_oracle.so"], check=True, capture_output=True)
     return _SO
 
@@ -73,6 +77,25 @@ def lib():
         L.orc_synth_vals.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64]
         L.orc_synth_nulls.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint32]
         L.orc_synth_join_keys.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int]
+        # typed_oracle.cpp
+        L.orc_typed_groupby.restype = C.c_void_p
+        L.orc_typed_groupby.argtypes = [C.POINTER(_Col), C.POINTER(C.c_int64), C.c_int, C.POINTER(_Col), C.POINTER(_Col), C.c_int, C.c_int64, C.c_int]
+        L.orc_typed_groupby_synth.restype = C.c_void_p
+        L.orc_typed_groupby_synth.argtypes = [C.c_int64, C.c_int64, C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_int]
+        L.orc_tg_ngroups.restype = C.c_int64
+        L.orc_tg_ngroups.argtypes = [C.c_void_p]
+        L.orc_tg_key.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_tg_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_tg_aggs.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+        L.orc_tg_free.argtypes = [C.c_void_p]
+        L.orc_typed_join.restype = C.c_void_p
+        L.orc_typed_join.argtypes = [C.POINTER(_Col), C.POINTER(_JSynth), C.POINTER(_Col), C.POINTER(_JSynth), C.c_int, C.c_int, C.c_int]
+        L.orc_tj_len.restype = C.c_int64
+        L.orc_tj_len.argtypes = [C.c_void_p]
+        L.orc_tj_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.orc_tg_exact.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.orc_tj_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_tj_free.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -192,3 +215,89 @@ def ideal_groupby(keys, vals, vnull=None, nthreads=1):
     cs = lib().orc_ideal_groupby_checksum(keys.ctypes.data, vals.ctypes.data,
                                           None if vnull is None else vnull.ctypes.data, len(keys), nthreads, C.byref(ng))
     return cs, ng.value
+
+
+# ---------------------------------------------------------------- typed-key oracle (typed_oracle.cpp)
+# Same results as groupby() / join() above, bit for bit (tests/test_oracle_golden.py), at 100+ M rows/s: the checker
+# for the CUDA path at BASELINE.json's sizes.
+def _tg_result(h, nkeys):
+    L = lib()
+    try:
+        G = L.orc_tg_ngroups(h)
+        keys = []
+        for k in range(nkeys):
+            v = np.empty(G, np.uint64)
+            isn = np.empty(G, np.uint8)
+            L.orc_tg_key(h, k, v.ctypes.data, isn.ctypes.data)
+            keys.append((v, isn.astype(bool)))
+        rows, nv, first = np.empty(G, np.int64), np.empty(G, np.int64), np.empty(G, np.int64)
+        L.orc_tg_rows(h, rows.ctypes.data, nv.ctypes.data, first.ctypes.data)
+        a = [np.empty(G, np.float64) for _ in range(6)]
+        L.orc_tg_aggs(h, *[x.ctypes.data for x in a])
+        x = [np.empty(G, np.float64) for _ in range(4)]
+        L.orc_tg_exact(h, *[y.ctypes.data for y in x])
+        return dict(n_groups=G, keys=keys, group_rows=rows, valid_n=nv, first_row=first,
+                    sum=a[0], mean=a[1], min=a[2], max=a[3], std=a[4], var=a[5],
+                    exact=dict(sum=x[0], mean=x[1], std=x[2], var=x[3]))
+    finally:
+        L.orc_tg_free(h)
+
+
+def typed_groupby(keys, val=None, filter=None, compat_nulls=False, null_alias=None, empty_id=0xFFFFFFFF, nthreads=None):
+    """keys: list of Col, val: one Col or None.  Returns dict(n_groups, keys=[(u64 values, isnull)], group_rows, valid_n,
+    first_row, sum, mean, min, max, std, var) - group order unspecified.  Key values are the physical bits as u64
+    (i64 / i32 sign-extended, f64 bit pattern with all NaNs canonical, dictionary ids, 0 / 1 for bools)."""
+    L = lib()
+    nthreads = nthreads or os.cpu_count() or 1
+    kc = (_Col * len(keys))(*[k.c() for k in keys])
+    na = None
+    if null_alias is not None:
+        na = (C.c_int64 * len(keys))(*[int(x) for x in null_alias])
+    vc = val.c() if val is not None else None
+    fc = filter.c() if filter is not None else None
+    h = L.orc_typed_groupby(kc, na, len(keys), C.byref(vc) if vc is not None else None, C.byref(fc) if fc is not None else None,
+                            int(compat_nulls), int(empty_id), nthreads)
+    return _tg_result(h, len(keys))
+
+
+def typed_groupby_synth(n, seed=42, card=1000, scramble=False, null_per_million=0, row0=0, nthreads=None):
+    """BASELINE.json configs[1] without materialising the columns: key = synth_keys, value = synth_vals, NULLs = synth_nulls."""
+    h = lib().orc_typed_groupby_synth(n, row0, seed, card, int(scramble), null_per_million, nthreads or os.cpu_count() or 1)
+    return _tg_result(h, 1)
+
+
+def typed_join(left=None, right=None, how=INNER, left_synth=None, right_synth=None, want_pairs=False, nthreads=None):
+    """left / right: Col, or *_synth = dict(n, seed, domain, unique) for synth_join_keys sides.  Returns dict(n, checksum,
+    sum_left, sum_right, unmatched_left[, left, right]); checksum = sum over pairs of (l * A) ^ (r * B) mod 2^64."""
+    L = lib()
+
+    def synth(d):
+        return _JSynth(int(d["n"]), int(d.get("seed", 42)), int(d.get("domain", 1)), int(bool(d.get("unique", False))))
+    lc = left.c() if left is not None else None
+    rc = right.c() if right is not None else None
+    ls = synth(left_synth) if left_synth is not None else None
+    rs = synth(right_synth) if right_synth is not None else None
+    h = L.orc_typed_join(C.byref(lc) if lc is not None else None, C.byref(ls) if ls is not None else None,
+                         C.byref(rc) if rc is not None else None, C.byref(rs) if rs is not None else None, how, int(want_pairs),
+                         nthreads or os.cpu_count() or 1)
+    try:
+        n = L.orc_tj_len(h)
+        cs, cu, sl, sr, ul = C.c_uint64(), C.c_uint64(), C.c_int64(), C.c_int64(), C.c_int64()
+        L.orc_tj_stats(h, C.byref(cs), C.byref(cu), C.byref(sl), C.byref(sr), C.byref(ul))
+        # a Left join of unique build keys holds the Inner join inside it: pairs with r >= 0
+        out = dict(n=n, checksum=cs.value, checksum_unmatched=cu.value, sum_left=sl.value, sum_right=sr.value, unmatched_left=ul.value)
+        if want_pairs:
+            out["left"], out["right"] = np.empty(n, np.int64), np.empty(n, np.int64)
+            L.orc_tj_pairs(h, out["left"].ctypes.data, out["right"].ctypes.data)
+        return out
+    finally:
+        L.orc_tj_free(h)
+
+
+PAIR_MIX_A, PAIR_MIX_B = 0x9E3779B97F4A7C15, 0xC2B2AE3D27D4EB4F
+
+
+def pair_checksum(left, right) -> int:
+    """The checksum typed_join reports, from numpy index arrays."""
+    with np.errstate(over="ignore"):
+        return int(((np.asarray(left).astype(np.uint64) * np.uint64(PAIR_MIX_A)) ^ (np.asarray(right).astype(np.uint64) * np.uint64(PAIR_MIX_B))).sum(dtype=np.uint64))

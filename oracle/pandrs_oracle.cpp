@@ -42,7 +42,11 @@ extern "C" {
 enum { ORC_I64 = 0, ORC_F64 = 1, ORC_DICT_U32 = 2, ORC_BOOL_BITS = 3, ORC_I32 = 4 };
 // AggregateOp discriminants in the order of group/types.rs:11-34
 enum { ORC_SUM = 0, ORC_MEAN = 1, ORC_MIN = 2, ORC_MAX = 3, ORC_COUNT = 4, ORC_STD = 5, ORC_VAR = 6 };
-enum { ORC_MODE_AGGREGATE = 0, ORC_MODE_PAR_AGGREGATE = 1, ORC_MODE_LAZY = 2 };
+enum { ORC_MODE_AGGREGATE = 0, ORC_MODE_PAR_AGGREGATE = 1, ORC_MODE_LAZY = 2,
+       // NOT a reference mode: the same grouping, but f64 Sum / Mean / Std / Var accumulated in 80-bit long double (two-pass
+       // variance).  tests/_util.py uses it to measure the reference's OWN rounding error, so that the 1e-12 tolerance can be
+       // asserted relative to the result instead of relative to max|x|.
+       ORC_MODE_EXACT = 3 };
 enum { ORC_INNER = 0, ORC_LEFT = 1, ORC_RIGHT = 2, ORC_OUTER = 3 };
 
 typedef struct {
@@ -149,9 +153,32 @@ inline double rust_fmin(double a, double b) { return std::fmin(a, b); }
 inline double rust_fmax(double a, double b) { return std::fmax(a, b); }
 
 // aggregation.rs:500-754.  ok=false stands for Err(OperationFailed).
-double calc_agg(const orc_col& col, int op, const std::vector<size_t>& rows, bool lazy, bool* ok) {
+// ORC_MODE_EXACT: long double accumulation of the same quantities (Int64 sums stay exact integers)
+double calc_agg_exact(const orc_col& col, int op, const std::vector<size_t>& rows) {
+  auto get = [&](size_t i) -> long double {
+    switch (col.dtype) {
+      case ORC_I64: return (long double)((const int64_t*)col.data)[i];
+      case ORC_I32: return (long double)((const int32_t*)col.data)[i];
+      default: return (long double)((const double*)col.data)[i];
+    }
+  };
+  long double s = 0.0L; int64_t c = 0;
+  for (size_t i : rows) if (!col_is_null(col, i)) { s += get(i); c++; }
+  if (c == 0) return 0.0;
+  if (op == ORC_SUM) return (double)s;
+  const long double mean = s / (long double)c;
+  if (op == ORC_MEAN) return (double)mean;
+  long double ssd = 0.0L;
+  for (size_t i : rows) if (!col_is_null(col, i)) { const long double d = get(i) - mean; ssd += d * d; }
+  const long double var = c > 1 ? ssd / (long double)(c - 1) : 0.0L;
+  return op == ORC_STD ? (double)sqrtl(var) : (double)var;
+}
+
+double calc_agg(const orc_col& col, int op, const std::vector<size_t>& rows, bool lazy, bool* ok, bool exact = false) {
   *ok = true;
   if (op == ORC_COUNT) return (double)rows.size();             // :743  (group size, NULLs included)
+  if (exact && (op == ORC_SUM || op == ORC_MEAN || op == ORC_STD || op == ORC_VAR) && col.dtype == ORC_F64) return calc_agg_exact(col, op, rows);
+  if (exact && (op == ORC_STD || op == ORC_VAR) && (col.dtype == ORC_I64 || col.dtype == ORC_I32)) return calc_agg_exact(col, op, rows);
   if (lazy && (op == ORC_STD || op == ORC_VAR)) { *ok = false; return 0.0; }  // lazy.rs:377-382
   if (col.dtype == ORC_I64 || col.dtype == ORC_I32) {
     auto get = [&](size_t i) -> int64_t { return col.dtype == ORC_I64 ? ((const int64_t*)col.data)[i] : (int64_t)((const int32_t*)col.data)[i]; };
@@ -219,7 +246,7 @@ void* orc_groupby(const orc_col* keys, int nkeys, const orc_col* vals, const int
   std::atomic<int> err{0};
   auto do_group = [&](size_t g) {                              // HOT LOOP 2 (aggregation.rs:802-807)
     for (int a = 0; a < naggs; a++) {
-      bool ok; double v = calc_agg(vals[agg_col[a]], agg_op[a], groups[g], lazy, &ok);
+      bool ok; double v = calc_agg(vals[agg_col[a]], agg_op[a], groups[g], lazy, &ok, mode == ORC_MODE_EXACT);
       if (!ok) { if (mode == ORC_MODE_PAR_AGGREGATE) v = 0.0; else err = 1; }   // aggregation.rs:114-117 vs :748-752
       res->aggs[a][g] = v;
     }

@@ -262,13 +262,10 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   u64* sidep = nside ? side.as<u64>() : nullptr;
   const long long side_base = nb1 * cap1, side_cap = nside * cap1;
   const size_t smem = (size_t)GP_TILE * 20 + (288 + 512) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // the attribute is per device (several contexts / GPUs may live in one process): set it on every call
+  PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
   GpIn in{};
   in.keys = reinterpret_cast<const u64*>(gp.ks.c[0].data); in.vals = reinterpret_cast<const u64*>(gp.val); in.vnull = gp.vnull;

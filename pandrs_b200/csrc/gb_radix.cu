@@ -182,8 +182,7 @@ int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, fl
   PDRS_TRY(pvals.alloc(c, (size_t)std::max<long long>(m, 1) * 8));
   PDRS_TRY(pflags.alloc(c, (size_t)std::max<long long>(m, 1) + 16));
   const size_t smem = (size_t)GR_TILE * 21 + 16;
-  static bool attr_set = false;
-  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(gr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  PDRS_CUDA(c, cudaFuncSetAttribute(gr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: every call
   gr_scatter_kernel<<<ctas, GR_THREADS, smem, c->stream>>>(src, log_nb, h + nb, pkeys.as<u64>(), pvals.as<u64>(), pflags.as<uint8_t>());
   PDRS_CUDA(c, cudaGetLastError());
   if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));

@@ -820,8 +820,7 @@ static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_
   PDRS_TRY(out->keys.alloc(c, (size_t)std::max<long long>(out->n, 1) * 8));
   PDRS_TRY(out->rows.alloc(c, (size_t)std::max<long long>(out->n, 1) * 4));
   const size_t smem = (size_t)JP_TILE * 16;
-  static bool attr_set = false;
-  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  PDRS_CUDA(c, cudaFuncSetAttribute(jpart_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device: every call
   jpart_scatter_kernel<<<ctas, JP_THREADS, smem, c->stream>>>(col, n, log_nb, h + nb, out->keys.as<u64>(), out->rows.as<uint32_t>());
   c->stats.kernel_launches += 3;
   PDRS_CUDA(c, cudaGetLastError());
@@ -844,12 +843,9 @@ static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log
   out->n = (long long)nb * cap;
   if ((unsigned long long)nb * (unsigned long long)cap >= (1ull << 32)) { *ok = false; return PDRS_OK; }   // 32-bit output positions
   const size_t smem = JQ_SMEM;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // the attribute is per device (several contexts / GPUs may live in one process): set it on every call
+  PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + JQ_TILE - 1) / JQ_TILE));
   JXDst x{};
   x.keys[0] = out->keys.as<u64>(); x.rows[0] = out->rows.as<uint32_t>();
@@ -1082,6 +1078,7 @@ struct pdrs_xjoin {
   int sh_log_nb = 0;                    // radix bits applied by the shuffle kernel itself (fused mode: log_nb, staged mode: 0)
   int row_shift = 0;                    // staged mode: left rows travel as (source rank << row_shift | local row)
   int64_t total_right = 0;
+  int64_t max_left = 0, max_right = 0;  // rows per rank the receive areas were sized for (pdrs_xjoin_create)
   XSide L, R;
   size_t bytes = 0;
   void* base = nullptr;                 // this rank's receive area (cudaMalloc: exportable through CUDA IPC)
@@ -1100,6 +1097,7 @@ int32_t pdrs_xjoin_create(pdrs_ctx* c, int32_t rank, int32_t world, int64_t max_
   PDRS_CUDA(c, cudaSetDevice(c->device));
   auto* x = new pdrs_xjoin();
   x->ctx = c; x->rank = rank; x->world = world; x->total_right = total_right_rows;
+  x->max_left = max_left_rows; x->max_right = max_right_rows;
   while ((1 << x->log_world) < world) x->log_world++;
   // radix buckets: the table region of one bucket of the rows this rank RECEIVES (~ total / world) stays L2-resident
   const size_t table_bytes = (size_t)(3 * (total_right_rows / world + 1) + 8) * 12;
@@ -1192,13 +1190,18 @@ int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_c
   ColView lv, rv;
   PDRS_TRY(pdrs_view_col(c, left_key, &lv));
   PDRS_TRY(pdrs_view_col(c, right_key, &rv));
-  if (right_row0 + rv.len > x->total_right) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: right rows beyond total_right_rows");
+  if (right_row0 < 0 || right_row0 + rv.len > x->total_right) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: right rows beyond total_right_rows");
+  // the padded regions and (staged layout) the row encoding were sized for the row counts given to pdrs_xjoin_create
+  if (lv.len > x->max_left || rv.len > x->max_right)
+    return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: %lld left / %lld right rows exceed the %lld / %lld given to pdrs_xjoin_create",
+                     (long long)lv.len, (long long)rv.len, (long long)x->max_left, (long long)x->max_right);
+  if (x->row_shift && lv.len >= (1ll << x->row_shift))
+    return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: %lld left rows do not fit the staged row encoding (2^%d)", (long long)lv.len, x->row_shift);
   const int ncb = 1 << (x->sh_log_nb + x->log_world);
   DevBuf cur;
   PDRS_TRY(cur.alloc(c, (size_t)(2 * ncb + 8) * 8, true));          // [ncb] right cursors, [ncb] left cursors, [1] overflow
   u64* ovf = cur.as<u64>() + 2 * ncb;
-  static bool attr_set = false;
-  if (!attr_set) { PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JQ_SMEM)); attr_set = true; }
+  PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JQ_SMEM));   // per device: every call
   if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
   for (int side = 0; side < 2; side++) {
     const ColView& v = side ? lv : rv;

@@ -297,7 +297,19 @@ class DistJoin:
         allinfo = [t.cpu().tolist() for t in allinfo]
         if not all(a[0] for a in allinfo):
             return None
-        j = self.x.local(how, [a[1] for a in allinfo])
-        if timings is not None:
-            timings["local_ms"] = self.b.ctx.stats()["total_ms"]
+        # local() can fail on ONE rank alone (a radix bucket of the staged layout overflowed, slot limit, OOM): the ranks
+        # must agree on the outcome before anybody returns, or the next collective deadlocks
+        j, ok = None, 1
+        try:
+            j = self.x.local(how, [a[1] for a in allinfo])
+            if timings is not None:
+                timings["local_ms"] = self.b.ctx.stats()["total_ms"]
+        except Exception as e:  # noqa: BLE001
+            ok, self.fused_error = 0, str(e)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if not int(flag.item()):
+            if j is not None:
+                j.close()
+            return None
         return j

@@ -211,3 +211,191 @@ def test_synth_matches_numpy_restatement(oracle):
         assert np.array_equal(o.synth_keys(1000), k.astype(np.int64))
         r = sm(np.uint64(43) * np.uint64(0x100000001B3) + rows)
         assert np.array_equal(o.synth_vals(1000), (r >> np.uint64(11)).astype(np.float64) * (1000.0 / 2**53))
+
+
+# ---------------------------------------------------------------- typed-key oracle (oracle/typed_oracle.cpp)
+# The checker for BASELINE.json's full sizes.  It is pinned by the string oracle above: identical results, bit for bit,
+# on inputs that exercise every rule of SURVEY.md §9.1-9.3.
+def _typed_key_string(o, dtype, v, isnull, pool):
+    if isnull:
+        return "NULL"
+    if dtype in (o.I64, o.I32):
+        return str(int(np.uint64(v).astype(np.int64)))
+    if dtype == o.F64:
+        d = float(np.uint64(v).view(np.float64))
+        if np.isnan(d):
+            return "NaN"
+        if np.isinf(d):
+            return "-inf" if d < 0 else "inf"
+        return np.format_float_positional(d, trim="-")
+    if dtype == o.DICT_U32:
+        return pool[int(v)] if pool is not None else "#" + str(int(v))
+    return "true" if v else "false"
+
+
+def _assert_typed_equals_string(o, keys, val, null_alias=None, nthreads=3):
+    ops = [o.SUM, o.MEAN, o.MIN, o.MAX, o.COUNT, o.STD, o.VAR]
+    want = o.groupby(keys, [val], [(0, op) for op in ops])
+    got = o.typed_groupby(keys, val, null_alias=null_alias, nthreads=nthreads)
+    assert got["n_groups"] == want["n_groups"]
+    index = {kt: g for g, kt in enumerate(want["key_strings"])}
+    for g in range(got["n_groups"]):
+        kt = tuple(_typed_key_string(o, k.dtype, got["keys"][c][0][g], got["keys"][c][1][g], k.pool) for c, k in enumerate(keys))
+        j = index[kt]
+        assert got["group_rows"][g] == want["group_rows"][j] and got["first_row"][g] == want["first_row"][j]
+        for a, name in enumerate(["sum", "mean", "min", "max", None, "std", "var"]):
+            w = want["aggs"][a][j]
+            x = got["group_rows"][g] if name is None else got[name][g]
+            assert x == w or (np.isnan(x) and np.isnan(w)), (kt, name, x, w)      # bit-identical, not "close"
+
+
+def test_typed_oracle_is_bit_identical_to_the_string_oracle(oracle):
+    o = oracle
+    rng = np.random.default_rng(21)
+    n = 40_000
+    pool = [f"s{i}" for i in range(40)] + ["NULL"]
+    ki = o.Col(o.I64, rng.integers(-30, 30, n) * 10**12, o.pack_bits(rng.random(n) < 0.05))
+    k32 = o.Col(o.I32, rng.integers(-5, 5, n).astype(np.int32))
+    kd = o.Col(o.DICT_U32, rng.integers(0, 41, n).astype(np.uint32), o.pack_bits(rng.random(n) < 0.03), pool=pool)
+    kb = o.Col(o.BOOL_BITS, o.pack_bits(rng.random(n) < 0.5), length=n)
+    fvals = rng.integers(0, 6, n).astype(np.float64) / 4
+    fvals[rng.random(n) < 0.02] = np.nan
+    fvals[rng.random(n) < 0.02] = -0.0
+    kf = o.Col(o.F64, fvals)
+    v = rng.normal(1e6, 3.0, n)
+    v[rng.random(n) < 0.01] = np.nan
+    v[rng.random(n) < 0.005] = np.inf
+    vf = o.Col(o.F64, v, o.pack_bits(rng.random(n) < 0.1))
+    vi = o.Col(o.I64, rng.integers(-2**62, 2**62, n), o.pack_bits(rng.random(n) < 0.1))
+    _assert_typed_equals_string(o, [ki], vf)
+    _assert_typed_equals_string(o, [ki], vi)
+    _assert_typed_equals_string(o, [k32, kd], vf, null_alias=[-1, 40])
+    _assert_typed_equals_string(o, [kb, kf], vf)
+    _assert_typed_equals_string(o, [ki, k32, kd, kb], vi, null_alias=[-1, -1, 40, -1], nthreads=5)
+    # all-NULL values, a single row, the i64 sentinels
+    _assert_typed_equals_string(o, [o.Col(o.I64, [7, 7, 8])], o.Col(o.F64, [1.0, 2.0, 3.0], o.pack_bits([True, True, True])))
+    _assert_typed_equals_string(o, [o.Col(o.I64, [1])], o.Col(o.I64, [np.iinfo(np.int64).max]))
+    _assert_typed_equals_string(o, [o.Col(o.I64, [1, 1, 2, 2])], o.Col(o.I64, [np.iinfo(np.int64).max, 5, np.iinfo(np.int64).min, np.iinfo(np.int64).min]))
+
+
+def test_typed_oracle_filter_and_synthetic_source(oracle):
+    o = oracle
+    rng = np.random.default_rng(22)
+    n = 30_000
+    k = rng.integers(0, 50, n)
+    kn = rng.random(n) < 0.1
+    v = rng.random(n) * 100
+    vn = rng.random(n) < 0.1
+    f = rng.random(n) < 0.8
+    fn = rng.random(n) < 0.05
+    keep = np.nonzero(f & ~fn)[0]
+    fcol = o.Col(o.BOOL_BITS, o.pack_bits(f), o.pack_bits(fn), length=n)
+    ops = [o.SUM, o.MEAN, o.MIN, o.MAX, o.COUNT, o.STD]
+    for compat in (False, True):
+        # the reference filters first (data_ops.rs:37-121; compat: NULLs of the kept rows become defaults, keys included)
+        kk, vv = k[keep].copy(), v[keep].copy()
+        knn, vnn = kn[keep], vn[keep]
+        if compat:
+            kk[knn] = 0
+            vv[vnn] = 0.0
+            want = o.groupby([o.Col(o.I64, kk)], [o.Col(o.F64, vv)], [(0, op) for op in ops])
+        else:
+            want = o.groupby([o.Col(o.I64, kk, o.pack_bits(knn))], [o.Col(o.F64, vv, o.pack_bits(vnn))], [(0, op) for op in ops])
+        got = o.typed_groupby([o.Col(o.I64, k, o.pack_bits(kn))], o.Col(o.F64, v, o.pack_bits(vn)), filter=fcol, compat_nulls=compat, nthreads=4)
+        assert got["n_groups"] == want["n_groups"]
+        index = {kt[0]: g for g, kt in enumerate(want["key_strings"])}
+        for g in range(got["n_groups"]):
+            ks = "NULL" if got["keys"][0][1][g] else str(int(got["keys"][0][0][g].astype(np.int64)))
+            j = index[ks]
+            for a, name in enumerate(["sum", "mean", "min", "max", None, "std"]):
+                x = got["group_rows"][g] if name is None else got[name][g]
+                assert x == want["aggs"][a][j], (compat, ks, name)
+    # generator-backed rows == the same rows materialised (BASELINE.json configs[1] shape, 5% NULLs)
+    m = 200_000
+    a = o.typed_groupby_synth(m, card=1000, null_per_million=50_000, nthreads=3)
+    b = o.typed_groupby([o.Col(o.I64, o.synth_keys(m, card=1000))], o.Col(o.F64, o.synth_vals(m), o.synth_nulls(m)), nthreads=2)
+    oa, ob = np.argsort(a["keys"][0][0]), np.argsort(b["keys"][0][0])
+    for name in ("group_rows", "valid_n", "sum", "mean", "min", "max", "std", "var"):
+        assert np.array_equal(a[name][oa], b[name][ob]), name
+
+
+def test_typed_join_equals_string_join(oracle):
+    o = oracle
+    rng = np.random.default_rng(23)
+    L = o.Col(o.I64, rng.integers(0, 400, 3000), o.pack_bits(rng.random(3000) < 0.05))
+    R = o.Col(o.I64, rng.integers(0, 400, 2000), o.pack_bits(rng.random(2000) < 0.05))
+    for how in (o.INNER, o.LEFT):
+        wl, wr = o.join(L, R, how)
+        t = o.typed_join(L, R, how, want_pairs=True, nthreads=3)
+        assert np.array_equal(t["left"], wl) and np.array_equal(t["right"], wr)          # same pairs in the same order
+        assert t["n"] == len(wl) and t["checksum"] == o.pair_checksum(wl, wr)
+        assert t["sum_left"] == int(wl.sum()) and t["sum_right"] == int(wr[wr >= 0].sum()) and t["unmatched_left"] == int((wr < 0).sum())
+    # generator-backed sides (configs[2] shape) == the same keys materialised
+    nb, npr = 5_000, 60_000
+    t = o.typed_join(left_synth=dict(n=npr, domain=2 * nb), right_synth=dict(n=nb, unique=True), how=o.LEFT)
+    wl, wr = o.join(o.Col(o.I64, o.synth_join_keys(npr, domain=2 * nb)), o.Col(o.I64, o.synth_join_keys(nb, unique=True)), o.LEFT)
+    assert t["n"] == len(wl) == npr and t["checksum"] == o.pair_checksum(wl, wr)
+
+
+def test_exact_mode_measures_the_reference_rounding_error(oracle):
+    # ORC_MODE_EXACT (80-bit accumulation) is what tests/_util.py uses to tell the reference's own rounding error from a
+    # defect of the CUDA path.  On offset data (values ~1e10, spread ~1) the reference's sequential f64 sum leaves its mean
+    # off by ~1e-5, and its two-pass Std is therefore only good to ~1e-9 RELATIVE (measured below) - a CUDA result that is
+    # closer to the truth than that cannot also be within 1e-12 of the reference, which is why compare_groupby() allows
+    # rtol * |w| + 2 * |w - exact| and records both errors.
+    o = oracle
+    rng = np.random.default_rng(3)
+    n = 50_000
+    g = rng.integers(0, 20, n)
+    v = 1e9 * (g + 1) + rng.normal(0, 1.0, n)
+    ops = [(0, o.STD), (0, o.VAR), (0, o.MEAN), (0, o.SUM)]
+    a = o.groupby([o.Col(o.I64, g)], [o.Col(o.F64, v)], ops)
+    b = o.groupby([o.Col(o.I64, g)], [o.Col(o.F64, v)], ops, mode=o.MODE_EXACT)
+    assert np.allclose(a["aggs"][2], b["aggs"][2], rtol=1e-12, atol=0) and np.allclose(a["aggs"][3], b["aggs"][3], rtol=1e-12, atol=0)
+    rel = np.abs(a["aggs"][0] / b["aggs"][0] - 1).max()
+    assert rel < 1e-7, rel
+    assert np.abs(b["aggs"][0] - 1.0).max() < 0.05
+    # well-conditioned data: the two modes agree to the last digits
+    w = rng.random(n) * 1000
+    a = o.groupby([o.Col(o.I64, g)], [o.Col(o.F64, w)], ops)
+    b = o.groupby([o.Col(o.I64, g)], [o.Col(o.F64, w)], ops, mode=o.MODE_EXACT)
+    for i in range(4):
+        assert np.allclose(a["aggs"][i], b["aggs"][i], rtol=1e-13, atol=0)
+
+
+def test_compare_groupby_typed_helper_on_a_mock_result(oracle):
+    # tests/_util.py: compare_groupby_typed (the checker of tests/test_gpu_scale.py) fed with a permuted copy of a typed
+    # result standing in for the CUDA result: passes as is, fails when one sum moves by 1e-11 relative or one key changes
+    import pandrs_b200._native as pbn
+    from _util import compare_groupby_typed
+    o = oracle
+    rng = np.random.default_rng(5)
+    n = 20_000
+    k1 = rng.integers(-20, 20, n).astype(np.int32)
+    k2 = rng.integers(0, 9, n) * -(10**15)
+    v = rng.random(n) * 1000
+    tg = o.typed_groupby([o.Col(o.I32, k1, o.pack_bits(rng.random(n) < 0.1)), o.Col(o.I64, k2)], o.Col(o.F64, v, o.pack_bits(rng.random(n) < 0.05)))
+    perm = rng.permutation(tg["n_groups"])
+    ops = [pbn.SUM, pbn.MEAN, pbn.MIN, pbn.MAX, pbn.COUNT, pbn.STD, pbn.VAR]
+
+    class Mock:
+        n_groups = tg["n_groups"]
+        sums = tg["sum"][perm].copy()
+        k0 = tg["keys"][0][0][perm].astype(np.int64).astype(np.int32)
+        def key(self, k): return (self.k0 if k == 0 else tg["keys"][1][0][perm].view(np.int64)), tg["keys"][k][1][perm]
+        def group_rows(self): return tg["group_rows"][perm]
+        def valid_n(self, v): return tg["valid_n"][perm]
+        def agg(self, a):
+            return [self.sums, tg["mean"][perm], tg["min"][perm], tg["max"][perm], tg["group_rows"][perm].astype(np.float64), tg["std"][perm], tg["var"][perm]][a]
+    m = Mock()
+    compare_groupby_typed(pbn, m, tg, [pbn.I32, pbn.I64], ops)
+    m.sums[3] *= 1 + 1e-11
+    with pytest.raises(AssertionError):
+        compare_groupby_typed(pbn, m, tg, [pbn.I32, pbn.I64], ops)
+    m.sums[3] = tg["sum"][perm][3]
+    m.k0 = m.k0.copy()
+    m.k0[5] += 1000
+    with pytest.raises(AssertionError):
+        compare_groupby_typed(pbn, m, tg, [pbn.I32, pbn.I64], ops)
+    import _util
+    _util.MEASURED.clear()          # a mock is not a measurement of the CUDA path
