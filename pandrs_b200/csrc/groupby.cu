@@ -241,6 +241,45 @@ static int32_t compress_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, long 
   return PDRS_OK;
 }
 
+// compat_filter_nulls: the reference's filter() replaces the NULLs of EVERY column of the kept rows by the type default
+// and drops the masks (data_ops.rs:64-108, parallel.rs:177-231) - key columns included: a NULL Int64 key joins group "0",
+// a NULL string key the group of the empty string.  The fused filter -> groupby does the same by grouping on a
+// defaulted copy of every key column that carries a null bitmap (one extra pass over that column, this case only).
+template <typename T>
+__global__ void gb_key_default_kernel(const T* __restrict__ src, const uint8_t* __restrict__ nulls, long long n, T* __restrict__ out, T dflt) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = pdrs_bit(nulls, i) ? dflt : src[i];
+}
+__global__ void gb_key_default_bits_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ nulls, long long nwords, uint32_t* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (long long)gridDim.x * blockDim.x) out[i] = src[i] & ~nulls[i];
+}
+static int32_t default_null_keys(pdrs_ctx* c, ColView* v) {
+  if (!v->nulls) return PDRS_OK;
+  const long long n = v->len;
+  DevBuf out;
+  if (v->dtype == PDRS_BOOL_BITS) {
+    const long long nwords = (n + 63) / 64 * 2;                      // bitmaps cover ceil(n / 64) * 8 bytes (pdrs_view_col)
+    PDRS_TRY(out.alloc(c, (size_t)nwords * 4 + 64, true));
+    if (n) gb_key_default_bits_kernel<<<pdrs_grid_for(c, nwords, 256), 256, 0, c->stream>>>((const uint32_t*)v->data, (const uint32_t*)v->nulls, nwords, out.as<uint32_t>());
+  } else {
+    const int esz = pdrs_dtype_bytes(v->dtype);
+    PDRS_TRY(out.alloc(c, (size_t)std::max<long long>(n, 1) * esz + 64));
+    const int g = pdrs_grid_for(c, n, 256);
+    if (n) switch (v->dtype) {
+      case PDRS_I64: case PDRS_F64: gb_key_default_kernel<u64><<<g, 256, 0, c->stream>>>((const u64*)v->data, v->nulls, n, out.as<u64>(), 0ull); break;       // 0 / +0.0
+      case PDRS_I32: gb_key_default_kernel<uint32_t><<<g, 256, 0, c->stream>>>((const uint32_t*)v->data, v->nulls, n, out.as<uint32_t>(), 0u); break;
+      default: gb_key_default_kernel<uint32_t><<<g, 256, 0, c->stream>>>((const uint32_t*)v->data, v->nulls, n, out.as<uint32_t>(), (uint32_t)c->opt_empty_string_id); break;   // ""
+    }
+  }
+  c->stats.kernel_launches++;
+  PDRS_CUDA(c, cudaGetLastError());
+  v->own_data = std::move(out);
+  v->data = v->own_data.p;
+  v->nulls = nullptr;
+  v->own_nulls.release();
+  return PDRS_OK;
+}
+
 int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* ks) {
   memset(ks, 0, sizeof(*ks));
   ks->nkeys = nkeys;
@@ -436,6 +475,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   for (int k = 0; k < nkeys; k++) PDRS_TRY(pdrs_view_col(c, &keys[k], &kv[k]));
   for (int v = 0; v < nvals; v++) if (need[v] >= 0) PDRS_TRY(pdrs_view_col(c, &vals[v], &vv[v]));
   if (filter) PDRS_TRY(pdrs_view_col(c, filter, &fv));
+  if (filter && c->opts.compat_filter_nulls) for (int k = 0; k < nkeys; k++) PDRS_TRY(default_null_keys(c, &kv[k]));
 
   KeySpec ks;
   PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));

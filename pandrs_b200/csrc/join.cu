@@ -13,8 +13,13 @@
 //                       buckets of (key, row id); the table slot is a monotone function of the same hash, so one
 //                       bucket owns one contiguous <= 32 MB region of the table and build / probe of a bucket run
 //                       out of the 126 MB L2 instead of DRAM.  Pairs then come out in bucket order.
-//   join_build_kernel   one CAS claims a 16-byte slot {key, head}; rows with the same key are chained
-//                       through next[] (head carries a MULTI flag so unique keys never touch next[])
+//   join_build_kernel   one CAS on the key word claims a slot, the row id is exchanged into the head word; a head that
+//                       was already set means the build keys are not unique
+//   jdup_*              duplicate build keys only: the rows of every key are collected into one segment
+//                       [count, row, row, ...] of a CSR array (count / reserve / fill passes over the build side) and
+//                       every segment is sorted ascending ONCE (join.rs:158-161 emits the matches of a key in ascending
+//                       right row); the head word then holds the segment's offset.  No chains, no per-probe sorting:
+//                       a key with k build rows costs O(k log^2 k) once, not O(k^2) per probe row.
 //   join_probe_kernel   one pass over the left keys: stash[i] = head word of the matching slot (or
 //                       NOMATCH / NULLKEY) and a per-CTA count of output rows
 //   join_write_kernel   per-CTA base offsets from the scan of those counts, block-level exclusive
@@ -32,11 +37,11 @@ typedef unsigned long long u64;
 
 // Structure of arrays: a probe reads one 32-byte sector = the 4 keys of a bucket; the head word is read on a hit only.
 struct JTab { u64* keys; uint32_t* heads; u64 slots; };   // slots is a multiple of 4; index `slots` is the reserved slot of the all-ones key
-// head word: newest build row of the key (rows < 2^31), bit 31 = the key has more rows (chained through next[]), all ones = none
-static constexpr uint32_t JH_EMPTY = 0xFFFFFFFFu, JH_MULTI = 0x80000000u;
-__device__ __forceinline__ long long jhead_decode(uint32_t h) { return (long long)(h & ~JH_MULTI) | ((h & JH_MULTI) ? (1ll << 62) : 0ll); }
-static constexpr long long J_EMPTY = -1, J_BUSY = -2, J_NOMATCH = -1, J_NULLKEY = -3;
-static constexpr long long J_MULTI = 1ll << 62;
+// head word: unique build keys: the build row of the key (rows < 2^32 - 1); duplicate build keys: offset of the key's
+// segment [count, rows ascending ...] in the CSR array; all ones = none
+static constexpr uint32_t JH_EMPTY = 0xFFFFFFFFu;
+__device__ __forceinline__ long long jhead_decode(uint32_t h) { return (long long)h; }
+static constexpr long long J_NOMATCH = -1, J_NULLKEY = -3;
 #define JOIN_THREADS 256
 #define JOIN_ITEMS 4
 
@@ -145,14 +150,17 @@ __device__ __forceinline__ void jprefetch_next_region(const JTab& t, const JSrc&
 }
 
 // Insertion: the slot is claimed by a CAS on the key word itself (all-ones = empty), so there is no "being
-// published" state, nobody ever waits and no fence is needed (the probe runs in a later kernel).  Rows with the
-// same key are chained: head <- row (exchange), next[row] <- old head; next[] is pre-filled with -1 so that
-// unique keys never write it, and a second row of a key sets the MULTI flag of the head.
+// published" state, nobody ever waits and no fence is needed (the probe runs in a later kernel).  The row id is
+// exchanged into the head word; an exchange that returns another row means the build keys are NOT unique
+// (counted in fail[3]: the host then builds the CSR segments below and the head words are rewritten).
 // The one key whose bit pattern is all-ones lives in the reserved slot `slots` (never reached by probing).
 static constexpr u64 J_EMPTY_KEY = ~0ull;
 #define JB_TILE 256    // rows per ticket: ~4700 resident warps x 256 rows keep the window of rows in flight inside one or two radix buckets
 #define JB_ITEMS 4
-__global__ void __launch_bounds__(256) join_build_kernel(JTab t, long long* next, JSrc src, long long n, u64* fail) {
+// MODE 0: insert (claim + head exchange).  MODE 1: count the rows of every key in its head word.  MODE 2: fill the CSR
+// segments (head word = segment offset, csr[offset] counts the rows placed so far and ends up as the segment length).
+template <int MODE>
+__global__ void __launch_bounds__(256) join_build_kernel(JTab t, uint32_t* __restrict__ csr, JSrc src, long long n, u64* fail) {
   // Every warp works on its own.  Tiles are handed out in order by a global counter (fail[1]): whatever the relative
   // speed of the warps, the rows in flight form one contiguous window, i.e. they stay inside one or two radix
   // buckets = L2-resident table regions.  A lane keeps JB_ITEMS insertions in flight (claim CAS, then head exchange).
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(256) join_build_kernel(JTab t, long long* next
     tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
     if (tile >= ntiles) break;
     const long long hi = jsrc_tile_hi(src, tile * JB_TILE, JB_TILE, n);
-    jprefetch_next_region(t, src, tile * JB_TILE, JB_TILE, pol_keep, lane, 32);
+    if (MODE == 0) jprefetch_next_region(t, src, tile * JB_TILE, JB_TILE, pol_keep, lane, 32);
     for (long long i0 = tile * JB_TILE + lane; i0 < hi; i0 += 32 * JB_ITEMS) {
       u64 key[JB_ITEMS], slot[JB_ITEMS], seen[JB_ITEMS];
       long long r[JB_ITEMS];
@@ -178,31 +186,125 @@ __global__ void __launch_bounds__(256) join_build_kernel(JTab t, long long* next
         if (i < hi && jsrc_load(src, i, &key[j], &r[j])) live |= 1u << j;
         slot[j] = key[j] == J_EMPTY_KEY ? slots : (jslot(key[j], slots) & ~3ull);   // the probe sequence starts at the first slot of the home bucket
       }
-      // claim: CAS straight away (the home slot is free for most keys at load factor 1/3)
+      // claim: CAS straight away (the home slot is free for most keys at load factor 1/3); MODE > 0: the key is there, find it
       uint32_t todo = live;
       for (u64 probe = 0; todo && probe <= slots; probe++) {
 #pragma unroll
         for (int j = 0; j < JB_ITEMS; j++)
-          if ((todo >> j) & 1u) seen[j] = key[j] == J_EMPTY_KEY ? key[j] : atomicCAS(&t.keys[slot[j]], J_EMPTY_KEY, key[j]);
+          if ((todo >> j) & 1u) seen[j] = key[j] == J_EMPTY_KEY ? key[j] : (MODE == 0 ? atomicCAS(&t.keys[slot[j]], J_EMPTY_KEY, key[j]) : ld_volatile_u64(&t.keys[slot[j]]));
 #pragma unroll
         for (int j = 0; j < JB_ITEMS; j++) {
           if (!((todo >> j) & 1u)) continue;
-          if (seen[j] == J_EMPTY_KEY || seen[j] == key[j]) todo &= ~(1u << j);
+          if ((MODE == 0 && seen[j] == J_EMPTY_KEY) || seen[j] == key[j]) todo &= ~(1u << j);
           else slot[j] = slot[j] + 1 >= slots ? 0 : slot[j] + 1;
         }
       }
       if (todo) { atomicAdd(fail, (u64)__popc(todo)); live &= ~todo; }
-      uint32_t old[JB_ITEMS];
+      if (MODE == 0) {
+        uint32_t old[JB_ITEMS];
 #pragma unroll
-      for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) old[j] = atomicExch(&t.heads[slot[j]], (uint32_t)r[j]);
+        for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) old[j] = atomicExch(&t.heads[slot[j]], (uint32_t)r[j]);
+        uint32_t dups = 0;
 #pragma unroll
-      for (int j = 0; j < JB_ITEMS; j++) {
-        if (!((live >> j) & 1u) || old[j] == JH_EMPTY) continue;
-        atomicAdd(&fail[3], 1ull);       // duplicate build keys: link, flag the head; the single-pass probe does not apply
-        next[r[j]] = (long long)(old[j] & ~JH_MULTI);
-        atomicOr(&t.heads[slot[j]], JH_MULTI);
+        for (int j = 0; j < JB_ITEMS; j++) if (((live >> j) & 1u) && old[j] != JH_EMPTY) dups++;
+        if (dups) atomicAdd(&fail[3], (u64)dups);       // duplicate build keys: the single-pass probe does not apply
+      } else if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) atomicAdd(&t.heads[slot[j]], 1u);
+      } else {
+        uint32_t off[JB_ITEMS], pos[JB_ITEMS];
+#pragma unroll
+        for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) off[j] = t.heads[slot[j]];
+#pragma unroll
+        for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) pos[j] = atomicAdd(&csr[off[j]], 1u);
+#pragma unroll
+        for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) csr[off[j] + 1u + pos[j]] = (uint32_t)r[j];
       }
     }
+  }
+}
+
+// Duplicate build keys, between the count and fill passes: every occupied slot (head word = number of rows of its key)
+// reserves a segment of count + 1 words in the CSR array (one warp-aggregated atomic per 32 slots); the head word
+// becomes the segment offset and the first word of the segment (the fill counter, finally the length) is cleared.
+__global__ void __launch_bounds__(256) jdup_reserve_kernel(JTab t, uint32_t* __restrict__ csr, u64* __restrict__ cursor) {
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)t.slots + 1;           // + the reserved slot of the all-ones key
+  for (long long s0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) - lane; s0 < total; s0 += (long long)gridDim.x * blockDim.x) {
+    const long long s = s0 + lane;
+    uint32_t c = 0;
+    if (s < total) { c = t.heads[s]; if (s < (long long)t.slots && t.keys[s] == J_EMPTY_KEY) c = 0; }
+    if (s == (long long)t.slots && c == JH_EMPTY) c = 0;   // (not reached: the count pass runs on zeroed head words)
+    uint32_t need = c ? c + 1u : 0u, incl = need;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+    const uint32_t tot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    u64 base = 0;
+    if (lane == 0 && tot) base = atomicAdd(cursor, (u64)tot);
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (s < total) {
+      if (c) { const uint32_t off = (uint32_t)(base + incl - need); t.heads[s] = off; csr[off] = 0u; }
+      else t.heads[s] = JH_EMPTY;
+    }
+  }
+}
+
+// Sort every segment ascending (join.rs:158-161: the matches of a key come out in ascending right row).  Segments of up to
+// 32 rows: one thread, insertion sort.  Longer ones are appended to a work list for jdup_sort_long_kernel.
+__global__ void __launch_bounds__(256) jdup_sort_short_kernel(JTab t, uint32_t* __restrict__ csr, u64* __restrict__ cursor /* [1] long segments, [2] padded length of the longest */,
+                                                              uint2* __restrict__ longs, long long longs_cap) {
+  const long long total = (long long)t.slots + 1;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < total; s += (long long)gridDim.x * blockDim.x) {
+    const uint32_t off = t.heads[s];
+    if (off == JH_EMPTY) continue;
+    const uint32_t c = csr[off];
+    if (c <= 1) continue;
+    uint32_t* a = csr + off + 1;
+    if (c <= 32) {
+      for (uint32_t i = 1; i < c; i++) {
+        const uint32_t x = a[i];
+        uint32_t q = i;
+        while (q > 0 && a[q - 1] > x) { a[q] = a[q - 1]; q--; }
+        a[q] = x;
+      }
+    } else {
+      const u64 at = atomicAdd(&cursor[1], 1ull);
+      if ((long long)at < longs_cap) longs[at] = make_uint2(off + 1, c);
+      uint32_t m = 64;
+      while (m < c) m <<= 1;
+      atomicMax(&cursor[2], (u64)m);
+    }
+  }
+}
+// One CTA per long segment: bitonic sort of the segment padded with all-ones to a power of two - in shared memory up to
+// 8192 rows, else in this CTA's slice of `scratch` (global memory, L2-resident for all but absurd segment lengths).
+#define JDS_NT 512
+#define JDS_SMEM_ROWS 8192
+__global__ void __launch_bounds__(JDS_NT) jdup_sort_long_kernel(uint32_t* __restrict__ csr, const uint2* __restrict__ longs, long long nlong, uint32_t* __restrict__ scratch, u64 scratch_stride) {
+  __shared__ uint32_t sh[JDS_SMEM_ROWS];
+  for (long long w = blockIdx.x; w < nlong; w += gridDim.x) {
+    const uint2 seg = longs[w];
+    uint32_t* a = csr + seg.x;
+    const uint32_t c = seg.y;
+    uint32_t m = 64;
+    while (m < c) m <<= 1;
+    uint32_t* b = m <= JDS_SMEM_ROWS ? sh : scratch + (u64)blockIdx.x * scratch_stride;
+    for (uint32_t i = threadIdx.x; i < m; i += JDS_NT) b[i] = i < c ? a[i] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (uint32_t k = 2; k <= m; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = threadIdx.x; i < m; i += JDS_NT) {
+          const uint32_t l = i ^ j;
+          if (l > i) {
+            const uint32_t x = b[i], y = b[l];
+            if ((x > y) == ((i & k) == 0)) { b[i] = y; b[l] = x; }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    for (uint32_t i = threadIdx.x; i < c; i += JDS_NT) a[i] = b[i];
+    __syncthreads();
   }
 }
 
@@ -239,13 +341,11 @@ __device__ __forceinline__ long long jprobe(const JTab& t, u64 key, u64 pol) {
   return jprobe_from(t, (uint32_t)jslot(key, t.slots) & ~3u, key, pol);
 }
 
-__device__ __forceinline__ long long jcount(long long stash, const long long* next, int left_join) {
+// pairs a probe row emits; csr != NULL: the build keys are not unique and the stash holds a segment offset
+__device__ __forceinline__ long long jcount(long long stash, const uint32_t* __restrict__ csr, int left_join) {
   if (stash == J_NULLKEY) return 0;
   if (stash == J_NOMATCH) return left_join ? 1 : 0;
-  if (!(stash & J_MULTI)) return 1;
-  long long c = 0;
-  for (long long r = stash & ~J_MULTI; r >= 0; r = __ldg(next + r)) c++;
-  return c;
+  return csr ? (long long)__ldg(csr + stash) : 1ll;
 }
 
 // Rows are processed in tiles of JOIN_TILE consecutive positions, tile t by CTA t mod grid: the output stays in
@@ -253,7 +353,7 @@ __device__ __forceinline__ long long jcount(long long stash, const long long* ne
 // work inside the same radix bucket at any time (L2-resident table region).
 #define JOIN_TILE (JOIN_THREADS * JOIN_ITEMS * 4)
 
-__global__ void __launch_bounds__(JOIN_THREADS) join_probe_kernel(JTab tab, const long long* __restrict__ next, JSrc src, long long n,
+__global__ void __launch_bounds__(JOIN_THREADS) join_probe_kernel(JTab tab, const uint32_t* __restrict__ csr, JSrc src, long long n,
                                                                   int left_join, long long* __restrict__ stash, u64* __restrict__ tile_counts, u64* __restrict__ tile_ctr) {
   __shared__ u64 wsum[JOIN_THREADS / 32];
   const long long ntiles = (n + JOIN_TILE - 1) / JOIN_TILE;
@@ -283,7 +383,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_probe_kernel(JTab tab, cons
 #pragma unroll
       for (int j = 0; j < JOIN_ITEMS; j++) {
         long long i = i0 + (long long)j * JOIN_THREADS;
-        if (i < hi) { st_stream_u64(stash + i, st[j], pol_stream); cnt += (u64)jcount(st[j], next, left_join); }
+        if (i < hi) { st_stream_u64(stash + i, st[j], pol_stream); cnt += (u64)jcount(st[j], csr, left_join); }
       }
     }
     for (int d = 16; d; d >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, d);
@@ -319,7 +419,7 @@ __global__ void join_scan_kernel(u64* v, int n, u64* total) {   // exclusive sca
   if (threadIdx.x == 0) *total = carry;
 }
 
-__global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long long* __restrict__ stash, const long long* __restrict__ next, long long n, int left_join,
+__global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long long* __restrict__ stash, const uint32_t* __restrict__ csr, long long n, int left_join,
                                                                   const u64* __restrict__ tile_offsets, JSrc src,
                                                                   long long* __restrict__ out_l, long long* __restrict__ out_r) {
   const uint32_t* __restrict__ prows = src.prows;
@@ -339,7 +439,7 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long lon
       for (int j = 0; j < JOIN_ITEMS; j++) {
         long long i = c0 + (long long)threadIdx.x * JOIN_ITEMS + j;
         st[j] = i < hi ? __ldcs(stash + i) : J_NULLKEY;
-        cn[j] = (u64)jcount(st[j], next, left_join);
+        cn[j] = (u64)jcount(st[j], csr, left_join);
         mine += cn[j];
       }
       u64 incl = mine;
@@ -355,15 +455,10 @@ __global__ void __launch_bounds__(JOIN_THREADS) join_write_kernel(const long lon
         if (cn[j] == 0) continue;
         if (prows) i = jsrc_left_row(src, __ldg(prows + i), jsrc_row_add(src, i));      // partitioned probe side: position -> original left row
         if (st[j] == J_NOMATCH) { out_l[pos] = i; out_r[pos] = -1; pos++; }
-        else if (!(st[j] & J_MULTI)) { out_l[pos] = i; out_r[pos] = st[j]; pos++; }
-        else {
-          const u64 p0 = pos;
-          for (long long r = st[j] & ~J_MULTI; r >= 0; r = __ldg(next + r)) {   // chain order is arbitrary:
-            u64 q = pos++;                                                     // insert in ascending right row (join.rs:158-161)
-            while (q > p0 && out_r[q - 1] > r) { out_r[q] = out_r[q - 1]; q--; }
-            out_r[q] = r;
-          }
-          for (u64 q = p0; q < pos; q++) out_l[q] = i;
+        else if (!csr) { out_l[pos] = i; out_r[pos] = st[j]; pos++; }
+        else {                                    // the key's segment: its build rows in ascending order (join.rs:158-161)
+          const uint32_t* __restrict__ seg = csr + st[j] + 1;
+          for (u64 q = 0; q < cn[j]; q++) { out_l[pos] = i; out_r[pos] = (long long)__ldg(seg + q); pos++; }
         }
       }
       __syncthreads();
@@ -867,24 +962,58 @@ struct pdrs_join_result {
 
 // Build the table from `rsrc`, probe it with `lsrc` and materialise the pairs into `res` (left / right arrays).
 // nl_out = number of probe rows (capacity of the single-pass output); nl_eff / nr_eff = positions to scan (padded
-// partition layouts scan cap rows per bucket).
-static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& next, DevBuf& fail, const JSrc& rsrc, long long nr_eff, const JSrc& lsrc, long long nl_eff,
+// partition layouts scan cap rows per bucket); nr_rows = build rows (size of the CSR array of the duplicate-key case).
+static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& fail, const JSrc& rsrc, long long nr_eff, int64_t nr_rows, const JSrc& lsrc, long long nl_eff,
                             int64_t nl, bool radix, int how, pdrs_join_result* res, int64_t* M_out, const std::function<void(const char*)>& mark) {
-  DevBuf counts;
+  DevBuf counts, csr_buf;
+  const int bctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (nr_eff + 255) / 256));
   if (nr_eff > 0) {
-    join_build_kernel<<<(int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (nr_eff + 255) / 256)), 256, 0, c->stream>>>(jt, next.as<long long>(), rsrc, nr_eff, fail.as<u64>());
+    join_build_kernel<0><<<bctas, 256, 0, c->stream>>>(jt, nullptr, rsrc, nr_eff, fail.as<u64>());
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
   }
   mark("build");
-  // unique build keys (the usual dimension-table join): single-pass probe + emit.  Needs one output slot per probe row.
-  bool single_pass = radix && c->opt_join_emit != 2;   // small inputs keep the reference's left-row-major order
-  if (single_pass) {
-    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, fail.p, 32, cudaMemcpyDeviceToHost, c->stream));
+  // fail[0] failed inserts, fail[3] build rows whose key was already in the table
+  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, fail.p, 32, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->pinned_scalars[0] != 0) return pdrs_fail(c, PDRS_ERR_CUDA, "join build: hash table insertion failed for %lld rows", (long long)c->pinned_scalars[0]);
+  const bool dups = c->pinned_scalars[3] != 0;
+  const uint32_t* csr = nullptr;
+  if (dups) {
+    // Duplicate build keys: head word = number of rows of the key (count pass) -> offset of its segment [length, rows ...] in
+    // the CSR array (reserve) -> rows filled in (fill pass) -> every segment sorted ascending, once.
+    if (nr_rows >= (1ll << 31) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: %lld build rows with duplicate keys (limit 2^31)", (long long)nr_rows);
+    DevBuf longs, scratch;
+    PDRS_TRY(csr_buf.alloc(c, (size_t)(2 * nr_rows + 8) * 4));
+    const long long longs_cap = nr_rows / 33 + 1;
+    PDRS_TRY(longs.alloc(c, (size_t)longs_cap * 8));
+    PDRS_CUDA(c, cudaMemsetAsync(jt.heads, 0, (size_t)(jt.slots + 4) * 4, c->stream));
+    PDRS_CUDA(c, cudaMemsetAsync(fail.as<u64>() + 5, 0, 24, c->stream));          // [5] CSR cursor, [6] long segments, [7] longest (padded)
+    PDRS_CUDA(c, cudaMemsetAsync(fail.as<u64>() + 1, 0, 8, c->stream));
+    join_build_kernel<1><<<bctas, 256, 0, c->stream>>>(jt, nullptr, rsrc, nr_eff, fail.as<u64>());
+    const int sg = pdrs_grid_for(c, (long long)jt.slots + 1, 256);
+    jdup_reserve_kernel<<<sg, 256, 0, c->stream>>>(jt, csr_buf.as<uint32_t>(), fail.as<u64>() + 5);
+    PDRS_CUDA(c, cudaMemsetAsync(fail.as<u64>() + 1, 0, 8, c->stream));
+    join_build_kernel<2><<<bctas, 256, 0, c->stream>>>(jt, csr_buf.as<uint32_t>(), rsrc, nr_eff, fail.as<u64>());
+    jdup_sort_short_kernel<<<sg, 256, 0, c->stream>>>(jt, csr_buf.as<uint32_t>(), fail.as<u64>() + 5, longs.as<uint2>(), longs_cap);
+    c->stats.kernel_launches += 4;
+    PDRS_CUDA(c, cudaGetLastError());
+    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, fail.p, 64, cudaMemcpyDeviceToHost, c->stream));
     PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->pinned_scalars[0] != 0) return pdrs_fail(c, PDRS_ERR_CUDA, "join build: hash table insertion failed for %lld rows", (long long)c->pinned_scalars[0]);
-    single_pass = c->pinned_scalars[3] == 0;
+    if (c->pinned_scalars[0] != 0) return pdrs_fail(c, PDRS_ERR_CUDA, "join build: %lld rows did not find their key again", (long long)c->pinned_scalars[0]);
+    const long long nlong = std::min<long long>(c->pinned_scalars[6], longs_cap), mmax = c->pinned_scalars[7];
+    if (nlong > 0) {
+      const int lg = (int)std::min<long long>(nlong, (long long)c->sm_count * 2);
+      if (mmax > JDS_SMEM_ROWS) PDRS_TRY(scratch.alloc(c, (size_t)lg * (size_t)mmax * 4));
+      jdup_sort_long_kernel<<<lg, JDS_NT, 0, c->stream>>>(csr_buf.as<uint32_t>(), longs.as<uint2>(), nlong, scratch.as<uint32_t>(), (u64)mmax);
+      c->stats.kernel_launches++;
+      PDRS_CUDA(c, cudaGetLastError());
+    }
+    csr = csr_buf.as<uint32_t>();
+    mark("duplicate keys: segments");
   }
+  // unique build keys (the usual dimension-table join): single-pass probe + emit.  Needs one output slot per probe row.
+  const bool single_pass = radix && c->opt_join_emit != 2 && !dups;   // small inputs keep the reference's left-row-major order
   int64_t M = 0;
   if (single_pass) {
     PDRS_TRY(res->left.alloc(c, (size_t)std::max<int64_t>(nl, 1) * 8));
@@ -913,7 +1042,7 @@ static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& next, DevBuf& f
   u64* cc = counts.as<u64>();
   if (nl_eff > 0) {
     if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
-    join_probe_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(jt, next.as<long long>(), lsrc, nl_eff, how == PDRS_LEFT, stash.as<long long>(), cc, fail.as<u64>() + 2);
+    join_probe_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(jt, csr, lsrc, nl_eff, how == PDRS_LEFT, stash.as<long long>(), cc, fail.as<u64>() + 2);
     if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
     join_scan_kernel<<<1, 1024, 0, c->stream>>>(cc, (int)ntiles, cc + ntiles + 2);
     c->stats.kernel_launches += 2;
@@ -929,7 +1058,7 @@ static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& next, DevBuf& f
   PDRS_TRY(res->left.alloc(c, (size_t)std::max<int64_t>(M, 1) * 8));
   PDRS_TRY(res->right.alloc(c, (size_t)std::max<int64_t>(M, 1) * 8));
   if (M > 0) {
-    join_write_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(stash.as<long long>(), next.as<long long>(), nl_eff, how == PDRS_LEFT, cc, lsrc,
+    join_write_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(stash.as<long long>(), csr, nl_eff, how == PDRS_LEFT, cc, lsrc,
                                                             res->left.as<long long>(), res->right.as<long long>());
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
@@ -978,12 +1107,10 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); marks.push_back({name, e});
   };
   mark("start");
-  DevBuf tab, next, fail;
+  DevBuf tab, fail;
   PDRS_TRY(tab.alloc(c, table_bytes));
   PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));   // key = all ones (EMPTY), head = -1 (EMPTY)
   JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
-  PDRS_TRY(next.alloc(c, (size_t)std::max<int64_t>(nr, 1) * 8));
-  PDRS_CUDA(c, cudaMemsetAsync(next.p, 0xFF, (size_t)std::max<int64_t>(nr, 1) * 8, c->stream));      // -1 = end of chain
   PDRS_TRY(fail.alloc(c, 64, true));      // [0] failed inserts, [1] build tile counter, [2] probe tile counter (two-pass) / output cursor (single pass), [3] duplicate build keys, [4] probe tile counter (single pass)
   c->stats.table_slots = slots;
   JKeyCol rc{rv.data, rv.nulls, rv.dtype}, lc{lv.data, lv.nulls, lv.dtype};
@@ -1009,7 +1136,7 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
     lsrc.pkeys = lp.keys.as<u64>(); lsrc.prows = lp.rows.as<uint32_t>(); nl_eff = lp.n;
   }
   int64_t M = 0;
-  PDRS_TRY(jbuild_probe(c, jt, next, fail, rsrc, nr_eff, lsrc, nl_eff, nl, radix, how, res, &M, mark));
+  PDRS_TRY(jbuild_probe(c, jt, fail, rsrc, nr_eff, nr, lsrc, nl_eff, nl, radix, how, res, &M, mark));
   mark("write");
   if (how_req == PDRS_RIGHT || how_req == PDRS_OUTER) {
     DevBuf matched, ucounts;
@@ -1261,12 +1388,10 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;
   if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
   const size_t table_bytes = (size_t)(slots + 4) * 12;
-  DevBuf tab, next, fail, row0;
+  DevBuf tab, fail, row0;
   PDRS_TRY(tab.alloc(c, table_bytes));
   PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));
   JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
-  PDRS_TRY(next.alloc(c, (size_t)std::max<int64_t>(x->total_right, 1) * 8));            // chains of duplicate build keys, indexed by GLOBAL right row
-  PDRS_CUDA(c, cudaMemsetAsync(next.p, 0xFF, (size_t)std::max<int64_t>(x->total_right, 1) * 8, c->stream));
   PDRS_TRY(fail.alloc(c, 64, true));
   PDRS_TRY(row0.alloc(c, 64));
   PDRS_CUDA(c, cudaMemcpyAsync(row0.p, left_row0, (size_t)x->world * 8, cudaMemcpyHostToDevice, c->stream));
@@ -1298,7 +1423,7 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
     }
   }
   int64_t M = 0;
-  PDRS_TRY(jbuild_probe(c, jt, next, fail, rsrc, nr_eff, lsrc, nl_eff, nl, true, how, res, &M, [](const char*) {}));
+  PDRS_TRY(jbuild_probe(c, jt, fail, rsrc, nr_eff, nr, lsrc, nl_eff, nl, true, how, res, &M, [](const char*) {}));
   c->stats.groupby_algo_used = 2;
   if (c->opt_timing) {
     PDRS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));

@@ -453,6 +453,7 @@ def _aggregate(df: OptimizedDataFrame, keys: List[str], aggs: List[AggSpec], mul
             raise ColumnTypeMismatch(f"column '{filter_col}': expected Boolean, found {f.column_type}")
         fcol = f.raw
         ctx.set_option("compat_filter_nulls", 1)                   # the reference filters first: NULLs of kept rows become defaults (data_ops.rs:64-71)
+        ctx.set_option("compat_empty_string_id", GLOBAL_STRING_POOL.get_or_insert(""))   # ... a NULL string key becomes "" (parallel.rs:224-231)
     try:
         res = ctx.groupby_agg([k.raw for k in kcols], [df._cols[v].raw for v in numeric], call_pairs, filter=fcol)
     except PandrsError as e:

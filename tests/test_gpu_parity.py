@@ -397,6 +397,47 @@ def test_fused_filter(ctx, oracle, compat):
     assert len(got) == 6 and got.keys() == got2.keys()
 
 
+def test_fused_filter_turns_null_keys_into_defaults(ctx, oracle):
+    # compat_filter_nulls: the reference filters first, and its filter() defaults the NULLs of every column of the kept
+    # rows - key columns included (data_ops.rs:64-108, parallel.rs:177-231): a NULL Int64 key joins group "0", a NULL f64
+    # key group "0", a NULL bool key "false", a NULL string key the group of "" - never the "NULL" group
+    n = 60_000
+    rng = np.random.default_rng(61)
+    ki = Spec(pb.I64, rng.integers(-3, 4, n), nulls=rng.random(n) < 0.2)
+    kf = Spec(pb.F64, rng.integers(0, 3, n).astype(np.float64), nulls=rng.random(n) < 0.2)
+    kb = Spec(pb.BOOL_BITS, rng.random(n) < 0.5, nulls=rng.random(n) < 0.2)
+    pool = ["a", "b", "NULL", "c"]
+    kd = Spec(pb.DICT_U32, rng.integers(0, 4, n).astype(np.uint32), nulls=rng.random(n) < 0.2, pool=pool, null_alias=2)
+    k32 = Spec(pb.I32, rng.integers(5, 9, n).astype(np.int32), nulls=rng.random(n) < 0.2)
+    v = Spec(pb.F64, rng.random(n) * 10, nulls=rng.random(n) < 0.1)
+    f = Spec(pb.BOOL_BITS, rng.random(n) < 0.7, nulls=rng.random(n) < 0.05)
+    aggs = [(0, op) for op in ALL6]
+    ctx.set_option("compat_filter_nulls", 1)
+    try:
+        for keys in ([ki], [kf], [kb], [kd], [k32, kd], [ki, kb, kd]):
+            got = compare_groupby(pb, oracle, ctx, keys, [v], aggs, filter_spec=f, compat_nulls=True, device=len(keys) == 1)
+            if len(keys) == 1 and keys[0] is not kd:
+                assert ("NULL",) not in got
+        got = compare_groupby(pb, oracle, ctx, [kd], [v], aggs, filter_spec=f, compat_nulls=True)
+        assert ("",) in got and ("NULL",) in got          # "" = the former NULLs, "NULL" = the literal string
+    finally:
+        ctx.set_option("compat_filter_nulls", 0)
+    # the frame mirror: LazyFrame filter -> aggregate (fused) == filter() then group_by (unfused), NULL keys included
+    from pandrs_b200 import frame as fr
+    df = fr.OptimizedDataFrame()
+    df.add_column("k", fr.StringColumn([pool[i] for i in kd.values[:5000]], nulls=kd.nulls[:5000]))
+    df.add_column("i", fr.Int64Column(ki.values[:5000], nulls=ki.nulls[:5000]))
+    df.add_column("v", fr.Float64Column(v.values[:5000], nulls=v.nulls[:5000]))
+    df.add_column("keep", fr.BooleanColumn(f.values[:5000], nulls=f.nulls[:5000]))
+    spec = [("v", fr.AggregateOp.Sum, "s"), ("v", fr.AggregateOp.Count, "c")]
+    fused = fr.LazyFrame.new(df).filter("keep").aggregate(["k", "i"], spec).execute()
+    plain = fr.LazyFrame.new(df.filter("keep")).aggregate(["k", "i"], spec).execute()
+    def rows(d):
+        lst = lambda name: [d.column(name).get(i) for i in range(len(d.column(name)))]
+        return sorted(zip(lst("k"), lst("i"), lst("c"), np.round(lst("s"), 9).tolist()))
+    assert rows(fused) == rows(plain) and any(r[0] == "" for r in rows(fused)) and any(r[1] == "0" for r in rows(fused))
+
+
 # ---------------------------------------------------------------- joins
 @pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
 def test_join_random_duplicates_and_nulls(ctx, oracle, how):
@@ -405,6 +446,31 @@ def test_join_random_duplicates_and_nulls(ctx, oracle, how):
     R = Spec(pb.I64, rng.integers(0, 400, 2000), nulls=rng.random(2000) < 0.05)
     compare_join(pb, oracle, ctx, L, R, how)
     compare_join(pb, oracle, ctx, L, R, how, device=True)
+
+
+@pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
+def test_join_low_cardinality_build_keys(ctx, oracle, how):
+    # A build key with k rows: its rows are collected into one CSR segment and sorted once (join.cu jdup_*), so the join
+    # costs O(k log^2 k + output) - not O(k^2) per probe row.  Segment lengths here cover every sort path: <= 32 rows (one
+    # thread), <= 8192 (bitonic in shared memory), 40 000 (bitonic in global scratch); matches must come out in ascending
+    # right row, left-row-major (join.rs:150-163) - compared with the oracle in ORDER, not after a sort.
+    rng = np.random.default_rng(71)
+    rk = np.concatenate([np.repeat(np.arange(5), 40_000), np.repeat(np.arange(100, 140), 3000), np.repeat(np.arange(1000, 3000), 20), np.arange(10_000, 12_000)])
+    rk = rk[rng.permutation(len(rk))]
+    R = Spec(pb.I64, rk, nulls=rng.random(len(rk)) < 0.01)
+    L = Spec(pb.I64, np.concatenate([rng.integers(0, 5, 20), rng.integers(100, 140, 50), rng.integers(1000, 3100, 400), rng.integers(9_000, 12_500, 2000)]),
+             nulls=None)
+    compare_join(pb, oracle, ctx, L, R, how)
+    compare_join(pb, oracle, ctx, L, R, how, device=True)
+    ctx.set_option("join_algo", 2)              # the radix-partitioned path: same multiset of pairs in bucket order
+    try:
+        compare_join(pb, oracle, ctx, L, R, how, device=True, check_order=False)
+    finally:
+        ctx.set_option("join_algo", 0)
+    # the all-ones key (the table's empty marker lives in a reserved slot) with duplicates
+    R2 = Spec(pb.I64, np.array([-1, 5, -1, 7, -1, 5] * 20))
+    L2 = Spec(pb.I64, np.array([-1, 5, 9, -1]))
+    compare_join(pb, oracle, ctx, L2, R2, how)
 
 
 @pytest.mark.parametrize("how", [pb.RIGHT, pb.OUTER])
