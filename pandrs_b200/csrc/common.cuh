@@ -24,6 +24,8 @@ struct pdrs_ctx {
   int sm_count = 148;
   int smem_optin = 0;
   cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};     // bucket-at-a-time join: two streams alternate over the radix buckets
+  cudaEvent_t aux_fork = nullptr, aux_done[2] = {nullptr, nullptr};
   void* flush_buf = nullptr;
   size_t flush_bytes = 0;
   int64_t* pinned_scalars = nullptr;   // small pinned host area for D2H of counters (64 x i64)
@@ -36,7 +38,9 @@ struct pdrs_ctx {
   int64_t opt_join_log_nb = 0;         // 0 = auto (log2 of the number of radix buckets)
   int64_t opt_join_ctas_per_sm = 0;    // 0 = auto
   int64_t opt_join_part = 0;           // 0 = auto (one-pass padded partition, exact two-pass on overflow), 2 = always two-pass
-  int64_t opt_join_slots_mult = 0;     // table slots per build row (0 = default 2)
+  int64_t opt_join_slots_mult = 0;     // table slots per build row (0 = default 3)
+  int64_t opt_join_bucketwise = 1;     // radix join: one reused, L2-resident table region per bucket (0 = one table for all buckets)
+  int64_t opt_join_region_mb = 0;      // ... size of that region (0 = default 24 MB)
   int64_t opt_join_prefetch = 1;       // stream the next radix bucket's table region into L2 ahead of its first probes
   int64_t opt_join_emit = 0;           // 0 = auto (single-pass probe + emit when the build keys are unique), 2 = always count / scan / write
   int64_t opt_key_compress = 1;        // pack multi-key tuples by value range when that brings them down to one 64-bit word

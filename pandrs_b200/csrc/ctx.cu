@@ -86,6 +86,8 @@ void pdrs_ctx_destroy(pdrs_ctx* c) {
   if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
   cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
   cudaEventDestroy(c->ev_t0); cudaEventDestroy(c->ev_t1);
+  for (int s = 0; s < 2; s++) { if (c->aux_stream[s]) cudaStreamDestroy(c->aux_stream[s]); if (c->aux_done[s]) cudaEventDestroy(c->aux_done[s]); }
+  if (c->aux_fork) cudaEventDestroy(c->aux_fork);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -124,6 +126,8 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "part_side")) c->opt_part_side = value;
   else if (!strcmp(name, "key_compress")) c->opt_key_compress = value;
   else if (!strcmp(name, "join_slots_mult")) c->opt_join_slots_mult = value;
+  else if (!strcmp(name, "join_bucketwise")) c->opt_join_bucketwise = value;
+  else if (!strcmp(name, "join_region_mb")) c->opt_join_region_mb = value;
   else if (!strcmp(name, "timing")) c->opt_timing = value;
   else if (!strcmp(name, "dense")) c->opt_dense = value;
   else if (!strcmp(name, "radix")) c->opt_radix = value;

@@ -36,7 +36,9 @@
 typedef unsigned long long u64;
 
 // Structure of arrays: a probe reads one 32-byte sector = the 4 keys of a bucket; the head word is read on a hit only.
-struct JTab { u64* keys; uint32_t* heads; u64 slots; };   // slots is a multiple of 4; index `slots` is the reserved slot of the all-ones key
+struct JTab { u64* keys; uint32_t* heads; u64 slots; uint32_t nbmul; };   // slots is a multiple of 4; index `slots` is the reserved slot of the all-ones key
+// nbmul: 1 = one table for all keys.  NB > 1 = the table of ONE radix bucket out of NB (bucket-at-a-time join): the bucket is
+// floor(hash * NB / 2^32), so inside a bucket the low 32 bits of hash * NB are uniform again and pick the slot.
 // head word: unique build keys: the build row of the key (rows < 2^32 - 1); duplicate build keys: offset of the key's
 // segment [count, rows ascending ...] in the CSR array; all ones = none
 static constexpr uint32_t JH_EMPTY = 0xFFFFFFFFu;
@@ -57,7 +59,7 @@ __device__ __forceinline__ uint32_t jhash32(u64 k) {
 
 // slot = floor(hash_hi32 * slots / 2^32): monotone in the hash, so the rows of one radix bucket (top hash bits)
 // fall into one contiguous region of the table; `slots` need not be a power of two
-__device__ __forceinline__ u64 jslot(u64 key, u64 slots) { return (u64)__umulhi(jhash32(key), (uint32_t)slots); }   // slots < 2^32
+__device__ __forceinline__ u64 jslot(u64 key, u64 slots, uint32_t nbmul = 1u) { return (u64)__umulhi(jhash32(key) * nbmul, (uint32_t)slots); }   // slots < 2^32
 
 // `Some(v) -> v.to_string()` equality restated on the physical values (join.rs:112-139)
 __device__ __forceinline__ bool jload_key(const JKeyCol& c, long long row, u64* k) {
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(256) join_build_kernel(JTab t, uint32_t* __res
         const long long i = i0 + 32 * j;
         key[j] = 0; r[j] = 0;
         if (i < hi && jsrc_load(src, i, &key[j], &r[j])) live |= 1u << j;
-        slot[j] = key[j] == J_EMPTY_KEY ? slots : (jslot(key[j], slots) & ~3ull);   // the probe sequence starts at the first slot of the home bucket
+        slot[j] = key[j] == J_EMPTY_KEY ? slots : (jslot(key[j], slots, t.nbmul) & ~3ull);   // the probe sequence starts at the first slot of the home bucket
       }
       // claim: CAS straight away (the home slot is free for most keys at load factor 1/3); MODE > 0: the key is there, find it
       uint32_t todo = live;
@@ -338,7 +340,7 @@ __device__ __forceinline__ long long jprobe_from(const JTab& t, uint32_t bkt, u6
 }
 __device__ __forceinline__ long long jprobe(const JTab& t, u64 key, u64 pol) {
   if (key == J_EMPTY_KEY) { const uint32_t h = __ldg(&t.heads[t.slots]); return h == JH_EMPTY ? J_NOMATCH : jhead_decode(h); }
-  return jprobe_from(t, (uint32_t)jslot(key, t.slots) & ~3u, key, pol);
+  return jprobe_from(t, (uint32_t)jslot(key, t.slots, t.nbmul) & ~3u, key, pol);
 }
 
 // pairs a probe row emits; csr != NULL: the build keys are not unique and the stash holds a segment offset
@@ -728,19 +730,20 @@ __device__ __forceinline__ uint32_t ld_stream_u32(const uint32_t* a, u64 pol) { 
 // overlaps with the chains of the 23 other warps of the SM.
 __global__ void __launch_bounds__(JE_THREADS, 3) join_probe_emit_kernel(JTab tab, JSrc src, long long n, int left_join,
                                                                       long long* __restrict__ out_l, long long* __restrict__ out_r,
-                                                                      u64* __restrict__ out_cursor, u64* __restrict__ tile_ctr) {
+                                                                      u64* __restrict__ out_cursor, u64* __restrict__ tile_ctr, int tile_units = 8) {
   constexpr uint32_t NONE = 0xFFFFFFFFu;
-  const long long ntiles = (n + JE_TILE - 1) / JE_TILE;
+  const long long tile_rows = (long long)JE_UNIT * tile_units;      // rows per ticket
+  const long long ntiles = (n + tile_rows - 1) / tile_rows;
   const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
   const int lane = threadIdx.x & 31;
-  const uint32_t nslots = (uint32_t)tab.slots;
+  const uint32_t nslots = (uint32_t)tab.slots, nbmul = tab.nbmul;
   for (;;) {
     long long tile = 0;
     if (lane == 0) tile = (long long)atomicAdd(tile_ctr, 1ull);
     tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
     if (tile >= ntiles) break;
-    const long long tlo = tile * JE_TILE, hi = jsrc_tile_hi(src, tlo, JE_TILE, n);
-    jprefetch_next_region(tab, src, tlo, JE_TILE, pol_keep, lane, 32);
+    const long long tlo = tile * tile_rows, hi = jsrc_tile_hi(src, tlo, tile_rows, n);
+    jprefetch_next_region(tab, src, tlo, tile_rows, pol_keep, lane, 32);
 #pragma unroll 1
     for (long long lo = tlo; lo < hi; lo += JE_UNIT) {
       uint32_t res[JE_ITEMS];             // matching right row (build rows < 2^32 on this path), NONE = no match
@@ -762,7 +765,7 @@ __global__ void __launch_bounds__(JE_THREADS, 3) join_probe_emit_kernel(JTab tab
           uint32_t home[JE_HALF];
 #pragma unroll
           for (int jj = 0; jj < JE_HALF; jj++) {
-            home[jj] = __umulhi(jhash32(key[half * JE_HALF + jj]), nslots) & ~3u;
+            home[jj] = __umulhi(jhash32(key[half * JE_HALF + jj]) * nbmul, nslots) & ~3u;
             bk[jj] = ld_bucket(tab.keys + home[jj], pol_keep);
           }
 #pragma unroll
@@ -790,12 +793,12 @@ __global__ void __launch_bounds__(JE_THREADS, 3) join_probe_emit_kernel(JTab tab
           ulonglong4 q0 = make_ulonglong4(0, 0, 0, J_EMPTY_KEY), q1 = q0;
           if (j0 >= 0) {
             const uint32_t st = ((steps >> (4 * j0)) & 15u) + 1u;
-            b0 = (uint32_t)(((u64)(__umulhi(jhash32(k0), nslots) & ~3u) + 4ull * st) % nslots);
+            b0 = (uint32_t)(((u64)(__umulhi(jhash32(k0) * nbmul, nslots) & ~3u) + 4ull * st) % nslots);
             q0 = ld_bucket(tab.keys + b0, pol_keep);
           }
           if (j1 >= 0) {
             const uint32_t st = ((steps >> (4 * j1)) & 15u) + 1u;
-            b1 = (uint32_t)(((u64)(__umulhi(jhash32(k1), nslots) & ~3u) + 4ull * st) % nslots);
+            b1 = (uint32_t)(((u64)(__umulhi(jhash32(k1) * nbmul, nslots) & ~3u) + 4ull * st) % nslots);
             q1 = ld_bucket(tab.keys + b1, pol_keep);
           }
           const int f0 = j0 >= 0 ? jbucket_find(q0, k0) : 4, f1 = j1 >= 0 ? jbucket_find(q1, k1) : 4;
@@ -900,6 +903,249 @@ __global__ void __launch_bounds__(256) junmatched_write_kernel(const uint8_t* __
   }
 }
 
+// ================================================================ bucket-at-a-time join (unique build keys, hash-uniform keys)
+// The radix join above keeps ONE table for all buckets (3.6 GB for 1e8 build rows): it has to be cleared with a memset,
+// every region is fetched from DRAM when its bucket starts and written back when it ends.  Here both sides are
+// partitioned into NB buckets as before, but then the buckets are joined ONE AT A TIME in a table region that is reused
+// for every bucket: clear the region (24 MB: stays in L2), insert the bucket's build rows, probe with the bucket's probe
+// rows, next bucket.  The table never touches DRAM.  Two streams with one region each alternate, so that the clear +
+// build of bucket b + 1 (latency bound, small) fills the tail of the probe of bucket b.
+//
+// Payload mode (pdrs_join_gather): up to two 8-byte columns of the BUILD side travel with their rows - through the
+// partition (a second / third round of the same tile through the same staging buffer, NULL -> 0) and into 32-byte table
+// slots {key, row, p0, p1} = one L2 sector: a hit returns the right row AND its payload values in the sector the key
+// comparison needed anyway.  That replaces the per-column gathers of join.rs:290-552 (random 8-byte DRAM reads over the
+// whole right column, once per PAIR) by sequential traffic (once per BUILD ROW) plus nothing.
+#define JP_MAXPAY 2
+struct JPay { const u64* src[JP_MAXPAY]; const uint8_t* nulls[JP_MAXPAY]; u64* dst[JP_MAXPAY]; int n; };
+
+__device__ __forceinline__ uint32_t jbucket_nb(u64 key, uint32_t nb) { return __umulhi(jhash32(key), nb); }
+
+// One-pass partition into `nb` (any number <= 1024) padded buckets of (key, row) [+ payload columns]: tiles of 8192 rows
+// (1024 threads x 8), bucket histogram in shared memory (the atomic's return value ranks the row inside its bucket), one
+// global reservation per bucket and tile, rows staged in bucket order, every bucket's run written out contiguously.
+#define JR_NT 1024
+#define JR_ITEMS 8
+#define JR_TILE (JR_NT * JR_ITEMS)
+#define JR_SMEM ((size_t)JR_TILE * 16 + 1056 * 4 + 1024 * 8)
+__global__ void __launch_bounds__(JR_NT, 1) jpartp_kernel(JKeyCol col, long long n, uint32_t nb, long long cap, u64* __restrict__ cursor,
+                                                          u64* __restrict__ out_keys, uint32_t* __restrict__ out_rows, u64* __restrict__ overflow, const JPay pay) {
+  extern __shared__ __align__(16) unsigned char jsm[];
+  u64* st_key = reinterpret_cast<u64*>(jsm);                                 // [JR_TILE] staged keys (then: staged payload values)
+  uint32_t* st_row = reinterpret_cast<uint32_t*>(st_key + JR_TILE);         // [JR_TILE] staged row ids
+  uint32_t* st_dst = st_row + JR_TILE;                                      // [JR_TILE] output position of the staged row
+  uint32_t* H = st_dst + JR_TILE;                                           // [1024 + 32] bucket counts of the tile
+  uint2* HD = reinterpret_cast<uint2*>(H + 1056);                           // [1024] {offset in the staging area, output position of the first row}
+  __shared__ uint32_t wsum[JR_NT / 32];
+  __shared__ uint32_t sh_total;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool fast = col.dtype == PDRS_I64 && !col.nulls;
+  const long long tstride = (long long)gridDim.x * JR_TILE;
+  long long t0 = (long long)blockIdx.x * JR_TILE;
+  u64 key[JR_ITEMS];
+  auto load_tile = [&](long long tb) {
+#pragma unroll
+    for (int j = 0; j < JR_ITEMS; j++) { const long long i = tb + (long long)j * JR_NT + tid; key[j] = i < n ? (u64)__ldcs((const long long*)col.data + i) : 0ull; }
+  };
+  if (fast && t0 < n) load_tile(t0);
+  for (; t0 < n; t0 += tstride) {
+    for (int i = tid; i < 1056; i += JR_NT) H[i] = 0;
+    __syncthreads();
+    uint32_t br[JR_ITEMS];            // bucket << 16 | rank inside the bucket (tile <= 8192 rows); all ones = no row
+#pragma unroll
+    for (int j = 0; j < JR_ITEMS; j++) {
+      const long long i = t0 + (long long)j * JR_NT + tid;
+      br[j] = 0xFFFFFFFFu;
+      bool live = i < n;
+      if (!fast) live = live && jload_key(col, i, &key[j]);
+      if (live) { const uint32_t b = jbucket_nb(key[j], nb); br[j] = (b << 16) | atomicAdd(&H[b], 1u); }
+    }
+    __syncthreads();
+    {   // exclusive scan of the bucket counts (thread t owns bucket t) + one global reservation per bucket
+      const uint32_t c = H[tid];
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
+      if (lane == 31) wsum[warp] = incl;
+      uint32_t g = 0xFFFFFFFFu;
+      if (c) { const u64 at = atomicAdd(&cursor[tid], (u64)c); if (at + c > (u64)cap) atomicAdd(overflow, 1ull); else g = (uint32_t)((u64)tid * (u64)cap + at); }
+      __syncthreads();
+      uint32_t ws = wsum[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
+      const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
+      const uint32_t excl = (warp ? wprefix : 0u) + incl - c;
+      HD[tid] = make_uint2(excl, g);
+      if (tid == JR_NT - 1) sh_total = excl + c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < JR_ITEMS; j++) {
+      if (br[j] == 0xFFFFFFFFu) continue;
+      const uint2 hd = HD[br[j] >> 16];
+      const uint32_t rank = br[j] & 0xFFFFu, pos = hd.x + rank;
+      st_key[pos] = key[j];
+      st_row[pos] = (uint32_t)(t0 + (long long)j * JR_NT + tid);
+      st_dst[pos] = hd.y == 0xFFFFFFFFu ? 0xFFFFFFFFu : hd.y + rank;       // all ones: the bucket overflowed, the caller discards this partitioning
+    }
+    if (fast && t0 + tstride < n) load_tile(t0 + tstride);
+    __syncthreads();
+    const uint32_t total = sh_total;
+    for (uint32_t pos = tid; pos < total; pos += JR_NT) {     // consecutive staged rows of a bucket go to consecutive output rows
+      const uint32_t d = st_dst[pos];
+      if (d == 0xFFFFFFFFu) continue;
+      out_keys[d] = st_key[pos];
+      out_rows[d] = st_row[pos];
+    }
+    for (int p = 0; p < pay.n; p++) {      // payload columns: the same tile, the same positions, through the same staging buffer
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < JR_ITEMS; j++) {
+        if (br[j] == 0xFFFFFFFFu) continue;
+        const long long i = t0 + (long long)j * JR_NT + tid;
+        u64 v = __ldcs(pay.src[p] + i);
+        if (pay.nulls[p] && pdrs_bit(pay.nulls[p], i)) v = 0ull;          // a NULL source value yields the type default (join.rs:290-361)
+        st_key[HD[br[j] >> 16].x + (br[j] & 0xFFFFu)] = v;
+      }
+      __syncthreads();
+      u64* __restrict__ dst = pay.dst[p];
+      for (uint32_t pos = tid; pos < total; pos += JR_NT) {
+        const uint32_t d = st_dst[pos];
+        if (d != 0xFFFFFFFFu) dst[d] = st_key[pos];
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---- 32-byte slots {key, row, p0, p1}; linear probing, one slot = one sector; slot `nslots` belongs to the all-ones key
+struct JFatTab { ulonglong4* slots; uint32_t nslots; uint32_t nbmul; };
+static constexpr u64 JF_NOROW = ~0ull;
+// fail[0] rows that found no slot, fail[3] rows whose key was already there (duplicate build keys: the caller falls back)
+__global__ void __launch_bounds__(256) jfat_build_kernel(JFatTab t, const u64* __restrict__ pkeys, const uint32_t* __restrict__ prows, const u64* __restrict__ p0,
+                                                         const u64* __restrict__ p1, const u64* __restrict__ cnt, long long cap, u64* __restrict__ fail) {
+  const long long n = min((long long)__ldg(cnt), cap);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const u64 key = __ldcs(pkeys + i), row = (u64)__ldcs(prows + i);
+    const u64 a = p0 ? __ldcs(p0 + i) : 0ull, b = p1 ? __ldcs(p1 + i) : 0ull;
+    if (key == J_EMPTY_KEY) {
+      ulonglong4* s = t.slots + t.nslots;
+      if (atomicCAS(&s->y, JF_NOROW, row) != JF_NOROW) atomicAdd(&fail[3], 1ull); else { s->z = a; s->w = b; }
+      continue;
+    }
+    uint32_t s = __umulhi(jhash32(key) * t.nbmul, t.nslots), probe = 0;
+    for (; probe <= t.nslots; probe++) {
+      const u64 old = atomicCAS(&t.slots[s].x, J_EMPTY_KEY, key);
+      if (old == J_EMPTY_KEY) { t.slots[s].y = row; t.slots[s].z = a; t.slots[s].w = b; break; }
+      if (old == key) { atomicAdd(&fail[3], 1ull); break; }
+      s = s + 1 == t.nslots ? 0 : s + 1;
+    }
+    if (probe > t.nslots) atomicAdd(&fail[0], 1ull);
+  }
+}
+
+// Probe + emit of one bucket: every warp takes tickets of 512 probe rows (in order), works through them in units of 128
+// (4 slot loads per lane in flight), follows longer probe sequences in warp-synchronous rounds, compacts the pairs
+// with ballots and reserves the output with one atomic per unit.  Emits (left row, right row [, p0, p1]); Left join:
+// (left row, -1 [, 0, 0]).
+#define JF_ITEMS 4
+#define JF_UNIT (32 * JF_ITEMS)
+#define JF_TICKET (4 * JF_UNIT)
+__global__ void __launch_bounds__(256, 4) jfat_probe_emit_kernel(JFatTab t, const u64* __restrict__ pkeys, const uint32_t* __restrict__ prows, const u64* __restrict__ cnt,
+                                                               long long cap, int left_join, int npay, long long* __restrict__ out_l, long long* __restrict__ out_r,
+                                                               u64* __restrict__ out_p0, u64* __restrict__ out_p1, u64* __restrict__ out_cursor, u64* __restrict__ tile_ctr) {
+  constexpr uint32_t NONE = 0xFFFFFFFFu;
+  const long long n = min((long long)__ldg(cnt), cap);
+  const long long ntickets = (n + JF_TICKET - 1) / JF_TICKET;
+  const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+  const int lane = threadIdx.x & 31;
+  const uint32_t nslots = t.nslots, nbmul = t.nbmul;
+  const u64* tab = reinterpret_cast<const u64*>(t.slots);
+  for (;;) {
+    long long ticket = 0;
+    if (lane == 0) ticket = (long long)atomicAdd(tile_ctr, 1ull);
+    ticket = __shfl_sync(0xFFFFFFFFu, ticket, 0);
+    if (ticket >= ntickets) break;
+#pragma unroll 1
+    for (long long lo = ticket * JF_TICKET; lo < min(n, (ticket + 1) * JF_TICKET); lo += JF_UNIT) {
+      u64 key[JF_ITEMS], pa[JF_ITEMS], pb[JF_ITEMS];
+      uint32_t lrow[JF_ITEMS], slot[JF_ITEMS], rrow[JF_ITEMS];
+      uint32_t okmask = 0, pend = 0;
+#pragma unroll
+      for (int j = 0; j < JF_ITEMS; j++) {
+        const long long i = lo + j * 32 + lane;
+        key[j] = 0; lrow[j] = 0;
+        if (i < n) { key[j] = ld_stream_u64(pkeys + i, pol_stream); lrow[j] = ld_stream_u32(prows + i, pol_stream); okmask |= 1u << j; }
+      }
+      {
+        ulonglong4 v[JF_ITEMS];
+#pragma unroll
+        for (int j = 0; j < JF_ITEMS; j++) {
+          slot[j] = key[j] == J_EMPTY_KEY ? nslots : __umulhi(jhash32(key[j]) * nbmul, nslots);
+          v[j] = ld_bucket(tab + 4ull * slot[j], pol_keep);
+        }
+#pragma unroll
+        for (int j = 0; j < JF_ITEMS; j++) {
+          rrow[j] = NONE; pa[j] = 0; pb[j] = 0;
+          if (!((okmask >> j) & 1u)) continue;
+          bool hit = v[j].x == key[j];
+          if (key[j] == J_EMPTY_KEY) hit = v[j].y != JF_NOROW;                 // the reserved slot of the all-ones key
+          if (hit) { rrow[j] = (uint32_t)v[j].y; pa[j] = v[j].z; pb[j] = v[j].w; }
+          else if (v[j].x != J_EMPTY_KEY) pend |= 1u << j;
+        }
+      }
+      // rows displaced from their home slot: every lane follows the probe sequence of its first pending row per round
+      uint32_t steps = 0;
+      while (__any_sync(0xFFFFFFFFu, pend != 0)) {
+        const int j0 = pend ? __ffs(pend) - 1 : -1;
+        u64 k0 = 0;
+        uint32_t s0 = 0;
+#pragma unroll
+        for (int j = 0; j < JF_ITEMS; j++) if (j == j0) { k0 = key[j]; s0 = slot[j]; }
+        if (j0 >= 0) {
+          s0 = s0 + 1 >= nslots ? 0 : s0 + 1;
+          const ulonglong4 q = ld_bucket(tab + 4ull * s0, pol_keep);
+          const bool hit = q.x == k0, end = q.x == J_EMPTY_KEY || ++steps > nslots;
+#pragma unroll
+          for (int j = 0; j < JF_ITEMS; j++) if (j == j0) { slot[j] = s0; if (hit) { rrow[j] = (uint32_t)q.y; pa[j] = q.z; pb[j] = q.w; } }
+          if (hit || end) { pend &= ~(1u << j0); steps = 0; }
+        }
+      }
+      // compaction inside the warp: slab j = the 32 rows of item j; one output reservation per unit
+      uint32_t emit = 0, wcnt = 0, woff[JF_ITEMS];
+#pragma unroll
+      for (int j = 0; j < JF_ITEMS; j++) {
+        const bool e = ((okmask >> j) & 1u) && (left_join || rrow[j] != NONE);
+        const uint32_t m = __ballot_sync(0xFFFFFFFFu, e);
+        if (e) emit |= 1u << j;
+        woff[j] = wcnt + __popc(m & ((1u << lane) - 1u));
+        wcnt += __popc(m);
+      }
+      u64 base = 0;
+      if (lane == 0 && wcnt) base = atomicAdd(out_cursor, (u64)wcnt);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+#pragma unroll
+      for (int j = 0; j < JF_ITEMS; j++) {
+        if (!((emit >> j) & 1u)) continue;
+        const u64 o = base + woff[j];
+        st_stream_u64(out_l + o, (long long)lrow[j], pol_stream);
+        st_stream_u64(out_r + o, rrow[j] == NONE ? -1ll : (long long)rrow[j], pol_stream);
+        if (npay > 0) st_stream_u64(reinterpret_cast<long long*>(out_p0) + o, (long long)pa[j], pol_stream);
+        if (npay > 1) st_stream_u64(reinterpret_cast<long long*>(out_p1) + o, (long long)pb[j], pol_stream);
+      }
+    }
+  }
+}
+
+struct pdrs_join_result {
+  pdrs_ctx* ctx = nullptr;
+  int64_t n = 0;
+  DevBuf left, right;
+  int npay = 0;                       // pdrs_join_gather: materialised columns of the right frame
+  int pay_dtype[PDRS_MAX_VALS] = {};
+  DevBuf pay[PDRS_MAX_VALS];
+};
+
 struct JPart { DevBuf keys, rows; long long n = 0; };
 static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out) {
   const int nb = 1 << log_nb;
@@ -954,11 +1200,6 @@ static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log
   return PDRS_OK;
 }
 
-struct pdrs_join_result {
-  pdrs_ctx* ctx = nullptr;
-  int64_t n = 0;
-  DevBuf left, right;
-};
 
 // Build the table from `rsrc`, probe it with `lsrc` and materialise the pairs into `res` (left / right arrays).
 // nl_out = number of probe rows (capacity of the single-pass output); nl_eff / nr_eff = positions to scan (padded
@@ -1069,6 +1310,128 @@ static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& fail, const JSr
 }
 
 
+static int32_t join_aux_streams(pdrs_ctx* c) {
+  if (c->aux_stream[0]) return PDRS_OK;
+  for (int s = 0; s < 2; s++) {
+    PDRS_CUDA(c, cudaStreamCreateWithFlags(&c->aux_stream[s], cudaStreamNonBlocking));
+    PDRS_CUDA(c, cudaEventCreateWithFlags(&c->aux_done[s], cudaEventDisableTiming));
+  }
+  PDRS_CUDA(c, cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+  return PDRS_OK;
+}
+
+// Bucket-at-a-time join (see the comment above jpartp_kernel).  *done = false: not applicable (a padded bucket overflowed =
+// skewed keys, duplicate build keys, sizes) - nothing was emitted and the caller takes the one-table path.
+static int32_t join_bucketwise(pdrs_ctx* c, const ColView& lv, const ColView& rv, int how, const ColView* pay, int npay, pdrs_join_result* res, bool* done,
+                               const std::function<void(const char*)>& mark) {
+  *done = false;
+  const int64_t nl = lv.len, nr = rv.len;
+  if (nl >= (1ll << 32) - 1 || nr >= (1ll << 32) - 1 || nr < 1 || nl < 1 || npay > JP_MAXPAY) return PDRS_OK;
+  const bool fat = npay > 0;
+  const long long spk = c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3;                   // slots per build key
+  const size_t slot_bytes = fat ? 32 : 12;
+  const size_t region_target = (size_t)(c->opt_join_region_mb > 0 ? c->opt_join_region_mb : 24) << 20;
+  long long NB = (long long)(((size_t)nr * spk * slot_bytes + region_target - 1) / region_target);
+  if (c->opt_join_log_nb > 0) NB = 1ll << c->opt_join_log_nb;
+  NB = std::max<long long>(2, std::min<long long>(1024, NB));
+  auto cap_for = [&](long long n) {
+    const double m = (double)n / (double)NB;
+    const long long cap = (long long)(m + m / 32.0 + 6.0 * std::sqrt(m + 1.0)) + 1024;
+    return (cap + 4095) / 4096 * 4096;
+  };
+  const long long rcap = cap_for(nr), lcap = cap_for(nl);
+  if ((unsigned long long)NB * rcap >= (1ull << 32) - 1 || (unsigned long long)NB * lcap >= (1ull << 32) - 1) return PDRS_OK;   // 32-bit output positions
+  PDRS_TRY(join_aux_streams(c));
+  // ---- partition both sides (one pass each; the build side carries its payload columns)
+  DevBuf ctr, rk, rr, lk, lr, pk[JP_MAXPAY];
+  PDRS_TRY(ctr.alloc(c, (size_t)(2 * NB + 8 + 8 * NB) * 8, true));     // [NB] build cursors, [NB] probe cursors, [8] {overflow, out cursor}, [NB][8] per-bucket counters
+  u64* rcur = ctr.as<u64>();
+  u64* lcur = rcur + NB;
+  u64* glob = lcur + NB;                 // [0] overflowed reservations, [1] output cursor
+  u64* bctr = glob + 8;                  // per bucket: [0] failed inserts, [1] build tickets, [3] duplicate keys, [4] probe tickets
+  PDRS_TRY(rk.alloc(c, (size_t)NB * rcap * 8));
+  PDRS_TRY(rr.alloc(c, (size_t)NB * rcap * 4));
+  PDRS_TRY(lk.alloc(c, (size_t)NB * lcap * 8));
+  PDRS_TRY(lr.alloc(c, (size_t)NB * lcap * 4));
+  JPay jp{};
+  jp.n = npay;
+  for (int p = 0; p < npay; p++) {
+    PDRS_TRY(pk[p].alloc(c, (size_t)NB * rcap * 8));
+    jp.src[p] = reinterpret_cast<const u64*>(pay[p].data); jp.nulls[p] = pay[p].nulls; jp.dst[p] = pk[p].as<u64>();
+  }
+  PDRS_CUDA(c, cudaFuncSetAttribute(jpartp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JR_SMEM));
+  const JKeyCol rc{rv.data, rv.nulls, rv.dtype}, lc{lv.data, lv.nulls, lv.dtype};
+  jpartp_kernel<<<(int)std::max<long long>(1, std::min<long long>(c->sm_count, (nr + JR_TILE - 1) / JR_TILE)), JR_NT, JR_SMEM, c->stream>>>(
+      rc, nr, (uint32_t)NB, rcap, rcur, rk.as<u64>(), rr.as<uint32_t>(), glob, jp);
+  mark("partition build side");
+  jpartp_kernel<<<(int)std::max<long long>(1, std::min<long long>(c->sm_count, (nl + JR_TILE - 1) / JR_TILE)), JR_NT, JR_SMEM, c->stream>>>(
+      lc, nl, (uint32_t)NB, lcap, lcur, lk.as<u64>(), lr.as<uint32_t>(), glob, JPay{});
+  c->stats.kernel_launches += 2;
+  PDRS_CUDA(c, cudaGetLastError());
+  mark("partition probe side");
+  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, glob, 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (c->pinned_scalars[8] != 0) return PDRS_OK;                       // skewed keys: a bucket overflowed its padded range
+  // ---- two table regions, one per stream
+  const long long slots = (spk * rcap + 3) / 4 * 4;
+  const size_t region_bytes = fat ? (size_t)(slots + 1) * 32 : (size_t)(slots + 4) * 12;
+  DevBuf region[2];
+  for (int s = 0; s < 2; s++) PDRS_TRY(region[s].alloc(c, region_bytes + 256));
+  PDRS_TRY(res->left.alloc(c, (size_t)nl * 8));
+  PDRS_TRY(res->right.alloc(c, (size_t)nl * 8));
+  for (int p = 0; p < npay; p++) PDRS_TRY(res->pay[p].alloc(c, (size_t)nl * 8));
+  c->stats.table_slots = slots;
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+  PDRS_CUDA(c, cudaEventRecord(c->aux_fork, c->stream));
+  for (int s = 0; s < 2; s++) PDRS_CUDA(c, cudaStreamWaitEvent(c->aux_stream[s], c->aux_fork, 0));
+  const int bgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (rcap + 255) / 256));
+  const int tile_units = 2;                                            // compact probe: tickets of 512 rows
+  const long long ptickets = fat ? (lcap + JF_TICKET - 1) / JF_TICKET : (lcap + JE_UNIT * tile_units - 1) / (JE_UNIT * tile_units);
+  const int pgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 4, (ptickets + 7) / 8));
+  for (long long b = 0; b < NB; b++) {
+    const int s = (int)(b & 1);
+    cudaStream_t st = c->aux_stream[s];
+    u64* bc = bctr + 8 * b;
+    PDRS_CUDA(c, cudaMemsetAsync(region[s].p, 0xFF, region_bytes, st));      // key = all ones (EMPTY), head / row = all ones (none)
+    if (fat) {
+      const JFatTab ft{region[s].as<ulonglong4>(), (uint32_t)slots, (uint32_t)NB};
+      jfat_build_kernel<<<bgrid, 256, 0, st>>>(ft, rk.as<u64>() + b * rcap, rr.as<uint32_t>() + b * rcap, pk[0].as<u64>() + b * rcap,
+                                              npay > 1 ? pk[1].as<u64>() + b * rcap : nullptr, rcur + b, rcap, bc);
+      jfat_probe_emit_kernel<<<pgrid, 256, 0, st>>>(ft, lk.as<u64>() + b * lcap, lr.as<uint32_t>() + b * lcap, lcur + b, lcap, how == PDRS_LEFT, npay,
+                                                   res->left.as<long long>(), res->right.as<long long>(), res->pay[0].as<u64>(), res->pay[1].as<u64>(), glob + 1, bc + 4);
+    } else {
+      const JTab jt{region[s].as<u64>(), reinterpret_cast<uint32_t*>(region[s].as<u64>() + slots + 4), (u64)slots, (uint32_t)NB};
+      JSrc rs{}, ls{};
+      rs.pkeys = rk.as<u64>() + b * rcap; rs.prows = rr.as<uint32_t>() + b * rcap; rs.cap = rcap; rs.cnt = rcur + b;
+      ls.pkeys = lk.as<u64>() + b * lcap; ls.prows = lr.as<uint32_t>() + b * lcap; ls.cap = lcap; ls.cnt = lcur + b;
+      join_build_kernel<0><<<bgrid, 256, 0, st>>>(jt, nullptr, rs, rcap, bc);
+      join_probe_emit_kernel<<<pgrid, JE_THREADS, 0, st>>>(jt, ls, lcap, how == PDRS_LEFT, res->left.as<long long>(), res->right.as<long long>(), glob + 1, bc + 4, tile_units);
+    }
+  }
+  c->stats.kernel_launches += 2 * NB;
+  PDRS_CUDA(c, cudaGetLastError());
+  for (int s = 0; s < 2; s++) {
+    PDRS_CUDA(c, cudaEventRecord(c->aux_done[s], c->aux_stream[s]));
+    PDRS_CUDA(c, cudaStreamWaitEvent(c->stream, c->aux_done[s], 0));
+  }
+  if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+  mark("buckets: clear + build + probe");
+  std::vector<u64> hc((size_t)8 * NB + 8);
+  PDRS_CUDA(c, cudaMemcpyAsync(hc.data(), glob, hc.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  u64 failed = 0, dups = 0;
+  for (long long b = 0; b < NB; b++) { failed += hc[8 + 8 * b]; dups += hc[8 + 8 * b + 3]; }
+  if (failed) return pdrs_fail(c, PDRS_ERR_CUDA, "join build: hash table insertion failed for %llu rows", (unsigned long long)failed);
+  if (dups) {                                                          // duplicate build keys: the one-table path builds the CSR segments
+    res->left.release(); res->right.release();
+    for (int p = 0; p < npay; p++) res->pay[p].release();
+    return PDRS_OK;
+  }
+  res->n = (int64_t)hc[1];
+  *done = true;
+  return PDRS_OK;
+}
+
 extern "C" {
 
 int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, pdrs_join_result** out) {
@@ -1110,7 +1473,7 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   DevBuf tab, fail;
   PDRS_TRY(tab.alloc(c, table_bytes));
   PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));   // key = all ones (EMPTY), head = -1 (EMPTY)
-  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
+  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots, 1u};
   PDRS_TRY(fail.alloc(c, 64, true));      // [0] failed inserts, [1] build tile counter, [2] probe tile counter (two-pass) / output cursor (single pass), [3] duplicate build keys, [4] probe tile counter (single pass)
   c->stats.table_slots = slots;
   JKeyCol rc{rv.data, rv.nulls, rv.dtype}, lc{lv.data, lv.nulls, lv.dtype};
@@ -1391,7 +1754,7 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   DevBuf tab, fail, row0;
   PDRS_TRY(tab.alloc(c, table_bytes));
   PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));
-  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots};
+  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots, 1u};
   PDRS_TRY(fail.alloc(c, 64, true));
   PDRS_TRY(row0.alloc(c, 64));
   PDRS_CUDA(c, cudaMemcpyAsync(row0.p, left_row0, (size_t)x->world * 8, cudaMemcpyHostToDevice, c->stream));
