@@ -189,6 +189,17 @@ int32_t pdrs_hash_partition(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, 
  * result arrays are sized for one pair per left row; pdrs_join_len() gives the number of valid pairs. */
 int32_t pdrs_join_pairs(pdrs_ctx* ctx, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how,
                         pdrs_join_result** out);
+/* pdrs_join_pairs + the materialisation of columns of the RIGHT frame in one call: replaces the build / probe loops AND
+ * the per-column gather loops join_impl runs for the right frame's non-key columns (join.rs:107-208 + 290-552):
+ *   out column k, pair j = right_row[j] < 0 || right_cols[k][right_row[j]] is NULL ? type default : right_cols[k][right_row[j]]
+ * (no null mask, defaults as in pdrs_gather).  Same pairs, same order rules as pdrs_join_pairs.  Inner / Left joins of large
+ * inputs on unique build keys carry up to two Int64 / Float64 columns WITH the build rows - through the radix partition
+ * and inside 32-byte hash-table slots {key, row, c0, c1} - so a match yields its column values in the L2 sector the key
+ * comparison read anyway; everything else is gathered by right row after the join.  The results are identical. */
+int32_t pdrs_join_gather(pdrs_ctx* ctx, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how,
+                         const pdrs_col* right_cols, int32_t n_right_cols, pdrs_join_result** out);
+int32_t pdrs_join_right_col(const pdrs_join_result* r, int32_t k, void* out_host);   /* pdrs_join_len() values of the column's physical type (BOOL: one byte each) */
+const void* pdrs_join_right_col_dev(const pdrs_join_result* r, int32_t k);
 int64_t pdrs_join_len(const pdrs_join_result* r);
 int32_t pdrs_join_indices(const pdrs_join_result* r, int64_t* left_out, int64_t* right_out); /* host copy-out */
 const int64_t* pdrs_join_left_dev(const pdrs_join_result* r);

@@ -75,6 +75,9 @@ SIGNATURES = {
     "pdrs_groupby_merge": (_i32, [_vp, _P(PdrsCol), _i32, _P(_vp), _P(_i32), _i32, _i64, _P(PdrsAgg), _i32, _P(_vp)]),
     "pdrs_hash_partition": (_i32, [_vp, _P(PdrsCol), _i32, _i32, _vp, _P(_i64)]),
     "pdrs_join_pairs": (_i32, [_vp, _P(PdrsCol), _P(PdrsCol), _i32, _P(_vp)]),
+    "pdrs_join_gather": (_i32, [_vp, _P(PdrsCol), _P(PdrsCol), _i32, _P(PdrsCol), _i32, _P(_vp)]),
+    "pdrs_join_right_col": (_i32, [_vp, _i32, _vp]),
+    "pdrs_join_right_col_dev": (_vp, [_vp, _i32]),
     "pdrs_join_len": (_i64, [_vp]),
     "pdrs_join_indices": (_i32, [_vp, _vp, _vp]),
     "pdrs_join_left_dev": (_vp, [_vp]),

@@ -143,9 +143,19 @@ class GroupByResult:
 
 
 class JoinResult:
-    def __init__(self, ctx: "Context", handle):
+    def __init__(self, ctx: "Context", handle, right_dtypes=()):
         self.ctx, self._h = ctx, handle
         self.n = int(ctx.L.pdrs_join_len(handle))
+        self.right_dtypes = list(right_dtypes)
+
+    def right_col(self, k: int) -> np.ndarray:
+        """Column k of the right frame materialised along the pairs (pdrs_join_gather)."""
+        out = np.empty(self.n, NP_DTYPE[self.right_dtypes[k]])
+        if self.n:
+            self.ctx._chk(self.ctx.L.pdrs_join_right_col(self._h, k, out.ctypes.data))
+        return out
+
+    def right_col_dev(self, k: int): return self.ctx.L.pdrs_join_right_col_dev(self._h, k)
 
     def indices(self):
         li = np.empty(self.n, np.int64)
@@ -367,6 +377,14 @@ class Context:
         h = C.c_void_p()
         self._chk(self.L.pdrs_join_pairs(self._h, C.byref(lc), C.byref(rc), how, C.byref(h)))
         return JoinResult(self, h)
+
+    def join_gather(self, left: Column, right: Column, how: int, right_cols: Sequence[Column]) -> JoinResult:
+        """join_impl's build / probe plus the materialisation of the right frame's columns (join.rs:107-208, 290-552)."""
+        lc, rc = left.c(), right.c()
+        cols = self._cols(right_cols)
+        h = C.c_void_p()
+        self._chk(self.L.pdrs_join_gather(self._h, C.byref(lc), C.byref(rc), how, cols, len(right_cols), C.byref(h)))
+        return JoinResult(self, h, [c.dtype for c in right_cols])
 
     def gather(self, col: Column, idx, n: Optional[int] = None, idx_dev: bool = False, out_dev: Optional[int] = None):
         """join.rs:290-552 / data_ops.rs:124-211: default-filled gather without a null mask."""

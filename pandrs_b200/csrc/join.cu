@@ -1434,10 +1434,15 @@ static int32_t join_bucketwise(pdrs_ctx* c, const ColView& lv, const ColView& rv
 
 extern "C" {
 
-int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, pdrs_join_result** out) {
+}  // extern "C"
+
+// pdrs_join_pairs (nrcols == 0) and pdrs_join_gather (columns of the right frame materialised along with the pairs)
+static int32_t join_run(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, const pdrs_col* rcols, int32_t nrcols, pdrs_join_result** out) {
   if (!c) return PDRS_ERR_BAD_ARG;
-  if (!left_key || !right_key || !out) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_pairs: NULL argument");
+  if (!left_key || !right_key || !out || nrcols < 0 || nrcols > PDRS_MAX_VALS || (nrcols && !rcols)) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join: bad argument");
   if (how < PDRS_INNER || how > PDRS_OUTER) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown join type %d", how);
+  for (int k = 0; k < nrcols; k++)
+    if (rcols[k].len != right_key->len) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "right column %d has %lld rows, the key column %lld", k, (long long)rcols[k].len, (long long)right_key->len);
   const int32_t how_req = how;
   how = (how == PDRS_RIGHT) ? PDRS_INNER : (how == PDRS_OUTER ? PDRS_LEFT : how);   // Right / Outer = Inner / Left + the unmatched right rows
   if (left_key->dtype != right_key->dtype)   // join.rs:98-104
@@ -1470,6 +1475,20 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); marks.push_back({name, e});
   };
   mark("start");
+  // Bucket-at-a-time path: unique, hash-uniform build keys (the usual dimension-table join).  Up to JP_MAXPAY 8-byte
+  // columns of the right frame travel with the build rows and come out with the pairs (pdrs_join_gather).
+  bool fused_pay = nrcols > 0 && nrcols <= JP_MAXPAY && how_req <= PDRS_LEFT;
+  for (int k = 0; k < nrcols; k++) fused_pay = fused_pay && (rcols[k].dtype == PDRS_I64 || rcols[k].dtype == PDRS_F64);
+  bool bucketwise_done = false;
+  long long nl_eff = nl, nr_eff = nr;
+  int64_t M = 0;
+  if (radix && c->opt_join_bucketwise != 0 && c->opt_join_part != 2 && c->opt_join_emit != 2) {
+    std::vector<ColView> pv(fused_pay ? nrcols : 0);
+    for (size_t k = 0; k < pv.size(); k++) PDRS_TRY(pdrs_view_col(c, &rcols[k], &pv[k]));
+    PDRS_TRY(join_bucketwise(c, lv, rv, how, pv.data(), (int)pv.size(), res, &bucketwise_done, mark));
+    if (bucketwise_done) { M = res->n; c->stats.groupby_algo_used = 3; if (fused_pay) { res->npay = nrcols; for (int k = 0; k < nrcols; k++) res->pay_dtype[k] = rcols[k].dtype; } }
+  }
+  if (!bucketwise_done) {
   DevBuf tab, fail;
   PDRS_TRY(tab.alloc(c, table_bytes));
   PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));   // key = all ones (EMPTY), head = -1 (EMPTY)
@@ -1480,7 +1499,6 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   JPart lp, rp;
   DevBuf lcnt, rcnt;
   JSrc rsrc{rc, nullptr, nullptr, 0, nullptr, 0}, lsrc{lc, nullptr, nullptr, 0, nullptr, 0};
-  long long nl_eff = nl, nr_eff = nr;
   if (radix) {
     mark("memset");
     // one-pass partition into padded buckets; exact two-pass partition when a bucket overflows (skewed keys)
@@ -1498,9 +1516,10 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
     rsrc.pkeys = rp.keys.as<u64>(); rsrc.prows = rp.rows.as<uint32_t>(); nr_eff = rp.n;
     lsrc.pkeys = lp.keys.as<u64>(); lsrc.prows = lp.rows.as<uint32_t>(); nl_eff = lp.n;
   }
-  int64_t M = 0;
   PDRS_TRY(jbuild_probe(c, jt, fail, rsrc, nr_eff, nr, lsrc, nl_eff, nl, radix, how, res, &M, mark));
   mark("write");
+  c->stats.groupby_algo_used = radix ? 2 : 1;
+  }
   if (how_req == PDRS_RIGHT || how_req == PDRS_OUTER) {
     DevBuf matched, ucounts;
     PDRS_TRY(matched.alloc(c, (size_t)std::max<int64_t>(nr, 1), true));
@@ -1533,7 +1552,18 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
     PDRS_CUDA(c, cudaGetLastError());
     mark("unmatched right rows");
   }
-  c->stats.groupby_algo_used = radix ? 2 : 1;
+  // columns of the right frame that did not travel with the build rows: gathered by right row, type default for a missing
+  // side or a NULL source value, no null mask (join.rs:290-552)
+  if (nrcols > 0 && res->npay == 0) {
+    for (int k = 0; k < nrcols; k++) {
+      const int esz = rcols[k].dtype == PDRS_BOOL_BITS ? 1 : pdrs_dtype_bytes(rcols[k].dtype);
+      PDRS_TRY(res->pay[k].alloc(c, (size_t)std::max<int64_t>(res->n, 1) * esz));
+      res->pay_dtype[k] = rcols[k].dtype;
+      PDRS_TRY(pdrs_gather(c, &rcols[k], res->right.as<int64_t>(), PDRS_MEM_DEVICE, res->n, res->pay[k].p, PDRS_MEM_DEVICE));
+    }
+    res->npay = nrcols;
+    mark("gather right columns");
+  }
   if (!marks.empty()) {
     cudaStreamSynchronize(c->stream);
     for (size_t i = 1; i < marks.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, marks[i - 1].second, marks[i].second); fprintf(stderr, "[pdrs join] %-22s %8.3f ms\n", marks[i].first, ms); }
@@ -1550,6 +1580,17 @@ int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   guard.r = nullptr;
   *out = res;
   return PDRS_OK;
+}
+
+extern "C" {
+
+int32_t pdrs_join_pairs(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, pdrs_join_result** out) {
+  return join_run(c, left_key, right_key, how, nullptr, 0, out);
+}
+
+int32_t pdrs_join_gather(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, const pdrs_col* right_cols, int32_t n_right_cols,
+                         pdrs_join_result** out) {
+  return join_run(c, left_key, right_key, how, right_cols, n_right_cols, out);
 }
 
 // ---------------------------------------------------------------- multi-GPU join: fused partition + shuffle over peer memory
@@ -1820,6 +1861,17 @@ int32_t pdrs_join_indices(const pdrs_join_result* r, int64_t* left_out, int64_t*
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
   return PDRS_OK;
 }
+int32_t pdrs_join_right_col(const pdrs_join_result* r, int32_t k, void* out_host) {
+  if (!r || k < 0 || k >= r->npay) return PDRS_ERR_BAD_ARG;
+  pdrs_ctx* c = r->ctx;
+  if (r->n == 0) return PDRS_OK;
+  if (!out_host) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_right_col: NULL output");
+  const int esz = r->pay_dtype[k] == PDRS_BOOL_BITS ? 1 : pdrs_dtype_bytes(r->pay_dtype[k]);
+  PDRS_CUDA(c, cudaMemcpyAsync(out_host, r->pay[k].p, (size_t)r->n * esz, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PDRS_OK;
+}
+const void* pdrs_join_right_col_dev(const pdrs_join_result* r, int32_t k) { return (r && k >= 0 && k < r->npay) ? r->pay[k].p : nullptr; }
 const int64_t* pdrs_join_left_dev(const pdrs_join_result* r) { return r ? r->left.as<int64_t>() : nullptr; }
 const int64_t* pdrs_join_right_dev(const pdrs_join_result* r) { return r ? r->right.as<int64_t>() : nullptr; }
 void pdrs_join_result_free(pdrs_join_result* r) {

@@ -528,13 +528,85 @@ def test_join_radix_partitioned_path(ctx, oracle, how):
         Ru = Spec(pb.I64, oracle.synth_join_keys(nb, unique=True))
         Lu = Spec(pb.I64, oracle.synth_join_keys(npr, domain=2 * nb))
         compare_join(pb, oracle, ctx, Lu, Ru, how, device=True, check_order=False)
-        assert ctx.stats()["groupby_algo_used"] == 2
+        assert ctx.stats()["groupby_algo_used"] == 3          # unique build keys: bucket-at-a-time, one reused table region
+        ctx.set_option("join_bucketwise", 0)
+        try:
+            compare_join(pb, oracle, ctx, Lu, Ru, how, device=True, check_order=False)
+            assert ctx.stats()["groupby_algo_used"] == 2      # one table for all buckets
+        finally:
+            ctx.set_option("join_bucketwise", 1)
         pool = [f"k{i}" for i in range(300)]
         Ld = Spec(pb.DICT_U32, rng.integers(0, 300, 5000).astype(np.uint32), pool=pool)
         Rd = Spec(pb.DICT_U32, rng.integers(0, 300, 700).astype(np.uint32), pool=pool)
         compare_join(pb, oracle, ctx, Ld, Rd, how, check_order=False)
     finally:
         ctx.set_option("join_algo", 0)
+
+
+def _compare_join_gather(ctx, oracle, L, R, how, cols, device=True):
+    """pdrs_join_gather against oracle join + oracle gather (join.rs:290-552), pair by pair after the canonical sort."""
+    lc, rc, cc = L.gpu(pb), R.gpu(pb), [c.gpu(pb) for c in cols]
+    ups = []
+    if device:
+        lc, rc = ctx.upload(lc), ctx.upload(rc)
+        cc = [ctx.upload(c) for c in cc]
+        ups = [lc, rc] + cc
+    j = ctx.join_gather(lc, rc, how, cc)
+    try:
+        gl, gr = j.indices()
+        got = [j.right_col(k) for k in range(len(cols))]
+    finally:
+        j.close()
+        for c in ups:
+            ctx.free(c)
+    wl, wr = oracle.join(L.cpu(oracle), R.cpu(oracle), how)
+    assert len(gl) == len(wl)
+    order = np.lexsort((gr, gl))
+    worder = np.lexsort((wr, wl))
+    assert np.array_equal(gl[order], wl[worder]) and np.array_equal(gr[order], wr[worder])
+    for k, c in enumerate(cols):
+        want = oracle.gather(c.cpu(oracle), wr[worder])
+        g = got[k][order]
+        if c.dtype == pb.F64:
+            assert np.array_equal(g.view(np.uint64), want.view(np.uint64)), k
+        else:
+            assert np.array_equal(g, want), k
+
+
+@pytest.mark.parametrize("how", [pb.INNER, pb.LEFT])
+def test_join_gather_right_columns(ctx, oracle, how):
+    # BASELINE.json configs[2]: unique i64 build keys + 2 payload columns of the build side.  Large inputs: the columns travel
+    # with the build rows through the partition and the 32-byte table slots; everything else (small inputs, other dtypes,
+    # more than two columns, duplicate keys, Right / Outer) gathers by right row.  Same results either way.
+    rng = np.random.default_rng(81)
+    nb, npr = 200_000, 1_500_007
+    Ru = Spec(pb.I64, oracle.synth_join_keys(nb, unique=True))
+    Lu = Spec(pb.I64, oracle.synth_join_keys(npr, domain=2 * nb), nulls=rng.random(npr) < 0.01)
+    p_i = Spec(pb.I64, rng.integers(-2**62, 2**62, nb), nulls=rng.random(nb) < 0.1)
+    p_f = Spec(pb.F64, rng.normal(0, 1e6, nb))
+    p_f.values[::97] = np.nan
+    p_32 = Spec(pb.I32, rng.integers(-1000, 1000, nb).astype(np.int32))
+    p_b = Spec(pb.BOOL_BITS, rng.random(nb) < 0.5, nulls=rng.random(nb) < 0.1)
+    _compare_join_gather(ctx, oracle, Lu, Ru, how, [p_i, p_f])                      # small table: direct path + gathers
+    ctx.set_option("join_algo", 2)
+    try:
+        for cols in ([p_f], [p_i, p_f]):
+            _compare_join_gather(ctx, oracle, Lu, Ru, how, cols)
+            assert ctx.stats()["groupby_algo_used"] == 3
+        _compare_join_gather(ctx, oracle, Lu, Ru, how, [p_i, p_f], device=False)    # host columns
+        _compare_join_gather(ctx, oracle, Lu, Ru, how, [p_i, p_f, p_32, p_b])      # more than two columns / other dtypes: gathered
+        keys_with_ones = Ru.values.copy()
+        keys_with_ones[7] = -1                                                       # the all-ones key lives in a reserved slot
+        Lones = Lu.values.copy()
+        Lones[::1000] = -1
+        _compare_join_gather(ctx, oracle, Spec(pb.I64, Lones), Spec(pb.I64, keys_with_ones), how, [p_i, p_f])
+        Rd = Spec(pb.I64, rng.integers(0, 50_000, nb))                               # duplicate build keys: falls back, same answer
+        Ld = Spec(pb.I64, rng.integers(0, 60_000, 300_000))
+        _compare_join_gather(ctx, oracle, Ld, Rd, how, [p_i, p_f])
+    finally:
+        ctx.set_option("join_algo", 0)
+    _compare_join_gather(ctx, oracle, Spec(pb.I64, [1, 2, 3]), Spec(pb.I64, [3, 1, 1]), pb.OUTER if how == pb.LEFT else pb.RIGHT,
+                         [Spec(pb.F64, [0.5, 1.5, 2.5]), Spec(pb.I64, [7, 8, 9])], device=False)
 
 
 @pytest.mark.parametrize("dtype", ["f64", "i32", "dict", "bool"])
