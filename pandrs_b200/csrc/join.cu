@@ -203,12 +203,17 @@ __global__ void __launch_bounds__(256) join_build_kernel(JTab t, uint32_t* __res
       }
       if (todo) { atomicAdd(fail, (u64)__popc(todo)); live &= ~todo; }
       if (MODE == 0) {
-        uint32_t old[JB_ITEMS];
-#pragma unroll
-        for (int j = 0; j < JB_ITEMS; j++) if ((live >> j) & 1u) old[j] = atomicExch(&t.heads[slot[j]], (uint32_t)r[j]);
+        // the lane whose CAS claimed the slot owns its head word: a plain store (measured: the build is bound by the SMs'
+        // atomic issue rate, ~50 G returning atomics / s - one atomic per row instead of two).  A CAS that found the key
+        // already there = duplicate build keys: the head words are rebuilt by the CSR passes, nothing to store here.
         uint32_t dups = 0;
 #pragma unroll
-        for (int j = 0; j < JB_ITEMS; j++) if (((live >> j) & 1u) && old[j] != JH_EMPTY) dups++;
+        for (int j = 0; j < JB_ITEMS; j++) {
+          if (!((live >> j) & 1u)) continue;
+          if (key[j] == J_EMPTY_KEY) { if (atomicExch(&t.heads[slot[j]], (uint32_t)r[j]) != JH_EMPTY) dups++; }      // reserved slot: no CAS on a key word
+          else if (seen[j] == J_EMPTY_KEY) t.heads[slot[j]] = (uint32_t)r[j];
+          else dups++;
+        }
         if (dups) atomicAdd(&fail[3], (u64)dups);       // duplicate build keys: the single-pass probe does not apply
       } else if (MODE == 1) {
 #pragma unroll
@@ -1387,7 +1392,7 @@ static int32_t join_bucketwise(pdrs_ctx* c, const ColView& lv, const ColView& rv
   const int bgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (rcap + 255) / 256));
   const int tile_units = 2;                                            // compact probe: tickets of 512 rows
   const long long ptickets = fat ? (lcap + JF_TICKET - 1) / JF_TICKET : (lcap + JE_UNIT * tile_units - 1) / (JE_UNIT * tile_units);
-  const int pgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 4, (ptickets + 7) / 8));
+  const int pgrid = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * (c->opt_join_ctas_per_sm > 0 ? c->opt_join_ctas_per_sm : 4), (ptickets + 7) / 8));
   for (long long b = 0; b < NB; b++) {
     const int s = (int)(b & 1);
     cudaStream_t st = c->aux_stream[s];
@@ -1482,7 +1487,10 @@ static int32_t join_run(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   bool bucketwise_done = false;
   long long nl_eff = nl, nr_eff = nr;
   int64_t M = 0;
-  if (radix && c->opt_join_bucketwise != 0 && c->opt_join_part != 2 && c->opt_join_emit != 2) {
+  // Measured (1e9 x 1e8, profiles/join_phases_r02.txt): for pairs only the one-table path is faster (the per-bucket launches do
+  // not overlap enough to pay for themselves, 21.2 vs 18.9 ms); with payload columns the bucket-at-a-time path wins (31.8 vs
+  // 41.9 ms with gathers).  join_bucketwise: 1 = auto (payload columns only), 2 = always, 0 = never.
+  if (radix && (c->opt_join_bucketwise == 2 || (c->opt_join_bucketwise == 1 && fused_pay)) && c->opt_join_part != 2 && c->opt_join_emit != 2) {
     std::vector<ColView> pv(fused_pay ? nrcols : 0);
     for (size_t k = 0; k < pv.size(); k++) PDRS_TRY(pdrs_view_col(c, &rcols[k], &pv[k]));
     PDRS_TRY(join_bucketwise(c, lv, rv, how, pv.data(), (int)pv.size(), res, &bucketwise_done, mark));

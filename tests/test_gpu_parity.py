@@ -528,11 +528,13 @@ def test_join_radix_partitioned_path(ctx, oracle, how):
         Ru = Spec(pb.I64, oracle.synth_join_keys(nb, unique=True))
         Lu = Spec(pb.I64, oracle.synth_join_keys(npr, domain=2 * nb))
         compare_join(pb, oracle, ctx, Lu, Ru, how, device=True, check_order=False)
-        assert ctx.stats()["groupby_algo_used"] == 3          # unique build keys: bucket-at-a-time, one reused table region
-        ctx.set_option("join_bucketwise", 0)
+        assert ctx.stats()["groupby_algo_used"] == 2          # one table for all buckets
+        ctx.set_option("join_bucketwise", 2)
         try:
             compare_join(pb, oracle, ctx, Lu, Ru, how, device=True, check_order=False)
-            assert ctx.stats()["groupby_algo_used"] == 2      # one table for all buckets
+            assert ctx.stats()["groupby_algo_used"] == 3      # bucket-at-a-time, one reused table region (default with payload columns)
+            compare_join(pb, oracle, ctx, L, R, how, check_order=False)     # duplicate build keys: detected, falls back to the one-table path
+            assert ctx.stats()["groupby_algo_used"] == 2
         finally:
             ctx.set_option("join_bucketwise", 1)
         pool = [f"k{i}" for i in range(300)]
