@@ -78,13 +78,26 @@ typedef struct pdrs_agg {
   int32_t op;               /* pdrs_agg_op */
 } pdrs_agg;
 
+/* A typed row predicate `column <op> constant` (Int64 / Float64 column): what a caller would otherwise turn into a Boolean
+ * column first and pass as `filter` (LazyFrame filter step, src/optimized/lazy.rs:170-182; data_ops.rs:37-62).  A NULL
+ * in the column keeps the row out, like a NULL in a Boolean filter column. */
+typedef enum pdrs_cmp_op { PDRS_CMP_LT = 0, PDRS_CMP_LE = 1, PDRS_CMP_GT = 2, PDRS_CMP_GE = 3, PDRS_CMP_EQ = 4, PDRS_CMP_NE = 5 } pdrs_cmp_op;
+typedef struct pdrs_pred {
+  pdrs_col col;             /* PDRS_I64 or PDRS_F64 */
+  int32_t op;               /* pdrs_cmp_op */
+  int32_t reserved;
+  int64_t ival;             /* constant for PDRS_I64 columns */
+  double fval;              /* constant for PDRS_F64 columns */
+} pdrs_pred;
+
 typedef enum pdrs_groupby_algo {
   PDRS_GB_AUTO = 0,
   PDRS_GB_SHARED = 1,       /* per-warp tables in shared memory, spill to the global table */
   PDRS_GB_GLOBAL = 2,       /* global open-addressing table only (high cardinality) */
   PDRS_GB_DENSE = 3,        /* direct-mapped shared tables for small dense integer key ranges */
   PDRS_GB_TILESORT = 4,     /* tile sort in shared memory + per-thread register aggregation (tens to ~2000 groups) */
-  PDRS_GB_PARTITIONED = 5   /* reported only: hash-partitioned rows + tile sort per partition (thousands to millions of groups) */
+  PDRS_GB_PARTITIONED = 5,  /* reported only: hash-partitioned rows + tile sort per partition (thousands to millions of groups) */
+  PDRS_GB_FEW = 6           /* reported only: <= 16 groups, sum / mean / count of up to 8 value columns in ONE scan (lane-private accumulators) */
 } pdrs_groupby_algo;
 
 typedef struct pdrs_options {
@@ -144,6 +157,12 @@ int32_t pdrs_host_free(pdrs_ctx* ctx, void* p);
 int32_t pdrs_groupby_agg(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals,
                          int32_t nvals, const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter,
                          pdrs_groupby_result** out);
+/* The same with a typed predicate evaluated inside the scan (filter and pred may both be given: rows must pass both).
+ * Fuses the comparison that would have produced the Boolean filter column: +8 bytes per row instead of a separate pass
+ * (the 48 B/row variant of configs[4]). */
+int32_t pdrs_groupby_agg_where(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
+                               const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, const pdrs_pred* pred,
+                               pdrs_groupby_result** out);
 int64_t pdrs_groupby_n_groups(const pdrs_groupby_result* r);
 /* copy-out to host: key k as its physical type (i64/f64/u32/i32; BOOL as one byte per group) + 1 byte
  * per group that is 1 where the key part is NULL (the Rust side prints "NULL", grouping.rs:74) */

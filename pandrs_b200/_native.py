@@ -18,7 +18,8 @@ I64, F64, DICT_U32, BOOL_BITS, I32 = 0, 1, 2, 3, 4
 SUM, MEAN, MIN, MAX, COUNT, STD, VAR = range(7)
 INNER, LEFT, RIGHT, OUTER = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
-GB_AUTO, GB_SHARED, GB_GLOBAL, GB_DENSE, GB_TILESORT, GB_PARTITIONED = 0, 1, 2, 3, 4, 5
+GB_AUTO, GB_SHARED, GB_GLOBAL, GB_DENSE, GB_TILESORT, GB_PARTITIONED, GB_FEW = 0, 1, 2, 3, 4, 5, 6
+CMP_LT, CMP_LE, CMP_GT, CMP_GE, CMP_EQ, CMP_NE = 0, 1, 2, 3, 4, 5
 
 OK, ERR_BAD_ARG, ERR_TYPE_MISMATCH, ERR_OOM, ERR_CUDA, ERR_NCCL, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6
 
@@ -30,6 +31,10 @@ class PdrsCol(C.Structure):
 
 class PdrsAgg(C.Structure):
     _fields_ = [("value_col", C.c_int32), ("op", C.c_int32)]
+
+
+class PdrsPred(C.Structure):
+    _fields_ = [("col", PdrsCol), ("op", C.c_int32), ("reserved", C.c_int32), ("ival", C.c_int64), ("fval", C.c_double)]
 
 
 class PdrsOptions(C.Structure):
@@ -60,6 +65,7 @@ SIGNATURES = {
     "pdrs_host_alloc": (_i32, [_vp, _i64, _P(_vp)]),
     "pdrs_host_free": (_i32, [_vp, _vp]),
     "pdrs_groupby_agg": (_i32, [_vp, _P(PdrsCol), _i32, _P(PdrsCol), _i32, _P(PdrsAgg), _i32, _P(PdrsCol), _P(_vp)]),
+    "pdrs_groupby_agg_where": (_i32, [_vp, _P(PdrsCol), _i32, _P(PdrsCol), _i32, _P(PdrsAgg), _i32, _P(PdrsCol), _P(PdrsPred), _P(_vp)]),
     "pdrs_groupby_n_groups": (_i64, [_vp]),
     "pdrs_groupby_key": (_i32, [_vp, _i32, _vp, _vp]),
     "pdrs_groupby_agg_values": (_i32, [_vp, _i32, _vp]),

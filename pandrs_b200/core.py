@@ -340,13 +340,20 @@ class Context:
         arr = (N.PdrsCol * max(1, len(cols)))(*[c.c() for c in cols])
         return arr
 
-    def groupby_agg(self, keys: Sequence[Column], vals: Sequence[Column], aggs: Sequence[tuple], filter: Optional[Column] = None) -> GroupByResult:
-        """aggs: [(value_col_index, op)].  Replaces group_by(...).aggregate(...) (grouping.rs:38, aggregation.rs:763)."""
+    def groupby_agg(self, keys: Sequence[Column], vals: Sequence[Column], aggs: Sequence[tuple], filter: Optional[Column] = None,
+                    pred: Optional[tuple] = None) -> GroupByResult:
+        """aggs: [(value_col_index, op)].  Replaces group_by(...).aggregate(...) (grouping.rs:38, aggregation.rs:763).
+        pred: (column, cmp op, constant) - a typed row predicate evaluated inside the scan (pdrs_groupby_agg_where)."""
         ka, va = self._cols(keys), self._cols(vals)
         aa = (N.PdrsAgg * max(1, len(aggs)))(*[N.PdrsAgg(int(v), int(op)) for v, op in aggs])
         f = filter.c() if filter is not None else None
         h = C.c_void_p()
-        self._chk(self.L.pdrs_groupby_agg(self._h, ka, len(keys), va, len(vals), aa, len(aggs), C.byref(f) if f is not None else None, C.byref(h)))
+        if pred is not None:
+            col, op, const = pred
+            pp = N.PdrsPred(col.c(), int(op), 0, int(const) if col.dtype == I64 else 0, float(const))
+            self._chk(self.L.pdrs_groupby_agg_where(self._h, ka, len(keys), va, len(vals), aa, len(aggs), C.byref(f) if f is not None else None, C.byref(pp), C.byref(h)))
+        else:
+            self._chk(self.L.pdrs_groupby_agg(self._h, ka, len(keys), va, len(vals), aa, len(aggs), C.byref(f) if f is not None else None, C.byref(h)))
         return GroupByResult(self, h, [k.dtype for k in keys], len(vals), len(aggs))
 
     def groupby_partial(self, keys, vals, filter=None, all_stats=True) -> GroupByResult:

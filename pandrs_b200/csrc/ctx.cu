@@ -139,6 +139,7 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "tsort_threads")) c->opt_tsort_threads = value;
   else if (!strcmp(name, "tsort_min_groups")) c->opt_tsort_min_groups = value;
   else if (!strcmp(name, "compat_empty_string_id")) c->opt_empty_string_id = value;
+  else if (!strcmp(name, "few")) c->opt_few = value;
   else return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown option '%s'", name);
   return PDRS_OK;
 }

@@ -9,6 +9,7 @@
 #include <cstring>
 
 #include "groupby_kernels.cuh"
+#include "gb_few.cuh"
 
 // ---------------------------------------------------------------- finalisation
 struct FinVal { const GState* st; int is_int; int flags; long long* validn_out; u64* states_out; };
@@ -280,6 +281,31 @@ static int32_t default_null_keys(pdrs_ctx* c, ColView* v) {
   return PDRS_OK;
 }
 
+// A typed predicate as a Boolean bitmask (general paths; the few-groups kernel evaluates it inside its scan): one 32-bit
+// word per thread; ANDed with an optional Boolean filter column (value & ~null).
+__global__ void gb_pred_mask_kernel(const u64* __restrict__ col, const uint8_t* __restrict__ cnull, int is_f64, int op, long long ival, double fval,
+                                    const uint32_t* __restrict__ fbits, const uint32_t* __restrict__ fnull, long long n, uint32_t* __restrict__ out) {
+  const long long nwords = (n + 31) / 32;
+  for (long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (long long)gridDim.x * blockDim.x) {
+    uint32_t m = 0;
+    for (int b = 0; b < 32; b++) {
+      const long long i = w * 32 + b;
+      if (i >= n) break;
+      const u64 bits = __ldcs(col + i);
+      bool k;
+      if (is_f64) { const double x = __longlong_as_double((long long)bits);
+        k = op == PDRS_CMP_LT ? x < fval : op == PDRS_CMP_LE ? x <= fval : op == PDRS_CMP_GT ? x > fval : op == PDRS_CMP_GE ? x >= fval : op == PDRS_CMP_EQ ? x == fval : x != fval; }
+      else { const long long x = (long long)bits;
+        k = op == PDRS_CMP_LT ? x < ival : op == PDRS_CMP_LE ? x <= ival : op == PDRS_CMP_GT ? x > ival : op == PDRS_CMP_GE ? x >= ival : op == PDRS_CMP_EQ ? x == ival : x != ival; }
+      if (k) m |= 1u << b;
+    }
+    if (cnull) m &= ~reinterpret_cast<const uint32_t*>(cnull)[w];
+    if (fbits) m &= fbits[w];
+    if (fnull) m &= ~fnull[w];
+    out[w] = m;
+  }
+}
+
 int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* ks) {
   memset(ks, 0, sizeof(*ks));
   ks->nkeys = nkeys;
@@ -433,7 +459,7 @@ enum { MODE_AGG = 0, MODE_PARTIAL = 1 };
 
 static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
                            const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, int mode, int partial_all,
-                           pdrs_groupby_result** out) {
+                           pdrs_groupby_result** out, const pdrs_pred* pred = nullptr) {
   if (!c) return PDRS_ERR_BAD_ARG;
   if (!out || !keys || nkeys < 1 || nkeys > PDRS_MAX_KEYS || nvals < 0 || nvals > PDRS_MAX_VALS || naggs < 0 || naggs > PDRS_MAX_AGGS ||
       (nvals && !vals) || (naggs && !aggs))
@@ -443,6 +469,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   for (int k = 0; k < nkeys; k++) if (keys[k].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "key column %d has %lld rows, expected %lld", k, (long long)keys[k].len, (long long)n);
   for (int v = 0; v < nvals; v++) if (vals[v].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "value column %d has %lld rows, expected %lld", v, (long long)vals[v].len, (long long)n);
   if (filter && (filter->dtype != PDRS_BOOL_BITS || filter->len != n)) return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "filter must be a Boolean column of the same length");
+  if (pred && ((pred->col.dtype != PDRS_I64 && pred->col.dtype != PDRS_F64) || pred->col.len != n || pred->op < PDRS_CMP_LT || pred->op > PDRS_CMP_NE))
+    return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "predicate: needs an Int64 / Float64 column of the same length and a pdrs_cmp_op");
 
   // ---- which statistics does each value column need
   int need[PDRS_MAX_VALS];   // -1 unused, GB_SUM, GB_ALL
@@ -474,8 +502,11 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   ColView fv;
   for (int k = 0; k < nkeys; k++) PDRS_TRY(pdrs_view_col(c, &keys[k], &kv[k]));
   for (int v = 0; v < nvals; v++) if (need[v] >= 0) PDRS_TRY(pdrs_view_col(c, &vals[v], &vv[v]));
+  ColView pcv;
   if (filter) PDRS_TRY(pdrs_view_col(c, filter, &fv));
-  if (filter && c->opts.compat_filter_nulls) for (int k = 0; k < nkeys; k++) PDRS_TRY(default_null_keys(c, &kv[k]));
+  if (pred) PDRS_TRY(pdrs_view_col(c, &pred->col, &pcv));
+  const bool filtered = filter || pred;
+  if (filtered && c->opts.compat_filter_nulls) for (int k = 0; k < nkeys; k++) PDRS_TRY(default_null_keys(c, &kv[k]));
 
   KeySpec ks;
   PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));
@@ -491,13 +522,21 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   base.n = n;
   base.fbits = filter ? (const uint8_t*)fv.data : nullptr;
   base.fnull = filter ? fv.nulls : nullptr;
-  base.compat_nulls = (filter && c->opts.compat_filter_nulls) ? 1 : 0;
+  base.compat_nulls = (filtered && c->opts.compat_filter_nulls) ? 1 : 0;
+
+  // ---- few-groups kernel (gb_few.cu): one-word key tuples without NULLs, sum / mean / count only, <= 8 value columns
+  bool few_eligible = c->opt_few != 0 && ks.nwords == 1 && n >= 4096 && (int)passes.size() <= GF_MAXV &&
+                      (c->opts.groupby_algo == PDRS_GB_AUTO || c->opts.groupby_algo == PDRS_GB_FEW);
+  for (int k = 0; k < nkeys; k++) if (kv[k].nulls || (kv[k].dtype == PDRS_DICT_U32 && kv[k].null_alias >= 0)) few_eligible = false;
+  for (auto& pp : passes) if (pp.flags != GB_SUM) few_eligible = false;
+  std::vector<u64> few_keys;
 
   // ---- cardinality estimate
   long long est = c->opts.groups_hint > 0 ? c->opts.groups_hint : 0;
   bool dense_ok = false;
   long long dense_base = 0, dense_range = 0;
-  if (n > 0 && est == 0) {
+  if (n > 0 && (est == 0 || (est <= GF_MAXG && few_eligible))) {
+    const long long hint = est;
     long long s_rows = std::min<long long>(n, std::max<long long>(4096, c->opt_sample_rows));
     long long nb = (s_rows + 255) / 256;
     long long stride = std::max<long long>(256, n / nb);
@@ -514,7 +553,20 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     if (s_rows >= n) est = (long long)d;
     else est = (long long)std::min<double>((double)n, invert_distinct(d, s) * 1.05 + 1.0);
     if (est < 1) est = 1;
+    if (hint > 0) est = hint;
     c->stats.est_groups = est;
+    // <= 16 groups and only sum / mean / count: the few-groups kernel scans all value columns at once (gb_few.cu); it needs the
+    // group keys up front - the sample table holds them
+    if (est <= GF_MAXG && few_eligible) {
+      DevBuf kb;
+      PDRS_TRY(kb.alloc(c, (GF_MAXG + 2) * 8, true));
+      PDRS_CUDA(c, gb_few_collect_keys(stm.t, kb.as<u64>(), c->sm_count * 4, c->stream));
+      c->stats.kernel_launches++;
+      u64 hk[GF_MAXG + 2];
+      PDRS_CUDA(c, cudaMemcpyAsync(hk, kb.p, sizeof(hk), cudaMemcpyDeviceToHost, c->stream));
+      PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+      if (hk[0] >= 1 && hk[0] <= GF_MAXG) { few_keys.assign(hk + 1, hk + 1 + hk[0]); std::sort(few_keys.begin(), few_keys.end()); }
+    }
     if (variant == 0 && cn[CNT_KMINC]) {     // small dense integer keys: direct-mapped group ids, no key table
       const long long kmin = (long long)(~cn[CNT_KMINC] ^ GB_SIGN), kmax = (long long)(cn[CNT_KMAX] ^ GB_SIGN);
       const unsigned long long range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
@@ -587,6 +639,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   bool part_ok = c->opt_part != 0 && c->opts.groupby_algo == PDRS_GB_AUTO;
   bool reestimated = false;      // the partitioned path may correct the sampled cardinality estimate once (gb_part_pass)
   bool ts_skew = false;          // the tile-sort kernel runs as the skew fallback: its spills go to a side buffer + a second pass
+  bool few_off = false;          // the few-groups kernel met too many keys the sample had not seen
+  DevBuf pred_mask;
   (void)radix_used;
   for (int attempt = 0;; attempt++) {
     if (attempt > 6) return pdrs_fail(c, PDRS_ERR_OOM, "groupby: hash table kept overflowing after %d retries", attempt);
@@ -607,7 +661,46 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     PDRS_TRY(alloc_table(c, slots, ks.nwords, &tm));
     c->stats.table_slots = slots;
     c->stats.groupby_algo_used = use_shared ? PDRS_GB_SHARED : PDRS_GB_GLOBAL;
-    if (n > 0) {
+    bool few_ok = !few_keys.empty() && !few_off && gb_few_smem((int)few_keys.size(), passes[0].val >= 0 ? (int)passes.size() : 0, true) <= (size_t)c->smem_optin;
+    if (n > 0 && few_ok) {
+      GfParams fp{};
+      fp.base = base;
+      fp.base.gt = tm.t;
+      fp.base.count_rows = 1;
+      fp.nv = passes[0].val >= 0 ? (int)passes.size() : 0;
+      for (int i = 0; i < fp.nv; i++) {
+        PDRS_TRY(states[i].alloc(c, (size_t)(slots + 1) * sizeof(GState), true));
+        fp.val[i] = vv[passes[i].val].data; fp.vnull[i] = vv[passes[i].val].nulls; fp.st[i] = states[i].as<GState>(); fp.is_int[i] = passes[i].is_int;
+        if (fp.vnull[i] && !base.compat_nulls) fp.any_vnull = 1;
+      }
+      fp.ng = (int)few_keys.size();
+      for (int g = 0; g < fp.ng; g++) fp.gkey[g] = few_keys[g];
+      if (pred) { fp.pcol = pcv.data; fp.pnull = pcv.nulls; fp.pdtype = pcv.dtype; fp.pop = pred->op; fp.pival = pred->ival; fp.pfval = pred->fval; }
+      const size_t smem = gb_few_smem(fp.ng, fp.nv, fp.any_vnull != 0);
+      const long long units = (n + 63) / 64;
+      const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * std::max<size_t>(1, std::min<size_t>(3, (size_t)c->smem_optin / std::max<size_t>(smem, 1))), (units + 7) / 8));
+      if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+      PDRS_CUDA(c, gb_few_launch(fp, ctas, smem, c->stream));
+      c->stats.kernel_launches++;
+      c->stats.groupby_algo_used = PDRS_GB_FEW;
+      if (c->opt_timing) {
+        PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+        PDRS_CUDA(c, cudaEventSynchronize(c->ev_b));
+        float ms = 0;
+        PDRS_CUDA(c, cudaEventElapsedTime(&ms, c->ev_a, c->ev_b));
+        c->stats.main_kernel_ms += ms;
+      }
+    } else if (n > 0) {
+      if (pred && !pred_mask.p) {      // general paths take the predicate as a Boolean mask (one more pass over that column)
+        const long long nwords = (n + 63) / 64 * 2;
+        PDRS_TRY(pred_mask.alloc(c, (size_t)nwords * 4 + 64, true));
+        gb_pred_mask_kernel<<<pdrs_grid_for(c, (n + 31) / 32, 256), 256, 0, c->stream>>>(reinterpret_cast<const u64*>(pcv.data), pcv.nulls, pcv.dtype == PDRS_F64, pred->op, pred->ival, pred->fval,
+            reinterpret_cast<const uint32_t*>(base.fbits), reinterpret_cast<const uint32_t*>(base.fnull), n, pred_mask.as<uint32_t>());
+        c->stats.kernel_launches++;
+        PDRS_CUDA(c, cudaGetLastError());
+        base.fbits = pred_mask.as<uint8_t>(); base.fnull = nullptr;
+        for (auto& g : gps) { g.fbits = base.fbits; g.fnull = nullptr; }
+      }
       for (size_t i = 0; i < passes.size(); i++) {
         GbParams& gp = gps[i];
         gp.gt = tm.t;
@@ -729,6 +822,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     if (cn[CNT_OVERFLOW] == 0 && cn[CNT_SPIN_FAIL] == 0) break;
     c->stats.retries++;
     slots_mult *= 4;
+    few_off = true;
     if ((use_shared || ts_fit) && (long long)cn[CNT_SPILLED] > n / 16) algo = PDRS_GB_GLOBAL;
     for (auto& s : states) s.release();
   }
@@ -791,6 +885,11 @@ extern "C" {
 int32_t pdrs_groupby_agg(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
                          const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, pdrs_groupby_result** out) {
   return groupby_run(ctx, keys, nkeys, vals, nvals, aggs, naggs, filter, MODE_AGG, 0, out);
+}
+
+int32_t pdrs_groupby_agg_where(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
+                               const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out) {
+  return groupby_run(ctx, keys, nkeys, vals, nvals, aggs, naggs, filter, MODE_AGG, 0, out, pred);
 }
 
 int32_t pdrs_groupby_partial(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,

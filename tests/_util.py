@@ -122,11 +122,16 @@ def oracle_groupby_dict(o, key_specs, val_specs, aggs, filter_spec=None, compat_
     return out
 
 
-def compare_groupby(pb, o, ctx, key_specs, val_specs, aggs, filter_spec=None, device=False, compat_nulls=False, rtol=RTOL):
-    """Runs both paths and asserts parity.  Returns the GPU dict."""
+_CMP = {0: np.less, 1: np.less_equal, 2: np.greater, 3: np.greater_equal, 4: np.equal, 5: np.not_equal}
+
+
+def compare_groupby(pb, o, ctx, key_specs, val_specs, aggs, filter_spec=None, device=False, compat_nulls=False, rtol=RTOL, pred=None):
+    """Runs both paths and asserts parity.  Returns the GPU dict.  pred = (Spec, cmp op, constant): a typed predicate the CUDA
+    path evaluates in its scan; the oracle gets the Boolean column a pandrs caller would have built (NULL -> not kept)."""
     kc = [s.gpu(pb) for s in key_specs]
     vc = [s.gpu(pb) for s in val_specs]
     fc = None if filter_spec is None else filter_spec.gpu(pb)
+    pc = None if pred is None else pred[0].gpu(pb)
     ups = []
     if device:
         kc = [ctx.upload(c) for c in kc]
@@ -135,7 +140,20 @@ def compare_groupby(pb, o, ctx, key_specs, val_specs, aggs, filter_spec=None, de
         if fc is not None:
             fc = ctx.upload(fc)
             ups.append(fc)
-    res = ctx.groupby_agg(kc, vc, aggs, filter=fc)
+        if pc is not None:
+            pc = ctx.upload(pc)
+            ups.append(pc)
+    if pred is not None:
+        with np.errstate(invalid="ignore"):
+            keep = _CMP[pred[1]](pred[0].values, pred[2])
+        if pred[0].nulls is not None:
+            keep = keep & ~pred[0].nulls
+        if filter_spec is not None:
+            keep = keep & filter_spec.values.astype(bool)
+            if filter_spec.nulls is not None:
+                keep = keep & ~filter_spec.nulls
+        filter_spec = Spec(pb.BOOL_BITS, keep)
+    res = ctx.groupby_agg(kc, vc, aggs, filter=fc, pred=None if pred is None else (pc, pred[1], pred[2]))
     try:
         got = gpu_groupby_dict(pb, res, key_specs, len(aggs))
     finally:

@@ -397,6 +397,57 @@ def test_fused_filter(ctx, oracle, compat):
     assert len(got) == 6 and got.keys() == got2.keys()
 
 
+def test_few_groups_many_value_columns_in_one_scan(ctx, oracle):
+    # BASELINE.json configs[4] shape: Boolean-mask filter -> groupby(returnflag, linestatus) -> sums / means / count of FIVE value
+    # columns: the few-groups kernel (gb_few.cu) reads keys, mask and all value columns once.  Every key layout (one Int64 key,
+    # raw 4-byte columns, generic tuples), int and float values, NULL values, filter NULLs, compat_filter_nulls, a ragged tail,
+    # keys the cardinality sample never saw (they spill to the global table), and a typed predicate evaluated in the scan.
+    n = 300_003
+    rng = np.random.default_rng(91)
+    rf = Spec(pb.DICT_U32, rng.integers(0, 3, n).astype(np.uint32), pool=["A", "N", "R"])
+    ls = Spec(pb.DICT_U32, rng.integers(0, 2, n).astype(np.uint32), pool=["F", "O"])
+    qty = Spec(pb.F64, rng.integers(1, 51, n).astype(np.float64), nulls=rng.random(n) < 0.02)
+    price = Spec(pb.F64, rng.random(n) * 1e5)
+    disc = Spec(pb.F64, rng.random(n) * 0.1, nulls=rng.random(n) < 0.3)
+    cnt_i = Spec(pb.I64, rng.integers(-2**60, 2**60, n), nulls=rng.random(n) < 0.05)
+    tax = Spec(pb.F64, rng.random(n) * 0.08)
+    ship = Spec(pb.I64, rng.integers(8000, 10600, n), nulls=rng.random(n) < 0.01)
+    mask = Spec(pb.BOOL_BITS, rng.random(n) < 0.98, nulls=rng.random(n) < 0.01)
+    vals = [qty, price, disc, cnt_i, tax]
+    aggs = [(0, pb.SUM), (1, pb.SUM), (2, pb.SUM), (3, pb.SUM), (4, pb.SUM), (0, pb.MEAN), (1, pb.MEAN), (2, pb.MEAN), (3, pb.MEAN), (0, pb.COUNT)]
+    k64 = Spec(pb.I64, rng.integers(-2, 3, n) * 10**15)
+    kb = Spec(pb.BOOL_BITS, rng.random(n) < 0.5)
+    k32 = Spec(pb.I32, rng.integers(-1, 2, n).astype(np.int32))
+    for keys in ([rf, ls], [k64], [rf], [kb, k32]):
+        for filt in (None, mask):
+            got = compare_groupby(pb, oracle, ctx, keys, vals, aggs, filter_spec=filt, device=True)
+            assert ctx.stats()["groupby_algo_used"] == pb.GB_FEW, ([k.dtype for k in keys], ctx.stats())
+    assert len(got) == 6
+    compare_groupby(pb, oracle, ctx, [rf, ls], vals, aggs, filter_spec=mask)                       # host columns
+    compare_groupby(pb, oracle, ctx, [rf, ls], vals, aggs, device=True, pred=(ship, pb.CMP_LE, 10_500))
+    assert ctx.stats()["groupby_algo_used"] == pb.GB_FEW
+    compare_groupby(pb, oracle, ctx, [rf, ls], vals, aggs, filter_spec=mask, device=True, pred=(price, pb.CMP_GT, 5e4))
+    ctx.set_option("compat_filter_nulls", 1)
+    try:
+        compare_groupby(pb, oracle, ctx, [rf, ls], vals, aggs, filter_spec=mask, compat_nulls=True, device=True)
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_FEW
+        compare_groupby(pb, oracle, ctx, [k64], vals, aggs, compat_nulls=True, device=True, pred=(ship, pb.CMP_GE, 8100))
+    finally:
+        ctx.set_option("compat_filter_nulls", 0)
+    # min / max / std need the full statistics: not this kernel; the predicate then becomes a mask in front of the other kernels
+    compare_groupby(pb, oracle, ctx, [rf, ls], [qty, price], [(0, pb.SUM), (1, pb.STD), (0, pb.MIN)], device=True, pred=(ship, pb.CMP_LT, 9000))
+    assert ctx.stats()["groupby_algo_used"] != pb.GB_FEW
+    # keys the sample never saw: the sample reads runs of 256 rows every n // 1024 rows; rows at offset 270 of a stride lie between runs
+    k = rng.integers(0, 4, n)
+    stride = n // 1024
+    assert stride > 280
+    out = stride * np.arange(3, 1000, 37) + 270
+    k[out] = 1000 + (np.arange(len(out)) % 3)
+    got = compare_groupby(pb, oracle, ctx, [Spec(pb.I64, k)], vals, aggs, device=True)
+    st = ctx.stats()
+    assert len(got) == 7 and st["groupby_algo_used"] == pb.GB_FEW and st["spilled_rows"] == len(out)
+
+
 def test_fused_filter_turns_null_keys_into_defaults(ctx, oracle):
     # compat_filter_nulls: the reference filters first, and its filter() defaults the NULLs of every column of the kept
     # rows - key columns included (data_ops.rs:64-108, parallel.rs:177-231): a NULL Int64 key joins group "0", a NULL f64
