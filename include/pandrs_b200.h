@@ -252,6 +252,43 @@ int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_c
 int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0 /* world */, pdrs_join_result** out);
 void pdrs_xjoin_destroy(pdrs_xjoin* x);
 
+/* ---- multi-GPU operators: one process per GPU, NCCL over NVLink / NVSwitch ----
+ * No reference counterpart (pandrs has no comms backend; PartitionStrategy::Hash is only an enum,
+ * src/distributed/core/partition.rs:11-18).  Semantics = the single-frame operator of the reference applied to the union of
+ * the ranks' rows.  NCCL is bound at run time (dlopen): single-GPU users never load it.
+ *   rank 0: pdrs_comm_unique_id(id) -> the host broadcasts the 128 bytes (MPI, TCP, torch.distributed ...) -> every rank:
+ *   pdrs_comm_init(ctx, nranks, rank, id, &comm).  All *_dist calls are collective: every rank calls them in the same order. */
+typedef struct pdrs_comm pdrs_comm;
+int32_t pdrs_comm_unique_id(uint8_t* id128 /* 128 bytes */);
+int32_t pdrs_comm_init(pdrs_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t* id128, pdrs_comm** out);
+int32_t pdrs_comm_rank(const pdrs_comm* comm);
+int32_t pdrs_comm_size(const pdrs_comm* comm);
+int32_t pdrs_comm_set_option(pdrs_comm* comm, const char* name, int64_t value);   /* "groups_cap": state rows per rank in the replicated groupby (default 4096) */
+int32_t pdrs_comm_barrier(pdrs_comm* comm);
+/* CUDA-event time of the exchange step (all-gather / all-to-all / peer-store shuffle) of the last *_dist call and the bytes this
+ * rank sent to other ranks in it (NVLink roofline: bytes / time against the per-direction peer bandwidth) */
+int32_t pdrs_comm_last_exchange(const pdrs_comm* comm, float* ms, int64_t* bytes_to_peers);
+void pdrs_comm_destroy(pdrs_comm* comm);
+/* groupby(keys).agg(...) over the union of the ranks' rows (same arguments as pdrs_groupby_agg_where on every rank's shard).
+ * Every rank aggregates its own rows into mergeable states, then
+ *   result_mode 1 (replicated)  one fixed-size all-gather of the per-group states + merge: EVERY rank returns ALL groups
+ *                               (low cardinality: at most "groups_cap" groups per rank);
+ *   result_mode 2 (sharded)     the states are exchanged by hash(key) mod ranks with one all-to-all and merged by their owner:
+ *                               every rank returns the groups it owns (high cardinality; the NULL-key group lives on rank 0);
+ *   result_mode 0 (auto)        replicated when every rank's group count fits, else sharded (the choice is collective).
+ * Only per-group states cross NVLink, never input rows.  pdrs_get_stats() reports the local aggregation kernel. */
+int32_t pdrs_groupby_agg_dist(pdrs_comm* comm, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
+                              const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, const pdrs_pred* pred,
+                              int32_t result_mode, pdrs_groupby_result** out);
+/* Inner / Left join over the union of the ranks' rows: the pdrs_xjoin protocol above (IPC handle exchange, shuffle through
+ * NVLink peer stores, barrier, local join) behind one collective call.  left_row0 / right_row0 = global number of this rank's
+ * first row; max_* = the largest shard of any rank (same values on every rank; the receive areas are set up for them once and
+ * reused).  Rank r returns the pairs of the keys whose rank hash maps to r, in GLOBAL row numbers.
+ * PDRS_ERR_UNSUPPORTED (on every rank): skewed keys overflowed a padded region. */
+int32_t pdrs_join_pairs_dist(pdrs_comm* comm, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, int64_t left_row0,
+                             int64_t right_row0, int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows,
+                             pdrs_join_result** out);
+
 /* Replaces the materialisation loops of join_impl (join.rs:290-552) and filter_by_indices
  * (data_ops.rs:124-211): out[j] = idx[j] < 0 || col[idx[j]] is NULL ? type default : col[idx[j]];
  * the output carries no null mask.  DICT_U32 default is 0xFFFFFFFF (the empty string ""), BOOL_BITS

@@ -98,6 +98,16 @@ SIGNATURES = {
     "pdrs_xjoin_shuffle": (_i32, [_vp, _P(PdrsCol), _P(PdrsCol), _i64]),
     "pdrs_xjoin_local": (_i32, [_vp, _i32, _P(_i64), _P(_vp)]),
     "pdrs_xjoin_destroy": (None, [_vp]),
+    "pdrs_comm_unique_id": (_i32, [_vp]),
+    "pdrs_comm_init": (_i32, [_vp, _i32, _i32, _vp, _P(_vp)]),
+    "pdrs_comm_rank": (_i32, [_vp]),
+    "pdrs_comm_size": (_i32, [_vp]),
+    "pdrs_comm_set_option": (_i32, [_vp, C.c_char_p, _i64]),
+    "pdrs_comm_barrier": (_i32, [_vp]),
+    "pdrs_comm_last_exchange": (_i32, [_vp, _P(C.c_float), _P(_i64)]),
+    "pdrs_comm_destroy": (None, [_vp]),
+    "pdrs_groupby_agg_dist": (_i32, [_vp, _P(PdrsCol), _i32, _P(PdrsCol), _i32, _P(PdrsAgg), _i32, _P(PdrsCol), _P(PdrsPred), _i32, _P(_vp)]),
+    "pdrs_join_pairs_dist": (_i32, [_vp, _P(PdrsCol), _P(PdrsCol), _i32, _i64, _i64, _i64, _i64, _i64, _P(_vp)]),
     "pdrs_gather": (_i32, [_vp, _P(PdrsCol), _vp, _i32, _i64, _vp, _i32]),
     "pdrs_filter_indices": (_i32, [_vp, _P(PdrsCol), _vp, _P(_i64)]),
     "pdrs_synth_keys": (_i32, [_vp, _vp, _i64, _i64, _u64, _u64, _i32]),

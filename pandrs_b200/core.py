@@ -420,6 +420,93 @@ class Context:
             self.dev_free(buf)
 
 
+class Comm:
+    """pdrs_comm: this rank's end of the multi-GPU operators (one process per GPU, NCCL bound inside the library).
+
+    `exchange_id(id_bytes_or_None) -> bytes` is the host's broadcast of rank 0's 128-byte NCCL id (torch.distributed, MPI ...);
+    it is only called when world > 1."""
+    REPLICATED, SHARDED, AUTO = 1, 2, 0
+
+    def __init__(self, ctx: "Context", rank: int, world: int, broadcast_id=None):
+        self.ctx, self.rank, self.world = ctx, rank, world
+        ident = None
+        if world > 1:
+            mine = None
+            if rank == 0:
+                buf = (C.c_uint8 * 128)()
+                rc = ctx.L.pdrs_comm_unique_id(buf)
+                if rc != 0:
+                    raise PandrsError(rc, (ctx.L.pdrs_last_error(None) or b"").decode())
+                mine = bytes(buf)
+            ident = broadcast_id(mine)
+            assert len(ident) == 128
+        h = C.c_void_p()
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(ident) if ident is not None else None
+        ctx._chk(ctx.L.pdrs_comm_init(ctx._h, world, rank, idbuf, C.byref(h)))
+        self._h = h
+
+    def set_option(self, name: str, value: int):
+        self.ctx._chk(self.ctx.L.pdrs_comm_set_option(self._h, name.encode(), int(value)))
+
+    def barrier(self):
+        self.ctx._chk(self.ctx.L.pdrs_comm_barrier(self._h))
+
+    def last_exchange(self):
+        ms, b = C.c_float(), C.c_int64()
+        self.ctx._chk(self.ctx.L.pdrs_comm_last_exchange(self._h, C.byref(ms), C.byref(b)))
+        return ms.value, b.value
+
+    def groupby_agg(self, keys, vals, aggs, filter=None, pred=None, result_mode: int = 0) -> GroupByResult:
+        """groupby over the union of the ranks' rows (pdrs_groupby_agg_dist); collective."""
+        ctx = self.ctx
+        ka, va = ctx._cols(keys), ctx._cols(vals)
+        aa = (N.PdrsAgg * max(1, len(aggs)))(*[N.PdrsAgg(int(v), int(op)) for v, op in aggs])
+        f = filter.c() if filter is not None else None
+        pp = None
+        if pred is not None:
+            col, op, const = pred
+            pp = N.PdrsPred(col.c(), int(op), 0, int(const) if col.dtype == I64 else 0, float(const))
+        h = C.c_void_p()
+        ctx._chk(ctx.L.pdrs_groupby_agg_dist(self._h, ka, len(keys), va, len(vals), aa, len(aggs), C.byref(f) if f is not None else None,
+                                             C.byref(pp) if pp is not None else None, int(result_mode), C.byref(h)))
+        nvs = sum(1 for v in vals if v.dtype in (I64, F64))
+        return GroupByResult(ctx, h, [k.dtype for k in keys], nvs, len(aggs))
+
+    def join_pairs(self, left: Column, right: Column, how: int, left_row0: int, right_row0: int, max_left_rows: int, max_right_rows: int,
+                   total_right_rows: int) -> JoinResult:
+        """Inner / Left join over the union of the ranks' rows (pdrs_join_pairs_dist); collective; GLOBAL row numbers."""
+        lc, rc = left.c(), right.c()
+        h = C.c_void_p()
+        self.ctx._chk(self.ctx.L.pdrs_join_pairs_dist(self._h, C.byref(lc), C.byref(rc), how, int(left_row0), int(right_row0), int(max_left_rows),
+                                                      int(max_right_rows), int(total_right_rows), C.byref(h)))
+        return JoinResult(self.ctx, h)
+
+    def close(self):
+        if self._h:
+            self.ctx.L.pdrs_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self.ctx._h:
+                self.close()
+        except Exception:
+            pass
+
+
+def torch_broadcast_id(dist, device):
+    """broadcast_id callback for Comm on top of torch.distributed (any backend)."""
+    import torch
+
+    def f(mine):
+        t = torch.zeros(128, dtype=torch.uint8, device=device)
+        if mine is not None:
+            t.copy_(torch.tensor(list(mine), dtype=torch.uint8))
+        dist.broadcast(t, src=0)
+        return bytes(t.cpu().tolist())
+    return f
+
+
 class _DevOwner:
     def __init__(self, ctx: Context, ptr: int):
         self.ctx, self.ptr = ctx, ptr

@@ -10,6 +10,7 @@
 
 #include "groupby_kernels.cuh"
 #include "gb_few.cuh"
+#include "comm.cuh"
 
 // ---------------------------------------------------------------- finalisation
 struct FinVal { const GState* st; int is_int; int flags; long long* validn_out; u64* states_out; };
@@ -880,6 +881,52 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   return PDRS_OK;
 }
 
+// Tail of every merge of partial states: read the table counters, allocate the result arrays, finalise.
+static std::vector<int> keys_dtypes(const pdrs_col* keys, int nkeys) { std::vector<int> d(nkeys); for (int k = 0; k < nkeys; k++) d[k] = keys[k].dtype; return d; }
+static int32_t finish_merged(pdrs_ctx* c, const KeySpec& ks, TableMem& tm, std::vector<DevBuf>& states, const int* key_dtype, int nkeys, int nvals,
+                             const int32_t* val_is_int, const pdrs_agg* aggs, int naggs, pdrs_groupby_result* res) {
+  u64 cn[CNT_N + 1];
+  PDRS_TRY(read_counters(c, tm, cn));
+  if (cn[CNT_OVERFLOW] || cn[CNT_SPIN_FAIL]) return pdrs_fail(c, PDRS_ERR_CUDA, "merge: hash table overflow");
+  const int64_t G = (int64_t)cn[CNT_NGROUPS] + ((cn[CNT_N] & GB_FULL) ? 1 : 0);
+  res->n_groups = G;
+  FinParams fp{};
+  fp.gt = tm.t; fp.ks = ks;
+  const size_t Galloc = (size_t)std::max<int64_t>(G, 1);
+  for (int k = 0; k < nkeys; k++) {
+    PDRS_TRY(res->key_vals[k].alloc(c, Galloc * key_out_bytes(key_dtype[k])));
+    PDRS_TRY(res->key_nulls[k].alloc(c, Galloc));
+    fp.key_out[k] = res->key_vals[k].p;
+    fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
+  }
+  PDRS_TRY(res->rows.alloc(c, Galloc * 8));
+  fp.rows_out = res->rows.as<long long>();
+  fp.nvals = nvals;
+  for (int v = 0; v < nvals; v++) {
+    fp.vals[v].st = states[v].as<GState>();
+    fp.vals[v].is_int = val_is_int ? val_is_int[v] : 0;
+    fp.vals[v].flags = GB_ALL;
+    PDRS_TRY(res->validn[v].alloc(c, Galloc * 8));
+    fp.vals[v].validn_out = res->validn[v].as<long long>();
+    PDRS_TRY(res->states[v].alloc(c, Galloc * 64));
+    fp.vals[v].states_out = res->states[v].as<u64>();
+  }
+  fp.naggs = naggs;
+  for (int a = 0; a < naggs; a++) {
+    PDRS_TRY(res->aggs[a].alloc(c, Galloc * 8));
+    fp.aggs[a].val = aggs[a].op == PDRS_COUNT ? -1 : aggs[a].value_col;
+    fp.aggs[a].op = aggs[a].op;
+    fp.aggs[a].out = res->aggs[a].as<double>();
+  }
+  if (G > 0) {
+    gb_finalize_kernel<<<pdrs_grid_for(c, tm.t.slots + 1, 256), 256, 0, c->stream>>>(fp);
+    c->stats.kernel_launches++;
+    PDRS_CUDA(c, cudaGetLastError());
+  }
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PDRS_OK;
+}
+
 extern "C" {
 
 int32_t pdrs_groupby_agg(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
@@ -935,49 +982,286 @@ int32_t pdrs_groupby_merge(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
   }
-  u64 cn[CNT_N + 1];
-  PDRS_TRY(read_counters(c, tm, cn));
-  if (cn[CNT_OVERFLOW] || cn[CNT_SPIN_FAIL]) return pdrs_fail(c, PDRS_ERR_CUDA, "merge: hash table overflow");
-  const int64_t G = (int64_t)cn[CNT_NGROUPS] + ((cn[CNT_N] & GB_FULL) ? 1 : 0);
-  res->n_groups = G;
-  FinParams fp{};
-  fp.gt = tm.t; fp.ks = ks;
-  const size_t Galloc = (size_t)std::max<int64_t>(G, 1);
-  for (int k = 0; k < nkeys; k++) {
-    PDRS_TRY(res->key_vals[k].alloc(c, Galloc * key_out_bytes(keys[k].dtype)));
-    PDRS_TRY(res->key_nulls[k].alloc(c, Galloc));
-    fp.key_out[k] = res->key_vals[k].p;
-    fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
-  }
-  PDRS_TRY(res->rows.alloc(c, Galloc * 8));
-  fp.rows_out = res->rows.as<long long>();
-  fp.nvals = nvals;
-  for (int v = 0; v < nvals; v++) {
-    fp.vals[v].st = states[v].as<GState>();
-    fp.vals[v].is_int = val_is_int ? val_is_int[v] : 0;
-    fp.vals[v].flags = GB_ALL;
-    PDRS_TRY(res->validn[v].alloc(c, Galloc * 8));
-    fp.vals[v].validn_out = res->validn[v].as<long long>();
-    PDRS_TRY(res->states[v].alloc(c, Galloc * 64));
-    fp.vals[v].states_out = res->states[v].as<u64>();
-  }
-  fp.naggs = naggs;
-  for (int a = 0; a < naggs; a++) {
-    PDRS_TRY(res->aggs[a].alloc(c, Galloc * 8));
-    fp.aggs[a].val = aggs[a].op == PDRS_COUNT ? -1 : aggs[a].value_col;
-    fp.aggs[a].op = aggs[a].op;
-    fp.aggs[a].out = res->aggs[a].as<double>();
-  }
-  if (G > 0) {
-    gb_finalize_kernel<<<pdrs_grid_for(c, slots + 1, 256), 256, 0, c->stream>>>(fp);
-    c->stats.kernel_launches++;
-    PDRS_CUDA(c, cudaGetLastError());
-  }
-  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  PDRS_TRY(finish_merged(c, ks, tm, states, keys_dtypes(keys, nkeys).data(), nkeys, nvals, val_is_int, aggs, naggs, res));
   guard.r = nullptr;
   *out = res;
   return PDRS_OK;
 }
+
+}  // extern "C"
+
+// ================================================================ multi-GPU groupby behind one call (pdrs_groupby_agg_dist)
+// One rank = one process = one GPU; the communicator (comm.cu) carries NCCL.  Semantics = the single-frame groupby of the
+// reference (grouping.rs:38-115 + aggregation.rs:500-903) applied to the UNION of the ranks' rows:
+//   every rank aggregates its own rows into mergeable states (the pdrs_groupby_partial kernels), packs one row per group
+//   [key words | NULL-group flag | group rows | 8 state words per value column], and then
+//   replicated  (few groups: <= groups_cap per rank) ONE fixed-size ncclAllGather of the packed rows, a merge kernel over the
+//               ranks' rows (Chan-style re-basing of S1 / S2 to a common pivot, like pdrs_groupby_merge) and the usual
+//               finalisation - every rank returns ALL groups.  No row ever crosses NVLink, no host round trip in between.
+//   sharded     (many groups) the packed rows are scattered by destination rank = hash(key) mod ranks, exchanged with one
+//               all-to-all (grouped ncclSend / ncclRecv) and merged by their owner - every rank returns the groups it owns.
+//               Only one row per (rank, group) crosses NVLink, not the input rows.
+// The key layout is the natural one with a NULL flag reserved for EVERY key part, so that ranks agree on it whatever
+// null bitmaps their shards happen to carry.
+struct DistPack {
+  KeySpec ks;                                   // layout only (data / nulls unused)
+  const void* key_vals[PDRS_MAX_KEYS];          // typed key arrays of the partial result
+  const uint8_t* key_null[PDRS_MAX_KEYS];       // one byte per group
+  const long long* rows;
+  const u64* states[PDRS_MAX_VALS];             // [G][8]
+  int nvals;
+  long long G, cap;                             // cap: rows that fit the destination (replicated mode)
+  int stride;                                   // u64 words per packed row = 5 + 8 * nvals
+  int world;
+};
+
+template <int NW>
+__device__ __forceinline__ bool dist_row_words(const DistPack& p, long long j, u64 (&w)[NW]) {
+#pragma unroll
+  for (int i = 0; i < NW; i++) w[i] = 0;
+  for (int k = 0; k < p.ks.nkeys; k++) {
+    const KeyColDev& c = p.ks.c[k];
+    const bool isnull = p.key_null[k][j] != 0;
+    u64 v = 0;
+    switch (c.dtype) {
+      case PDRS_I64: v = reinterpret_cast<const u64*>(p.key_vals[k])[j]; break;
+      case PDRS_F64: { v = reinterpret_cast<const u64*>(p.key_vals[k])[j]; const double d = __longlong_as_double((long long)v); if (d != d) v = 0x7FF8000000000000ull; break; }
+      case PDRS_I32: v = (u64)(long long)reinterpret_cast<const int*>(p.key_vals[k])[j] & 0xFFFFFFFFull; break;
+      case PDRS_DICT_U32: v = reinterpret_cast<const uint32_t*>(p.key_vals[k])[j]; break;
+      default: v = reinterpret_cast<const uint8_t*>(p.key_vals[k])[j] ? 1ull : 0ull; break;
+    }
+    if (isnull) {
+      if (p.ks.single_null) return true;
+      if (c.nword >= 0) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) if (i == c.nword) w[i] |= 1ull << c.nshift;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NW; i++) if (i == c.word) w[i] |= v << c.shift;
+    }
+  }
+  return false;
+}
+template <int NW>
+__device__ __forceinline__ int dist_dest(const u64 (&w)[NW], bool nullgroup, int world) {
+  if (nullgroup) return 0;                       // the NULL-key group lives on rank 0 (like pdrs_hash_partition)
+  return (int)(pdrs_mix64(key_hash<NW>(w) ^ 0x5851F42D4C957F2Dull) % (u64)world);
+}
+// MODE 0: row j -> out[8 + j * stride] (replicated; out[0] = G).  MODE 1: count the rows per destination rank.
+// MODE 2: scatter into out[(off[dest] + ticket) * stride].
+template <int NW, int MODE>
+__global__ void dist_pack_kernel(const DistPack p, u64* __restrict__ out, u64* __restrict__ counts, const u64* __restrict__ off) {
+  if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = (u64)p.G;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < p.G; j += (long long)gridDim.x * blockDim.x) {
+    if (MODE == 0 && j >= p.cap) break;
+    u64 w[NW];
+    const bool ng = dist_row_words<NW>(p, j, w);
+    if (MODE == 1) { atomicAdd(&counts[dist_dest<NW>(w, ng, p.world)], 1ull); continue; }
+    long long at = j;
+    if (MODE == 2) { const int d = dist_dest<NW>(w, ng, p.world); at = (long long)(off[d] + atomicAdd(&counts[d], 1ull)); }
+    u64* q = out + (MODE == 0 ? 8 : 0) + at * p.stride;
+    q[0] = w[0]; q[1] = NW > 1 ? w[NW > 1 ? 1 : 0] : 0ull; q[2] = NW > 2 ? w[NW > 2 ? 2 : 0] : 0ull;
+    q[3] = ng ? 1ull : 0ull;
+    q[4] = (u64)p.rows[j];
+    for (int v = 0; v < p.nvals; v++) {
+      const u64* s = p.states[v] + 8 * j;
+#pragma unroll
+      for (int i = 0; i < 8; i++) q[5 + 8 * v + i] = s[i];
+    }
+  }
+}
+
+struct DistMerge {
+  const u64* buf; long long nrows; long long cap; long long block;      // block > 0: rank r's rows start at buf[r * block + 8], count = buf[r * block]
+  int stride, nvals;
+  GTable gt;
+  GState* st[PDRS_MAX_VALS];
+};
+template <int NW>
+__global__ void dist_merge_kernel(const DistMerge p) {
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i - lane < p.nrows; i += (long long)gridDim.x * blockDim.x) {
+    bool inb = i < p.nrows;
+    const u64* q = p.buf + i * p.stride;
+    if (p.block > 0 && inb) {
+      const long long r = i / p.cap, j = i - r * p.cap;
+      inb = j < (long long)p.buf[r * p.block];
+      q = p.buf + r * p.block + 8 + j * p.stride;
+    }
+    u64 w[NW];
+#pragma unroll
+    for (int k = 0; k < NW; k++) w[k] = inb ? q[k] : 0ull;
+    const bool knull = inb && q[3] != 0;
+    long long gs = g_find_or_insert<NW>(p.gt, w, inb && !knull);
+    if (knull) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
+    if (!inb || gs < 0) continue;
+    atomicAdd(&p.gt.hdr[gs].rowsw, q[4]);
+    for (int v = 0; v < p.nvals; v++) {
+      const u64* s = q + 5 + 8 * v;
+      GTable t = p.gt;
+      t.st = p.st[v];
+      g_update_batch<GB_ALL, true>(t, gs, 0ull, s[1], fin_pivot(s[2]), s[2] != 0, __longlong_as_double((long long)s[3]), __longlong_as_double((long long)s[4]), s[7], s[5], s[6]);
+    }
+  }
+}
+
+static int32_t dist_merge_launch(pdrs_ctx* c, int nw, const DistMerge& mp) {
+  if (mp.nrows <= 0) return PDRS_OK;
+  const int g = pdrs_grid_for(c, mp.nrows, 256);
+  switch (nw) {
+    case 1: dist_merge_kernel<1><<<g, 256, 0, c->stream>>>(mp); break;
+    case 2: dist_merge_kernel<2><<<g, 256, 0, c->stream>>>(mp); break;
+    default: dist_merge_kernel<3><<<g, 256, 0, c->stream>>>(mp); break;
+  }
+  c->stats.kernel_launches++;
+  PDRS_CUDA(c, cudaGetLastError());
+  return PDRS_OK;
+}
+template <int MODE>
+static int32_t dist_pack_launch(pdrs_ctx* c, int nw, const DistPack& pk, u64* out, u64* counts, const u64* off) {
+  const int g = pdrs_grid_for(c, std::max<long long>(pk.G, 1), 256);
+  switch (nw) {
+    case 1: dist_pack_kernel<1, MODE><<<g, 256, 0, c->stream>>>(pk, out, counts, off); break;
+    case 2: dist_pack_kernel<2, MODE><<<g, 256, 0, c->stream>>>(pk, out, counts, off); break;
+    default: dist_pack_kernel<3, MODE><<<g, 256, 0, c->stream>>>(pk, out, counts, off); break;
+  }
+  c->stats.kernel_launches++;
+  PDRS_CUDA(c, cudaGetLastError());
+  return PDRS_OK;
+}
+
+extern "C" int32_t pdrs_groupby_agg_dist(pdrs_comm* cm, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_agg* aggs, int32_t naggs,
+                                         const pdrs_col* filter, const pdrs_pred* pred, int32_t result_mode, pdrs_groupby_result** out) {
+  if (!cm) return PDRS_ERR_BAD_ARG;
+  pdrs_ctx* c = cm->ctx;
+  if (!out || !keys || nkeys < 1 || nkeys > PDRS_MAX_KEYS || nvals < 0 || nvals > PDRS_MAX_VALS || naggs < 0 || naggs > PDRS_MAX_AGGS || (naggs && !aggs) ||
+      result_mode < 0 || result_mode > 2)
+    return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby_agg_dist: bad argument");
+  bool all_stats = false;
+  for (int a = 0; a < naggs; a++) {
+    if (aggs[a].op < PDRS_SUM || aggs[a].op > PDRS_VAR) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: unknown op %d", a, aggs[a].op);
+    if (aggs[a].op != PDRS_COUNT && (aggs[a].value_col < 0 || aggs[a].value_col >= nvals)) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: value column out of range", a);
+    if (aggs[a].op != PDRS_COUNT && vals[aggs[a].value_col].dtype != PDRS_I64 && vals[aggs[a].value_col].dtype != PDRS_F64)
+      return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "aggregate %d: op %d needs an Int64 / Float64 column", a, aggs[a].op);
+    if (aggs[a].op == PDRS_MIN || aggs[a].op == PDRS_MAX || aggs[a].op == PDRS_STD || aggs[a].op == PDRS_VAR) all_stats = true;
+  }
+  // value columns that no aggregate reads travel as nothing: only Int64 / Float64 columns have states
+  std::vector<pdrs_col> nv;
+  std::vector<int> vmap(nvals, -1);
+  for (int v = 0; v < nvals; v++) if (vals[v].dtype == PDRS_I64 || vals[v].dtype == PDRS_F64) { vmap[v] = (int)nv.size(); nv.push_back(vals[v]); }
+  std::vector<pdrs_agg> ag(aggs, aggs + naggs);
+  for (auto& a : ag) if (a.op != PDRS_COUNT) a.value_col = vmap[a.value_col];
+  const int nvs = (int)nv.size();
+  // ---- local partial aggregation (every rank; the kernels of pdrs_groupby_partial)
+  pdrs_groupby_result* part = nullptr;
+  PDRS_TRY(groupby_run(c, keys, nkeys, nv.data(), nvs, nullptr, 0, filter, MODE_PARTIAL, all_stats ? 1 : 0, &part, pred));
+  struct PartGuard { pdrs_groupby_result* r; ~PartGuard() { if (r) { cudaSetDevice(r->ctx->device); delete r; } } } pguard{part};
+  const float local_ms = c->stats.main_kernel_ms;
+  const int local_algo = c->stats.groupby_algo_used;
+  // ---- the layout all ranks agree on
+  KeySpec ks;
+  {
+    std::vector<ColView> kv(nkeys);
+    for (int k = 0; k < nkeys; k++) { kv[k].dtype = keys[k].dtype; kv[k].len = 0; kv[k].nulls = reinterpret_cast<const uint8_t*>(1); kv[k].null_alias = -1; }
+    PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));
+    for (int k = 0; k < nkeys; k++) { ks.c[k].data = nullptr; ks.c[k].nulls = nullptr; ks.c[k].null_alias = -1; kv[k].nulls = nullptr; }
+  }
+  const int NW = ks.nwords, stride = 5 + 8 * nvs, world = cm->world;
+  DistPack pk{};
+  pk.ks = ks; pk.nvals = nvs; pk.G = part->n_groups; pk.stride = stride; pk.world = world; pk.rows = part->rows.as<long long>();
+  for (int k = 0; k < nkeys; k++) { pk.key_vals[k] = part->key_vals[k].p; pk.key_null[k] = part->key_nulls[k].as<uint8_t>(); }
+  for (int v = 0; v < nvs; v++) pk.states[v] = part->states[v].as<u64>();
+  auto* res = new pdrs_groupby_result();
+  res->ctx = c; res->nkeys = nkeys; res->nvals = nvs; res->naggs = naggs;
+  for (int k = 0; k < nkeys; k++) res->key_dtype[k] = keys[k].dtype;
+  struct Guard { pdrs_groupby_result* r; ~Guard() { delete r; } } guard{res};
+  std::vector<int32_t> val_is_int(std::max(nvs, 1));
+  for (int v = 0; v < nvs; v++) val_is_int[v] = nv[v].dtype == PDRS_I64;
+  auto grow = [&](DevBuf& b, size_t bytes) -> int32_t { if (b.bytes < bytes) { b.release(); PDRS_TRY(b.alloc(c, bytes + bytes / 4)); } return PDRS_OK; };
+  bool sharded = result_mode == 2;
+  TableMem tm;
+  std::vector<DevBuf> states(nvs);
+  DistMerge mp{};
+  mp.stride = stride; mp.nvals = nvs;
+  auto make_table = [&](long long rows) -> int32_t {
+    const long long slots = std::max<long long>(1024, pow2ceil(2 * rows + 16));
+    PDRS_TRY(alloc_table(c, slots, NW, &tm));
+    for (int v = 0; v < nvs; v++) { PDRS_TRY(states[v].alloc(c, (size_t)(slots + 1) * sizeof(GState), true)); mp.st[v] = states[v].as<GState>(); }
+    mp.gt = tm.t;
+    return PDRS_OK;
+  };
+  if (!sharded) {
+    const long long cap = cm->groups_cap, block = 8 + cap * stride;
+    pk.cap = cap;
+    PDRS_TRY(grow(cm->send, (size_t)block * 8));
+    PDRS_TRY(grow(cm->recv, (size_t)block * 8 * world));
+    PDRS_TRY(dist_pack_launch<0>(c, NW, pk, cm->send.as<u64>(), nullptr, nullptr));
+    PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+    PDRS_TRY(pdrs_comm_allgather(cm, cm->send.p, cm->recv.p, (size_t)block * 8));
+    PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    cm->last_exchange_bytes = (int64_t)block * 8 * (world - 1);
+    // merge right away (same stream, no host round trip); the group counts are checked afterwards
+    PDRS_TRY(make_table((long long)world * cap));
+    mp.buf = cm->recv.as<u64>(); mp.nrows = (long long)world * cap; mp.cap = cap; mp.block = block;
+    PDRS_TRY(dist_merge_launch(c, NW, mp));
+    std::vector<u64> counts((size_t)world);
+    PDRS_CUDA(c, cudaMemcpy2DAsync(counts.data(), 8, cm->recv.p, (size_t)block * 8, 8, (size_t)world, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    bool fits = true;
+    for (int r = 0; r < world; r++) fits = fits && (long long)counts[r] <= cap;       // every rank sees the same counts: the decision is collective
+    if (!fits) {
+      if (result_mode == 1) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_groupby_agg_dist: a rank holds more than groups_cap = %lld groups; use the sharded result mode", cap);
+      sharded = true;
+      for (auto& s : states) s.release();
+      tm = TableMem();
+    }
+  }
+  if (sharded) {
+    // rows by destination rank: count, offsets, scatter
+    DevBuf cnt;
+    PDRS_TRY(cnt.alloc(c, (size_t)(3 * world + 2) * 8, true));
+    u64* dcount = cnt.as<u64>();
+    u64* dcur = dcount + world;
+    u64* doff = dcur + world;
+    std::vector<u64> hc((size_t)world, 0), off((size_t)world + 1, 0);
+    if (pk.G > 0) PDRS_TRY(dist_pack_launch<1>(c, NW, pk, nullptr, dcount, nullptr));
+    PDRS_CUDA(c, cudaMemcpyAsync(hc.data(), dcount, (size_t)world * 8, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < world; r++) off[r + 1] = off[r] + hc[r];
+    PDRS_CUDA(c, cudaMemcpyAsync(doff, off.data(), (size_t)world * 8, cudaMemcpyHostToDevice, c->stream));
+    PDRS_TRY(grow(cm->send, (size_t)std::max<long long>(pk.G, 1) * stride * 8));
+    if (pk.G > 0) PDRS_TRY(dist_pack_launch<2>(c, NW, pk, cm->send.as<u64>(), dcur, doff));
+    std::vector<u64> all((size_t)world * world);
+    PDRS_TRY(pdrs_comm_allgather_host(cm, hc.data(), all.data(), (size_t)world * 8));     // all[src][dst]
+    std::vector<size_t> soff(world), sb(world), roff(world), rb(world);
+    size_t T = 0;
+    int64_t to_peers = 0;
+    for (int r = 0; r < world; r++) {
+      soff[r] = (size_t)off[r] * stride * 8; sb[r] = (size_t)hc[r] * stride * 8;
+      roff[r] = T * stride * 8; rb[r] = (size_t)all[(size_t)r * world + cm->rank] * stride * 8;
+      T += (size_t)all[(size_t)r * world + cm->rank];
+      if (r != cm->rank) to_peers += (int64_t)sb[r];
+    }
+    PDRS_TRY(grow(cm->recv, std::max<size_t>(T, 1) * stride * 8));
+    PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
+    PDRS_TRY(pdrs_comm_alltoallv(cm, cm->send.p, soff.data(), sb.data(), cm->recv.p, roff.data(), rb.data()));
+    PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
+    cm->last_exchange_bytes = to_peers;
+    PDRS_TRY(make_table((long long)T));
+    mp.buf = cm->recv.as<u64>(); mp.nrows = (long long)T; mp.cap = 0; mp.block = 0;
+    PDRS_TRY(dist_merge_launch(c, NW, mp));
+  }
+  PDRS_TRY(finish_merged(c, ks, tm, states, res->key_dtype, nkeys, nvs, val_is_int.data(), ag.data(), naggs, res));
+  PDRS_CUDA(c, cudaEventElapsedTime(&cm->last_exchange_ms, c->ev_a, c->ev_b));
+  c->stats.main_kernel_ms = local_ms;
+  c->stats.groupby_algo_used = local_algo;
+  guard.r = nullptr;
+  *out = res;
+  return PDRS_OK;
+}
+
+extern "C" {
 
 int64_t pdrs_groupby_n_groups(const pdrs_groupby_result* r) { return r ? r->n_groups : -1; }
 
