@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
       const long long i = tb + (long long)j * GP_NT + tid;
       const bool inb = i < lim;
       if (FROM_COLS) {
-        if (GENERIC) { u64 w[1] = {0ull}; if (inb) load_key_generic<1>(in.ks, i, w); key[j] = w[0]; }
+        if (GENERIC) { u64 w[1] = {0ull}; if (inb) load_key_inline<1>(in.ks, i, w); key[j] = w[0]; }
         else key[j] = inb ? __ldcs(in.keys + i) : 0ull;
         val[j] = inb ? __ldcs(in.vals + i) : 0ull;
       } else {

@@ -180,6 +180,43 @@ __device__ __noinline__ bool load_key_generic(const KeySpec& ks, long long row, 
   return false;
 }
 
+// The same packing, fully inlined with a compile-time bound on the key loop, for kernels whose parameter block must stay in the
+// constant bank: load_key_generic() takes the KeySpec by ADDRESS, and a kernel that passes (part of) its parameter struct by
+// address gets the whole struct copied to local memory and read back with LDL in its hot loop.
+template <int NW>
+__device__ __forceinline__ bool load_key_inline(const KeySpec& ks, long long row, u64 (&w)[NW]) {
+#pragma unroll
+  for (int i = 0; i < NW; i++) w[i] = 0;
+  bool nullgroup = false;
+#pragma unroll
+  for (int k = 0; k < PDRS_MAX_KEYS; k++) {
+    if (k >= ks.nkeys) break;
+    const KeyColDev& c = ks.c[k];
+    bool isnull = c.nulls && pdrs_bit(c.nulls, row);
+    u64 v = 0;
+    if (!isnull) {
+      switch (c.dtype) {
+        case PDRS_I64: v = (u64)__ldg((const long long*)c.data + row) - (u64)c.offset; break;
+        case PDRS_F64: { const double d = __ldg((const double*)c.data + row); v = (d != d) ? 0x7FF8000000000000ull : (u64)__double_as_longlong(d); break; }
+        case PDRS_I32: v = ((u64)(long long)__ldg((const int*)c.data + row) - (u64)c.offset) & 0xFFFFFFFFull; break;
+        case PDRS_DICT_U32: { const uint32_t id = __ldg((const uint32_t*)c.data + row); if ((long long)id == c.null_alias) isnull = true; else v = (u64)id - (u64)c.offset; break; }
+        default: v = pdrs_bit((const uint8_t*)c.data, row); break;
+      }
+    }
+    if (isnull) {
+      if (ks.single_null) nullgroup = true;
+      else if (c.nword >= 0) {
+#pragma unroll
+        for (int i = 0; i < NW; i++) if (i == c.nword) w[i] |= 1ull << c.nshift;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NW; i++) if (i == c.word) w[i] |= v << c.shift;
+    }
+  }
+  return nullgroup;
+}
+
 // ---------------------------------------------------------------- global table
 // Slots are claimed with one CAS on the header word (0 -> BUSY), then the key words are written and the
 // header is published (FULL).  A thread that meets a BUSY slot must NOT spin on it: the publisher may be a
