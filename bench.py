@@ -55,24 +55,60 @@ def log(msg):
 
 # ---------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi sampled every 20 ms from before the warm-up; the summary uses the samples that fall inside the
-    timed region (mark_begin / mark_end), or, if the region was shorter than one sample, the samples under load."""
+    """SM clock, power and throttle reasons sampled through NVML every 25 ms from before the warm-up (a thread of this process;
+    `nvidia-smi -lms 20` as a child process was measured to stall every driver call of an allocation-heavy step by one polling
+    period).  The summary uses the samples inside the timed region (mark_begin / mark_end), or, if the region was shorter than
+    one sample, the samples under load.  Falls back to nvidia-smi at 200 ms when NVML cannot be loaded."""
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index=0):
         self.samples, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
+        self.stop_flag, self.thread, self.how = False, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.index
+            h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+            def loop():
+                while not self.stop_flag:
+                    try:
+                        sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                        rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        self.samples.append((time.perf_counter(), sm, mx, {k for k, b in self.BITS.items() if rs & b}))
+                    except Exception:
+                        pass
+                    time.sleep(0.025)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.how = "NVML, 25 ms"
+            return
+        except Exception:
+            pass
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.how = "nvidia-smi, 200 ms"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            rs = {name for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]) if v.lower().startswith("active")}
+            self.samples.append((time.perf_counter(), sm, mx, rs))
 
     def mark_begin(self):
         self.t0 = time.perf_counter()
@@ -81,23 +117,15 @@ class ClockSampler:
         self.t1 = time.perf_counter()
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             time.sleep(0.05)
             self.proc.terminate()
 
         def parse(rows):
             sm, mx, reasons = [], 0, set()
-            for _, s in rows:
-                f = [x.strip() for x in s.split(",")]
-                if len(f) < 7:
-                    continue
-                try:
-                    sm.append(float(f[0])); mx = max(mx, float(f[1]))
-                except ValueError:
-                    continue
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
+            for _, s, m, rs in rows:
+                sm.append(s); mx = max(mx, m); reasons |= rs
             return sm, mx, reasons
         inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1 + 0.03]
         sm, mx, reasons = parse(inside)
@@ -107,7 +135,7 @@ class ClockSampler:
             where = "whole run (timed region shorter than one sample)"
         sm.sort()
         hi = [x for x in sm if x > 0.5 * mx] or sm
-        return {"sm_mhz": hi[len(hi) // 2] if hi else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": where}
+        return {"sm_mhz": hi[len(hi) // 2] if hi else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": where, "sampler": self.how}
 
 
 # ---------------------------------------------------------------- the reference arm / CPU baselines (oracle/ = the checker, timed here only)
