@@ -22,6 +22,7 @@
 #include <cmath>
 
 #include "groupby_kernels.cuh"
+#include "gb_final.cuh"
 
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
@@ -186,6 +187,194 @@ __global__ void gp_counts_kernel(const u64* __restrict__ cursor, const u64* __re
   }
 }
 
+// ---------------------------------------------------------------- hash aggregation of COMPLETE partitions, straight to the result
+// After hash partitioning a group lives in exactly one partition.  When that partition received all of its rows (no run of it
+// was parked in a side area: hot keys), the CTA that aggregates it holds the FINAL state of each of its groups and can write
+// them to the result directly - one output reservation per partition - instead of adding one batch per group to the global
+// table (~10 L2 atomics per group, a second scan of the table by the finalisation kernel).  Few rows per group (heavy-tailed
+// key tuples: 3 - 20 rows per group) are also where the tile-sort kernel is weakest: every row of a partition's first tile is
+// a new key.  So this kernel keeps one open-addressing table per partition in shared memory - keys + state planes, ~600
+// groups in 2048 slots - and updates it with shared-memory atomics (~150 SM-cycles per 32 rows: affordable next to the three
+// passes over HBM the partitioning costs).  Per tile of 2048 rows: (A) find / claim the slot of every row, (B) the first
+// finite value of a group becomes its pivot (plain store, any winner is fine), (C) rows / n / S1 / S2 / min / max / isum atomics.
+// A partition whose table fills up spills rows to the global table and then flushes its groups there as well (a group must
+// not be reported twice); partitions flagged incomplete are left to the tile-sort kernel, which flushes to the table.
+struct GpDirect {
+  FinParams fin;            // result arrays with room for `cap` groups
+  long long cap;
+  u64* cursor;              // [0] groups written straight to the result, [1] partition tickets
+  int dv;                   // index of the value column this pass aggregates
+};
+constexpr int GH_NT = 512, GH_ITEMS = 4, GH_TILE = GH_NT * GH_ITEMS;
+static size_t gh_smem(int S) { return (size_t)(S + 1) * 64 + 64; }
+
+template <typename VT, int FLAGS>
+__global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p, const GpDirect d, const u64* __restrict__ part_cnt, int log_s) {
+  using T = ValTraits<VT>;
+  constexpr bool IS_INT = T::is_int, ALL = FLAGS == GB_ALL;
+  constexpr u64 EMPTY = ~0ull;
+  extern __shared__ __align__(16) unsigned char gsm[];
+  const int S = 1 << log_s, S1n = S + 1;                         // slot S belongs to the key whose packed word is all ones
+  u64* keys = reinterpret_cast<u64*>(gsm);
+  u64* piv = keys + S1n;
+  double* aS1 = reinterpret_cast<double*>(piv + S1n);
+  double* aS2 = aS1 + S1n;
+  u64* amn = reinterpret_cast<u64*>(aS2 + S1n);
+  u64* amx = amn + S1n;
+  u64* aisum = amx + S1n;
+  uint32_t* arows = reinterpret_cast<uint32_t*>(aisum + S1n);
+  uint32_t* an = arows + S1n;
+  __shared__ long long sh_q;
+  __shared__ uint32_t sh_groups, sh_spilled, sh_out;
+  __shared__ u64 sh_base;
+  const int tid = threadIdx.x;
+  const int limit = S - (S >> 3);                                // claim at most 7/8 of the slots
+  for (;;) {
+    if (tid == 0) sh_q = (long long)atomicAdd(&d.cursor[1], 1ull);
+    __syncthreads();
+    const long long q = sh_q;
+    if (q >= p.part_n) break;
+    const long long cnt = min((long long)__ldg(part_cnt + q), p.part_cap);
+    if (cnt == 0) { __syncthreads(); continue; }
+    for (int i = tid; i < S1n; i += GH_NT) { keys[i] = EMPTY; piv[i] = 0; aS1[i] = 0.0; aS2[i] = 0.0; amn[i] = 0; amx[i] = 0; aisum[i] = 0; arows[i] = 0; an[i] = 0; }
+    if (tid == 0) { sh_groups = 0; sh_spilled = 0; sh_out = 0; }
+    __syncthreads();
+    const long long base = q * p.part_cap;
+    for (long long t0 = 0; t0 < cnt; t0 += GH_TILE) {
+      u64 key[GH_ITEMS], vb[GH_ITEMS];
+      int slot[GH_ITEMS];
+      uint32_t live = 0, vnull = 0, spill = 0;
+#pragma unroll
+      for (int j = 0; j < GH_ITEMS; j++) {
+        const long long i = t0 + (long long)j * GH_NT + tid;
+        key[j] = 0; vb[j] = 0; slot[j] = -1;
+        if (i < cnt) {
+          live |= 1u << j;
+          key[j] = __ldcs(p.part_keys + base + i);
+          vb[j] = __ldcs(p.part_vals + base + i);
+          if (p.part_flags && (__ldcs(p.part_flags + base + i) & 1)) vnull |= 1u << j;
+        }
+      }
+      // ---- (A) slot of every row
+#pragma unroll
+      for (int j = 0; j < GH_ITEMS; j++) {
+        if (!((live >> j) & 1u)) continue;
+        if (key[j] == EMPTY) { slot[j] = S; if (keys[S] == EMPTY) { if (atomicCAS(&keys[S], EMPTY, 0ull) == EMPTY) atomicAdd(&sh_groups, 1u); } continue; }
+        uint32_t s = (gp_hash32(key[j]) << p.part_bits) >> (32 - log_s);
+        for (int probe = 0; probe < S; probe++) {
+          u64 k = *reinterpret_cast<volatile u64*>(&keys[s]);
+          if (k == EMPTY) {
+            if (*reinterpret_cast<volatile uint32_t*>(&sh_groups) >= (uint32_t)limit) break;          // table full: the row spills
+            k = atomicCAS(&keys[s], EMPTY, key[j]);
+            if (k == EMPTY) { atomicAdd(&sh_groups, 1u); k = key[j]; }
+          }
+          if (k == key[j]) { slot[j] = (int)s; break; }
+          s = (s + 1) & (uint32_t)(S - 1);
+        }
+        if (slot[j] < 0) spill |= 1u << j;
+      }
+      if (__any_sync(0xFFFFFFFFu, spill != 0)) {        // rare: more groups than the table holds -> global table, row by row
+        if (spill) sh_spilled = 1;
+#pragma unroll
+        for (int j = 0; j < GH_ITEMS; j++)
+          gb_spill_rows<1, VT, FLAGS>(p.gt, key[j], 0ull, 0ull, (spill >> j) & 1u, p.count_rows != 0, !((vnull >> j) & 1u), T::from_bits(vb[j]));
+      }
+      __syncthreads();
+      // ---- (B) pivot = some finite value of the group (all racers belong to this tile; everybody reads it after the barrier)
+      if (ALL) {
+#pragma unroll
+        for (int j = 0; j < GH_ITEMS; j++) {
+          if (slot[j] < 0 || ((vnull >> j) & 1u)) continue;
+          const double x = T::to_f64(T::from_bits(vb[j]));
+          if (is_finite_f64(x) && *reinterpret_cast<volatile u64*>(&piv[slot[j]]) == 0) *reinterpret_cast<volatile u64*>(&piv[slot[j]]) = (u64)__double_as_longlong(x) | 1ull;
+        }
+        __syncthreads();
+      }
+      // ---- (C) accumulate
+#pragma unroll
+      for (int j = 0; j < GH_ITEMS; j++) {
+        if (slot[j] < 0) continue;
+        const int s = slot[j];
+        atomicAdd(&arows[s], 1u);
+        if ((vnull >> j) & 1u) continue;
+        atomicAdd(&an[s], 1u);
+        const VT v = T::from_bits(vb[j]);
+        if (IS_INT) atomicAdd(&aisum[s], vb[j]);
+        if (ALL) {
+          const double dd = T::to_f64(v) - __longlong_as_double((long long)piv[s]);
+          atomicAdd(&aS1[s], dd);
+          atomicAdd(&aS2[s], dd * dd);
+          if (T::orderable(v)) {
+            const u64 o = T::ord(v);
+            if (~o > *reinterpret_cast<volatile u64*>(&amn[s])) atomicMax(&amn[s], ~o);
+            if (o > *reinterpret_cast<volatile u64*>(&amx[s])) atomicMax(&amx[s], o);
+          }
+        } else if (!IS_INT) atomicAdd(&aS1[s], T::to_f64(v));
+      }
+      __syncthreads();
+    }
+    // ---- the partition is done: its groups are final
+    const uint32_t ng = sh_groups;
+    if (tid == 0) {
+      u64 b = ~0ull;
+      if (!sh_spilled) { b = atomicAdd(&d.cursor[0], (u64)ng); if (b + ng > (u64)d.cap) { atomicAdd(&d.cursor[0], (u64)0 - (u64)ng); b = ~0ull; } }
+      sh_base = b;
+    }
+    __syncthreads();
+    const u64 obase = sh_base;
+    for (int s0 = 0; s0 < S1n; s0 += GH_NT) {            // uniform trip count: the table insertion below is warp-synchronous
+      const int s = s0 + tid;
+      const bool have = s < S1n && keys[s] != EMPTY;
+      GState st;
+      st.n = 0; st.pivotx = 0; st.S1 = 0; st.S2 = 0; st.mnc = 0; st.mxo = 0; st.isum = 0; st.pad = 0;
+      u64 rows = 0, kw = 0;
+      if (have) {
+        rows = arows[s]; kw = s == S ? EMPTY : keys[s];
+        st.n = an[s]; st.S1 = aS1[s]; st.S2 = aS2[s]; st.mnc = amn[s]; st.mxo = amx[s]; st.isum = aisum[s];
+        st.pivotx = piv[s] ? (piv[s] ^ GB_PIV_X) : 0ull;
+      }
+      if (obase != ~0ull) {
+        if (!have) continue;
+        const long long o = (long long)(obase + atomicAdd(&sh_out, 1u));
+        const u64 w[PDRS_MAX_WORDS] = {kw, 0ull, 0ull};
+        fin_write_group(d.fin, o, w, false, rows, [&](int v) -> const GState* { return v == d.dv ? &st : nullptr; });
+      } else {                                             // spilled rows / result capacity: through the global table like everybody else
+        u64 w[1] = {kw};
+        const long long gs = g_find_or_insert<1>(p.gt, w, have);
+        if (!have || gs < 0) continue;
+        if (p.count_rows) atomicAdd(&p.gt.hdr[gs].rowsw, rows);
+        g_update_batch<FLAGS, IS_INT>(p.gt, gs, 0ull, st.n, fin_pivot(st.pivotx), st.pivotx != 0, st.S1, st.S2, st.isum, st.mnc, st.mxo);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename VT, int FLAGS>
+static cudaError_t gh_launch(const GbParams& p, const GpDirect& d, const u64* cnt, int log_s, int ctas, cudaStream_t s) {
+  const size_t smem = gh_smem(1 << log_s);
+  auto k = gp_hash_agg_kernel<VT, FLAGS>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k<<<ctas, GH_NT, smem, s>>>(p, d, cnt, log_s);
+  return cudaGetLastError();
+}
+
+// which partitions are complete: hash partitions none of whose rows (nor of its level-1 bucket's rows) went to a side area.
+// out_hash[q] = rows for the hash-aggregation kernel, out_ts[q] = rows for the tile-sort kernel (incomplete partitions and the
+// chunks of the side area); cnt = the clamped counts (gp_counts_kernel) or the raw cursors when there is no side area.
+__global__ void gp_split_counts_kernel(const u64* __restrict__ cnt, const u64* __restrict__ cur1, long long cap1, int bits2, const u64* __restrict__ cur2, long long cap2,
+                                       int nparts, int nall, int use_hash, u64* __restrict__ out_hash, u64* __restrict__ out_ts) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nall) return;
+  const u64 c = cnt[q];
+  bool complete = use_hash && q < nparts;
+  if (complete && cur2) complete = cur2[q] <= (u64)cap2 && cur1[q >> bits2] <= (u64)cap1;
+  else if (complete) complete = cur1[q] <= (u64)cap1;
+  out_hash[q] = complete ? c : 0ull;
+  out_ts[q] = complete ? 0ull : c;
+}
+
 long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 
 }  // namespace
@@ -197,8 +386,9 @@ long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
 // holds ALL rows of 1 / 2^bits1 of the key space, so a sample of it sees 2^bits1 times more of that slice: when
 // groups(bucket 0) x 2^bits1 exceeds the estimate by more than 1.5x the pass stops, *est_refined is set, and the
 // caller starts over with the better estimate (right-sized table, right number of partitions).
+struct GbDirectOut { const FinParams* fin; long long cap; u64* cursor; int dv; };   // (declared in groupby.cu as well)
 int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed,
-                     long long* est_refined) {
+                     long long* est_refined, const GbDirectOut* direct) {
   *dirty = false;
   *skewed = false;
   if (est_refined) *est_refined = 0;
@@ -354,6 +544,32 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   int lg = 0;
   while ((1 << lg) < ts_slots) lg++;
   tp.sh_log_slots = lg;
+  // Complete partitions (all rows of their groups are in them): aggregated by the shared-memory hash kernel, groups written
+  // straight to the result.  Chosen when a group has few rows (the tile-sort kernel pays for every new key of a partition's
+  // first tile); the tile-sort kernel then only sees the incomplete partitions and the side-area chunks.
+  DevBuf split;
+  const bool use_hash = direct && c->opt_part_hash != 2 && (c->opt_part_hash == 1 || n / std::max<long long>(est_groups, 1) < 64);
+  if (direct) {
+    PDRS_TRY(split.alloc(c, (size_t)(2 * nparts_all + 2) * 8));
+    u64* cnt_hash = split.as<u64>();
+    u64* cnt_ts = cnt_hash + nparts_all;
+    gp_split_counts_kernel<<<(int)((nparts_all + 255) / 256), 256, 0, c->stream>>>(pc, cur1, cap1, bits2, bits2 ? cur2 : nullptr, cap2, (int)nparts, (int)nparts_all, use_hash ? 1 : 0, cnt_hash, cnt_ts);
+    c->stats.kernel_launches++;
+    if (use_hash) {
+      GpDirect gd{};
+      gd.fin = *direct->fin; gd.cap = direct->cap; gd.cursor = direct->cursor; gd.dv = direct->dv;
+      int log_s = 8;
+      while (log_s < 11 && (1ll << log_s) < 3 * std::max<long long>(1, est_groups >> bits)) log_s++;
+      const int hctas = (int)std::min<long long>(c->sm_count, nparts);
+      GbParams hp = tp;
+      cudaError_t e;
+      if (!is_int) e = flags == GB_SUM ? gh_launch<double, GB_SUM>(hp, gd, cnt_hash, log_s, hctas, c->stream) : gh_launch<double, GB_ALL>(hp, gd, cnt_hash, log_s, hctas, c->stream);
+      else e = flags == GB_SUM ? gh_launch<long long, GB_SUM>(hp, gd, cnt_hash, log_s, hctas, c->stream) : gh_launch<long long, GB_ALL>(hp, gd, cnt_hash, log_s, hctas, c->stream);
+      PDRS_CUDA(c, e);
+      c->stats.kernel_launches++;
+      tp.part_cnt = cnt_ts;
+    }
+  }
   PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts_all * tp.part_cpp), ts_smem, c->stream));
   c->stats.kernel_launches++;
   if (c->opt_timing) {

@@ -10,58 +10,10 @@
 
 #include "groupby_kernels.cuh"
 #include "gb_few.cuh"
+#include "gb_final.cuh"
 #include "comm.cuh"
 
-// ---------------------------------------------------------------- finalisation
-struct FinVal { const GState* st; int is_int; int flags; long long* validn_out; u64* states_out; };
-struct FinAgg { int val; int op; double* out; };
-struct FinParams {
-  GTable gt;
-  KeySpec ks;
-  void* key_out[PDRS_MAX_KEYS];
-  uint8_t* key_null_out[PDRS_MAX_KEYS];
-  long long* rows_out;
-  int nvals, naggs;
-  FinVal vals[PDRS_MAX_VALS];
-  FinAgg aggs[PDRS_MAX_AGGS];
-};
-
-__device__ __forceinline__ double fin_pivot(u64 px) { return px ? __longlong_as_double((long long)(px ^ GB_PIV_X)) : 0.0; }
-
-// aggregation.rs:500-754: every aggregate is an f64; empty / all-NULL -> 0.0; Min/Max sentinel collapse.
-__device__ double fin_eval(const GState& s, int is_int, int op, u64 rows) {
-  const double n = (double)s.n;
-  const double c = fin_pivot(s.pivotx);
-  switch (op) {
-    case PDRS_COUNT: return (double)rows;                                     // :743 group size, NULLs included
-    case PDRS_SUM:
-      if (s.n == 0) return 0.0;
-      return is_int ? (double)(long long)s.isum : (s.S1 + n * c);              // :507-515 / :625-633
-    case PDRS_MEAN:
-      if (s.n == 0) return 0.0;
-      return is_int ? (double)(long long)s.isum / n : (c + s.S1 / n);          // :516-530 / :634-648
-    case PDRS_MIN: {
-      if (s.mnc == 0) return 0.0;
-      u64 o = ~s.mnc;
-      if (is_int) return (double)(long long)(o ^ GB_SIGN);                     // :531-543 (i64::MAX never stored: collapses to 0.0)
-      double v = pdrs_unord_f64(o);
-      return v == __longlong_as_double(0x7FF0000000000000ll) ? 0.0 : v;        // :649-661 (min == +INF -> 0.0)
-    }
-    case PDRS_MAX: {
-      if (s.mxo == 0) return 0.0;
-      if (is_int) return (double)(long long)(s.mxo ^ GB_SIGN);                 // :544-556
-      { double v = pdrs_unord_f64(s.mxo); return v == __longlong_as_double((long long)0xFFF0000000000000ull) ? 0.0 : v; }   // :662-674 (max == -INF -> 0.0)
-    }
-    case PDRS_STD: case PDRS_VAR: {                                            // :557-584 / :675-702 / :881-903
-      if (s.n <= 1) return 0.0;
-      double var = (s.S2 - s.S1 * s.S1 / n) / (n - 1.0);
-      if (var < 0.0) var = 0.0;
-      return op == PDRS_STD ? sqrt(var) : var;
-    }
-  }
-  return 0.0;
-}
-
+// ---------------------------------------------------------------- finalisation (formulas + key decoding: gb_final.cuh)
 __global__ void gb_finalize_kernel(const FinParams p) {
   const long long total = p.gt.slots + 1;
   const int lane = threadIdx.x & 31;
@@ -77,8 +29,6 @@ __global__ void gb_finalize_kernel(const FinParams p) {
     basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
     if (!full) continue;
     const long long o = (long long)(basepos + __popc(m & ((1u << lane) - 1u)));
-    const u64 rows = rw & GB_CNT_MASK;
-    // keys
     u64 w[PDRS_MAX_WORDS] = {0, 0, 0};
     const bool nullgroup = s == p.gt.slots;
     if (!nullgroup) {
@@ -86,37 +36,7 @@ __global__ void gb_finalize_kernel(const FinParams p) {
       if (p.ks.nwords > 1) w[1] = p.gt.kw1[s];
       if (p.ks.nwords > 2) w[2] = p.gt.kw2[s];
     }
-    for (int k = 0; k < p.ks.nkeys; k++) {
-      const KeyColDev& c = p.ks.c[k];
-      bool isnull = nullgroup;
-      if (!nullgroup && c.nword >= 0) isnull = (w[c.nword] >> c.nshift) & 1;
-      u64 v = 0;
-      if (!isnull) { v = w[c.word] >> c.shift; if (c.bits < 64) v &= (1ull << c.bits) - 1ull; v += (u64)c.offset; }
-      switch (c.dtype) {
-        case PDRS_I64: case PDRS_F64: reinterpret_cast<u64*>(p.key_out[k])[o] = v; break;
-        case PDRS_I32: case PDRS_DICT_U32: reinterpret_cast<uint32_t*>(p.key_out[k])[o] = (uint32_t)v; break;
-        case PDRS_BOOL_BITS: reinterpret_cast<uint8_t*>(p.key_out[k])[o] = (uint8_t)v; break;
-      }
-      p.key_null_out[k][o] = isnull ? 1 : 0;
-    }
-    p.rows_out[o] = (long long)rows;
-    GState zero;
-    zero.n = 0; zero.pivotx = 0; zero.S1 = 0; zero.S2 = 0; zero.mnc = 0; zero.mxo = 0; zero.isum = 0; zero.pad = 0;
-    for (int v = 0; v < p.nvals; v++) {
-      const GState st = p.vals[v].st ? p.vals[v].st[s] : zero;
-      if (p.vals[v].validn_out) p.vals[v].validn_out[o] = (long long)st.n;
-      if (p.vals[v].states_out) {
-        u64* q = p.vals[v].states_out + 8 * o;
-        q[0] = rows; q[1] = st.n; q[2] = st.pivotx; q[3] = (u64)__double_as_longlong(st.S1);
-        q[4] = (u64)__double_as_longlong(st.S2); q[5] = st.mnc; q[6] = st.mxo; q[7] = st.isum;
-      }
-    }
-    for (int a = 0; a < p.naggs; a++) {
-      const FinAgg& ag = p.aggs[a];
-      if (ag.val < 0 || !p.vals[ag.val].st) { ag.out[o] = ag.op == PDRS_COUNT ? (double)rows : 0.0; continue; }
-      const GState st = p.vals[ag.val].st[s];
-      ag.out[o] = fin_eval(st, p.vals[ag.val].is_int, ag.op, rows);
-    }
+    fin_write_group(p, o, w, nullgroup, rw & GB_CNT_MASK, [&](int v) -> const GState* { return p.vals[v].st ? &p.vals[v].st[s] : nullptr; });
   }
 }
 
@@ -349,8 +269,9 @@ int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* k
 }
 
 int32_t gb_radix_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, float* kernel_ms);   // gb_radix.cu
+struct GbDirectOut { const FinParams* fin; long long cap; u64* cursor; int dv; };   // finished groups written straight to the result (defined in gb_part.cu too)
 int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, long long est_groups, float* kernel_ms, bool* dirty, bool* skewed,
-                     long long* est_refined);   // gb_part.cu
+                     long long* est_refined, const GbDirectOut* direct = nullptr);   // gb_part.cu
 // gb_tsort.cu
 bool gb_tsort_geometry(long long cap, bool dense, int smem_budget, int nt_pref, int* nt, int* gpt, int* slots, size_t* smem);
 long long gb_tsort_tile_rows();
@@ -630,6 +551,45 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   if (c->opts.groupby_algo == PDRS_GB_TILESORT && !ts_fit && c->opts.groups_hint > 0)
     return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "groupby_algo=TILESORT: needs one Int64 key column and at most ~2000 groups (estimated %lld)", est);
 
+  // result arrays for `cap` groups + the finalisation parameters that point at them (state pointers are filled in later)
+  FinParams fp{};
+  fp.ks = ks;
+  auto alloc_outputs = [&](size_t cap) -> int32_t {
+    for (int k = 0; k < nkeys; k++) {
+      PDRS_TRY(res->key_vals[k].alloc(c, cap * key_out_bytes(keys[k].dtype)));
+      PDRS_TRY(res->key_nulls[k].alloc(c, cap));
+      fp.key_out[k] = res->key_vals[k].p;
+      fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
+    }
+    PDRS_TRY(res->rows.alloc(c, cap * 8));
+    fp.rows_out = res->rows.as<long long>();
+    fp.nvals = nvals;
+    for (int v = 0; v < nvals; v++) { fp.vals[v].st = nullptr; fp.vals[v].is_int = vals[v].dtype == PDRS_I64; fp.vals[v].flags = std::max(need[v], 0); fp.vals[v].validn_out = nullptr; fp.vals[v].states_out = nullptr; }
+    for (size_t i = 0; i < passes.size(); i++) {
+      const int v = passes[i].val;
+      if (v < 0) continue;
+      PDRS_TRY(res->validn[v].alloc(c, cap * 8));
+      fp.vals[v].validn_out = res->validn[v].as<long long>();
+      if (mode == MODE_PARTIAL) {
+        PDRS_TRY(res->states[v].alloc(c, cap * 64));
+        fp.vals[v].states_out = res->states[v].as<u64>();
+      }
+    }
+    fp.naggs = naggs;
+    for (int a = 0; a < naggs; a++) {
+      PDRS_TRY(res->aggs[a].alloc(c, cap * 8));
+      fp.aggs[a].val = aggs[a].op == PDRS_COUNT ? -1 : aggs[a].value_col;
+      fp.aggs[a].op = aggs[a].op;
+      fp.aggs[a].out = res->aggs[a].as<double>();
+    }
+    return PDRS_OK;
+  };
+  // Partitioned path with ONE value column: finished groups of complete partitions go straight to the result (gb_part.cu);
+  // direct_cap = room in the result arrays, direct_cur[0] = groups written that way.
+  DevBuf direct_cur;
+  long long direct_cap = 0, direct_groups = 0;
+  bool direct_off = c->opt_part_direct == 0;
+
   int algo = c->opts.groupby_algo;
   if (algo == PDRS_GB_DENSE || algo == PDRS_GB_TILESORT) algo = PDRS_GB_SHARED;
   long long slots_mult = 1;
@@ -717,8 +677,17 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           float ms = 0;
           bool dirty = false, skewed = false;
           long long est_new = 0;
-          int32_t rs = gb_part_pass(c, gp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed, reestimated ? nullptr : &est_new);
+          GbDirectOut dout{};
+          if (passes.size() == 1 && !direct_off) {
+            direct_cap = std::min<long long>(n, 2 * est + (1 << 20));
+            PDRS_TRY(alloc_outputs((size_t)direct_cap));
+            PDRS_TRY(direct_cur.alloc(c, 64, true));
+            fp.gt = gp.gt;
+            dout.fin = &fp; dout.cap = direct_cap; dout.cursor = direct_cur.as<u64>(); dout.dv = passes[i].val;
+          }
+          int32_t rs = gb_part_pass(c, gp, passes[i].is_int, passes[i].flags, est, &ms, &dirty, &skewed, reestimated ? nullptr : &est_new, dout.fin ? &dout : nullptr);
           if (rs == PDRS_OK) { c->stats.main_kernel_ms += ms; c->stats.groupby_algo_used = PDRS_GB_PARTITIONED; continue; }
+          direct_cap = 0;
           if (rs != PDRS_ERR_UNSUPPORTED) return rs;
           if (est_new > 0) {        // the first bucket shows far more groups than the sample predicted: start over with that estimate
             est = est_new; c->stats.est_groups = est; reestimated = true; restart = true;
@@ -817,53 +786,34 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
         }
       }
     }
-    if (restart) { restart = false; for (auto& s : states) s.release(); attempt--; continue; }
+    if (restart) { restart = false; for (auto& s : states) s.release(); direct_cap = 0; attempt--; continue; }
     PDRS_TRY(read_counters(c, tm, cn));
     c->stats.spilled_rows = (int64_t)cn[CNT_SPILLED];
     if (cn[CNT_OVERFLOW] == 0 && cn[CNT_SPIN_FAIL] == 0) break;
     c->stats.retries++;
     slots_mult *= 4;
     few_off = true;
+    direct_cap = 0;
     if ((use_shared || ts_fit) && (long long)cn[CNT_SPILLED] > n / 16) algo = PDRS_GB_GLOBAL;
     for (auto& s : states) s.release();
   }
 
-  // ---- finalise
-  const int64_t G = (int64_t)cn[CNT_NGROUPS] + ((cn[CNT_N] & GB_FULL) ? 1 : 0);
+  // ---- finalise: the groups of the table are appended behind the groups that were written straight to the result
+  const int64_t Gt = (int64_t)cn[CNT_NGROUPS] + ((cn[CNT_N] & GB_FULL) ? 1 : 0);
+  if (direct_cap > 0) {
+    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 12, direct_cur.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    direct_groups = c->pinned_scalars[12];
+    if (direct_groups + Gt > direct_cap) return pdrs_fail(c, PDRS_ERR_OOM, "groupby: %lld groups exceed the %lld the result was sized for (cardinality estimate %lld); set groups_hint", (long long)(direct_groups + Gt), direct_cap, est);
+    PDRS_CUDA(c, cudaMemcpyAsync(tm.t.counters + CNT_OUT, direct_cur.p, 8, cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    PDRS_TRY(alloc_outputs((size_t)std::max<int64_t>(Gt, 1)));
+  }
+  const int64_t G = Gt + direct_groups;
   res->n_groups = G;
-  FinParams fp{};
   fp.gt = tm.t;
-  fp.ks = ks;
-  const size_t Galloc = (size_t)std::max<int64_t>(G, 1);
-  for (int k = 0; k < nkeys; k++) {
-    PDRS_TRY(res->key_vals[k].alloc(c, Galloc * key_out_bytes(keys[k].dtype)));
-    PDRS_TRY(res->key_nulls[k].alloc(c, Galloc));
-    fp.key_out[k] = res->key_vals[k].p;
-    fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
-  }
-  PDRS_TRY(res->rows.alloc(c, Galloc * 8));
-  fp.rows_out = res->rows.as<long long>();
-  fp.nvals = nvals;
-  for (int v = 0; v < nvals; v++) { fp.vals[v].st = nullptr; fp.vals[v].is_int = vals[v].dtype == PDRS_I64; fp.vals[v].flags = std::max(need[v], 0); }
-  for (size_t i = 0; i < passes.size(); i++) {
-    const int v = passes[i].val;
-    if (v < 0) continue;
-    fp.vals[v].st = states[i].as<GState>();
-    PDRS_TRY(res->validn[v].alloc(c, Galloc * 8));
-    fp.vals[v].validn_out = res->validn[v].as<long long>();
-    if (mode == MODE_PARTIAL) {
-      PDRS_TRY(res->states[v].alloc(c, Galloc * 64));
-      fp.vals[v].states_out = res->states[v].as<u64>();
-    }
-  }
-  fp.naggs = naggs;
-  for (int a = 0; a < naggs; a++) {
-    PDRS_TRY(res->aggs[a].alloc(c, Galloc * 8));
-    fp.aggs[a].val = aggs[a].op == PDRS_COUNT ? -1 : aggs[a].value_col;
-    fp.aggs[a].op = aggs[a].op;
-    fp.aggs[a].out = res->aggs[a].as<double>();
-  }
-  if (G > 0) {
+  for (size_t i = 0; i < passes.size(); i++) if (passes[i].val >= 0) fp.vals[passes[i].val].st = states[i].as<GState>();
+  if (Gt > 0) {
     int g = pdrs_grid_for(c, tm.t.slots + 1, 256);
     gb_finalize_kernel<<<g, 256, 0, c->stream>>>(fp);
     c->stats.kernel_launches++;

@@ -238,6 +238,52 @@ def test_partitioned_high_cardinality_path(ctx, oracle):
             ctx.set_option("part", 1)
 
 
+@pytest.mark.parametrize("part_hash", [1, 2])
+def test_partitioned_groups_written_straight_to_the_result(ctx, oracle, part_hash):
+    # gb_part.cu: complete hash partitions are aggregated in a shared-memory table and their groups are written to the result
+    # directly (part_hash = 1); incomplete partitions (a hot key parked part of them in the side area) and part_hash = 2 go
+    # through the tile-sort kernel and the global table.  Few rows per group, the all-ones key word, Int64 values, sum-only,
+    # a moderately hot key, partial states (the multi-GPU path merges them).
+    rng = np.random.default_rng(66)
+    n = 2_500_000
+    kv = rng.integers(0, 300_000, n) * 1_000_003 - 7
+    kv[::1001] = -1                                     # the key whose bits are all ones has a reserved table slot
+    hot = rng.random(n) < 0.08
+    kv[hot] = 424_242_424_242                           # its partition overflows into the side area: incomplete -> table
+    k = Spec(pb.I64, kv)
+    v = Spec(pb.F64, rng.normal(1e6, 3.0, n), nulls=rng.random(n) < 0.05)
+    vi = Spec(pb.I64, rng.integers(-2**61, 2**61, n), nulls=rng.random(n) < 0.05)
+    ctx.set_option("part_hash", part_hash)
+    try:
+        got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6] + [(0, pb.VAR)], device=True)
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED and len(got) == len(np.unique(kv))
+        compare_groupby(pb, oracle, ctx, [k], [vi], [(0, op) for op in ALL6], device=True)
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+        compare_groupby(pb, oracle, ctx, [k], [v], [(0, pb.SUM), (0, pb.MEAN), (0, pb.COUNT)], device=True)
+        k2 = Spec(pb.I32, rng.integers(0, 700, n).astype(np.int32))
+        k3 = Spec(pb.DICT_U32, rng.integers(0, 900, n).astype(np.uint32), pool=[f"s{i}" for i in range(900)])
+        compare_groupby(pb, oracle, ctx, [k2, k3], [v], [(0, op) for op in ALL6], device=True)          # packed two-key tuples, ~4 rows per group
+        assert ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
+        # partial states of the same groups merge to the same result (pdrs_groupby_partial + pdrs_groupby_merge)
+        kc, vc = ctx.upload(k.gpu(pb)), ctx.upload(v.gpu(pb))
+        whole = ctx.groupby_agg([kc], [vc], [(0, op) for op in ALL6])
+        part = ctx.groupby_partial([kc], [vc], all_stats=True)
+        G = part.n_groups
+        assert G == whole.n_groups
+        kcol = pb.Column(pb.I64, device_ptr=part.key_dev(0), length=G)
+        merged = ctx.groupby_merge([kcol], [part.states_dev(0)], [False], G, [(0, op) for op in ALL6])
+        wk, mk = whole.key(0)[0], merged.key(0)[0]
+        wo, mo = np.argsort(wk), np.argsort(mk)
+        assert np.array_equal(wk[wo], mk[mo])
+        for a in range(6):
+            assert np.allclose(whole.agg(a)[wo], merged.agg(a)[mo], rtol=1e-12, atol=0)
+        for r in (whole, part, merged):
+            r.close()
+        ctx.free(kc); ctx.free(vc)
+    finally:
+        ctx.set_option("part_hash", 0)
+
+
 def test_partition_overflow_falls_back(ctx, oracle):
     # heavily skewed high-cardinality keys: one key owns half of the rows, so its hash bucket overflows the padded
     # range of the one-pass partition; the call must restart on the global-table path and still match the oracle
