@@ -554,30 +554,38 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   // result arrays for `cap` groups + the finalisation parameters that point at them (state pointers are filled in later)
   FinParams fp{};
   fp.ks = ks;
-  auto alloc_outputs = [&](size_t cap) -> int32_t {
+  // keep > 0: the arrays already hold `keep` finished groups (written straight to the result) that move to the new arrays
+  auto alloc_outputs = [&](size_t cap, size_t keep = 0) -> int32_t {
+    auto renew = [&](DevBuf& b, size_t elem) -> int32_t {
+      DevBuf nb;
+      PDRS_TRY(nb.alloc(c, cap * elem));
+      if (keep && b.p) PDRS_CUDA(c, cudaMemcpyAsync(nb.p, b.p, keep * elem, cudaMemcpyDeviceToDevice, c->stream));
+      b = std::move(nb);
+      return PDRS_OK;
+    };
     for (int k = 0; k < nkeys; k++) {
-      PDRS_TRY(res->key_vals[k].alloc(c, cap * key_out_bytes(keys[k].dtype)));
-      PDRS_TRY(res->key_nulls[k].alloc(c, cap));
+      PDRS_TRY(renew(res->key_vals[k], key_out_bytes(keys[k].dtype)));
+      PDRS_TRY(renew(res->key_nulls[k], 1));
       fp.key_out[k] = res->key_vals[k].p;
       fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
     }
-    PDRS_TRY(res->rows.alloc(c, cap * 8));
+    PDRS_TRY(renew(res->rows, 8));
     fp.rows_out = res->rows.as<long long>();
     fp.nvals = nvals;
     for (int v = 0; v < nvals; v++) { fp.vals[v].st = nullptr; fp.vals[v].is_int = vals[v].dtype == PDRS_I64; fp.vals[v].flags = std::max(need[v], 0); fp.vals[v].validn_out = nullptr; fp.vals[v].states_out = nullptr; }
     for (size_t i = 0; i < passes.size(); i++) {
       const int v = passes[i].val;
       if (v < 0) continue;
-      PDRS_TRY(res->validn[v].alloc(c, cap * 8));
+      PDRS_TRY(renew(res->validn[v], 8));
       fp.vals[v].validn_out = res->validn[v].as<long long>();
       if (mode == MODE_PARTIAL) {
-        PDRS_TRY(res->states[v].alloc(c, cap * 64));
+        PDRS_TRY(renew(res->states[v], 64));
         fp.vals[v].states_out = res->states[v].as<u64>();
       }
     }
     fp.naggs = naggs;
     for (int a = 0; a < naggs; a++) {
-      PDRS_TRY(res->aggs[a].alloc(c, cap * 8));
+      PDRS_TRY(renew(res->aggs[a], 8));
       fp.aggs[a].val = aggs[a].op == PDRS_COUNT ? -1 : aggs[a].value_col;
       fp.aggs[a].op = aggs[a].op;
       fp.aggs[a].out = res->aggs[a].as<double>();
@@ -679,7 +687,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
           long long est_new = 0;
           GbDirectOut dout{};
           if (passes.size() == 1 && !direct_off) {
-            direct_cap = std::min<long long>(n, 2 * est + (1 << 20));
+            direct_cap = std::min<long long>(n, 4 * est + (1 << 20));      // heavy-tailed tuples: the estimate is often low; partitions that find no room flush to the table
             PDRS_TRY(alloc_outputs((size_t)direct_cap));
             PDRS_TRY(direct_cur.alloc(c, 64, true));
             fp.gt = gp.gt;
@@ -804,7 +812,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 12, direct_cur.p, 8, cudaMemcpyDeviceToHost, c->stream));
     PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
     direct_groups = c->pinned_scalars[12];
-    if (direct_groups + Gt > direct_cap) return pdrs_fail(c, PDRS_ERR_OOM, "groupby: %lld groups exceed the %lld the result was sized for (cardinality estimate %lld); set groups_hint", (long long)(direct_groups + Gt), direct_cap, est);
+    if (direct_groups + Gt > direct_cap) PDRS_TRY(alloc_outputs((size_t)(direct_groups + Gt), (size_t)direct_groups));      // the table holds more groups than expected: larger arrays, the direct groups move over
     PDRS_CUDA(c, cudaMemcpyAsync(tm.t.counters + CNT_OUT, direct_cur.p, 8, cudaMemcpyDeviceToDevice, c->stream));
   } else {
     PDRS_TRY(alloc_outputs((size_t)std::max<int64_t>(Gt, 1)));
