@@ -206,7 +206,7 @@ struct GpDirect {
   int dv;                   // index of the value column this pass aggregates
 };
 constexpr int GH_NT = 512, GH_ITEMS = 4, GH_TILE = GH_NT * GH_ITEMS;
-static size_t gh_smem(int S) { return (size_t)(S + 1) * 64 + 64; }
+static size_t gh_smem(int S, bool is_int) { return (size_t)(S + 1) * (is_int ? 64 : 56) + 64; }     // keys, pivot, S1, S2, min, max (+ isum) + rows, n
 
 template <typename VT, int FLAGS>
 __global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p, const GpDirect d, const u64* __restrict__ part_cnt, int log_s) {
@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p,
   double* aS2 = aS1 + S1n;
   u64* amn = reinterpret_cast<u64*>(aS2 + S1n);
   u64* amx = amn + S1n;
-  u64* aisum = amx + S1n;
-  uint32_t* arows = reinterpret_cast<uint32_t*>(aisum + S1n);
+  u64* aisum = amx + S1n;                                         // Int64 values only (the plane does not exist otherwise)
+  uint32_t* arows = reinterpret_cast<uint32_t*>(IS_INT ? aisum + S1n : aisum);
   uint32_t* an = arows + S1n;
   __shared__ long long sh_q;
   __shared__ uint32_t sh_groups, sh_spilled, sh_out;
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p,
     if (q >= p.part_n) break;
     const long long cnt = min((long long)__ldg(part_cnt + q), p.part_cap);
     if (cnt == 0) { __syncthreads(); continue; }
-    for (int i = tid; i < S1n; i += GH_NT) { keys[i] = EMPTY; piv[i] = 0; aS1[i] = 0.0; aS2[i] = 0.0; amn[i] = 0; amx[i] = 0; aisum[i] = 0; arows[i] = 0; an[i] = 0; }
+    for (int i = tid; i < S1n; i += GH_NT) { keys[i] = EMPTY; piv[i] = 0; aS1[i] = 0.0; aS2[i] = 0.0; amn[i] = 0; amx[i] = 0; if (IS_INT) aisum[i] = 0; arows[i] = 0; an[i] = 0; }
     if (tid == 0) { sh_groups = 0; sh_spilled = 0; sh_out = 0; }
     __syncthreads();
     const long long base = q * p.part_cap;
@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p,
       u64 rows = 0, kw = 0;
       if (have) {
         rows = arows[s]; kw = s == S ? EMPTY : keys[s];
-        st.n = an[s]; st.S1 = aS1[s]; st.S2 = aS2[s]; st.mnc = amn[s]; st.mxo = amx[s]; st.isum = aisum[s];
+        st.n = an[s]; st.S1 = aS1[s]; st.S2 = aS2[s]; st.mnc = amn[s]; st.mxo = amx[s]; st.isum = IS_INT ? aisum[s] : 0ull;
         st.pivotx = piv[s] ? (piv[s] ^ GB_PIV_X) : 0ull;
       }
       if (obase != ~0ull) {
@@ -352,12 +352,28 @@ __global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p,
 
 template <typename VT, int FLAGS>
 static cudaError_t gh_launch(const GbParams& p, const GpDirect& d, const u64* cnt, int log_s, int ctas, cudaStream_t s) {
-  const size_t smem = gh_smem(1 << log_s);
+  const size_t smem = gh_smem(1 << log_s, ValTraits<VT>::is_int);
   auto k = gp_hash_agg_kernel<VT, FLAGS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   k<<<ctas, GH_NT, smem, s>>>(p, d, cnt, log_s);
   return cudaGetLastError();
+}
+
+// Cardinality from the first level-1 bucket, exact for any key distribution: the bucket holds ALL rows of 1 / nb1 of the hash
+// space; the rows whose NEXT `sub_bits` hash bits are zero are all rows of 1 / (nb1 * 2^sub_bits) of it.  Their distinct keys are
+// counted exactly in a scratch table (the whole bucket is scanned - sequential, cheap - but only the slice is inserted).
+__global__ void gp_slice_distinct_kernel(const u64* __restrict__ keys, long long n, int used_bits, int sub_bits, GTable t) {
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += (long long)gridDim.x * blockDim.x) {
+    u64 w[1] = {0ull};
+    bool in = false;
+    if (i < n) {
+      w[0] = __ldcs(keys + i);
+      in = sub_bits == 0 || ((gp_hash32(w[0]) << used_bits) >> (32 - sub_bits)) == 0u;
+    }
+    g_find_or_insert<1>(t, w, in);
+  }
 }
 
 // which partitions are complete: hash partitions none of whose rows (nor of its level-1 bucket's rows) went to a side area.
@@ -400,9 +416,13 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
     if (gp.ks.c[k].nulls || (gp.ks.c[k].dtype == PDRS_DICT_U32 && gp.ks.c[k].null_alias >= 0)) return PDRS_ERR_UNSUPPORTED;   // NULL keys: other paths
   // partitions of <= ~600 expected groups (the tile-sort kernel holds 1023 ids with 512 threads x 2 groups).  Few
   // partitions are fine: the aggregation kernel cuts every partition into chunks of tiles, one work item each.
+  // Few rows per group (and room to write groups straight to the result): the shared-memory hash kernel aggregates the
+  // partitions - its table holds up to 3584 groups (f64 values; 1792 for Int64 values) and a partition may be smaller than a tile.
+  const bool use_hash = direct && c->opt_part_hash != 2 && (c->opt_part_hash == 1 || n / std::max<long long>(est_groups, 1) < 64);
+  const long long hash_groups_max = is_int ? 1400 : 2800;
   int bits = 1;
   while (bits < 16 && (est_groups >> bits) > 600) bits++;
-  if ((est_groups >> bits) > 700 || (n >> bits) < T / 2) return PDRS_ERR_UNSUPPORTED;
+  if ((est_groups >> bits) > (use_hash ? hash_groups_max : 700) || (n >> bits) < (use_hash ? 1024 : T / 2)) return PDRS_ERR_UNSUPPORTED;
   const int bits1 = bits <= 8 ? bits : (bits + 1) / 2, bits2 = bits - bits1;
   const long long nb1 = 1ll << bits1, nparts = 1ll << bits;
   // a bucket holds whole groups: with m groups per bucket its size varies by ~1/sqrt(m) -> 6 sigma of slack
@@ -479,8 +499,28 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   if (est_refined && nb1 >= 4) {
     const long long cnt0 = std::min<long long>((long long)c->pinned_scalars[9], cap1);
     long long est0 = 0;
-    PDRS_TRY(gb_estimate_groups_i64(c, k1.as<u64>(), cnt0, 1 << 20, &est0));
-    const long long refined = std::min<long long>(est0 * nb1, n);
+    // (the uniform-model inversion of a row sample is far too low for Zipf tuples: count a hash slice of the bucket exactly)
+    int sub_bits = 0;
+    while (sub_bits < 10 && (cnt0 >> sub_bits) > (1ll << 21)) sub_bits++;
+    {
+      DevBuf sh, sc;
+      long long slots = 1024;
+      while (slots < 4 * ((cnt0 >> sub_bits) + 1024)) slots <<= 1;
+      PDRS_TRY(sh.alloc(c, (size_t)(slots + 1) * sizeof(GHdr), true));
+      PDRS_TRY(sc.alloc(c, CNT_N * 8, true));
+      GTable st{};
+      st.hdr = sh.as<GHdr>(); st.mask = (u64)slots - 1; st.slots = slots; st.counters = sc.as<u64>();
+      int lg = 0;
+      while ((1ll << lg) < slots) lg++;
+      st.shift = 64 - lg;
+      if (cnt0 > 0) gp_slice_distinct_kernel<<<pdrs_grid_for(c, cnt0, 256), 256, 0, c->stream>>>(k1.as<u64>(), cnt0, bits1, sub_bits, st);
+      c->stats.kernel_launches++;
+      PDRS_CUDA(c, cudaGetLastError());
+      PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 9, st.counters + CNT_NGROUPS, 8, cudaMemcpyDeviceToHost, c->stream));
+      PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+      est0 = (long long)c->pinned_scalars[9] << sub_bits;
+    }
+    const long long refined = std::min<long long>(est0 * nb1 + est0 * nb1 / 32, n);
     if (refined > est_groups + est_groups / 2) { *est_refined = refined; return PDRS_ERR_UNSUPPORTED; }
   }
   const u64 *pk = k1.as<u64>(), *pv = v1.as<u64>(), *pc = nside ? pcnt.as<u64>() : cur1;
@@ -548,7 +588,6 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   // straight to the result.  Chosen when a group has few rows (the tile-sort kernel pays for every new key of a partition's
   // first tile); the tile-sort kernel then only sees the incomplete partitions and the side-area chunks.
   DevBuf split;
-  const bool use_hash = direct && c->opt_part_hash != 2 && (c->opt_part_hash == 1 || n / std::max<long long>(est_groups, 1) < 64);
   if (direct) {
     PDRS_TRY(split.alloc(c, (size_t)(2 * nparts_all + 2) * 8));
     u64* cnt_hash = split.as<u64>();
@@ -559,7 +598,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       GpDirect gd{};
       gd.fin = *direct->fin; gd.cap = direct->cap; gd.cursor = direct->cursor; gd.dv = direct->dv;
       int log_s = 8;
-      while (log_s < 11 && (1ll << log_s) < 3 * std::max<long long>(1, est_groups >> bits)) log_s++;
+      while (log_s < (is_int ? 11 : 12) && (1ll << log_s) < 3 * std::max<long long>(1, est_groups >> bits)) log_s++;
       const int hctas = (int)std::min<long long>(c->sm_count, nparts);
       GbParams hp = tp;
       cudaError_t e;
