@@ -20,6 +20,8 @@
 // caller fall back (tile-sort over the columns with a spill buffer, or the global-table path).
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <vector>
 
 #include "groupby_kernels.cuh"
 #include "gb_final.cuh"
@@ -408,6 +410,18 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   *dirty = false;
   *skewed = false;
   if (est_refined) *est_refined = 0;
+  // timing = 2: CUDA-event time of every phase on stderr
+  struct Marks {
+    pdrs_ctx* c; std::vector<std::pair<const char*, cudaEvent_t>> ev;
+    void operator()(const char* name) { if (c->opt_timing < 2) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, c->stream); ev.push_back({name, e}); }
+    ~Marks() {
+      if (ev.empty()) return;
+      cudaStreamSynchronize(c->stream);
+      for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1].second, ev[i].second); fprintf(stderr, "[pdrs groupby part] %-28s %8.3f ms\n", ev[i].first, ms); }
+      for (auto& e : ev) cudaEventDestroy(e.second);
+    }
+  } mark{c, {}};
+  mark("start");
   const long long n = gp.n;
   const long long T = gb_tsort_tile_rows();
   const bool generic = !(gp.ks.nkeys == 1 && gp.ks.c[0].dtype == PDRS_I64);
@@ -486,6 +500,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
   if (nside) { gp_counts_kernel<<<(int)((nb1 + nside + 255) / 256), 256, 0, c->stream>>>(cur1, sidep, (int)nb1, cap1, (int)nside, pcnt.as<u64>()); c->stats.kernel_launches++; }
   c->stats.kernel_launches++;
+  mark("level-1 partition");
   long long side_rows1 = 0;         // rows level 1 parked in its side area
   if ((est_refined && nb1 >= 4) || (bits2 && nside)) {
     PDRS_CUDA(c, cudaGetLastError());
@@ -497,7 +512,16 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
     if (nside) side_rows1 = std::min<long long>((long long)c->pinned_scalars[10], side_cap);
   }
   if (est_refined && nb1 >= 4) {
-    const long long cnt0 = std::min<long long>((long long)c->pinned_scalars[9], cap1);
+    // Not bucket 0: the packed tuple of all-minimum parts is the word 0, hash(0) = 0, and under skew that is the HOTTEST key - its
+    // bucket overflows into the side area and shows only part of its rows.  The bucket with the fewest rows has no hot key
+    // and holds all of its rows.
+    std::vector<u64> hcur((size_t)nb1);
+    PDRS_CUDA(c, cudaMemcpyAsync(hcur.data(), cur1, (size_t)nb1 * 8, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    long long qmin = 0;
+    for (long long q = 1; q < nb1; q++) if (hcur[q] < hcur[qmin]) qmin = q;
+    const long long cnt0 = std::min<long long>((long long)hcur[qmin], cap1);
+    const u64* kq = k1.as<u64>() + qmin * cap1;
     long long est0 = 0;
     // (the uniform-model inversion of a row sample is far too low for Zipf tuples: count a hash slice of the bucket exactly)
     int sub_bits = 0;
@@ -513,13 +537,14 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       int lg = 0;
       while ((1ll << lg) < slots) lg++;
       st.shift = 64 - lg;
-      if (cnt0 > 0) gp_slice_distinct_kernel<<<pdrs_grid_for(c, cnt0, 256), 256, 0, c->stream>>>(k1.as<u64>(), cnt0, bits1, sub_bits, st);
+      if (cnt0 > 0) gp_slice_distinct_kernel<<<pdrs_grid_for(c, cnt0, 256), 256, 0, c->stream>>>(kq, cnt0, bits1, sub_bits, st);
       c->stats.kernel_launches++;
       PDRS_CUDA(c, cudaGetLastError());
       PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 9, st.counters + CNT_NGROUPS, 8, cudaMemcpyDeviceToHost, c->stream));
       PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
       est0 = (long long)c->pinned_scalars[9] << sub_bits;
     }
+    mark("cardinality from one bucket");
     const long long refined = std::min<long long>(est0 * nb1 + est0 * nb1 / 32, n);
     if (refined > est_groups + est_groups / 2) { *est_refined = refined; return PDRS_ERR_UNSUPPORTED; }
   }
@@ -561,6 +586,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
     pk = k2.as<u64>(); pv = v2.as<u64>(); pc = nside2 ? pcnt2.as<u64>() : cur2; pcap = cap2;
     pf = has_flags ? f2.as<uint8_t>() : nullptr;
   }
+  mark("level-2 partition");
   PDRS_CUDA(c, cudaGetLastError());
   PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, ovf, 8, cudaMemcpyDeviceToHost, c->stream));
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -607,10 +633,12 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       PDRS_CUDA(c, e);
       c->stats.kernel_launches++;
       tp.part_cnt = cnt_ts;
+      mark("hash aggregation (direct)");
     }
   }
   PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts_all * tp.part_cpp), ts_smem, c->stream));
   c->stats.kernel_launches++;
+  mark("tile-sort aggregation");
   if (c->opt_timing) {
     PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
     PDRS_CUDA(c, cudaEventSynchronize(c->ev_b));

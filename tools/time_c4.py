@@ -45,11 +45,13 @@ for name, keys, bpr in (("dictionary key", [col(pb.DICT_U32, k3)], 12.0), ("(i32
     for opt in ((0, 1), (2, 1)) if len(sys.argv) > 2 else ((0, 1),):
         ctx.set_option("part_hash", opt[0])
         best = 1e9
-        for _ in range(3):
+        for rep in range(3):
+            ctx.set_option("timing", 2 if rep == 2 else 1)
             ctx.timer_begin()
             r = ctx.groupby_agg(keys, [col(pb.F64, v)], ALL6)
             G = r.n_groups
             r.close()
             best = min(best, ctx.timer_end())
+        ctx.set_option("timing", 1)
         st = ctx.stats()
         print(f"{name:24s} part_hash={opt[0]}: {best:8.2f} ms  kernels {st['main_kernel_ms']:8.2f} ms  {G} groups  algo {st['groupby_algo_used']} retries {st['retries']} est {st['est_groups']}  = {bpr * n / best / 1e6 / 6504.1 * 100:.2f}% of roofline", flush=True)
