@@ -211,7 +211,7 @@ constexpr int GH_NT = 512, GH_ITEMS = 4, GH_TILE = GH_NT * GH_ITEMS;
 static size_t gh_smem(int S, bool is_int) { return (size_t)(S + 1) * (is_int ? 64 : 56) + 64; }     // keys, pivot, S1, S2, min, max (+ isum) + rows, n
 
 template <typename VT, int FLAGS>
-__global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p, const GpDirect d, const u64* __restrict__ part_cnt, int log_s) {
+__global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p, const GpDirect d, const u64* __restrict__ part_cnt, const uint8_t* __restrict__ part_complete, int log_s) {
   using T = ValTraits<VT>;
   constexpr bool IS_INT = T::is_int, ALL = FLAGS == GB_ALL;
   constexpr u64 EMPTY = ~0ull;
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p,
     const long long cnt = min((long long)__ldg(part_cnt + q), p.part_cap);
     if (cnt == 0) { __syncthreads(); continue; }
     for (int i = tid; i < S1n; i += GH_NT) { keys[i] = EMPTY; piv[i] = 0; aS1[i] = 0.0; aS2[i] = 0.0; amn[i] = 0; amx[i] = 0; if (IS_INT) aisum[i] = 0; arows[i] = 0; an[i] = 0; }
-    if (tid == 0) { sh_groups = 0; sh_spilled = 0; sh_out = 0; }
+    if (tid == 0) { sh_groups = 0; sh_spilled = part_complete[q] ? 0u : 1u; sh_out = 0; }      // incomplete partition: its groups go through the global table
     __syncthreads();
     const long long base = q * p.part_cap;
     for (long long t0 = 0; t0 < cnt; t0 += GH_TILE) {
@@ -353,12 +353,12 @@ __global__ void __launch_bounds__(GH_NT, 1) gp_hash_agg_kernel(const GbParams p,
 }
 
 template <typename VT, int FLAGS>
-static cudaError_t gh_launch(const GbParams& p, const GpDirect& d, const u64* cnt, int log_s, int ctas, cudaStream_t s) {
+static cudaError_t gh_launch(const GbParams& p, const GpDirect& d, const u64* cnt, const uint8_t* complete, int log_s, int ctas, cudaStream_t s) {
   const size_t smem = gh_smem(1 << log_s, ValTraits<VT>::is_int);
   auto k = gp_hash_agg_kernel<VT, FLAGS>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<ctas, GH_NT, smem, s>>>(p, d, cnt, log_s);
+  k<<<ctas, GH_NT, smem, s>>>(p, d, cnt, complete, log_s);
   return cudaGetLastError();
 }
 
@@ -379,18 +379,21 @@ __global__ void gp_slice_distinct_kernel(const u64* __restrict__ keys, long long
 }
 
 // which partitions are complete: hash partitions none of whose rows (nor of its level-1 bucket's rows) went to a side area.
-// out_hash[q] = rows for the hash-aggregation kernel, out_ts[q] = rows for the tile-sort kernel (incomplete partitions and the
-// chunks of the side area); cnt = the clamped counts (gp_counts_kernel) or the raw cursors when there is no side area.
+// out_hash[q] = rows for the hash-aggregation kernel (complete partitions: groups straight to the result; incomplete ones: flushed
+// to the global table), out_ts[q] = rows for the tile-sort kernel (the chunks of the side area: hot keys); cnt = the clamped
+// counts (gp_counts_kernel) or the raw cursors when there is no side area.
 __global__ void gp_split_counts_kernel(const u64* __restrict__ cnt, const u64* __restrict__ cur1, long long cap1, int bits2, const u64* __restrict__ cur2, long long cap2,
-                                       int nparts, int nall, int use_hash, u64* __restrict__ out_hash, u64* __restrict__ out_ts) {
+                                       int nparts, int nall, int use_hash, u64* __restrict__ out_hash, u64* __restrict__ out_ts, uint8_t* __restrict__ out_complete) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= nall) return;
   const u64 c = cnt[q];
-  bool complete = use_hash && q < nparts;
+  const bool hashed = use_hash && q < nparts;            // every hash partition goes to the hash kernel; the side-area chunks to the tile-sort kernel
+  bool complete = hashed;
   if (complete && cur2) complete = cur2[q] <= (u64)cap2 && cur1[q >> bits2] <= (u64)cap1;
   else if (complete) complete = cur1[q] <= (u64)cap1;
-  out_hash[q] = complete ? c : 0ull;
-  out_ts[q] = complete ? 0ull : c;
+  out_hash[q] = hashed ? c : 0ull;
+  out_ts[q] = hashed ? 0ull : c;
+  out_complete[q] = complete ? 1 : 0;
 }
 
 long long round_up(long long x, long long m) { return (x + m - 1) / m * m; }
@@ -615,10 +618,11 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   // first tile); the tile-sort kernel then only sees the incomplete partitions and the side-area chunks.
   DevBuf split;
   if (direct) {
-    PDRS_TRY(split.alloc(c, (size_t)(2 * nparts_all + 2) * 8));
+    PDRS_TRY(split.alloc(c, (size_t)(2 * nparts_all + 2) * 8 + (size_t)nparts_all + 64));
     u64* cnt_hash = split.as<u64>();
     u64* cnt_ts = cnt_hash + nparts_all;
-    gp_split_counts_kernel<<<(int)((nparts_all + 255) / 256), 256, 0, c->stream>>>(pc, cur1, cap1, bits2, bits2 ? cur2 : nullptr, cap2, (int)nparts, (int)nparts_all, use_hash ? 1 : 0, cnt_hash, cnt_ts);
+    uint8_t* complete = reinterpret_cast<uint8_t*>(cnt_ts + nparts_all + 2);
+    gp_split_counts_kernel<<<(int)((nparts_all + 255) / 256), 256, 0, c->stream>>>(pc, cur1, cap1, bits2, bits2 ? cur2 : nullptr, cap2, (int)nparts, (int)nparts_all, use_hash ? 1 : 0, cnt_hash, cnt_ts, complete);
     c->stats.kernel_launches++;
     if (use_hash) {
       GpDirect gd{};
@@ -628,8 +632,8 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       const int hctas = (int)std::min<long long>(c->sm_count, nparts);
       GbParams hp = tp;
       cudaError_t e;
-      if (!is_int) e = flags == GB_SUM ? gh_launch<double, GB_SUM>(hp, gd, cnt_hash, log_s, hctas, c->stream) : gh_launch<double, GB_ALL>(hp, gd, cnt_hash, log_s, hctas, c->stream);
-      else e = flags == GB_SUM ? gh_launch<long long, GB_SUM>(hp, gd, cnt_hash, log_s, hctas, c->stream) : gh_launch<long long, GB_ALL>(hp, gd, cnt_hash, log_s, hctas, c->stream);
+      if (!is_int) e = flags == GB_SUM ? gh_launch<double, GB_SUM>(hp, gd, cnt_hash, complete, log_s, hctas, c->stream) : gh_launch<double, GB_ALL>(hp, gd, cnt_hash, complete, log_s, hctas, c->stream);
+      else e = flags == GB_SUM ? gh_launch<long long, GB_SUM>(hp, gd, cnt_hash, complete, log_s, hctas, c->stream) : gh_launch<long long, GB_ALL>(hp, gd, cnt_hash, complete, log_s, hctas, c->stream);
       PDRS_CUDA(c, e);
       c->stats.kernel_launches++;
       tp.part_cnt = cnt_ts;

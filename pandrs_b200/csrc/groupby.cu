@@ -202,6 +202,24 @@ static int32_t default_null_keys(pdrs_ctx* c, ColView* v) {
   return PDRS_OK;
 }
 
+// Exact cardinality for ANY key distribution from one scan of the key columns: the keys whose hash falls into 1 / 2^slice_bits of
+// the hash space are counted exactly in a scratch table (every row is read, only the slice is inserted).  The row sample above,
+// inverted under a uniform model, underestimates heavy-tailed key tuples (Zipf) several times over - and a wrong estimate costs
+// a whole partition pass.
+__global__ void gb_slice_distinct_kernel(const KeySpec ks, long long n, int slice_bits, GTable t) {
+  const int lane = threadIdx.x & 31;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i - lane < n; i += (long long)gridDim.x * blockDim.x) {
+    u64 w[1] = {0ull};
+    bool in = false;
+    if (i < n) {
+      in = !load_key_inline<1>(ks, i, w);
+      const uint32_t lo = (uint32_t)w[0] ^ (uint32_t)(w[0] >> 32);
+      in = in && (slice_bits == 0 || ((lo * 0x85EBCA6Bu) >> (32 - slice_bits)) == 0u);
+    }
+    g_find_or_insert<1>(t, w, in);
+  }
+}
+
 // A typed predicate as a Boolean bitmask (general paths; the few-groups kernel evaluates it inside its scan): one 32-bit
 // word per thread; ANDed with an optional Boolean filter column (value & ~null).
 __global__ void gb_pred_mask_kernel(const u64* __restrict__ col, const uint8_t* __restrict__ cnull, int is_f64, int op, long long ival, double fval,
@@ -496,6 +514,23 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     }
   }
   if (est < 1) est = 1;
+  bool est_exact = false;
+  if (variant == 1 && ks.nwords == 1 && est > 2047 && n >= (1ll << 22) && c->opts.groups_hint == 0 && c->opt_part != 0 && c->opts.groupby_algo == PDRS_GB_AUTO) {
+    // packed multi-column / dictionary keys headed for the partitioned path: these are the heavy-tailed ones in practice
+    int sb = 0;
+    while ((n >> sb) > (1ll << 21)) sb++;
+    TableMem stm;
+    PDRS_TRY(alloc_table(c, pow2ceil(4 * ((n >> sb) + 1024)), 1, &stm));
+    gb_slice_distinct_kernel<<<pdrs_grid_for(c, n, 256), 256, 0, c->stream>>>(ks, n, sb, stm.t);
+    c->stats.kernel_launches++;
+    PDRS_CUDA(c, cudaGetLastError());
+    u64 cn2[CNT_N + 1];
+    PDRS_TRY(read_counters(c, stm, cn2));
+    const long long exact = (long long)cn2[CNT_NGROUPS] << sb;
+    est = std::max<long long>(1, exact + exact / 32);
+    c->stats.est_groups = est;
+    est_exact = true;
+  }
 
   // ---- geometry of the shared-memory kernel per pass; fall back to the global table when it does not fit
   auto shared_geometry = [&](const PassPlan& pp, GbParams* gp, GbCfg* cfg, size_t* smem) -> bool {
@@ -606,7 +641,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   u64 cn[CNT_N + 1] = {0};
   bool radix_used = false, restart = false;
   bool part_ok = c->opt_part != 0 && c->opts.groupby_algo == PDRS_GB_AUTO;
-  bool reestimated = false;      // the partitioned path may correct the sampled cardinality estimate once (gb_part_pass)
+  bool reestimated = est_exact;  // the partitioned path may correct the sampled cardinality estimate once (gb_part_pass)
   bool ts_skew = false;          // the tile-sort kernel runs as the skew fallback: its spills go to a side buffer + a second pass
   bool few_off = false;          // the few-groups kernel met too many keys the sample had not seen
   DevBuf pred_mask;
