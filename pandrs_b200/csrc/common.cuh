@@ -57,6 +57,7 @@ struct pdrs_ctx {
   int64_t opt_tsort_team = 0;          // 0 = auto (estimated groups < 500), 1 = always, 2 = never
   int64_t opt_tsort_threads = 0;       // 0 = auto, else 512 / 1024 threads per CTA
   int64_t opt_empty_string_id = 0xFFFFFFFFll;   // compat_filter_nulls: the dictionary id NULL string keys turn into (the pool id of ""; default = the id pdrs_gather fills in for "")
+  int64_t opt_part_hot = 1;            // partitioned groupby: rows of the sample's hot keys bypass the hash partitions (skewed keys)
   int64_t opt_part_direct = 1;         // partitioned groupby: complete partitions write their groups straight to the result
   int64_t opt_part_hash = 0;           // ... aggregated by the shared-memory hash kernel: 0 = auto (few rows per group), 1 = always, 2 = never (tile sort)
   int64_t opt_few = 1;                 // allow the few-groups multi-column kernel (gb_few.cu)

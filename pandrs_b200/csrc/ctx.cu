@@ -141,6 +141,7 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "compat_empty_string_id")) c->opt_empty_string_id = value;
   else if (!strcmp(name, "few")) c->opt_few = value;
   else if (!strcmp(name, "part_direct")) c->opt_part_direct = value;
+  else if (!strcmp(name, "part_hot")) c->opt_part_hot = value;
   else if (!strcmp(name, "part_hash")) c->opt_part_hash = value;
   else return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown option '%s'", name);
   return PDRS_OK;

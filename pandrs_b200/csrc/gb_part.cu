@@ -50,6 +50,8 @@ struct GpIn {
   const u64* pkeys; const u64* pvals; const uint8_t* pflags; const u64* pcnt; long long pcap;
   // level 1, GENERIC: any key tuple that packs into one 64-bit word (dictionary ids, i32, bool and pairs of them, no NULLs)
   KeySpec ks;
+  // level 1: hot keys (open-addressing set, all ones = empty) whose rows go straight to the side area
+  const u64* hot_tab; int hot_log_slots;
 };
 
 template <bool FROM_COLS, bool GENERIC = false>
@@ -59,8 +61,12 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
   extern __shared__ __align__(16) unsigned char gsm[];
   ulonglong2* st_kv = reinterpret_cast<ulonglong2*>(gsm);      // [GP_TILE] staged (key, value)
   uint32_t* st_dst = reinterpret_cast<uint32_t*>(st_kv + GP_TILE);   // [GP_TILE] output position of the staged row (< 2^31), bit 31 = value is NULL
-  uint32_t* H = st_dst + GP_TILE;                         // [256 + 32] bucket counts of the tile
-  uint2* HD = reinterpret_cast<uint2*>(H + 288);          // [256] {offset of the bucket in the staging area, output position of its first row}
+  uint32_t* H = st_dst + GP_TILE;                         // [256 + 32] bucket counts of the tile; entry nb = the rows of hot keys
+  uint2* HD = reinterpret_cast<uint2*>(H + 288);          // [288] {offset of the bucket in the staging area, output position of its first row}
+  u64* hot = reinterpret_cast<u64*>(HD + 288);            // [2^hot_log_slots] hot-key set (level 1 only)
+  const bool use_hot = FROM_COLS && in.hot_tab != nullptr && side != nullptr;
+  const int hot_mask = (1 << in.hot_log_slots) - 1;
+  if (use_hot) { for (int i = threadIdx.x; i <= hot_mask; i += GP_NT) hot[i] = in.hot_tab[i]; }
   __shared__ uint32_t sh_total;
   __shared__ uint32_t wsum[GP_NT / 32];
   const int nb = 1 << local_bits;
@@ -117,18 +123,25 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
         if ((vn >> lane) & 1u) { if (in.compat_nulls) val[j] = 0; else vnullmask |= 1u << j; }
       } else if (fl[j] & 1u) vnullmask |= 1u << j;
       if (!live) continue;
-      const uint32_t b = (gp_hash32(key[j]) >> hash_shr) & lmask;
+      uint32_t b = (gp_hash32(key[j]) >> hash_shr) & lmask;
+      if (use_hot) {        // a hot key's rows bypass the hash buckets (they would overflow one): virtual bucket nb = the side area
+        uint32_t hs = gb_hot_slot(key[j], in.hot_log_slots);
+        for (;;) { const u64 hk = hot[hs]; if (hk == key[j]) { b = (uint32_t)nb; break; } if (hk == ~0ull) break; hs = (hs + 1) & (uint32_t)hot_mask; }
+      }
       br[j] = (b << 16) | atomicAdd(&H[b], 1u);
     }
     __syncthreads();
     {   // exclusive scan of the bucket counts (thread b owns bucket b) + one global reservation per bucket
-      const uint32_t c = tid < nb ? H[tid] : 0u;
+      const uint32_t c = tid <= nb ? H[tid] : 0u;            // (H[nb] = rows of hot keys, 0 when there are none)
       uint32_t incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, d); if (lane >= d) incl += o; }
       if (lane == 31) wsum[warp] = incl;
       uint32_t g = 0xFFFFFFFFu;
-      if (c) {
+      if (c && tid == nb) {      // rows of hot keys: one reservation in the side area
+        const u64 at2 = atomicAdd(&side[0], (u64)c);
+        if (at2 + c <= (u64)side_cap) g = (uint32_t)((u64)side_base + at2); else atomicAdd(overflow, 1ull);
+      } else if (c) {
         // output bucket: level 1 = the local bucket; level 2 = (level-1 bucket of this CTA's rows) * 2^bits + local bucket
         const u64 q = FROM_COLS ? (u64)tid : (((u64)blockIdx.y << local_bits) | (u64)tid);
         const u64 at = atomicAdd(&cursor[q], (u64)c);
@@ -151,7 +164,7 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
       for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, ws, d); if (lane >= d) ws += o; }
       const uint32_t wprefix = __shfl_sync(0xFFFFFFFFu, ws, (warp + 31) & 31);
       const uint32_t excl = (warp ? wprefix : 0u) + incl - c;
-      if (tid < 256) HD[tid] = make_uint2(excl, g);
+      if (tid < 288) HD[tid] = make_uint2(excl, g);
       if (tid == GP_NT - 1) sh_total = excl + c;
     }
     __syncthreads();
@@ -374,7 +387,7 @@ __global__ void gp_slice_distinct_kernel(const u64* __restrict__ keys, long long
       w[0] = __ldcs(keys + i);
       in = sub_bits == 0 || ((gp_hash32(w[0]) << used_bits) >> (32 - sub_bits)) == 0u;
     }
-    g_find_or_insert<1>(t, w, in);
+    if (__any_sync(0xFFFFFFFFu, in)) g_find_or_insert<1>(t, w, in);
   }
 }
 
@@ -457,7 +470,9 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   // anyway), and the whole area is aggregated as extra partitions of cap2 rows.
   long long nside = 0;
   if (c->opt_part_side != 0) {
-    nside = std::max<long long>(1, (n / 4 + cap1 - 1) / cap1);
+    long long side_rows = n / 4;
+    if (use_hash && gp.hot_tab) side_rows = std::max<long long>(side_rows, (long long)((double)n * std::min(0.95, (double)gp.hot_frac * 1.15 + 0.05)) + n / 16);
+    nside = std::max<long long>(1, (side_rows + cap1 - 1) / cap1);
     while (nside > 0 && (unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31)) nside--;
   }
   if ((unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31) || (unsigned long long)nparts * cap2 >= (1ull << 31)) return PDRS_ERR_UNSUPPORTED;   // 31-bit output positions
@@ -488,7 +503,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   }
   u64* sidep = nside ? side.as<u64>() : nullptr;
   const long long side_base = nb1 * cap1, side_cap = nside * cap1;
-  const size_t smem = (size_t)GP_TILE * 20 + (288 + 512) * 4;
+  const size_t smem = (size_t)GP_TILE * 20 + 288 * 4 + 288 * 8 + ((size_t)8 << GB_HOT_LOG_SLOTS);
   // the attribute is per device (several contexts / GPUs may live in one process): set it on every call
   PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -499,6 +514,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   in.fbits = gp.fbits; in.fnull = gp.fnull; in.n = n; in.compat_nulls = gp.compat_nulls;
   const int ctas1 = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + GP_TILE - 1) / GP_TILE));
   in.ks = gp.ks;
+  if (nside && use_hash) { in.hot_tab = gp.hot_tab; in.hot_log_slots = gp.hot_log_slots; }      // (hot rows land in the side area: one tile-sort pass over it)
   if (generic) gp_part_kernel<true, true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
   else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
   if (nside) { gp_counts_kernel<<<(int)((nb1 + nside + 255) / 256), 256, 0, c->stream>>>(cur1, sidep, (int)nb1, cap1, (int)nside, pcnt.as<u64>()); c->stats.kernel_launches++; }
@@ -592,7 +608,13 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   mark("level-2 partition");
   PDRS_CUDA(c, cudaGetLastError());
   PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 8, ovf, 8, cudaMemcpyDeviceToHost, c->stream));
+  // rows in the final side area (hot keys, runs of full buckets) and where it lies
+  const u64* side_cursor = bits2 ? (nside2 ? side2.as<u64>() : nullptr) : sidep;
+  const long long side_at = bits2 ? nparts * cap2 : side_base, side_room = bits2 ? nside2 * cap2 : side_cap;
+  c->pinned_scalars[13] = 0;
+  if (side_cursor) PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + 13, side_cursor, 8, cudaMemcpyDeviceToHost, c->stream));
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  const long long side_rows_final = std::min<long long>((long long)c->pinned_scalars[13], side_room);
   if (c->pinned_scalars[8] != 0) { *skewed = true; return PDRS_ERR_UNSUPPORTED; }      // skewed keys: a bucket overflowed its padded range
   if (bits2) { k1.release(); v1.release(); f1.release(); }                        // only the last level is read below
   GbParams tp = gp;
@@ -640,8 +662,25 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       mark("hash aggregation (direct)");
     }
   }
-  PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts_all * tp.part_cpp), ts_smem, c->stream));
-  c->stats.kernel_launches++;
+  if (use_hash) {
+    // the side area as ONE input of the tile-sort kernel: hot keys + the runs of buckets that filled up - few distinct keys, many
+    // rows each (its sweet spot); every CTA takes a run of tiles and adds one batch per group to the global table at its end
+    if (side_rows_final > 0) {
+      GbParams sp = tp;
+      sp.part_keys = pk + side_at; sp.part_vals = pv + side_at; sp.part_flags = pf ? pf + side_at : nullptr;
+      sp.part_cnt = side_cursor; sp.part_cap = side_room; sp.part_n = 1;
+      const long long tiles = (side_rows_final + T - 1) / T;
+      const int sctas = (int)std::min<long long>(c->sm_count, tiles);
+      sp.part_chunk_tiles = (int)((tiles + sctas - 1) / sctas);
+      sp.part_cpp = (int)((tiles + sp.part_chunk_tiles - 1) / sp.part_chunk_tiles);
+      sp.ts_team = 0;
+      PDRS_CUDA(c, gb_tsort_launch(sp, is_int, flags, ts_nt, ts_gpt, sctas, ts_smem, c->stream));
+      c->stats.kernel_launches++;
+    }
+  } else {
+    PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts_all * tp.part_cpp), ts_smem, c->stream));
+    c->stats.kernel_launches++;
+  }
   mark("tile-sort aggregation");
   if (c->opt_timing) {
     PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));

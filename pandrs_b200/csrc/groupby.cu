@@ -216,7 +216,17 @@ __global__ void gb_slice_distinct_kernel(const KeySpec ks, long long n, int slic
       const uint32_t lo = (uint32_t)w[0] ^ (uint32_t)(w[0] >> 32);
       in = in && (slice_bits == 0 || ((lo * 0x85EBCA6Bu) >> (32 - slice_bits)) == 0u);
     }
-    g_find_or_insert<1>(t, w, in);
+    if (__any_sync(0xFFFFFFFFu, in)) g_find_or_insert<1>(t, w, in);      // (its fail-fast check reads a hot counter line: not for warps with nothing to insert)
+  }
+}
+
+// keys of the cardinality sample that occurred at least `min_count` times: out[0] = how many, then (key word, occurrences) pairs
+__global__ void gb_hot_keys_kernel(const GHdr* __restrict__ hdr, long long slots, u64 min_count, int cap, u64* __restrict__ out) {
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += (long long)gridDim.x * blockDim.x) {
+    const u64 rw = hdr[s].rowsw;
+    if (!(rw & GB_FULL) || (rw & GB_CNT_MASK) < min_count) continue;
+    const u64 at = atomicAdd(&out[0], 1ull);
+    if (at < (u64)cap) { out[1 + 2 * at] = hdr[s].key0; out[2 + 2 * at] = rw & GB_CNT_MASK; }
   }
 }
 
@@ -470,6 +480,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   for (int k = 0; k < nkeys; k++) if (kv[k].nulls || (kv[k].dtype == PDRS_DICT_U32 && kv[k].null_alias >= 0)) few_eligible = false;
   for (auto& pp : passes) if (pp.flags != GB_SUM) few_eligible = false;
   std::vector<u64> few_keys;
+  DevBuf hot_dev;
 
   // ---- cardinality estimate
   long long est = c->opts.groups_hint > 0 ? c->opts.groups_hint : 0;
@@ -506,6 +517,37 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
       PDRS_CUDA(c, cudaMemcpyAsync(hk, kb.p, sizeof(hk), cudaMemcpyDeviceToHost, c->stream));
       PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
       if (hk[0] >= 1 && hk[0] <= GF_MAXG) { few_keys.assign(hk + 1, hk + 1 + hk[0]); std::sort(few_keys.begin(), few_keys.end()); }
+    }
+    // hot keys of a skewed distribution (one-word keys, high cardinality): the partitioned path routes their rows around the
+    // hash partitions, so that no partition overflows and every partition's groups can be written straight to the result
+    if (ks.nwords == 1 && est > 2047 && s_rows < n && c->opt_part != 0 && c->opt_part_hot != 0) {
+      const int HOTCAP = 4096;
+      DevBuf hb;
+      PDRS_TRY(hb.alloc(c, (size_t)(2 * HOTCAP + 2) * 8, true));
+      gb_hot_keys_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(stm.t.hdr, stm.t.slots, 8ull, HOTCAP, hb.as<u64>());
+      c->stats.kernel_launches++;
+      std::vector<u64> hh((size_t)2 * HOTCAP + 2);
+      PDRS_CUDA(c, cudaMemcpyAsync(hh.data(), hb.p, hh.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+      PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+      const size_t nh = (size_t)std::min<u64>(hh[0], HOTCAP);
+      std::vector<std::pair<u64, u64>> hk;      // (occurrences, key)
+      for (size_t i = 0; i < nh; i++) if (hh[1 + 2 * i] != ~0ull) hk.push_back({hh[2 + 2 * i], hh[1 + 2 * i]});
+      std::sort(hk.begin(), hk.end(), [](const std::pair<u64, u64>& a, const std::pair<u64, u64>& b) { return a.first > b.first; });
+      if (hk.size() > 900) hk.resize(900);
+      if (!hk.empty()) {
+        std::vector<u64> tab((size_t)1 << GB_HOT_LOG_SLOTS, ~0ull);
+        u64 hot_rows = 0;
+        for (auto& kc : hk) {
+          uint32_t sl = gb_hot_slot(kc.second, GB_HOT_LOG_SLOTS);
+          while (tab[sl] != ~0ull) sl = (sl + 1) & ((1u << GB_HOT_LOG_SLOTS) - 1u);
+          tab[sl] = kc.second;
+          hot_rows += kc.first;
+        }
+        PDRS_TRY(hot_dev.alloc(c, tab.size() * 8));
+        PDRS_CUDA(c, cudaMemcpyAsync(hot_dev.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+        base.hot_tab = hot_dev.as<u64>(); base.hot_log_slots = GB_HOT_LOG_SLOTS; base.hot_frac = (float)((double)hot_rows / s);
+      }
     }
     if (variant == 0 && cn[CNT_KMINC]) {     // small dense integer keys: direct-mapped group ids, no key table
       const long long kmin = (long long)(~cn[CNT_KMINC] ^ GB_SIGN), kmax = (long long)(cn[CNT_KMAX] ^ GB_SIGN);

@@ -96,7 +96,15 @@ struct GbParams {
   int ts_team;                      // tile-sort kernel: use the variant with the team-of-8 reduce
   int ts_mid;                       // ... longer than this (and up to ts_heavy) by a team of 8 lanes, shorter ones by their owner thread
   int ts_generic;                   // tile-sort kernel: keys are generic tuples packed into one word (not one Int64 column)
+  // Hot keys of a skewed distribution (the keys the cardinality sample met >= 8 times; at most 900): an open-addressing set of
+  // packed key words (all ones = empty).  The partitioned path routes their rows around the hash partitions (gb_part.cu).
+  const u64* hot_tab; int hot_log_slots; float hot_frac;      // hot_frac = share of the sampled rows that carry a hot key
 };
+#define GB_HOT_LOG_SLOTS 11
+__host__ __device__ __forceinline__ uint32_t gb_hot_slot(u64 k, int log_slots) {
+  const uint32_t lo = (uint32_t)k ^ (uint32_t)(k >> 32);
+  return (lo * 0x9E3779B1u + (uint32_t)(k >> 32) * 0x85EBCA6Bu) >> (32 - log_slots);
+}
 
 // ---------------------------------------------------------------- small device helpers
 // Loads of words that other threads publish (slot headers, keys, pivots): volatile, so that a spin on a
@@ -941,7 +949,8 @@ __global__ void gb_sample_kernel(const GbParams p, long long nblocks, long long 
       else knull = load_key_generic<NW>(p.ks, row, w);
     }
     if (KM == 0 && inb && !knull) { const u64 o = w[0] ^ GB_SIGN; kmax = max(kmax, o); kminc = max(kminc, ~o); }
-    g_find_or_insert<NW>(p.gt, w, inb && !knull);
+    const long long gs = g_find_or_insert<NW>(p.gt, w, inb && !knull);
+    if (inb && !knull && gs >= 0) atomicAdd(&p.gt.hdr[gs].rowsw, 1ull);      // occurrences in the sample: hot keys of a skewed distribution
   }
   if (KM == 0) {   // range of the sampled keys (dense-key fast path)
     for (int d = 16; d; d >>= 1) { kmax = max(kmax, __shfl_xor_sync(0xFFFFFFFFu, kmax, d)); kminc = max(kminc, __shfl_xor_sync(0xFFFFFFFFu, kminc, d)); }
