@@ -471,7 +471,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   long long nside = 0;
   if (c->opt_part_side != 0) {
     long long side_rows = n / 4;
-    if (use_hash && gp.hot_tab) side_rows = std::max<long long>(side_rows, (long long)((double)n * std::min(0.95, (double)gp.hot_frac * 1.15 + 0.05)) + n / 16);
+    if (gp.hot_tab) side_rows = std::max<long long>(side_rows, (long long)((double)n * std::min(0.95, (double)gp.hot_frac * 1.15 + 0.05)) + n / 16);
     nside = std::max<long long>(1, (side_rows + cap1 - 1) / cap1);
     while (nside > 0 && (unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31)) nside--;
   }
@@ -514,7 +514,8 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   in.fbits = gp.fbits; in.fnull = gp.fnull; in.n = n; in.compat_nulls = gp.compat_nulls;
   const int ctas1 = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 2, (n + GP_TILE - 1) / GP_TILE));
   in.ks = gp.ks;
-  if (nside && use_hash) { in.hot_tab = gp.hot_tab; in.hot_log_slots = gp.hot_log_slots; }      // (hot rows land in the side area: one tile-sort pass over it)
+  const bool side_single = nside && gp.hot_tab != nullptr;      // hot keys known: their rows go to the side area, which one tile-sort pass aggregates as a single input
+  if (side_single) { in.hot_tab = gp.hot_tab; in.hot_log_slots = gp.hot_log_slots; }
   if (generic) gp_part_kernel<true, true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
   else gp_part_kernel<true><<<ctas1, GP_NT, smem, c->stream>>>(in, 32 - bits1, bits1, cap1, cur1, k1.as<u64>(), v1.as<u64>(), has_flags ? f1.as<uint8_t>() : nullptr, ovf, sidep, side_base, side_cap);
   if (nside) { gp_counts_kernel<<<(int)((nb1 + nside + 255) / 256), 256, 0, c->stream>>>(cur1, sidep, (int)nb1, cap1, (int)nside, pcnt.as<u64>()); c->stats.kernel_launches++; }
@@ -662,7 +663,13 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       mark("hash aggregation (direct)");
     }
   }
-  if (use_hash) {
+  if (!use_hash && side_single) {      // tile-sort over the hash partitions only (their chunk counts), then the side area below
+    tp.part_n = (int)nparts;
+    PDRS_CUDA(c, gb_tsort_launch(tp, is_int, flags, ts_nt, ts_gpt, (int)std::min<long long>(c->sm_count, nparts * tp.part_cpp), ts_smem, c->stream));
+    c->stats.kernel_launches++;
+    mark("tile-sort aggregation (partitions)");
+  }
+  if (use_hash || side_single) {
     // the side area as ONE input of the tile-sort kernel: hot keys + the runs of buckets that filled up - few distinct keys, many
     // rows each (its sweet spot); every CTA takes a run of tiles and adds one batch per group to the global table at its end
     if (side_rows_final > 0) {

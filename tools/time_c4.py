@@ -40,8 +40,10 @@ def col(dtype, t):
 
 
 ALL6 = [(0, op) for op in (pb.SUM, pb.MEAN, pb.MIN, pb.MAX, pb.COUNT, pb.STD)]
-for name, keys, bpr in (("dictionary key", [col(pb.DICT_U32, k3)], 12.0), ("(i32, i64)", [col(pb.I32, k1), col(pb.I64, k2)], 20.0),
-                        ("(i32, i64, dictionary)", [col(pb.I32, k1), col(pb.I64, k2), col(pb.DICT_U32, k3)], 24.0)):
+ku = torch.randint(0, 24_000_000, (n,), device=dev, generator=g, dtype=torch.int64)
+torch.cuda.synchronize()
+for name, keys, bpr in (("uniform i64, 24M groups", [col(pb.I64, ku)], 16.0),("dictionary key", [col(pb.DICT_U32, k3)], 12.0), ("(i32, i64)", [col(pb.I32, k1), col(pb.I64, k2)], 20.0),
+                        ("(i32, i64, dictionary)", [col(pb.I32, k1), col(pb.I64, k2), col(pb.DICT_U32, k3)], 24.0))[0 if len(sys.argv) < 4 else 1:]:
     for opt in ((0, 1), (2, 1)) if len(sys.argv) > 2 else ((0, 1),):
         ctx.set_option("part_hash", opt[0])
         best = 1e9
@@ -54,4 +56,4 @@ for name, keys, bpr in (("dictionary key", [col(pb.DICT_U32, k3)], 12.0), ("(i32
             best = min(best, ctx.timer_end())
         ctx.set_option("timing", 1)
         st = ctx.stats()
-        print(f"{name:24s} part_hash={opt[0]}: {best:8.2f} ms  kernels {st['main_kernel_ms']:8.2f} ms  {G} groups  algo {st['groupby_algo_used']} retries {st['retries']} est {st['est_groups']}  = {bpr * n / best / 1e6 / 6504.1 * 100:.2f}% of roofline", flush=True)
+        print(f"{name:24s} part_hash={opt[0]}: {best:8.2f} ms  kernels {st['main_kernel_ms']:8.2f} ms  {G} groups  algo {st['groupby_algo_used']} retries {st['retries']} est {st['est_groups']}  = {bpr * n / best / 1e6 / 6504.1 * 100:.2f}% of roofline  spilled {st['spilled_rows']}", flush=True)
