@@ -51,7 +51,7 @@ struct GpIn {
   // level 1, GENERIC: any key tuple that packs into one 64-bit word (dictionary ids, i32, bool and pairs of them, no NULLs)
   KeySpec ks;
   // level 1: hot keys (open-addressing set, all ones = empty) whose rows go straight to the side area
-  const u64* hot_tab; int hot_log_slots;
+  const uint32_t* hot_tab; int hot_log_slots;
 };
 
 template <bool FROM_COLS, bool GENERIC = false>
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
   uint32_t* st_dst = reinterpret_cast<uint32_t*>(st_kv + GP_TILE);   // [GP_TILE] output position of the staged row (< 2^31), bit 31 = value is NULL
   uint32_t* H = st_dst + GP_TILE;                         // [256 + 32] bucket counts of the tile; entry nb = the rows of hot keys
   uint2* HD = reinterpret_cast<uint2*>(H + 288);          // [288] {offset of the bucket in the staging area, output position of its first row}
-  u64* hot = reinterpret_cast<u64*>(HD + 288);            // [2^hot_log_slots] hot-key set (level 1 only)
+  uint32_t* hot = reinterpret_cast<uint32_t*>(HD + 288);  // [2^hot_log_slots] tags of the hot keys (level 1 only)
   const bool use_hot = FROM_COLS && in.hot_tab != nullptr && side != nullptr;
   const int hot_mask = (1 << in.hot_log_slots) - 1;
   if (use_hot) { for (int i = threadIdx.x; i <= hot_mask; i += GP_NT) hot[i] = in.hot_tab[i]; }
@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(GP_NT, 2) gp_part_kernel(GpIn in, int hash_shr
       uint32_t b = (gp_hash32(key[j]) >> hash_shr) & lmask;
       if (use_hot) {        // a hot key's rows bypass the hash buckets (they would overflow one): virtual bucket nb = the side area
         uint32_t hs = gb_hot_slot(key[j], in.hot_log_slots);
-        for (;;) { const u64 hk = hot[hs]; if (hk == key[j]) { b = (uint32_t)nb; break; } if (hk == ~0ull) break; hs = (hs + 1) & (uint32_t)hot_mask; }
+        const uint32_t tag = gb_hot_tag(key[j]);
+        for (;;) { const uint32_t hk = hot[hs]; if (hk == tag) { b = (uint32_t)nb; break; } if (hk == 0u) break; hs = (hs + 1) & (uint32_t)hot_mask; }
       }
       br[j] = (b << 16) | atomicAdd(&H[b], 1u);
     }
@@ -448,7 +449,11 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   // partitions are fine: the aggregation kernel cuts every partition into chunks of tiles, one work item each.
   // Few rows per group (and room to write groups straight to the result): the shared-memory hash kernel aggregates the
   // partitions - its table holds up to 3584 groups (f64 values; 1792 for Int64 values) and a partition may be smaller than a tile.
-  const bool use_hash = direct && c->opt_part_hash != 2 && (c->opt_part_hash == 1 || n / std::max<long long>(est_groups, 1) < 64);
+  // Measured (profiles/c4_phases_r02.txt, 5e8 rows): uniform keys, 20 rows per group: hash kernel 14.2 ms vs tile sort 16.4 ms; Zipf
+  // tuples (moderately hot keys inside the partitions): its shared-memory atomics serialise, 45 ms vs 18 ms - so with hot keys
+  // around it is used only where the tile-sort kernel cannot go (more than ~700 groups per partition: near-unique tuples).
+  const bool use_hash = direct && c->opt_part_hash != 2 &&
+                        (c->opt_part_hash == 1 || (n / std::max<long long>(est_groups, 1) < 64 && (!gp.hot_tab || (est_groups >> 16) > 700)));
   const long long hash_groups_max = is_int ? 1400 : 2800;
   int bits = 1;
   while (bits < 16 && (est_groups >> bits) > 600) bits++;
@@ -503,7 +508,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   }
   u64* sidep = nside ? side.as<u64>() : nullptr;
   const long long side_base = nb1 * cap1, side_cap = nside * cap1;
-  const size_t smem = (size_t)GP_TILE * 20 + 288 * 4 + 288 * 8 + ((size_t)8 << GB_HOT_LOG_SLOTS);
+  const size_t smem = (size_t)GP_TILE * 20 + 288 * 4 + 288 * 8 + ((size_t)4 << GB_HOT_LOG_SLOTS);
   // the attribute is per device (several contexts / GPUs may live in one process): set it on every call
   PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PDRS_CUDA(c, cudaFuncSetAttribute(gp_part_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -681,7 +686,15 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       sp.part_chunk_tiles = (int)((tiles + sctas - 1) / sctas);
       sp.part_cpp = (int)((tiles + sp.part_chunk_tiles - 1) / sp.part_chunk_tiles);
       sp.ts_team = 0;
-      PDRS_CUDA(c, gb_tsort_launch(sp, is_int, flags, ts_nt, ts_gpt, sctas, ts_smem, c->stream));
+      int s_nt = ts_nt, s_gpt = ts_gpt, s_slots = ts_slots;
+      size_t s_smem = ts_smem;
+      if (gb_tsort_geometry(2047, false, c->smem_optin, 512, &s_nt, &s_gpt, &s_slots, &s_smem)) {      // room for every hot key (<= 1800) + some more
+        sp.sh_cap = 2047; sp.sh_slots = s_slots;
+        int l2 = 0;
+        while ((1 << l2) < s_slots) l2++;
+        sp.sh_log_slots = l2;
+      } else { s_nt = ts_nt; s_gpt = ts_gpt; s_smem = ts_smem; }
+      PDRS_CUDA(c, gb_tsort_launch(sp, is_int, flags, s_nt, s_gpt, sctas, s_smem, c->stream));
       c->stats.kernel_launches++;
     }
   } else {

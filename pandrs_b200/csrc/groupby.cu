@@ -524,29 +524,29 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
       const int HOTCAP = 4096;
       DevBuf hb;
       PDRS_TRY(hb.alloc(c, (size_t)(2 * HOTCAP + 2) * 8, true));
-      gb_hot_keys_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(stm.t.hdr, stm.t.slots, 8ull, HOTCAP, hb.as<u64>());
+      gb_hot_keys_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(stm.t.hdr, stm.t.slots, 6ull, HOTCAP, hb.as<u64>());
       c->stats.kernel_launches++;
       std::vector<u64> hh((size_t)2 * HOTCAP + 2);
       PDRS_CUDA(c, cudaMemcpyAsync(hh.data(), hb.p, hh.size() * 8, cudaMemcpyDeviceToHost, c->stream));
       PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
       const size_t nh = (size_t)std::min<u64>(hh[0], HOTCAP);
       std::vector<std::pair<u64, u64>> hk;      // (occurrences, key)
-      for (size_t i = 0; i < nh; i++) if (hh[1 + 2 * i] != ~0ull) hk.push_back({hh[2 + 2 * i], hh[1 + 2 * i]});
+      for (size_t i = 0; i < nh; i++) hk.push_back({hh[2 + 2 * i], hh[1 + 2 * i]});
       std::sort(hk.begin(), hk.end(), [](const std::pair<u64, u64>& a, const std::pair<u64, u64>& b) { return a.first > b.first; });
-      if (hk.size() > 900) hk.resize(900);
+      if (hk.size() > 1800) hk.resize(1800);
       if (!hk.empty()) {
-        std::vector<u64> tab((size_t)1 << GB_HOT_LOG_SLOTS, ~0ull);
+        std::vector<uint32_t> tab((size_t)1 << GB_HOT_LOG_SLOTS, 0u);
         u64 hot_rows = 0;
         for (auto& kc : hk) {
           uint32_t sl = gb_hot_slot(kc.second, GB_HOT_LOG_SLOTS);
-          while (tab[sl] != ~0ull) sl = (sl + 1) & ((1u << GB_HOT_LOG_SLOTS) - 1u);
-          tab[sl] = kc.second;
+          while (tab[sl] != 0u) sl = (sl + 1) & ((1u << GB_HOT_LOG_SLOTS) - 1u);
+          tab[sl] = gb_hot_tag(kc.second);
           hot_rows += kc.first;
         }
-        PDRS_TRY(hot_dev.alloc(c, tab.size() * 8));
-        PDRS_CUDA(c, cudaMemcpyAsync(hot_dev.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        PDRS_TRY(hot_dev.alloc(c, tab.size() * 4));
+        PDRS_CUDA(c, cudaMemcpyAsync(hot_dev.p, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, c->stream));
         PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
-        base.hot_tab = hot_dev.as<u64>(); base.hot_log_slots = GB_HOT_LOG_SLOTS; base.hot_frac = (float)((double)hot_rows / s);
+        base.hot_tab = hot_dev.as<uint32_t>(); base.hot_log_slots = GB_HOT_LOG_SLOTS; base.hot_frac = (float)((double)hot_rows / s);
       }
     }
     if (variant == 0 && cn[CNT_KMINC]) {     // small dense integer keys: direct-mapped group ids, no key table

@@ -96,14 +96,20 @@ struct GbParams {
   int ts_team;                      // tile-sort kernel: use the variant with the team-of-8 reduce
   int ts_mid;                       // ... longer than this (and up to ts_heavy) by a team of 8 lanes, shorter ones by their owner thread
   int ts_generic;                   // tile-sort kernel: keys are generic tuples packed into one word (not one Int64 column)
-  // Hot keys of a skewed distribution (the keys the cardinality sample met >= 8 times; at most 900): an open-addressing set of
+  // Hot keys of a skewed distribution (the keys the cardinality sample met >= 6 times; at most 1800): an open-addressing set of
   // packed key words (all ones = empty).  The partitioned path routes their rows around the hash partitions (gb_part.cu).
-  const u64* hot_tab; int hot_log_slots; float hot_frac;      // hot_frac = share of the sampled rows that carry a hot key
+  const uint32_t* hot_tab; int hot_log_slots; float hot_frac;      // hot_frac = share of the sampled rows that carry a hot key
 };
-#define GB_HOT_LOG_SLOTS 11
+// The set holds a 32-bit TAG per key (0 = empty), not the key: a false positive (2^-31 per probe) only sends a row of a cold key
+// to the side area, which aggregates any key - 4 bytes per slot keep the partition kernel at two CTAs per SM.
+#define GB_HOT_LOG_SLOTS 12
 __host__ __device__ __forceinline__ uint32_t gb_hot_slot(u64 k, int log_slots) {
   const uint32_t lo = (uint32_t)k ^ (uint32_t)(k >> 32);
   return (lo * 0x9E3779B1u + (uint32_t)(k >> 32) * 0x85EBCA6Bu) >> (32 - log_slots);
+}
+__host__ __device__ __forceinline__ uint32_t gb_hot_tag(u64 k) {
+  const uint32_t lo = (uint32_t)k, hi = (uint32_t)(k >> 32);
+  return ((lo * 0xC2B2AE35u) ^ (hi * 0x27D4EB2Fu) ^ (lo >> 15)) | 1u;
 }
 
 // ---------------------------------------------------------------- small device helpers
