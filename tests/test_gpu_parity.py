@@ -292,8 +292,16 @@ def test_partition_overflow_falls_back(ctx, oracle):
     kv = np.where(rng.random(n) < 0.5, 123_456_789, rng.integers(0, 40_000, n) * 104_729)
     k = Spec(pb.I64, kv)
     v = Spec(pb.F64, rng.normal(1.0, 1.0, n), nulls=rng.random(n) < 0.05)
+    ctx.set_option("part_hot", 0)            # without the hot-key routing
+    try:
+        got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
+        assert len(got) == len(np.unique(kv)) and ctx.stats()["groupby_algo_used"] != pb.GB_PARTITIONED
+    finally:
+        ctx.set_option("part_hot", 1)
+    # default: the cardinality sample has seen the hot key; its rows bypass the hash partitions (side area, one tile-sort pass),
+    # nothing overflows and the partitioned path applies
     got = compare_groupby(pb, oracle, ctx, [k], [v], [(0, op) for op in ALL6], device=True)
-    assert len(got) == len(np.unique(kv)) and ctx.stats()["groupby_algo_used"] != pb.GB_PARTITIONED
+    assert len(got) == len(np.unique(kv)) and ctx.stats()["groupby_algo_used"] == pb.GB_PARTITIONED
     # a milder hot key (12% of the rows): its bucket fills up and the excess runs are parked in the side area behind
     # the buckets, which is aggregated as extra partitions - the partitioned path still applies
     kv = np.where(rng.random(n) < 0.12, 123_456_789, rng.integers(0, 40_000, n) * 104_729)
