@@ -52,7 +52,8 @@ typedef enum pdrs_dtype {
 
 /* AggregateOp, same order as src/optimized/split_dataframe/group/types.rs:11-34 */
 typedef enum pdrs_agg_op {
-  PDRS_SUM = 0, PDRS_MEAN = 1, PDRS_MIN = 2, PDRS_MAX = 3, PDRS_COUNT = 4, PDRS_STD = 5, PDRS_VAR = 6
+  PDRS_SUM = 0, PDRS_MEAN = 1, PDRS_MIN = 2, PDRS_MAX = 3, PDRS_COUNT = 4, PDRS_STD = 5, PDRS_VAR = 6,
+  PDRS_MEDIAN = 7, PDRS_FIRST = 8, PDRS_LAST = 9   /* order-dependent: computed from the row lists, pdrs_group_rows_agg() */
 } pdrs_agg_op;
 
 /* JoinType (src/optimized/split_dataframe/join.rs:11-20) */
@@ -152,6 +153,9 @@ int32_t pdrs_host_free(pdrs_ctx* ctx, void* p);
  *  aggs[naggs]   (value_col, op); every aggregate is returned as f64 (aggregation.rs:865)
  *  filter        optional BOOL_BITS column: only rows where it is Some(true) take part
  *                (data_ops.rs:49-55 fused in front of the aggregation), NULL = no filter
+ * HOST columns of >= "stream_rows" rows (pdrs_set_option, default 2^25) are processed CHUNK BY CHUNK (src/large/mod.rs): chunk
+ * i + 1 travels to the device (pageable sources through a pool of staging threads with pinned buffers, pinned sources by direct
+ * DMA) while chunk i is aggregated into mergeable states, so the input may be larger than device memory.
  * Semantics follow SURVEY.md §9.1-9.2: NULL keys form one group, Count = group size incl. NULL values,
  * empty/all-NULL -> 0.0, Min/Max sentinel collapse, Std/Var with n-1.  Group order is unspecified. */
 int32_t pdrs_groupby_agg(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals,
@@ -195,6 +199,56 @@ int32_t pdrs_groupby_merge(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, c
  * permutation perm_dev[nrows] that groups the row ids by destination, and counts_host[nparts]. */
 int32_t pdrs_hash_partition(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, int32_t nparts,
                             int64_t* perm_dev, int64_t* counts_host);
+
+/* ---- row lists per group ----
+ * Replaces OptimizedDataFrame::par_groupby (group/grouping.rs:124-331) up to the sub-frame construction, and the row lists of
+ * GroupBy (`groups: HashMap<Vec<String>, Vec<usize>>`, grouping.rs:62-104) for the order-dependent aggregates:
+ *   ids[offsets[g] .. offsets[g + 1]) = the rows of group g in ASCENDING order (what the reference pushes, grouping.rs:103, 188),
+ *   keys as in pdrs_groupby_key (the caller labels a NULL part "NA" and joins the parts with "_", grouping.rs:158-186).
+ * One sub-frame per group = one pdrs_gather per column over the WHOLE permutation `ids` (filter_by_indices, data_ops.rs:124-211)
+ * and a slice [offsets[g], offsets[g + 1]) of the gathered column per group.  At most 2^32 - 2 rows per call.  Group order is
+ * unspecified (HashMap). */
+typedef struct pdrs_group_rows pdrs_group_rows;
+int32_t pdrs_groupby_rows(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, pdrs_group_rows** out);
+int64_t pdrs_group_rows_n_groups(const pdrs_group_rows* r);
+int64_t pdrs_group_rows_n_rows(const pdrs_group_rows* r);
+int32_t pdrs_group_rows_key(const pdrs_group_rows* r, int32_t k, void* out_values, uint8_t* out_is_null);
+int32_t pdrs_group_rows_offsets(const pdrs_group_rows* r, int64_t* out /* n_groups + 1 */);
+int32_t pdrs_group_rows_ids(const pdrs_group_rows* r, int64_t* out /* n_rows */);
+const int64_t* pdrs_group_rows_offsets_dev(const pdrs_group_rows* r);
+const int64_t* pdrs_group_rows_ids_dev(const pdrs_group_rows* r);
+/* AggregateOp::Median / First / Last of an Int64 / Float64 column over the row lists (group/aggregation.rs:585-624, 703-742):
+ * First / Last = the value of the group's first / last row as f64, 0.0 when it is NULL; Median = middle of the sorted non-NULL
+ * values (mean of the two middle ones for an even count; Int64: wrapping i64 sum, then / 2.0), 0.0 for an all-NULL group.
+ * Groups holding NaN: unspecified (the reference sorts with partial_cmp(..).unwrap_or(Equal)).  out_host[n_groups]. */
+int32_t pdrs_group_rows_agg(pdrs_group_rows* r, const pdrs_col* val, int32_t op, double* out_host);
+void pdrs_group_rows_free(pdrs_group_rows* r);
+
+/* ---- columnar ingest (the step in front of the path) ----
+ * Arrow validity bitmap -> pandrs null mask.  Arrow: bit SET = valid, row i at bit (bit_offset + i), LSB first; pandrs: bit SET =
+ * NULL, row i at bit i (src/column/common/utils create_bitmask, core/column.rs:163-177).  Replaces the per-element is_null() loops
+ * of ArrowConverter::arrow_array_to_series (src/arrow_integration.rs:160-225).  out_null_bits: ceil(len / 8) bytes (trailing bits
+ * of the last byte are 0).  validity == NULL means "all valid" (an all-zero mask).  n_nulls_host (optional) = number of NULL rows. */
+int32_t pdrs_arrow_validity_to_nulls(pdrs_ctx* ctx, const uint8_t* validity, int32_t validity_mem, int64_t bit_offset, int64_t len,
+                                     uint8_t* out_null_bits, int32_t out_mem, int64_t* n_nulls_host);
+/* Dictionary encoding of an Arrow Utf8 (32-bit offsets) / LargeUtf8 (64-bit offsets) array on the device: what
+ * StringColumn::with_nulls -> GLOBAL_STRING_POOL.add_strings (src/column/string_column.rs:95-112, string_pool.rs:28-52) does on the
+ * host under an RwLock.  ids[i] = dense id of row i's string, handed out in order of FIRST OCCURRENCE (the order get_or_insert assigns
+ * in a row loop); a NULL row is the empty string (its placeholder in StringColumn::with_nulls) and keeps its bit in the null mask.
+ * first_rows[id] = the first row carrying that string (the host reads the text from its own copy of the array and interns it;
+ * pdrs_dict_remap then rewrites the ids into the ids of an existing pool).  Strings are compared through two independent 64-bit
+ * hashes; a verification pass compares the BYTES of every row with those of its id's first row and the call fails with
+ * PDRS_ERR_UNSUPPORTED should they ever differ - ids are never wrong.  offsets / bytes / validity live where `mem` says. */
+typedef struct pdrs_dict pdrs_dict;
+int32_t pdrs_dict_encode(pdrs_ctx* ctx, const void* offsets /* len + 1 */, int32_t offsets_are_64, const uint8_t* bytes, int64_t nbytes,
+                         const uint8_t* validity, int64_t bit_offset, int64_t len, int32_t mem, pdrs_dict** out);
+int64_t pdrs_dict_n_unique(const pdrs_dict* d);
+int32_t pdrs_dict_ids(const pdrs_dict* d, uint32_t* out_host /* len */);
+const uint32_t* pdrs_dict_ids_dev(const pdrs_dict* d);
+int32_t pdrs_dict_first_rows(const pdrs_dict* d, int64_t* out_host /* n_unique */);
+const uint8_t* pdrs_dict_nulls_dev(const pdrs_dict* d);     /* pandrs null mask of the column (NULL when validity was NULL) */
+int32_t pdrs_dict_remap(pdrs_dict* d, const uint32_t* new_ids_host /* n_unique */);
+void pdrs_dict_free(pdrs_dict* d);
 
 /* ---- hash join ----
  * Replaces the build/probe part of OptimizedDataFrame::join_impl (split_dataframe/join.rs:107-208).

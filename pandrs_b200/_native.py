@@ -15,7 +15,7 @@ CSRC = os.path.join(_HERE, "csrc")
 
 # pdrs_dtype / pdrs_agg_op / pdrs_join_type / pdrs_mem / pdrs_groupby_algo (include/pandrs_b200.h)
 I64, F64, DICT_U32, BOOL_BITS, I32 = 0, 1, 2, 3, 4
-SUM, MEAN, MIN, MAX, COUNT, STD, VAR = range(7)
+SUM, MEAN, MIN, MAX, COUNT, STD, VAR, MEDIAN, FIRST, LAST = range(10)
 INNER, LEFT, RIGHT, OUTER = 0, 1, 2, 3
 MEM_HOST, MEM_DEVICE = 0, 1
 GB_AUTO, GB_SHARED, GB_GLOBAL, GB_DENSE, GB_TILESORT, GB_PARTITIONED, GB_FEW = 0, 1, 2, 3, 4, 5, 6
@@ -80,6 +80,25 @@ SIGNATURES = {
     "pdrs_groupby_states_dev": (_vp, [_vp, _i32]),
     "pdrs_groupby_merge": (_i32, [_vp, _P(PdrsCol), _i32, _P(_vp), _P(_i32), _i32, _i64, _P(PdrsAgg), _i32, _P(_vp)]),
     "pdrs_hash_partition": (_i32, [_vp, _P(PdrsCol), _i32, _i32, _vp, _P(_i64)]),
+    "pdrs_groupby_rows": (_i32, [_vp, _P(PdrsCol), _i32, _P(_vp)]),
+    "pdrs_group_rows_n_groups": (_i64, [_vp]),
+    "pdrs_group_rows_n_rows": (_i64, [_vp]),
+    "pdrs_group_rows_key": (_i32, [_vp, _i32, _vp, _vp]),
+    "pdrs_group_rows_offsets": (_i32, [_vp, _vp]),
+    "pdrs_group_rows_ids": (_i32, [_vp, _vp]),
+    "pdrs_group_rows_offsets_dev": (_vp, [_vp]),
+    "pdrs_group_rows_ids_dev": (_vp, [_vp]),
+    "pdrs_group_rows_agg": (_i32, [_vp, _P(PdrsCol), _i32, _vp]),
+    "pdrs_group_rows_free": (None, [_vp]),
+    "pdrs_arrow_validity_to_nulls": (_i32, [_vp, _vp, _i32, _i64, _i64, _vp, _i32, _P(_i64)]),
+    "pdrs_dict_encode": (_i32, [_vp, _vp, _i32, _vp, _i64, _vp, _i64, _i64, _i32, _P(_vp)]),
+    "pdrs_dict_n_unique": (_i64, [_vp]),
+    "pdrs_dict_ids": (_i32, [_vp, _vp]),
+    "pdrs_dict_ids_dev": (_vp, [_vp]),
+    "pdrs_dict_first_rows": (_i32, [_vp, _vp]),
+    "pdrs_dict_nulls_dev": (_vp, [_vp]),
+    "pdrs_dict_remap": (_i32, [_vp, _vp]),
+    "pdrs_dict_free": (None, [_vp]),
     "pdrs_join_pairs": (_i32, [_vp, _P(PdrsCol), _P(PdrsCol), _i32, _P(_vp)]),
     "pdrs_join_gather": (_i32, [_vp, _P(PdrsCol), _P(PdrsCol), _i32, _P(PdrsCol), _i32, _P(_vp)]),
     "pdrs_join_right_col": (_i32, [_vp, _i32, _vp]),

@@ -142,6 +142,94 @@ class GroupByResult:
             pass
 
 
+class GroupRows:
+    """Owns a pdrs_group_rows: the row lists of every group (par_groupby, grouping.rs:124-331) and the order-dependent
+    aggregates over them (Median / First / Last, aggregation.rs:585-624, 703-742)."""
+
+    def __init__(self, ctx: "Context", handle, key_dtypes):
+        self.ctx, self._h, self.key_dtypes = ctx, handle, key_dtypes
+        self.n_groups = int(ctx.L.pdrs_group_rows_n_groups(handle))
+        self.n_rows = int(ctx.L.pdrs_group_rows_n_rows(handle))
+
+    def key(self, k: int):
+        out = np.empty(self.n_groups, KEY_OUT_DTYPE[self.key_dtypes[k]])
+        isnull = np.empty(self.n_groups, np.uint8)
+        if self.n_groups:
+            self.ctx._chk(self.ctx.L.pdrs_group_rows_key(self._h, k, out.ctypes.data, isnull.ctypes.data))
+        return out, isnull.astype(bool)
+
+    def offsets(self) -> np.ndarray:
+        out = np.zeros(self.n_groups + 1, np.int64)
+        if self.n_groups:
+            self.ctx._chk(self.ctx.L.pdrs_group_rows_offsets(self._h, out.ctypes.data))
+        return out
+
+    def ids(self) -> np.ndarray:
+        out = np.empty(self.n_rows, np.int64)
+        if self.n_rows:
+            self.ctx._chk(self.ctx.L.pdrs_group_rows_ids(self._h, out.ctypes.data))
+        return out
+
+    def ids_dev(self): return self.ctx.L.pdrs_group_rows_ids_dev(self._h)
+    def offsets_dev(self): return self.ctx.L.pdrs_group_rows_offsets_dev(self._h)
+
+    def agg(self, val: "Column", op: int) -> np.ndarray:
+        out = np.zeros(self.n_groups, np.float64)
+        vc = val.c()
+        self.ctx._chk(self.ctx.L.pdrs_group_rows_agg(self._h, C.byref(vc), int(op), out.ctypes.data if self.n_groups else None))
+        return out
+
+    def close(self):
+        if self._h:
+            self.ctx.L.pdrs_group_rows_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DictEncoded:
+    """Owns a pdrs_dict: dictionary ids of an Arrow string array built on the device (string_pool.rs:28-52)."""
+
+    def __init__(self, ctx: "Context", handle, length: int):
+        self.ctx, self._h, self.len = ctx, handle, int(length)
+        self.n_unique = int(ctx.L.pdrs_dict_n_unique(handle))
+
+    def ids(self) -> np.ndarray:
+        out = np.empty(self.len, np.uint32)
+        if self.len:
+            self.ctx._chk(self.ctx.L.pdrs_dict_ids(self._h, out.ctypes.data))
+        return out
+
+    def first_rows(self) -> np.ndarray:
+        out = np.empty(self.n_unique, np.int64)
+        if self.n_unique:
+            self.ctx._chk(self.ctx.L.pdrs_dict_first_rows(self._h, out.ctypes.data))
+        return out
+
+    def ids_dev(self): return self.ctx.L.pdrs_dict_ids_dev(self._h)
+    def nulls_dev(self): return self.ctx.L.pdrs_dict_nulls_dev(self._h)
+
+    def remap(self, new_ids):
+        m = np.ascontiguousarray(new_ids, np.uint32)
+        assert len(m) == self.n_unique
+        self.ctx._chk(self.ctx.L.pdrs_dict_remap(self._h, m.ctypes.data if m.size else None))
+
+    def close(self):
+        if self._h:
+            self.ctx.L.pdrs_dict_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class JoinResult:
     def __init__(self, ctx: "Context", handle, right_dtypes=()):
         self.ctx, self._h = ctx, handle
@@ -355,6 +443,34 @@ class Context:
         else:
             self._chk(self.L.pdrs_groupby_agg(self._h, ka, len(keys), va, len(vals), aa, len(aggs), C.byref(f) if f is not None else None, C.byref(h)))
         return GroupByResult(self, h, [k.dtype for k in keys], len(vals), len(aggs))
+
+    def groupby_rows(self, keys: Sequence[Column]) -> GroupRows:
+        """Row lists per group: replaces par_groupby's grouping (grouping.rs:124-331) and GroupBy.groups for Median / First / Last."""
+        ka = self._cols(keys)
+        h = C.c_void_p()
+        self._chk(self.L.pdrs_groupby_rows(self._h, ka, len(keys), C.byref(h)))
+        return GroupRows(self, h, [k.dtype for k in keys])
+
+    def arrow_validity_to_nulls(self, validity, length: int, bit_offset: int = 0):
+        """Arrow validity bitmap (numpy uint8 array, or None = all valid) -> (pandrs null mask as numpy uint8, number of NULLs)."""
+        out = np.zeros((length + 7) // 8, np.uint8)
+        n = C.c_int64()
+        v = None if validity is None else np.ascontiguousarray(validity, np.uint8)
+        self._chk(self.L.pdrs_arrow_validity_to_nulls(self._h, v.ctypes.data if v is not None and v.size else None, MEM_HOST, int(bit_offset), int(length),
+                                                      out.ctypes.data if out.size else None, MEM_HOST, C.byref(n)))
+        return out, int(n.value)
+
+    def dict_encode(self, offsets, data, validity=None, bit_offset: int = 0, length: Optional[int] = None) -> DictEncoded:
+        """Arrow Utf8 / LargeUtf8 buffers (numpy int32 / int64 offsets, uint8 bytes, optional validity bitmap) -> dictionary ids."""
+        off = np.ascontiguousarray(offsets)
+        assert off.dtype in (np.int32, np.int64)
+        n = int(length if length is not None else len(off) - 1)
+        by = np.ascontiguousarray(data, np.uint8)
+        v = None if validity is None else np.ascontiguousarray(validity, np.uint8)
+        h = C.c_void_p()
+        self._chk(self.L.pdrs_dict_encode(self._h, off.ctypes.data if off.size else None, int(off.dtype == np.int64), by.ctypes.data if by.size else None, by.size,
+                                          v.ctypes.data if v is not None and v.size else None, int(bit_offset), n, MEM_HOST, C.byref(h)))
+        return DictEncoded(self, h, n)
 
     def groupby_partial(self, keys, vals, filter=None, all_stats=True) -> GroupByResult:
         ka, va = self._cols(keys), self._cols(vals)

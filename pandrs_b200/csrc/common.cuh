@@ -14,6 +14,8 @@
 #define PDRS_MAX_VALS 16
 #define PDRS_MAX_AGGS 64
 
+struct PdrsStager;   // stage.cu
+
 struct pdrs_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -62,9 +64,18 @@ struct pdrs_ctx {
   int64_t opt_part_hash = 0;           // ... aggregated by the shared-memory hash kernel: 0 = auto (few rows per group), 1 = always, 2 = never (tile sort)
   int64_t opt_few = 1;                 // allow the few-groups multi-column kernel (gb_few.cu)
   int64_t opt_tsort_min_groups = 2;    // a single group serialises the tile histogram: the per-warp shared tables win
+  int64_t opt_stage_threads = 0;       // staging engine (stage.cu): worker threads, 0 = auto (<= 8), -1 = plain cudaMemcpyAsync from the caller's memory
+  int64_t opt_stream_rows = 1 << 25;   // groupby over HOST columns with at least this many rows runs chunk by chunk (0 = never)
+  int64_t opt_stream_chunk_rows = 0;   // rows per chunk of that path (0 = default 2^26)
+  int64_t opt_stream_compact_rows = 1 << 22;   // ... appended state rows beyond which (and beyond 4x the groups of a chunk) they are re-merged
+  PdrsStager* stager = nullptr;
 };
 
 int32_t pdrs_fail(pdrs_ctx* ctx, int32_t code, const char* fmt, ...);
+// stage.cu: asynchronous host -> device copies through a pool of staging threads (pageable sources) / direct DMA (pinned sources)
+int32_t pdrs_stage_copy_async(pdrs_ctx* c, void* dst_dev, const void* src_host, size_t bytes);
+int32_t pdrs_stage_join(pdrs_ctx* c, cudaStream_t consumer);
+void pdrs_stage_destroy(pdrs_ctx* c);
 
 #define PDRS_CUDA(ctx, call)                                                                   \
   do {                                                                                         \

@@ -82,6 +82,7 @@ void pdrs_ctx_destroy(pdrs_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  pdrs_stage_destroy(c);
   if (c->flush_buf) cudaFree(c->flush_buf);
   if (c->pinned_scalars) cudaFreeHost(c->pinned_scalars);
   cudaEventDestroy(c->ev_a); cudaEventDestroy(c->ev_b);
@@ -143,6 +144,10 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "part_direct")) c->opt_part_direct = value;
   else if (!strcmp(name, "part_hot")) c->opt_part_hot = value;
   else if (!strcmp(name, "part_hash")) c->opt_part_hash = value;
+  else if (!strcmp(name, "stage_threads")) { if (c->stager && value != c->opt_stage_threads) pdrs_stage_destroy(c); c->opt_stage_threads = value; }
+  else if (!strcmp(name, "stream_rows")) c->opt_stream_rows = value;
+  else if (!strcmp(name, "stream_chunk_rows")) c->opt_stream_chunk_rows = value;
+  else if (!strcmp(name, "stream_compact_rows")) c->opt_stream_compact_rows = value;
   else return pdrs_fail(c, PDRS_ERR_BAD_ARG, "unknown option '%s'", name);
   return PDRS_OK;
 }

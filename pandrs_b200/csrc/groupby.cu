@@ -962,15 +962,21 @@ static int32_t finish_merged(pdrs_ctx* c, const KeySpec& ks, TableMem& tm, std::
   return PDRS_OK;
 }
 
+static bool stream_eligible(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_col* filter, const pdrs_pred* pred);
+static int32_t groupby_stream(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_agg* aggs, int32_t naggs,
+                              const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out);
+
 extern "C" {
 
 int32_t pdrs_groupby_agg(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
                          const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, pdrs_groupby_result** out) {
+  if (stream_eligible(ctx, keys, nkeys, vals, nvals, filter, nullptr)) return groupby_stream(ctx, keys, nkeys, vals, nvals, aggs, naggs, filter, nullptr, out);
   return groupby_run(ctx, keys, nkeys, vals, nvals, aggs, naggs, filter, MODE_AGG, 0, out);
 }
 
 int32_t pdrs_groupby_agg_where(pdrs_ctx* ctx, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals,
                                const pdrs_agg* aggs, int32_t naggs, const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out) {
+  if (stream_eligible(ctx, keys, nkeys, vals, nvals, filter, pred)) return groupby_stream(ctx, keys, nkeys, vals, nvals, aggs, naggs, filter, pred, out);
   return groupby_run(ctx, keys, nkeys, vals, nvals, aggs, naggs, filter, MODE_AGG, 0, out, pred);
 }
 
@@ -1084,7 +1090,7 @@ __device__ __forceinline__ int dist_dest(const u64 (&w)[NW], bool nullgroup, int
   return (int)(pdrs_mix64(key_hash<NW>(w) ^ 0x5851F42D4C957F2Dull) % (u64)world);
 }
 // MODE 0: row j -> out[8 + j * stride] (replicated; out[0] = G).  MODE 1: count the rows per destination rank.
-// MODE 2: scatter into out[(off[dest] + ticket) * stride].
+// MODE 2: scatter into out[(off[dest] + ticket) * stride].  MODE 3: row j -> out[j * stride] (plain append, no header).
 template <int NW, int MODE>
 __global__ void dist_pack_kernel(const DistPack p, u64* __restrict__ out, u64* __restrict__ counts, const u64* __restrict__ off) {
   if (MODE == 0 && blockIdx.x == 0 && threadIdx.x == 0) out[0] = (u64)p.G;
@@ -1095,7 +1101,7 @@ __global__ void dist_pack_kernel(const DistPack p, u64* __restrict__ out, u64* _
     if (MODE == 1) { atomicAdd(&counts[dist_dest<NW>(w, ng, p.world)], 1ull); continue; }
     long long at = j;
     if (MODE == 2) { const int d = dist_dest<NW>(w, ng, p.world); at = (long long)(off[d] + atomicAdd(&counts[d], 1ull)); }
-    u64* q = out + (MODE == 0 ? 8 : 0) + at * p.stride;
+    u64* q = out + (MODE == 0 ? 8 : 0) + at * p.stride;   // MODE 3: at = j
     q[0] = w[0]; q[1] = NW > 1 ? w[NW > 1 ? 1 : 0] : 0ull; q[2] = NW > 2 ? w[NW > 2 ? 2 : 0] : 0ull;
     q[3] = ng ? 1ull : 0ull;
     q[4] = (u64)p.rows[j];
@@ -1163,6 +1169,232 @@ static int32_t dist_pack_launch(pdrs_ctx* c, int nw, const DistPack& pk, u64* ou
   }
   c->stats.kernel_launches++;
   PDRS_CUDA(c, cudaGetLastError());
+  return PDRS_OK;
+}
+
+// ================================================================ chunked groupby over HOST columns (out-of-core inputs)
+// SURVEY.md 8(f) row 4 / src/large/mod.rs (ChunkedDataFrame: a frame larger than memory is processed chunk by chunk): the same
+// groupby(keys).agg(...) as pdrs_groupby_agg, for columns that live in HOST memory.  Instead of staging whole columns (which caps
+// the input at what fits in HBM next to the work areas, and leaves the GPU idle during the transfer) the rows are cut into chunks:
+//   chunk i + 1 travels host -> device (staging engine of stage.cu: pinned sources by direct DMA, pageable sources through the
+//   worker threads' pinned slots) WHILE chunk i is aggregated into mergeable per-group states (the kernels of pdrs_groupby_partial);
+//   the states of all chunks are appended as packed rows [key words | NULL-group flag | rows | 8 words per value column] and merged
+//   at the end exactly like the ranks' states of pdrs_groupby_agg_dist (Chan-style re-basing of S1 / S2; compaction in between
+//   when the appended rows outgrow the groups).  Device memory: two chunk buffers per column + the states, whatever n is.
+static bool stream_eligible(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_col* filter, const pdrs_pred* pred) {
+  if (!c || !keys || nkeys < 1 || nkeys > PDRS_MAX_KEYS || nvals < 0 || nvals > PDRS_MAX_VALS || (nvals && !vals)) return false;
+  if (c->opt_stream_rows <= 0 || keys[0].len < c->opt_stream_rows) return false;
+  const int64_t n = keys[0].len;
+  for (int k = 0; k < nkeys; k++) if (keys[k].mem != PDRS_MEM_HOST || keys[k].len != n || keys[k].dtype < 0 || keys[k].dtype > PDRS_I32) return false;
+  for (int v = 0; v < nvals; v++) if (vals[v].mem != PDRS_MEM_HOST || vals[v].len != n || vals[v].dtype < 0 || vals[v].dtype > PDRS_I32) return false;
+  if (filter && (filter->mem != PDRS_MEM_HOST || filter->len != n || filter->dtype != PDRS_BOOL_BITS)) return false;
+  if (pred && (pred->col.mem != PDRS_MEM_HOST || pred->col.len != n)) return false;
+  return true;
+}
+
+namespace {
+struct StreamCol {              // one host column and its two device chunk buffers
+  const pdrs_col* h = nullptr;
+  DevBuf data[2], nulls[2];
+  size_t data_cap = 0, null_cap = 0;
+};
+}  // namespace
+
+static int32_t groupby_stream(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_agg* aggs, int32_t naggs,
+                              const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out) {
+  if (!out || naggs < 0 || naggs > PDRS_MAX_AGGS || (naggs && !aggs)) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby: bad argument");
+  PDRS_CUDA(c, cudaSetDevice(c->device));
+  const int64_t n = keys[0].len;
+  bool all_stats = false;
+  for (int a = 0; a < naggs; a++) {
+    if (aggs[a].op < PDRS_SUM || aggs[a].op > PDRS_VAR) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: unknown op %d", a, aggs[a].op);
+    if (aggs[a].op == PDRS_COUNT) { if (aggs[a].value_col >= nvals) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: value column %d out of range", a, aggs[a].value_col); continue; }
+    if (aggs[a].value_col < 0 || aggs[a].value_col >= nvals) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "aggregate %d: value column %d out of range", a, aggs[a].value_col);
+    const int dt = vals[aggs[a].value_col].dtype;
+    if (dt != PDRS_I64 && dt != PDRS_F64) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "aggregate %d: op %d is not supported on a column of dtype %d (only Count is)", a, aggs[a].op, dt);
+    if (aggs[a].op != PDRS_SUM && aggs[a].op != PDRS_MEAN) all_stats = true;
+  }
+  if (pred && ((pred->col.dtype != PDRS_I64 && pred->col.dtype != PDRS_F64) || pred->op < PDRS_CMP_LT || pred->op > PDRS_CMP_NE))
+    return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "predicate: needs an Int64 / Float64 column of the same length and a pdrs_cmp_op");
+  // only the value columns an aggregate reads travel
+  std::vector<int> vmap(nvals, -1);
+  std::vector<const pdrs_col*> used;
+  for (int a = 0; a < naggs; a++) if (aggs[a].op != PDRS_COUNT && vmap[aggs[a].value_col] < 0) { vmap[aggs[a].value_col] = (int)used.size(); used.push_back(&vals[aggs[a].value_col]); }
+  const int nvs = (int)used.size();
+  std::vector<pdrs_agg> ag(aggs, aggs + naggs);
+  for (auto& a : ag) if (a.op != PDRS_COUNT) a.value_col = vmap[a.value_col];
+  std::vector<int32_t> val_is_int(std::max(nvs, 1));
+  for (int v = 0; v < nvs; v++) val_is_int[v] = used[v]->dtype == PDRS_I64;
+
+  long long chunk = c->opt_stream_chunk_rows > 0 ? c->opt_stream_chunk_rows : (1ll << 26);
+  chunk = std::max<long long>(1 << 16, (chunk + 65535) / 65536 * 65536);      // bitmap words and 128-bit loads stay aligned
+  const long long nchunks = (n + chunk - 1) / chunk;
+
+  const int ncols = nkeys + nvs + (filter ? 1 : 0) + (pred ? 1 : 0);
+  std::vector<StreamCol> cols(ncols);
+  {
+    int i = 0;
+    for (int k = 0; k < nkeys; k++) cols[i++].h = &keys[k];
+    for (int v = 0; v < nvs; v++) cols[i++].h = used[v];
+    if (filter) cols[i++].h = filter;
+    if (pred) cols[i++].h = &pred->col;
+  }
+  const long long crow = std::min<long long>(chunk, n);
+  for (auto& sc : cols) {
+    sc.data_cap = (sc.h->dtype == PDRS_BOOL_BITS ? (size_t)(crow + 7) / 8 : (size_t)crow * pdrs_dtype_bytes(sc.h->dtype)) + 128;
+    sc.null_cap = (size_t)(crow + 7) / 8 + 128;
+    for (int b = 0; b < 2 && b < nchunks; b++) {
+      PDRS_TRY(sc.data[b].alloc(c, sc.data_cap, sc.h->dtype == PDRS_BOOL_BITS));
+      if (sc.h->null_bits) PDRS_TRY(sc.nulls[b].alloc(c, sc.null_cap, true));
+    }
+  }
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));      // the buffers exist before the staging streams write into them
+
+  auto rows_of = [&](long long i) { return std::min<long long>(chunk, n - i * chunk); };
+  // queue the copies of chunk i into buffer i & 1 (its previous user, chunk i - 2, has been aggregated: the caller synchronised)
+  auto issue = [&](long long i) -> int32_t {
+    const long long r0 = i * chunk, rows = rows_of(i);
+    const int b = (int)(i & 1);
+    bool cleared = false;
+    for (auto& sc : cols) {
+      const bool bits = sc.h->dtype == PDRS_BOOL_BITS;
+      const size_t need = (size_t)(rows + 7) / 8;
+      long long have = 0;
+      if (sc.h->null_bits) have = std::max<long long>(0, std::min<long long>((long long)need, sc.h->null_len - r0 / 8));
+      // a partial last chunk / a short null mask must not see the bits of the chunk that used the buffer before
+      if (rows < chunk || (sc.h->null_bits && (size_t)have < need)) {
+        if (bits) PDRS_CUDA(c, cudaMemsetAsync(sc.data[b].p, 0, sc.data_cap, c->stream));
+        if (sc.h->null_bits) PDRS_CUDA(c, cudaMemsetAsync(sc.nulls[b].p, 0, sc.null_cap, c->stream));
+        cleared = true;
+      }
+    }
+    if (cleared) PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& sc : cols) {
+      const bool bits = sc.h->dtype == PDRS_BOOL_BITS;
+      const size_t esz = bits ? 0 : (size_t)pdrs_dtype_bytes(sc.h->dtype);
+      const size_t nb = bits ? (size_t)(rows + 7) / 8 : (size_t)rows * esz;
+      const char* src = (const char*)sc.h->data + (bits ? (size_t)(r0 / 8) : (size_t)r0 * esz);
+      PDRS_TRY(pdrs_stage_copy_async(c, sc.data[b].p, src, nb));
+      if (sc.h->null_bits) {
+        const long long have = std::max<long long>(0, std::min<long long>((rows + 7) / 8, sc.h->null_len - r0 / 8));
+        if (have > 0) PDRS_TRY(pdrs_stage_copy_async(c, sc.nulls[b].p, sc.h->null_bits + r0 / 8, (size_t)have));
+      }
+    }
+    return PDRS_OK;
+  };
+  auto dev_col = [&](const StreamCol& sc, long long i) {
+    pdrs_col d = *sc.h;
+    const int b = (int)(i & 1);
+    d.mem = PDRS_MEM_DEVICE;
+    d.len = rows_of(i);
+    d.data = sc.data[b].p;
+    d.null_bits = sc.h->null_bits ? sc.nulls[b].as<uint8_t>() : nullptr;
+    d.null_len = sc.h->null_bits ? (int64_t)sc.null_cap : 0;
+    return d;
+  };
+
+  // the key layout every chunk's states are packed in: natural widths, a NULL flag for every key part
+  KeySpec ks;
+  {
+    std::vector<ColView> kv(nkeys);
+    for (int k = 0; k < nkeys; k++) { kv[k].dtype = keys[k].dtype; kv[k].len = 0; kv[k].nulls = reinterpret_cast<const uint8_t*>(1); kv[k].null_alias = -1; }
+    PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));
+    for (int k = 0; k < nkeys; k++) { ks.c[k].data = nullptr; ks.c[k].nulls = nullptr; ks.c[k].null_alias = -1; kv[k].nulls = nullptr; }
+  }
+  const int NW = ks.nwords, stride = 5 + 8 * nvs;
+  DevBuf acc;
+  long long acc_rows = 0, acc_cap = 0;
+  auto reserve = [&](long long rows) -> int32_t {
+    if (rows <= acc_cap) return PDRS_OK;
+    const long long ncap = std::max<long long>(rows + rows / 2, 1 << 16);
+    DevBuf nb;
+    PDRS_TRY(nb.alloc(c, (size_t)ncap * stride * 8));
+    if (acc_rows) PDRS_CUDA(c, cudaMemcpyAsync(nb.p, acc.p, (size_t)acc_rows * stride * 8, cudaMemcpyDeviceToDevice, c->stream));
+    acc = std::move(nb);
+    acc_cap = ncap;
+    return PDRS_OK;
+  };
+  auto append = [&](const pdrs_groupby_result* part) -> int32_t {
+    if (part->n_groups == 0) return PDRS_OK;
+    PDRS_TRY(reserve(acc_rows + part->n_groups));
+    DistPack pk{};
+    pk.ks = ks; pk.nvals = nvs; pk.G = part->n_groups; pk.cap = part->n_groups; pk.stride = stride; pk.world = 1; pk.rows = part->rows.as<long long>();
+    for (int k = 0; k < nkeys; k++) { pk.key_vals[k] = part->key_vals[k].p; pk.key_null[k] = part->key_nulls[k].as<uint8_t>(); }
+    for (int v = 0; v < nvs; v++) pk.states[v] = part->states[v].as<u64>();
+    PDRS_TRY(dist_pack_launch<3>(c, NW, pk, acc.as<u64>() + acc_rows * stride, nullptr, nullptr));
+    acc_rows += part->n_groups;
+    return PDRS_OK;
+  };
+  // merge the appended rows: `fin` = with the caller's aggregates (the result), else states only (compaction)
+  auto merge = [&](bool fin, pdrs_groupby_result* res) -> int32_t {
+    res->ctx = c; res->nkeys = nkeys; res->nvals = nvs; res->naggs = fin ? naggs : 0;
+    for (int k = 0; k < nkeys; k++) res->key_dtype[k] = keys[k].dtype;
+    TableMem tm;
+    std::vector<DevBuf> states(nvs);
+    DistMerge mp{};
+    mp.stride = stride; mp.nvals = nvs;
+    const long long slots = std::max<long long>(1024, pow2ceil(2 * acc_rows + 16));
+    PDRS_TRY(alloc_table(c, slots, NW, &tm));
+    for (int v = 0; v < nvs; v++) { PDRS_TRY(states[v].alloc(c, (size_t)(slots + 1) * sizeof(GState), true)); mp.st[v] = states[v].as<GState>(); }
+    mp.gt = tm.t;
+    mp.buf = acc.as<u64>(); mp.nrows = acc_rows; mp.cap = 0; mp.block = 0;
+    PDRS_TRY(dist_merge_launch(c, NW, mp));
+    return finish_merged(c, ks, tm, states, res->key_dtype, nkeys, nvs, val_is_int.data(), fin ? ag.data() : nullptr, fin ? naggs : 0, res);
+  };
+
+  std::vector<pdrs_col> kc(nkeys), vc(std::max(nvs, 1));
+  pdrs_pred pd{};
+  if (pred) pd = *pred;
+  float kernel_ms = 0;
+  int algo = 0;
+  long long spilled = 0, est = 0, last_groups = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  if (c->opt_timing) { PDRS_CUDA(c, cudaEventCreate(&t0)); PDRS_CUDA(c, cudaEventCreate(&t1)); PDRS_CUDA(c, cudaEventRecord(t0, c->stream)); }
+  struct EvGuard { cudaEvent_t a, b; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{t0, t1};
+  int32_t st = issue(0);
+  for (long long i = 0; i < nchunks && st == PDRS_OK; i++) {
+    st = pdrs_stage_join(c, c->stream);                       // chunk i is on its way; the aggregation below is ordered behind it
+    if (st == PDRS_OK && i + 1 < nchunks) st = issue(i + 1);  // chunk i + 1 travels while chunk i is aggregated
+    if (st != PDRS_OK) break;
+    int j = 0;
+    for (int k = 0; k < nkeys; k++) kc[k] = dev_col(cols[j++], i);
+    for (int v = 0; v < nvs; v++) vc[v] = dev_col(cols[j++], i);
+    pdrs_col fc{};
+    if (filter) fc = dev_col(cols[j++], i);
+    if (pred) pd.col = dev_col(cols[j++], i);
+    pdrs_groupby_result* part = nullptr;
+    st = groupby_run(c, kc.data(), nkeys, vc.data(), nvs, nullptr, 0, filter ? &fc : nullptr, MODE_PARTIAL, all_stats ? 1 : 0, &part, pred ? &pd : nullptr);
+    if (st != PDRS_OK) break;
+    kernel_ms += c->stats.main_kernel_ms; algo = c->stats.groupby_algo_used; spilled += c->stats.spilled_rows; est = std::max<long long>(est, c->stats.est_groups);
+    last_groups = part->n_groups;
+    st = append(part);
+    cudaStreamSynchronize(c->stream);       // the buffers of chunk i are free again (and `part` may go)
+    delete part;
+    // compaction: the appended rows are re-merged into one row per group once they outgrow the groups
+    if (st == PDRS_OK && i + 1 < nchunks && acc_rows > std::max<long long>(4 * last_groups, c->opt_stream_compact_rows)) {
+      pdrs_groupby_result tmp;
+      st = merge(false, &tmp);
+      if (st == PDRS_OK) { acc_rows = 0; st = append(&tmp); cudaStreamSynchronize(c->stream); }
+    }
+  }
+  if (st != PDRS_OK) { pdrs_stage_join(c, c->stream); cudaStreamSynchronize(c->stream); return st; }
+  auto* res = new pdrs_groupby_result();
+  st = merge(true, res);
+  if (st != PDRS_OK) { delete res; return st; }
+  // the caller's value column numbering
+  if (nvs != nvals) {
+    DevBuf vn[PDRS_MAX_VALS], vs[PDRS_MAX_VALS];
+    for (int v = 0; v < nvals; v++) if (vmap[v] >= 0) { vn[v] = std::move(res->validn[vmap[v]]); vs[v] = std::move(res->states[vmap[v]]); }
+    for (int v = 0; v < PDRS_MAX_VALS; v++) { res->validn[v] = std::move(vn[v]); res->states[v] = std::move(vs[v]); }
+  }
+  res->nvals = nvals;
+  c->stats.main_kernel_ms = kernel_ms; c->stats.groupby_algo_used = algo; c->stats.spilled_rows = spilled; c->stats.est_groups = est;
+  if (c->opt_timing) {
+    PDRS_CUDA(c, cudaEventRecord(t1, c->stream));
+    PDRS_CUDA(c, cudaEventSynchronize(t1));
+    PDRS_CUDA(c, cudaEventElapsedTime(&c->stats.total_ms, t0, t1));
+  }
+  *out = res;
   return PDRS_OK;
 }
 

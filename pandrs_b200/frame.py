@@ -7,6 +7,8 @@ methods that would call the C ABI:
   LazyFrame::aggregate(...).execute()                     src/optimized/lazy.rs:186-404
   OptimizedDataFrame::inner_join / left_join              split_dataframe/join.rs:32-47, 76-555
   OptimizedDataFrame::filter                              split_dataframe/data_ops.rs:37-121
+  OptimizedDataFrame::par_groupby                         split_dataframe/group/grouping.rs:124-331
+  ArrowConverter::record_batch_to_dataframe               src/arrow_integration.rs:75-100, 160-225 (typed columns of this path)
 
 Every compute step (grouping, aggregation, build / probe, gathers, filter indices) runs in libpandrs_b200.so;
 this module only does what the Rust side does around the shim: schema checks, key re-stringification, result
@@ -50,11 +52,12 @@ class InconsistentRowCount(ValueError):
 
 # ---------------------------------------------------------------- enums
 class AggregateOp:
-    """group/types.rs:11-34.  Median / First / Last / Custom are outside the accelerated path (no CPU fallback)."""
+    """group/types.rs:11-34, same discriminants.  Median / First / Last are computed from the row lists of the groups
+    (pdrs_groupby_rows + pdrs_group_rows_agg); Custom needs a host closure and is outside the accelerated path (no CPU fallback)."""
     Sum, Mean, Min, Max, Count, Std, Var = N.SUM, N.MEAN, N.MIN, N.MAX, N.COUNT, N.STD, N.VAR
-    Median, First, Last, Custom = 100, 101, 102, 103
+    Median, First, Last, Custom = N.MEDIAN, N.FIRST, N.LAST, 10
     NAMES = {N.SUM: "sum", N.MEAN: "mean", N.MIN: "min", N.MAX: "max", N.COUNT: "count", N.STD: "std", N.VAR: "var",
-             100: "median", 101: "first", 102: "last", 103: "custom"}
+             N.MEDIAN: "median", N.FIRST: "first", N.LAST: "last", 10: "custom"}
 
 
 class JoinType:
@@ -99,12 +102,23 @@ class _TypedColumn:
     def __init__(self, raw: RawColumn, nulls: Optional[np.ndarray]):
         self.raw = raw
         self.nulls = nulls          # bool flags or None
+        self._packed = None         # columns built from packed buffers (Arrow ingest): the pandrs null mask itself
 
     def __len__(self):
         return self.raw.len
 
     def is_null(self, i: int) -> bool:
+        if self._packed is not None:
+            return bool(i // 8 < len(self._packed) and (self._packed[i // 8] >> (i % 8)) & 1)
         return bool(self.nulls is not None and i < len(self.nulls) and self.nulls[i])
+
+    @classmethod
+    def _from_buffers(cls, dtype, data, packed_nulls, length, **kw):
+        """A column over existing buffers (values / bit-packed Booleans / pool ids + pandrs null mask): nothing is re-packed."""
+        self = cls.__new__(cls)
+        _TypedColumn.__init__(self, RawColumn(dtype, data, packed_nulls, length=length, **kw), None)
+        self._packed = packed_nulls
+        return self
 
 
 class Int64Column(_TypedColumn):
@@ -293,6 +307,108 @@ class OptimizedDataFrame:
 
     par_filter = filter
 
+    # -- par_groupby (grouping.rs:124-331): one sub-frame per group.  Group label: parts joined with "_", NULL -> "NA" (:158-186);
+    #    labels that collide ("a_b" + "c" vs "a" + "b_c", or a literal "NA") share one entry, like the reference's HashMap<String, _>
+    def par_groupby(self, group_by_columns: Sequence[str]) -> Dict[str, "OptimizedDataFrame"]:
+        if isinstance(group_by_columns, str):
+            group_by_columns = [group_by_columns]
+        for c in group_by_columns:
+            if c not in self._cols:
+                raise ColumnNotFound(c)
+        if self._rows == 0:
+            return {}
+        ctx = get_context()
+        kcols = [self._cols[c] for c in group_by_columns]
+        try:
+            gr = ctx.groupby_rows([k.raw for k in kcols])
+        except PandrsError as e:
+            raise OperationFailed(str(e)) from e
+        try:
+            parts = []
+            for i, k in enumerate(kcols):
+                v, isnull = gr.key(i)
+                parts.append([("NA" if s == "NULL" and nl else s) for s, nl in zip(_key_strings(k, v, isnull), isnull)])
+            labels = ["_".join(p) for p in zip(*parts)]
+            off = gr.offsets()
+            # one gather per column over the whole permutation (filter_by_indices, data_ops.rs:124-211); a group is a slice of it
+            gathered = {name: ctx.gather(self._cols[name].raw, gr.ids_dev(), n=gr.n_rows, idx_dev=True) for name in self._order}
+            ids = None
+            out: Dict[str, OptimizedDataFrame] = {}
+            merged: Dict[str, List[int]] = {}
+            for g, lab in enumerate(labels):
+                merged.setdefault(lab, []).append(g)
+            for lab, gs in merged.items():
+                if len(gs) == 1:
+                    sel = slice(int(off[gs[0]]), int(off[gs[0] + 1]))
+                else:                                              # colliding labels: their rows interleave in ascending row order
+                    if ids is None:
+                        ids = gr.ids()
+                    pos = np.concatenate([np.arange(off[g], off[g + 1]) for g in gs])
+                    sel = pos[np.argsort(ids[pos], kind="stable")]
+                sub = OptimizedDataFrame()
+                for name in self._order:
+                    sub.add_column(name, _wrap_gathered(self._cols[name], gathered[name][sel]))
+                out[lab] = sub
+            return out
+        finally:
+            gr.close()
+
+    # -- Arrow ingest (src/arrow_integration.rs:75-100, 160-225): validity bitmaps are converted to pandrs null masks and string
+    #    arrays are dictionary-encoded on the device; only the distinct strings are interned in the pool on the host
+    @staticmethod
+    def from_record_batch(batch) -> "OptimizedDataFrame":
+        import pyarrow as pa
+        ctx = get_context()
+        out = OptimizedDataFrame()
+        for name, arr in zip(batch.schema.names, batch.columns):
+            if isinstance(arr, pa.ChunkedArray):
+                arr = arr.combine_chunks()
+            n, t, bufs = len(arr), arr.type, arr.buffers()
+            validity = None if bufs[0] is None or arr.null_count == 0 else np.frombuffer(bufs[0], np.uint8)
+            packed = None
+            if pa.types.is_int64(t) or pa.types.is_float64(t):
+                if validity is not None:
+                    packed, _ = ctx.arrow_validity_to_nulls(validity, n, arr.offset)
+                dt = np.int64 if pa.types.is_int64(t) else np.float64
+                vals = np.frombuffer(bufs[1], dt)[arr.offset:arr.offset + n] if n else np.empty(0, dt)
+                cls = Int64Column if pa.types.is_int64(t) else Float64Column
+                col = cls._from_buffers(cls.dtype, vals, packed, n)
+                col.values = vals
+            elif pa.types.is_boolean(t):
+                if arr.offset % 8:
+                    arr = pa.concat_arrays([arr])                  # re-aligns the bit-packed values to offset 0
+                    bufs = arr.buffers()
+                    validity = None if bufs[0] is None or arr.null_count == 0 else np.frombuffer(bufs[0], np.uint8)
+                if validity is not None:
+                    packed, _ = ctx.arrow_validity_to_nulls(validity, n, arr.offset)
+                bits = np.frombuffer(bufs[1], np.uint8)[arr.offset // 8:arr.offset // 8 + (n + 7) // 8].copy() if n else np.empty(0, np.uint8)
+                if n % 8:
+                    bits[-1] &= (1 << (n % 8)) - 1
+                col = BooleanColumn._from_buffers(N.BOOL_BITS, bits, packed, n)
+                col.values = np.unpackbits(bits, bitorder="little")[:n].astype(bool)
+            elif pa.types.is_string(t) or pa.types.is_large_string(t):
+                odt = np.int64 if pa.types.is_large_string(t) else np.int32
+                offsets = np.frombuffer(bufs[1], odt)[arr.offset:arr.offset + n + 1] if n else np.zeros(1, odt)
+                data = np.frombuffer(bufs[2], np.uint8) if bufs[2] is not None else np.empty(0, np.uint8)
+                enc = ctx.dict_encode(offsets, data, validity, arr.offset, n)
+                try:
+                    first = enc.first_rows()
+                    raw = data.tobytes()
+                    nullrow = (lambda r: False) if validity is None else (lambda r: not (validity[(arr.offset + r) >> 3] >> ((arr.offset + r) & 7)) & 1)
+                    texts = ["" if nullrow(int(r)) else raw[int(offsets[r]):int(offsets[r + 1])].decode("utf-8") for r in first]
+                    enc.remap([GLOBAL_STRING_POOL.get_or_insert(s) for s in texts])      # local first-occurrence ids -> pool ids, same order
+                    ids = enc.ids()
+                    if validity is not None:
+                        packed = ctx.to_host(enc.nulls_dev(), (n + 7) // 8, np.uint8)
+                finally:
+                    enc.close()
+                col = StringColumn._from_buffers(N.DICT_U32, ids, packed, n, null_alias=GLOBAL_STRING_POOL.index.get("NULL", -1))
+                col.ids = ids
+            else:
+                raise OperationFailed(f"column '{name}': Arrow type {t} has no typed pandrs column on this path")
+            out.add_column(name, col)
+        return out
+
     def _take(self, idx: np.ndarray) -> "OptimizedDataFrame":
         ctx = get_context()
         out = OptimizedDataFrame()
@@ -370,7 +486,10 @@ def _empty_like(col: _TypedColumn) -> _TypedColumn:
 
 def _gathered(ctx: Context, col: _TypedColumn, idx: np.ndarray) -> _TypedColumn:
     """pdrs_gather: idx < 0 or a NULL source value -> the type default, no null mask (join.rs:290-552)."""
-    vals = ctx.gather(col.raw, idx)
+    return _wrap_gathered(col, ctx.gather(col.raw, idx))
+
+
+def _wrap_gathered(col: _TypedColumn, vals: np.ndarray) -> _TypedColumn:
     if col.dtype == N.I64:
         return Int64Column(vals)
     if col.dtype == N.F64:
@@ -427,12 +546,17 @@ def _aggregate(df: OptimizedDataFrame, keys: List[str], aggs: List[AggSpec], mul
     numeric: List[str] = []
     call_pairs: List[Tuple[int, int]] = []
     zero_aggs: List[int] = []
+    rows_aggs: List[int] = []                                      # Median / First / Last: from the row lists (aggregation.rs:585-624, 703-742)
     for i, (col, op, alias) in enumerate(aggs):
         if col not in df._cols:
             raise ColumnNotFound(col)
-        if op not in (N.SUM, N.MEAN, N.MIN, N.MAX, N.COUNT, N.STD, N.VAR) or (allowed_ops is not None and op not in allowed_ops):
+        if op not in (N.SUM, N.MEAN, N.MIN, N.MAX, N.COUNT, N.STD, N.VAR, N.MEDIAN, N.FIRST, N.LAST) or (allowed_ops is not None and op not in allowed_ops):
             raise OperationFailed(f"aggregate op '{AggregateOp.NAMES.get(op, op)}' is outside the accelerated path (no CPU fallback)")
         c = df._cols[col]
+        if op in (N.MEDIAN, N.FIRST, N.LAST) and c.dtype in (N.I64, N.F64):
+            rows_aggs.append(i)
+            call_pairs.append((-1, N.COUNT))
+            continue
         if op == N.COUNT:                                          # group size, NULLs included, any column type (aggregation.rs:743)
             call_pairs.append((-1, N.COUNT))
         elif c.dtype not in (N.I64, N.F64):
@@ -471,6 +595,23 @@ def _aggregate(df: OptimizedDataFrame, keys: List[str], aggs: List[AggSpec], mul
         res.close()
     for i in zero_aggs:
         cols[i] = np.zeros_like(cols[i])
+    if rows_aggs:
+        try:
+            gr = ctx.groupby_rows([k.raw for k in kcols])
+        except PandrsError as e:
+            raise OperationFailed(str(e)) from e
+        try:
+            gk = []
+            for i, k in enumerate(kcols):
+                v, isnull = gr.key(i)
+                gk.append(_key_strings(k, v, isnull))             # the key text identifies a group in both results ("NULL" = the NULL part)
+            where = {kt: g for g, kt in enumerate(zip(*gk))}
+            order = np.array([where[kt] for kt in zip(*key_strs)], dtype=np.int64)
+            for i in rows_aggs:
+                col, op, _ = aggs[i]
+                cols[i] = gr.agg(df._cols[col].raw, op)[order]
+        finally:
+            gr.close()
     out = OptimizedDataFrame()
     if multi_index and len(keys) > 1:                              # aggregation.rs:812-853: keys only in the StringMultiIndex
         out.index = list(zip(*key_strs)) if key_strs else []
