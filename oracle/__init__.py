@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libpandrs_oracle.so")
 
 I64, F64, DICT_U32, BOOL_BITS, I32 = 0, 1, 2, 3, 4
-SUM, MEAN, MIN, MAX, COUNT, STD, VAR = range(7)
+SUM, MEAN, MIN, MAX, COUNT, STD, VAR, MEDIAN, FIRST, LAST = range(10)
 MODE_AGGREGATE, MODE_PAR_AGGREGATE, MODE_LAZY, MODE_EXACT = 0, 1, 2, 3
 INNER, LEFT, RIGHT, OUTER = 0, 1, 2, 3
 
@@ -60,6 +60,16 @@ def lib():
         L.orc_gb_key.restype = C.c_char_p
         L.orc_gb_key.argtypes = [C.c_void_p, C.c_int64, C.c_int]
         L.orc_gb_free.argtypes = [C.c_void_p]
+        L.orc_par_groupby.restype = C.c_void_p
+        L.orc_par_groupby.argtypes = [C.POINTER(_Col), C.c_int, C.c_int64]
+        L.orc_pg_ngroups.restype = C.c_int64
+        L.orc_pg_ngroups.argtypes = [C.c_void_p]
+        L.orc_pg_label.restype = C.c_char_p
+        L.orc_pg_label.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_pg_size.restype = C.c_int64
+        L.orc_pg_size.argtypes = [C.c_void_p, C.c_int64]
+        L.orc_pg_rows.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_pg_free.argtypes = [C.c_void_p]
         L.orc_join.restype = C.c_void_p
         L.orc_join.argtypes = [C.POINTER(_Col), C.POINTER(_Col), C.c_int]
         L.orc_join_len.restype = C.c_int64
@@ -155,6 +165,22 @@ def groupby(keys, vals, aggs, mode=MODE_AGGREGATE, nthreads=1, want_key_strings=
         return dict(n_groups=G, first_row=first, group_rows=rows, aggs=out, key_strings=ks, error=L.orc_gb_error(h))
     finally:
         L.orc_gb_free(h)
+
+
+def par_groupby(keys) -> dict:
+    """grouping.rs:124-331: {label: ascending row ids}; label = key parts joined with "_", NULL -> "NA"."""
+    L = lib()
+    kc = (_Col * max(1, len(keys)))(*[k.c() for k in keys])
+    h = L.orc_par_groupby(kc, len(keys), keys[0].len)
+    try:
+        out = {}
+        for g in range(L.orc_pg_ngroups(h)):
+            rows = np.empty(L.orc_pg_size(h, g), np.int64)
+            L.orc_pg_rows(h, g, rows.ctypes.data)
+            out[L.orc_pg_label(h, g).decode()] = rows
+        return out
+    finally:
+        L.orc_pg_free(h)
 
 
 def join(left: Col, right: Col, how=INNER):

@@ -19,6 +19,7 @@
 //   src/core/column.rs:112-129,163-177        -> col_is_null / get_* (null bit = 1, LSB first,
 //                                                short masks mean "not NULL")
 //   src/optimized/split_dataframe/group/grouping.rs:38-115   -> orc_groupby grouping loop
+//   src/optimized/split_dataframe/group/grouping.rs:124-331  -> orc_par_groupby ("NA" / "_" labels, ascending row lists)
 //   src/optimized/split_dataframe/group/aggregation.rs:500-754,875-903 -> calc_agg / variance
 //   src/optimized/split_dataframe/group/aggregation.rs:22-182,763-871  -> serial / parallel drivers
 //   src/optimized/lazy.rs:186-404                                      -> mode ORC_MODE_LAZY
@@ -41,7 +42,7 @@ extern "C" {
 
 enum { ORC_I64 = 0, ORC_F64 = 1, ORC_DICT_U32 = 2, ORC_BOOL_BITS = 3, ORC_I32 = 4 };
 // AggregateOp discriminants in the order of group/types.rs:11-34
-enum { ORC_SUM = 0, ORC_MEAN = 1, ORC_MIN = 2, ORC_MAX = 3, ORC_COUNT = 4, ORC_STD = 5, ORC_VAR = 6 };
+enum { ORC_SUM = 0, ORC_MEAN = 1, ORC_MIN = 2, ORC_MAX = 3, ORC_COUNT = 4, ORC_STD = 5, ORC_VAR = 6, ORC_MEDIAN = 7, ORC_FIRST = 8, ORC_LAST = 9 };
 enum { ORC_MODE_AGGREGATE = 0, ORC_MODE_PAR_AGGREGATE = 1, ORC_MODE_LAZY = 2,
        // NOT a reference mode: the same grouping, but f64 Sum / Mean / Std / Var accumulated in 80-bit long double (two-pass
        // variance).  tests/_util.py uses it to measure the reference's OWN rounding error, so that the 1e-12 tolerance can be
@@ -191,6 +192,15 @@ double calc_agg(const orc_col& col, int op, const std::vector<size_t>& rows, boo
       case ORC_STD: case ORC_VAR: {
         std::vector<double> v; for (size_t i : rows) if (!col_is_null(col, i)) v.push_back((double)get(i));
         if (v.empty()) return 0.0; double var = calculate_variance(v); return op == ORC_STD ? std::sqrt(var) : var; }                // :557-584
+      case ORC_MEDIAN: {                                                                                                            // :585-604
+        std::vector<int64_t> v; for (size_t i : rows) if (!col_is_null(col, i)) v.push_back(get(i));
+        if (v.empty()) return 0.0;
+        std::sort(v.begin(), v.end());
+        size_t mid = v.size() / 2;
+        if (v.size() % 2 == 0) return (double)(int64_t)((uint64_t)v[mid - 1] + (uint64_t)v[mid]) / 2.0;   // i64 add (wrapping in a release build), then as f64 / 2.0
+        return (double)v[mid]; }
+      case ORC_FIRST: { if (rows.empty()) return 0.0; size_t i = rows.front(); return col_is_null(col, i) ? 0.0 : (double)get(i); }  // :605-614
+      case ORC_LAST: { if (rows.empty()) return 0.0; size_t i = rows.back(); return col_is_null(col, i) ? 0.0 : (double)get(i); }    // :615-624
     }
   } else if (col.dtype == ORC_F64) {
     const double* d = (const double*)col.data;
@@ -202,6 +212,15 @@ double calc_agg(const orc_col& col, int op, const std::vector<size_t>& rows, boo
       case ORC_STD: case ORC_VAR: {
         std::vector<double> v; for (size_t i : rows) if (!col_is_null(col, i)) v.push_back(d[i]);
         if (v.empty()) return 0.0; double var = calculate_variance(v); return op == ORC_STD ? std::sqrt(var) : var; }                // :675-702
+      case ORC_MEDIAN: {                                                                                                            // :703-722
+        std::vector<double> v; for (size_t i : rows) if (!col_is_null(col, i)) v.push_back(d[i]);
+        if (v.empty()) return 0.0;
+        std::stable_sort(v.begin(), v.end());           // sort_by(partial_cmp().unwrap_or(Equal)): a total order only without NaN
+        size_t mid = v.size() / 2;
+        if (v.size() % 2 == 0) return (v[mid - 1] + v[mid]) / 2.0;
+        return v[mid]; }
+      case ORC_FIRST: { if (rows.empty()) return 0.0; size_t i = rows.front(); return col_is_null(col, i) ? 0.0 : d[i]; }            // :723-732
+      case ORC_LAST: { if (rows.empty()) return 0.0; size_t i = rows.back(); return col_is_null(col, i) ? 0.0 : d[i]; }              // :733-742
     }
   }
   *ok = false;  // :748-752  String/Boolean value columns support Count only
@@ -271,6 +290,32 @@ void orc_gb_group_rows(void* h, int64_t* out) { auto* r = (GroupByResult*)h; std
 void orc_gb_agg(void* h, int a, double* out) { auto* r = (GroupByResult*)h; std::copy(r->aggs[a].begin(), r->aggs[a].end(), out); }
 const char* orc_gb_key(void* h, int64_t g, int k) { return ((GroupByResult*)h)->keys[g][k].c_str(); }
 void orc_gb_free(void* h) { delete (GroupByResult*)h; }
+
+// grouping.rs:124-331 (par_groupby): label = parts joined with "_", NULL -> "NA" (:158-186); rows pushed in row order (the parallel
+// branch merges its chunk maps in chunk order, :265-282, so the lists are ascending too).  Groups in first-appearance order.
+struct ParGroups { std::vector<std::string> labels; std::vector<std::vector<int64_t>> rows; };
+void* orc_par_groupby(const orc_col* keys, int nkeys, int64_t nrows) {
+  auto* res = new ParGroups();
+  std::unordered_map<std::string, size_t, StrHash> index;
+  for (int64_t row = 0; row < nrows; row++) {
+    std::string label;
+    for (int k = 0; k < nkeys; k++) {
+      if (k) label += "_";
+      label += col_is_null(keys[k], row) ? std::string("NA") : key_part(keys[k], row);
+    }
+    auto it = index.find(label);
+    size_t g;
+    if (it == index.end()) { g = res->labels.size(); index.emplace(label, g); res->labels.push_back(label); res->rows.emplace_back(); }
+    else g = it->second;
+    res->rows[g].push_back(row);
+  }
+  return res;
+}
+int64_t orc_pg_ngroups(void* h) { return (int64_t)((ParGroups*)h)->labels.size(); }
+const char* orc_pg_label(void* h, int64_t g) { return ((ParGroups*)h)->labels[g].c_str(); }
+int64_t orc_pg_size(void* h, int64_t g) { return (int64_t)((ParGroups*)h)->rows[g].size(); }
+void orc_pg_rows(void* h, int64_t g, int64_t* out) { auto& r = ((ParGroups*)h)->rows[g]; std::copy(r.begin(), r.end(), out); }
+void orc_pg_free(void* h) { delete (ParGroups*)h; }
 
 // join.rs:107-224.  Pairs in reference order: left-row-major, matches in ascending right row,
 // then (Right/Outer) unmatched right rows.  -1 stands for None.

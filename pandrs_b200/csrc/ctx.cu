@@ -286,7 +286,13 @@ int32_t pdrs_view_col(pdrs_ctx* c, const pdrs_col* col, ColView* v) {
   }
   int64_t nb = col->dtype == PDRS_BOOL_BITS ? need : col->len * (int64_t)pdrs_dtype_bytes(col->dtype);
   PDRS_TRY(v->own_data.alloc(c, (size_t)nb + 64, col->dtype == PDRS_BOOL_BITS));
-  if (nb) PDRS_CUDA(c, cudaMemcpyAsync(v->own_data.p, col->data, nb, cudaMemcpyHostToDevice, c->stream));
+  if (nb >= (64ll << 20) && c->opt_stage_threads >= 0) {
+    // large host column: through the staging engine (stage.cu) - a pageable source moves at PCIe speed instead of the driver's
+    // ~11 GB/s bounce path.  The stream-ordered allocation must exist before other streams write into it.
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    PDRS_TRY(pdrs_stage_copy_async(c, v->own_data.p, col->data, (size_t)nb));
+    PDRS_TRY(pdrs_stage_join(c, c->stream));
+  } else if (nb) PDRS_CUDA(c, cudaMemcpyAsync(v->own_data.p, col->data, nb, cudaMemcpyHostToDevice, c->stream));
   v->data = v->own_data.p;
   if (col->null_bits) {
     PDRS_TRY(v->own_nulls.alloc(c, (size_t)need + 64, true));

@@ -964,7 +964,7 @@ static int32_t finish_merged(pdrs_ctx* c, const KeySpec& ks, TableMem& tm, std::
 
 static bool stream_eligible(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_col* filter, const pdrs_pred* pred);
 static int32_t groupby_stream(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_agg* aggs, int32_t naggs,
-                              const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out);
+                              const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out, int partial = 0);
 
 extern "C" {
 
@@ -1200,8 +1200,11 @@ struct StreamCol {              // one host column and its two device chunk buff
 };
 }  // namespace
 
+// partial: 0 = the caller's aggregates; 1 / 2 = mergeable states of ALL value columns instead ({rows, n, sum} / everything), the
+// result pdrs_groupby_partial would give (used by pdrs_groupby_agg_dist for its local step)
 static int32_t groupby_stream(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, const pdrs_col* vals, int32_t nvals, const pdrs_agg* aggs, int32_t naggs,
-                              const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out) {
+                              const pdrs_col* filter, const pdrs_pred* pred, pdrs_groupby_result** out, int partial) {
+  if (partial) { aggs = nullptr; naggs = 0; }
   if (!out || naggs < 0 || naggs > PDRS_MAX_AGGS || (naggs && !aggs)) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby: bad argument");
   PDRS_CUDA(c, cudaSetDevice(c->device));
   const int64_t n = keys[0].len;
@@ -1219,6 +1222,13 @@ static int32_t groupby_stream(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, 
   // only the value columns an aggregate reads travel
   std::vector<int> vmap(nvals, -1);
   std::vector<const pdrs_col*> used;
+  if (partial) {
+    all_stats = partial == 2;
+    for (int v = 0; v < nvals; v++) {
+      if (vals[v].dtype != PDRS_I64 && vals[v].dtype != PDRS_F64) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "partial aggregation needs Int64/Float64 value columns");
+      vmap[v] = v; used.push_back(&vals[v]);
+    }
+  }
   for (int a = 0; a < naggs; a++) if (aggs[a].op != PDRS_COUNT && vmap[aggs[a].value_col] < 0) { vmap[aggs[a].value_col] = (int)used.size(); used.push_back(&vals[aggs[a].value_col]); }
   const int nvs = (int)used.size();
   std::vector<pdrs_agg> ag(aggs, aggs + naggs);
@@ -1379,7 +1389,7 @@ static int32_t groupby_stream(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, 
   }
   if (st != PDRS_OK) { pdrs_stage_join(c, c->stream); cudaStreamSynchronize(c->stream); return st; }
   auto* res = new pdrs_groupby_result();
-  st = merge(true, res);
+  st = merge(!partial, res);
   if (st != PDRS_OK) { delete res; return st; }
   // the caller's value column numbering
   if (nvs != nvals) {
@@ -1422,7 +1432,10 @@ extern "C" int32_t pdrs_groupby_agg_dist(pdrs_comm* cm, const pdrs_col* keys, in
   const int nvs = (int)nv.size();
   // ---- local partial aggregation (every rank; the kernels of pdrs_groupby_partial)
   pdrs_groupby_result* part = nullptr;
-  PDRS_TRY(groupby_run(c, keys, nkeys, nv.data(), nvs, nullptr, 0, filter, MODE_PARTIAL, all_stats ? 1 : 0, &part, pred));
+  if (stream_eligible(c, keys, nkeys, nv.data(), nvs, filter, pred))      // host shards: chunk by chunk through the staging engine
+    PDRS_TRY(groupby_stream(c, keys, nkeys, nv.data(), nvs, nullptr, 0, filter, pred, &part, all_stats ? 2 : 1));
+  else
+    PDRS_TRY(groupby_run(c, keys, nkeys, nv.data(), nvs, nullptr, 0, filter, MODE_PARTIAL, all_stats ? 1 : 0, &part, pred));
   struct PartGuard { pdrs_groupby_result* r; ~PartGuard() { if (r) { cudaSetDevice(r->ctx->device); delete r; } } } pguard{part};
   const float local_ms = c->stats.main_kernel_ms;
   const int local_algo = c->stats.groupby_algo_used;

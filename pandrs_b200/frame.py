@@ -16,6 +16,7 @@ frame assembly.  There is no CPU fallback: unsupported operations raise Operatio
 """
 from __future__ import annotations
 
+import copy
 from typing import Dict, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -319,8 +320,13 @@ class OptimizedDataFrame:
             return {}
         ctx = get_context()
         kcols = [self._cols[c] for c in group_by_columns]
+        raws = []
+        for k in kcols:                                            # a literal "NULL" string is its own group here (only group_by merges it)
+            r = copy.copy(k.raw)
+            r.null_alias = -1
+            raws.append(r)
         try:
-            gr = ctx.groupby_rows([k.raw for k in kcols])
+            gr = ctx.groupby_rows(raws)
         except PandrsError as e:
             raise OperationFailed(str(e)) from e
         try:

@@ -399,3 +399,38 @@ def test_compare_groupby_typed_helper_on_a_mock_result(oracle):
         compare_groupby_typed(pbn, m, tg, [pbn.I32, pbn.I64], ops)
     import _util
     _util.MEASURED.clear()          # a mock is not a measurement of the CUDA path
+
+
+# ---------------------------------------------------------------- par_groupby / Median / First / Last (pinned by restatement)
+def test_par_groupby_labels_and_row_lists(oracle):
+    # grouping.rs:124-331: label = parts joined with "_", NULL -> "NA"; rows ascending.  The fixtures of
+    # tests/optimized_groupby_test.rs:6-31, 138-171 (the reference asserts only "not empty" there)
+    pool = ["A", "B", "C"]
+    g = oracle.par_groupby([oracle.Col(oracle.DICT_U32, np.array([0, 1, 0, 1, 2], np.uint32), pool=pool)])
+    assert {k: list(v) for k, v in g.items()} == {"A": [0, 2], "B": [1, 3], "C": [4]}
+    pool = ["X", "Y", "A", "B"]
+    g = oracle.par_groupby([oracle.Col(oracle.DICT_U32, np.array([0, 0, 1, 1, 0, 1], np.uint32), pool=pool),
+                            oracle.Col(oracle.DICT_U32, np.array([2, 3, 2, 3, 2, 3], np.uint32), pool=pool)])
+    assert {k: list(v) for k, v in g.items()} == {"X_A": [0, 4], "X_B": [1], "Y_A": [2], "Y_B": [3, 5]}
+    # NULL -> "NA"; a literal "NULL" string stays its own group; ("a_b", "c") and ("a", "b_c") collide
+    pool = ["a_b", "c", "a", "b_c", "NULL"]
+    k0 = oracle.Col(oracle.DICT_U32, np.array([0, 2, 4, 4], np.uint32), oracle.pack_bits([False, False, False, True]), pool=pool)
+    k1 = oracle.Col(oracle.DICT_U32, np.array([1, 3, 1, 1], np.uint32), pool=pool)
+    g = oracle.par_groupby([k0, k1])
+    assert {k: list(v) for k, v in g.items()} == {"a_b_c": [0, 1], "NULL_c": [2], "NA_c": [3]}
+
+
+def test_median_first_last_semantics(oracle):
+    # aggregation.rs:585-624 (Int64), 703-742 (Float64): NULLs are skipped by Median, First / Last look at the row itself
+    k = oracle.Col(oracle.I64, np.array([1, 1, 1, 1, 2, 2, 3], np.int64))
+    v = oracle.Col(oracle.I64, np.array([7, 1, 5, 3, 10, 4, 9], np.int64), oracle.pack_bits([False, False, False, True, True, False, True]))
+    f = oracle.Col(oracle.F64, np.array([0.5, 2.5, 1.5, 9.0, 4.0, 8.0, 1.0]))
+    r = oracle.groupby([k], [v, f], [(0, oracle.MEDIAN), (0, oracle.FIRST), (0, oracle.LAST), (1, oracle.MEDIAN), (1, oracle.FIRST), (1, oracle.LAST)])
+    assert r["error"] == 0 and r["key_strings"] == [("1",), ("2",), ("3",)]
+    assert [list(a) for a in r["aggs"]] == [[5.0, 4.0, 0.0], [7.0, 0.0, 0.0], [0.0, 4.0, 0.0], [2.0, 6.0, 1.0], [0.5, 4.0, 1.0], [9.0, 8.0, 1.0]]
+    # even count: (values[mid - 1] + values[mid]) as f64 / 2.0 with the i64 sum computed first
+    big = np.iinfo(np.int64).max
+    r = oracle.groupby([oracle.Col(oracle.I64, np.zeros(2, np.int64))], [oracle.Col(oracle.I64, np.array([big, big], np.int64))], [(0, oracle.MEDIAN)])
+    assert r["aggs"][0][0] == -1.0          # wrapping add (release build), then / 2.0
+    s = oracle.Col(oracle.DICT_U32, np.zeros(2, np.uint32))
+    assert oracle.groupby([oracle.Col(oracle.I64, np.zeros(2, np.int64))], [s], [(0, oracle.MEDIAN)])["error"] == 1     # aggregation.rs:748-752
