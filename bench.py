@@ -65,6 +65,7 @@ class ClockSampler:
     def __init__(self, index=0):
         self.samples, self.proc, self.index, self.t0, self.t1 = [], None, index, None, None
         self.stop_flag, self.thread, self.how = False, None, None
+        self.period = 0.025          # seconds between samples; timed_region() stretches it to 10 steps for long, driver-call-heavy steps
 
     def start(self):
         try:
@@ -76,14 +77,20 @@ class ClockSampler:
             mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
             def loop():
+                # An NVML query holds a driver lock that CUDA calls of this process (allocations, launches) wait for: the
+                # sampler keeps its duty cycle under 5% (a query was measured to stall an allocation-heavy join step by tens of ms
+                # when issued every 25 ms regardless of its own duration)
                 while not self.stop_flag:
+                    t = time.perf_counter()
                     try:
                         sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
                         rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
                         self.samples.append((time.perf_counter(), sm, mx, {k for k, b in self.BITS.items() if rs & b}))
                     except Exception:
                         pass
-                    time.sleep(0.025)
+                    took = time.perf_counter() - t
+                    self.query_ms = max(getattr(self, "query_ms", 0.0), took * 1e3)
+                    time.sleep(max(self.period, 20.0 * took))
             self.thread = threading.Thread(target=loop, daemon=True)
             self.thread.start()
             self.how = "NVML, 25 ms"
@@ -135,7 +142,8 @@ class ClockSampler:
             where = "whole run (timed region shorter than one sample)"
         sm.sort()
         hi = [x for x in sm if x > 0.5 * mx] or sm
-        return {"sm_mhz": hi[len(hi) // 2] if hi else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": where, "sampler": self.how}
+        return {"sm_mhz": hi[len(hi) // 2] if hi else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "window": where, "sampler": (self.how or "").replace("25 ms", "%d ms" % round(self.period * 1e3)),
+                "sampler_query_ms_max": round(getattr(self, "query_ms", 0.0), 3)}
 
 
 # ---------------------------------------------------------------- the reference arm / CPU baselines (oracle/ = the checker, timed here only)
@@ -290,23 +298,31 @@ def timed_region(env, step, warmup, steps, stats_key="main_kernel_ms"):
     clocks = ClockSampler(env.local)
     if env.rank == 0:
         clocks.start()
+    tw = 0.0
     for _ in range(warmup):
+        tw = time.perf_counter()
         step()
+        tw = time.perf_counter() - tw
+    clocks.period = min(0.25, max(0.025, 10.0 * tw))       # (measured: at 25 ms the queries made a 19 ms join step take 30 - 80 ms)
     launches0 = env.ctx.stats()["kernel_launches"]
     env.barrier()
     clocks.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
+    kms, walls = [], []
     e0.record(env.stream)
     for _ in range(steps):
+        tw = time.perf_counter()
         step()
         kms.append(env.ctx.stats()[stats_key])
+        walls.append((time.perf_counter() - tw) * 1e3)
     e1.record(env.stream)
     env.barrier()
     clocks.mark_end()
     ms = env.max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop() if env.rank == 0 else None
     launches = (env.ctx.stats()["kernel_launches"] - launches0) // max(steps, 1)
+    if walls:
+        log("host wall clock per step (ms): min %.3f  median %.3f  max %.3f" % (min(walls), sorted(walls)[len(walls) // 2], max(walls)))
     return ms / steps, sum(kms) / max(len(kms), 1), int(launches), clk
 
 
@@ -951,6 +967,7 @@ def extras_c4_c5(ctx, pb, peak, timed, scale=1.0):
     k3 = zipf(n, 10_000, torch.int32)           # dictionary ids over a 10,000-string pool (u32, same bits)
     v = uniform(n, 0.0, 1000.0)
     torch.cuda.current_stream(dev).synchronize()
+    torch.cuda.empty_cache()                    # the generator's temporaries go back to the driver (the library checks what it can still allocate)
     aggs6 = [(0, op) for op in ALL6]
     run("c4_dict_key_zipf", [col(pb.DICT_U32, k3)], [col(pb.F64, v)], aggs6, n * 12.0, n)
     run("c4_i32_i64_keys_zipf", [col(pb.I32, k1), col(pb.I64, k2)], [col(pb.F64, v)], aggs6, n * 20.0, n)

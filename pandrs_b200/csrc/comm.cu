@@ -9,6 +9,7 @@
 // stable C entry points are used; their prototypes are restated here (nccl.h 2.x).
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -159,12 +160,53 @@ int32_t pdrs_comm_barrier(pdrs_comm* cm) {
 // Every rank passes its shard of both key columns and the global number of its first row on each side; rank r returns the
 // pairs of the keys whose rank hash maps to r, in GLOBAL row numbers.  max_* describe the largest shard of any rank (same
 // values on every rank): the receive areas are allocated for them once and reused by later calls.
+static int32_t join_pairs_dist_round(pdrs_comm* cm, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, int64_t left_row0, int64_t right_row0,
+                                     int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result** out);
+
 int32_t pdrs_join_pairs_dist(pdrs_comm* cm, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, int64_t left_row0, int64_t right_row0,
                              int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result** out) {
   if (!cm) return PDRS_ERR_BAD_ARG;
   pdrs_ctx* c = cm->ctx;
   if (!left_key || !right_key || !out) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_pairs_dist: NULL argument");
   if (how != PDRS_INNER && how != PDRS_LEFT) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_join_pairs_dist: only Inner and Left joins are sharded");
+  if (left_key->len > max_left_rows || max_left_rows < 0) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_pairs_dist: %lld left rows exceed max_left_rows = %lld", (long long)left_key->len, (long long)max_left_rows);
+  // The staged exchange (line-aligned peer stores at ~80% of the NVLink peak) carries a left row as (source rank << s | local row) in 32
+  // bits, s = 32 - log2(ranks): larger shards are joined in ROUNDS of < 2^s left rows each against the same build side (the
+  // probe rows of a join are independent of each other; the build side - the small one - is shuffled again per round).
+  int log_world = 0;
+  while ((1 << log_world) < cm->world) log_world++;
+  int64_t lim = (1ll << (32 - log_world)) - 64;
+  if (c->opt_xjoin_round_rows > 0) lim = std::min<int64_t>(lim, std::max<int64_t>(64, c->opt_xjoin_round_rows));
+  int rounds = 1;
+  if ((cm->world > 1 && c->opt_xjoin_mode != 1) || c->opt_xjoin_round_rows > 0) while ((max_left_rows + rounds - 1) / rounds > lim) rounds++;
+  if (rounds == 1) return join_pairs_dist_round(cm, left_key, right_key, how, left_row0, right_row0, max_left_rows, max_right_rows, total_right_rows, out);
+  const int64_t chunk = ((max_left_rows + rounds - 1) / rounds + 63) / 64 * 64;       // bitmap bytes and 128-bit loads stay aligned
+  std::vector<pdrs_join_result*> parts;
+  float ex_ms = 0.f;
+  int64_t ex_bytes = 0;
+  int32_t rc = PDRS_OK;
+  for (int r = 0; r < rounds && rc == PDRS_OK; r++) {
+    const int64_t lo = std::min<int64_t>(left_key->len, r * chunk), hi = std::min<int64_t>(left_key->len, lo + chunk);
+    pdrs_col sl = *left_key;
+    sl.len = hi - lo;
+    sl.data = (const char*)left_key->data + (left_key->dtype == PDRS_BOOL_BITS ? lo / 8 : lo * (int64_t)pdrs_dtype_bytes(left_key->dtype));
+    if (left_key->null_bits) {
+      const int64_t have = std::max<int64_t>(0, left_key->null_len - lo / 8);
+      sl.null_bits = have > 0 ? left_key->null_bits + lo / 8 : nullptr;
+      sl.null_len = have;
+    }
+    pdrs_join_result* part = nullptr;
+    rc = join_pairs_dist_round(cm, &sl, right_key, how, left_row0 + lo, right_row0, chunk, max_right_rows, total_right_rows, &part);   // collective: every rank runs every round
+    if (rc == PDRS_OK) { parts.push_back(part); ex_ms += cm->last_exchange_ms; ex_bytes += cm->last_exchange_bytes; }
+  }
+  if (rc != PDRS_OK) { for (auto* p : parts) pdrs_join_result_free(p); return rc; }
+  cm->last_exchange_ms = ex_ms; cm->last_exchange_bytes = ex_bytes;
+  return pdrs_join_result_concat(c, parts.data(), (int)parts.size(), out);
+}
+
+static int32_t join_pairs_dist_round(pdrs_comm* cm, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, int64_t left_row0, int64_t right_row0,
+                                     int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result** out) {
+  pdrs_ctx* c = cm->ctx;
   PDRS_CUDA(c, cudaSetDevice(c->device));
   if (!cm->xj || cm->xj_left != max_left_rows || cm->xj_right != max_right_rows || cm->xj_total_right != total_right_rows) {
     if (cm->xj) { PDRS_TRY(pdrs_comm_barrier(cm)); pdrs_xjoin_destroy(cm->xj); cm->xj = nullptr; }

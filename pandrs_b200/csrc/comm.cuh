@@ -24,3 +24,6 @@ int32_t pdrs_comm_alltoallv(pdrs_comm* cm, const void* send, const size_t* send_
                             const size_t* recv_bytes);
 // host-visible all-gather of a few bytes per rank (device staging + one stream synchronisation): the "everybody agrees" step
 int32_t pdrs_comm_allgather_host(pdrs_comm* cm, const void* mine, void* all, size_t bytes_per_rank);
+
+struct pdrs_join_result;
+int32_t pdrs_join_result_concat(pdrs_ctx* c, pdrs_join_result** parts, int n, pdrs_join_result** out);   // join.cu

@@ -68,12 +68,19 @@ struct pdrs_ctx {
   int64_t opt_stream_rows = 1 << 25;   // groupby over HOST columns with at least this many rows runs chunk by chunk (0 = never)
   int64_t opt_stream_chunk_rows = 0;   // rows per chunk of that path (0 = default 2^26)
   int64_t opt_stream_compact_rows = 1 << 22;   // ... appended state rows beyond which (and beyond 4x the groups of a chunk) they are re-merged
+  int64_t opt_xjoin_round_rows = 0;    // pdrs_join_pairs_dist: left rows per round (0 = as many as the staged row encoding allows)
+  int64_t opt_trace = 0;               // 1: print host-clock phase marks of the collective operators to stderr (each mark synchronises the stream)
+  double trace_t0 = 0.0;
   PdrsStager* stager = nullptr;
 };
+void pdrs_trace(pdrs_ctx* c, const char* label);     // ctx.cu; no-op unless opt_trace
 
 int32_t pdrs_fail(pdrs_ctx* ctx, int32_t code, const char* fmt, ...);
 // stage.cu: asynchronous host -> device copies through a pool of staging threads (pageable sources) / direct DMA (pinned sources)
-int32_t pdrs_stage_copy_async(pdrs_ctx* c, void* dst_dev, const void* src_host, size_t bytes);
+// d2h = 1: the other direction (dst = host, src = device); the data is in place after pdrs_stage_join + a stream synchronisation
+int32_t pdrs_stage_copy_async(pdrs_ctx* c, void* dst, const void* src, size_t bytes, int d2h = 0);
+// device -> host copy of a finished result: through the staging engine when large, plain cudaMemcpyAsync otherwise; returns synchronised
+int32_t pdrs_copy_to_host(pdrs_ctx* c, void* dst_host, const void* src_dev, size_t bytes);
 int32_t pdrs_stage_join(pdrs_ctx* c, cudaStream_t consumer);
 void pdrs_stage_destroy(pdrs_ctx* c);
 
@@ -118,6 +125,9 @@ struct ColView {
 };
 int32_t pdrs_view_col(pdrs_ctx* ctx, const pdrs_col* c, ColView* out);
 int pdrs_dtype_bytes(int32_t dtype);
+// device memory a stream-ordered allocation can still get: what the driver reports free PLUS what the context's memory pool holds
+// in reserve (blocks freed by earlier calls stay cached in the pool and do not show up as free)
+int32_t pdrs_mem_available(pdrs_ctx* c, size_t* bytes);
 int pdrs_grid_for(pdrs_ctx* c, int64_t n, int threads);
 
 // ---- device helpers ----

@@ -2,6 +2,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 
 #include "common.cuh"
 
@@ -15,6 +16,41 @@ int32_t pdrs_fail(pdrs_ctx* ctx, int32_t code, const char* fmt, ...) {
   va_end(ap);
   if (ctx) ctx->err = buf; else g_create_err = buf;
   return code;
+}
+
+void pdrs_trace(pdrs_ctx* c, const char* label) {
+  if (!c || !c->opt_trace) return;
+  cudaStreamSynchronize(c->stream);
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  const double t = ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+  if (label) fprintf(stderr, "[pdrs trace] %-34s %8.3f ms\n", label, t - c->trace_t0);
+  c->trace_t0 = t;
+}
+
+int32_t pdrs_mem_available(pdrs_ctx* c, size_t* bytes) {
+  size_t free_b = 0, total_b = 0;
+  PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+    uint64_t reserved = 0, used = 0;
+    if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+      free_b += (size_t)(reserved - used);
+  } else cudaGetLastError();
+  *bytes = free_b;
+  return PDRS_OK;
+}
+
+int32_t pdrs_copy_to_host(pdrs_ctx* c, void* dst_host, const void* src_dev, size_t bytes) {
+  if (bytes == 0) return PDRS_OK;
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));           // the result is complete before other streams read it
+  if (bytes >= (64ull << 20) && c->opt_stage_threads >= 0) {
+    PDRS_TRY(pdrs_stage_copy_async(c, dst_host, src_dev, bytes, 1));
+    PDRS_TRY(pdrs_stage_join(c, c->stream));
+  } else PDRS_CUDA(c, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  return PDRS_OK;
 }
 
 int pdrs_dtype_bytes(int32_t dtype) {
@@ -145,6 +181,8 @@ int32_t pdrs_set_option(pdrs_ctx* c, const char* name, int64_t value) {
   else if (!strcmp(name, "part_hot")) c->opt_part_hot = value;
   else if (!strcmp(name, "part_hash")) c->opt_part_hash = value;
   else if (!strcmp(name, "stage_threads")) { if (c->stager && value != c->opt_stage_threads) pdrs_stage_destroy(c); c->opt_stage_threads = value; }
+  else if (!strcmp(name, "trace")) c->opt_trace = value;
+  else if (!strcmp(name, "xjoin_round_rows")) c->opt_xjoin_round_rows = value;
   else if (!strcmp(name, "stream_rows")) c->opt_stream_rows = value;
   else if (!strcmp(name, "stream_chunk_rows")) c->opt_stream_chunk_rows = value;
   else if (!strcmp(name, "stream_compact_rows")) c->opt_stream_compact_rows = value;

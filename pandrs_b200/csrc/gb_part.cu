@@ -482,8 +482,8 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
   }
   if ((unsigned long long)(nb1 + nside) * cap1 >= (1ull << 31) || (unsigned long long)nparts * cap2 >= (1ull << 31)) return PDRS_ERR_UNSUPPORTED;   // 31-bit output positions
   const size_t need = (size_t)(nb1 + nside) * cap1 * 17 + (bits2 ? ((size_t)nparts * cap2 + (nside ? (size_t)n / 2 : 0)) * 17 : 0);
-  size_t free_b = 0, total_b = 0;
-  PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  size_t free_b = 0;
+  PDRS_TRY(pdrs_mem_available(c, &free_b));
   if (need + (2ull << 30) > free_b) return PDRS_ERR_UNSUPPORTED;
 
   int ts_nt = 0, ts_gpt = 0, ts_slots = 0;

@@ -574,6 +574,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     est_exact = true;
   }
 
+  pdrs_trace(c, "gb: views + estimate");
   // ---- geometry of the shared-memory kernel per pass; fall back to the global table when it does not fit
   auto shared_geometry = [&](const PassPlan& pp, GbParams* gp, GbCfg* cfg, size_t* smem) -> bool {
     const int rec_bytes = (pp.flags == GB_SUM ? 8 : 16) + ((pp.flags == GB_ALL && pp.is_int) ? 8 : 0) + 4;   // ShPlanes::REC_BYTES
@@ -801,8 +802,8 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
         DevBuf spill_k, spill_v;
         if (use_ts && ts_skew && c->opt_spillbuf != 0) {
           const long long cap = std::max<long long>(n / 3, 1 << 20);
-          size_t free_b = 0, total_b = 0;
-          PDRS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+          size_t free_b = 0;
+          PDRS_TRY(pdrs_mem_available(c, &free_b));
           if ((size_t)cap * 16 + (4ull << 30) < free_b) {
             PDRS_TRY(spill_k.alloc(c, (size_t)cap * 8));
             PDRS_TRY(spill_v.alloc(c, (size_t)cap * 8));
@@ -883,6 +884,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
     for (auto& s : states) s.release();
   }
 
+  pdrs_trace(c, "gb: aggregation passes");
   // ---- finalise: the groups of the table are appended behind the groups that were written straight to the result
   const int64_t Gt = (int64_t)cn[CNT_NGROUPS] + ((cn[CNT_N] & GB_FULL) ? 1 : 0);
   if (direct_cap > 0) {
@@ -911,6 +913,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
   } else {
     PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
   }
+  pdrs_trace(c, "gb: finalise");
   guard.r = nullptr;
   *out = res;
   return PDRS_OK;
@@ -1431,12 +1434,14 @@ extern "C" int32_t pdrs_groupby_agg_dist(pdrs_comm* cm, const pdrs_col* keys, in
   for (auto& a : ag) if (a.op != PDRS_COUNT) a.value_col = vmap[a.value_col];
   const int nvs = (int)nv.size();
   // ---- local partial aggregation (every rank; the kernels of pdrs_groupby_partial)
+  pdrs_trace(c, nullptr);
   pdrs_groupby_result* part = nullptr;
   if (stream_eligible(c, keys, nkeys, nv.data(), nvs, filter, pred))      // host shards: chunk by chunk through the staging engine
     PDRS_TRY(groupby_stream(c, keys, nkeys, nv.data(), nvs, nullptr, 0, filter, pred, &part, all_stats ? 2 : 1));
   else
     PDRS_TRY(groupby_run(c, keys, nkeys, nv.data(), nvs, nullptr, 0, filter, MODE_PARTIAL, all_stats ? 1 : 0, &part, pred));
   struct PartGuard { pdrs_groupby_result* r; ~PartGuard() { if (r) { cudaSetDevice(r->ctx->device); delete r; } } } pguard{part};
+  pdrs_trace(c, "dist: local partial");
   const float local_ms = c->stats.main_kernel_ms;
   const int local_algo = c->stats.groupby_algo_used;
   // ---- the layout all ranks agree on
@@ -1477,10 +1482,12 @@ extern "C" int32_t pdrs_groupby_agg_dist(pdrs_comm* cm, const pdrs_col* keys, in
     PDRS_TRY(grow(cm->send, (size_t)block * 8));
     PDRS_TRY(grow(cm->recv, (size_t)block * 8 * world));
     PDRS_TRY(dist_pack_launch<0>(c, NW, pk, cm->send.as<u64>(), nullptr, nullptr));
+    pdrs_trace(c, "dist: pack");
     PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
     PDRS_TRY(pdrs_comm_allgather(cm, cm->send.p, cm->recv.p, (size_t)block * 8));
     PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
     cm->last_exchange_bytes = (int64_t)block * 8 * (world - 1);
+    pdrs_trace(c, "dist: all-gather");
     // merge right away (same stream, no host round trip); the group counts are checked afterwards
     PDRS_TRY(make_table((long long)world * cap));
     mp.buf = cm->recv.as<u64>(); mp.nrows = (long long)world * cap; mp.cap = cap; mp.block = block;
@@ -1489,6 +1496,7 @@ extern "C" int32_t pdrs_groupby_agg_dist(pdrs_comm* cm, const pdrs_col* keys, in
     PDRS_CUDA(c, cudaMemcpy2DAsync(counts.data(), 8, cm->recv.p, (size_t)block * 8, 8, (size_t)world, cudaMemcpyDeviceToHost, c->stream));
     PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
     bool fits = true;
+    pdrs_trace(c, "dist: table + merge + counts");
     for (int r = 0; r < world; r++) fits = fits && (long long)counts[r] <= cap;       // every rank sees the same counts: the decision is collective
     if (!fits) {
       if (result_mode == 1) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_groupby_agg_dist: a rank holds more than groups_cap = %lld groups; use the sharded result mode", cap);
@@ -1533,6 +1541,7 @@ extern "C" int32_t pdrs_groupby_agg_dist(pdrs_comm* cm, const pdrs_col* keys, in
     PDRS_TRY(dist_merge_launch(c, NW, mp));
   }
   PDRS_TRY(finish_merged(c, ks, tm, states, res->key_dtype, nkeys, nvs, val_is_int.data(), ag.data(), naggs, res));
+  pdrs_trace(c, "dist: finalise");
   PDRS_CUDA(c, cudaEventElapsedTime(&cm->last_exchange_ms, c->ev_a, c->ev_b));
   c->stats.main_kernel_ms = local_ms;
   c->stats.groupby_algo_used = local_algo;

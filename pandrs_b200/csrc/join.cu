@@ -1151,6 +1151,31 @@ struct pdrs_join_result {
   DevBuf pay[PDRS_MAX_VALS];
 };
 
+// pairs of several join results, one after the other (the rounds of pdrs_join_pairs_dist); takes ownership of the parts
+int32_t pdrs_join_result_concat(pdrs_ctx* c, pdrs_join_result** parts, int n, pdrs_join_result** out) {
+  auto* res = new pdrs_join_result();
+  res->ctx = c;
+  int64_t total = 0;
+  for (int i = 0; i < n; i++) total += parts[i]->n;
+  int32_t st = res->left.alloc(c, (size_t)std::max<int64_t>(total, 1) * 8);
+  if (st == PDRS_OK) st = res->right.alloc(c, (size_t)std::max<int64_t>(total, 1) * 8);
+  int64_t at = 0;
+  for (int i = 0; i < n && st == PDRS_OK; i++) {
+    if (parts[i]->n) {
+      if (cudaMemcpyAsync(res->left.as<int64_t>() + at, parts[i]->left.p, (size_t)parts[i]->n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess ||
+          cudaMemcpyAsync(res->right.as<int64_t>() + at, parts[i]->right.p, (size_t)parts[i]->n * 8, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess)
+        st = pdrs_fail(c, PDRS_ERR_CUDA, "join: concatenating the rounds failed");
+    }
+    at += parts[i]->n;
+  }
+  for (int i = 0; i < n; i++) { delete parts[i]; parts[i] = nullptr; }
+  if (st != PDRS_OK) { delete res; return st; }
+  res->n = total;
+  cudaStreamSynchronize(c->stream);
+  *out = res;
+  return PDRS_OK;
+}
+
 struct JPart { DevBuf keys, rows; long long n = 0; };
 static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out) {
   const int nb = 1 << log_nb;
@@ -1864,9 +1889,8 @@ int32_t pdrs_join_indices(const pdrs_join_result* r, int64_t* left_out, int64_t*
   pdrs_ctx* c = r->ctx;
   if (r->n == 0) return PDRS_OK;
   if (!left_out || !right_out) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_indices: NULL output");
-  PDRS_CUDA(c, cudaMemcpyAsync(left_out, r->left.p, (size_t)r->n * 8, cudaMemcpyDeviceToHost, c->stream));
-  PDRS_CUDA(c, cudaMemcpyAsync(right_out, r->right.p, (size_t)r->n * 8, cudaMemcpyDeviceToHost, c->stream));
-  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  PDRS_TRY(pdrs_copy_to_host(c, left_out, r->left.p, (size_t)r->n * 8));
+  PDRS_TRY(pdrs_copy_to_host(c, right_out, r->right.p, (size_t)r->n * 8));
   return PDRS_OK;
 }
 int32_t pdrs_join_right_col(const pdrs_join_result* r, int32_t k, void* out_host) {
@@ -1875,9 +1899,7 @@ int32_t pdrs_join_right_col(const pdrs_join_result* r, int32_t k, void* out_host
   if (r->n == 0) return PDRS_OK;
   if (!out_host) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_right_col: NULL output");
   const int esz = r->pay_dtype[k] == PDRS_BOOL_BITS ? 1 : pdrs_dtype_bytes(r->pay_dtype[k]);
-  PDRS_CUDA(c, cudaMemcpyAsync(out_host, r->pay[k].p, (size_t)r->n * esz, cudaMemcpyDeviceToHost, c->stream));
-  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
-  return PDRS_OK;
+  return pdrs_copy_to_host(c, out_host, r->pay[k].p, (size_t)r->n * esz);
 }
 const void* pdrs_join_right_col_dev(const pdrs_join_result* r, int32_t k) { return (r && k >= 0 && k < r->npay) ? r->pay[k].p : nullptr; }
 const int64_t* pdrs_join_left_dev(const pdrs_join_result* r) { return r ? r->left.as<int64_t>() : nullptr; }

@@ -6,6 +6,7 @@
 // (two per worker, so a worker fills one slot while the DMA engine drains the other) and issues the H2D copies on their own
 // streams; eight workers keep the link busy.  Sources that are already pinned (cudaHostAlloc / cudaHostRegister) skip the
 // bounce copy.  The consumer stream is ordered behind the copies with one event per worker (pdrs_stage_join).
+// Large results travel the other way through the same workers (pdrs_copy_to_host: DMA into a pinned slot, copy-out by the thread).
 #include <condition_variable>
 #include <cstring>
 #include <deque>
@@ -18,7 +19,7 @@ namespace {
 
 constexpr size_t PIECE = 8u << 20;
 
-struct Piece { char* dst; const char* src; size_t bytes; bool direct; };
+struct Piece { char* dst; const char* src; size_t bytes; bool direct; bool d2h; };
 
 struct Worker {
   cudaStream_t s = nullptr;
@@ -56,7 +57,16 @@ struct PdrsStager {
       }
       cudaError_t e = cudaSuccess;
       if (p.direct) {
-        e = cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyHostToDevice, me.s);
+        e = cudaMemcpyAsync(p.dst, p.src, p.bytes, p.d2h ? cudaMemcpyDeviceToHost : cudaMemcpyHostToDevice, me.s);
+      } else if (p.d2h) {
+        // device -> pageable host: DMA into the pinned slot, then this thread copies it out (the other workers' DMAs run meanwhile)
+        const int k = me.cur;
+        me.cur ^= 1;
+        if (me.used[k]) e = cudaEventSynchronize(me.ev[k]);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(me.slot[k], p.src, p.bytes, cudaMemcpyDeviceToHost, me.s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(me.s);
+        if (e == cudaSuccess) memcpy(p.dst, me.slot[k], p.bytes);
+        me.used[k] = false;
       } else {
         const int k = me.cur;
         me.cur ^= 1;
@@ -108,20 +118,20 @@ static int32_t stager_get(pdrs_ctx* c, PdrsStager** out) {
   return PDRS_OK;
 }
 
-int32_t pdrs_stage_copy_async(pdrs_ctx* c, void* dst_dev, const void* src_host, size_t bytes) {
+int32_t pdrs_stage_copy_async(pdrs_ctx* c, void* dst_dev, const void* src_host, size_t bytes, int d2h) {
   if (bytes == 0) return PDRS_OK;
   PdrsStager* st = nullptr;
   PDRS_TRY(stager_get(c, &st));
   cudaPointerAttributes at{};
   bool direct = false;
-  if (cudaPointerGetAttributes(&at, src_host) == cudaSuccess) direct = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeDevice;
+  if (cudaPointerGetAttributes(&at, d2h ? (const void*)dst_dev : src_host) == cudaSuccess) direct = at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeDevice;
   else cudaGetLastError();
   if (c->opt_stage_threads < 0) direct = true;   // -1: plain cudaMemcpyAsync from whatever the source is (the driver's pageable path)
   {
     std::lock_guard<std::mutex> lk(st->m);
     const size_t step = direct ? (64u << 20) : PIECE;
     for (size_t off = 0; off < bytes; off += step) {
-      st->q.push_back({(char*)dst_dev + off, (const char*)src_host + off, std::min(step, bytes - off), direct});
+      st->q.push_back({(char*)dst_dev + off, (const char*)src_host + off, std::min(step, bytes - off), direct, d2h != 0});
       st->inflight++;
     }
   }

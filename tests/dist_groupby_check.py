@@ -128,7 +128,10 @@ def main():
     lc = ctx.upload(pb.Column.int64(pk[lcut[rank]:lcut[rank + 1]], pnull[lcut[rank]:lcut[rank + 1]]))
     rc = ctx.upload(pb.Column.int64(bk[rcut[rank]:rcut[rank + 1]]))
     ml, mr = max(lcut[i + 1] - lcut[i] for i in range(world)), max(rcut[i + 1] - rcut[i] for i in range(world))
-    for how in (pb.INNER, pb.LEFT, pb.INNER):
+    # the last two joins run in ROUNDS of at most 100 000 left rows per rank (what shards beyond the 32-bit row encoding of
+    # the staged exchange do): same pairs
+    for how, round_rows in ((pb.INNER, 0), (pb.LEFT, 0), (pb.INNER, 0), (pb.LEFT, 100_000), (pb.INNER, 100_000)):
+        ctx.set_option("xjoin_round_rows", round_rows)
         j = comm.join_pairs(lc, rc, how, lcut[rank], rcut[rank], ml, mr, nb)
         li, ri = j.indices()
         j.close()
@@ -141,7 +144,8 @@ def main():
             want = want[np.lexsort((want[:, 1], want[:, 0]))]
             assert got.shape == want.shape and np.array_equal(got, want), (how, got.shape, want.shape)
             ms, nbytes = comm.last_exchange()
-            print(f"  join how={how}: {len(want)} pairs ok (shuffle {ms:.3f} ms, {nbytes / 1e6:.1f} MB to peers)", flush=True)
+            print(f"  join how={how}{' in rounds' if round_rows else ''}: {len(want)} pairs ok (shuffle {ms:.3f} ms, {nbytes / 1e6:.1f} MB to peers)", flush=True)
+    ctx.set_option("xjoin_round_rows", 0)
     comm.close()
     ctx.close()
     dist.barrier()

@@ -215,5 +215,6 @@ def test_from_record_batch_then_groupby(ctx, oracle):
         ka, kc = a.column("cat").to_list(), c.column("cat").to_list()
         assert sorted(ka) == sorted(kc) and len(ka) == 13
         oa, oc = np.argsort(ka), np.argsort(kc)
-        for name in ("s", "m", "c", "mx"):
+        for name in ("s", "c", "mx"):
             assert np.array_equal(a.column(name).values[oa], c.column(name).values[oc]), name
+        assert np.allclose(a.column("m").values[oa], c.column("m").values[oc], rtol=1e-12, atol=0)      # f64 sums: the order of the partial sums varies

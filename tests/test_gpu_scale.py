@@ -127,3 +127,65 @@ def test_config3_zipf_multi_key_vs_typed_oracle(ctx, oracle, nkeys, rows):
     finally:
         r.close()
     print(f"\n[scale] configs[3] {nkeys} keys, {n} rows: {tg['n_groups']} groups, algo {algo}, retries {retries}, worst relative error {worst}")
+
+
+def test_chunked_host_groupby_vs_typed_oracle(ctx, oracle):
+    # out-of-core path (pdrs_groupby_agg on HOST columns, 2^26-row chunks through the staging engine) against the typed oracle on
+    # the whole input: 2e8 rows = 3 chunks, pageable numpy memory
+    n = _rows(200_000_000)
+    if mem_available_gb() < 8 * n * 16 / 1e9 / 4:
+        pytest.skip("not enough host memory")
+    hk = np.empty(n, np.int64)
+    hv = np.empty(n, np.float64)
+    hn = np.empty((n + 7) // 8, np.uint8)
+    keys = ctx.synth_keys(n, card=1000)
+    vals = ctx.synth_vals(n, null_per_million=50_000)
+    ctx.memcpy(hk.ctypes.data, keys.ptr, 8 * n, 1)
+    ctx.memcpy(hv.ctypes.data, vals.ptr, 8 * n, 1)
+    ctx.memcpy(hn.ctypes.data, vals.nulls_ptr, (n + 7) // 8, 1)
+    ctx.free(keys); ctx.free(vals)
+    launches0 = ctx.stats()["kernel_launches"]
+    r = ctx.groupby_agg([pb.Column(pb.I64, hk)], [pb.Column(pb.F64, hv, hn)], [(0, op) for op in ALL7])
+    try:
+        assert ctx.stats()["kernel_launches"] - launches0 >= 3 * ((n + (1 << 26) - 1) >> 26)     # one partial aggregation per chunk
+        tg = oracle.typed_groupby_synth(n, card=1000, null_per_million=50_000)
+        worst = compare_groupby_typed(pb, r, tg, [pb.I64], ALL7)
+    finally:
+        r.close()
+    print(f"\n[scale] chunked host groupby {n} rows: worst relative error vs reference / vs exact: {worst}")
+
+
+@pytest.mark.parametrize("card", [1000, 3_000_000])
+def test_row_lists_at_scale(ctx, oracle, card):
+    # pdrs_groupby_rows (par_groupby, grouping.rs:124-331) at 2e8 rows: a permutation of the rows, ascending inside every group,
+    # every group holds one key only, sizes = the typed oracle's group sizes
+    import torch
+    n = _rows(200_000_000)
+    keys = ctx.synth_keys(n, card=card)
+    res = ctx.groupby_rows([keys])
+    try:
+        G = res.n_groups
+        tg = oracle.typed_groupby_synth(n, card=card, null_per_million=0)
+        assert G == tg["n_groups"] and res.n_rows == n
+        kv, kn = res.key(0)
+        off = res.offsets()
+        assert not kn.any() and off[0] == 0 and off[-1] == n
+        o, to = np.argsort(kv), np.argsort(tg["keys"][0][0].view(np.int64))
+        assert np.array_equal(kv[o], tg["keys"][0][0].view(np.int64)[to]) and np.array_equal(np.diff(off)[o], tg["group_rows"][to])
+        dev = torch.device("cuda", ctx.device)
+        ids = torch.empty(n, dtype=torch.int64, device=dev)
+        k = torch.empty(n, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+        ctx.memcpy(ids.data_ptr(), res.ids_dev(), 8 * n, 2)
+        ctx.memcpy(k.data_ptr(), keys.ptr, 8 * n, 2)
+        assert int(ids.sum().item()) == n * (n - 1) // 2 and int(ids.min().item()) == 0 and int(ids.max().item()) == n - 1
+        gk = k[ids]                                           # keys in grouped order
+        offs = torch.from_numpy(off).to(dev)
+        seg = torch.repeat_interleave(torch.arange(G, device=dev), offs[1:] - offs[:-1])
+        assert bool((gk == torch.from_numpy(kv).to(dev)[seg]).all()), "a group holds rows of another key"
+        d = ids[1:] - ids[:-1]
+        inside = seg[1:] == seg[:-1]
+        assert bool((d[inside] > 0).all()), "rows of a group must ascend"
+    finally:
+        res.close()
+        ctx.free(keys)

@@ -116,3 +116,21 @@ def test_chunked_pinned_source_and_empty_chunks(sctx, oracle):
     finally:
         sctx.host_free(pk)
         sctx.host_free(pv)
+
+
+def test_large_results_and_columns_through_the_staging_engine(ctx, oracle):
+    # host key columns >= 64 MB are uploaded by the staging threads and index pairs >= 64 MB come back through them (pageable numpy
+    # memory on both sides): same pairs as the oracle's join of the same keys
+    n = 9_000_000
+    rng = np.random.default_rng(31)
+    right = rng.permutation(n).astype(np.int64) * 7 + 3
+    left = (rng.integers(0, 2 * n, n) * 7 + 3).astype(np.int64)
+    j = ctx.join_pairs(pb.Column.int64(left), pb.Column.int64(right), pb.LEFT)
+    try:
+        li, ri = j.indices()
+    finally:
+        j.close()
+    assert len(li) == n and np.array_equal(np.sort(li), np.arange(n))
+    where = np.full(2 * n, -1, np.int64)
+    where[(right - 3) // 7] = np.arange(n)
+    assert np.array_equal(ri, where[(left[li] - 3) // 7])
