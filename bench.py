@@ -296,7 +296,7 @@ def timed_region(env, step, warmup, steps, stats_key="main_kernel_ms"):
     ranks.  Returns (ms per step, kernel ms per step [stats], launches per step, clocks)."""
     import torch
     clocks = ClockSampler(env.local)
-    if env.rank == 0:
+    if env.rank == 0 and not os.environ.get("PDRS_BENCH_NO_CLOCKS"):
         clocks.start()
     tw = 0.0
     for _ in range(warmup):
@@ -322,7 +322,8 @@ def timed_region(env, step, warmup, steps, stats_key="main_kernel_ms"):
     clk = clocks.stop() if env.rank == 0 else None
     launches = (env.ctx.stats()["kernel_launches"] - launches0) // max(steps, 1)
     if walls:
-        log("host wall clock per step (ms): min %.3f  median %.3f  max %.3f" % (min(walls), sorted(walls)[len(walls) // 2], max(walls)))
+        log("library CUDA-event time per step (ms): " + " ".join("%.1f" % k for k in kms[:24]))
+        log("host wall clock per step (ms): min %.3f  median %.3f  max %.3f   [%s]" % (min(walls), sorted(walls)[len(walls) // 2], max(walls), " ".join("%.1f" % w for w in walls[:24])))
     return ms / steps, sum(kms) / max(len(kms), 1), int(launches), clk
 
 
@@ -1006,6 +1007,9 @@ def main():
         env.dist = dist
     env.stream = torch.cuda.current_stream()
     env.ctx = pb.Context(device=env.local, stream=env.stream.cuda_stream)
+    for kv in filter(None, os.environ.get("PDRS_OPTS", "").split(",")):      # e.g. PDRS_OPTS=timing=2,trace=1 (debugging)
+        k, v = kv.split("=")
+        env.ctx.set_option(k, int(v))
     env.comm = pb.Comm(env.ctx, env.rank, env.world, pb.torch_broadcast_id(env.dist, torch.device("cuda", env.local))) if env.world > 1 else None
 
     def barrier():

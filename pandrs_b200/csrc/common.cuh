@@ -72,7 +72,12 @@ struct pdrs_ctx {
   int64_t opt_trace = 0;               // 1: print host-clock phase marks of the collective operators to stderr (each mark synchronises the stream)
   double trace_t0 = 0.0;
   PdrsStager* stager = nullptr;
+  bool big_free_pending = false;       // a block of >= 256 MB went back to the pool since the last synchronisation (pdrs_settle_frees)
 };
+// Multi-GB blocks given back with cudaFreeAsync are only cheap to get again once the host has SEEN the stream pass the frees
+// (measured, tools/bisect_join.py: back-to-back joins without a synchronisation in between took 40 - 80 ms instead of 18.9 ms -
+// the pool grew by fresh driver allocations instead of reusing its blocks).  Operators call this before they allocate.
+inline void pdrs_settle_frees(pdrs_ctx* c) { if (c->big_free_pending) { cudaStreamSynchronize(c->stream); c->big_free_pending = false; } }
 void pdrs_trace(pdrs_ctx* c, const char* label);     // ctx.cu; no-op unless opt_trace
 
 int32_t pdrs_fail(pdrs_ctx* ctx, int32_t code, const char* fmt, ...);

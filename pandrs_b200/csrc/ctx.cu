@@ -70,7 +70,7 @@ int32_t DevBuf::alloc(pdrs_ctx* c, size_t n, bool zero) {
   return PDRS_OK;
 }
 void DevBuf::release() {
-  if (p && ctx) cudaFreeAsync(p, ctx->stream);
+  if (p && ctx) { cudaFreeAsync(p, ctx->stream); if (bytes >= (256ull << 20)) ctx->big_free_pending = true; }
   p = nullptr;
   bytes = 0;
 }

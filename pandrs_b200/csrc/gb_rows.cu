@@ -171,6 +171,7 @@ int32_t pdrs_groupby_rows(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, pdrs
   if (!c) return PDRS_ERR_BAD_ARG;
   if (!out || !keys || nkeys < 1 || nkeys > PDRS_MAX_KEYS) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby_rows: bad argument (nkeys %d)", nkeys);
   PDRS_CUDA(c, cudaSetDevice(c->device));
+  pdrs_settle_frees(c);
   const int64_t n = keys[0].len;
   for (int k = 0; k < nkeys; k++) if (keys[k].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "key column %d has %lld rows, expected %lld", k, (long long)keys[k].len, (long long)n);
   if (n >= (1ll << 32) - 1) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_groupby_rows: at most 2^32 - 2 rows per call");
@@ -340,8 +341,10 @@ int32_t pdrs_group_rows_agg(pdrs_group_rows* r, const pdrs_col* val, int32_t op,
 
 void pdrs_group_rows_free(pdrs_group_rows* r) {
   if (!r) return;
-  cudaSetDevice(r->ctx->device);
+  pdrs_ctx* c = r->ctx;
+  cudaSetDevice(c->device);
   delete r;
+  pdrs_settle_frees(c);
 }
 
 }  // extern "C"

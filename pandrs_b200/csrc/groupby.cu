@@ -415,6 +415,7 @@ static int32_t groupby_run(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, con
       (nvals && !vals) || (naggs && !aggs))
     return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby: bad argument (nkeys %d, nvals %d, naggs %d)", nkeys, nvals, naggs);
   PDRS_CUDA(c, cudaSetDevice(c->device));
+  pdrs_settle_frees(c);
   const int64_t n = keys[0].len;
   for (int k = 0; k < nkeys; k++) if (keys[k].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "key column %d has %lld rows, expected %lld", k, (long long)keys[k].len, (long long)n);
   for (int v = 0; v < nvals; v++) if (vals[v].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "value column %d has %lld rows, expected %lld", v, (long long)vals[v].len, (long long)n);
@@ -1589,8 +1590,10 @@ const int64_t* pdrs_groupby_group_rows_dev(const pdrs_groupby_result* r) { retur
 const uint64_t* pdrs_groupby_states_dev(const pdrs_groupby_result* r, int32_t v) { return (r && v >= 0 && v < r->nvals) ? r->states[v].as<uint64_t>() : nullptr; }
 void pdrs_groupby_result_free(pdrs_groupby_result* r) {
   if (!r) return;
-  cudaSetDevice(r->ctx->device);
+  pdrs_ctx* c = r->ctx;
+  cudaSetDevice(c->device);
   delete r;
+  pdrs_settle_frees(c);
 }
 
 }  // extern "C"

@@ -1478,6 +1478,7 @@ static int32_t join_run(pdrs_ctx* c, const pdrs_col* left_key, const pdrs_col* r
   if (left_key->dtype != right_key->dtype)   // join.rs:98-104
     return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "join key columns have different types (%d vs %d)", left_key->dtype, right_key->dtype);
   PDRS_CUDA(c, cudaSetDevice(c->device));
+  pdrs_settle_frees(c);       // the multi-GB buffers of the previous call are reusable once the host has seen their frees (common.cuh)
   if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
   c->stats.main_kernel_ms = 0; c->stats.total_ms = 0;
   ColView lv, rv;
@@ -1808,6 +1809,7 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   if (how != PDRS_INNER && how != PDRS_LEFT) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_local: only Inner and Left joins are sharded");
   if (!x->shuffled) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_local: nothing was shuffled");
   PDRS_CUDA(c, cudaSetDevice(c->device));
+  pdrs_settle_frees(c);
   if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
   c->stats.main_kernel_ms = 0; c->stats.total_ms = 0;
   const long long sb = 1ll << (x->sh_log_nb + x->log_world);
@@ -1906,8 +1908,10 @@ const int64_t* pdrs_join_left_dev(const pdrs_join_result* r) { return r ? r->lef
 const int64_t* pdrs_join_right_dev(const pdrs_join_result* r) { return r ? r->right.as<int64_t>() : nullptr; }
 void pdrs_join_result_free(pdrs_join_result* r) {
   if (!r) return;
-  cudaSetDevice(r->ctx->device);
+  pdrs_ctx* c = r->ctx;
+  cudaSetDevice(c->device);
   delete r;
+  pdrs_settle_frees(c);
 }
 
 }  // extern "C"
