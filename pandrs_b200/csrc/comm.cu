@@ -160,8 +160,10 @@ int32_t pdrs_comm_barrier(pdrs_comm* cm) {
 // Every rank passes its shard of both key columns and the global number of its first row on each side; rank r returns the
 // pairs of the keys whose rank hash maps to r, in GLOBAL row numbers.  max_* describe the largest shard of any rank (same
 // values on every rank): the receive areas are allocated for them once and reused by later calls.
+// one shuffle + local join; right_key == NULL: a later round (only left rows travel, the table of round 0 is probed again);
+// the pairs are appended to `res`
 static int32_t join_pairs_dist_round(pdrs_comm* cm, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, int64_t left_row0, int64_t right_row0,
-                                     int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result** out);
+                                     int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result* res, int64_t cap_hint);
 
 int32_t pdrs_join_pairs_dist(pdrs_comm* cm, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, int64_t left_row0, int64_t right_row0,
                              int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result** out) {
@@ -172,16 +174,16 @@ int32_t pdrs_join_pairs_dist(pdrs_comm* cm, const pdrs_col* left_key, const pdrs
   if (left_key->len > max_left_rows || max_left_rows < 0) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_join_pairs_dist: %lld left rows exceed max_left_rows = %lld", (long long)left_key->len, (long long)max_left_rows);
   // The staged exchange (line-aligned peer stores at ~80% of the NVLink peak) carries a left row as (source rank << s | local row) in 32
   // bits, s = 32 - log2(ranks): larger shards are joined in ROUNDS of < 2^s left rows each against the same build side (the
-  // probe rows of a join are independent of each other; the build side - the small one - is shuffled again per round).
+  // probe rows of a join are independent of each other): round 0 shuffles both sides and builds the hash table, the later rounds only
+  // shuffle and probe their slice of the left rows.
   int log_world = 0;
   while ((1 << log_world) < cm->world) log_world++;
   int64_t lim = (1ll << (32 - log_world)) - 64;
   if (c->opt_xjoin_round_rows > 0) lim = std::min<int64_t>(lim, std::max<int64_t>(64, c->opt_xjoin_round_rows));
   int rounds = 1;
   if ((cm->world > 1 && c->opt_xjoin_mode != 1) || c->opt_xjoin_round_rows > 0) while ((max_left_rows + rounds - 1) / rounds > lim) rounds++;
-  if (rounds == 1) return join_pairs_dist_round(cm, left_key, right_key, how, left_row0, right_row0, max_left_rows, max_right_rows, total_right_rows, out);
-  const int64_t chunk = ((max_left_rows + rounds - 1) / rounds + 63) / 64 * 64;       // bitmap bytes and 128-bit loads stay aligned
-  std::vector<pdrs_join_result*> parts;
+  const int64_t chunk = rounds == 1 ? max_left_rows : ((max_left_rows + rounds - 1) / rounds + 63) / 64 * 64;       // bitmap bytes and 128-bit loads stay aligned
+  pdrs_join_result* res = pdrs_join_result_new(c);
   float ex_ms = 0.f;
   int64_t ex_bytes = 0;
   int32_t rc = PDRS_OK;
@@ -195,17 +197,21 @@ int32_t pdrs_join_pairs_dist(pdrs_comm* cm, const pdrs_col* left_key, const pdrs
       sl.null_bits = have > 0 ? left_key->null_bits + lo / 8 : nullptr;
       sl.null_len = have;
     }
-    pdrs_join_result* part = nullptr;
-    rc = join_pairs_dist_round(cm, &sl, right_key, how, left_row0 + lo, right_row0, chunk, max_right_rows, total_right_rows, &part);   // collective: every rank runs every round
-    if (rc == PDRS_OK) { parts.push_back(part); ex_ms += cm->last_exchange_ms; ex_bytes += cm->last_exchange_bytes; }
+    // collective: every rank runs every round.  Round 0 shuffles the build side too and builds the table; the later rounds only
+    // shuffle and probe their slice of the left rows; the pairs of all rounds are appended to one result (room for all of them
+    // is reserved in round 0: a join on unique build keys emits at most one pair per left row)
+    rc = join_pairs_dist_round(cm, &sl, r == 0 ? right_key : nullptr, how, left_row0 + lo, right_row0, chunk, max_right_rows, total_right_rows, res,
+                               rounds > 1 ? left_key->len + left_key->len / 16 + 1024 : 0);
+    if (rc == PDRS_OK) { ex_ms += cm->last_exchange_ms; ex_bytes += cm->last_exchange_bytes; }
   }
-  if (rc != PDRS_OK) { for (auto* p : parts) pdrs_join_result_free(p); return rc; }
+  if (rc != PDRS_OK) { pdrs_join_result_free(res); return rc; }
   cm->last_exchange_ms = ex_ms; cm->last_exchange_bytes = ex_bytes;
-  return pdrs_join_result_concat(c, parts.data(), (int)parts.size(), out);
+  *out = res;
+  return PDRS_OK;
 }
 
 static int32_t join_pairs_dist_round(pdrs_comm* cm, const pdrs_col* left_key, const pdrs_col* right_key, int32_t how, int64_t left_row0, int64_t right_row0,
-                                     int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result** out) {
+                                     int64_t max_left_rows, int64_t max_right_rows, int64_t total_right_rows, pdrs_join_result* res, int64_t cap_hint) {
   pdrs_ctx* c = cm->ctx;
   PDRS_CUDA(c, cudaSetDevice(c->device));
   if (!cm->xj || cm->xj_left != max_left_rows || cm->xj_right != max_right_rows || cm->xj_total_right != total_right_rows) {
@@ -238,7 +244,7 @@ static int32_t join_pairs_dist_round(pdrs_comm* cm, const pdrs_col* left_key, co
   }
   int32_t rc = pdrs_xjoin_shuffle(cm->xj, left_key, right_key, right_row0);
   cm->last_exchange_ms = c->stats.total_ms;
-  cm->last_exchange_bytes = (int64_t)((double)(left_key->len + right_key->len) * 12.0 * (cm->world - 1) / cm->world);
+  cm->last_exchange_bytes = (int64_t)((double)(left_key->len + (right_key ? right_key->len : 0)) * 12.0 * (cm->world - 1) / cm->world);
   struct Info { int64_t ok, left_row0; } mine{rc == PDRS_OK ? 1 : 0, left_row0};
   std::vector<Info> all((size_t)cm->world);
   PDRS_TRY(pdrs_comm_allgather_host(cm, &mine, all.data(), sizeof(Info)));      // doubles as the barrier: all stores into my area are complete
@@ -246,18 +252,13 @@ static int32_t join_pairs_dist_round(pdrs_comm* cm, const pdrs_col* left_key, co
   bool ok = true;
   for (int r = 0; r < cm->world; r++) { ok = ok && all[r].ok; row0[r] = all[r].left_row0; }
   if (!ok) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_join_pairs_dist: a padded region overflowed on some rank (skewed keys)");
-  pdrs_join_result* res = nullptr;
-  rc = pdrs_xjoin_local(cm->xj, how, row0.data(), &res);
+  rc = pdrs_xjoin_local_append(cm->xj, how, row0.data(), res, cap_hint);
   const std::string local_err = c->err;
   uint8_t f = rc == PDRS_OK ? 1 : 0;           // local() can fail on one rank alone: agree before anybody returns
   std::vector<uint8_t> fa((size_t)cm->world);
   PDRS_TRY(pdrs_comm_allgather_host(cm, &f, fa.data(), 1));
   for (int r = 0; r < cm->world; r++) ok = ok && fa[r];
-  if (!ok) {
-    if (res) pdrs_join_result_free(res);
-    return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_join_pairs_dist: the local join failed on some rank (%s)", rc == PDRS_OK ? "another rank" : local_err.c_str());
-  }
-  *out = res;
+  if (!ok) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_join_pairs_dist: the local join failed on some rank (%s)", rc == PDRS_OK ? "another rank" : local_err.c_str());
   return PDRS_OK;
 }
 

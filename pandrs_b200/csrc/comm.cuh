@@ -27,3 +27,6 @@ int32_t pdrs_comm_allgather_host(pdrs_comm* cm, const void* mine, void* all, siz
 
 struct pdrs_join_result;
 int32_t pdrs_join_result_concat(pdrs_ctx* c, pdrs_join_result** parts, int n, pdrs_join_result** out);   // join.cu
+// join.cu: build (unless the table of the current build side exists) + probe, pairs appended to `res`; cap_hint = pairs to make room for
+int32_t pdrs_xjoin_local_append(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, pdrs_join_result* res, int64_t cap_hint);
+pdrs_join_result* pdrs_join_result_new(pdrs_ctx* c);

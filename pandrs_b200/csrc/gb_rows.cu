@@ -9,19 +9,17 @@
 //   aggregates need them: AggregateOp::First / Last / Median, group/aggregation.rs:585-624, 703-742.
 //
 // Device algorithm (no CPU fallback):
-//   1. exact number of groups from the groupby kernels (count-only pdrs_groupby_agg)            -> table size
-//   2. gr_assign_kernel   row -> slot of its key tuple in an open-addressing table (same key packing, same claim protocol as the
-//                         global-table groupby kernel); slot counts by warp-aggregated atomics
-//   3. gr_compact_kernel  slots -> dense group numbers, decoded key columns, group sizes; exclusive scan -> offsets
-//   4. a STABLE least-significant-digit radix sort of the row numbers by group number, 8 bits per pass
-//      (rs_hist_kernel / scan / rs_scatter_kernel: per-tile digit histograms, one global exclusive scan in digit-major order,
-//      then every warp walks its rows in order and ranks them inside the warp with MATCH.ANY - no atomics, order preserved)
+//   1. the groups (keys, sizes) from the groupby kernels (count-only pdrs_groupby_agg); exclusive scan of the sizes -> offsets
+//   2. gr_table_build_kernel  key words of the G groups -> a read-only open-addressing table {key -> group number}
+//      gr_assign_kernel       row -> group number with plain cached loads (no atomics; the table of a few thousand groups is L1 / L2)
+//   3. a STABLE least-significant-digit radix sort of (group number, row number), 8 bits per pass (gb_sort.cuh)
 //      -> rows[offsets[g] .. offsets[g + 1]) = the rows of group g in ascending order, exactly the reference's Vec<usize>.
 // Median sorts (ord(value), position) with the same passes (8 value digits, then the group digits) and reads the middle element(s).
 #include <algorithm>
 
 #include "groupby_kernels.cuh"
 #include "gb_final.cuh"
+#include "gb_pack.cuh"
 #include "gb_sort.cuh"
 
 int32_t pdrs_build_keyspec(pdrs_ctx* c, const ColView* kv, int nkeys, KeySpec* ks);   // groupby.cu
@@ -40,60 +38,49 @@ struct pdrs_group_rows {
 namespace {
 
 // ---------------------------------------------------------------- row -> slot -> group number
-struct AssignParams { KeySpec ks; long long n; GTable gt; uint32_t* slot_of_row; };
+// The groups are known before the rows are looked at (count-only groupby): group j = entry j of its key arrays.  A read-only
+// open-addressing table {key words -> j} is built from those G entries; a row then finds its group number with plain cached loads -
+// no atomics, no claim protocol, and for a few thousand groups the table lives in L1 / L2.
+struct LookupTab { u64* k0; u64* k1; u64* k2; uint32_t* gid; u64 mask; int shift; uint32_t* null_gid; };   // gid: all ones = empty slot
+static constexpr uint32_t GR_EMPTY = 0xFFFFFFFFu;
 
 template <int NW>
-__global__ void __launch_bounds__(256) gr_assign_kernel(const AssignParams p) {
-  const int lane = threadIdx.x & 31;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i - lane < p.n; i += (long long)gridDim.x * blockDim.x) {
-    const bool inb = i < p.n;
+__global__ void gr_table_build_kernel(const DistPack pk, const LookupTab t) {
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < pk.G; j += (long long)gridDim.x * blockDim.x) {
     u64 w[NW];
-#pragma unroll
-    for (int k = 0; k < NW; k++) w[k] = 0;
-    const bool knull = inb ? load_key_generic<NW>(p.ks, i, w) : false;
-    long long gs = g_find_or_insert<NW>(p.gt, w, inb && !knull);
-    if (knull) { gs = p.gt.slots; if (!(ld_cg_u64(&p.gt.hdr[gs].rowsw) & GB_FULL)) atomicOr(&p.gt.hdr[gs].rowsw, GB_FULL); }
-    const bool ok = inb && gs >= 0;
-    // group sizes: one atomic per distinct slot of the warp's 32 rows
-    const unsigned long long tag = ok ? (unsigned long long)gs : ~0ull - (unsigned long long)lane;
-    const uint32_t m = __match_any_sync(0xFFFFFFFFu, tag);
-    if (ok) {
-      if (lane == __ffs(m) - 1) atomicAdd(&p.gt.hdr[gs].rowsw, (u64)__popc(m));
-      p.slot_of_row[i] = (uint32_t)gs;
+    if (dist_row_words<NW>(pk, j, w)) { *t.null_gid = (uint32_t)j; continue; }       // the NULL-key group of a single-key grouping
+    u64 slot = key_hash<NW>(w) >> t.shift;
+    for (;;) {       // the keys are distinct: a slot is claimed by one CAS on its group number, the key words are plain stores
+      if (atomicCAS(&t.gid[slot], GR_EMPTY, (uint32_t)j) == GR_EMPTY) { t.k0[slot] = w[0]; if (NW > 1) t.k1[slot] = w[NW > 1 ? 1 : 0]; if (NW > 2) t.k2[slot] = w[NW > 2 ? 2 : 0]; break; }
+      slot = (slot + 1) & t.mask;
     }
   }
 }
-
-struct CompactParams { FinParams fp; uint32_t* gid_of_slot; };
-__global__ void gr_compact_kernel(const CompactParams p) {
-  const GTable& gt = p.fp.gt;
-  const long long total = gt.slots + 1;
-  const int lane = threadIdx.x & 31;
-  for (long long s0 = (long long)blockIdx.x * blockDim.x; s0 < total; s0 += (long long)gridDim.x * blockDim.x) {
-    const long long s = s0 + threadIdx.x;
-    u64 rw = 0;
-    if (s < total) rw = gt.hdr[s].rowsw;
-    const bool full = (rw & GB_FULL) != 0;
-    const unsigned m = __ballot_sync(0xFFFFFFFFu, full);
-    if (!m) continue;
-    u64 basepos = 0;
-    if (lane == 0) basepos = atomicAdd(&gt.counters[CNT_OUT], (u64)__popc(m));
-    basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
-    if (!full) continue;
-    const long long o = (long long)(basepos + __popc(m & ((1u << lane) - 1u)));
-    u64 w[PDRS_MAX_WORDS] = {0, 0, 0};
-    const bool nullgroup = s == gt.slots;
-    if (!nullgroup) {
-      w[0] = gt.hdr[s].key0;
-      if (p.fp.ks.nwords > 1) w[1] = gt.kw1[s];
-      if (p.fp.ks.nwords > 2) w[2] = gt.kw2[s];
+struct AssignParams { KeySpec ks; long long n; LookupTab t; uint32_t* gid_of_row; unsigned long long* missing; };
+template <int NW>
+__global__ void __launch_bounds__(256) gr_assign_kernel(const AssignParams p) {
+  const uint32_t null_gid = *p.t.null_gid;
+  unsigned long long miss = 0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
+    u64 w[NW];
+    uint32_t g = GR_EMPTY;
+    if (load_key_generic<NW>(p.ks, i, w)) g = null_gid;
+    else {
+      u64 slot = key_hash<NW>(w) >> p.t.shift;
+      for (u64 probe = 0; probe <= p.t.mask; probe++) {
+        const uint32_t cand = __ldg(p.t.gid + slot);
+        if (cand == GR_EMPTY) break;
+        bool match = __ldg(p.t.k0 + slot) == w[0];
+        if (NW > 1) match = match && __ldg(p.t.k1 + slot) == w[NW > 1 ? 1 : 0];
+        if (NW > 2) match = match && __ldg(p.t.k2 + slot) == w[NW > 2 ? 2 : 0];
+        if (match) { g = cand; break; }
+        slot = (slot + 1) & p.t.mask;
+      }
     }
-    fin_write_group(p.fp, o, w, nullgroup, rw & GB_CNT_MASK, [](int) -> const GState* { return nullptr; });
-    p.gid_of_slot[s] = (uint32_t)o;
+    if (g == GR_EMPTY) { miss++; g = 0; }
+    p.gid_of_row[i] = g;
   }
-}
-__global__ void gr_slot_to_gid_kernel(uint32_t* __restrict__ slot_of_row, long long n, const uint32_t* __restrict__ gid_of_slot) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) slot_of_row[i] = gid_of_slot[slot_of_row[i]];
+  if (miss) atomicAdd(p.missing, miss);
 }
 
 // ---------------------------------------------------------------- First / Last / Median over the row lists
@@ -109,6 +96,9 @@ __global__ void gr_first_last_kernel(const VT* __restrict__ val, const uint8_t* 
     }
     out[g] = r;
   }
+}
+__global__ void gr_gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, long long n, uint32_t* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = src[idx[i]];
 }
 // position j of the grouped order: its group number and the order-preserving image of its value (NULL -> all ones: sorts last)
 template <typename VT>
@@ -172,6 +162,7 @@ int32_t pdrs_groupby_rows(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, pdrs
   if (!out || !keys || nkeys < 1 || nkeys > PDRS_MAX_KEYS) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_groupby_rows: bad argument (nkeys %d)", nkeys);
   PDRS_CUDA(c, cudaSetDevice(c->device));
   pdrs_settle_frees(c);
+  pdrs_trace(c, nullptr);
   const int64_t n = keys[0].len;
   for (int k = 0; k < nkeys; k++) if (keys[k].len != n) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "key column %d has %lld rows, expected %lld", k, (long long)keys[k].len, (long long)n);
   if (n >= (1ll << 32) - 1) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_groupby_rows: at most 2^32 - 2 rows per call");
@@ -181,81 +172,79 @@ int32_t pdrs_groupby_rows(pdrs_ctx* c, const pdrs_col* keys, int32_t nkeys, pdrs
   struct Guard { pdrs_group_rows* r; ~Guard() { delete r; } } guard{res};
   std::vector<ColView> kv(nkeys);
   for (int k = 0; k < nkeys; k++) PDRS_TRY(pdrs_view_col(c, &keys[k], &kv[k]));
-  // 1. exact group count (the staged views are handed on as device columns: nothing is copied twice)
-  long long G0 = 0;
+  // 1. the groups: keys and sizes from the count-only groupby (the staged views are handed on as device columns: nothing is copied
+  //    twice); group j of the row lists = entry j of that result
+  long long G = 0;
+  pdrs_groupby_result* cnt = nullptr;
   if (n > 0) {
     std::vector<pdrs_col> dk(nkeys);
     for (int k = 0; k < nkeys; k++) dk[k] = view_as_col(kv[k]);
-    pdrs_groupby_result* cnt = nullptr;
     const int32_t saved = c->opts.compat_filter_nulls;
     c->opts.compat_filter_nulls = 0;
     const int32_t st = pdrs_groupby_agg(c, dk.data(), nkeys, nullptr, 0, nullptr, 0, nullptr, &cnt);
     c->opts.compat_filter_nulls = saved;
     PDRS_TRY(st);
-    G0 = pdrs_groupby_n_groups(cnt);
-    pdrs_groupby_result_free(cnt);
+    G = pdrs_groupby_n_groups(cnt);
   }
+  struct CntGuard { pdrs_groupby_result* r; ~CntGuard() { if (r) pdrs_groupby_result_free(r); } } cguard{cnt};
+  pdrs_trace(c, "rows: views + group count");
+  res->n_groups = G;
+  const size_t Galloc = (size_t)std::max<long long>(G, 1);
   KeySpec ks;
   PDRS_TRY(pdrs_build_keyspec(c, kv.data(), nkeys, &ks));
-  // 2. row -> slot
-  const long long slots = std::max<long long>(1024, pow2ceil_ll(2 * G0 + 16));
-  if (slots >= (1ll << 32) - 1) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_groupby_rows: too many groups (%lld)", G0);
-  DevBuf hdr, kw1, kw2, counters, slot_of_row, gid_of_slot;
-  PDRS_TRY(hdr.alloc(c, (size_t)(slots + 1) * sizeof(GHdr), true));
-  if (ks.nwords > 1) PDRS_TRY(kw1.alloc(c, (size_t)(slots + 1) * 8));
-  if (ks.nwords > 2) PDRS_TRY(kw2.alloc(c, (size_t)(slots + 1) * 8));
-  PDRS_TRY(counters.alloc(c, CNT_N * 8, true));
-  PDRS_TRY(slot_of_row.alloc(c, (size_t)std::max<int64_t>(n, 1) * 4));
-  PDRS_TRY(gid_of_slot.alloc(c, (size_t)(slots + 1) * 4));
-  GTable gt{};
-  gt.hdr = hdr.as<GHdr>(); gt.kw1 = kw1.as<u64>(); gt.kw2 = kw2.as<u64>(); gt.st = nullptr;
-  gt.mask = (u64)slots - 1; gt.shift = 64 - ceil_log2(slots); gt.slots = slots; gt.counters = counters.as<u64>();
-  if (n > 0) {
-    AssignParams ap{ks, n, gt, slot_of_row.as<uint32_t>()};
-    const int g = pdrs_grid_for(c, n, 256);
-    switch (ks.nwords) {
-      case 1: gr_assign_kernel<1><<<g, 256, 0, c->stream>>>(ap); break;
-      case 2: gr_assign_kernel<2><<<g, 256, 0, c->stream>>>(ap); break;
-      default: gr_assign_kernel<3><<<g, 256, 0, c->stream>>>(ap); break;
-    }
-    c->stats.kernel_launches++;
-    PDRS_CUDA(c, cudaGetLastError());
-  }
-  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, gt.counters, CNT_N * 8, cudaMemcpyDeviceToHost, c->stream));
-  PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars + CNT_N, &gt.hdr[slots].rowsw, 8, cudaMemcpyDeviceToHost, c->stream));
-  PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
-  if (c->pinned_scalars[CNT_OVERFLOW] || c->pinned_scalars[CNT_SPIN_FAIL]) return pdrs_fail(c, PDRS_ERR_CUDA, "pdrs_groupby_rows: group table overflow");
-  const int64_t G = c->pinned_scalars[CNT_NGROUPS] + (((u64)c->pinned_scalars[CNT_N] & GB_FULL) ? 1 : 0);
-  res->n_groups = G;
-  // 3. dense group numbers, keys, sizes, offsets
-  const size_t Galloc = (size_t)std::max<int64_t>(G, 1);
-  CompactParams cp{};
-  cp.fp.gt = gt; cp.fp.ks = ks; cp.fp.nvals = 0; cp.fp.naggs = 0;
+  DistPack pk{};
+  pk.ks = ks; pk.G = G;
   for (int k = 0; k < nkeys; k++) {
     const int kb = (keys[k].dtype == PDRS_I64 || keys[k].dtype == PDRS_F64) ? 8 : (keys[k].dtype == PDRS_BOOL_BITS ? 1 : 4);
     PDRS_TRY(res->key_vals[k].alloc(c, Galloc * kb));
     PDRS_TRY(res->key_nulls[k].alloc(c, Galloc));
-    cp.fp.key_out[k] = res->key_vals[k].p;
-    cp.fp.key_null_out[k] = res->key_nulls[k].as<uint8_t>();
+    if (G > 0) {
+      PDRS_CUDA(c, cudaMemcpyAsync(res->key_vals[k].p, pdrs_groupby_key_dev(cnt, k), (size_t)G * kb, cudaMemcpyDeviceToDevice, c->stream));
+      PDRS_CUDA(c, cudaMemcpyAsync(res->key_nulls[k].p, pdrs_groupby_key_null_dev(cnt, k), (size_t)G, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    pk.key_vals[k] = res->key_vals[k].p;
+    pk.key_null[k] = res->key_nulls[k].as<uint8_t>();
   }
   PDRS_TRY(res->sizes.alloc(c, Galloc * 8));
   PDRS_TRY(res->offsets.alloc(c, (Galloc + 1) * 8, true));
   PDRS_TRY(res->rows.alloc(c, (size_t)std::max<int64_t>(n, 1) * 8));
-  cp.fp.rows_out = res->sizes.as<long long>();
-  cp.gid_of_slot = gid_of_slot.as<uint32_t>();
   if (G > 0) {
-    gr_compact_kernel<<<pdrs_grid_for(c, slots + 1, 256), 256, 0, c->stream>>>(cp);
-    gr_slot_to_gid_kernel<<<pdrs_grid_for(c, n, 256), 256, 0, c->stream>>>(slot_of_row.as<uint32_t>(), n, gid_of_slot.as<uint32_t>());
+    PDRS_CUDA(c, cudaMemcpyAsync(res->sizes.p, pdrs_groupby_group_rows_dev(cnt), (size_t)G * 8, cudaMemcpyDeviceToDevice, c->stream));
+    PDRS_TRY((scan_exclusive<long long, long long>(c, res->sizes.as<long long>(), G, res->offsets.as<long long>(), res->offsets.as<long long>() + G)));
+    // 2. key words -> group number, then row -> group number
+    const long long slots = std::max<long long>(1024, pow2ceil_ll(2 * G + 16));
+    if (slots >= (1ll << 32) - 1) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_groupby_rows: too many groups (%lld)", G);
+    DevBuf k0, k1, k2, tg, misc, gid_of_row;
+    PDRS_TRY(k0.alloc(c, (size_t)slots * 8));
+    if (ks.nwords > 1) PDRS_TRY(k1.alloc(c, (size_t)slots * 8));
+    if (ks.nwords > 2) PDRS_TRY(k2.alloc(c, (size_t)slots * 8));
+    PDRS_TRY(tg.alloc(c, (size_t)slots * 4));
+    PDRS_CUDA(c, cudaMemsetAsync(tg.p, 0xFF, (size_t)slots * 4, c->stream));
+    PDRS_TRY(misc.alloc(c, 16, true));        // [0] the NULL-key group's number (u32), [1] rows whose key was not found (u64)
+    PDRS_TRY(gid_of_row.alloc(c, (size_t)n * 4));
+    LookupTab lt{k0.as<u64>(), k1.as<u64>(), k2.as<u64>(), tg.as<uint32_t>(), (u64)slots - 1, 64 - ceil_log2(slots), misc.as<uint32_t>()};
+    AssignParams ap{ks, n, lt, gid_of_row.as<uint32_t>(), reinterpret_cast<unsigned long long*>(misc.as<u64>() + 1)};
+    const int gb = pdrs_grid_for(c, G, 256), ga = pdrs_grid_for(c, n, 256);
+    switch (ks.nwords) {
+      case 1: gr_table_build_kernel<1><<<gb, 256, 0, c->stream>>>(pk, lt); gr_assign_kernel<1><<<ga, 256, 0, c->stream>>>(ap); break;
+      case 2: gr_table_build_kernel<2><<<gb, 256, 0, c->stream>>>(pk, lt); gr_assign_kernel<2><<<ga, 256, 0, c->stream>>>(ap); break;
+      default: gr_table_build_kernel<3><<<gb, 256, 0, c->stream>>>(pk, lt); gr_assign_kernel<3><<<ga, 256, 0, c->stream>>>(ap); break;
+    }
     c->stats.kernel_launches += 2;
     PDRS_CUDA(c, cudaGetLastError());
-    PDRS_TRY((scan_exclusive<long long, long long>(c, res->sizes.as<long long>(), G, res->offsets.as<long long>(), res->offsets.as<long long>() + G)));
-    // 4. stable sort of the row numbers by group number
-    DevBuf b0, b1;
+    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, misc.as<u64>() + 1, 8, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    pdrs_trace(c, "rows: offsets, table, row -> group");
+    if (c->pinned_scalars[0] != 0) return pdrs_fail(c, PDRS_ERR_CUDA, "pdrs_groupby_rows: %lld rows carry a key the grouping did not report", (long long)c->pinned_scalars[0]);
+    // 3. stable sort of the row numbers by group number
+    DevBuf kb0, kb1, pb0, pb1;
     const int bits = ceil_log2(std::max<long long>(G, 2));
-    if (bits > 8) { PDRS_TRY(b0.alloc(c, (size_t)n * 4)); PDRS_TRY(b1.alloc(c, (size_t)n * 4)); }
-    PDRS_TRY((radix_sort_by_key<uint32_t>(c, slot_of_row.as<uint32_t>(), nullptr, n, bits, b0.as<uint32_t>(), b1.as<uint32_t>(), res->rows.as<long long>(), nullptr)));
+    if (bits > 8) { PDRS_TRY(kb0.alloc(c, (size_t)n * 4)); PDRS_TRY(kb1.alloc(c, (size_t)n * 4)); PDRS_TRY(pb0.alloc(c, (size_t)n * 4)); PDRS_TRY(pb1.alloc(c, (size_t)n * 4)); }
+    PDRS_TRY((radix_sort_pairs<uint32_t>(c, gid_of_row.as<uint32_t>(), nullptr, n, bits, kb0.as<uint32_t>(), kb1.as<uint32_t>(), pb0.as<uint32_t>(), pb1.as<uint32_t>(),
+                                         res->rows.as<long long>(), nullptr)));
   }
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  pdrs_trace(c, "rows: radix sort");
   guard.r = nullptr;
   *out = res;
   return PDRS_OK;
@@ -325,10 +314,18 @@ int32_t pdrs_group_rows_agg(pdrs_group_rows* r, const pdrs_col* val, int32_t op,
     else gr_median_keys_kernel<double><<<gn, 256, 0, c->stream>>>((const double*)v.data, v.nulls, off, rows, G, n, vkey.as<u64>(), gid.as<uint32_t>(), validn.as<unsigned long long>());
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
+    // sort by value (8 passes over the 64-bit images), then - stably - by group number
+    DevBuf k0, k1, gk;
+    PDRS_TRY(k0.alloc(c, (size_t)n * 8));
+    PDRS_TRY(k1.alloc(c, (size_t)n * 8));
     const uint32_t* by_val = nullptr;
-    PDRS_TRY((radix_sort_by_key<u64>(c, vkey.as<u64>(), nullptr, n, 64, b0.as<uint32_t>(), b1.as<uint32_t>(), nullptr, &by_val)));
+    PDRS_TRY((radix_sort_pairs<u64>(c, vkey.as<u64>(), nullptr, n, 64, k0.as<u64>(), k1.as<u64>(), b0.as<uint32_t>(), b1.as<uint32_t>(), nullptr, &by_val)));
+    PDRS_TRY(gk.alloc(c, (size_t)n * 4));
+    gr_gather_u32_kernel<<<gn, 256, 0, c->stream>>>(gid.as<uint32_t>(), by_val, n, gk.as<uint32_t>());
+    c->stats.kernel_launches++;
     const uint32_t* order = nullptr;
-    PDRS_TRY((radix_sort_by_key<uint32_t>(c, gid.as<uint32_t>(), by_val, n, ceil_log2(std::max<long long>(G, 2)), b0.as<uint32_t>(), b1.as<uint32_t>(), nullptr, &order)));
+    PDRS_TRY((radix_sort_pairs<uint32_t>(c, gk.as<uint32_t>(), by_val, n, ceil_log2(std::max<long long>(G, 2)), k0.as<uint32_t>(), k1.as<uint32_t>(), b0.as<uint32_t>(), b1.as<uint32_t>(),
+                                         nullptr, &order)));
     if (is_int) gr_median_pick_kernel<long long><<<gg, 256, 0, c->stream>>>((const long long*)v.data, v.nulls, off, rows, order, validn.as<unsigned long long>(), G, outd.as<double>());
     else gr_median_pick_kernel<double><<<gg, 256, 0, c->stream>>>((const double*)v.data, v.nulls, off, rows, order, validn.as<unsigned long long>(), G, outd.as<double>());
     c->stats.kernel_launches++;

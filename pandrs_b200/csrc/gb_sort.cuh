@@ -1,9 +1,10 @@
-// Device-wide exclusive scan and a STABLE least-significant-digit radix sort of 32-bit payloads by a gathered key (8 bits per pass),
+// Device-wide exclusive scan and a STABLE least-significant-digit radix sort of (key, 32-bit payload) pairs (8 bits per pass),
 // shared by the row-list grouping (gb_rows.cu) and the dictionary encoder (ingest.cu).  Hand-written: no CUB / thrust.
 //   rs_hist_kernel     per-tile (8192 elements) digit histograms, stored digit-major
 //   scan_exclusive     one exclusive scan over [256][tiles] = where every (digit, tile) run starts
 //   rs_scatter_kernel  every warp walks its 1024 elements IN ORDER, 32 per step, ranks them inside the step with MATCH.ANY and
-//                      bumps its private per-digit cursor: no atomics on the output side and equal digits keep their order
+//                      bumps its private per-digit cursor (no atomics, equal digits keep their order); the tile is staged in shared
+//                      memory in output order and written out as contiguous runs
 #pragma once
 #include <algorithm>
 
@@ -73,98 +74,132 @@ inline int32_t scan_exclusive(pdrs_ctx* c, const T* in, long long n, TO* out, T*
   return PDRS_OK;
 }
 
-// ---------------------------------------------------------------- stable LSD radix sort of 32-bit payloads by a gathered key
-// element i of a pass: payload p = pin ? pin[i] : i, key = keys[p], digit = (key >> shift) & 255
+// ---------------------------------------------------------------- stable LSD radix sort of (key, 32-bit payload) pairs
+// Keys travel WITH the payloads (sequential reads in every pass; a gathered key cost one random DRAM sector per element and pass:
+// 20 ms per 1e9 rows just for the histogram).  A pass over one 8192-element tile:
+//   per-warp digit counts -> tile-local exclusive prefix per (digit, warp) -> every warp walks its 1024 elements IN ORDER, 32 per
+//   step, ranks them inside the step with MATCH.ANY and bumps its private cursor (stable, no atomics) -> the element is staged in
+//   shared memory at its tile-local position -> the tile is written out with consecutive threads on consecutive staged elements:
+//   the run of a digit (32 elements on average) goes to consecutive addresses, i.e. whole sectors instead of one 4-byte store each.
+template <typename KT> __device__ __forceinline__ uint32_t rs_dig(KT k, int shift) { return (uint32_t)(k >> shift) & 255u; }
+
 template <typename KT>
-__device__ __forceinline__ uint32_t rs_digit(const KT* __restrict__ keys, const uint32_t* __restrict__ pin, long long i, int shift, uint32_t* payload) {
-  const uint32_t p = pin ? pin[i] : (uint32_t)i;
-  *payload = p;
-  return (uint32_t)(keys[p] >> shift) & 255u;
-}
-template <typename KT>
-__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KT* __restrict__ keys, const uint32_t* __restrict__ pin, long long n, int shift, long long ntiles,
-                                                               uint32_t* __restrict__ hist /*[256][ntiles]*/) {
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KT* __restrict__ keys, long long n, int shift, long long ntiles, uint32_t* __restrict__ hist /*[256][ntiles]*/) {
   __shared__ uint32_t h[256];
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     h[threadIdx.x] = 0;
     __syncthreads();
     const long long base = tile * RS_TILE;
-    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS) {
-      if (base + i < n) { uint32_t p; atomicAdd(&h[rs_digit<KT>(keys, pin, base + i, shift, &p)], 1u); }
-    }
+    for (int i = threadIdx.x; i < RS_TILE; i += RS_THREADS)
+      if (base + i < n) atomicAdd(&h[rs_dig<KT>(keys[base + i], shift)], 1u);
     __syncthreads();
     hist[(long long)threadIdx.x * ntiles + tile] = h[threadIdx.x];
     __syncthreads();
   }
 }
+template <typename KT> constexpr size_t rs_scatter_smem() { return (size_t)RS_TILE * (sizeof(KT) + 4) + (size_t)RS_WARPS * 256 * 4 + 256 * 4 + 64; }
+
+// pay_in == nullptr: payload = element index.  keys_out may be nullptr (last pass).  OUT64: payloads are written as i64.
 template <typename KT, bool OUT64>
-__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KT* __restrict__ keys, const uint32_t* __restrict__ pin, long long n, int shift, long long ntiles,
-                                                                  const uint32_t* __restrict__ gbase /*[256][ntiles] scanned*/, uint32_t* __restrict__ pout, long long* __restrict__ pout64) {
-  __shared__ uint32_t wh[RS_WARPS][256];
+__global__ void __launch_bounds__(RS_THREADS) rs_scatter_kernel(const KT* __restrict__ keys_in, const uint32_t* __restrict__ pay_in, long long n, int shift, long long ntiles,
+                                                                  const uint32_t* __restrict__ gbase /*[256][ntiles] scanned*/, KT* __restrict__ keys_out,
+                                                                  uint32_t* __restrict__ pay_out, long long* __restrict__ pay_out64) {
+  extern __shared__ __align__(16) unsigned char rs_sm[];
+  KT* st_k = reinterpret_cast<KT*>(rs_sm);                               // [RS_TILE] staged keys, tile-local order
+  uint32_t* st_p = reinterpret_cast<uint32_t*>(st_k + RS_TILE);          // [RS_TILE] staged payloads
+  uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(st_p + RS_TILE);   // [RS_WARPS][256] counts, then cursors
+  uint32_t* gdelta = reinterpret_cast<uint32_t*>(wh + RS_WARPS);        // [256] global position - tile-local position of a digit's run
+  __shared__ uint32_t wsum[RS_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     for (int w = 0; w < RS_WARPS; w++) wh[w][threadIdx.x] = 0;
     __syncthreads();
-    const long long wbase = tile * RS_TILE + (long long)warp * RS_WROWS;
-    // the warp's digit counts
+    const long long tbase = tile * RS_TILE, wbase = tbase + (long long)warp * RS_WROWS;
+    const int tcount = (int)min((long long)RS_TILE, n - tbase);
     for (int s = 0; s < RS_WROWS / 32; s++) {
       const long long i = wbase + 32 * s + lane;
-      if (i < n) { uint32_t p; atomicAdd(&wh[warp][rs_digit<KT>(keys, pin, i, shift, &p)], 1u); }
+      if (i < n) atomicAdd(&wh[warp][rs_dig<KT>(keys_in[i], shift)], 1u);
     }
     __syncthreads();
-    // digit d: where the rows of warp 0, 1, ... of this tile go
-    {
+    {   // digit d = threadIdx.x: exclusive prefix over digits (tile-local start of the digit's run), then over the warps inside it
       const int d = threadIdx.x;
-      uint32_t run = gbase[(long long)d * ntiles + tile];
+      uint32_t tot = 0;
+      for (int w = 0; w < RS_WARPS; w++) tot += wh[w][d];
+      uint32_t incl = tot;
+      for (int k = 1; k < 32; k <<= 1) { const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, incl, k); if (lane >= k) incl += o; }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      uint32_t wpre = 0;
+      for (int w = 0; w < warp; w++) wpre += wsum[w];
+      uint32_t run = wpre + incl - tot;
+      gdelta[d] = gbase[(long long)d * ntiles + tile] - run;
       for (int w = 0; w < RS_WARPS; w++) { const uint32_t t = wh[w][d]; wh[w][d] = run; run += t; }
     }
     __syncthreads();
-    // in order: 32 rows per step, ranked inside the warp (rows of one digit keep their order)
     for (int s = 0; s < RS_WROWS / 32; s++) {
       const long long i = wbase + 32 * s + lane;
       const bool act = i < n;
-      uint32_t p = 0;
-      const uint32_t d = act ? rs_digit<KT>(keys, pin, i, shift, &p) : 256u + lane;
+      KT k = 0;
+      if (act) k = keys_in[i];
+      const uint32_t p = act ? (pay_in ? pay_in[i] : (uint32_t)i) : 0u;
+      const uint32_t d = act ? rs_dig<KT>(k, shift) : 256u + lane;
       const uint32_t m = __match_any_sync(0xFFFFFFFFu, d);
       const int leader = __ffs(m) - 1;
       uint32_t b = 0;
       if (act && lane == leader) { b = wh[warp][d]; wh[warp][d] = b + __popc(m); }
       b = __shfl_sync(0xFFFFFFFFu, b, leader);
       if (act) {
-        const uint32_t dst = b + __popc(m & ((1u << lane) - 1u));
-        if (OUT64) pout64[dst] = (long long)p; else pout[dst] = p;
+        const uint32_t pos = b + __popc(m & ((1u << lane) - 1u));
+        st_k[pos] = k;
+        st_p[pos] = p;
       }
       __syncwarp();
+    }
+    __syncthreads();
+    for (int pos = threadIdx.x; pos < tcount; pos += RS_THREADS) {
+      const KT k = st_k[pos];
+      const uint32_t g = (uint32_t)pos + gdelta[rs_dig<KT>(k, shift)];
+      if (keys_out) keys_out[g] = k;
+      if (OUT64) pay_out64[g] = (long long)st_p[pos]; else pay_out[g] = st_p[pos];
     }
     __syncthreads();
   }
 }
 
-// Sorts the payloads 0 .. n-1 (or `first_in`) by keys[payload], stably, looking at key bits [0, bits).  The last pass writes
-// out64 (when given) or leaves the result in *result (one of the two u32 work buffers).
+// Sorts the pairs (keys[i], pay[i]) (pay == nullptr: payload i) by key bits [0, bits), stably.  kbuf / pbuf: two work buffers each
+// (n elements; unused when one pass suffices and out64 is given).  The last pass writes the payloads to out64 (as i64) when given,
+// else leaves them in *result_pay (one of pbuf).  The sorted keys are not kept.
 template <typename KT>
-inline int32_t radix_sort_by_key(pdrs_ctx* c, const KT* keys, const uint32_t* first_in, long long n, int bits, uint32_t* buf0, uint32_t* buf1,
-                          long long* out64, const uint32_t** result) {
+inline int32_t radix_sort_pairs(pdrs_ctx* c, const KT* keys, const uint32_t* pay, long long n, int bits, KT* kbuf0, KT* kbuf1, uint32_t* pbuf0, uint32_t* pbuf1,
+                                long long* out64, const uint32_t** result_pay) {
   const int npass = std::max(1, (bits + 7) / 8);
   const long long ntiles = (n + RS_TILE - 1) / RS_TILE;
   DevBuf hist;
   PDRS_TRY(hist.alloc(c, (size_t)256 * ntiles * 4));
+  const size_t smem = rs_scatter_smem<KT>();
+  PDRS_CUDA(c, cudaFuncSetAttribute(rs_scatter_kernel<KT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     // per device: every call
+  PDRS_CUDA(c, cudaFuncSetAttribute(rs_scatter_kernel<KT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)c->sm_count * 16);
-  const uint32_t* in = first_in;
-  uint32_t* bufs[2] = {buf0, buf1};
-  int nb = in == buf0 ? 1 : 0;
+  const KT* kin = keys;
+  const uint32_t* pin = pay;
+  KT* kb[2] = {kbuf0, kbuf1};
+  uint32_t* pb2[2] = {pbuf0, pbuf1};
+  int nb = (pin == pbuf0 || kin == kbuf0) ? 1 : 0;
   for (int ps = 0; ps < npass; ps++) {
     const bool last = ps + 1 == npass;
-    rs_hist_kernel<KT><<<grid, RS_THREADS, 0, c->stream>>>(keys, in, n, 8 * ps, ntiles, hist.as<uint32_t>());
+    rs_hist_kernel<KT><<<grid, RS_THREADS, 0, c->stream>>>(kin, n, 8 * ps, ntiles, hist.as<uint32_t>());
     c->stats.kernel_launches++;
+    pdrs_trace(c, "  sort: histogram");
     PDRS_TRY((scan_exclusive<uint32_t, uint32_t>(c, hist.as<uint32_t>(), 256 * ntiles, hist.as<uint32_t>(), nullptr)));
-    if (last && out64) rs_scatter_kernel<KT, true><<<grid, RS_THREADS, 0, c->stream>>>(keys, in, n, 8 * ps, ntiles, hist.as<uint32_t>(), nullptr, out64);
-    else rs_scatter_kernel<KT, false><<<grid, RS_THREADS, 0, c->stream>>>(keys, in, n, 8 * ps, ntiles, hist.as<uint32_t>(), bufs[nb], nullptr);
+    pdrs_trace(c, "  sort: scan");
+    if (last && out64) rs_scatter_kernel<KT, true><<<grid, RS_THREADS, smem, c->stream>>>(kin, pin, n, 8 * ps, ntiles, hist.as<uint32_t>(), nullptr, nullptr, out64);
+    else rs_scatter_kernel<KT, false><<<grid, RS_THREADS, smem, c->stream>>>(kin, pin, n, 8 * ps, ntiles, hist.as<uint32_t>(), last ? nullptr : kb[nb], pb2[nb], nullptr);
     c->stats.kernel_launches++;
     PDRS_CUDA(c, cudaGetLastError());
-    if (!(last && out64)) { in = bufs[nb]; nb ^= 1; }
+    pdrs_trace(c, "  sort: scatter");
+    if (!(last && out64)) { kin = kb[nb]; pin = pb2[nb]; nb ^= 1; }
   }
-  if (result) *result = in;
+  if (result_pay) *result_pay = pin;
   return PDRS_OK;
 }
 

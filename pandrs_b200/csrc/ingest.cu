@@ -227,18 +227,21 @@ int32_t pdrs_dict_encode(pdrs_ctx* c, const void* offsets, int32_t offsets_are_6
   }
   if (D < 0) return pdrs_fail(c, PDRS_ERR_CUDA, "pdrs_dict_encode: hash table overflow");
   res->n_unique = D;
-  DevBuf cfirst, cslot, b0, b1, id_of_slot, bad;
+  DevBuf cfirst, cslot, b0, b1, kb0, kb1, id_of_slot, bad;
   PDRS_TRY(cfirst.alloc(c, (size_t)D * 4));
   PDRS_TRY(cslot.alloc(c, (size_t)D * 4));
   PDRS_TRY(b0.alloc(c, (size_t)D * 4));
   PDRS_TRY(b1.alloc(c, (size_t)D * 4));
+  PDRS_TRY(kb0.alloc(c, (size_t)D * 4));
+  PDRS_TRY(kb1.alloc(c, (size_t)D * 4));
   PDRS_TRY(id_of_slot.alloc(c, (size_t)(slots + 1) * 4));
   PDRS_TRY(res->first_rows.alloc(c, (size_t)D * 8));
   PDRS_TRY(bad.alloc(c, 8, true));
   de_compact_kernel<<<pdrs_grid_for(c, slots, 256), 256, 0, c->stream>>>(gt, first.as<uint32_t>(), cfirst.as<uint32_t>(), cslot.as<uint32_t>());
   c->stats.kernel_launches++;
   const uint32_t* order = nullptr;
-  PDRS_TRY((radix_sort_by_key<uint32_t>(c, cfirst.as<uint32_t>(), nullptr, D, ilog2c(std::max<long long>(len, 2)), b0.as<uint32_t>(), b1.as<uint32_t>(), nullptr, &order)));
+  PDRS_TRY((radix_sort_pairs<uint32_t>(c, cfirst.as<uint32_t>(), nullptr, D, ilog2c(std::max<long long>(len, 2)), kb0.as<uint32_t>(), kb1.as<uint32_t>(), b0.as<uint32_t>(), b1.as<uint32_t>(),
+                                       nullptr, &order)));
   de_rank_kernel<<<pdrs_grid_for(c, D, 256), 256, 0, c->stream>>>(order, cfirst.as<uint32_t>(), cslot.as<uint32_t>(), D, id_of_slot.as<uint32_t>(), res->first_rows.as<long long>());
   PDRS_CUDA(c, cudaMemcpyAsync(res->ids.p, slot_of_row.p, (size_t)len * 4, cudaMemcpyDeviceToDevice, c->stream));
   de_map_kernel<<<pdrs_grid_for(c, len, 256), 256, 0, c->stream>>>(res->ids.as<uint32_t>(), len, id_of_slot.as<uint32_t>());

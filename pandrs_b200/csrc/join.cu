@@ -1145,6 +1145,7 @@ __global__ void __launch_bounds__(256, 4) jfat_probe_emit_kernel(JFatTab t, cons
 struct pdrs_join_result {
   pdrs_ctx* ctx = nullptr;
   int64_t n = 0;
+  int64_t cap = 0;                    // pairs the left / right arrays have room for (single-pass path; rounds append)
   DevBuf left, right;
   int npay = 0;                       // pdrs_join_gather: materialised columns of the right frame
   int pay_dtype[PDRS_MAX_VALS] = {};
@@ -1175,6 +1176,8 @@ int32_t pdrs_join_result_concat(pdrs_ctx* c, pdrs_join_result** parts, int n, pd
   *out = res;
   return PDRS_OK;
 }
+
+pdrs_join_result* pdrs_join_result_new(pdrs_ctx* c) { auto* r = new pdrs_join_result(); r->ctx = c; return r; }
 
 struct JPart { DevBuf keys, rows; long long n = 0; };
 static int32_t jpartition(pdrs_ctx* c, const JKeyCol& col, long long n, int log_nb, JPart* out) {
@@ -1234,10 +1237,20 @@ static int32_t jpartition1(pdrs_ctx* c, const JKeyCol& col, long long n, int log
 // Build the table from `rsrc`, probe it with `lsrc` and materialise the pairs into `res` (left / right arrays).
 // nl_out = number of probe rows (capacity of the single-pass output); nl_eff / nr_eff = positions to scan (padded
 // partition layouts scan cap rows per bucket); nr_rows = build rows (size of the CSR array of the duplicate-key case).
+// phases: 1 = build, 2 = probe (3 = both).  `bst` carries what the probe needs to know about the build (duplicate keys: the CSR
+// segments) when the two run in different calls (exchange join in rounds: one build, several probes that APPEND to `res`;
+// cap_hint = pairs to make room for when the arrays are first allocated).
+struct JBuildState { bool dups = false; DevBuf csr; };
 static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& fail, const JSrc& rsrc, long long nr_eff, int64_t nr_rows, const JSrc& lsrc, long long nl_eff,
-                            int64_t nl, bool radix, int how, pdrs_join_result* res, int64_t* M_out, const std::function<void(const char*)>& mark) {
-  DevBuf counts, csr_buf;
+                            int64_t nl, bool radix, int how, pdrs_join_result* res, int64_t* M_out, const std::function<void(const char*)>& mark,
+                            int phases = 3, JBuildState* bst = nullptr, int64_t cap_hint = 0) {
+  DevBuf counts;
+  JBuildState local_state;
+  if (!bst) bst = &local_state;
+  DevBuf& csr_buf = bst->csr;
   const int bctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 8, (nr_eff + 255) / 256));
+  if (phases & 1) {
+  bst->dups = false;
   if (nr_eff > 0) {
     join_build_kernel<0><<<bctas, 256, 0, c->stream>>>(jt, nullptr, rsrc, nr_eff, fail.as<u64>());
     c->stats.kernel_launches++;
@@ -1248,9 +1261,8 @@ static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& fail, const JSr
   PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, fail.p, 32, cudaMemcpyDeviceToHost, c->stream));
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
   if (c->pinned_scalars[0] != 0) return pdrs_fail(c, PDRS_ERR_CUDA, "join build: hash table insertion failed for %lld rows", (long long)c->pinned_scalars[0]);
-  const bool dups = c->pinned_scalars[3] != 0;
-  const uint32_t* csr = nullptr;
-  if (dups) {
+  bst->dups = c->pinned_scalars[3] != 0;
+  if (bst->dups) {
     // Duplicate build keys: head word = number of rows of the key (count pass) -> offset of its segment [length, rows ...] in
     // the CSR array (reserve) -> rows filled in (fill pass) -> every segment sorted ascending, once.
     if (nr_rows >= (1ll << 31) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: %lld build rows with duplicate keys (limit 2^31)", (long long)nr_rows);
@@ -1280,15 +1292,34 @@ static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& fail, const JSr
       c->stats.kernel_launches++;
       PDRS_CUDA(c, cudaGetLastError());
     }
-    csr = csr_buf.as<uint32_t>();
     mark("duplicate keys: segments");
   }
+  }   // phases & 1
+  if (!(phases & 2)) { *M_out = res ? res->n : 0; return PDRS_OK; }
+  const bool dups = bst->dups;
+  const uint32_t* csr = dups ? csr_buf.as<uint32_t>() : nullptr;
   // unique build keys (the usual dimension-table join): single-pass probe + emit.  Needs one output slot per probe row.
   const bool single_pass = radix && c->opt_join_emit != 2 && !dups;   // small inputs keep the reference's left-row-major order
   int64_t M = 0;
   if (single_pass) {
-    PDRS_TRY(res->left.alloc(c, (size_t)std::max<int64_t>(nl, 1) * 8));
-    PDRS_TRY(res->right.alloc(c, (size_t)std::max<int64_t>(nl, 1) * 8));
+    // the pairs of this probe are appended behind the res->n pairs already there (0 except in the later rounds of an exchange join)
+    const int64_t base = res->n, need = base + std::max<int64_t>(nl, 1);
+    if (res->cap < need) {
+      const int64_t ncap = std::max<int64_t>(need, cap_hint);
+      DevBuf nl_buf, nr_buf;
+      PDRS_TRY(nl_buf.alloc(c, (size_t)ncap * 8));
+      PDRS_TRY(nr_buf.alloc(c, (size_t)ncap * 8));
+      if (base > 0) {
+        PDRS_CUDA(c, cudaMemcpyAsync(nl_buf.p, res->left.p, (size_t)base * 8, cudaMemcpyDeviceToDevice, c->stream));
+        PDRS_CUDA(c, cudaMemcpyAsync(nr_buf.p, res->right.p, (size_t)base * 8, cudaMemcpyDeviceToDevice, c->stream));
+      }
+      res->left = std::move(nl_buf); res->right = std::move(nr_buf); res->cap = ncap;
+    }
+    // output cursor = pairs so far, probe tile tickets from 0
+    c->pinned_scalars[16] = base; c->pinned_scalars[17] = 0;
+    PDRS_CUDA(c, cudaMemcpyAsync(fail.as<u64>() + 2, c->pinned_scalars + 16, 8, cudaMemcpyHostToDevice, c->stream));
+    PDRS_CUDA(c, cudaMemcpyAsync(fail.as<u64>() + 4, c->pinned_scalars + 17, 8, cudaMemcpyHostToDevice, c->stream));
+    M = base;
     if (nl_eff > 0) {
       const long long ntiles = (nl_eff + JE_TILE - 1) / JE_TILE;
       const int ctas = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * (c->opt_join_ctas_per_sm > 0 ? c->opt_join_ctas_per_sm : 8), ntiles));
@@ -1312,6 +1343,7 @@ static int32_t jbuild_probe(pdrs_ctx* c, const JTab& jt, DevBuf& fail, const JSr
   PDRS_TRY(stash.alloc(c, (size_t)std::max<int64_t>(nl_eff, 1) * 8));
   u64* cc = counts.as<u64>();
   if (nl_eff > 0) {
+    PDRS_CUDA(c, cudaMemsetAsync(fail.as<u64>() + 2, 0, 8, c->stream));          // tile tickets from 0 (the buffer may have served an earlier probe)
     if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_a, c->stream));
     join_probe_kernel<<<ctas, JOIN_THREADS, 0, c->stream>>>(jt, csr, lsrc, nl_eff, how == PDRS_LEFT, stash.as<long long>(), cc, fail.as<u64>() + 2);
     if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_b, c->stream));
@@ -1650,6 +1682,12 @@ struct pdrs_xjoin {
   void* peer[8] = {};                   // receive areas of all ranks as seen from this process (peer[rank] == base)
   bool ipc_open[8] = {};
   bool attached = false, shuffled = false;
+  // the hash table of the build side outlives a call: later rounds of pdrs_join_pairs_dist shuffle and probe more left rows only
+  DevBuf tab, failb;
+  JTab jt{};
+  JBuildState bst;
+  bool table_ready = false;
+  int64_t nr_built = 0;
 };
 extern "C" {
 
@@ -1746,16 +1784,18 @@ int32_t pdrs_xjoin_attach_ptrs(pdrs_xjoin* x, void* const* bases) {
 // ones (the receiver adds the source's left_row0).  Returns PDRS_ERR_UNSUPPORTED when a sub-bucket overflowed
 // (heavily duplicated / skewed keys): the caller falls back to the all_to_all path.
 int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_col* right_key, int64_t right_row0) {
-  if (!x || !left_key || !right_key) return PDRS_ERR_BAD_ARG;
+  if (!x || !left_key) return PDRS_ERR_BAD_ARG;
   pdrs_ctx* c = x->ctx;
   if (!x->attached) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: peers are not attached");
-  if (left_key->dtype != right_key->dtype)
+  // right_key == NULL: only left rows travel; the build side (and its hash table) of the previous shuffle stays (rounds)
+  if (!right_key && !x->shuffled) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: no build side has been shuffled yet");
+  if (right_key && left_key->dtype != right_key->dtype)
     return pdrs_fail(c, PDRS_ERR_TYPE_MISMATCH, "join key columns have different types (%d vs %d)", left_key->dtype, right_key->dtype);
   PDRS_CUDA(c, cudaSetDevice(c->device));
   ColView lv, rv;
   PDRS_TRY(pdrs_view_col(c, left_key, &lv));
-  PDRS_TRY(pdrs_view_col(c, right_key, &rv));
-  if (right_row0 < 0 || right_row0 + rv.len > x->total_right) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: right rows beyond total_right_rows");
+  if (right_key) { PDRS_TRY(pdrs_view_col(c, right_key, &rv)); x->table_ready = false; }
+  if (right_key && (right_row0 < 0 || right_row0 + rv.len > x->total_right)) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: right rows beyond total_right_rows");
   // the padded regions and (staged layout) the row encoding were sized for the row counts given to pdrs_xjoin_create
   if (lv.len > x->max_left || rv.len > x->max_right)
     return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_shuffle: %lld left / %lld right rows exceed the %lld / %lld given to pdrs_xjoin_create",
@@ -1768,7 +1808,7 @@ int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_c
   u64* ovf = cur.as<u64>() + 2 * ncb;
   PDRS_CUDA(c, cudaFuncSetAttribute(jpart1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)JQ_SMEM));   // per device: every call
   if (c->opt_timing) PDRS_CUDA(c, cudaEventRecord(c->ev_t0, c->stream));
-  for (int side = 0; side < 2; side++) {
+  for (int side = right_key ? 0 : 1; side < 2; side++) {
     const ColView& v = side ? lv : rv;
     const XSide& s = side ? x->L : x->R;
     u64* cursor = cur.as<u64>() + side * ncb;
@@ -1803,8 +1843,9 @@ int32_t pdrs_xjoin_shuffle(pdrs_xjoin* x, const pdrs_col* left_key, const pdrs_c
 // Local join of the received rows (after the barrier): same build / probe kernels as pdrs_join_pairs on the radix
 // path.  left_row0[world] = global number of the first left row of every rank.  Pairs are in GLOBAL row numbers;
 // this rank returns the pairs of the keys whose rank hash maps to it.  Inner and Left only.
-int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, pdrs_join_result** out) {
-  if (!x || !out || !left_row0) return PDRS_ERR_BAD_ARG;
+}  // extern "C"
+// Build (unless the table of this build side exists already) and probe; the pairs are appended to `res`.
+int32_t pdrs_xjoin_local_append(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, pdrs_join_result* res, int64_t cap_hint) {
   pdrs_ctx* c = x->ctx;
   if (how != PDRS_INNER && how != PDRS_LEFT) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_local: only Inner and Left joins are sharded");
   if (!x->shuffled) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_xjoin_local: nothing was shuffled");
@@ -1821,20 +1862,9 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
   int64_t nr = 0, nl = 0;
   for (long long i = 0; i < sb; i++) { nr += (int64_t)hc[i]; nl += (int64_t)hc[sb + i]; }
-  auto* res = new pdrs_join_result();
-  res->ctx = c;
-  struct Guard { pdrs_join_result* r; ~Guard() { delete r; } } guard{res};
-  const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;
-  if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
-  const size_t table_bytes = (size_t)(slots + 4) * 12;
-  DevBuf tab, fail, row0;
-  PDRS_TRY(tab.alloc(c, table_bytes));
-  PDRS_CUDA(c, cudaMemsetAsync(tab.p, 0xFF, table_bytes, c->stream));
-  JTab jt{tab.as<u64>(), reinterpret_cast<uint32_t*>(tab.as<u64>() + slots + 4), (u64)slots, 1u};
-  PDRS_TRY(fail.alloc(c, 64, true));
+  DevBuf row0;
   PDRS_TRY(row0.alloc(c, 64));
   PDRS_CUDA(c, cudaMemcpyAsync(row0.p, left_row0, (size_t)x->world * 8, cudaMemcpyHostToDevice, c->stream));
-  c->stats.table_slots = slots;
   JSrc rsrc{}, lsrc{};
   rsrc.pkeys = reinterpret_cast<const u64*>(base + x->R.keys); rsrc.prows = reinterpret_cast<const uint32_t*>(base + x->R.rows);
   rsrc.cap = x->R.cap; rsrc.cnt = reinterpret_cast<const u64*>(base + x->R.cnt);
@@ -1842,27 +1872,64 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   lsrc.cap = x->L.cap; lsrc.cnt = reinterpret_cast<const u64*>(base + x->L.cnt);
   lsrc.row0 = row0.as<long long>(); lsrc.log_srcs = x->log_world; lsrc.row_shift = x->row_shift;
   long long nr_eff = sb * x->R.cap, nl_eff = sb * x->L.cap;
-  JPart lp, rp;
-  DevBuf lcnt, rcnt;
-  if (x->row_shift && x->log_nb > 1) {
-    // staged mode: the ordinary one-pass radix partition of the single-GPU join, reading the received records
-    for (int side = 0; side < 2; side++) {
-      const XSide& s = side ? x->L : x->R;
-      JSrc& src = side ? lsrc : rsrc;
-      JPart& part = side ? lp : rp;
-      DevBuf& cnt = side ? lcnt : rcnt;
-      const JStaged st{src.pkeys, src.prows, src.cnt, s.cap};
-      long long cap = 0;
-      bool ok = true;
-      PDRS_TRY(jpartition1(c, JKeyCol{}, sb * s.cap, x->log_nb, &part, &cnt, &cap, &ok, &st, side ? nl : nr));
-      if (!ok) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_local: a radix bucket overflowed its padded range (skewed keys)");
-      src.pkeys = part.keys.as<u64>(); src.prows = part.rows.as<uint32_t>(); src.cap = cap; src.cnt = cnt.as<u64>();
-      src.log_nb = c->opt_join_prefetch ? x->log_nb : 0;
-      (side ? nl_eff : nr_eff) = part.n;
-    }
-  }
+  const bool staged = x->row_shift && x->log_nb > 1;
+  // staged mode: the ordinary one-pass radix partition of the single-GPU join, reading the received records
+  auto partition_side = [&](int side, JPart& part, DevBuf& cnt) -> int32_t {
+    const XSide& s = side ? x->L : x->R;
+    JSrc& src = side ? lsrc : rsrc;
+    const JStaged st{src.pkeys, src.prows, src.cnt, s.cap};
+    long long cap = 0;
+    bool ok = true;
+    PDRS_TRY(jpartition1(c, JKeyCol{}, sb * s.cap, x->log_nb, &part, &cnt, &cap, &ok, &st, side ? nl : nr));
+    if (!ok) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "pdrs_xjoin_local: a radix bucket overflowed its padded range (skewed keys)");
+    src.pkeys = part.keys.as<u64>(); src.prows = part.rows.as<uint32_t>(); src.cap = cap; src.cnt = cnt.as<u64>();
+    src.log_nb = c->opt_join_prefetch ? x->log_nb : 0;
+    (side ? nl_eff : nr_eff) = part.n;
+    return PDRS_OK;
+  };
   int64_t M = 0;
-  PDRS_TRY(jbuild_probe(c, jt, fail, rsrc, nr_eff, nr, lsrc, nl_eff, nl, true, how, res, &M, [](const char*) {}));
+  if (!x->table_ready) {
+    const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;
+    if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
+    const size_t table_bytes = (size_t)(slots + 4) * 12;
+    PDRS_TRY(x->tab.alloc(c, table_bytes));
+    PDRS_CUDA(c, cudaMemsetAsync(x->tab.p, 0xFF, table_bytes, c->stream));
+    x->jt = JTab{x->tab.as<u64>(), reinterpret_cast<uint32_t*>(x->tab.as<u64>() + slots + 4), (u64)slots, 1u};
+    PDRS_TRY(x->failb.alloc(c, 64, true));
+    x->bst = JBuildState();
+    JPart rp;
+    DevBuf rcnt;
+    if (staged) PDRS_TRY(partition_side(0, rp, rcnt));
+    PDRS_TRY(jbuild_probe(c, x->jt, x->failb, rsrc, nr_eff, nr, lsrc, 0, 0, true, how, res, &M, [](const char*) {}, 1, &x->bst));
+    x->table_ready = true;
+    x->nr_built = nr;
+  }
+  c->stats.table_slots = (int64_t)x->jt.slots;
+  JPart lp;
+  DevBuf lcnt;
+  if (staged) PDRS_TRY(partition_side(1, lp, lcnt));
+  if (!x->bst.dups || res->n == 0) {
+    PDRS_TRY(jbuild_probe(c, x->jt, x->failb, rsrc, 0, x->nr_built, lsrc, nl_eff, nl, true, how, res, &M, [](const char*) {}, 2, &x->bst, cap_hint));
+  } else {
+    // duplicate build keys take the count / scan / write path, which sizes its own arrays: probe into a temporary, then append
+    pdrs_join_result tmp;
+    tmp.ctx = c;
+    PDRS_TRY(jbuild_probe(c, x->jt, x->failb, rsrc, 0, x->nr_built, lsrc, nl_eff, nl, true, how, &tmp, &M, [](const char*) {}, 2, &x->bst));
+    const int64_t need = res->n + tmp.n;
+    DevBuf nl_buf, nr_buf;
+    PDRS_TRY(nl_buf.alloc(c, (size_t)std::max<int64_t>(need, 1) * 8));
+    PDRS_TRY(nr_buf.alloc(c, (size_t)std::max<int64_t>(need, 1) * 8));
+    if (res->n) {
+      PDRS_CUDA(c, cudaMemcpyAsync(nl_buf.p, res->left.p, (size_t)res->n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      PDRS_CUDA(c, cudaMemcpyAsync(nr_buf.p, res->right.p, (size_t)res->n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (tmp.n) {
+      PDRS_CUDA(c, cudaMemcpyAsync(nl_buf.as<int64_t>() + res->n, tmp.left.p, (size_t)tmp.n * 8, cudaMemcpyDeviceToDevice, c->stream));
+      PDRS_CUDA(c, cudaMemcpyAsync(nr_buf.as<int64_t>() + res->n, tmp.right.p, (size_t)tmp.n * 8, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    res->left = std::move(nl_buf); res->right = std::move(nr_buf); res->n = need; res->cap = need;
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   c->stats.groupby_algo_used = 2;
   if (c->opt_timing) {
     PDRS_CUDA(c, cudaEventRecord(c->ev_t1, c->stream));
@@ -1871,7 +1938,16 @@ int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, p
   } else {
     PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
   }
-  guard.r = nullptr;
+  return PDRS_OK;
+}
+extern "C" {
+
+int32_t pdrs_xjoin_local(pdrs_xjoin* x, int32_t how, const int64_t* left_row0, pdrs_join_result** out) {
+  if (!x || !out || !left_row0) return PDRS_ERR_BAD_ARG;
+  auto* res = new pdrs_join_result();
+  res->ctx = x->ctx;
+  const int32_t rc = pdrs_xjoin_local_append(x, how, left_row0, res, 0);
+  if (rc != PDRS_OK) { delete res; return rc; }
   *out = res;
   return PDRS_OK;
 }

@@ -1,0 +1,13 @@
+import sys
+sys.path.insert(0, ".")
+import pandrs_b200 as pb
+ctx = pb.Context(0)
+n = 1_000_000_000
+for card in (1000, 10_000_000):
+    keys = ctx.synth_keys(n, card=card)
+    r = ctx.groupby_rows([keys]); r.close()
+    ctx.set_option("trace", 1)
+    print("card", card, file=sys.stderr, flush=True)
+    r = ctx.groupby_rows([keys]); r.close()
+    ctx.set_option("trace", 0)
+    ctx.free(keys)
