@@ -869,6 +869,24 @@ def extras(ctx, pb, args, n, keys, vals, peak):
     log("extras: sum only, 10M groups, joins")
     ms, kms = timed(lambda: gb(keys, vals, [(0, pb.SUM)]))
     ex["groupby_sum_1k"] = {"rows_per_s": n / (ms * 1e-3), "ms": ms, "kernel_ms": kms, "roofline_frac": ALG_BYTES_PER_ROW * n / (kms * 1e-3) / 1e9 / peak}
+    # rows next to the path: the row lists of the groups (par_groupby, grouping.rs:124-331) and Median over them
+    try:
+        def rows():
+            r = ctx.groupby_rows([keys])
+            r.close()
+        ms, _ = timed(rows, reps=2)
+        ex["par_groupby_rows_1k"] = {"rows_per_s": n / (ms * 1e-3), "ms": ms, "alg_bytes_per_row": 16.0, "roofline_frac": 16.0 * n / (ms * 1e-3) / 1e9 / peak,
+                                     "what": "pdrs_groupby_rows: keys in (8 B/row), ascending row ids per group out (8 B/row)"}
+        m = min(n, 200_000_000)
+        km, vm = pb.Column(pb.I64, device_ptr=keys.ptr, length=m), pb.Column(pb.F64, device_ptr=vals.ptr, nulls_ptr=vals.nulls_ptr, null_len=(m + 7) // 8, length=m)
+        r = ctx.groupby_rows([km])
+        try:
+            ms, _ = timed(lambda: r.agg(vm, pb.MEDIAN), reps=2)
+        finally:
+            r.close()
+        ex["median_1k_2e8_rows"] = {"rows_per_s": m / (ms * 1e-3), "ms": ms, "rows": m}
+    except Exception as e:  # noqa: BLE001
+        ex["par_groupby_rows_1k"] = {"error": str(e)[:200]}
     try:
         k10 = ctx.synth_keys(n, card=10_000_000, seed=7)
         ms, kms = timed(lambda: gb(k10, vals, [(0, op) for op in (pb.SUM, pb.MEAN, pb.MIN, pb.MAX, pb.COUNT, pb.STD)]), reps=2)

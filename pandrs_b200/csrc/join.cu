@@ -1888,17 +1888,26 @@ int32_t pdrs_xjoin_local_append(pdrs_xjoin* x, int32_t how, const int64_t* left_
     return PDRS_OK;
   };
   int64_t M = 0;
+  JPart rp;               // (alive until the end of the call: a multi-GB free in the middle of it would slow the allocations that follow)
+  DevBuf rcnt;
   if (!x->table_ready) {
     const long long slots = (std::max<long long>(1024, (c->opt_join_slots_mult > 0 ? c->opt_join_slots_mult : 3) * nr) + 3) / 4 * 4;
     if (slots >= (1ll << 32) - 8) return pdrs_fail(c, PDRS_ERR_UNSUPPORTED, "join: build side too large (%lld rows)", (long long)nr);
     const size_t table_bytes = (size_t)(slots + 4) * 12;
-    PDRS_TRY(x->tab.alloc(c, table_bytes));
+    // the table of the previous call is reused when it is large enough (a free immediately followed by an allocation of the same
+    // multi-GB size is exactly what the pool handles badly, see pdrs_settle_frees)
+    if (x->tab.bytes < table_bytes || x->tab.bytes > table_bytes + table_bytes / 4) {
+      x->tab.release();
+      pdrs_settle_frees(c);
+      PDRS_TRY(x->tab.alloc(c, table_bytes));
+    }
     PDRS_CUDA(c, cudaMemsetAsync(x->tab.p, 0xFF, table_bytes, c->stream));
     x->jt = JTab{x->tab.as<u64>(), reinterpret_cast<uint32_t*>(x->tab.as<u64>() + slots + 4), (u64)slots, 1u};
-    PDRS_TRY(x->failb.alloc(c, 64, true));
-    x->bst = JBuildState();
-    JPart rp;
-    DevBuf rcnt;
+    if (!x->failb.p) PDRS_TRY(x->failb.alloc(c, 64));
+    PDRS_CUDA(c, cudaMemsetAsync(x->failb.p, 0, 64, c->stream));
+    x->bst.csr.release();
+    x->bst.dups = false;
+    pdrs_settle_frees(c);
     if (staged) PDRS_TRY(partition_side(0, rp, rcnt));
     PDRS_TRY(jbuild_probe(c, x->jt, x->failb, rsrc, nr_eff, nr, lsrc, 0, 0, true, how, res, &M, [](const char*) {}, 1, &x->bst));
     x->table_ready = true;
