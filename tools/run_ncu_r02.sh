@@ -8,4 +8,6 @@ F="python tools/time_c5.py 200000000"
 $F > gpurun_out/plain_c5_r02.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:gb_few_kernel -c 1 -f -o gpurun_out/prof_few_r02 $F > gpurun_out/ncu_few_r02.log 2>&1
 R="python tools/trace_rows.py 200000000"
 $R > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:rs_scatter_kernel -c 1 -f -o gpurun_out/prof_rs_r02 $R > gpurun_out/ncu_rs_r02.log 2>&1
+for r in ts few rs; do python tools/ncu_summary.py gpurun_out/prof_${r}_r02.ncu-rep --top 25 > gpurun_out/ncu_${r}_r02_summary.txt 2>&1; done
 ls -la gpurun_out/*.ncu-rep | tail -4
+rm -f gpurun_out/prof_ts_r02.ncu-rep gpurun_out/prof_few_r02.ncu-rep gpurun_out/prof_rs_r02.ncu-rep      # (> 64 MiB together: only the summaries travel back)
