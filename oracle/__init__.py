@@ -327,3 +327,85 @@ def pair_checksum(left, right) -> int:
     """The checksum typed_join reports, from numpy index arrays."""
     with np.errstate(over="ignore"):
         return int(((np.asarray(left).astype(np.uint64) * np.uint64(PAIR_MIX_A)) ^ (np.asarray(right).astype(np.uint64) * np.uint64(PAIR_MIX_B))).sum(dtype=np.uint64))
+
+
+# ---------------------------------------------------------------- the LEGACY DataFrame::groupby (string-materialised Series)
+_LEGACY_F64 = None
+
+
+def _rust_parse_f64(s: str):
+    """`str::parse::<f64>()`: sign, digits with optional fraction / exponent, or inf / infinity / nan in any case; nothing else."""
+    global _LEGACY_F64
+    if _LEGACY_F64 is None:
+        import re
+        _LEGACY_F64 = re.compile(r"^[+-]?((\d+\.?\d*|\.\d+)([eE][+-]?\d+)?|inf|infinity|nan)$", re.IGNORECASE)
+    return float(s) if _LEGACY_F64.match(s) else None
+
+
+def rust_f64_to_string(v: float) -> str:
+    if np.isnan(v):
+        return "NaN"
+    if np.isinf(v):
+        return "-inf" if v < 0 else "inf"
+    return np.format_float_positional(v, trim="-")
+
+
+def legacy_groupby(columns: dict, by, aggs) -> dict:
+    """Pure-Python restatement (small inputs only) of src/dataframe/groupby.rs: DataFrameGroupBy::new (:196-228, groups keyed by
+    the key STRINGS), agg (:258-300) and calculate_aggregation (:443-532: the value cells of a group parsed as f64, unparseable ones
+    skipped; no parseable cell -> 0.0; Count = parseable cells; Std / Var two-pass with n - 1, <= 1 value -> 0.0; Median of the
+    sorted values).  columns: {name: [str, ...]}; by: [names]; aggs: [(column, func name, alias)].
+    Returns {key tuple: {alias: result string}} with the results formatted like `agg_result.to_string()` (:291)."""
+    n = len(next(iter(columns.values()))) if columns else 0
+    groups = {}
+    for row in range(n):
+        groups.setdefault(tuple(columns[c][row] for c in by), []).append(row)
+    out = {}
+    for key, rows in groups.items():
+        rec = {}
+        for col, func, alias in aggs:
+            vals = [p for p in (_rust_parse_f64(columns[col][r]) for r in rows) if p is not None]
+            if not vals:
+                r = 0.0
+            elif func == "sum":
+                r = 0.0
+                for x in vals:
+                    r += x
+            elif func == "mean":
+                s = 0.0
+                for x in vals:
+                    s += x
+                r = s / len(vals)
+            elif func == "min":
+                r = float("inf")
+                for x in vals:
+                    r = r if x != x else (x if r != r else min(r, x))          # f64::min ignores a NaN operand
+            elif func == "max":
+                r = float("-inf")
+                for x in vals:
+                    r = r if x != x else (x if r != r else max(r, x))
+            elif func == "count":
+                r = float(len(vals))
+            elif func in ("std", "var"):
+                if len(vals) <= 1:
+                    r = 0.0
+                else:
+                    s = 0.0
+                    for x in vals:
+                        s += x
+                    m = s / len(vals)
+                    q = 0.0
+                    for x in vals:
+                        q += (x - m) * (x - m)
+                    r = q / (len(vals) - 1)
+                    if func == "std":
+                        r = float(np.sqrt(r))
+            elif func == "median":
+                sv = sorted(vals)
+                mid = len(sv) // 2
+                r = (sv[mid - 1] + sv[mid]) / 2.0 if len(sv) % 2 == 0 else sv[mid]
+            else:
+                raise ValueError(func)
+            rec[alias] = rust_f64_to_string(r)
+        out[key] = rec
+    return out

@@ -685,7 +685,7 @@ int32_t gb_part_pass(pdrs_ctx* c, const GbParams& gp, int is_int, int flags, lon
       const int sctas = (int)std::min<long long>(c->sm_count, tiles);
       sp.part_chunk_tiles = (int)((tiles + sctas - 1) / sctas);
       sp.part_cpp = (int)((tiles + sp.part_chunk_tiles - 1) / sp.part_chunk_tiles);
-      sp.ts_team = 0;
+      sp.ts_team = c->opt_tsort_team == 1 ? 1 : 0;
       int s_nt = ts_nt, s_gpt = ts_gpt, s_slots = ts_slots;
       size_t s_smem = ts_smem;
       if (gb_tsort_geometry(2047, false, c->smem_optin, 512, &s_nt, &s_gpt, &s_slots, &s_smem)) {      // room for every hot key (<= 1800) + some more

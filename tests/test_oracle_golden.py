@@ -434,3 +434,15 @@ def test_median_first_last_semantics(oracle):
     assert r["aggs"][0][0] == -1.0          # wrapping add (release build), then / 2.0
     s = oracle.Col(oracle.DICT_U32, np.zeros(2, np.uint32))
     assert oracle.groupby([oracle.Col(oracle.I64, np.zeros(2, np.int64))], [s], [(0, oracle.MEDIAN)])["error"] == 1     # aggregation.rs:748-752
+
+
+def test_legacy_dataframe_groupby_restatement(oracle):
+    # src/dataframe/groupby.rs:443-532 on the value fixture of src/dataframe/pandas_compat/groupby.rs:480-510 (A: 10, 30, 50; B: 20, 40):
+    # sums 90 / 60, means 30 / 30, std 20 / 14.14..., Count = parseable cells, results formatted like f64::to_string()
+    cols = {"category": ["A", "B", "A", "B", "A"], "value": ["10", "20", "30", "40", "50"]}
+    r = oracle.legacy_groupby(cols, ["category"], [("value", f, f) for f in ("sum", "mean", "min", "max", "count", "std", "var", "median")])
+    assert r[("A",)] == {"sum": "90", "mean": "30", "min": "10", "max": "50", "count": "3", "std": "20", "var": "400", "median": "30"}
+    assert r[("B",)] == {"sum": "60", "mean": "30", "min": "20", "max": "40", "count": "2", "std": "14.142135623730951", "var": "200", "median": "30"}
+    # unparseable cells are skipped; a group without a parseable cell gives 0; the parse grammar is Rust's, not Python's
+    r = oracle.legacy_groupby({"k": ["a", "a", "a", "b"], "v": [" 4", "1_0", "+.5", "x"]}, ["k"], [("v", "sum", "s"), ("v", "count", "c")])
+    assert r == {("a",): {"s": "0.5", "c": "1"}, ("b",): {"s": "0", "c": "0"}}

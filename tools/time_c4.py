@@ -42,8 +42,13 @@ def col(dtype, t):
 ALL6 = [(0, op) for op in (pb.SUM, pb.MEAN, pb.MIN, pb.MAX, pb.COUNT, pb.STD)]
 ku = torch.randint(0, 24_000_000, (n,), device=dev, generator=g, dtype=torch.int64)
 torch.cuda.synchronize()
+for kv in filter(None, os.environ.get("PDRS_OPTS", "").split(",")):       # e.g. PDRS_OPTS=tsort_heavy=128 (experiments)
+    ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+only = os.environ.get("C4_CASE")
 for name, keys, bpr in (("uniform i64, 24M groups", [col(pb.I64, ku)], 16.0),("dictionary key", [col(pb.DICT_U32, k3)], 12.0), ("(i32, i64)", [col(pb.I32, k1), col(pb.I64, k2)], 20.0),
                         ("(i32, i64, dictionary)", [col(pb.I32, k1), col(pb.I64, k2), col(pb.DICT_U32, k3)], 24.0))[0 if len(sys.argv) < 4 else 1:]:
+    if only and only not in name:
+        continue
     for opt in ((0, 1), (2, 1)) if len(sys.argv) > 2 else ((0, 1),):
         ctx.set_option("part_hash", opt[0])
         best = 1e9
