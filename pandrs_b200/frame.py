@@ -589,8 +589,9 @@ def _aggregate(df: OptimizedDataFrame, keys: List[str], aggs: List[AggSpec], mul
     except PandrsError as e:
         raise OperationFailed(str(e)) from e
     finally:
-        if filter_col is not None:
+        if filter_col is not None:                                 # the context may be shared: leave no option behind
             ctx.set_option("compat_filter_nulls", 0)
+            ctx.set_option("compat_empty_string_id", 0xFFFFFFFF)
     try:
         key_strs = []
         for i, k in enumerate(kcols):

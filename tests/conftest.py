@@ -29,6 +29,16 @@ def ctx():
     c.close()
 
 
+@pytest.fixture
+def fctx(ctx):
+    """The shared context as the context of the frame mirror (pandrs_b200.frame) for ONE test: whatever was there before comes back."""
+    import pandrs_b200.frame as fr
+    prev = fr._CTX
+    fr.set_context(ctx)
+    yield ctx
+    fr.set_context(prev)
+
+
 def pytest_sessionfinish(session, exitstatus):
     """The measured f64 errors of the CUDA path (tests/_util.py: compare_groupby) - printed and kept, so that the 1e-12
     claim is a number on record: per op [max |gpu - reference| / scale, max |gpu - exact| / |exact|]."""

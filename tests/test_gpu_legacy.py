@@ -39,9 +39,9 @@ def _compare(oracle, cols, by, value_cols):
     return got
 
 
-def test_legacy_groupby_goldens(ctx, oracle):
+def test_legacy_groupby_goldens(fctx, oracle):
     # the value fixture of src/dataframe/pandas_compat/groupby.rs:480-510 through DataFrame::groupby
-    F.set_context(ctx)
+    ctx = fctx
     cols = {"category": ["A", "B", "A", "B", "A"], "value": ["10", "20", "30", "40", "50"], "score": ["1", "2", "3", "4", "5"]}
     got = _compare(oracle, cols, ["category"], ["value", "score"])
     rows = dict(zip(got.get_column_string_values("category"), zip(got.get_column_string_values("value_sum"), got.get_column_string_values("value_mean"),
@@ -59,9 +59,9 @@ def test_legacy_groupby_goldens(ctx, oracle):
         g.agg([L.NamedAgg("value", L.AggFunc.Nunique, "u")])
 
 
-def test_legacy_groupby_random_strings(ctx, oracle):
+def test_legacy_groupby_random_strings(fctx, oracle):
     # unparseable cells are skipped (Count = parseable cells), empty strings, a literal "NULL" key is just a string, inf / nan / exponents
-    F.set_context(ctx)
+    ctx = fctx
     rng = np.random.default_rng(3)
     n = 4000
     pool = ["x", "NULL", "", "7", "a_b"]
@@ -83,7 +83,7 @@ def test_legacy_groupby_random_strings(ctx, oracle):
     assert all(got.get_column_string_values(f"v_{nm}")[i] == "0" for _, nm in FUNCS)
 
 
-def test_optimize_dataframe_type_inference(ctx):
+def test_optimize_dataframe_type_inference(fctx):
     # optimized/convert.rs:13-110
     df = L.DataFrame()
     df.add_column("i", L.Series(["1", "", "-3"])).add_column("f", L.Series(["1.5", "2", ""])).add_column("b", L.Series(["true", "0", ""]))
@@ -92,6 +92,6 @@ def test_optimize_dataframe_type_inference(ctx):
     assert [o.column_type(c) for c in "ifbs"] == [F.ColumnType.Int64, F.ColumnType.Float64, F.ColumnType.Boolean, F.ColumnType.String]
     assert list(o.column("i").values) == [1, 0, -3] and list(o.column("f").values) == [1.5, 2.0, 0.0]
     assert list(o.column("b").values) == [True, False, False] and o.column("s").to_list() == ["a", "1", ""]
-    F.set_context(ctx)
+    ctx = fctx
     out = o.group_by(["s"]).aggregate([("i", F.AggregateOp.Sum, "t")])
     assert dict(zip(out.column("s").to_list(), out.column("t").values)) == {"a": 1.0, "1": 0.0, "": -3.0}

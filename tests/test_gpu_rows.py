@@ -63,10 +63,10 @@ def test_row_lists_multi_key_and_label_collisions(ctx, oracle):
     _check_rows(ctx, oracle, [Spec(pb.I32, rng.integers(-3, 3, n).astype(np.int32), nulls=rng.random(n) < 0.1), k2])
 
 
-def test_frame_par_groupby_fixtures(ctx, oracle):
+def test_frame_par_groupby_fixtures(fctx, oracle):
     # tests/optimized_groupby_test.rs:6-31 and :138-171 (the reference only asserts "not empty"; the oracle restates the rest)
     from pandrs_b200 import frame as F
-    F.set_context(ctx)
+    ctx = fctx
     df = F.OptimizedDataFrame()
     df.add_int_column("values", [10, 20, 30, 40, 50])
     df.add_string_column("keys", ["A", "B", "A", "B", "C"])
@@ -123,9 +123,9 @@ def test_median_first_last(ctx, oracle, n, card):
         res.close()
 
 
-def test_frame_median_first_last(ctx, oracle):
+def test_frame_median_first_last(fctx, oracle):
     from pandrs_b200 import frame as F
-    F.set_context(ctx)
+    ctx = fctx
     df = F.OptimizedDataFrame()
     df.add_string_column("k", ["A", "B", "A", "B", "A", "C"])
     df.add_column("v", F.Int64Column([5, 20, 1, 40, 3, 9], nulls=[False, False, False, False, False, True]))
@@ -186,10 +186,10 @@ def test_dict_encode_first_occurrence_ids(ctx, n, card, large):
             enc.close()
 
 
-def test_from_record_batch_then_groupby(ctx, oracle):
+def test_from_record_batch_then_groupby(fctx, oracle):
     pa = pytest.importorskip("pyarrow")
     from pandrs_b200 import frame as F
-    F.set_context(ctx)
+    ctx = fctx
     rng = np.random.default_rng(77)
     n = 20_000
     cat = [None if rng.random() < 0.03 else "c%d" % rng.integers(0, 12) for _ in range(n)]

@@ -17,6 +17,7 @@ def sctx(ctx):
     # every host input streams: 65 536-row chunks
     ctx.set_option("stream_rows", 1)
     ctx.set_option("stream_chunk_rows", 65536)
+    ctx.set_option("compat_empty_string_id", 0xFFFFFFFF)       # (the session context is shared: start from the default)
     yield ctx
     ctx.set_option("stream_rows", 1 << 25)
     ctx.set_option("stream_chunk_rows", 0)
