@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) gr_assign_kernel(const AssignParams p) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += (long long)gridDim.x * blockDim.x) {
     u64 w[NW];
     uint32_t g = GR_EMPTY;
-    if (load_key_generic<NW>(p.ks, i, w)) g = null_gid;
+    if (load_key_inline<NW>(p.ks, i, w)) g = null_gid;       // (inlined packer: the parameter block stays in the constant bank, no local copy of the KeySpec)
     else {
       u64 slot = key_hash<NW>(w) >> p.t.shift;
       for (u64 probe = 0; probe <= p.t.mask; probe++) {
