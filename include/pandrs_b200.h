@@ -237,7 +237,7 @@ int32_t pdrs_arrow_validity_to_nulls(pdrs_ctx* ctx, const uint8_t* validity, int
  * in a row loop); a NULL row is the empty string (its placeholder in StringColumn::with_nulls) and keeps its bit in the null mask.
  * first_rows[id] = the first row carrying that string (the host reads the text from its own copy of the array and interns it;
  * pdrs_dict_remap then rewrites the ids into the ids of an existing pool).  Strings are compared through two independent 64-bit
- * hashes; a verification pass compares the BYTES of every row with those of its id's first row and the call fails with
+ * hashes (the offsets are validated first: ascending, inside the value bytes - PDRS_ERR_BAD_ARG otherwise); a verification pass compares the BYTES of every row with those of its id's first row and the call fails with
  * PDRS_ERR_UNSUPPORTED should they ever differ - ids are never wrong.  offsets / bytes / validity live where `mem` says. */
 typedef struct pdrs_dict pdrs_dict;
 int32_t pdrs_dict_encode(pdrs_ctx* ctx, const void* offsets /* len + 1 */, int32_t offsets_are_64, const uint8_t* bytes, int64_t nbytes,

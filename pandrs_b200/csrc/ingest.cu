@@ -67,6 +67,16 @@ __device__ __forceinline__ void de_range(const DictIn& in, long long i, long lon
   else { *lo = reinterpret_cast<const int*>(in.offsets)[i]; *hi = reinterpret_cast<const int*>(in.offsets)[i + 1]; }
 }
 
+// the offsets must describe the byte array before any kernel follows them: ascending, inside [0, nbytes]
+__global__ void de_check_offsets_kernel(const DictIn in, long long nbytes, unsigned long long* __restrict__ bad) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += (long long)gridDim.x * blockDim.x) {
+    long long lo, hi;
+    if (in.off64) { lo = reinterpret_cast<const long long*>(in.offsets)[i]; hi = reinterpret_cast<const long long*>(in.offsets)[i + 1]; }
+    else { lo = reinterpret_cast<const int*>(in.offsets)[i]; hi = reinterpret_cast<const int*>(in.offsets)[i + 1]; }
+    if (lo < 0 || hi < lo || hi > nbytes) atomicAdd(bad, 1ull);
+  }
+}
+
 struct HashParams { DictIn in; GTable gt; uint32_t* first; uint32_t* slot_of_row; };
 __global__ void __launch_bounds__(256) de_hash_kernel(const HashParams p) {
   const int lane = threadIdx.x & 31;
@@ -198,8 +208,16 @@ int32_t pdrs_dict_encode(pdrs_ctx* c, const void* offsets, int32_t offsets_are_6
     c->stats.kernel_launches++;
     res->has_nulls = true;
   }
-  // the offsets must describe the byte array: checked on the host side of the boundary only for their ends (a kernel that walks
-  // a corrupt offsets array would fault, like any borrowed-memory API)
+  {
+    DevBuf badoff;
+    PDRS_TRY(badoff.alloc(c, 8, true));
+    de_check_offsets_kernel<<<pdrs_grid_for(c, len, 256), 256, 0, c->stream>>>(in, nbytes, badoff.as<unsigned long long>());
+    c->stats.kernel_launches++;
+    PDRS_CUDA(c, cudaGetLastError());
+    PDRS_CUDA(c, cudaMemcpyAsync(c->pinned_scalars, badoff.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    PDRS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->pinned_scalars[0]) return pdrs_fail(c, PDRS_ERR_BAD_ARG, "pdrs_dict_encode: %lld offsets are descending or outside the %lld value bytes", (long long)c->pinned_scalars[0], (long long)nbytes);
+  }
   DevBuf slot_of_row;
   PDRS_TRY(slot_of_row.alloc(c, (size_t)len * 4));
   // table: first for at most ~n / 10 distinct strings, then for any number of them

@@ -186,6 +186,17 @@ def test_dict_encode_first_occurrence_ids(ctx, n, card, large):
             enc.close()
 
 
+def test_dict_encode_rejects_corrupt_offsets(ctx):
+    data = np.frombuffer(b"abcdef", np.uint8)
+    for off in ([0, 2, 1, 6], [0, 2, 4, 9], [-1, 2, 4, 6]):
+        with pytest.raises(pb.PandrsError) as e:
+            ctx.dict_encode(np.array(off, np.int32), data)
+        assert e.value.kind == "InvalidInput"
+    enc = ctx.dict_encode(np.array([0, 2, 4, 6], np.int64), data)
+    assert enc.n_unique == 3 and list(enc.ids()) == [0, 1, 2]
+    enc.close()
+
+
 def test_from_record_batch_then_groupby(fctx, oracle):
     pa = pytest.importorskip("pyarrow")
     from pandrs_b200 import frame as F
