@@ -365,9 +365,14 @@ def bench_groupby(env, args, pb, out_extra):
     vals = ctx.synth_vals(n, row0=rank * n, null_per_million=NULL_PER_MILLION)
     ctx.sync()
 
+    # up to groups_cap (4096) groups per rank every rank returns ALL groups (one all-gather of the states); beyond that the states are
+    # exchanged by hash(key) mod ranks (one all-to-all) and every rank returns the groups it owns
+    sharded = world > 1 and args.groups > 4000
+    env.sharded_result = sharded
+
     def run(k=keys, v=vals):
         if world > 1:
-            return env.comm.groupby_agg([k], [v], aggs, result_mode=pb.Comm.REPLICATED)
+            return env.comm.groupby_agg([k], [v], aggs, result_mode=pb.Comm.SHARDED if sharded else pb.Comm.REPLICATED)
         return ctx.groupby_agg([k], [v], aggs)
 
     def step():
@@ -394,7 +399,10 @@ def bench_groupby(env, args, pb, out_extra):
            "config": groupby_config(args, n, args.scaling), "roofline": roofline, "gpu_launches": launches, "clocks": clk}
     if world > 1:
         ex_ms, ex_bytes = env.comm.last_exchange()
-        out["exchange"] = {"kind": "ncclAllGather of per-group states (fixed size) + merge kernel, inside pdrs_groupby_agg_dist", "ms": ex_ms, "bytes_to_peers_per_gpu": ex_bytes}
+        nvl = float(env.peaks.get("nvlink_gbs", 770.0))
+        out["exchange"] = {"kind": ("all-to-all (ncclSend / ncclRecv) of per-group states by hash(key) mod ranks + merge by the owner" if sharded else
+                                    "ncclAllGather of per-group states (fixed size) + merge kernel") + ", inside pdrs_groupby_agg_dist",
+                           "ms": ex_ms, "bytes_to_peers_per_gpu": ex_bytes, "nvlink_gbs_achieved": ex_bytes / (ex_ms * 1e-3) / 1e9 if ex_ms else None, "nvlink_peak_gbs": nvl}
     log(f"headline: {ms_per_step:.3f} ms/step (kernel {k_ms:.3f} ms)")
 
     # ---- the result of one more step, checked outside the timed region
@@ -439,10 +447,18 @@ def parity_groupby(env, pb, run, keys, vals, n, args, ops):
     if env.dist is not None:
         env.dist.all_reduce(t)
     ref_sum, ref_cnt = float(t[0].item()), int(t[1].item())
-    rec["groups"] = int(G)
-    rec["rows_total"] = int(rows.sum())
-    rec["valid_total"] = int(nv.sum())
-    rec["sum_rel_err_vs_torch_reduction"] = abs(float(sums.sum()) - ref_sum) / max(abs(ref_sum), 1e-300)
+    G, rows_total, valid_total, sum_total = int(G), int(rows.sum()), int(nv.sum()), float(sums.sum())
+    if getattr(env, "sharded_result", False):      # every rank holds the groups it owns: the invariants are sums over the ranks
+        ti = torch.tensor([G, rows_total, valid_total], dtype=torch.int64, device="cuda")
+        tf = torch.tensor([sum_total], dtype=torch.float64, device="cuda")
+        env.dist.all_reduce(ti)
+        env.dist.all_reduce(tf)
+        G, rows_total, valid_total, sum_total = int(ti[0].item()), int(ti[1].item()), int(ti[2].item()), float(tf[0].item())
+        rec["result"] = "sharded by hash(key) mod ranks"
+    rec["groups"] = G
+    rec["rows_total"] = rows_total
+    rec["valid_total"] = valid_total
+    rec["sum_rel_err_vs_torch_reduction"] = abs(sum_total - ref_sum) / max(abs(ref_sum), 1e-300)
     ok = G == min(args.groups, n * world) and rec["rows_total"] == n * world and rec["valid_total"] == ref_cnt and rec["sum_rel_err_vs_torch_reduction"] < 1e-9
     m = min(n, 4_000_000)
     if rank == 0:
