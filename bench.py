@@ -77,9 +77,8 @@ class ClockSampler:
             mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
 
             def loop():
-                # An NVML query holds a driver lock that CUDA calls of this process (allocations, launches) wait for: the
-                # sampler keeps its duty cycle under 5% (a query was measured to stall an allocation-heavy join step by tens of ms
-                # when issued every 25 ms regardless of its own duration)
+                # An NVML query takes 1 - 11 ms on these boxes and holds a driver lock that CUDA calls of this process (allocations,
+                # launches) wait for: the sampler keeps its duty cycle under 5% and reports its slowest query
                 while not self.stop_flag:
                     t = time.perf_counter()
                     try:
@@ -303,7 +302,7 @@ def timed_region(env, step, warmup, steps, stats_key="main_kernel_ms"):
         tw = time.perf_counter()
         step()
         tw = time.perf_counter() - tw
-    clocks.period = min(0.25, max(0.025, 10.0 * tw))       # (measured: at 25 ms the queries made a 19 ms join step take 30 - 80 ms)
+    clocks.period = min(0.25, max(0.025, 10.0 * tw))       # about one sample per 10 steps: a host-bound step can run into the query's driver lock
     launches0 = env.ctx.stats()["kernel_launches"]
     env.barrier()
     clocks.mark_begin()
