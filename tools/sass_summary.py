@@ -15,7 +15,10 @@ PATTERNS = collections.OrderedDict([
     ("VOTE", r"\bVOTE"), ("MATCH", r"\bMATCH"), ("SHFL", r"\bSHFL"), ("BAR", r"\bBAR\.SYNC"), ("LDS", r"\bLDS"), ("STS", r"\bSTS"),
 ])
 WANT = ("gb_tsort_kernel", "gp_part_kernel", "jpart1_kernel", "join_build_kernel", "join_probe_emit_kernel", "gb_finalize_kernel",
-        "gb_key_range_kernel", "jx_publish_counts_kernel", "gb_sample_kernel")
+        "gb_key_range_kernel", "jx_publish_counts_kernel", "gb_sample_kernel",
+        # round 2
+        "gb_few_kernel", "gp_hash_kernel", "gh_kernel", "rs_scatter_kernel", "rs_hist_kernel", "gr_assign_kernel", "gr_table_build_kernel", "de_hash_kernel", "de_verify_kernel",
+        "validity_to_nulls_kernel", "dist_merge_kernel", "dist_pack_kernel", "jfat_probe_emit_kernel", "jfat_build_kernel", "gr_median_keys_kernel")
 
 
 def demangle(names):
